@@ -1,0 +1,164 @@
+/*
+ * tdet_b200.h -- C ABI of libtdet_b200.so: the B200 (sm_100a) implementation of the
+ * ResNet + FPN feature-extraction hot path of TCGGroup/Torch_Detection.
+ *
+ * The reference implements this path entirely as torch.nn modules (there is no native code and no
+ * FFI in the reference), so "what the reference's FFI for this path would bind" is the set of
+ * ATen ops its modules dispatch to.  Each entry point / op kind below cites the reference call site
+ * it replaces (paths relative to the reference root):
+ *
+ *   TDET_OP_PREP       image hand-off: NCHW fp32/bf16 batch from datasets/loader/collate.py:42-63
+ *                      -> padded NHWC4 bf16 staging for the stem (no reference op; layout change)
+ *   TDET_OP_STEM       conv1 7x7/2 p3 + bn1 + relu        models/backbone/resnet.py:254-257
+ *                      (conv7x7_group models/utils/layers.py:35-47, norm_layer :50-54)
+ *   TDET_OP_MAXPOOL    nn.MaxPool2d(3, 2, 1)              models/backbone/resnet.py:218,258
+ *   TDET_OP_CONV       every other conv with its fused epilogue:
+ *                        Bottleneck / BasicBlock conv+BN(+ReLU)(+residual add+ReLU)
+ *                                                         models/backbone/resnet.py:42-59,97-119
+ *                        downsample 1x1 stride s + BN     models/backbone/resnet.py:129-136
+ *                        FPN lateral 1x1 + bias (+ nearest-x2 upsample-add of the coarser level)
+ *                                                         models/necks/fpn.py:92-101
+ *                        FPN output 3x3 p1 + bias         models/necks/fpn.py:106-108
+ *                        FPN extra stride-2 3x3 (+ReLU on input done by producer) fpn.py:118-124
+ *   TDET_OP_SUBSAMPLE  F.max_pool2d(x, 1, stride=2)       models/necks/fpn.py:114-116
+ *   tdet_pack_conv_weight / tdet_pack_stem_weight / tdet_fold_bn
+ *                      derive the kernels' operand formats from the reference's fp32 OIHW
+ *                      parameters and BatchNorm2d buffers (state_dict layout of resnet.py/fpn.py)
+ *
+ * Conventions
+ *   - extern "C", plain C types only; no torch types cross this boundary.
+ *   - Every function returns 0 (TDET_OK) or a negative tdet_status; nothing throws.
+ *     tdet_last_error() returns a thread-local, human-readable message for the last failure.
+ *   - The library never allocates or frees caller tensors.  All device buffers (activations,
+ *     packed weights, outputs) are owned by the caller (torch's caching allocator on the Python side).
+ *   - All GPU work is enqueued asynchronously on the caller's stream (cudaStream_t passed as void*);
+ *     no hidden synchronisation.
+ *   - Activations are dense NHWC bf16 unless stated otherwise; conv weights are packed
+ *     [Cout][kh][kw][Cin] bf16 (K-major rows, the tcgen05 B operand); per-channel epilogue
+ *     parameters are fp32.
+ *   - A plan is bound to one device, is not re-entrant (one in-flight run per plan); distinct plans
+ *     are independent.
+ *   - There is no CPU fallback: on a device that is not sm_100 every compute entry point returns
+ *     TDET_ERR_UNSUPPORTED_DEVICE.
+ */
+#ifndef TDET_B200_H_
+#define TDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDET_ABI_VERSION 1
+
+typedef enum tdet_status {
+  TDET_OK = 0,
+  TDET_ERR_INVALID_ARGUMENT = -1,
+  TDET_ERR_UNSUPPORTED_SHAPE = -2,
+  TDET_ERR_UNSUPPORTED_DEVICE = -3,
+  TDET_ERR_CUDA = -4,
+  TDET_ERR_DRIVER = -5,
+  TDET_ERR_OUT_OF_MEMORY = -6
+} tdet_status;
+
+typedef enum tdet_op_kind {
+  TDET_OP_PREP = 0,
+  TDET_OP_STEM = 1,
+  TDET_OP_MAXPOOL = 2,
+  TDET_OP_CONV = 3,
+  TDET_OP_SUBSAMPLE = 4
+} tdet_op_kind;
+
+typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1 } tdet_dtype;
+
+enum {
+  TDET_FLAG_RELU = 1 /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
+};
+
+/*
+ * One step of the path.  Unused fields must be zero / NULL.
+ *
+ * TDET_OP_PREP      x: logical (n, 3, h, w) image batch of x_dtype with element strides
+ *                   x_stride[] = {n, c, h, w} (NCHW-contiguous or channels_last both work)
+ *                   y: bf16 [n][hp][wp][4] with hp = 2*ho + 6, wp = 2*wo + 16 (ho/wo = stem output
+ *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
+ * TDET_OP_STEM      x: the PREP output; wgt: tdet_pack_stem_weight output (bf16 [64][448]);
+ *                   scale/shift: folded bn1; y: bf16 [n][ho][wo][64].  h,w = original image size.
+ * TDET_OP_MAXPOOL   x: bf16 [n][h][w][cin]; y: bf16 [n][ho][wo][cin]; kh=kw=3, stride 2, pad 1.
+ * TDET_OP_CONV      x: bf16 [n][h][w][cin]; wgt: bf16 [cout][kh][kw][cin]; y: bf16 [n][ho][wo][cout]
+ *                   y = act( conv(x) * scale + shift + residual + up2(coarse) )
+ *                   scale == NULL means 1; shift == NULL means 0 (shift is the conv bias for FPN);
+ *                   residual: bf16 [n][ho][wo][cout] or NULL; coarse: bf16 [n][hc][wc][cout] or NULL,
+ *                   with ho == 2*hc and wo == 2*wc (nearest x2, fpn.py:100-101).
+ *                   cin and cout must be multiples of 64.
+ * TDET_OP_SUBSAMPLE y[n][i][j][:] = x[n][2i][2j][:]   (ho = (h-1)/2+1)
+ */
+typedef struct tdet_op {
+  int32_t kind;  /* tdet_op_kind */
+  int32_t flags; /* TDET_FLAG_* */
+  int32_t n, h, w, cin;
+  int32_t cout, kh, kw;
+  int32_t stride, pad, dil;
+  int32_t ho, wo;
+  int32_t hc, wc;     /* coarse level size for the upsample-add epilogue */
+  int32_t x_dtype;    /* PREP only: tdet_dtype of x */
+  int32_t reserved0;
+  int64_t x_stride[4]; /* PREP only: element strides of x for (n, c, h, w) */
+  const void* x;
+  const void* wgt;
+  void* y;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  const void* coarse;
+} tdet_op;
+
+typedef struct tdet_plan tdet_plan; /* opaque */
+
+/* ---- library / device ------------------------------------------------------------------- */
+int tdet_abi_version(void);
+const char* tdet_last_error(void);
+/* 0 if `device` is an sm_100 part this build can run on, else TDET_ERR_UNSUPPORTED_DEVICE. */
+int tdet_device_supported(int device);
+
+/* ---- operand preparation (run once per weight version) ----------------------------------- */
+/* fp32 OIHW [cout][cin][kh][kw] -> bf16 [cout][kh][kw][cin] (round-to-nearest-even). */
+int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw,
+                          void* stream);
+/* fp32 [64][3][7][7] -> bf16 [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
+int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
+/* eval-mode BatchNorm2d -> per-channel fp32 scale = gamma/sqrt(var+eps), shift = beta-mean*scale
+ * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
+int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
+                 float eps, float* scale, float* shift, int channels, void* stream);
+
+/* ---- execution ---------------------------------------------------------------------------- */
+/* Validates and runs one op immediately (descriptors are built on the fly). */
+int tdet_op_run(const tdet_op* op, int device, void* stream);
+
+/*
+ * A plan is a validated op sequence with pre-built TMA descriptors and launch configurations.
+ * ext_ptrs lists the n_ext caller pointers that may change between runs (network input, returned
+ * outputs); every op field equal to ext_ptrs[i] is re-bound to the i-th pointer given to
+ * tdet_plan_run.  Pass n_ext = 0 for a fully static plan.
+ */
+int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void* const* ext_ptrs,
+                     int n_ext, int device);
+int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream);
+int tdet_plan_num_launches(const tdet_plan* plan);
+/* Sum over TDET_OP_CONV/STEM ops of 2*M*N*K (un-padded dims), for roofline accounting. */
+double tdet_plan_flops(const tdet_plan* plan);
+int tdet_plan_destroy(tdet_plan* plan);
+
+/* Test hook: runs the TMA im2col loader alone and dumps one 128x64 A tile (un-swizzled, bf16
+ * [128][64]) for output rows [m0, m0+128), filter tap (r, s), channel chunk kc.  Used by the
+ * GPU tests to pin the descriptor semantics independently of the MMA. */
+int tdet_debug_im2col_tile(const tdet_op* op, int m0, int r, int s, int kc, void* tile_out,
+                           int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDET_B200_H_ */

@@ -1,0 +1,67 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference via the import
+shim).  Dev-container only; the fixtures it writes are committed and travel to the GPU box.
+
+    python oracle/make_golden.py
+
+Each fixture holds: the build config, the seeds, a SHA-256 of the reference's state_dict bytes (so a
+consumer can prove it rebuilt the same weights from the seed), the input batch and every output
+level (C2..C5, P2..P6) in fp32, exactly as the reference produced them on CPU.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_shim, resnet_fpn_oracle as orc  # noqa: E402
+
+CASES = [
+    # name, depth, seed, input shape, randomise BN stats
+    ("r18_fpn_64x64", 18, 0, (1, 3, 64, 64), False),
+    ("r50_fpn_64x96", 50, 0, (1, 3, 64, 96), False),
+    ("r50_fpn_64x64_bnstats", 50, 1, (1, 3, 64, 64), True),
+]
+
+
+def state_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def main():
+    assert reference_shim.available(), "needs /root/reference"
+    torch.set_num_threads(1)  # fixed reduction order
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, depth, seed, shape, bnstats in CASES:
+        bb, neck = reference_shim.build_pair(depth, seed=seed)
+        if bnstats:
+            sd = bb.state_dict()
+            g = torch.Generator().manual_seed(1000 + seed)
+            orc.randomize_bn_stats(sd, generator=g)
+            bb.load_state_dict(sd)
+        g = torch.Generator().manual_seed(77 + seed)
+        x = torch.randn(*shape, generator=g)
+        with torch.no_grad():
+            feats = bb(x)
+            outs = neck(feats)
+        arrays = {"x": x.numpy()}
+        for i, t in enumerate(feats):
+            arrays["C%d" % (i + 2)] = t.numpy()
+        for i, t in enumerate(outs):
+            arrays["P%d" % (i + 2)] = t.numpy()
+        meta = dict(depth=depth, seed=seed, bnstats=int(bnstats), input_seed=77 + seed,
+                    bb_hash=state_hash(bb.state_dict()), neck_hash=state_hash(neck.state_dict()))
+        np.savez(os.path.join(out_dir, name + ".npz"),
+                 **arrays, **{"meta_" + k: np.array(v) for k, v in meta.items()})
+        print(name, {k: v.shape for k, v in arrays.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+"""End-to-end parity of the CUDA path (product ResNet + FPN modules -> C ABI plan -> sm_100a
+kernels) against the fp32 CPU oracle and the reference-generated golden vectors.
+
+Gate (BASELINE.json north_star): every FPN level within relative L2 <= 1e-2 with bf16 I/O.
+C2..C5 are checked to the same bound for diagnosis.
+"""
+import pytest
+import torch
+
+from oracle import resnet_fpn_oracle as orc
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+BF16_GATE = 1e-2
+
+
+def _run_product(bb, neck, x, dev):
+    bb = bb.to(dev)
+    neck = neck.to(dev)
+    bb.eval()
+    neck.eval()
+    with torch.no_grad():
+        feats = bb(x.to(dev))
+        outs = neck(feats)
+    torch.cuda.synchronize()
+    return feats, outs
+
+
+def _check_levels(got, want, names, gate=BF16_GATE):
+    errs = {}
+    for n, a, b in zip(names, got, want):
+        assert tuple(a.shape) == tuple(b.shape), (n, a.shape, b.shape)
+        errs[n] = orc.rel_l2(a.float(), b)
+    bad = {k: v for k, v in errs.items() if not v <= gate}
+    assert not bad, "rel-L2 over gate: %s (all: %s)" % (bad, errs)
+    return errs
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_CASES)
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_golden_vectors(cuda_device, name, dtype):
+    meta, arrays = helpers.load_golden(name)
+    bb, neck = helpers.build_product_pair(meta["depth"], seed=meta["seed"], bnstats=bool(meta["bnstats"]))
+    assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
+    feats, outs = _run_product(bb, neck, arrays["x"].to(dtype), cuda_device)
+    assert all(t.dtype == dtype for t in feats + outs)
+    _check_levels(feats, [arrays["C%d" % i] for i in range(2, 6)], ["C2", "C3", "C4", "C5"])
+    _check_levels(outs, [arrays["P%d" % i] for i in range(2, 7)], ["P2", "P3", "P4", "P5", "P6"])
+
+
+@pytest.mark.parametrize("depth,shape,bnstats", [
+    (18, (2, 3, 128, 160), False),
+    (34, (1, 3, 96, 128), True),
+    (50, (2, 3, 128, 160), False),
+    (50, (1, 3, 224, 320), True),
+    (101, (1, 3, 128, 128), False),
+])
+def test_against_cpu_oracle(cuda_device, depth, shape, bnstats):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    bb, neck = helpers.build_product_pair(depth, seed=11, bnstats=bnstats)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(5))
+    xb = x.to(torch.bfloat16)
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, xb.float(), depth)
+    feats, outs = _run_product(bb, neck, xb, cuda_device)
+    e1 = _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
+    e2 = _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"])
+    print("rel-L2", depth, shape, e1, e2)
+
+
+def test_full_size_r50_fpn_single_image(cuda_device):
+    """BASELINE config geometry: one 800x1333 image zero-padded to 800x1344."""
+    bb, neck = helpers.build_product_pair(50, seed=0)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    g = torch.Generator().manual_seed(0)
+    x = torch.zeros(1, 3, 800, 1344)
+    x[:, :, :, :1333] = torch.randn(1, 3, 800, 1333, generator=g)
+    xb = x.to(torch.bfloat16)
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, xb.float(), 50)
+    feats, outs = _run_product(bb, neck, xb, cuda_device)
+    assert [tuple(t.shape) for t in outs] == [(1, 256, 200, 336), (1, 256, 100, 168), (1, 256, 50, 84),
+                                              (1, 256, 25, 42), (1, 256, 13, 21)]
+    e1 = _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
+    e2 = _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"])
+    print("rel-L2 full size", e1, e2)
+
+
+def test_batch_independence_and_determinism(cuda_device):
+    """Images are independent units (eval BN): batch of 3 == three batches of 1, bit for bit, and a
+    second run reproduces the first exactly (size-independent property)."""
+    bb, neck = helpers.build_product_pair(50, seed=2)
+    x = torch.randn(3, 3, 96, 128, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16)
+    f3, p3 = _run_product(bb, neck, x, cuda_device)
+    f3b, p3b = _run_product(bb, neck, x, cuda_device)
+    for a, b in zip(f3 + p3, f3b + p3b):
+        assert torch.equal(a, b)
+    for i in range(3):
+        f1, p1 = _run_product(bb, neck, x[i:i + 1], cuda_device)
+        for a, b in zip(f3 + p3, f1 + p1):
+            assert torch.equal(a[i:i + 1], b)
+
+
+def test_odd_size_backbone_and_fpn_mismatch_error(cuda_device):
+    """Raw 1333-derived odd sizes run through the backbone; the FPN raises RuntimeError like the
+    reference (fpn.py:100-101) instead of cropping."""
+    bb, neck = helpers.build_product_pair(18, seed=0)
+    bsd = helpers.cpu_state(bb)
+    x = torch.randn(1, 3, 100, 167, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    want = orc.resnet_forward(bsd, x.float(), 18)
+    bb = bb.to(cuda_device)
+    bb.eval()
+    with torch.no_grad():
+        feats = bb(x.to(cuda_device))
+    _check_levels(feats, want, ["C2", "C3", "C4", "C5"])
+    with pytest.raises(RuntimeError):
+        neck.to(cuda_device)(feats)
+
+
+def test_variants(cuda_device):
+    """single out index -> bare tensor; RetinaNet-style extra convs with start_level=1."""
+    from torch_detection_b200.models.backbone import ResNet
+    from torch_detection_b200.models.necks import FPN
+    dev = cuda_device
+    torch.manual_seed(4)
+    bb1 = ResNet(50, out_indices=(3,))
+    bb1.init_weights()
+    bb1.eval()
+    x = torch.randn(1, 3, 128, 128).to(torch.bfloat16)
+    want = orc.resnet_forward(helpers.cpu_state(bb1), x.float(), 50, out_indices=(3,))
+    with torch.no_grad():
+        got = bb1.to(dev)(x.to(dev))
+    assert isinstance(got, torch.Tensor)
+    assert orc.rel_l2(got.float(), want) <= BF16_GATE
+    bb, _ = helpers.build_product_pair(50, seed=4)
+    neck = FPN([256, 512, 1024, 2048], 256, 5, start_level=1, add_extra_convs=True)
+    neck.init_weights()
+    neck.eval()
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    wf = orc.resnet_forward(bsd, x.float(), 50)
+    wp = orc.fpn_forward(nsd, wf, [256, 512, 1024, 2048], 256, 5, start_level=1, add_extra_convs=True)
+    feats, outs = _run_product(bb, neck, x, dev)
+    assert len(outs) == 5
+    _check_levels(outs, wp, ["P3", "P4", "P5", "P6", "P7"])
+
+
+def test_weight_update_invalidates_packed_operands(cuda_device):
+    bb, neck = helpers.build_product_pair(18, seed=0)
+    x = torch.randn(1, 3, 64, 64).to(torch.bfloat16)
+    f0, _ = _run_product(bb, neck, x, cuda_device)
+    with torch.no_grad():
+        bb.layer1[0].conv1.weight.mul_(0.5)
+    f1, _ = _run_product(bb, neck, x, cuda_device)
+    assert not torch.equal(f0[0], f1[0])
+    want = orc.resnet_forward(helpers.cpu_state(bb), x.float(), 18)
+    _check_levels(f1, want, ["C2", "C3", "C4", "C5"])
+
+
+def test_cpu_tensor_and_train_mode_bn_are_refused(cuda_device):
+    from torch_detection_b200.models.backbone import ResNet
+    bb = ResNet(18)
+    with pytest.raises(NotImplementedError):
+        bb.eval()(torch.randn(1, 3, 64, 64))
+    bb = ResNet(18, bn_eval=False).to(cuda_device)
+    bb.train()
+    with pytest.raises(NotImplementedError):
+        bb(torch.randn(1, 3, 64, 64, device=cuda_device))

@@ -1,0 +1,42 @@
+"""Oracle vs the committed golden vectors (produced by the reference itself, oracle/make_golden.py).
+CPU-only; runs on the GPU box too, where the reference tree is absent."""
+import pytest
+import torch
+
+from oracle import resnet_fpn_oracle as orc
+from tests import helpers
+
+
+@pytest.mark.parametrize("name", helpers.GOLDEN_CASES)
+def test_oracle_matches_golden(name):
+    torch.set_num_threads(1)
+    meta, arrays = helpers.load_golden(name)
+    bb, neck = helpers.build_product_pair(meta["depth"], seed=meta["seed"], bnstats=bool(meta["bnstats"]))
+    # the product's host-side mirror rebuilds the reference's weights from the seed
+    assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
+    assert helpers.state_hash(neck.state_dict()) == meta["neck_hash"]
+    feats, outs = orc.resnet_fpn_forward(helpers.cpu_state(bb), helpers.cpu_state(neck), arrays["x"],
+                                         meta["depth"])
+    for i, t in enumerate(feats):
+        assert torch.equal(t, arrays["C%d" % (i + 2)]), "C%d" % (i + 2)
+    for i, t in enumerate(outs):
+        assert torch.equal(t, arrays["P%d" % (i + 2)]), "P%d" % (i + 2)
+
+
+def test_flop_model_matches_survey():
+    assert orc.conv_flops(50, 800, 1344)[0] == 296961638400
+    assert orc.conv_flops(101, 800, 1344)[0] == 456056832000
+    assert orc.conv_flops(18, 800, 1344)[0] == 187136409600
+    assert orc.conv_flops(50, 800, 1333, with_fpn=False)[0] == 174666598400
+
+
+def test_bf16_emulation_is_within_gate():
+    """The emulated fused-bf16 pipeline (what the kernels implement) vs the fp32 oracle: documents the
+    margin the <=1e-2 gate leaves."""
+    meta, arrays = helpers.load_golden("r50_fpn_64x96")
+    bb, neck = helpers.build_product_pair(50, seed=0)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    _, outs = orc.resnet_fpn_forward(bsd, nsd, arrays["x"], 50)
+    _, emu = orc.resnet_fpn_forward_bf16_emulated(bsd, nsd, arrays["x"], 50)
+    errs = [orc.rel_l2(a, b) for a, b in zip(emu, outs)]
+    assert max(errs) < 1.5e-2, errs

@@ -1,0 +1,90 @@
+"""Pins the oracle (oracle/resnet_fpn_oracle.py) and the product's host-side mirror against the
+LIVE, unmodified reference.  Runs only where /root/reference exists (the dev container); the same
+facts are re-checked everywhere through the committed golden fixtures (test_oracle_golden.py)."""
+import pytest
+import torch
+
+from oracle import reference_shim, resnet_fpn_oracle as orc
+from tests import helpers
+
+pytestmark = pytest.mark.skipif(not reference_shim.available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("depth", [18, 34, 50, 101])
+def test_oracle_bit_identical_to_reference(depth):
+    torch.set_num_threads(4)
+    bb, neck = reference_shim.build_pair(depth, seed=3)
+    x = torch.randn(2, 3, 64, 96)
+    with torch.no_grad():
+        feats = bb(x)
+        outs = neck(feats)
+        f, p = orc.resnet_fpn_forward(bb.state_dict(), neck.state_dict(), x, depth)
+    for a, b in zip(tuple(feats) + tuple(outs), tuple(f) + tuple(p)):
+        assert torch.equal(a, b)
+
+
+def test_oracle_odd_sizes_and_fpn_mismatch_error():
+    """F2: the backbone runs at 1333-derived odd sizes; the FPN raises RuntimeError on them."""
+    bb, neck = reference_shim.build_pair(18, seed=0)
+    x = torch.randn(1, 3, 100, 167)
+    with torch.no_grad():
+        feats = bb(x)
+        f = orc.resnet_forward(bb.state_dict(), x, 18)
+    assert all(torch.equal(a, b) for a, b in zip(feats, f))
+    with pytest.raises(RuntimeError):
+        neck(feats)
+    with pytest.raises(RuntimeError):
+        orc.fpn_forward(neck.state_dict(), f, [64, 128, 256, 512], 256, 5)
+
+
+def test_oracle_variants_match_reference():
+    ref_backbone, ref_necks, obj_from_dict = reference_shim.load()
+    torch.manual_seed(0)
+    bb = obj_from_dict(dict(type="ResNet", depth=50, out_indices=(3,)), parent=ref_backbone)
+    bb.init_weights()
+    bb.eval()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        single = bb(x)
+        mine = orc.resnet_forward(bb.state_dict(), x, 50, out_indices=(3,))
+    assert isinstance(single, torch.Tensor) and torch.equal(single, mine)
+    # RetinaNet-style extra convs, start_level=1
+    neck = obj_from_dict(dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256,
+                              num_outs=5, start_level=1, add_extra_convs=True), parent=ref_necks)
+    neck.init_weights()
+    neck.eval()
+    bb4 = obj_from_dict(dict(type="ResNet", depth=50), parent=ref_backbone)
+    bb4.init_weights()
+    bb4.eval()
+    with torch.no_grad():
+        feats = bb4(x)
+        ref = neck(feats)
+        mine = orc.fpn_forward(neck.state_dict(), feats, [256, 512, 1024, 2048], 256, 5,
+                               start_level=1, add_extra_convs=True)
+    assert len(ref) == len(mine) == 5
+    assert all(torch.equal(a, b) for a, b in zip(ref, mine))
+
+
+@pytest.mark.parametrize("depth", [18, 50, 101])
+def test_product_modules_mirror_reference_state(depth):
+    """Same seed -> same state_dict keys, shapes AND values as the reference (construction and
+    init_weights consume the RNG identically), for backbone and neck."""
+    bb_ref, neck_ref = reference_shim.build_pair(depth, seed=5)
+    bb, neck = helpers.build_product_pair(depth, seed=5)
+    for ref, mine in ((bb_ref, bb), (neck_ref, neck)):
+        a, b = ref.state_dict(), mine.state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+
+
+def test_golden_fixtures_are_reproducible_from_reference():
+    for name in helpers.GOLDEN_CASES:
+        meta, arrays = helpers.load_golden(name)
+        bb, neck = reference_shim.build_pair(meta["depth"], seed=meta["seed"])
+        if meta["bnstats"]:
+            sd = bb.state_dict()
+            orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(1000 + meta["seed"]))
+            bb.load_state_dict(sd)
+        assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
+        assert helpers.state_hash(neck.state_dict()) == meta["neck_hash"]

@@ -1,0 +1,98 @@
+"""ctypes binding of ``libtdet_b200.so`` (C ABI: ``include/tdet_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an exception
+is raised.  Build it with ``python -m torch_detection_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
+
+# tdet_status
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_UNSUPPORTED_SHAPE = -2
+ERR_UNSUPPORTED_DEVICE = -3
+ERR_CUDA = -4
+ERR_DRIVER = -5
+ERR_OUT_OF_MEMORY = -6
+
+# tdet_op_kind
+OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
+# tdet_dtype
+BF16, F32 = 0, 1
+FLAG_RELU = 1
+
+
+class TdetOp(ctypes.Structure):
+    """Mirror of ``struct tdet_op``."""
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("cin", ctypes.c_int32),
+        ("cout", ctypes.c_int32), ("kh", ctypes.c_int32), ("kw", ctypes.c_int32),
+        ("stride", ctypes.c_int32), ("pad", ctypes.c_int32), ("dil", ctypes.c_int32),
+        ("ho", ctypes.c_int32), ("wo", ctypes.c_int32),
+        ("hc", ctypes.c_int32), ("wc", ctypes.c_int32),
+        ("x_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("x_stride", ctypes.c_int64 * 4),
+        ("x", ctypes.c_void_p), ("wgt", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
+        ("residual", ctypes.c_void_p), ("coarse", ctypes.c_void_p),
+    ]
+
+
+class TdetError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libtdet_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+EXPORTS = [
+    "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
+    "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
+    "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_num_launches",
+    "tdet_plan_flops", "tdet_plan_destroy", "tdet_debug_im2col_tile",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads the extension (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "libtdet_b200.so is not built (%s missing). Run `python -m torch_detection_b200.build`. "
+            "There is no CPU/PyTorch fallback for this path." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.tdet_abi_version.restype = i32
+    L.tdet_last_error.restype = ctypes.c_char_p
+    L.tdet_device_supported.argtypes = [i32]
+    L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
+    L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
+    L.tdet_op_run.argtypes = [ctypes.POINTER(TdetOp), i32, vp]
+    L.tdet_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(TdetOp), i32,
+                                   ctypes.POINTER(vp), i32, i32]
+    L.tdet_plan_run.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
+    L.tdet_plan_num_launches.argtypes = [vp]
+    L.tdet_plan_flops.argtypes = [vp]
+    L.tdet_plan_flops.restype = ctypes.c_double
+    L.tdet_plan_destroy.argtypes = [vp]
+    L.tdet_debug_im2col_tile.argtypes = [ctypes.POINTER(TdetOp), i32, i32, i32, i32, vp, i32, vp]
+    for name in EXPORTS:
+        if name not in ("tdet_last_error", "tdet_plan_flops"):
+            getattr(L, name).restype = i32
+    if L.tdet_abi_version() != 1:
+        raise ImportError("libtdet_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        raise TdetError(rc, lib().tdet_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,179 @@
+"""Feature Pyramid Network neck, B200 execution -- drop-in for reference ``models/necks/fpn.py``.
+
+Constructor arguments, attributes (``lateral_convs`` / ``fpn_convs`` ``ModuleList``s of
+``ConvModule`` with a ``.conv``), ``state_dict`` keys, ``init_weights`` and the returned tuple are
+those of the reference ``FPN`` (fpn.py:8-125).  ``forward`` compiles, once per input geometry, the
+op list
+
+    lateral[j]  = conv1x1(C[j]) + bias (+ nearest-x2 upsample of lateral[j+1])   coarse -> fine
+    P[j]        = conv3x3(lateral[j]) + bias
+    extra       = stride-2 subsample of the last P (fpn.py:114-116) or stride-2 3x3 convs (RetinaNet)
+
+where the top-down add (fpn.py:98-101) is fused into the lateral conv's epilogue in fp32, so each
+merged lateral is written exactly once.  Like the reference, mismatching pyramid levels
+(fine != 2 x coarse, e.g. a raw 800x1333 image) raise ``RuntimeError``; nothing is cropped silently.
+"""
+import torch
+import torch.nn as nn
+
+from ... import engine
+from ...registry import NECKS
+from ..utils import ConvModule, xavier_init, constant_init
+
+
+@NECKS.register_module
+class FPN(nn.Module):
+
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1,
+                 add_extra_convs=False, normalize=None, use_gn=False):
+        super(FPN, self).__init__()
+        assert isinstance(in_channels, list)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_ins = len(in_channels)
+        self.num_outs = num_outs
+        self.with_bias = normalize is None
+        if end_level == -1:
+            self.backbone_end_level = self.num_ins
+            assert num_outs >= self.num_ins - start_level
+        else:
+            # if end_level < inputs, no extra level is allowed
+            self.backbone_end_level = end_level
+            assert end_level <= len(in_channels)
+            assert num_outs == end_level - start_level
+        self.start_level = start_level
+        self.end_level = end_level
+        self.add_extra_convs = add_extra_convs
+
+        self.lateral_convs = nn.ModuleList()
+        self.fpn_convs = nn.ModuleList()
+        # lateral and output conv of a level are created pairwise (fpn.py:43-61): RNG order matters
+        for i in range(self.start_level, self.backbone_end_level):
+            self.lateral_convs.append(ConvModule(in_channels[i], out_channels, 1,
+                                                 normalize=normalize, bias=self.with_bias,
+                                                 use_gn=use_gn))
+            self.fpn_convs.append(ConvModule(out_channels, out_channels, 3, padding=1,
+                                             normalize=normalize, bias=self.with_bias,
+                                             use_gn=use_gn))
+        extra_levels = num_outs - self.backbone_end_level + self.start_level
+        if add_extra_convs and extra_levels >= 1:
+            for i in range(extra_levels):
+                cin = in_channels[self.backbone_end_level - 1] if i == 0 else out_channels
+                self.fpn_convs.append(ConvModule(cin, out_channels, 3, stride=2, padding=1,
+                                                 normalize=normalize, bias=self.with_bias,
+                                                 use_gn=use_gn))
+        self._plans = {}
+        self._operands = None
+        self._operand_key = None
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                xavier_init(m, distribution="uniform")
+            if isinstance(m, (nn.BatchNorm2d, nn.GroupNorm)):
+                constant_init(m, 1)
+
+    # ------------------------------------------------------------------ B200 execution
+    def _get_operands(self, device):
+        key = (device,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._operands is not None and key == self._operand_key:
+            return self._operands
+        ops = {}
+        for kind, convs in (("lat", self.lateral_convs), ("out", self.fpn_convs)):
+            for j, cm in enumerate(convs):
+                ops["%s%d.w" % (kind, j)] = engine.pack_conv_weight(cm.conv.weight)
+                ops["%s%d.b" % (kind, j)] = cm.conv.bias.detach().float().contiguous() \
+                    if cm.conv.bias is not None else None
+        self._operands = ops
+        self._operand_key = key
+        self._plans = {}
+        return ops
+
+    def _build_plan(self, feats, operands):
+        dev = feats[0].device
+        n = feats[0].shape[0]
+        used = feats[self.start_level:self.backbone_end_level]
+        nl = len(used)
+        shapes = [(t.shape[0], t.shape[2], t.shape[3], t.shape[1]) for t in used]  # n,h,w,c
+        for j in range(nl - 1, 0, -1):
+            for dim, a, b in ((2, shapes[j - 1][1], 2 * shapes[j][1]), (3, shapes[j - 1][2], 2 * shapes[j][2])):
+                if a != b:
+                    # same failure class/message as the reference's in-place add (fpn.py:100-101)
+                    raise RuntimeError(
+                        "The size of tensor a (%d) must match the size of tensor b (%d) at "
+                        "non-singleton dimension %d" % (a, b, dim))
+        co = self.out_channels
+        ops = []
+        lats = [None] * nl
+        for j in range(nl - 1, -1, -1):
+            nb, h, w, c = shapes[j]
+            lats[j] = torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev)
+            coarse = lats[j + 1] if j < nl - 1 else None
+            chw = (shapes[j + 1][1], shapes[j + 1][2]) if j < nl - 1 else (0, 0)
+            ops.append(engine.op_conv(shapes[j], used[j], operands["lat%d.w" % j], lats[j], 1, 1, 1, 0,
+                                      1, shift=operands["lat%d.b" % j], coarse=coarse, coarse_hw=chw))
+        outs = []
+        for j in range(nl):
+            nb, h, w, _ = shapes[j]
+            o = engine.nhwc_empty(nb, h, w, co, dev)
+            ops.append(engine.op_conv((nb, h, w, co), lats[j], operands["out%d.w" % j], o, 3, 3, 1, 1,
+                                      1, shift=operands["out%d.b" % j]))
+            outs.append(o)
+        if self.num_outs > nl:
+            if not self.add_extra_convs:
+                for _ in range(self.num_outs - nl):
+                    nb, c_, h, w = outs[-1].shape
+                    o = engine.nhwc_empty(nb, (h - 1) // 2 + 1, (w - 1) // 2 + 1, co, dev)
+                    ops.append(engine.op_subsample(nb, h, w, co, outs[-1], o))
+                    outs.append(o)
+            else:
+                src = feats[self.backbone_end_level - 1]
+                src_shape = (src.shape[0], src.shape[2], src.shape[3], src.shape[1])
+                for j in range(nl, self.num_outs):
+                    nb, h, w, c = src_shape
+                    oh, ow = engine.conv_out(h, 3, 2, 1), engine.conv_out(w, 3, 2, 1)
+                    o = engine.nhwc_empty(nb, oh, ow, co, dev)
+                    # the reference applies ReLU *in place* to P_j before the next extra conv
+                    # (fpn.py:123-124), so every extra level that feeds another one is returned
+                    # post-ReLU: fold that ReLU into the producing conv's epilogue.
+                    ops.append(engine.op_conv(src_shape, src, operands["out%d.w" % j], o, 3, 3, 2, 1,
+                                              1, shift=operands["out%d.b" % j],
+                                              relu=(j < self.num_outs - 1)))
+                    outs.append(o)
+                    src, src_shape = o, (nb, oh, ow, co)
+        ext = list(feats) + outs
+        plan = engine.Plan(ops, ext, [operands, lats], dev)
+        return plan, [tuple(o.shape) for o in outs]
+
+    @staticmethod
+    def _as_bf16_nhwc(t):
+        engine.require_cuda(t, "FPN input")
+        src = getattr(t, "_tdet_bf16", None)
+        if src is not None:
+            return src
+        if t.dtype == torch.bfloat16 and t.is_contiguous(memory_format=torch.channels_last):
+            return t
+        # foreign producer (NCHW-contiguous and/or fp32): one layout/precision adaptation copy
+        return t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)
+        want_fp32 = all(t.dtype == torch.float32 for t in inputs)
+        feats = [self._as_bf16_nhwc(t) for t in inputs]
+        for t, c in zip(feats, self.in_channels):
+            if t.dim() != 4 or t.shape[1] != c:
+                raise ValueError("FPN input with %s channels, expected %d" % (tuple(t.shape), c))
+        dev = feats[0].device
+        operands = self._get_operands(dev)
+        key = tuple(tuple(t.shape) for t in feats) + (dev,)
+        entry = self._plans.get(key)
+        if entry is None:
+            entry = self._build_plan(feats, operands)
+            self._plans[key] = entry
+        plan, out_shapes = entry
+        outs = [torch.empty(s, dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+                for s in out_shapes]
+        plan.run(feats + outs)
+        if want_fp32:
+            outs = [o.float() for o in outs]
+        return tuple(outs)
