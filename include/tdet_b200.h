@@ -34,7 +34,9 @@
  *   - All GPU work is enqueued asynchronously on the caller's stream (cudaStream_t passed as void*);
  *     no hidden synchronisation.
  *   - Activations are dense NHWC bf16 unless stated otherwise; conv weights are packed
- *     [Cout][kh][kw][Cin] bf16 (K-major rows, the tcgen05 B operand); per-channel epilogue
+ *     [Cout][kh][kw][Cin] in the 16-bit format tdet_weight_dtype() reports (fp16 by default:
+ *     weights are bounded constants, so the 3 extra mantissa bits are free accuracy; K-major rows,
+ *     the tcgen05 B operand); per-channel epilogue
  *     parameters are fp32.
  *   - A plan is bound to one device, is not re-entrant (one in-flight run per plan); distinct plans
  *     are independent.
@@ -71,7 +73,7 @@ typedef enum tdet_op_kind {
   TDET_OP_SUBSAMPLE = 4
 } tdet_op_kind;
 
-typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1 } tdet_dtype;
+typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2 } tdet_dtype;
 
 enum {
   TDET_FLAG_RELU = 1 /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
@@ -119,15 +121,17 @@ typedef struct tdet_plan tdet_plan; /* opaque */
 
 /* ---- library / device ------------------------------------------------------------------- */
 int tdet_abi_version(void);
+/* 16-bit format of packed conv weights (the tcgen05 B operand): TDET_F16 or TDET_BF16. */
+int tdet_weight_dtype(void);
 const char* tdet_last_error(void);
 /* 0 if `device` is an sm_100 part this build can run on, else TDET_ERR_UNSUPPORTED_DEVICE. */
 int tdet_device_supported(int device);
 
 /* ---- operand preparation (run once per weight version) ----------------------------------- */
-/* fp32 OIHW [cout][cin][kh][kw] -> bf16 [cout][kh][kw][cin] (round-to-nearest-even). */
+/* fp32 OIHW [cout][cin][kh][kw] -> 16-bit [cout][kh][kw][cin] in tdet_weight_dtype() (RNE). */
 int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw,
                           void* stream);
-/* fp32 [64][3][7][7] -> bf16 [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
+/* fp32 [64][3][7][7] -> 16-bit [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
 int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
 /* eval-mode BatchNorm2d -> per-channel fp32 scale = gamma/sqrt(var+eps), shift = beta-mean*scale
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
@@ -147,7 +151,25 @@ int tdet_op_run(const tdet_op* op, int device, void* stream);
 int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void* const* ext_ptrs,
                      int n_ext, int device);
 int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream);
+/* Same as tdet_plan_run with unchanged external pointers, but brackets every kernel launch with
+ * CUDA events on `stream` and returns the per-launch device time in milliseconds
+ * (ms_per_launch[tdet_plan_num_launches]).  Synchronises the stream; measurement only. */
+int tdet_plan_run_timed(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream,
+                        float* ms_per_launch);
 int tdet_plan_num_launches(const tdet_plan* plan);
+/* Per-launch accounting for roofline reports: GEMM view, algorithmic FLOPs (2*M*N*K, real dims)
+ * and algorithmic HBM bytes (each operand read once, the output written once). */
+typedef struct tdet_launch_info {
+  int32_t kind;   /* tdet_op_kind */
+  int32_t tile_n; /* GEMM tile width (0 for non-GEMM kernels) */
+  int32_t grid;   /* CTAs launched (GEMM kernels) */
+  int32_t a_mode; /* 0 tiled, 1 im2col, 2 stem; -1 for non-GEMM kernels */
+  int32_t m, n, k;
+  int32_t reserved;
+  double flops;
+  double bytes;
+} tdet_launch_info;
+int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* out);
 /* Sum over TDET_OP_CONV/STEM ops of 2*M*N*K (un-padded dims), for roofline accounting. */
 double tdet_plan_flops(const tdet_plan* plan);
 int tdet_plan_destroy(tdet_plan* plan);

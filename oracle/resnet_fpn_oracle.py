@@ -247,11 +247,18 @@ def _r(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def resnet_fpn_forward_bf16_emulated(bb_sd, neck_sd, x, depth, out_channels=256, num_outs=5):
+def resnet_fpn_forward_bf16_emulated(bb_sd, neck_sd, x, depth, out_channels=256, num_outs=5,
+                                     weight_dtype=torch.float16):
+    """weight_dtype: 16-bit format the kernels keep conv weights in (fp16 by default; pass
+    torch.bfloat16 for SURVEY.md's original 'emulation A')."""
     kind, counts = ARCH[depth]
+    bb_sd = {k: (v.to(weight_dtype).float() if k.endswith("weight") and v.dim() == 4 else v)
+             for k, v in bb_sd.items()}
+    neck_sd = {k: (v.to(weight_dtype).float() if k.endswith("weight") and v.dim() == 4 else v)
+               for k, v in neck_sd.items()}
 
     def cbn(inp, wkey, bnp, stride=1, pad=0, relu=False, res=None):
-        y = F.conv2d(inp, _r(bb_sd[wkey]), None, stride, pad)
+        y = F.conv2d(inp, bb_sd[wkey], None, stride, pad)
         scale = bb_sd[bnp + ".weight"] / torch.sqrt(bb_sd[bnp + ".running_var"] + BN_EPS)
         shift = bb_sd[bnp + ".bias"] - bb_sd[bnp + ".running_mean"] * scale
         y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
@@ -282,12 +289,12 @@ def resnet_fpn_forward_bf16_emulated(bb_sd, neck_sd, x, depth, out_channels=256,
     n = len(feats)
     lats = [None] * n
     for j in range(n - 1, -1, -1):
-        y = F.conv2d(feats[j], _r(neck_sd["lateral_convs.%d.conv.weight" % j]),
+        y = F.conv2d(feats[j], neck_sd["lateral_convs.%d.conv.weight" % j],
                      neck_sd["lateral_convs.%d.conv.bias" % j])
         if j < n - 1:
             y = y + F.interpolate(lats[j + 1], scale_factor=2, mode="nearest")
         lats[j] = _r(y)
-    outs = [_r(F.conv2d(lats[j], _r(neck_sd["fpn_convs.%d.conv.weight" % j]),
+    outs = [_r(F.conv2d(lats[j], neck_sd["fpn_convs.%d.conv.weight" % j],
                         neck_sd["fpn_convs.%d.conv.bias" % j], 1, 1)) for j in range(n)]
     for _ in range(num_outs - n):
         outs.append(F.max_pool2d(outs[-1], 1, stride=2))

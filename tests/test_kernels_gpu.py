@@ -44,7 +44,7 @@ def test_im2col_tile_semantics(cuda_device, case):
     x = torch.randn(n, cin, h, w, generator=g).to(dev)
     xb = _nhwc(x)
     ho, wo = engine.conv_out(h, k, stride, pad, dil), engine.conv_out(w, k, stride, pad, dil)
-    wgt = torch.zeros(64, k, k, cin, dtype=torch.bfloat16, device=dev)
+    wgt = torch.zeros(64, k, k, cin, dtype=engine.weight_dtype(), device=dev)
     y = engine.nhwc_empty(n, ho, wo, 64, dev)
     op = engine.op_conv((n, h, w, cin), xb, wgt, y, k, k, stride, pad, dil)
     M = n * ho * wo
@@ -100,7 +100,7 @@ def test_conv_op(cuda_device, case, epi):
     wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(dev)
     xb = _nhwc(x)
     wp = engine.pack_conv_weight(wt)
-    assert torch.equal(wp.permute(0, 3, 1, 2).float(), wt.to(torch.bfloat16).float())
+    assert torch.equal(wp.permute(0, 3, 1, 2).float(), wt.to(engine.weight_dtype()).float())
     ho, wo = engine.conv_out(h, k, stride, pad, dil), engine.conv_out(w, k, stride, pad, dil)
     y = engine.nhwc_empty(n, ho, wo, cout, dev)
     scale = shift = res = None
@@ -117,7 +117,7 @@ def test_conv_op(cuda_device, case, epi):
                         residual=res, relu=relu)
     engine.run_op(op, dev)
     torch.cuda.synchronize()
-    ref = F.conv2d(xb.float(), wt.to(torch.bfloat16).float(), None, stride, pad, dil)
+    ref = F.conv2d(xb.float(), wt.to(engine.weight_dtype()).float(), None, stride, pad, dil)
     if scale is not None:
         ref = ref * scale.view(1, -1, 1, 1)
     if shift is not None:
@@ -127,6 +127,7 @@ def test_conv_op(cuda_device, case, epi):
     if relu:
         ref = F.relu(ref)
     err = rel_l2(y.float(), ref)
+    print("rel-L2 %s %s %.3e" % (case[0], epi, err))
     assert err <= TOL, "rel-L2 %.3e" % err
 
 
@@ -147,7 +148,7 @@ def test_conv_upsample_add(cuda_device):
                         coarse_hw=(h // 2, w // 2))
     engine.run_op(op, dev)
     torch.cuda.synchronize()
-    ref = F.conv2d(xb.float(), wt.to(torch.bfloat16).float(), bias)
+    ref = F.conv2d(xb.float(), wt.to(engine.weight_dtype()).float(), bias)
     ref = ref + F.interpolate(coarse.float(), scale_factor=2, mode="nearest")
     err = rel_l2(y.float(), ref)
     assert err <= TOL, "rel-L2 %.3e" % err
@@ -177,7 +178,7 @@ def test_prep_and_stem(cuda_device, shape, dtype):
     y = engine.nhwc_empty(n, ho, wo, 64, dev)
     engine.run_op(engine.op_stem(n, h, w, staged, wpk, y, scale, shift), dev)
     torch.cuda.synchronize()
-    ref = F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), None, 2, 3)
+    ref = F.conv2d(x.to(torch.bfloat16).float(), wt.to(engine.weight_dtype()).float(), None, 2, 3)
     ref = F.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     err = rel_l2(y.float(), ref)
     assert err <= TOL, "rel-L2 %.3e" % err
@@ -221,7 +222,7 @@ def test_unsupported_shapes_fail_loudly(cuda_device):
     from torch_detection_b200 import engine, _C
     dev = cuda_device
     x = engine.nhwc_empty(1, 8, 8, 48, dev)
-    wgt = torch.zeros(64, 1, 1, 48, dtype=torch.bfloat16, device=dev)
+    wgt = torch.zeros(64, 1, 1, 48, dtype=engine.weight_dtype(), device=dev)
     y = engine.nhwc_empty(1, 8, 8, 64, dev)
     with pytest.raises(_C.TdetError):
         engine.run_op(engine.op_conv((1, 8, 8, 48), x, wgt, y, 1, 1, 1, 0), dev)

@@ -21,7 +21,7 @@ ERR_OUT_OF_MEMORY = -6
 # tdet_op_kind
 OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 # tdet_dtype
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 FLAG_RELU = 1
 
 
@@ -42,6 +42,14 @@ class TdetOp(ctypes.Structure):
     ]
 
 
+class TdetLaunchInfo(ctypes.Structure):
+    """Mirror of ``struct tdet_launch_info``."""
+    _fields_ = [("kind", ctypes.c_int32), ("tile_n", ctypes.c_int32), ("grid", ctypes.c_int32),
+                ("a_mode", ctypes.c_int32), ("m", ctypes.c_int32), ("n", ctypes.c_int32),
+                ("k", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
+
+
 class TdetError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libtdet_b200 error %d: %s" % (code, msg))
@@ -49,9 +57,10 @@ class TdetError(RuntimeError):
 
 
 EXPORTS = [
-    "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
+    "tdet_abi_version", "tdet_weight_dtype", "tdet_last_error", "tdet_device_supported",
     "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
-    "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_num_launches",
+    "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_timed",
+    "tdet_plan_num_launches", "tdet_plan_launch_info",
     "tdet_plan_flops", "tdet_plan_destroy", "tdet_debug_im2col_tile",
 ]
 
@@ -79,6 +88,8 @@ def lib():
     L.tdet_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(TdetOp), i32,
                                    ctypes.POINTER(vp), i32, i32]
     L.tdet_plan_run.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
+    L.tdet_plan_run_timed.argtypes = [vp, ctypes.POINTER(vp), i32, vp, ctypes.POINTER(f32)]
+    L.tdet_plan_launch_info.argtypes = [vp, i32, ctypes.POINTER(TdetLaunchInfo)]
     L.tdet_plan_num_launches.argtypes = [vp]
     L.tdet_plan_flops.argtypes = [vp]
     L.tdet_plan_flops.restype = ctypes.c_double

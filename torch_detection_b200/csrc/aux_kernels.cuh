@@ -3,7 +3,7 @@
 // All activation kernels use 8- or 16-byte vector accesses on dense NHWC bf16.
 #pragma once
 #include <cuda_bf16.h>
-#include "ptx_sm100.cuh"
+#include "conv_gemm.cuh"
 
 namespace tdet {
 
@@ -91,9 +91,9 @@ subsample2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int
   }
 }
 
-// fp32 OIHW -> bf16 [O][kh][kw][I]
+// fp32 OIHW -> weight_t [O][kh][kw][I]
 __global__ void __launch_bounds__(256)
-pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
+pack_weight_kernel(const float* __restrict__ w, weight_t* __restrict__ out, int cout, int cin,
                    int kh, int kw) {
   const long long total = static_cast<long long>(cout) * cin * kh * kw;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -104,14 +104,14 @@ pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
     t /= kw;
     const int r = static_cast<int>(t % kh);
     const int co = static_cast<int>(t / kh);
-    out[i] = __float2bfloat16_rn(w[((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s]);
+    out[i] = to_weight(w[((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s]);
   }
 }
 
 // fp32 [64][3][7][7] -> bf16 [64][448], k = r*64 + s*4 + c for s < 7, c < 3 (zero elsewhere): one
 // 64-wide k-block per filter row, matching the 16-pixel x 4-channel window rows the stem loads.
 __global__ void __launch_bounds__(256)
-pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+pack_stem_weight_kernel(const float* __restrict__ w, weight_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 448) return;
   const int co = i / 448;
@@ -121,7 +121,7 @@ pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__
   const int c = k & 3;
   float v = 0.0f;
   if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = to_weight(v);
 }
 
 __global__ void __launch_bounds__(256)

@@ -16,6 +16,7 @@
 //                                        with the next tile's main loop through tmem_full/empty.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ptx_sm100.cuh"
 
 namespace tdet {
@@ -27,6 +28,23 @@ constexpr int kGemmThreads = 192;
 constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
 
 enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2 };
+
+// Operand formats.  Activations (A) are bf16 (8-bit exponent: the residual stream of a randomly
+// initialised ResNet-101 reaches ~2.4e5).  Weights (B) use the same format: a mixed
+// bf16 x fp16 tcgen05.mma (idesc a_format != b_format) raises "illegal instruction" on B200
+// (measured), so TDET_WEIGHT_FP16=1 is only usable together with fp16 activations.
+#ifndef TDET_WEIGHT_FP16
+#define TDET_WEIGHT_FP16 0
+#endif
+#if TDET_WEIGHT_FP16
+constexpr uint32_t kWeightFmt = kFmtF16;
+using weight_t = __half;
+__device__ __forceinline__ weight_t to_weight(float v) { return __float2half_rn(v); }
+#else
+constexpr uint32_t kWeightFmt = kFmtBF16;
+using weight_t = __nv_bfloat16;
+__device__ __forceinline__ weight_t to_weight(float v) { return __float2bfloat16_rn(v); }
+#endif
 
 struct ConvGemmParams {
   CUtensorMap tmap_a;
@@ -70,7 +88,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_bf16_f32(kBM, BN);
+  constexpr uint32_t kIdesc = make_idesc_f16kind(kBM, BN, kFmtBF16, kWeightFmt);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);

@@ -164,11 +164,13 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, dense, M x N tile.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
+// Instruction descriptor, kind::f16: D fp32, A/B 16-bit floats (format 0 = fp16, 1 = bf16, chosen
+// independently for A and B), both K-major, dense, M x N tile.
+constexpr uint32_t kFmtF16 = 0, kFmtBF16 = 1;
+__host__ __device__ constexpr uint32_t make_idesc_f16kind(int m, int n, uint32_t a_fmt, uint32_t b_fmt) {
   return (1u << 4)                         // c_format = F32
-         | (1u << 7)                       // a_format = BF16
-         | (1u << 10)                      // b_format = BF16
+         | (a_fmt << 7)                    // a_format
+         | (b_fmt << 10)                   // b_format
          | (static_cast<uint32_t>(n >> 3) << 17)   // n_dim
          | (static_cast<uint32_t>(m >> 4) << 24);  // m_dim
 }

@@ -12,8 +12,8 @@
 #include <new>
 #include <vector>
 
-#include "aux_kernels.cuh"
 #include "conv_gemm.cuh"
+#include "aux_kernels.cuh"
 
 namespace {
 
@@ -122,6 +122,8 @@ struct Launch {
   dim3 grid{1, 1, 1};
   // flops (2*M*N*K, real dims)
   double flops = 0.0;
+  // algorithmic HBM bytes: every operand read once, output written once
+  double bytes = 0.0;
 };
 
 const void* get_field(const tdet_op& o, int f) {
@@ -151,7 +153,7 @@ int encode_b(CUtensorMap* tm, const void* wgt, int ktot, int cout, int bn) {
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(bn)};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = driver().encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt),
+  CUresult r = driver().encode_tiled(tm, TDET_WEIGHT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt),
                                      dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -273,6 +275,10 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   if (g > num_tiles) g = num_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.flops = 2.0 * static_cast<double>(gp.M) * o.cout * (static_cast<double>(o.cin) * o.kh * o.kw);
+  l.bytes = 2.0 * (static_cast<double>(o.n) * o.h * o.w * o.cin +
+                   static_cast<double>(o.cout) * o.cin * o.kh * o.kw +
+                   static_cast<double>(gp.M) * o.cout * (1 + (o.residual ? 1 : 0)) +
+                   (o.coarse ? static_cast<double>(o.n) * o.hc * o.wc * o.cout : 0.0));
   return TDET_OK;
 }
 
@@ -336,6 +342,8 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   if (g > gp.num_m_tiles) g = gp.num_m_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.flops = 2.0 * static_cast<double>(o.n) * o.ho * o.wo * 64.0 * 147.0;
+  l.bytes = 2.0 * (static_cast<double>(o.n) * hp * wp * 4 + 64.0 * 448 +
+                   static_cast<double>(o.n) * o.ho * o.wo * 64);
   return TDET_OK;
 }
 
@@ -349,15 +357,19 @@ int build_launch(Launch& l, const DeviceInfo& di) {
       if (o.cin != 3 || !o.x || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad arguments");
       if (o.x_dtype != TDET_BF16 && o.x_dtype != TDET_F32)
         return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad dtype");
+      l.bytes = static_cast<double>(o.n) * o.h * o.w * 3 * (o.x_dtype == TDET_F32 ? 4 : 2) +
+                static_cast<double>(o.n) * (2 * o.ho + 6) * (2 * o.wo + 16) * 8;
       return TDET_OK;
     case TDET_OP_MAXPOOL:
       if (o.cin % 8 || !o.x || !o.y || o.ho != out_dim(o.h, 3, 2, 1, 1) ||
           o.wo != out_dim(o.w, 3, 2, 1, 1))
         return fail(TDET_ERR_INVALID_ARGUMENT, "maxpool: bad arguments");
+      l.bytes = 2.0 * o.n * o.cin * (static_cast<double>(o.h) * o.w + static_cast<double>(o.ho) * o.wo);
       return TDET_OK;
     case TDET_OP_SUBSAMPLE:
       if (o.cin % 8 || !o.x || !o.y || o.ho != (o.h - 1) / 2 + 1 || o.wo != (o.w - 1) / 2 + 1)
         return fail(TDET_ERR_INVALID_ARGUMENT, "subsample: bad arguments");
+      l.bytes = 4.0 * o.n * o.cin * static_cast<double>(o.ho) * o.wo;
       return TDET_OK;
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
@@ -440,6 +452,8 @@ extern "C" {
 
 int tdet_abi_version(void) { return TDET_ABI_VERSION; }
 
+int tdet_weight_dtype(void) { return TDET_WEIGHT_FP16 ? TDET_F16 : TDET_BF16; }
+
 const char* tdet_last_error(void) { return g_err; }
 
 int tdet_device_supported(int device) {
@@ -454,7 +468,7 @@ int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin
   const long long total = static_cast<long long>(cout) * cin * kh * kw;
   const int g = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
   pack_weight_kernel<<<g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, static_cast<__nv_bfloat16*>(w_packed), cout, cin, kh, kw);
+      w_oihw, static_cast<weight_t*>(w_packed), cout, cin, kh, kw);
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }
@@ -462,7 +476,7 @@ int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin
 int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream) {
   if (!w_oihw || !w_packed) return fail(TDET_ERR_INVALID_ARGUMENT, "pack_stem_weight: null pointer");
   pack_stem_weight_kernel<<<(64 * 448 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, static_cast<__nv_bfloat16*>(w_packed));
+      w_oihw, static_cast<weight_t*>(w_packed));
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }
@@ -563,6 +577,53 @@ int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void*
     rc = run_launch(l, *plan->di, st);
     if (rc) return rc;
   }
+  return TDET_OK;
+}
+
+int tdet_plan_run_timed(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream,
+                        float* ms_per_launch) {
+  if (!plan || !ms_per_launch) return fail(TDET_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_ext != static_cast<int>(plan->ext.size()))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "plan_run_timed: wrong number of external pointers");
+  for (int e = 0; e < n_ext; ++e)
+    if (ext_ptrs[e] != plan->ext[e])
+      return fail(TDET_ERR_INVALID_ARGUMENT,
+                  "plan_run_timed: external pointers must match the last tdet_plan_run");
+  DeviceGuard guard;
+  int rc = guard.enter(plan->device);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = plan->launches.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) TDET_CUDA(cudaEventCreate(&e));
+  TDET_CUDA(cudaEventRecord(ev[0], st));
+  for (size_t i = 0; i < n; ++i) {
+    rc = run_launch(plan->launches[i], *plan->di, st);
+    if (rc) break;
+    TDET_CUDA(cudaEventRecord(ev[i + 1], st));
+  }
+  if (!rc) {
+    TDET_CUDA(cudaEventSynchronize(ev[n]));
+    for (size_t i = 0; i < n; ++i) TDET_CUDA(cudaEventElapsedTime(&ms_per_launch[i], ev[i], ev[i + 1]));
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* out) {
+  if (!plan || !out || index < 0 || index >= static_cast<int>(plan->launches.size()))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "launch_info: bad arguments");
+  const Launch& l = plan->launches[index];
+  out->kind = l.kind;
+  out->tile_n = l.bn;
+  out->grid = static_cast<int32_t>(l.grid.x);
+  out->a_mode = (l.kind == TDET_OP_CONV || l.kind == TDET_OP_STEM) ? l.gp.a_mode : -1;
+  out->m = l.gp.M;
+  out->n = l.gp.N;
+  out->k = (l.kind == TDET_OP_STEM) ? 147 : l.op.cin * l.op.kh * l.op.kw;
+  out->reserved = 0;
+  out->flops = l.flops;
+  out->bytes = l.bytes;
   return TDET_OK;
 }
 

@@ -26,6 +26,11 @@ def require_cuda(t, what):
             "%s must be a CUDA tensor: the B200 path has no CPU fallback" % what)
 
 
+def weight_dtype():
+    """torch dtype of packed conv weights (what tdet_weight_dtype() reports)."""
+    return torch.float16 if _C.lib().tdet_weight_dtype() == _C.F16 else torch.bfloat16
+
+
 def conv_out(v, k, s, p, d=1):
     return (v + 2 * p - d * (k - 1) - 1) // s + 1
 
@@ -41,7 +46,7 @@ def pack_conv_weight(w):
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     o, i, kh, kw = w.shape
-    out = torch.empty((o, kh, kw, i), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((o, kh, kw, i), dtype=weight_dtype(), device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_conv_weight(w.data_ptr(), out.data_ptr(), o, i, kh, kw,
                                                 _stream_ptr(w.device)))
@@ -56,7 +61,7 @@ def pack_stem_weight(w):
         raise ValueError("stem weight must be (64,3,7,7)")
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    out = torch.empty((64, 448), dtype=torch.bfloat16, device=w.device)
+    out = torch.empty((64, 448), dtype=weight_dtype(), device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_stem_weight(w.data_ptr(), out.data_ptr(), _stream_ptr(w.device)))
     return out
@@ -209,6 +214,24 @@ class Plan:
         with torch.cuda.device(self.index):
             _C.check(_C.lib().tdet_plan_run(self._handle, ext_arr, self.n_ext,
                                             _stream_ptr(self.device)))
+
+    def run_timed(self, ext):
+        """Per-launch device milliseconds (CUDA events between launches); measurement only."""
+        self.run(ext)
+        ext_arr = (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
+        ms = (ctypes.c_float * self.num_launches)()
+        with torch.cuda.device(self.index):
+            _C.check(_C.lib().tdet_plan_run_timed(self._handle, ext_arr, self.n_ext,
+                                                  _stream_ptr(self.device), ms))
+        return list(ms)
+
+    def launch_info(self):
+        out = []
+        for i in range(self.num_launches):
+            info = _C.TdetLaunchInfo()
+            _C.check(_C.lib().tdet_plan_launch_info(self._handle, i, ctypes.byref(info)))
+            out.append({f: getattr(info, f) for f, _ in _C.TdetLaunchInfo._fields_ if f != "reserved"})
+        return out
 
     def __del__(self):
         h = getattr(self, "_handle", None)

@@ -174,6 +174,7 @@ class FPN(nn.Module):
         outs = [torch.empty(s, dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
                 for s in out_shapes]
         plan.run(feats + outs)
+        self._last_run = (plan, feats + outs)  # for profiling tools (bench.py)
         if want_fp32:
             outs = [o.float() for o in outs]
         return tuple(outs)
