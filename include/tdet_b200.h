@@ -21,7 +21,7 @@
  *                        FPN output 3x3 p1 + bias         models/necks/fpn.py:106-108
  *                        FPN extra stride-2 3x3 (+ReLU on input done by producer) fpn.py:118-124
  *   TDET_OP_SUBSAMPLE  F.max_pool2d(x, 1, stride=2)       models/necks/fpn.py:114-116
- *   tdet_pack_conv_weight / tdet_pack_stem_weight / tdet_fold_bn
+ *   tdet_pack_conv_weight / tdet_pack_stem_weight / tdet_fold_bn / tdet_conv_bound_consts
  *                      derive the kernels' operand formats from the reference's fp32 OIHW
  *                      parameters and BatchNorm2d buffers (state_dict layout of resnet.py/fpn.py)
  *
@@ -32,12 +32,15 @@
  *   - The library never allocates or frees caller tensors.  All device buffers (activations,
  *     packed weights, outputs) are owned by the caller (torch's caching allocator on the Python side).
  *   - All GPU work is enqueued asynchronously on the caller's stream (cudaStream_t passed as void*);
- *     no hidden synchronisation.
- *   - Activations are dense NHWC bf16 unless stated otherwise; conv weights are packed
- *     [Cout][kh][kw][Cin] in the 16-bit format tdet_weight_dtype() reports (fp16 by default:
- *     weights are bounded constants, so the 3 extra mantissa bits are free accuracy; K-major rows,
- *     the tcgen05 B operand); per-channel epilogue
- *     parameters are fp32.
+ *     no hidden synchronisation (tdet_plan_run_timed is the one documented exception).
+ *   - Activations are dense NHWC 16-bit.  At the module boundary (network input, returned feature
+ *     maps) they are plain bf16.  Internal tensors may instead be fp16 significands with ONE
+ *     power-of-two exponent per tensor (tdet_tensor_meta): 3 more mantissa bits than bf16 at the same
+ *     tensor-core rate, with the exponent chosen on the device from a rigorous bound so that no
+ *     input can overflow (see DESIGN.md "Numerics").  tcgen05 requires A and B of one MMA to share a
+ *     format, so a conv's weights are packed in the format of its input tensor.
+ *   - Conv weights are packed [Cout][kh][kw][Cin] (K-major rows, the tcgen05 B operand);
+ *     per-channel epilogue parameters are fp32.
  *   - A plan is bound to one device, is not re-entrant (one in-flight run per plan); distinct plans
  *     are independent.
  *   - There is no CPU fallback: on a device that is not sm_100 every compute entry point returns
@@ -53,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 1
+#define TDET_ABI_VERSION 2
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -76,26 +79,40 @@ typedef enum tdet_op_kind {
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2 } tdet_dtype;
 
 enum {
-  TDET_FLAG_RELU = 1 /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
+  TDET_FLAG_RELU = 1,       /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
+  TDET_FLAG_SCALED_OUT = 2  /* y is stored with a device-chosen power-of-two exponent (needs y_meta,
+                               x_meta and bound_consts) */
 };
+
+/* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
+ * the IEEE-754 bit pattern of the true max |value| (accumulated with atomicMax, so the caller must
+ * zero it before the producing op runs; tdet_plan_run does that for the arena it is told about). */
+typedef struct tdet_tensor_meta {
+  int32_t e;
+  uint32_t amax_bits;
+} tdet_tensor_meta;
 
 /*
  * One step of the path.  Unused fields must be zero / NULL.
  *
- * TDET_OP_PREP      x: logical (n, 3, h, w) image batch of x_dtype with element strides
+ * TDET_OP_PREP      x: logical (n, 3, h, w) image batch of x_dtype (F32/BF16) with element strides
  *                   x_stride[] = {n, c, h, w} (NCHW-contiguous or channels_last both work)
  *                   y: bf16 [n][hp][wp][4] with hp = 2*ho + 6, wp = 2*wo + 16 (ho/wo = stem output
  *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
- * TDET_OP_STEM      x: the PREP output; wgt: tdet_pack_stem_weight output (bf16 [64][448]);
- *                   scale/shift: folded bn1; y: bf16 [n][ho][wo][64].  h,w = original image size.
- * TDET_OP_MAXPOOL   x: bf16 [n][h][w][cin]; y: bf16 [n][ho][wo][cin]; kh=kw=3, stride 2, pad 1.
- * TDET_OP_CONV      x: bf16 [n][h][w][cin]; wgt: bf16 [cout][kh][kw][cin]; y: bf16 [n][ho][wo][cout]
- *                   y = act( conv(x) * scale + shift + residual + up2(coarse) )
+ *                   y_meta (optional): receives the image's |max| (exponent 0).
+ * TDET_OP_STEM      x: the PREP output (bf16); wgt: tdet_pack_stem_weight output (bf16 [64][448]);
+ *                   scale/shift: folded bn1; y: [n][ho][wo][64] of y_dtype.  h,w = image size.
+ * TDET_OP_MAXPOOL   x: [n][h][w][cin] of x_dtype; y: [n][ho][wo][cin] same dtype; 3x3, stride 2,
+ *                   pad 1.  (Metadata passes through unchanged: the caller aliases it.)
+ * TDET_OP_CONV      x: [n][h][w][cin] of x_dtype; wgt: [cout][kh][kw][cin] of the SAME dtype;
+ *                   y: [n][ho][wo][cout] of y_dtype
+ *                   y = act( conv(x) * scale + shift + residual + up2(coarse) )   (true values)
  *                   scale == NULL means 1; shift == NULL means 0 (shift is the conv bias for FPN);
- *                   residual: bf16 [n][ho][wo][cout] or NULL; coarse: bf16 [n][hc][wc][cout] or NULL,
- *                   with ho == 2*hc and wo == 2*wc (nearest x2, fpn.py:100-101).
- *                   cin and cout must be multiples of 64.
- * TDET_OP_SUBSAMPLE y[n][i][j][:] = x[n][2i][2j][:]   (ho = (h-1)/2+1)
+ *                   residual: [n][ho][wo][cout] of residual_dtype or NULL; coarse: [n][hc][wc][cout]
+ *                   of coarse_dtype or NULL, with ho == 2*hc and wo == 2*wc (nearest x2,
+ *                   fpn.py:100-101).  cin and cout must be multiples of 64.
+ *                   *_meta: optional tdet_tensor_meta of each tensor (NULL = exponent 0, unknown max).
+ * TDET_OP_SUBSAMPLE y[n][i][j][:] = x[n][2i][2j][:]   (ho = (h-1)/2+1), any 16-bit dtype
  */
 typedef struct tdet_op {
   int32_t kind;  /* tdet_op_kind */
@@ -105,8 +122,10 @@ typedef struct tdet_op {
   int32_t stride, pad, dil;
   int32_t ho, wo;
   int32_t hc, wc;     /* coarse level size for the upsample-add epilogue */
-  int32_t x_dtype;    /* PREP only: tdet_dtype of x */
-  int32_t reserved0;
+  int32_t x_dtype;    /* tdet_dtype of x (and of wgt for conv ops) */
+  int32_t y_dtype;    /* tdet_dtype of y (BF16 or F16) */
+  int32_t residual_dtype;
+  int32_t coarse_dtype;
   int64_t x_stride[4]; /* PREP only: element strides of x for (n, c, h, w) */
   const void* x;
   const void* wgt;
@@ -115,28 +134,36 @@ typedef struct tdet_op {
   const float* shift;
   const void* residual;
   const void* coarse;
+  const tdet_tensor_meta* x_meta;
+  const tdet_tensor_meta* residual_meta;
+  const tdet_tensor_meta* coarse_meta;
+  tdet_tensor_meta* y_meta;
+  const float* bound_consts; /* tdet_conv_bound_consts output; needed with TDET_FLAG_SCALED_OUT */
 } tdet_op;
 
 typedef struct tdet_plan tdet_plan; /* opaque */
 
 /* ---- library / device ------------------------------------------------------------------- */
 int tdet_abi_version(void);
-/* 16-bit format of packed conv weights (the tcgen05 B operand): TDET_F16 or TDET_BF16. */
-int tdet_weight_dtype(void);
 const char* tdet_last_error(void);
 /* 0 if `device` is an sm_100 part this build can run on, else TDET_ERR_UNSUPPORTED_DEVICE. */
 int tdet_device_supported(int device);
 
 /* ---- operand preparation (run once per weight version) ----------------------------------- */
-/* fp32 OIHW [cout][cin][kh][kw] -> 16-bit [cout][kh][kw][cin] in tdet_weight_dtype() (RNE). */
+/* fp32 OIHW [cout][cin][kh][kw] -> 16-bit [cout][kh][kw][cin] (round-to-nearest-even);
+ * dtype = TDET_BF16 or TDET_F16. */
 int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw,
-                          void* stream);
-/* fp32 [64][3][7][7] -> 16-bit [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
+                          int dtype, void* stream);
+/* fp32 [64][3][7][7] -> bf16 [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
 int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
 /* eval-mode BatchNorm2d -> per-channel fp32 scale = gamma/sqrt(var+eps), shift = beta-mean*scale
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
 int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
                  float eps, float* scale, float* shift, int channels, void* stream);
+/* consts[0] = max_c |scale_c| * sum_k |w_packed[c][k]|, consts[1] = max_c |shift_c|  (scale NULL = 1,
+ * shift NULL = 0): |conv(x)*scale + shift| <= consts[0] * max|x| + consts[1] for any x. */
+int tdet_conv_bound_consts(const void* w_packed, int dtype, const float* scale, const float* shift,
+                           int cout, int k, float* consts, void* stream);
 
 /* ---- execution ---------------------------------------------------------------------------- */
 /* Validates and runs one op immediately (descriptors are built on the fly). */
@@ -147,9 +174,11 @@ int tdet_op_run(const tdet_op* op, int device, void* stream);
  * ext_ptrs lists the n_ext caller pointers that may change between runs (network input, returned
  * outputs); every op field equal to ext_ptrs[i] is re-bound to the i-th pointer given to
  * tdet_plan_run.  Pass n_ext = 0 for a fully static plan.
+ * meta_arena/meta_count (optional): the contiguous tdet_tensor_meta array the ops' *_meta pointers
+ * live in; it is zeroed (one cudaMemsetAsync) at the start of every run.
  */
 int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void* const* ext_ptrs,
-                     int n_ext, int device);
+                     int n_ext, tdet_tensor_meta* meta_arena, int meta_count, int device);
 int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream);
 /* Same as tdet_plan_run with unchanged external pointers, but brackets every kernel launch with
  * CUDA events on `stream` and returns the per-launch device time in milliseconds
@@ -165,7 +194,7 @@ typedef struct tdet_launch_info {
   int32_t grid;   /* CTAs launched (GEMM kernels) */
   int32_t a_mode; /* 0 tiled, 1 im2col, 2 stem; -1 for non-GEMM kernels */
   int32_t m, n, k;
-  int32_t reserved;
+  int32_t variant; /* GEMM kernel instantiation: stages * 16 + residual slabs */
   double flops;
   double bytes;
 } tdet_launch_info;
@@ -174,7 +203,7 @@ int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* ou
 double tdet_plan_flops(const tdet_plan* plan);
 int tdet_plan_destroy(tdet_plan* plan);
 
-/* Test hook: runs the TMA im2col loader alone and dumps one 128x64 A tile (un-swizzled, bf16
+/* Test hook: runs the TMA im2col loader alone and dumps one 128x64 A tile (un-swizzled, 16-bit
  * [128][64]) for output rows [m0, m0+128), filter tap (r, s), channel chunk kc.  Used by the
  * GPU tests to pin the descriptor semantics independently of the MMA. */
 int tdet_debug_im2col_tile(const tdet_op* op, int m0, int r, int s, int kc, void* tile_out,

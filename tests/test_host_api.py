@@ -142,8 +142,8 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_C.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _C.lib().tdet_abi_version() == 1
-    assert ctypes.sizeof(_C.TdetOp) == 160
+    assert _C.lib().tdet_abi_version() == _C.ABI_VERSION
+    assert ctypes.sizeof(_C.TdetOp) == 208
 
 
 def test_no_gpu_calls_fail_cleanly_without_device():

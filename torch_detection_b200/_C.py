@@ -8,6 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
+ABI_VERSION = 2
 
 # tdet_status
 OK = 0
@@ -23,6 +24,7 @@ OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 # tdet_dtype
 BF16, F32, F16 = 0, 1, 2
 FLAG_RELU = 1
+FLAG_SCALED_OUT = 2
 
 
 class TdetOp(ctypes.Structure):
@@ -34,11 +36,15 @@ class TdetOp(ctypes.Structure):
         ("stride", ctypes.c_int32), ("pad", ctypes.c_int32), ("dil", ctypes.c_int32),
         ("ho", ctypes.c_int32), ("wo", ctypes.c_int32),
         ("hc", ctypes.c_int32), ("wc", ctypes.c_int32),
-        ("x_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("x_dtype", ctypes.c_int32), ("y_dtype", ctypes.c_int32),
+        ("residual_dtype", ctypes.c_int32), ("coarse_dtype", ctypes.c_int32),
         ("x_stride", ctypes.c_int64 * 4),
         ("x", ctypes.c_void_p), ("wgt", ctypes.c_void_p), ("y", ctypes.c_void_p),
         ("scale", ctypes.c_void_p), ("shift", ctypes.c_void_p),
         ("residual", ctypes.c_void_p), ("coarse", ctypes.c_void_p),
+        ("x_meta", ctypes.c_void_p), ("residual_meta", ctypes.c_void_p),
+        ("coarse_meta", ctypes.c_void_p), ("y_meta", ctypes.c_void_p),
+        ("bound_consts", ctypes.c_void_p),
     ]
 
 
@@ -46,7 +52,7 @@ class TdetLaunchInfo(ctypes.Structure):
     """Mirror of ``struct tdet_launch_info``."""
     _fields_ = [("kind", ctypes.c_int32), ("tile_n", ctypes.c_int32), ("grid", ctypes.c_int32),
                 ("a_mode", ctypes.c_int32), ("m", ctypes.c_int32), ("n", ctypes.c_int32),
-                ("k", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("k", ctypes.c_int32), ("variant", ctypes.c_int32),
                 ("flops", ctypes.c_double), ("bytes", ctypes.c_double)]
 
 
@@ -57,8 +63,8 @@ class TdetError(RuntimeError):
 
 
 EXPORTS = [
-    "tdet_abi_version", "tdet_weight_dtype", "tdet_last_error", "tdet_device_supported",
-    "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
+    "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
+    "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn", "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_timed",
     "tdet_plan_num_launches", "tdet_plan_launch_info",
     "tdet_plan_flops", "tdet_plan_destroy", "tdet_debug_im2col_tile",
@@ -81,12 +87,13 @@ def lib():
     L.tdet_abi_version.restype = i32
     L.tdet_last_error.restype = ctypes.c_char_p
     L.tdet_device_supported.argtypes = [i32]
-    L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
     L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
+    L.tdet_conv_bound_consts.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
     L.tdet_op_run.argtypes = [ctypes.POINTER(TdetOp), i32, vp]
     L.tdet_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(TdetOp), i32,
-                                   ctypes.POINTER(vp), i32, i32]
+                                   ctypes.POINTER(vp), i32, vp, i32, i32]
     L.tdet_plan_run.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
     L.tdet_plan_run_timed.argtypes = [vp, ctypes.POINTER(vp), i32, vp, ctypes.POINTER(f32)]
     L.tdet_plan_launch_info.argtypes = [vp, i32, ctypes.POINTER(TdetLaunchInfo)]
@@ -98,8 +105,8 @@ def lib():
     for name in EXPORTS:
         if name not in ("tdet_last_error", "tdet_plan_flops"):
             getattr(L, name).restype = i32
-    if L.tdet_abi_version() != 1:
-        raise ImportError("libtdet_b200.so ABI version mismatch")
+    if L.tdet_abi_version() != ABI_VERSION:
+        raise ImportError("libtdet_b200.so ABI version mismatch (rebuild it)")
     _lib = L
     return L
 

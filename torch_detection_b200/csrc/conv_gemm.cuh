@@ -1,19 +1,29 @@
 // Implicit-GEMM convolution for sm_100a: TMA (tiled / im2col) -> shared memory ring ->
-// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue (BN scale/shift or bias, residual add,
-// FPN nearest-x2 upsample-add, ReLU) -> NHWC bf16.
+// tcgen05.mma (16-bit x 16-bit -> fp32 in TMEM) -> fused epilogue (BN scale/shift or bias, residual
+// add, FPN nearest-x2 upsample-add, ReLU) -> shared-memory staging -> TMA store, NHWC 16-bit.
 //
 // GEMM view: D[M = N_img*Ho*Wo, Cout] = A[M, K = kh*kw*Cin] * W[Cout, K]^T.
 // A rows are output pixels (NHWC), gathered by the TMA unit:
 //   A_TILED  : 1x1 stride-1 conv -> A is the activation matrix itself (2D tiled tensor map)
 //   A_IM2COL : kxk / strided conv -> 4D im2col tensor map, one load per (filter tap, 64-ch chunk)
 //   A_STEM   : 7x7/2 stem on the padded NHWC4 staging -> 5D tiled map with overlapping windows
-// W is pre-packed [Cout][kh][kw][Cin] bf16, i.e. K-major rows, loaded by a 2D tiled map.
+// W is pre-packed [Cout][kh][kw][Cin], i.e. K-major rows, loaded by a 2D tiled map.
 //
-// Persistent, warp-specialised CTA (192 threads):
-//   warp 0      TMA producer            (full/empty mbarrier ring, kStages deep)
-//   warp 1      tcgen05.mma issuer      (lane 0 issues; accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue                (tcgen05.ld 32x32b -> registers -> global), overlapped
-//                                        with the next tile's main loop through tmem_full/empty.
+// Persistent, warp-specialised CTA (224 threads), every global<->shared transfer is asynchronous:
+//   warp 0      TMA producer for A/B     (full/empty mbarrier ring, STAGES deep)
+//   warp 1      tcgen05.mma issuer       (lane 0 issues; accumulators double-buffered in TMEM)
+//   warps 2..5  epilogue                 (tcgen05.ld 32x32b -> registers -> fp32 math -> 128B-swizzled
+//                                         staging slab -> TMA store), overlapped with the next tile's
+//                                         main loop through tmem_full/empty
+//   warp 6      TMA producer for the residual operand (64-column slabs, RES_SLABS-deep ring) so the
+//                                         residual of tile i+1 streams in while tile i is finished
+//
+// Numerics: every stored activation tensor may carry a per-tensor power-of-two exponent
+// (TensorMeta::e, value = stored * 2^e) and its true |max| (TensorMeta::amax_bits).  A kernel picks
+// its output exponent from a rigorous bound |out| <= G*amax(in) + max|shift| + amax(res) +
+// amax(coarse) (G = max_c |scale_c| * ||w_c||_1), which keeps fp16 storage (11-bit significand)
+// overflow-free for any input without calibration.  With all metadata pointers null the exponents
+// are 0 and the tensors are plain bf16/fp16.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -22,33 +32,25 @@
 namespace tdet {
 
 constexpr int kBM = 128;         // UMMA M (cta_group::1)
-constexpr int kBK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int kBK = 64;          // 16-bit elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
-constexpr int kGemmThreads = 192;
-constexpr int kABytes = kBM * kBK * 2;  // 16 KiB per stage
+constexpr int kGemmThreads = 224;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
+constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
+constexpr int kOutSlabs = 2;             // staging double buffer for TMA stores
 
 enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2 };
 
-// Operand formats.  Activations (A) are bf16 (8-bit exponent: the residual stream of a randomly
-// initialised ResNet-101 reaches ~2.4e5).  Weights (B) use the same format: a mixed
-// bf16 x fp16 tcgen05.mma (idesc a_format != b_format) raises "illegal instruction" on B200
-// (measured), so TDET_WEIGHT_FP16=1 is only usable together with fp16 activations.
-#ifndef TDET_WEIGHT_FP16
-#define TDET_WEIGHT_FP16 0
-#endif
-#if TDET_WEIGHT_FP16
-constexpr uint32_t kWeightFmt = kFmtF16;
-using weight_t = __half;
-__device__ __forceinline__ weight_t to_weight(float v) { return __float2half_rn(v); }
-#else
-constexpr uint32_t kWeightFmt = kFmtBF16;
-using weight_t = __nv_bfloat16;
-__device__ __forceinline__ weight_t to_weight(float v) { return __float2bfloat16_rn(v); }
-#endif
+struct TensorMeta {
+  int e;                  // stored value * 2^e = true value
+  unsigned amax_bits;     // float bits of the true |max| (atomicMax on the bit pattern; values >= 0)
+};
 
 struct ConvGemmParams {
   CUtensorMap tmap_a;
   CUtensorMap tmap_b;
+  CUtensorMap tmap_out;   // 2D (Cout, M) box (64,128); A_STEM: 4D (64, Wo, Ho, N) box (64,bw,bh,1)
+  CUtensorMap tmap_res;   // 2D (Cout, M) box (64,128) over the residual tensor (if any)
   int M;            // valid output rows (pixels); for A_STEM rows are masked per pixel instead
   int N;            // Cout
   int num_m_tiles;
@@ -63,45 +65,76 @@ struct ConvGemmParams {
   int tile_bw, tile_bh;  // A_STEM: tile shape in output pixels (tile_bw * tile_bh == 128)
   int Hc, Wc;       // coarse level size (upsample-add)
   int relu;
+  int has_res;
+  int ab_fp16;      // operand format of A and B: 1 = fp16, 0 = bf16 (must match, see idesc)
+  int out_fp16, res_fp16, coarse_fp16;  // storage formats
+  int out_scaled;   // choose a power-of-two output exponent from the bound (else exponent 0)
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* residual;
-  const __nv_bfloat16* coarse;
-  __nv_bfloat16* out;
+  const void* coarse;
+  const TensorMeta* in_meta;      // nullable
+  const TensorMeta* res_meta;     // nullable
+  const TensorMeta* coarse_meta;  // nullable
+  TensorMeta* out_meta;           // nullable; when set the true |max| of the output is recorded
+  const float* bound_consts;      // {G, max|shift|}, required iff out_scaled
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int RES_SLABS>
 struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kNumBars = 2 * STAGES + 4;
+  static constexpr int kResOffset = STAGES * kStageBytes;
+  static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
+  static constexpr int kBarOffset = kOutOffset + kOutSlabs * kSlabBytes;
+  static constexpr int kNumBars = 2 * STAGES + 4 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1);
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
-  static constexpr int kTotal = kParamOffset + 2 * BN * 4;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-byte alignment
+  static constexpr int kDynamic = kParamOffset + 2 * BN * 4;
+  static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
 };
 
-template <int BN, int STAGES>
+__device__ __forceinline__ void unpack16x2(uint32_t w, bool fp16, float& lo, float& hi) {
+  if (fp16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x;
+    hi = f.y;
+  } else {
+    lo = bf16_lo(w);
+    hi = bf16_hi(w);
+  }
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
+  if (fp16) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+
+template <int BN, int STAGES, int RES_SLABS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
-  constexpr uint32_t kIdesc = make_idesc_f16kind(kBM, BN, kFmtBF16, kWeightFmt);
+  constexpr int kSlabsPerTile = BN / 64;
+  constexpr int kRS = RES_SLABS > 0 ? RES_SLABS : 1;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
 
   const uint32_t smem_a = base;
   const uint32_t smem_b = base + STAGES * kABytes;
+  const uint32_t smem_res = base + L::kResOffset;
+  const uint32_t smem_out = base + L::kOutOffset;
   const uint32_t bar0 = base + L::kBarOffset;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
+  auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kRS + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
   float* s_scale = reinterpret_cast<float*>(smem + L::kParamOffset);
   float* s_shift = s_scale + BN;
@@ -112,6 +145,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
+    tma_prefetch_desc(&p.tmap_out);
+    if (p.has_res) tma_prefetch_desc(&p.tmap_res);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -121,6 +156,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < kRS; ++s) {
+      mbar_init(rfull_bar(s), 1);
+      mbar_init(rempty_bar(s), 1);
     }
     fence_mbar_init();
   }
@@ -137,7 +176,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int num_kb = p.kh * p.kw * p.k_chunks;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (A, B)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -162,10 +201,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         cw = tw * p.tile_bw;
         ch = th * p.tile_bh;
       }
-      int kb = 0;
       for (int r = 0; r < p.kh; ++r) {
         for (int s = 0; s < p.kw; ++s) {
-          for (int kc = 0; kc < p.k_chunks; ++kc, ++kb) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
               const uint32_t fb = full_bar(stage);
@@ -192,6 +230,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    const uint32_t fmt = p.ab_fp16 ? kFmtF16 : kFmtBF16;
+    const uint32_t idesc = make_idesc_f16kind(kBM, BN, fmt, fmt);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -208,8 +248,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint64_t db = make_smem_desc_sw128(smem_b + stage * L::kBBytes);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
+            umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
@@ -220,16 +260,63 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------ TMA producer (residual)
+    if (RES_SLABS > 0 && p.has_res) {
+      int rs = 0;
+      uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        for (int s = 0; s < kSlabsPerTile; ++s) {
+          mbar_wait(rempty_bar(rs), rphase ^ 1u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
+            tma_load_2d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
+                        m_tile * kBM);
+          }
+          __syncwarp();
+          if (++rs == kRS) { rs = 0; rphase ^= 1u; }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;      // accumulator row == TMEM lane
+    const int row = quad * 32 + lane;      // accumulator row == TMEM lane == staging row
     const int epi_tid = threadIdx.x - 64;  // 0..127
+    const bool issuer = epi_tid == 0;      // issues TMA stores, frees residual slabs
+    const bool has_res = RES_SLABS > 0 && p.has_res;
+    const bool has_coarse = p.coarse != nullptr;
+    const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
+
+    // per-tensor exponents (all zero when no metadata is attached)
+    const int e_in = p.in_meta ? p.in_meta->e : 0;
+    const int e_res = p.res_meta ? p.res_meta->e : 0;
+    const int e_co = p.coarse_meta ? p.coarse_meta->e : 0;
+    int e_out = 0;
+    if (p.out_scaled) {
+      float bound = p.bound_consts[1];
+      const float a_in = p.in_meta ? __uint_as_float(p.in_meta->amax_bits) : 0.0f;
+      bound += p.bound_consts[0] * a_in;
+      if (p.res_meta && p.has_res) bound += __uint_as_float(p.res_meta->amax_bits);
+      if (p.coarse_meta && has_coarse) bound += __uint_as_float(p.coarse_meta->amax_bits);
+      if (bound > 0.0f && bound < 3.0e38f) e_out = ilogbf(bound) - 14;  // bound * 2^-e_out < 2^15
+      e_out = max(-100, min(100, e_out));
+      if (blockIdx.x == 0 && epi_tid == 0) p.out_meta->e = e_out;
+    }
+    const float mul_in = ldexpf(1.0f, e_in - e_out);
+    const float mul_shift = ldexpf(1.0f, -e_out);
+    const float mul_res = ldexpf(1.0f, e_res - e_out);
+    const float mul_co = ldexpf(1.0f, e_co - e_out);
+    float amax_local = 0.0f;
+
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_n_tile = -1;
-    const bool has_res = p.residual != nullptr;
-    const bool has_coarse = p.coarse != nullptr;
+    int rs = 0;
+    uint32_t rphase = 0;
+    int ob = 0;  // staging buffer of the next slab
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -237,15 +324,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       if (n_tile != cur_n_tile) {
         named_bar_sync(1, 128);
         for (int i = epi_tid; i < BN; i += 128) {
-          s_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.0f;
-          s_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.0f;
+          s_scale[i] = (p.scale ? __ldg(p.scale + n0 + i) : 1.0f) * mul_in;
+          s_shift[i] = (p.shift ? __ldg(p.shift + n0 + i) : 0.0f) * mul_shift;
         }
         named_bar_sync(1, 128);
         cur_n_tile = n_tile;
       }
-      // output row of this thread
+      // output pixel of this thread's row
       bool valid;
-      long long pix;  // linear NHWC pixel index of the output row
+      long long pix;
+      int st_c1 = 0, st_c2 = 0, st_c3 = 0;  // TMA store coordinates beyond the channel
       if (p.a_mode == A_STEM) {
         const int tw = m_tile % p.tiles_w;
         const int t = m_tile / p.tiles_w;
@@ -257,95 +345,156 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int wo = tw * p.tile_bw + wl;
         valid = (ho < p.Ho) && (wo < p.Wo);
         pix = (static_cast<long long>(img) * p.Ho + ho) * p.Wo + wo;
+        st_c1 = tw * p.tile_bw;
+        st_c2 = th * p.tile_bh;
+        st_c3 = img;
       } else {
         const int m = m_tile * kBM + row;
         valid = m < p.M;
         pix = m;
+        st_c1 = m_tile * kBM;
       }
-      const __nv_bfloat16* res_row = nullptr;
-      const __nv_bfloat16* coarse_row = nullptr;
-      if (valid && has_res) res_row = p.residual + pix * p.N + n0;
+      const uint8_t* coarse_row = nullptr;
       if (valid && has_coarse) {
         const int m = static_cast<int>(pix);
         const int q = m % p.Wo;
         const int t = m / p.Wo;
         const int pp = t % p.Ho;
         const int img = t / p.Ho;
-        coarse_row = p.coarse + ((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0;
+        coarse_row = static_cast<const uint8_t*>(p.coarse) +
+                     (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
       }
-      __nv_bfloat16* out_row = p.out + pix * p.N + n0;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_addr + chunk * 32, v);
-        uint4 rres[4], rco[4];
-        if (res_row) {
+      for (int slab = 0; slab < kSlabsPerTile; ++slab) {
+        // the staging buffer `ob` was last read by the TMA store issued two slabs ago
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        if (has_res) mbar_wait(rfull_bar(rs), rphase);
+        named_bar_sync(1, 128);
+        const uint32_t out_row = smem_out + ob * kSlabBytes + row * 128;
+        const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = ldg_nc_v4(res_row + chunk * 32 + j * 8);
-        }
-        if (coarse_row) {
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + slab * 64 + half * 32, v);
+          uint4 rco[4];
+          if (coarse_row) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + chunk * 32 + j * 8);
-        }
-        tmem_ld_wait();
-        float x[32];
+            for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
+          }
+          uint4 rres[4];
+          if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + chunk * 32 + j * 4);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + chunk * 32 + j * 4);
-          x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-          x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-          x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-          x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-        }
-        if (res_row) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w4[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              x[8 * j + 2 * e] += bf16_lo(w4[e]);
-              x[8 * j + 2 * e + 1] += bf16_hi(w4[e]);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = res_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rres[j].x), "=r"(rres[j].y), "=r"(rres[j].z), "=r"(rres[j].w)
+                           : "r"(a));
             }
           }
-        }
-        if (coarse_row) {
+          tmem_ld_wait();
+          float x[32];
+          const int cb = slab * 64 + half * 32;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t w4[4] = {rco[j].x, rco[j].y, rco[j].z, rco[j].w};
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + cb + j * 4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + cb + j * 4);
+            x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+            x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+            x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+            x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+          }
+          if (has_res) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              x[8 * j + 2 * e] += bf16_lo(w4[e]);
-              x[8 * j + 2 * e + 1] += bf16_hi(w4[e]);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo, hi;
+                unpack16x2(w4[e], res_fp16, lo, hi);
+                x[8 * j + 2 * e] = fmaf(lo, mul_res, x[8 * j + 2 * e]);
+                x[8 * j + 2 * e + 1] = fmaf(hi, mul_res, x[8 * j + 2 * e + 1]);
+              }
             }
           }
-        }
-        if (p.relu) {
+          if (coarse_row) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
-        }
-        if (valid) {
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {rco[j].x, rco[j].y, rco[j].z, rco[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo, hi;
+                unpack16x2(w4[e], co_fp16, lo, hi);
+                x[8 * j + 2 * e] = fmaf(lo, mul_co, x[8 * j + 2 * e]);
+                x[8 * j + 2 * e + 1] = fmaf(hi, mul_co, x[8 * j + 2 * e + 1]);
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+          }
+          if (valid && p.out_meta) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) amax_local = fmaxf(amax_local, fabsf(x[i]));
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(x[8 * j + 0], x[8 * j + 1]);
-            o.y = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
-            o.z = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]);
-            o.w = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
-            stg_v4(out_row + chunk * 32 + j * 8, o);
+            o.x = pack16x2(x[8 * j + 0], x[8 * j + 1], out_fp16);
+            o.y = pack16x2(x[8 * j + 2], x[8 * j + 3], out_fp16);
+            o.z = pack16x2(x[8 * j + 4], x[8 * j + 5], out_fp16);
+            o.w = pack16x2(x[8 * j + 6], x[8 * j + 7], out_fp16);
+            const uint32_t a = out_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
+                         "r"(o.z), "r"(o.w)
+                         : "memory");
           }
         }
+        if (slab == kSlabsPerTile - 1) {
+          // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        fence_proxy_async_smem();  // staging writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (issuer) {
+          const uint32_t src = smem_out + ob * kSlabBytes;
+          if (p.a_mode == A_STEM) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),
+                "r"(st_c1), "r"(st_c2), "r"(st_c3)
+                : "memory");
+          } else {
+            asm volatile(
+                "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),
+                "r"(st_c1)
+                : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (has_res) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
+        }
+        ob ^= 1;
+        if (has_res) {
+          if (++rs == kRS) { rs = 0; rphase ^= 1u; }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.out_meta) {
+      float a = amax_local;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      if (lane == 0) atomicMax(&p.out_meta->amax_bits, __float_as_uint(ldexpf(a, e_out)));
     }
   }
 
@@ -357,14 +506,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
-// Debug/test kernel: load ONE im2col A tile and write it out un-swizzled as [128][64] bf16.
+// Debug/test kernel: load ONE im2col A tile and write it out un-swizzled as [128][64] 16-bit.
 __global__ void __launch_bounds__(128, 1)
 im2col_tile_dump_kernel(const __grid_constant__ CUtensorMap tmap, int c, int w, int h, int n,
                         int off_w, int off_h, __nv_bfloat16* out) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  const uint32_t base = (raw_addr + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw_addr);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0u) __trap();
   const uint32_t bar = base + kABytes;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);

@@ -11,13 +11,15 @@ from . import _C
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default (reference models/utils/layers.py:50-54)
 
+_TD = {torch.bfloat16: _C.BF16, torch.float16: _C.F16, torch.float32: _C.F32}
+
 
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _dev_index(t):
-    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+def _index(device):
+    return device.index if device.index is not None else torch.cuda.current_device()
 
 
 def require_cuda(t, what):
@@ -26,30 +28,68 @@ def require_cuda(t, what):
             "%s must be a CUDA tensor: the B200 path has no CPU fallback" % what)
 
 
-def weight_dtype():
-    """torch dtype of packed conv weights (what tdet_weight_dtype() reports)."""
-    return torch.float16 if _C.lib().tdet_weight_dtype() == _C.F16 else torch.bfloat16
-
-
 def conv_out(v, k, s, p, d=1):
     return (v + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class Act(object):
+    """Handle of a dense NHWC 16-bit activation tensor: device buffer, logical (n, h, w, c) shape,
+    storage dtype and the device address of its ``tdet_tensor_meta`` (None = plain values)."""
+    __slots__ = ("buf", "shape", "dtype", "meta")
+
+    def __init__(self, buf, shape, dtype=None, meta=None):
+        self.buf = buf
+        self.shape = tuple(shape)
+        self.dtype = dtype if dtype is not None else buf.dtype
+        self.meta = meta
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+
+def act_of(t, meta=None):
+    """Act view of a logical-NCHW channels_last tensor (zero copy)."""
+    n, c, h, w = t.shape
+    return Act(t, (n, h, w, c), t.dtype, meta)
+
+
+class MetaArena(object):
+    """Contiguous array of ``tdet_tensor_meta`` (8 bytes each) in device memory."""
+
+    def __init__(self, count, device):
+        self.tensor = torch.zeros((max(count, 1), 2), dtype=torch.int32, device=device)
+        self.count = count
+        self._next = 0
+
+    def new(self):
+        assert self._next < self.count
+        addr = self.tensor.data_ptr() + 8 * self._next
+        self._next += 1
+        return addr
+
+    def read(self):
+        """[(exponent, amax)] -- synchronises; debugging / tests only."""
+        raw = self.tensor.cpu()
+        amax = raw[:, 1].contiguous().view(torch.float32)
+        return [(int(raw[i, 0]), float(amax[i])) for i in range(self._next)]
 
 
 # --------------------------------------------------------------------------------------------
 # operand preparation
 # --------------------------------------------------------------------------------------------
 
-def pack_conv_weight(w):
-    """fp32 OIHW parameter -> bf16 [O][kh][kw][I] (tcgen05 B operand rows)."""
+def pack_conv_weight(w, dtype=torch.bfloat16):
+    """fp32 OIHW parameter -> 16-bit [O][kh][kw][I] (tcgen05 B operand rows) in `dtype`."""
     require_cuda(w, "weight")
     w = w.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     o, i, kh, kw = w.shape
-    out = torch.empty((o, kh, kw, i), dtype=weight_dtype(), device=w.device)
+    out = torch.empty((o, kh, kw, i), dtype=dtype, device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_conv_weight(w.data_ptr(), out.data_ptr(), o, i, kh, kw,
-                                                _stream_ptr(w.device)))
+                                                _TD[dtype], _stream_ptr(w.device)))
     return out
 
 
@@ -61,7 +101,7 @@ def pack_stem_weight(w):
         raise ValueError("stem weight must be (64,3,7,7)")
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    out = torch.empty((64, 448), dtype=weight_dtype(), device=w.device)
+    out = torch.empty((64, 448), dtype=torch.bfloat16, device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_stem_weight(w.data_ptr(), out.data_ptr(), _stream_ptr(w.device)))
     return out
@@ -82,6 +122,18 @@ def fold_bn(bn):
     return scale, shift
 
 
+def bound_consts(w_packed, scale, shift):
+    """{G, max|shift|} with |conv(x)*scale + shift| <= G*max|x| + max|shift| (device, fp32[2])."""
+    cout = w_packed.shape[0]
+    k = w_packed.numel() // cout
+    out = torch.empty(2, dtype=torch.float32, device=w_packed.device)
+    with torch.cuda.device(w_packed.device):
+        _C.check(_C.lib().tdet_conv_bound_consts(w_packed.data_ptr(), _TD[w_packed.dtype], _ptr(scale),
+                                                 _ptr(shift), cout, k, out.data_ptr(),
+                                                 _stream_ptr(w_packed.device)))
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # op descriptors
 # --------------------------------------------------------------------------------------------
@@ -90,91 +142,106 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def nhwc_empty(n, h, w, c, device):
-    """Dense NHWC bf16 buffer exposed as a logical-NCHW channels_last tensor (zero-copy view)."""
-    return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device,
-                       memory_format=torch.channels_last)
+def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
+    """Dense NHWC 16-bit buffer exposed as a logical-NCHW channels_last tensor (zero-copy view)."""
+    return torch.empty((n, c, h, w), dtype=dtype, device=device, memory_format=torch.channels_last)
 
 
-def op_conv(x_shape, x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
-            coarse=None, coarse_hw=(0, 0), relu=False):
-    """x_shape = (n, h, w, cin) of the NHWC input; wgt packed [cout][kh][kw][cin]."""
-    n, h, w, cin = x_shape
+def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
+            coarse=None, relu=False, consts=None, scaled_out=False):
+    """x, y, residual, coarse: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype."""
+    n, h, w, cin = x.shape
     cout = wgt.shape[0]
+    if wgt.dtype != x.dtype:
+        raise ValueError("conv weights must be packed in the input tensor's format (%s vs %s)"
+                         % (wgt.dtype, x.dtype))
     op = _C.TdetOp()
     op.kind = _C.OP_CONV
-    op.flags = _C.FLAG_RELU if relu else 0
+    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0)
     op.n, op.h, op.w, op.cin = n, h, w, cin
     op.cout, op.kh, op.kw = cout, kh, kw
     op.stride, op.pad, op.dil = stride, pad, dil
     op.ho, op.wo = conv_out(h, kh, stride, pad, dil), conv_out(w, kw, stride, pad, dil)
-    op.hc, op.wc = coarse_hw
-    op.x, op.wgt, op.y = _ptr(x), _ptr(wgt), _ptr(y)
+    assert y.shape == (n, op.ho, op.wo, cout), (y.shape, (n, op.ho, op.wo, cout))
+    op.x_dtype, op.y_dtype = _TD[x.dtype], _TD[y.dtype]
+    op.x, op.wgt, op.y = x.ptr, wgt.data_ptr(), y.ptr
+    op.x_meta, op.y_meta = x.meta, y.meta
     op.scale, op.shift = _ptr(scale), _ptr(shift)
-    op.residual, op.coarse = _ptr(residual), _ptr(coarse)
+    if residual is not None:
+        op.residual, op.residual_dtype, op.residual_meta = residual.ptr, _TD[residual.dtype], residual.meta
+    if coarse is not None:
+        op.coarse, op.coarse_dtype, op.coarse_meta = coarse.ptr, _TD[coarse.dtype], coarse.meta
+        op.hc, op.wc = coarse.shape[1], coarse.shape[2]
+    op.bound_consts = _ptr(consts)
     return op
 
 
-def op_prep(x, y, ho, wo):
+def op_prep(x, y, ho, wo, y_meta=None):
     n, c, h, w = x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_PREP
     op.n, op.h, op.w, op.cin = n, h, w, c
     op.ho, op.wo = ho, wo
-    if x.dtype == torch.float32:
-        op.x_dtype = _C.F32
-    elif x.dtype == torch.bfloat16:
-        op.x_dtype = _C.BF16
-    else:
+    if x.dtype not in (torch.float32, torch.bfloat16):
         raise NotImplementedError("input dtype %s (supported: float32, bfloat16)" % x.dtype)
+    op.x_dtype = _TD[x.dtype]
     for i, s in enumerate(x.stride()):
         op.x_stride[i] = s
     op.x, op.y = _ptr(x), _ptr(y)
+    op.y_meta = y_meta
     return op
 
 
-def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True):
+def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False):
+    """x: staged image buffer (bf16); y: ``Act`` of shape (n, ho, wo, 64)."""
     op = _C.TdetOp()
     op.kind = _C.OP_STEM
-    op.flags = _C.FLAG_RELU if relu else 0
+    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0)
     op.n, op.h, op.w, op.cin = n, h, w, 3
     op.cout, op.kh, op.kw = 64, 7, 7
     op.stride, op.pad, op.dil = 2, 3, 1
     op.ho, op.wo = conv_out(h, 7, 2, 3), conv_out(w, 7, 2, 3)
-    op.x, op.wgt, op.y = _ptr(x), _ptr(wgt), _ptr(y)
+    op.x_dtype, op.y_dtype = _C.BF16, _TD[y.dtype]
+    op.x, op.wgt, op.y = _ptr(x), _ptr(wgt), y.ptr
+    op.x_meta, op.y_meta = x_meta, y.meta
     op.scale, op.shift = _ptr(scale), _ptr(shift)
+    op.bound_consts = _ptr(consts)
     return op
 
 
-def op_maxpool(n, h, w, c, x, y):
+def op_maxpool(x, y):
+    n, h, w, c = x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_MAXPOOL
     op.n, op.h, op.w, op.cin = n, h, w, c
     op.cout, op.kh, op.kw, op.stride, op.pad, op.dil = c, 3, 3, 2, 1, 1
     op.ho, op.wo = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
-    op.x, op.y = _ptr(x), _ptr(y)
+    op.x_dtype = op.y_dtype = _TD[x.dtype]
+    op.x, op.y = x.ptr, y.ptr
     return op
 
 
-def op_subsample(n, h, w, c, x, y):
+def op_subsample(x, y):
+    n, h, w, c = x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_SUBSAMPLE
     op.n, op.h, op.w, op.cin = n, h, w, c
     op.cout, op.kh, op.kw, op.stride, op.pad, op.dil = c, 1, 1, 2, 0, 1
     op.ho, op.wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-    op.x, op.y = _ptr(x), _ptr(y)
+    op.x_dtype = op.y_dtype = _TD[x.dtype]
+    op.x, op.y = x.ptr, y.ptr
     return op
 
 
 def run_op(op, device):
     """Runs one op immediately on the current stream of `device` (tests / debugging)."""
-    idx = device.index if device.index is not None else torch.cuda.current_device()
+    idx = _index(device)
     with torch.cuda.device(idx):
         _C.check(_C.lib().tdet_op_run(ctypes.byref(op), idx, _stream_ptr(device)))
 
 
 def debug_im2col_tile(op, m0, r, s, kc, device):
-    idx = device.index if device.index is not None else torch.cuda.current_device()
+    idx = _index(device)
     out = torch.empty((128, 64), dtype=torch.bfloat16, device=device)
     with torch.cuda.device(idx):
         _C.check(_C.lib().tdet_debug_im2col_tile(ctypes.byref(op), m0, r, s, kc, out.data_ptr(), idx,
@@ -191,37 +258,40 @@ class Plan:
 
     `keepalive` holds every tensor the ops point at (packed weights, folded BN vectors, workspace
     activations) so the device memory outlives the plan.  `ext` are the tensors whose pointers may be
-    re-bound per run (network inputs and returned outputs)."""
+    re-bound per run (network inputs and returned outputs).  `meta` is the plan's ``MetaArena``."""
 
-    def __init__(self, ops, ext, keepalive, device):
+    def __init__(self, ops, ext, keepalive, device, meta=None):
         self.device = device
-        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        self.index = _index(device)
         self.keepalive = keepalive
+        self.meta = meta
         self.n_ext = len(ext)
         arr = (_C.TdetOp * len(ops))(*ops)
         ext_arr = (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.index):
-            _C.check(_C.lib().tdet_plan_create(ctypes.byref(handle), arr, len(ops), ext_arr,
-                                               self.n_ext, self.index))
+            _C.check(_C.lib().tdet_plan_create(
+                ctypes.byref(handle), arr, len(ops), ext_arr, self.n_ext,
+                meta.tensor.data_ptr() if meta is not None else None,
+                meta.count if meta is not None else 0, self.index))
         self._handle = handle
         self.num_launches = _C.lib().tdet_plan_num_launches(handle)
         self.flops = _C.lib().tdet_plan_flops(handle)
 
-    def run(self, ext):
+    def _ext_array(self, ext):
         assert len(ext) == self.n_ext
-        ext_arr = (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
+        return (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
+
+    def run(self, ext):
         with torch.cuda.device(self.index):
-            _C.check(_C.lib().tdet_plan_run(self._handle, ext_arr, self.n_ext,
+            _C.check(_C.lib().tdet_plan_run(self._handle, self._ext_array(ext), self.n_ext,
                                             _stream_ptr(self.device)))
 
     def run_timed(self, ext):
         """Per-launch device milliseconds (CUDA events between launches); measurement only."""
-        self.run(ext)
-        ext_arr = (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
         ms = (ctypes.c_float * self.num_launches)()
         with torch.cuda.device(self.index):
-            _C.check(_C.lib().tdet_plan_run_timed(self._handle, ext_arr, self.n_ext,
+            _C.check(_C.lib().tdet_plan_run_timed(self._handle, self._ext_array(ext), self.n_ext,
                                                   _stream_ptr(self.device), ms))
         return list(ms)
 
@@ -230,7 +300,7 @@ class Plan:
         for i in range(self.num_launches):
             info = _C.TdetLaunchInfo()
             _C.check(_C.lib().tdet_plan_launch_info(self._handle, i, ctypes.byref(info)))
-            out.append({f: getattr(info, f) for f, _ in _C.TdetLaunchInfo._fields_ if f != "reserved"})
+            out.append({f: getattr(info, f) for f, _ in _C.TdetLaunchInfo._fields_})
         return out
 
     def __del__(self):

@@ -16,6 +16,7 @@ Unsupported on this path -> ``NotImplementedError``: ``use_gn=True``, batch-stat
 (a BN child in training mode), CPU tensors.  There is no fallback.
 """
 import logging
+import os
 
 import torch
 import torch.nn as nn
@@ -205,45 +206,61 @@ class ResNet(nn.Module):
             tuple((b.data_ptr(), b._version) for b in self.buffers())
 
     def _get_operands(self, device):
-        """Packed bf16 weights + folded BN vectors; rebuilt whenever a parameter/buffer changes."""
+        """Lazy cache of derived operands (packed weights per format, folded BN vectors, bound
+        constants); dropped together with all plans whenever a parameter or buffer changes."""
         key = self._param_key(device)
-        if self._operands is not None and key == self._operand_key:
-            return self._operands
-        ops = {"stem_w": engine.pack_stem_weight(self.conv1.weight),
-               "stem_bn": engine.fold_bn(getattr(self, self.norm_name))}
-        for lname in self.res_layers:
-            for bi, unit in enumerate(getattr(self, lname)):
-                pre = "%s.%d." % (lname, bi)
-                for ci in range(len(unit.kernel_sizes)):
-                    ops[pre + "w%d" % ci] = engine.pack_conv_weight(
-                        getattr(unit, "conv%d" % (ci + 1)).weight)
-                    ops[pre + "bn%d" % ci] = engine.fold_bn(getattr(unit, unit.norm_names[ci]))
-                if unit.downsample is not None:
-                    ops[pre + "wd"] = engine.pack_conv_weight(unit.downsample[0].weight)
-                    ops[pre + "bnd"] = engine.fold_bn(unit.downsample[1])
-        self._operands = ops
-        self._operand_key = key
-        self._plans = {}
-        return ops
+        if self._operands is None or key != self._operand_key:
+            self._operands = _OperandCache()
+            self._operand_key = key
+            self._plans = {}
+        return self._operands
 
-    def _build_plan(self, x, operands):
+    def _build_plan(self, x, cache):
+        """Compiles the topology for one input geometry into tdet_ops.
+
+        Internal activations are fp16 significands with a per-tensor power-of-two exponent chosen on
+        the device (TDET_FLAG_SCALED_OUT); returned stage outputs are plain bf16.  tcgen05 needs both
+        MMA operands in one format, so each conv's weights are packed in its input's format."""
         n, _, h, w = x.shape
         dev = x.device
-        keep = [operands]
+        internal = INTERNAL_DTYPE
+        scaled = internal == torch.float16
         ops = []
         pool = _BufferPool(dev)
+        n_meta = 4 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)
+        meta = engine.MetaArena(n_meta, dev)
+
+        def new_act(shape, dtype):
+            return engine.Act(pool.get(shape), shape, dtype, meta.new())
+
+        def conv(name, module, bn, src, dst, residual=None, relu=True):
+            k = module.kernel_size[0]
+            wgt = cache.get((name, "w", src.dtype), lambda: engine.pack_conv_weight(module.weight, src.dtype))
+            sc, sh = cache.get((name, "bn"), lambda: engine.fold_bn(bn))
+            is_scaled = scaled and dst.dtype == torch.float16
+            consts = cache.get((name, "consts", src.dtype),
+                               lambda: engine.bound_consts(wgt, sc, sh)) if is_scaled else None
+            ops.append(engine.op_conv(src, wgt, dst, k, k, module.stride[0], module.padding[0],
+                                      module.dilation[0], scale=sc, shift=sh, residual=residual,
+                                      relu=relu, consts=consts, scaled_out=is_scaled))
+
         ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
         staged = pool.get((n, 2 * ho + 6, 2 * wo + 16, 4))
-        ops.append(engine.op_prep(x, staged, ho, wo))
-        stem_out = pool.get((n, ho, wo, 64))
-        sc, sh = operands["stem_bn"]
-        ops.append(engine.op_stem(n, h, w, staged, operands["stem_w"], stem_out, sc, sh))
+        staged_meta = meta.new()
+        ops.append(engine.op_prep(x, staged, ho, wo, y_meta=staged_meta))
+        stem_out = new_act((n, ho, wo, 64), internal)
+        stem_w = cache.get(("conv1", "w"), lambda: engine.pack_stem_weight(self.conv1.weight))
+        sc, sh = cache.get(("conv1", "bn"), lambda: engine.fold_bn(getattr(self, self.norm_name)))
+        stem_consts = cache.get(("conv1", "consts"),
+                                lambda: engine.bound_consts(stem_w, sc, sh)) if scaled else None
+        ops.append(engine.op_stem(n, h, w, staged, stem_w, stem_out, sc, sh, x_meta=staged_meta,
+                                  consts=stem_consts, scaled_out=scaled))
         pool.release(staged)
         hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
-        cur = pool.get((n, hq, wq, 64))
-        ops.append(engine.op_maxpool(n, ho, wo, 64, stem_out, cur))
-        pool.release(stem_out)
-        cur_shape = (n, hq, wq, 64)
+        # max-pool commutes with the (positive) per-tensor scale: metadata passes through
+        cur = engine.Act(pool.get((n, hq, wq, 64)), (n, hq, wq, 64), internal, stem_out.meta)
+        ops.append(engine.op_maxpool(stem_out, cur))
+        pool.release(stem_out.buf)
         outs = []
         for li, lname in enumerate(self.res_layers):
             stage = getattr(self, lname)
@@ -251,60 +268,55 @@ class ResNet(nn.Module):
             for bi, unit in enumerate(stage):
                 pre = "%s.%d." % (lname, bi)
                 last = bi == len(stage) - 1
-                nb, hb, wb, cb = cur_shape
-                stride = unit.stride
-                dil = unit.dilation
-                hn, wn = engine.conv_out(hb, 3, stride, dil, dil), engine.conv_out(wb, 3, stride, dil, dil)
+                nb, hb, wb, _ = cur.shape
+                hn = engine.conv_out(hb, 3, unit.stride, unit.dilation, unit.dilation)
+                wn = engine.conv_out(wb, 3, unit.stride, unit.dilation, unit.dilation)
                 residual = cur
-                shortcut_buf = None
+                shortcut = None
                 if unit.downsample is not None:
                     cd = unit.downsample[0].out_channels
-                    shortcut_buf = pool.get((nb, hn, wn, cd))
-                    s_, h_ = operands[pre + "bnd"]
-                    ops.append(engine.op_conv(cur_shape, cur, operands[pre + "wd"], shortcut_buf, 1, 1,
-                                              stride, 0, 1, scale=s_, shift=h_))
-                    residual = shortcut_buf
+                    shortcut = new_act((nb, hn, wn, cd), internal)
+                    conv(pre + "downsample", unit.downsample[0], unit.downsample[1], cur, shortcut,
+                         relu=False)
+                    residual = shortcut
                 nconv = len(unit.kernel_sizes)
-                t_in, t_shape = cur, cur_shape
+                src = cur
                 temps = []
                 for ci, k in enumerate(unit.kernel_sizes):
-                    conv = getattr(unit, "conv%d" % (ci + 1))
-                    cst, cdl = conv.stride[0], conv.dilation[0]
-                    pad = conv.padding[0]
-                    co = conv.out_channels
-                    oh = engine.conv_out(t_shape[1], k, cst, pad, cdl)
-                    ow = engine.conv_out(t_shape[2], k, cst, pad, cdl)
+                    module = getattr(unit, "conv%d" % (ci + 1))
+                    oh = engine.conv_out(src.shape[1], k, module.stride[0], module.padding[0], module.dilation[0])
+                    ow = engine.conv_out(src.shape[2], k, module.stride[0], module.padding[0], module.dilation[0])
+                    shape = (nb, oh, ow, module.out_channels)
                     final = ci == nconv - 1
                     if final and last and is_out:
-                        dst = engine.nhwc_empty(nb, oh, ow, co, dev)  # external output
+                        # returned feature map: plain bf16, bound to the caller's tensor at run time
+                        dst = engine.Act(engine.nhwc_empty(nb, oh, ow, module.out_channels, dev), shape,
+                                         torch.bfloat16, meta.new())
                         outs.append(dst)
                     else:
-                        dst = pool.get((nb, oh, ow, co))
+                        dst = new_act(shape, internal)
                         if not final:
                             temps.append(dst)
-                    s_, h_ = operands[pre + "bn%d" % ci]
-                    ops.append(engine.op_conv(t_shape, t_in, operands[pre + "w%d" % ci], dst, k, k, cst,
-                                              pad, cdl, scale=s_, shift=h_,
-                                              residual=residual if final else None, relu=True))
-                    t_in, t_shape = dst, (nb, oh, ow, co)
+                    conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src, dst,
+                         residual=residual if final else None)
+                    src = dst
                 for t in temps:
-                    pool.release(t)
-                if shortcut_buf is not None:
-                    pool.release(shortcut_buf)
+                    pool.release(t.buf)
+                if shortcut is not None:
+                    pool.release(shortcut.buf)
                 if not any(cur is o for o in outs):
-                    pool.release(cur)
-                cur, cur_shape = t_in, t_shape
-        keep.append(pool.all_buffers)
-        plan = engine.Plan(ops, [x] + outs, keep, dev)
-        return plan, [tuple(o.shape) for o in outs]
+                    pool.release(cur.buf)
+                cur = src
+        plan = engine.Plan(ops, [x] + [o.buf for o in outs], [cache, pool.all_buffers], dev, meta=meta)
+        return plan, [tuple(o.buf.shape) for o in outs]
 
     def forward(self, x):
         self._check_supported(x)
-        operands = self._get_operands(x.device)
-        key = (tuple(x.shape), x.dtype, tuple(x.stride()), x.device)
+        cache = self._get_operands(x.device)
+        key = (tuple(x.shape), x.dtype, tuple(x.stride()), x.device, INTERNAL_DTYPE)
         entry = self._plans.get(key)
         if entry is None:
-            entry = self._build_plan(x, operands)
+            entry = self._build_plan(x, cache)
             self._plans[key] = entry
         plan, out_shapes = entry
         outs = [torch.empty(s, dtype=torch.bfloat16, device=x.device,
@@ -314,6 +326,23 @@ class ResNet(nn.Module):
         if x.dtype == torch.float32:
             outs = [_upcast(o) for o in outs]
         return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+# Storage format of the backbone's internal activations: float16 = fp16 significand + per-tensor
+# power-of-two exponent (default; ~8x lower rounding error than bf16 at the same tensor-core rate),
+# bfloat16 = plain bf16 everywhere (TDET_INTERNAL_DTYPE=bf16).
+INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16").lower() in (
+    "bf16", "bfloat16") else torch.float16
+
+
+class _OperandCache(object):
+    def __init__(self):
+        self.store = {}
+
+    def get(self, key, make):
+        if key not in self.store:
+            self.store[key] = make()
+        return self.store[key]
 
 
 def _upcast(t):
@@ -334,6 +363,7 @@ class _BufferPool(object):
         self.all_buffers = []
 
     def get(self, shape):
+        """16-bit buffer with at least prod(shape) elements (dtype-agnostic: raw storage)."""
         numel = 1
         for s in shape:
             numel *= s

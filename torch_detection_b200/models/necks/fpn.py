@@ -104,46 +104,46 @@ class FPN(nn.Module):
                         "non-singleton dimension %d" % (a, b, dim))
         co = self.out_channels
         ops = []
+        srcs = [engine.act_of(t) for t in used]
         lats = [None] * nl
         for j in range(nl - 1, -1, -1):
             nb, h, w, c = shapes[j]
-            lats[j] = torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev)
-            coarse = lats[j + 1] if j < nl - 1 else None
-            chw = (shapes[j + 1][1], shapes[j + 1][2]) if j < nl - 1 else (0, 0)
-            ops.append(engine.op_conv(shapes[j], used[j], operands["lat%d.w" % j], lats[j], 1, 1, 1, 0,
-                                      1, shift=operands["lat%d.b" % j], coarse=coarse, coarse_hw=chw))
+            lats[j] = engine.Act(torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev),
+                                 (nb, h, w, co), torch.bfloat16)
+            ops.append(engine.op_conv(srcs[j], operands["lat%d.w" % j], lats[j], 1, 1, 1, 0, 1,
+                                      shift=operands["lat%d.b" % j],
+                                      coarse=lats[j + 1] if j < nl - 1 else None))
         outs = []
         for j in range(nl):
             nb, h, w, _ = shapes[j]
-            o = engine.nhwc_empty(nb, h, w, co, dev)
-            ops.append(engine.op_conv((nb, h, w, co), lats[j], operands["out%d.w" % j], o, 3, 3, 1, 1,
-                                      1, shift=operands["out%d.b" % j]))
+            o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
+            ops.append(engine.op_conv(lats[j], operands["out%d.w" % j], o, 3, 3, 1, 1, 1,
+                                      shift=operands["out%d.b" % j]))
             outs.append(o)
         if self.num_outs > nl:
             if not self.add_extra_convs:
                 for _ in range(self.num_outs - nl):
-                    nb, c_, h, w = outs[-1].shape
-                    o = engine.nhwc_empty(nb, (h - 1) // 2 + 1, (w - 1) // 2 + 1, co, dev)
-                    ops.append(engine.op_subsample(nb, h, w, co, outs[-1], o))
+                    nb, h, w, _ = outs[-1].shape
+                    o = engine.act_of(engine.nhwc_empty(nb, (h - 1) // 2 + 1, (w - 1) // 2 + 1, co, dev))
+                    ops.append(engine.op_subsample(outs[-1], o))
                     outs.append(o)
             else:
-                src = feats[self.backbone_end_level - 1]
-                src_shape = (src.shape[0], src.shape[2], src.shape[3], src.shape[1])
+                src = engine.act_of(feats[self.backbone_end_level - 1])
                 for j in range(nl, self.num_outs):
-                    nb, h, w, c = src_shape
+                    nb, h, w, c = src.shape
                     oh, ow = engine.conv_out(h, 3, 2, 1), engine.conv_out(w, 3, 2, 1)
-                    o = engine.nhwc_empty(nb, oh, ow, co, dev)
+                    o = engine.act_of(engine.nhwc_empty(nb, oh, ow, co, dev))
                     # the reference applies ReLU *in place* to P_j before the next extra conv
                     # (fpn.py:123-124), so every extra level that feeds another one is returned
                     # post-ReLU: fold that ReLU into the producing conv's epilogue.
-                    ops.append(engine.op_conv(src_shape, src, operands["out%d.w" % j], o, 3, 3, 2, 1,
-                                              1, shift=operands["out%d.b" % j],
+                    ops.append(engine.op_conv(src, operands["out%d.w" % j], o, 3, 3, 2, 1, 1,
+                                              shift=operands["out%d.b" % j],
                                               relu=(j < self.num_outs - 1)))
                     outs.append(o)
-                    src, src_shape = o, (nb, oh, ow, co)
-        ext = list(feats) + outs
-        plan = engine.Plan(ops, ext, [operands, lats], dev)
-        return plan, [tuple(o.shape) for o in outs]
+                    src = o
+        ext = list(feats) + [o.buf for o in outs]
+        plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats]], dev)
+        return plan, [tuple(o.buf.shape) for o in outs]
 
     @staticmethod
     def _as_bf16_nhwc(t):
