@@ -9,14 +9,17 @@
 //   A_STEM   : 7x7/2 stem on the padded NHWC4 staging -> 5D tiled map with overlapping windows
 // W is pre-packed [Cout][kh][kw][Cin], i.e. K-major rows, loaded by a 2D tiled map.
 //
-// Persistent, warp-specialised CTA (224 threads), every global<->shared transfer is asynchronous:
+// Persistent, warp-specialised CTA (352 threads), every global<->shared transfer is asynchronous:
 //   warp 0      TMA producer for A/B     (full/empty mbarrier ring, STAGES deep)
 //   warp 1      tcgen05.mma issuer       (lane 0 issues; accumulators double-buffered in TMEM)
-//   warps 2..5  epilogue                 (tcgen05.ld 32x32b -> registers -> fp32 math -> 128B-swizzled
-//                                         staging slab -> TMA store), overlapped with the next tile's
-//                                         main loop through tmem_full/empty
-//   warp 6      TMA producer for the residual operand (64-column slabs, RES_SLABS-deep ring) so the
+//   warp 2      TMA producer for the residual operand (64-column slabs, RES_SLABS-deep ring) so the
 //                                         residual of tile i+1 streams in while tile i is finished
+//   warps 3..10 epilogue                 (tcgen05.ld 32x32b -> registers -> fp32 math -> 128B-swizzled
+//                                         staging slab -> TMA store), overlapped with the next tile's
+//                                         main loop through tmem_full/empty.  A warp may only read
+//                                         TMEM lanes 32*(warp%4)..+31, so the 8 warps form two groups
+//                                         of four; group g converts the g-th 32-column half of every
+//                                         64-column slab (the epilogue is FMA/convert-issue bound).
 //
 // Numerics: every stored activation tensor may carry a per-tensor power-of-two exponent
 // (TensorMeta::e, value = stored * 2^e) and its true |max| (TensorMeta::amax_bits).  A kernel picks
@@ -34,7 +37,8 @@ namespace tdet {
 constexpr int kBM = 128;         // UMMA M (cta_group::1)
 constexpr int kBK = 64;          // 16-bit elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
-constexpr int kGemmThreads = 224;
+constexpr int kGemmThreads = 352;
+constexpr int kEpiThreads = 256;         // 8 epilogue warps: two warps per TMEM lane quadrant
 constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
 constexpr int kOutSlabs = 2;             // staging double buffer for TMA stores
@@ -155,7 +159,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
     }
     for (int s = 0; s < kRS; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -163,7 +167,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == 3) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
@@ -260,7 +264,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ------------------------------------------------------------------ TMA producer (residual)
     if (RES_SLABS > 0 && p.has_res) {
       int rs = 0;
@@ -281,10 +285,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 3..10)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == TMEM lane == staging row
-    const int epi_tid = threadIdx.x - 64;  // 0..127
+    const int epi_tid = threadIdx.x - 96;  // 0..255
+    const int half = (warp - 3) >> 2;      // which 32-column half of each slab this warp converts
     const bool issuer = epi_tid == 0;      // issues TMA stores, frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
     const bool has_coarse = p.coarse != nullptr;
@@ -322,12 +327,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BN;
       if (n_tile != cur_n_tile) {
-        named_bar_sync(1, 128);
-        for (int i = epi_tid; i < BN; i += 128) {
+        named_bar_sync(1, kEpiThreads);
+        for (int i = epi_tid; i < BN; i += kEpiThreads) {
           s_scale[i] = (p.scale ? __ldg(p.scale + n0 + i) : 1.0f) * mul_in;
           s_shift[i] = (p.shift ? __ldg(p.shift + n0 + i) : 0.0f) * mul_shift;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         cur_n_tile = n_tile;
       }
       // output pixel of this thread's row
@@ -374,11 +379,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // the staging buffer `ob` was last read by the TMA store issued two slabs ago
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         if (has_res) mbar_wait(rfull_bar(rs), rphase);
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         const uint32_t out_row = smem_out + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_addr + slab * 64 + half * 32, v);
           uint4 rco[4];
@@ -462,7 +466,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         fence_proxy_async_smem();  // staging writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (issuer) {
           const uint32_t src = smem_out + ob * kSlabBytes;
           if (p.a_mode == A_STEM) {
@@ -500,7 +504,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 3) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }

@@ -189,8 +189,8 @@ int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
 int launch_gemm(const Launch& l, cudaStream_t st) {
   const int v = l.bn * 10000 + l.stages * 100 + l.res_slabs;
   switch (v) {
-    case 64 * 10000 + 402: return launch_gemm_t<64, 4, 2>(l.gp, l.grid, st);
-    case 128 * 10000 + 404: return launch_gemm_t<128, 4, 4>(l.gp, l.grid, st);
+    case 64 * 10000 + 602: return launch_gemm_t<64, 6, 2>(l.gp, l.grid, st);
+    case 128 * 10000 + 502: return launch_gemm_t<128, 5, 2>(l.gp, l.grid, st);
     case 256 * 10000 + 400: return launch_gemm_t<256, 4, 0>(l.gp, l.grid, st);
     case 256 * 10000 + 303: return launch_gemm_t<256, 3, 3>(l.gp, l.grid, st);
   }
@@ -275,11 +275,11 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     l.res_slabs = o.residual ? 3 : 0;
   } else if (o.cout % 128 == 0) {
     l.bn = 128;
-    l.stages = 4;
-    l.res_slabs = 4;
+    l.stages = 5;
+    l.res_slabs = 2;
   } else {
     l.bn = 64;
-    l.stages = 4;
+    l.stages = 6;
     l.res_slabs = 2;
   }
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
@@ -370,7 +370,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   gp.M = gp.num_m_tiles * kBM;
   gp.ab_fp16 = 0;
   l.bn = 64;
-  l.stages = 4;
+  l.stages = 6;
   l.res_slabs = 2;
   rc = encode_2d(&gp.tmap_b, o.wgt, TDET_BF16, 448, 64, 64, "stem weights");
   if (rc) return rc;
