@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 2
+#define TDET_ABI_VERSION 3
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -171,14 +171,16 @@ int tdet_op_run(const tdet_op* op, int device, void* stream);
 
 /*
  * A plan is a validated op sequence with pre-built TMA descriptors and launch configurations.
- * ext_ptrs lists the n_ext caller pointers that may change between runs (network input, returned
- * outputs); every op field equal to ext_ptrs[i] is re-bound to the i-th pointer given to
- * tdet_plan_run.  Pass n_ext = 0 for a fully static plan.
+ * ext_ptrs/ext_bytes list the n_ext caller tensors (base pointer, size in bytes) that may move
+ * between runs (network input, returned outputs); every op field pointing into
+ * [ext_ptrs[i], ext_ptrs[i] + ext_bytes[i]) is re-bound, keeping its byte offset, to the i-th pointer
+ * given to tdet_plan_run.  Pass n_ext = 0 for a fully static plan.
  * meta_arena/meta_count (optional): the contiguous tdet_tensor_meta array the ops' *_meta pointers
  * live in; it is zeroed (one cudaMemsetAsync) at the start of every run.
  */
 int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void* const* ext_ptrs,
-                     int n_ext, tdet_tensor_meta* meta_arena, int meta_count, int device);
+                     const size_t* ext_bytes, int n_ext, tdet_tensor_meta* meta_arena,
+                     int meta_count, int device);
 int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream);
 /* Same as tdet_plan_run with unchanged external pointers, but brackets every kernel launch with
  * CUDA events on `stream` and returns the per-launch device time in milliseconds

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # tdet_status
 OK = 0
@@ -93,7 +93,8 @@ def lib():
     L.tdet_conv_bound_consts.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
     L.tdet_op_run.argtypes = [ctypes.POINTER(TdetOp), i32, vp]
     L.tdet_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(TdetOp), i32,
-                                   ctypes.POINTER(vp), i32, vp, i32, i32]
+                                   ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, vp, i32,
+                                   i32]
     L.tdet_plan_run.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
     L.tdet_plan_run_timed.argtypes = [vp, ctypes.POINTER(vp), i32, vp, ctypes.POINTER(f32)]
     L.tdet_plan_launch_info.argtypes = [vp, i32, ctypes.POINTER(TdetLaunchInfo)]

@@ -117,6 +117,7 @@ struct Launch {
   int kind = 0;  // tdet_op_kind
   tdet_op op{};
   int ext_slot[5] = {-1, -1, -1, -1, -1};  // x, wgt, y, residual, coarse
+  long long ext_offset[5] = {0, 0, 0, 0, 0};  // byte offset of the field inside its external tensor
   bool has_ext = false;
   // conv / stem
   ConvGemmParams gp{};
@@ -544,8 +545,10 @@ int plan_rebind(tdet_plan* plan, const void* const* ext_ptrs, int n_ext) {
     bool touched = false;
     for (int f = 0; f < 5; ++f) {
       const int s = l.ext_slot[f];
-      if (s >= 0 && get_field(l.op, f) != ext_ptrs[s]) {
-        set_field(l.op, f, ext_ptrs[s]);
+      if (s < 0) continue;
+      const void* want = static_cast<const char*>(ext_ptrs[s]) + l.ext_offset[f];
+      if (get_field(l.op, f) != want) {
+        set_field(l.op, f, want);
         touched = true;
       }
     }
@@ -643,8 +646,10 @@ int tdet_op_run(const tdet_op* op, int device, void* stream) {
 }
 
 int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void* const* ext_ptrs,
-                     int n_ext, tdet_tensor_meta* meta_arena, int meta_count, int device) {
-  if (!out || !ops || n_ops <= 0 || n_ext < 0 || (n_ext > 0 && !ext_ptrs) || meta_count < 0)
+                     const size_t* ext_bytes, int n_ext, tdet_tensor_meta* meta_arena,
+                     int meta_count, int device) {
+  if (!out || !ops || n_ops <= 0 || n_ext < 0 || (n_ext > 0 && (!ext_ptrs || !ext_bytes)) ||
+      meta_count < 0)
     return fail(TDET_ERR_INVALID_ARGUMENT, "plan_create: bad arguments");
   DeviceInfo* di = nullptr;
   int rc = require_sm100(device, &di);
@@ -663,12 +668,18 @@ int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void*
   for (int i = 0; i < n_ops; ++i) {
     Launch& l = plan->launches[i];
     l.op = ops[i];
-    for (int f = 0; f < 5; ++f)
-      for (int e = 0; e < n_ext; ++e)
-        if (get_field(l.op, f) && get_field(l.op, f) == ext_ptrs[e]) {
+    for (int f = 0; f < 5; ++f) {
+      const char* fp = static_cast<const char*>(get_field(l.op, f));
+      if (!fp) continue;
+      for (int e = 0; e < n_ext; ++e) {
+        const char* base = static_cast<const char*>(ext_ptrs[e]);
+        if (fp >= base && fp < base + ext_bytes[e]) {
           l.ext_slot[f] = e;
+          l.ext_offset[f] = fp - base;
           l.has_ext = true;
         }
+      }
+    }
     rc = build_launch(l, *di);
     if (rc) {
       char msg[400];

@@ -35,17 +35,18 @@ def conv_out(v, k, s, p, d=1):
 class Act(object):
     """Handle of a dense NHWC 16-bit activation tensor: device buffer, logical (n, h, w, c) shape,
     storage dtype and the device address of its ``tdet_tensor_meta`` (None = plain values)."""
-    __slots__ = ("buf", "shape", "dtype", "meta")
+    __slots__ = ("buf", "shape", "dtype", "meta", "offset")
 
-    def __init__(self, buf, shape, dtype=None, meta=None):
+    def __init__(self, buf, shape, dtype=None, meta=None, offset=0):
         self.buf = buf
         self.shape = tuple(shape)
         self.dtype = dtype if dtype is not None else buf.dtype
         self.meta = meta
+        self.offset = offset  # in elements, from the start of `buf`
 
     @property
     def ptr(self):
-        return self.buf.data_ptr()
+        return self.buf.data_ptr() + 2 * self.offset
 
 
 def act_of(t, meta=None):
@@ -268,10 +269,11 @@ class Plan:
         self.n_ext = len(ext)
         arr = (_C.TdetOp * len(ops))(*ops)
         ext_arr = (ctypes.c_void_p * max(1, self.n_ext))(*[t.data_ptr() for t in ext])
+        ext_bytes = (ctypes.c_size_t * max(1, self.n_ext))(*[t.numel() * t.element_size() for t in ext])
         handle = ctypes.c_void_p()
         with torch.cuda.device(self.index):
             _C.check(_C.lib().tdet_plan_create(
-                ctypes.byref(handle), arr, len(ops), ext_arr, self.n_ext,
+                ctypes.byref(handle), arr, len(ops), ext_arr, ext_bytes, self.n_ext,
                 meta.tensor.data_ptr() if meta is not None else None,
                 meta.count if meta is not None else 0, self.index))
         self._handle = handle

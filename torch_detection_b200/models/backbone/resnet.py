@@ -215,19 +215,38 @@ class ResNet(nn.Module):
             self._plans = {}
         return self._operands
 
+    def _segments(self, n):
+        """[(stage indices, images per chunk)]: the stem travels with the first segment.  Early stages
+        are HBM-bound layer by layer; running them a few images at a time keeps each block's tensors
+        in the 126 MB L2 between consecutive kernels (DESIGN.md "L2-resident scheduling")."""
+        nst = len(self.res_layers)
+        spec = [int(v) for v in os.environ.get("TDET_CHUNKS", DEFAULT_CHUNKS).split(",") if v.strip()]
+        segs = []
+        for i in range(nst):
+            c = spec[i] if i < len(spec) and spec[i] > 0 else n
+            c = min(c, n)
+            if segs and segs[-1][1] == c:
+                segs[-1][0].append(i)
+            else:
+                segs.append(([i], c))
+        return segs
+
     def _build_plan(self, x, cache):
         """Compiles the topology for one input geometry into tdet_ops.
 
         Internal activations are fp16 significands with a per-tensor power-of-two exponent chosen on
-        the device (TDET_FLAG_SCALED_OUT); returned stage outputs are plain bf16.  tcgen05 needs both
-        MMA operands in one format, so each conv's weights are packed in its input's format."""
+        the device (TDET_FLAG_SCALED_OUT); stage outputs are plain bf16 (they are what the module
+        returns and what crosses chunk boundaries).  tcgen05 needs both MMA operands in one format,
+        so each conv's weights are packed in its input's format."""
         n, _, h, w = x.shape
         dev = x.device
         internal = INTERNAL_DTYPE
         scaled = internal == torch.float16
         ops = []
         pool = _BufferPool(dev)
-        n_meta = 4 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)
+        segs = self._segments(n)
+        max_chunks = max((n + c - 1) // c for _, c in segs)
+        n_meta = 8 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
         meta = engine.MetaArena(n_meta, dev)
 
         def new_act(shape, dtype):
@@ -244,71 +263,103 @@ class ResNet(nn.Module):
                                       module.dilation[0], scale=sc, shift=sh, residual=residual,
                                       relu=relu, consts=consts, scaled_out=is_scaled))
 
+        # geometry of every stage output, and the full-batch bf16 tensors that hold them
         ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
-        staged = pool.get((n, 2 * ho + 6, 2 * wo + 16, 4))
-        staged_meta = meta.new()
-        ops.append(engine.op_prep(x, staged, ho, wo, y_meta=staged_meta))
-        stem_out = new_act((n, ho, wo, 64), internal)
-        stem_w = cache.get(("conv1", "w"), lambda: engine.pack_stem_weight(self.conv1.weight))
-        sc, sh = cache.get(("conv1", "bn"), lambda: engine.fold_bn(getattr(self, self.norm_name)))
-        stem_consts = cache.get(("conv1", "consts"),
-                                lambda: engine.bound_consts(stem_w, sc, sh)) if scaled else None
-        ops.append(engine.op_stem(n, h, w, staged, stem_w, stem_out, sc, sh, x_meta=staged_meta,
-                                  consts=stem_consts, scaled_out=scaled))
-        pool.release(staged)
         hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
-        # max-pool commutes with the (positive) per-tensor scale: metadata passes through
-        cur = engine.Act(pool.get((n, hq, wq, 64)), (n, hq, wq, 64), internal, stem_out.meta)
-        ops.append(engine.op_maxpool(stem_out, cur))
-        pool.release(stem_out.buf)
-        outs = []
-        for li, lname in enumerate(self.res_layers):
+        geo = []
+        hh, ww = hq, wq
+        for lname in self.res_layers:
             stage = getattr(self, lname)
-            is_out = li in self.out_indices
-            for bi, unit in enumerate(stage):
-                pre = "%s.%d." % (lname, bi)
-                last = bi == len(stage) - 1
-                nb, hb, wb, _ = cur.shape
-                hn = engine.conv_out(hb, 3, unit.stride, unit.dilation, unit.dilation)
-                wn = engine.conv_out(wb, 3, unit.stride, unit.dilation, unit.dilation)
-                residual = cur
-                shortcut = None
-                if unit.downsample is not None:
-                    cd = unit.downsample[0].out_channels
-                    shortcut = new_act((nb, hn, wn, cd), internal)
-                    conv(pre + "downsample", unit.downsample[0], unit.downsample[1], cur, shortcut,
-                         relu=False)
-                    residual = shortcut
-                nconv = len(unit.kernel_sizes)
-                src = cur
-                temps = []
-                for ci, k in enumerate(unit.kernel_sizes):
-                    module = getattr(unit, "conv%d" % (ci + 1))
-                    oh = engine.conv_out(src.shape[1], k, module.stride[0], module.padding[0], module.dilation[0])
-                    ow = engine.conv_out(src.shape[2], k, module.stride[0], module.padding[0], module.dilation[0])
-                    shape = (nb, oh, ow, module.out_channels)
-                    final = ci == nconv - 1
-                    if final and last and is_out:
-                        # returned feature map: plain bf16, bound to the caller's tensor at run time
-                        dst = engine.Act(engine.nhwc_empty(nb, oh, ow, module.out_channels, dev), shape,
-                                         torch.bfloat16, meta.new())
-                        outs.append(dst)
-                    else:
-                        dst = new_act(shape, internal)
-                        if not final:
-                            temps.append(dst)
-                    conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src, dst,
-                         residual=residual if final else None)
-                    src = dst
-                for t in temps:
-                    pool.release(t.buf)
-                if shortcut is not None:
-                    pool.release(shortcut.buf)
-                if not any(cur is o for o in outs):
-                    pool.release(cur.buf)
-                cur = src
-        plan = engine.Plan(ops, [x] + [o.buf for o in outs], [cache, pool.all_buffers], dev, meta=meta)
-        return plan, [tuple(o.buf.shape) for o in outs]
+            for unit in stage:
+                hh = engine.conv_out(hh, 3, unit.stride, unit.dilation, unit.dilation)
+                ww = engine.conv_out(ww, 3, unit.stride, unit.dilation, unit.dilation)
+            last = stage[len(stage) - 1]
+            cout = getattr(last, "conv%d" % len(last.kernel_sizes)).out_channels
+            geo.append((hh, ww, cout))
+        outs = []
+        boundary = []
+        for li, (sh_, sw_, sc_) in enumerate(geo):
+            if li in self.out_indices:
+                t = engine.nhwc_empty(n, sh_, sw_, sc_, dev)  # placeholder, re-bound at run time
+                outs.append(t)
+            else:
+                t = pool.get((n, sh_, sw_, sc_))
+            boundary.append((t, meta.new()))
+
+        def boundary_act(li, i0, cn):
+            t, m = boundary[li]
+            sh_, sw_, sc_ = geo[li]
+            return engine.Act(t, (cn, sh_, sw_, sc_), torch.bfloat16, m, offset=i0 * sh_ * sw_ * sc_)
+
+        for stages, chunk in segs:
+            for i0 in range(0, n, chunk):
+                cn = min(chunk, n - i0)
+                if stages[0] == 0:
+                    staged = pool.get((cn, 2 * ho + 6, 2 * wo + 16, 4))
+                    staged_meta = meta.new()
+                    ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta))
+                    stem_out = new_act((cn, ho, wo, 64), internal)
+                    stem_w = cache.get(("conv1", "w"), lambda: engine.pack_stem_weight(self.conv1.weight))
+                    sc, sh = cache.get(("conv1", "bn"), lambda: engine.fold_bn(getattr(self, self.norm_name)))
+                    stem_consts = cache.get(("conv1", "consts"),
+                                            lambda: engine.bound_consts(stem_w, sc, sh)) if scaled else None
+                    ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh,
+                                              x_meta=staged_meta, consts=stem_consts, scaled_out=scaled))
+                    pool.release(staged)
+                    # max-pool commutes with the (positive) per-tensor scale: metadata passes through
+                    cur = engine.Act(pool.get((cn, hq, wq, 64)), (cn, hq, wq, 64), internal, stem_out.meta)
+                    ops.append(engine.op_maxpool(stem_out, cur))
+                    pool.release(stem_out.buf)
+                    cur_pooled = True
+                else:
+                    cur = boundary_act(stages[0] - 1, i0, cn)
+                    cur_pooled = False
+                for li in stages:
+                    lname = self.res_layers[li]
+                    stage = getattr(self, lname)
+                    for bi, unit in enumerate(stage):
+                        pre = "%s.%d." % (lname, bi)
+                        last = bi == len(stage) - 1
+                        nb, hb, wb, _ = cur.shape
+                        hn = engine.conv_out(hb, 3, unit.stride, unit.dilation, unit.dilation)
+                        wn = engine.conv_out(wb, 3, unit.stride, unit.dilation, unit.dilation)
+                        residual = cur
+                        shortcut = None
+                        if unit.downsample is not None:
+                            cd = unit.downsample[0].out_channels
+                            shortcut = new_act((nb, hn, wn, cd), internal)
+                            conv(pre + "downsample", unit.downsample[0], unit.downsample[1], cur, shortcut,
+                                 relu=False)
+                            residual = shortcut
+                        nconv = len(unit.kernel_sizes)
+                        src = cur
+                        temps = []
+                        for ci, k in enumerate(unit.kernel_sizes):
+                            module = getattr(unit, "conv%d" % (ci + 1))
+                            oh = engine.conv_out(src.shape[1], k, module.stride[0], module.padding[0],
+                                                 module.dilation[0])
+                            ow = engine.conv_out(src.shape[2], k, module.stride[0], module.padding[0],
+                                                 module.dilation[0])
+                            final = ci == nconv - 1
+                            if final and last:
+                                dst = boundary_act(li, i0, cn)  # stage output: plain bf16
+                            else:
+                                dst = new_act((nb, oh, ow, module.out_channels), internal)
+                                if not final:
+                                    temps.append(dst)
+                            conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src,
+                                 dst, residual=residual if final else None)
+                            src = dst
+                        for t in temps:
+                            pool.release(t.buf)
+                        if shortcut is not None:
+                            pool.release(shortcut.buf)
+                        if cur_pooled:
+                            pool.release(cur.buf)
+                        cur = src
+                        cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
+        plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers], dev, meta=meta)
+        return plan, [tuple(o.shape) for o in outs]
 
     def forward(self, x):
         self._check_supported(x)
@@ -333,6 +384,9 @@ class ResNet(nn.Module):
 # bfloat16 = plain bf16 everywhere (TDET_INTERNAL_DTYPE=bf16).
 INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16").lower() in (
     "bf16", "bfloat16") else torch.float16
+
+# Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
+DEFAULT_CHUNKS = "0"
 
 
 class _OperandCache(object):
