@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 3
+#define TDET_ABI_VERSION 4
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -97,7 +97,7 @@ typedef struct tdet_tensor_meta {
  *
  * TDET_OP_PREP      x: logical (n, 3, h, w) image batch of x_dtype (F32/BF16) with element strides
  *                   x_stride[] = {n, c, h, w} (NCHW-contiguous or channels_last both work)
- *                   y: bf16 [n][hp][wp][4] with hp = 2*ho + 6, wp = 2*wo + 16 (ho/wo = stem output
+ *                   y: bf16 [n][hp][wp][4] with (hp, wp) = tdet_stem_staging_dims(ho, wo) (ho/wo = stem output
  *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
  *                   y_meta (optional): receives the image's |max| (exponent 0).
  * TDET_OP_STEM      x: the PREP output (bf16); wgt: tdet_pack_stem_weight output (bf16 [64][448]);
@@ -149,6 +149,10 @@ const char* tdet_last_error(void);
 /* 0 if `device` is an sm_100 part this build can run on, else TDET_ERR_UNSUPPORTED_DEVICE. */
 int tdet_device_supported(int device);
 
+/* Geometry of the TDET_OP_PREP output for a stem output of ho x wo pixels: hp = 2*ho + 6 rows,
+ * wp = 2*wo + 16 rounded up to a multiple of 16 pixels (the image sits at offset (3,3)). */
+int tdet_stem_staging_dims(int ho, int wo, int* hp, int* wp);
+
 /* ---- operand preparation (run once per weight version) ----------------------------------- */
 /* fp32 OIHW [cout][cin][kh][kw] -> 16-bit [cout][kh][kw][cin] (round-to-nearest-even);
  * dtype = TDET_BF16 or TDET_F16. */
@@ -196,7 +200,7 @@ typedef struct tdet_launch_info {
   int32_t grid;   /* CTAs launched (GEMM kernels) */
   int32_t a_mode; /* 0 tiled, 1 im2col, 2 stem; -1 for non-GEMM kernels */
   int32_t m, n, k;
-  int32_t variant; /* GEMM kernel instantiation: stages * 16 + residual slabs */
+  int32_t variant; /* GEMM kernel instantiation: 4096 * patch-mode + stages * 256 + residual slabs * 16 + resident-B k-blocks */
   double flops;
   double bytes;
 } tdet_launch_info;

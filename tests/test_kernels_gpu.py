@@ -226,7 +226,7 @@ def test_prep_and_stem(cuda_device, shape, dtype):
     scale = (0.5 + torch.rand(64, generator=g)).to(dev)
     shift = (0.3 * torch.randn(64, generator=g)).to(dev)
     ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
-    hp, wp_ = 2 * ho + 6, 2 * wo + 16
+    hp, wp_ = engine.stem_staging_dims(ho, wo)
     staged = torch.empty((n, hp, wp_, 4), dtype=torch.bfloat16, device=dev)
     arena = engine.MetaArena(1, dev)
     engine.run_op(engine.op_prep(x, staged, ho, wo, y_meta=arena.new()), dev)

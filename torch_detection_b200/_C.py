@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # tdet_status
 OK = 0
@@ -64,6 +64,7 @@ class TdetError(RuntimeError):
 
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
+    "tdet_stem_staging_dims",
     "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn", "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_timed",
     "tdet_plan_num_launches", "tdet_plan_launch_info",
@@ -91,6 +92,7 @@ def lib():
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
     L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.tdet_conv_bound_consts.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
+    L.tdet_stem_staging_dims.argtypes = [i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
     L.tdet_op_run.argtypes = [ctypes.POINTER(TdetOp), i32, vp]
     L.tdet_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(TdetOp), i32,
                                    ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, vp, i32,

@@ -37,13 +37,25 @@ namespace tdet {
 constexpr int kBM = 128;         // UMMA M (cta_group::1)
 constexpr int kBK = 64;          // 16-bit elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
-constexpr int kGemmThreads = 352;
+constexpr int kGemmThreads = 384;       // 12 warps; warp 11 is the B producer of the patch mode
 constexpr int kEpiThreads = 256;         // 8 epilogue warps: two warps per TMEM lane quadrant
 constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
 constexpr int kOutSlabs = 2;             // staging double buffer for TMA stores
 
-enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2 };
+enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2, A_STEM2 = 3, A_PATCH = 4 };
+
+// A_PATCH (3x3, stride 1, pad 1, dil 1): an M tile is 8 x 16 output pixels; per 64-channel chunk ONE
+// tiled TMA load deposits the (8+2) x (16+2) pixel halo patch (180 rows of 128 B, SWIZZLE_128B) and the
+// nine filter taps are nine *shifted views* of it: the A descriptor of tap (r,s) starts at patch row
+// r*10+s with 1280 B between 8-row groups.  tcgen05 applies the 128B swizzle as a function of the
+// shared-memory address, so any 128-byte-row start and any group stride address the TMA-written
+// pattern consistently (tools/probe_umma_shift.cu).  A traffic drops from 9x to 1.41x the input.
+constexpr int kPatchBW = 8, kPatchBH = 16;
+constexpr int kPatchPW = kPatchBW + 2, kPatchPH = kPatchBH + 2;
+constexpr int kPatchBytes = kPatchPW * kPatchPH * 128;          // 23040
+constexpr int kPatchStageBytes = (kPatchBytes + 1023) / 1024 * 1024;  // 23552
+constexpr int kPatchStages = 3;
 
 struct TensorMeta {
   int e;                  // stored value * 2^e = true value
@@ -67,6 +79,9 @@ struct ConvGemmParams {
   int stride, pad;
   int tiles_w, tiles_h;  // A_STEM: spatial tiles per image
   int tile_bw, tile_bh;  // A_STEM: tile shape in output pixels (tile_bw * tile_bh == 128)
+  int a_stage_bytes;     // bytes one A load deposits per stage (kABytes except A_STEM2)
+  int num_kb_b;          // number of 64-wide k-blocks of the weight matrix (resident-B kernels)
+  int stem_row_bytes;    // A_STEM2: shared-memory pitch of one staged image row segment
   int Hc, Wc;       // coarse level size (upsample-add)
   int relu;
   int has_res;
@@ -83,14 +98,20 @@ struct ConvGemmParams {
   const float* bound_consts;      // {G, max|shift|}, required iff out_scaled
 };
 
-template <int BN, int STAGES, int RES_SLABS>
+// BRES_KB > 0: the whole weight panel (up to BRES_KB k-blocks; requires a single n-tile) is loaded
+// once per CTA and stays resident in shared memory; only A tiles stream through the ring.
+// PATCH: A_PATCH pipeline (A ring of kPatchStages halo patches; STAGES then counts B tiles).
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH>
 struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kResOffset = STAGES * kStageBytes;
+  static constexpr int kBSlots = BRES_KB > 0 ? BRES_KB : STAGES;
+  static constexpr int kAStages = PATCH ? kPatchStages : STAGES;
+  static constexpr int kAStageBytes = PATCH ? kPatchStageBytes : kABytes;
+  static constexpr int kBOffset = kAStages * kAStageBytes;
+  static constexpr int kResOffset = kBOffset + kBSlots * kBBytes;
   static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
   static constexpr int kBarOffset = kOutOffset + kOutSlabs * kSlabBytes;
-  static constexpr int kNumBars = 2 * STAGES + 4 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1);
+  static constexpr int kNumBars = 2 * STAGES + 5 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1) + 2 * kPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
   static constexpr int kDynamic = kParamOffset + 2 * BN * 4;
@@ -115,10 +136,10 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
   return pack_bf16x2(lo, hi);
 }
 
-template <int BN, int STAGES, int RES_SLABS>
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = GemmSmem<BN, STAGES, RES_SLABS>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
   constexpr int kSlabsPerTile = BN / 64;
@@ -129,7 +150,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if ((base & 1023u) != 0u) __trap();  // SWIZZLE_128B operands need 1024-byte alignment
 
   const uint32_t smem_a = base;
-  const uint32_t smem_b = base + STAGES * kABytes;
+  const uint32_t smem_b = base + L::kBOffset;
   const uint32_t smem_res = base + L::kResOffset;
   const uint32_t smem_out = base + L::kOutOffset;
   const uint32_t bar0 = base + L::kBarOffset;
@@ -139,6 +160,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
   auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
   auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kRS + s); };
+  const uint32_t bres_bar = bar0 + 8u * (2 * STAGES + 4 + 2 * kRS);
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + kPatchStages + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
   float* s_scale = reinterpret_cast<float*>(smem + L::kParamOffset);
   float* s_shift = s_scale + BN;
@@ -165,6 +189,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(rfull_bar(s), 1);
       mbar_init(rempty_bar(s), 1);
     }
+    mbar_init(bres_bar, 1);
+    for (int s = 0; s < kPatchStages; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 3) {
@@ -183,6 +212,32 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ TMA producer (A, B)
     int stage = 0;
     uint32_t phase = 0;
+    if (BRES_KB > 0 && lane == 0) {
+      mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.num_kb_b) * L::kBBytes);
+      for (int kb = 0; kb < p.num_kb_b; ++kb)
+        tma_load_2d(smem_b + kb * L::kBBytes, &p.tmap_b, bres_bar, kb * kBK, 0);
+    }
+    const uint32_t stage_tx = static_cast<uint32_t>(p.a_stage_bytes) + (BRES_KB > 0 ? 0u : L::kBBytes);
+    if (PATCH) {
+      // one halo patch per (tile, 64-channel chunk); OOB pixels (the conv padding) are zero-filled
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        const int t = m_tile / p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int img = t / p.tiles_h;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(aempty_bar(stage), phase ^ 1u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(afull_bar(stage), kPatchBytes);
+            tma_load_4d(smem_a + stage * kPatchStageBytes, &p.tmap_a, afull_bar(stage), kc * kBK,
+                        tw * kPatchBW - 1, th * kPatchBH - 1, img);
+          }
+          __syncwarp();
+          if (++stage == kPatchStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -197,7 +252,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         cn = t / p.Ho;
         cw = q0 * p.stride - p.pad;
         ch = p0 * p.stride - p.pad;
-      } else if (p.a_mode == A_STEM) {
+      } else if (p.a_mode >= A_STEM) {
         const int tw = m_tile % p.tiles_w;
         const int t = m_tile / p.tiles_w;
         const int th = t % p.tiles_h;
@@ -211,7 +266,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
               const uint32_t fb = full_bar(stage);
-              mbar_arrive_expect_tx(fb, L::kStageBytes);
+              mbar_arrive_expect_tx(fb, stage_tx);
               const uint32_t dst_a = smem_a + stage * kABytes;
               const uint32_t dst_b = smem_b + stage * L::kBBytes;
               if (p.a_mode == A_TILED) {
@@ -220,11 +275,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 tma_load_im2col_4d(dst_a, &p.tmap_a, fb, kc * kBK, cw, ch, cn,
                                    static_cast<uint16_t>(s * p.dil),
                                    static_cast<uint16_t>(r * p.dil));
-              } else {
+              } else if (p.a_mode == A_STEM) {
                 // filter row r of the 7x7 window = staged image row 2*(ho + r/2) + (r & 1)
                 tma_load_5d(dst_a, &p.tmap_a, fb, 0, r & 1, cw, ch + (r >> 1), cn);
+              } else {
+                // A_STEM2: the 7 staged image rows x 272 pixels all windows of this tile live in,
+                // copied linearly (no swizzle); coordinates (64-element chunk, chunk index, row, image)
+                tma_load_4d(dst_a, &p.tmap_a, fb, 0, cw >> 3, 2 * ch, cn);
               }
-              tma_load_2d(dst_b, &p.tmap_b, fb, (r * p.kw + s) * p.cin + kc * kBK, n0);
+              if (BRES_KB == 0)
+                tma_load_2d(dst_b, &p.tmap_b, fb, (r * p.kw + s) * p.cin + kc * kBK, n0);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -240,6 +300,48 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (BRES_KB > 0) mbar_wait(bres_bar, 0);
+    if (PATCH) {
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(afull_bar(as), aphase);
+          tc_fence_after();
+          const uint32_t a0 = smem_a + as * kPatchStageBytes;
+          for (int tap = 0; tap < 9; ++tap) {
+            if (BRES_KB == 0) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+            }
+            if (lane == 0) {
+              const int r = tap / 3, sx = tap - 3 * r;
+              const uint64_t da = make_smem_desc_sw128_sbo(a0 + (r * kPatchPW + sx) * 128, kPatchPW * 128);
+              const uint64_t db = make_smem_desc_sw128(
+                  smem_b + (BRES_KB > 0 ? tap * p.k_chunks + kc : stage) * L::kBBytes);
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              if (BRES_KB == 0) umma_commit(empty_bar(stage));
+              if (tap == 8) {
+                umma_commit(aempty_bar(as));
+                if (kc == p.k_chunks - 1) umma_commit(tfull_bar(acc));
+              }
+            }
+            __syncwarp();
+            if (BRES_KB == 0) {
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+          if (++as == kPatchStages) { as = 0; aphase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -248,12 +350,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t da = make_smem_desc_sw128(smem_a + stage * kABytes);
-          const uint64_t db = make_smem_desc_sw128(smem_b + stage * L::kBBytes);
+          if (BRES_KB > 0 && p.a_mode == A_STEM2) {
+            // Row i of the A operand is the 8-pixel x 4-channel window starting at staged pixel 2*i:
+            // an un-swizzled K-major view whose rows are 16 bytes apart and OVERLAP (the second
+            // 8-element K chunk of row i is the first chunk of row i+1): LBO = 16 B, SBO = 128 B.
+            const uint32_t a0 = smem_a + stage * kABytes;
+            for (int r = 0; r < p.num_kb_b; ++r) {
+              const uint64_t db = make_smem_desc_sw128(smem_b + r * L::kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
-            umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 2; ++k) {
+                const uint64_t da = make_smem_desc_nosw(a0 + r * p.stem_row_bytes + k * 32, 16, 128);
+                umma_bf16_ss(d_tmem, da, db + 2u * k, idesc, (r | k) != 0 ? 1u : 0u);
+              }
+            }
+          } else {
+            const uint64_t da = make_smem_desc_sw128(smem_a + stage * kABytes);
+            const uint64_t db = make_smem_desc_sw128(smem_b + (BRES_KB > 0 ? kb : stage) * L::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
+              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
@@ -276,11 +393,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           mbar_wait(rempty_bar(rs), rphase ^ 1u);
           if (lane == 0) {
             mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
-            tma_load_2d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
-                        m_tile * kBM);
+            if (p.a_mode >= A_STEM) {
+              const int tw = m_tile % p.tiles_w;
+              const int t = m_tile / p.tiles_w;
+              tma_load_4d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
+                          tw * p.tile_bw, (t % p.tiles_h) * p.tile_bh, t / p.tiles_h);
+            } else {
+              tma_load_2d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
+                          m_tile * kBM);
+            }
           }
           __syncwarp();
           if (++rs == kRS) { rs = 0; rphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 11) {
+    // ------------------------------------------------------------------ TMA producer (B, patch mode)
+    if (PATCH && BRES_KB == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(full_bar(stage), L::kBBytes);
+              tma_load_2d(smem_b + stage * L::kBBytes, &p.tmap_b, full_bar(stage), tap * p.cin + kc * kBK, n0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -339,7 +483,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       bool valid;
       long long pix;
       int st_c1 = 0, st_c2 = 0, st_c3 = 0;  // TMA store coordinates beyond the channel
-      if (p.a_mode == A_STEM) {
+      if (p.a_mode >= A_STEM) {
         const int tw = m_tile % p.tiles_w;
         const int t = m_tile / p.tiles_w;
         const int th = t % p.tiles_h;
@@ -469,7 +613,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         named_bar_sync(1, kEpiThreads);
         if (issuer) {
           const uint32_t src = smem_out + ob * kSlabBytes;
-          if (p.a_mode == A_STEM) {
+          if (p.a_mode >= A_STEM) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),

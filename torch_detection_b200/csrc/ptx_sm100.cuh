@@ -74,6 +74,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -162,6 +170,28 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;                      // version = 1, bits [46,48)
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B, bits [61,64)
   return d;
+}
+
+// Same layout with an explicit stride between 8-row groups (rows of a group stay 128 B apart).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// Un-swizzled K-major descriptor: 8-row x 16-byte core matrices; `lbo` = byte distance between the
+// two 8-element K chunks of one MMA, `sbo` = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // version = 1
+  return d;                              // layout type 0 = no swizzle
 }
 
 // Instruction descriptor, kind::f16: D fp32, A/B 16-bit floats (format 0 = fp16, 1 = bf16, chosen

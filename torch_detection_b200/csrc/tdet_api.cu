@@ -7,6 +7,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -121,7 +122,9 @@ struct Launch {
   bool has_ext = false;
   // conv / stem
   ConvGemmParams gp{};
-  int bn = 0, stages = 0, res_slabs = 0;
+  int bn = 0, stages = 0, res_slabs = 0, bres_kb = 0;
+  bool patch = false;
+  bool no_patch = false;  // debugging hook: force the im2col loader
   dim3 grid{1, 1, 1};
   double flops = 0.0;  // 2*M*N*K, real dims
   double bytes = 0.0;  // algorithmic HBM bytes: every operand read once, output written once
@@ -149,6 +152,15 @@ void set_field(tdet_op& o, int f, const void* p) {
 
 int out_dim(int v, int k, int s, int p, int d) { return (v + 2 * p - d * (k - 1) - 1) / s + 1; }
 
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
+// A_PATCH is used when the 8x16 spatial tiling wastes at most this many percent of the MMA rows.
+int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
+int stem_version() { return env_int("TDET_STEM", 2); }
+
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
 
 CUtensorMapDataType tm_dtype(int dt) {
@@ -171,32 +183,66 @@ int encode_2d(CUtensorMap* tm, const void* ptr, int dt, long long cols, long lon
   return TDET_OK;
 }
 
-template <int BN, int STAGES, int RES_SLABS>
+// NHWC [n][h][w][c] 16-bit tensor seen as (c, w, h, n); box = 64 channels x bw x bh pixels of one image.
+int encode_4d(CUtensorMap* tm, const void* ptr, int dt, int c, int w, int h, int n, int bw, int bh,
+              const char* what) {
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                        static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w) * c * 2,
+                           static_cast<cuuint64_t>(h) * w * c * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = driver().encode_tiled(tm, tm_dtype(dt), 4, const_cast<void*>(ptr), dims, strides, box, es,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(TDET_ERR_DRIVER, "cuTensorMapEncodeTiled(%s) failed: %d", what, static_cast<int>(r));
+  return TDET_OK;
+}
+
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH = false>
 int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES, RES_SLABS>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH>;
   static bool attr_set[64] = {};
   int dev = 0;
   TDET_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS>,
+    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  conv_gemm_kernel<BN, STAGES, RES_SLABS><<<grid, kGemmThreads, L::kDynamic, st>>>(gp);
+  conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH><<<grid, kGemmThreads, L::kDynamic, st>>>(gp);
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }
 
 int launch_gemm(const Launch& l, cudaStream_t st) {
-  const int v = l.bn * 10000 + l.stages * 100 + l.res_slabs;
-  switch (v) {
-    case 64 * 10000 + 602: return launch_gemm_t<64, 6, 2>(l.gp, l.grid, st);
-    case 128 * 10000 + 502: return launch_gemm_t<128, 5, 2>(l.gp, l.grid, st);
-    case 256 * 10000 + 400: return launch_gemm_t<256, 4, 0>(l.gp, l.grid, st);
-    case 256 * 10000 + 303: return launch_gemm_t<256, 3, 3>(l.gp, l.grid, st);
+  const int v = l.bn * 1000000 + l.stages * 10000 + l.res_slabs * 100 + l.bres_kb;
+  if (l.patch) {
+    switch (v) {
+      case 64 * 1000000 + 40209: return launch_gemm_t<64, 4, 2, 9, true>(l.gp, l.grid, st);
+      case 128 * 1000000 + 40200: return launch_gemm_t<128, 4, 2, 0, true>(l.gp, l.grid, st);
+      case 128 * 1000000 + 70000: return launch_gemm_t<128, 7, 0, 0, true>(l.gp, l.grid, st);
+      case 256 * 1000000 + 30000: return launch_gemm_t<256, 3, 0, 0, true>(l.gp, l.grid, st);
+    }
+    return fail(TDET_ERR_INVALID_ARGUMENT, "no patch-mode GEMM instantiation for tile %d/%d/%d/%d", l.bn,
+                l.stages, l.res_slabs, l.bres_kb);
   }
-  return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d", l.bn, l.stages,
-              l.res_slabs);
+  switch (v) {
+    // streaming weights
+    case 64 * 1000000 + 60200: return launch_gemm_t<64, 6, 2, 0>(l.gp, l.grid, st);
+    case 128 * 1000000 + 50200: return launch_gemm_t<128, 5, 2, 0>(l.gp, l.grid, st);
+    case 256 * 1000000 + 40000: return launch_gemm_t<256, 4, 0, 0>(l.gp, l.grid, st);
+    case 256 * 1000000 + 30300: return launch_gemm_t<256, 3, 3, 0>(l.gp, l.grid, st);
+    // resident weights (single n-tile, small K)
+    case 64 * 1000000 + 40007: return launch_gemm_t<64, 4, 0, 7>(l.gp, l.grid, st);    // stem
+    case 64 * 1000000 + 40209: return launch_gemm_t<64, 4, 2, 9>(l.gp, l.grid, st);
+    case 128 * 1000000 + 40204: return launch_gemm_t<128, 4, 2, 4>(l.gp, l.grid, st);
+    case 256 * 1000000 + 40301: return launch_gemm_t<256, 4, 3, 1>(l.gp, l.grid, st);
+    case 256 * 1000000 + 40004: return launch_gemm_t<256, 4, 0, 4>(l.gp, l.grid, st);
+  }
+  return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d", l.bn, l.stages,
+              l.res_slabs, l.bres_kb);
 }
 
 // Fills the epilogue / numerics part of the GEMM parameters shared by conv and stem.
@@ -285,19 +331,76 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   }
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
   gp.num_n_tiles = o.cout / l.bn;
+  gp.a_stage_bytes = kABytes;
+  gp.num_kb_b = o.kh * o.kw * gp.k_chunks;
+  l.bres_kb = 0;
+  l.patch = false;
+  const double real_rows = static_cast<double>(gp.M);
   const bool tiled = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0);
-  gp.a_mode = tiled ? A_TILED : A_IM2COL;
+  if (o.kh == 3 && o.kw == 3 && o.stride == 1 && o.pad == 1 && o.dil == 1 && !l.no_patch && patch_max_waste_pct() >= 0) {
+    const int tw = (o.wo + kPatchBW - 1) / kPatchBW, th = (o.ho + kPatchBH - 1) / kPatchBH;
+    const double rows = static_cast<double>(o.n) * tw * th * kBM;
+    const bool fits = rows <= 0x7FFFFF00LL && rows * 100.0 <= real_rows * (100.0 + patch_max_waste_pct());
+    const bool variant = (l.bn == 64 && gp.num_kb_b <= 9) || l.bn == 128 || (l.bn == 256 && !o.residual);
+    if (fits && variant) {
+      l.patch = true;
+      gp.a_mode = A_PATCH;
+      gp.tile_bw = kPatchBW;
+      gp.tile_bh = kPatchBH;
+      gp.tiles_w = tw;
+      gp.tiles_h = th;
+      gp.num_m_tiles = o.n * tw * th;
+      gp.a_stage_bytes = kPatchBytes;
+      if (l.bn == 64) {
+        l.stages = 4; l.res_slabs = 2; l.bres_kb = 9;
+      } else if (l.bn == 128) {
+        // 16 KiB weight tiles are consumed every 256 MMA cycles: without a residual operand the
+        // freed shared memory buys a deeper B ring
+        if (o.residual) { l.stages = 4; l.res_slabs = 2; } else { l.stages = 7; l.res_slabs = 0; }
+      } else {
+        l.stages = 3; l.res_slabs = 0;
+      }
+    }
+  }
+  if (!l.patch) {
+    gp.a_mode = tiled ? A_TILED : A_IM2COL;
+    if (resident_b_enabled() && gp.num_n_tiles == 1 && gp.num_m_tiles >= 4 * di.num_sms) {
+      // the weight panel fits beside the A ring: load it once per CTA instead of once per k-block
+      if (l.bn == 64 && gp.num_kb_b <= 9) {
+        l.stages = 4; l.res_slabs = 2; l.bres_kb = 9;
+      } else if (l.bn == 128 && gp.num_kb_b <= 4) {
+        l.stages = 4; l.res_slabs = 2; l.bres_kb = 4;
+      } else if (l.bn == 256 && gp.num_kb_b <= 1) {
+        l.stages = 4; l.res_slabs = 3; l.bres_kb = 1;
+      } else if (l.bn == 256 && gp.num_kb_b <= 4 && !o.residual) {
+        l.stages = 4; l.res_slabs = 0; l.bres_kb = 4;
+      }
+    }
+  }
 
   rc = encode_2d(&gp.tmap_b, o.wgt, o.x_dtype, static_cast<long long>(o.kh) * o.kw * o.cin, o.cout,
                  l.bn, "weights");
   if (rc) return rc;
-  rc = encode_2d(&gp.tmap_out, o.y, o.y_dtype, o.cout, gp.M, kBM, "output");
-  if (rc) return rc;
-  if (o.residual) {
-    rc = encode_2d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout, gp.M, kBM, "residual");
+  if (l.patch) {
+    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
     if (rc) return rc;
+    if (o.residual) {
+      rc = encode_4d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW,
+                     kPatchBH, "residual");
+      if (rc) return rc;
+    }
+    rc = encode_4d(&gp.tmap_a, o.x, o.x_dtype, o.cin, o.w, o.h, o.n, kPatchPW, kPatchPH, "halo patch");
+    if (rc) return rc;
+  } else {
+    rc = encode_2d(&gp.tmap_out, o.y, o.y_dtype, o.cout, gp.M, kBM, "output");
+    if (rc) return rc;
+    if (o.residual) {
+      rc = encode_2d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout, gp.M, kBM, "residual");
+      if (rc) return rc;
+    }
   }
-  if (tiled) {
+  if (l.patch) {
+  } else if (tiled) {
     rc = encode_2d(&gp.tmap_a, o.x, o.x_dtype, o.cin, gp.M, kBM, "activations");
     if (rc) return rc;
   } else {
@@ -329,15 +432,20 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   int g = di.num_sms;
   if (g > num_tiles) g = num_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
-  l.flops = 2.0 * static_cast<double>(gp.M) * o.cout * (static_cast<double>(o.cin) * o.kh * o.kw);
+  l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) * o.kh * o.kw);
   l.bytes = 2.0 * (static_cast<double>(o.n) * o.h * o.w * o.cin +
                    static_cast<double>(o.cout) * o.cin * o.kh * o.kw +
-                   static_cast<double>(gp.M) * o.cout * (1 + (o.residual ? 1 : 0)) +
+                   real_rows * o.cout * (1 + (o.residual ? 1 : 0)) +
                    (o.coarse ? static_cast<double>(o.n) * o.hc * o.wc * o.cout : 0.0));
   return TDET_OK;
 }
 
-constexpr int kStemBW = 32, kStemBH = 4;
+constexpr int kStemBW = 32, kStemBH = 4;  // TDET_STEM=1: 32x4 output pixels per tile (window gather)
+constexpr int kStem2BW = 128;             // TDET_STEM=2: 128x1 output pixels per tile (linear rows)
+
+// staged image geometry (TDET_OP_PREP output): rows = 2*ho + 6, pitch = 2*wo + 16 rounded up to 16 px
+int stem_hp(int ho) { return 2 * ho + 6; }
+int stem_wp(int wo) { return (2 * wo + 16 + 15) / 16 * 16; }
 
 int build_stem(Launch& l, const DeviceInfo& di) {
   const tdet_op& o = l.op;
@@ -348,33 +456,57 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   if (!o.x || !o.wgt || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: null tensor pointer");
   if (o.x_dtype != TDET_BF16) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: staged image must be BF16");
   if (o.residual || o.coarse) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: no residual/coarse");
-  const int hp = 2 * o.ho + 6, wp = 2 * o.wo + 16;
+  const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
+  const bool v2 = stem_version() >= 2;
+  const int bw = v2 ? kStem2BW : kStemBW, bh = v2 ? 1 : kStemBH;
   ConvGemmParams& gp = l.gp;
   memset(&gp, 0, sizeof(gp));
   int rc = fill_epilogue(l);
   if (rc) return rc;
   gp.N = 64;
   gp.k_chunks = 1;
-  gp.kh = 7;  // one k-block per filter row
+  gp.kh = v2 ? 1 : 7;  // v1: one k-block per filter row; v2: one A load per tile, 7 filter rows inside
   gp.kw = 1;
   gp.dil = 1;
   gp.cin = 64;  // B column offset per filter row = 64
-  gp.a_mode = A_STEM;
+  gp.a_mode = v2 ? A_STEM2 : A_STEM;
   gp.Ho = o.ho;
   gp.Wo = o.wo;
-  gp.tile_bw = kStemBW;
-  gp.tile_bh = kStemBH;
-  gp.tiles_w = (o.wo + kStemBW - 1) / kStemBW;
-  gp.tiles_h = (o.ho + kStemBH - 1) / kStemBH;
+  gp.tile_bw = bw;
+  gp.tile_bh = bh;
+  gp.tiles_w = (o.wo + bw - 1) / bw;
+  gp.tiles_h = (o.ho + bh - 1) / bh;
   gp.num_m_tiles = o.n * gp.tiles_w * gp.tiles_h;
   gp.num_n_tiles = 1;
   gp.M = gp.num_m_tiles * kBM;
   gp.ab_fp16 = 0;
+  gp.num_kb_b = 7;
+  gp.a_stage_bytes = kABytes;
   l.bn = 64;
-  l.stages = 6;
-  l.res_slabs = 2;
+  l.stages = v2 ? 4 : 6;
+  l.res_slabs = v2 ? 0 : 2;
+  l.bres_kb = v2 ? 7 : 0;
   rc = encode_2d(&gp.tmap_b, o.wgt, TDET_BF16, 448, 64, 64, "stem weights");
   if (rc) return rc;
+  if (v2) {
+    // Linear view of the staging: (64 elements = 16 px, chunks per row, rows, images); one box =
+    // 17 chunks (272 px) x 7 rows = every pixel the 128 windows of a tile touch.
+    constexpr int kChunks = 17;
+    gp.stem_row_bytes = kChunks * 128;
+    gp.a_stage_bytes = 7 * gp.stem_row_bytes;
+    cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(wp / 16), static_cast<cuuint64_t>(hp),
+                          static_cast<cuuint64_t>(o.n)};
+    cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(wp) * 8, static_cast<cuuint64_t>(hp) * wp * 8};
+    cuuint32_t box[4] = {64, kChunks, 7, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = driver().encode_tiled(&gp.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                       const_cast<void*>(o.x), dims, strides, box, es,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return fail(TDET_ERR_DRIVER, "cuTensorMapEncodeTiled(stem A v2) failed: %d", static_cast<int>(r));
+  } else
   // Overlapping-window view of the padded NHWC4 staging [n][hp][wp][4]:
   //   d0: 64 elements = 16 consecutive pixels x 4 ch of one image row = one 128-byte swizzle row
   //       (taps 0..6 of one filter row carry weights; the other 9 pixels meet zero weights).
@@ -405,7 +537,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
                           static_cast<cuuint64_t>(o.n)};
     cuuint64_t strides[3] = {128, static_cast<cuuint64_t>(o.wo) * 128,
                              static_cast<cuuint64_t>(o.ho) * o.wo * 128};
-    cuuint32_t box[4] = {64, kStemBW, kStemBH, 1};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = driver().encode_tiled(&gp.tmap_out, tm_dtype(o.y_dtype), 4, o.y, dims, strides, box, es,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -434,7 +566,7 @@ int build_launch(Launch& l, const DeviceInfo& di) {
       if (o.x_dtype != TDET_BF16 && o.x_dtype != TDET_F32)
         return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad dtype");
       l.bytes = static_cast<double>(o.n) * o.h * o.w * 3 * (o.x_dtype == TDET_F32 ? 4 : 2) +
-                static_cast<double>(o.n) * (2 * o.ho + 6) * (2 * o.wo + 16) * 8;
+                static_cast<double>(o.n) * stem_hp(o.ho) * stem_wp(o.wo) * 8;
       return TDET_OK;
     case TDET_OP_MAXPOOL:
       if (o.cin % 8 || !o.x || !o.y || o.ho != out_dim(o.h, 3, 2, 1, 1) ||
@@ -465,7 +597,7 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
     case TDET_OP_CONV:
     case TDET_OP_STEM: return launch_gemm(l, st);
     case TDET_OP_PREP: {
-      const int hp = 2 * o.ho + 6, wp = 2 * o.wo + 16;
+      const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
       const long long total = static_cast<long long>(o.n) * hp * wp;
       const int g = grid_for(total, di.num_sms);
       TensorMeta* meta = reinterpret_cast<TensorMeta*>(o.y_meta);
@@ -578,6 +710,13 @@ const char* tdet_last_error(void) { return g_err; }
 int tdet_device_supported(int device) {
   DeviceInfo* di = nullptr;
   return require_sm100(device, &di);
+}
+
+int tdet_stem_staging_dims(int ho, int wo, int* hp, int* wp) {
+  if (ho <= 0 || wo <= 0 || !hp || !wp) return fail(TDET_ERR_INVALID_ARGUMENT, "stem_staging_dims: bad arguments");
+  *hp = stem_hp(ho);
+  *wp = stem_wp(wo);
+  return TDET_OK;
 }
 
 int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw,
@@ -755,7 +894,7 @@ int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* ou
   out->m = gemm ? l.gp.M : 0;
   out->n = gemm ? l.gp.N : 0;
   out->k = (l.kind == TDET_OP_STEM) ? 147 : (gemm ? l.op.cin * l.op.kh * l.op.kw : 0);
-  out->variant = l.stages * 16 + l.res_slabs;
+  out->variant = (l.patch ? 4096 : 0) + l.stages * 256 + l.res_slabs * 16 + l.bres_kb;
   out->flops = l.flops;
   out->bytes = l.bytes;
   return TDET_OK;
@@ -789,6 +928,7 @@ int tdet_debug_im2col_tile(const tdet_op* op, int m0, int r, int s, int kc, void
   Launch l;
   l.op = *op;
   l.op.kind = TDET_OP_CONV;
+  l.no_patch = true;
   rc = build_conv(l, *di);
   if (rc) return rc;
   if (l.gp.a_mode != A_IM2COL) return fail(TDET_ERR_INVALID_ARGUMENT, "op does not use im2col");

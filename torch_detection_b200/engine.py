@@ -32,6 +32,13 @@ def conv_out(v, k, s, p, d=1):
     return (v + 2 * p - d * (k - 1) - 1) // s + 1
 
 
+def stem_staging_dims(ho, wo):
+    """(hp, wp) of the padded NHWC4 staging buffer TDET_OP_PREP writes for a stem output ho x wo."""
+    hp, wp = ctypes.c_int32(), ctypes.c_int32()
+    _C.check(_C.lib().tdet_stem_staging_dims(ho, wo, ctypes.byref(hp), ctypes.byref(wp)))
+    return hp.value, wp.value
+
+
 class Act(object):
     """Handle of a dense NHWC 16-bit activation tensor: device buffer, logical (n, h, w, c) shape,
     storage dtype and the device address of its ``tdet_tensor_meta`` (None = plain values)."""

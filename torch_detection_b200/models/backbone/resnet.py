@@ -295,7 +295,7 @@ class ResNet(nn.Module):
             for i0 in range(0, n, chunk):
                 cn = min(chunk, n - i0)
                 if stages[0] == 0:
-                    staged = pool.get((cn, 2 * ho + 6, 2 * wo + 16, 4))
+                    staged = pool.get((cn,) + engine.stem_staging_dims(ho, wo) + (4,))
                     staged_meta = meta.new()
                     ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta))
                     stem_out = new_act((cn, ho, wo, 64), internal)
