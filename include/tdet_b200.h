@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 4
+#define TDET_ABI_VERSION 5
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -73,15 +73,27 @@ typedef enum tdet_op_kind {
   TDET_OP_STEM = 1,
   TDET_OP_MAXPOOL = 2,
   TDET_OP_CONV = 3,
-  TDET_OP_SUBSAMPLE = 4
+  TDET_OP_SUBSAMPLE = 4,
+  /* ---- training path (config 4: frozen BN, hand-written dgrad / wgrad) ---- */
+  TDET_OP_WGRAD = 5,     /* weight gradient of a conv (implicit GEMM over pixels) */
+  TDET_OP_DW_UNPACK = 6, /* fp32 [cout][kh][kw][cin] wgrad accumulator -> fp32 OIHW parameter gradient */
+  TDET_OP_COLSUM = 7,    /* bias gradient: per-channel sum over all pixels */
+  TDET_OP_SUMPOOL2 = 8,  /* adjoint of the nearest-x2 upsample (fpn.py:100-101): 2x2 sum pool */
+  TDET_OP_DILATE2 = 9,   /* adjoint of a stride-2 subsample: zero-insertion upsample to (ho, wo) */
+  TDET_OP_ADD_MASK = 10, /* y = (x + residual) * (mask > 0): gradient merge / ReLU backward */
+  TDET_OP_ZERO = 11      /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2 } tdet_dtype;
 
 enum {
   TDET_FLAG_RELU = 1,       /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
-  TDET_FLAG_SCALED_OUT = 2  /* y is stored with a device-chosen power-of-two exponent (needs y_meta,
+  TDET_FLAG_SCALED_OUT = 2, /* y is stored with a device-chosen power-of-two exponent (needs y_meta,
                                x_meta and bound_consts) */
+  TDET_FLAG_COARSE_PARITY = 4, /* coarse[i][j] is added at y[2i][2j] only (adjoint of a stride-2 1x1 conv,
+                                  resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */
+  TDET_FLAG_WGT_BF16 = 8    /* wgt is bf16 although x is fp16 (tcgen05 kind::f16 takes one format per
+                               operand); default: wgt has x's format */
 };
 
 /* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
@@ -112,7 +124,26 @@ typedef struct tdet_tensor_meta {
  *                   of coarse_dtype or NULL, with ho == 2*hc and wo == 2*wc (nearest x2,
  *                   fpn.py:100-101).  cin and cout must be multiples of 64.
  *                   *_meta: optional tdet_tensor_meta of each tensor (NULL = exponent 0, unknown max).
+ *                   mask (optional): 16-bit [n][ho][wo][cout] forward activation (post-ReLU, so
+ *                   >= 0); y is zeroed wherever mask == 0.  This is how a dgrad conv applies the ReLU
+ *                   backward of the layer it feeds (resnet.py:48,58,103,108,118).
+ *                   A data-gradient (dgrad) of a stride-1 conv IS a TDET_OP_CONV over the output
+ *                   gradient with weights from tdet_pack_dgrad_weight and pad' = dil*(k-1) - pad.
  * TDET_OP_SUBSAMPLE y[n][i][j][:] = x[n][2i][2j][:]   (ho = (h-1)/2+1), any 16-bit dtype
+ * TDET_OP_WGRAD     x: the conv's forward input [n][h][w][cin] (x_dtype, x_meta); gy: the gradient
+ *                   w.r.t. the BN output of that conv (ReLU mask already applied)
+ *                   [n][ho][wo][cout] of gy_dtype (BF16);
+ *                   dw: fp32 [cout][kh][kw][cin], ACCUMULATED (caller zeroes it):
+ *                   dw[co][r][s][ci] += scale[co] * sum_{n,p,q} gy[n][p][q][co] * x[n][p*stride-pad+r*dil][..][ci]
+ *                   (scale = folded BN scale or NULL = 1).  geometry fields as for the forward conv.
+ * TDET_OP_DW_UNPACK x: fp32 [cout][kh][kw][cin]; y: fp32 [cout][cin][kh][kw]
+ * TDET_OP_COLSUM    x: 16-bit [n*h*w][cin]; dw: fp32 [cin] += column sums (caller zeroes it)
+ * TDET_OP_SUMPOOL2  y[n][i][j][:] = sum_{a,b<2} x[n][2i+a][2j+b][:]   (h == 2*ho, w == 2*wo), bf16,
+ *                   fp32 accumulation
+ * TDET_OP_DILATE2   y[n][u][v][:] = (u,v even) ? x[n][u/2][v/2][:] : 0; y is (ho, wo) with
+ *                   h == (ho+1)/2, w == (wo+1)/2
+ * TDET_OP_ADD_MASK  y = (x + residual) * (mask != 0); residual and mask optional; all [n][h][w][cin] bf16
+ * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled
  */
 typedef struct tdet_op {
   int32_t kind;  /* tdet_op_kind */
@@ -139,6 +170,12 @@ typedef struct tdet_op {
   const tdet_tensor_meta* coarse_meta;
   tdet_tensor_meta* y_meta;
   const float* bound_consts; /* tdet_conv_bound_consts output; needed with TDET_FLAG_SCALED_OUT */
+  /* ---- training path ---- */
+  const void* mask;          /* CONV / ADD_MASK: forward activation to mask the result against */
+  const void* gy;            /* WGRAD: output gradient */
+  int32_t gy_dtype;
+  int32_t reserved0;
+  float* dw;                 /* WGRAD / COLSUM: fp32 accumulator */
 } tdet_op;
 
 typedef struct tdet_plan tdet_plan; /* opaque */
@@ -164,6 +201,10 @@ int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
 int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
                  float eps, float* scale, float* shift, int channels, void* stream);
+/* Operand of the data-gradient conv: out[ci][kh-1-r][kw-1-s][co] = scale[co] * w[co][ci][r][s]
+ * (scale = folded BN scale of the forward conv, NULL = 1), 16-bit, round-to-nearest-even. */
+int tdet_pack_dgrad_weight(const float* w_oihw, const float* scale, void* w_packed, int cout, int cin,
+                           int kh, int kw, int dtype, void* stream);
 /* consts[0] = max_c |scale_c| * sum_k |w_packed[c][k]|, consts[1] = max_c |shift_c|  (scale NULL = 1,
  * shift NULL = 0): |conv(x)*scale + shift| <= consts[0] * max|x| + consts[1] for any x. */
 int tdet_conv_bound_consts(const void* w_packed, int dtype, const float* scale, const float* shift,
@@ -186,6 +227,10 @@ int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void*
                      const size_t* ext_bytes, int n_ext, tdet_tensor_meta* meta_arena,
                      int meta_count, int device);
 int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void* stream);
+/* Runs ops [first, last) only (no metadata reset unless first == 0): lets the caller interleave its
+ * own stream work -- the bucketed gradient all-reduce of the training path -- between segments. */
+int tdet_plan_run_range(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, int first, int last,
+                        void* stream);
 /* Same as tdet_plan_run with unchanged external pointers, but brackets every kernel launch with
  * CUDA events on `stream` and returns the per-launch device time in milliseconds
  * (ms_per_launch[tdet_plan_num_launches]).  Synchronises the stream; measurement only. */

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # tdet_status
 OK = 0
@@ -21,10 +21,13 @@ ERR_OUT_OF_MEMORY = -6
 
 # tdet_op_kind
 OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
+OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO = 5, 6, 7, 8, 9, 10, 11
 # tdet_dtype
 BF16, F32, F16 = 0, 1, 2
 FLAG_RELU = 1
 FLAG_SCALED_OUT = 2
+FLAG_COARSE_PARITY = 4
+FLAG_WGT_BF16 = 8
 
 
 class TdetOp(ctypes.Structure):
@@ -45,6 +48,9 @@ class TdetOp(ctypes.Structure):
         ("x_meta", ctypes.c_void_p), ("residual_meta", ctypes.c_void_p),
         ("coarse_meta", ctypes.c_void_p), ("y_meta", ctypes.c_void_p),
         ("bound_consts", ctypes.c_void_p),
+        ("mask", ctypes.c_void_p), ("gy", ctypes.c_void_p),
+        ("gy_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("dw", ctypes.c_void_p),
     ]
 
 
@@ -65,8 +71,9 @@ class TdetError(RuntimeError):
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
     "tdet_stem_staging_dims",
-    "tdet_pack_conv_weight", "tdet_pack_stem_weight", "tdet_fold_bn", "tdet_conv_bound_consts",
-    "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_timed",
+    "tdet_pack_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
+    "tdet_conv_bound_consts",
+    "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_range", "tdet_plan_run_timed",
     "tdet_plan_num_launches", "tdet_plan_launch_info",
     "tdet_plan_flops", "tdet_plan_destroy", "tdet_debug_im2col_tile",
 ]
@@ -89,6 +96,7 @@ def lib():
     L.tdet_last_error.restype = ctypes.c_char_p
     L.tdet_device_supported.argtypes = [i32]
     L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.tdet_pack_dgrad_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
     L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.tdet_conv_bound_consts.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
@@ -98,6 +106,7 @@ def lib():
                                    ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t), i32, vp, i32,
                                    i32]
     L.tdet_plan_run.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
+    L.tdet_plan_run_range.argtypes = [vp, ctypes.POINTER(vp), i32, i32, i32, vp]
     L.tdet_plan_run_timed.argtypes = [vp, ctypes.POINTER(vp), i32, vp, ctypes.POINTER(f32)]
     L.tdet_plan_launch_info.argtypes = [vp, i32, ctypes.POINTER(TdetLaunchInfo)]
     L.tdet_plan_num_launches.argtypes = [vp]

@@ -185,4 +185,144 @@ bound_consts_kernel(const W* __restrict__ w, const float* __restrict__ scale,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// training path: small memory-bound helpers of the backward pass (all dense NHWC bf16, 16-byte accesses)
+// ---------------------------------------------------------------------------------------------------
+
+// Operand of the data-gradient conv: out[ci][kh-1-r][kw-1-s][co] = scale[co] * w[co][ci][r][s].
+template <typename W>
+__global__ void __launch_bounds__(256)
+pack_dgrad_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, W* __restrict__ out,
+                         int cout, int cin, int kh, int kw) {
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % cout);
+    long long t = i / cout;
+    const int s = static_cast<int>(t % kw);
+    t /= kw;
+    const int r = static_cast<int>(t % kh);
+    const int ci = static_cast<int>(t / kh);
+    const float v = w[((static_cast<long long>(co) * cin + ci) * kh + (kh - 1 - r)) * kw + (kw - 1 - s)];
+    out[i] = to_w16<W>(v * (scale ? scale[co] : 1.0f));
+  }
+}
+
+// fp32 [cout][kh][kw][cin] -> fp32 [cout][cin][kh][kw]
+__global__ void __launch_bounds__(256)
+dw_unpack_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int kh, int kw) {
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int s = static_cast<int>(i % kw);
+    long long t = i / kw;
+    const int r = static_cast<int>(t % kh);
+    t /= kh;
+    const int ci = static_cast<int>(t % cin);
+    const int co = static_cast<int>(t / cin);
+    out[i] = in[((static_cast<long long>(co) * kh + r) * kw + s) * cin + ci];
+  }
+}
+
+// dw[c] += sum_m x[m][c]   (bf16 x, fp32 sums).  blockIdx.y = 64-channel chunk, blockIdx.x = row strip;
+// thread = (8-channel group, row lane).
+__global__ void __launch_bounds__(256)
+colsum_kernel(const uint4* __restrict__ x, float* __restrict__ dw, long long rows, int c8, int rows_per_block) {
+  const int cg = threadIdx.x & 7;
+  const int rl = threadIdx.x >> 3;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0 + rl; r < r1; r += 32) {
+    const uint4 v = __ldg(x + r * c8 + blockIdx.y * 8 + cg);
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x);
+    acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z);
+    acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+  }
+  __shared__ float red[32][65];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
+    atomicAdd(dw + blockIdx.y * 64 + threadIdx.x, s);
+  }
+}
+
+__device__ __forceinline__ uint32_t add4_bf16x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return pack_bf16x2(bf16_lo(a) + bf16_lo(b) + bf16_lo(c) + bf16_lo(d),
+                     bf16_hi(a) + bf16_hi(b) + bf16_hi(c) + bf16_hi(d));
+}
+
+// y[n][i][j][:] = sum over the 2x2 block of x (adjoint of nearest-x2 upsample)
+__global__ void __launch_bounds__(256)
+sumpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int c8, int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int ow = static_cast<int>(t % wo);
+    t /= wo;
+    const int oh = static_cast<int>(t % ho);
+    const int img = static_cast<int>(t / ho);
+    const uint4* px = x + ((static_cast<long long>(img) * h + 2 * oh) * w + 2 * ow) * c8 + cg;
+    const uint4 a = __ldg(px), b = __ldg(px + c8), c = __ldg(px + static_cast<long long>(w) * c8),
+                d = __ldg(px + static_cast<long long>(w) * c8 + c8);
+    uint4 o;
+    o.x = add4_bf16x2(a.x, b.x, c.x, d.x);
+    o.y = add4_bf16x2(a.y, b.y, c.y, d.y);
+    o.z = add4_bf16x2(a.z, b.z, c.z, d.z);
+    o.w = add4_bf16x2(a.w, b.w, c.w, d.w);
+    y[i] = o;
+  }
+}
+
+// y[n][u][v][:] = (u, v even) ? x[n][u/2][v/2][:] : 0   (adjoint of a stride-2 subsample)
+__global__ void __launch_bounds__(256)
+dilate2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int c8, int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int ow = static_cast<int>(t % wo);
+    t /= wo;
+    const int oh = static_cast<int>(t % ho);
+    const int img = static_cast<int>(t / ho);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (((oh | ow) & 1) == 0)
+      o = __ldg(x + ((static_cast<long long>(img) * h + (oh >> 1)) * w + (ow >> 1)) * c8 + cg);
+    y[i] = o;
+  }
+}
+
+__device__ __forceinline__ uint32_t add_mask_bf16x2(uint32_t a, uint32_t b, uint32_t m) {
+  float lo = bf16_lo(a) + bf16_lo(b), hi = bf16_hi(a) + bf16_hi(b);
+  if ((m & 0x00007FFFu) == 0u) lo = 0.0f;
+  if ((m & 0x7FFF0000u) == 0u) hi = 0.0f;
+  return pack_bf16x2(lo, hi);
+}
+
+// y = (x + residual) * (mask != 0); residual / mask nullable
+__global__ void __launch_bounds__(256)
+add_mask_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, const uint4* __restrict__ mask,
+                uint4* __restrict__ y, long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = __ldg(x + i);
+    const uint4 b = res ? __ldg(res + i) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 m = mask ? __ldg(mask + i) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+    uint4 o;
+    o.x = add_mask_bf16x2(a.x, b.x, m.x);
+    o.y = add_mask_bf16x2(a.y, b.y, m.y);
+    o.z = add_mask_bf16x2(a.z, b.z, m.z);
+    o.w = add_mask_bf16x2(a.w, b.w, m.w);
+    y[i] = o;
+  }
+}
+
 }  // namespace tdet

@@ -85,12 +85,17 @@ struct ConvGemmParams {
   int Hc, Wc;       // coarse level size (upsample-add)
   int relu;
   int has_res;
-  int ab_fp16;      // operand format of A and B: 1 = fp16, 0 = bf16 (must match, see idesc)
+  int ab_fp16;      // operand format of A: 1 = fp16, 0 = bf16
+  int b_fp16;       // operand format of B (weights); kind::f16 takes the two formats independently
   int out_fp16, res_fp16, coarse_fp16;  // storage formats
   int out_scaled;   // choose a power-of-two output exponent from the bound (else exponent 0)
   const float* scale;
   const float* shift;
   const void* coarse;
+  int coarse_parity;              // 1: add coarse[p/2][q/2] only where p and q are even (dgrad of a
+                                  //    stride-2 1x1 shortcut); 0: nearest-x2 upsample-add (FPN)
+  const void* mask_src;           // nullable 16-bit [M][N] tensor: output is zeroed where it is <= 0
+                                  //    (ReLU backward against the stored forward activation)
   const TensorMeta* in_meta;      // nullable
   const TensorMeta* res_meta;     // nullable
   const TensorMeta* coarse_meta;  // nullable
@@ -294,8 +299,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t fmt = p.ab_fp16 ? kFmtF16 : kFmtBF16;
-    const uint32_t idesc = make_idesc_f16kind(kBM, BN, fmt, fmt);
+    const uint32_t idesc = make_idesc_f16kind(kBM, BN, p.ab_fp16 ? kFmtF16 : kFmtBF16,
+                                              p.b_fp16 ? kFmtF16 : kFmtBF16);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -510,9 +515,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int t = m / p.Wo;
         const int pp = t % p.Ho;
         const int img = t / p.Ho;
-        coarse_row = static_cast<const uint8_t*>(p.coarse) +
-                     (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
+        if (!(p.coarse_parity && ((pp | q) & 1)))
+          coarse_row = static_cast<const uint8_t*>(p.coarse) +
+                       (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
       }
+      const uint8_t* mask_row = nullptr;
+      if (valid && p.mask_src)
+        mask_row = static_cast<const uint8_t*>(p.mask_src) + (pix * p.N + n0) * 2;
 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -533,6 +542,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (coarse_row) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
+          }
+          uint4 rmk[4];
+          if (mask_row) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rmk[j] = ldg_nc_v4(mask_row + (slab * 64 + half * 32 + j * 8) * 2);
           }
           uint4 rres[4];
           if (has_res) {
@@ -585,6 +599,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+          }
+          if (mask_row) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w4[4] = {rmk[j].x, rmk[j].y, rmk[j].z, rmk[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // forward activations are post-ReLU (>= 0): positive <=> non-zero magnitude bits
+                if ((w4[e] & 0x00007FFFu) == 0u) x[8 * j + 2 * e] = 0.0f;
+                if ((w4[e] & 0x7FFF0000u) == 0u) x[8 * j + 2 * e + 1] = 0.0f;
+              }
+            }
           }
           if (valid && p.out_meta) {
 #pragma unroll

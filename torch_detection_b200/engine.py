@@ -101,6 +101,21 @@ def pack_conv_weight(w, dtype=torch.bfloat16):
     return out
 
 
+def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16):
+    """fp32 OIHW parameter (+ folded BN scale per O) -> 16-bit [I][kh][kw][O] with the filter rotated by
+    180 degrees: the B operand of the data-gradient conv (a conv over the output gradient)."""
+    require_cuda(w, "weight")
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    o, i, kh, kw = w.shape
+    out = torch.empty((i, kh, kw, o), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().tdet_pack_dgrad_weight(w.data_ptr(), _ptr(scale), out.data_ptr(), o, i, kh, kw,
+                                                 _TD[dtype], _stream_ptr(w.device)))
+    return out
+
+
 def pack_stem_weight(w):
     """fp32 [64][3][7][7] -> bf16 [64][448] stem operand."""
     require_cuda(w, "weight")
@@ -156,16 +171,21 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
-            coarse=None, relu=False, consts=None, scaled_out=False):
-    """x, y, residual, coarse: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype."""
+            coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False):
+    """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype (or
+    bf16 with an fp16 x: the two MMA operand formats are independent)."""
     n, h, w, cin = x.shape
     cout = wgt.shape[0]
-    if wgt.dtype != x.dtype:
-        raise ValueError("conv weights must be packed in the input tensor's format (%s vs %s)"
+    wgt_bf16 = wgt.dtype == torch.bfloat16 and x.dtype == torch.float16
+    if wgt.dtype != x.dtype and not wgt_bf16:
+        raise ValueError("conv weights must be packed in the input tensor's format or bf16 (%s vs %s)"
                          % (wgt.dtype, x.dtype))
     op = _C.TdetOp()
     op.kind = _C.OP_CONV
-    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0)
+    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
+        (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_WGT_BF16 if wgt_bf16 else 0)
+    if mask is not None:
+        op.mask = mask.ptr
     op.n, op.h, op.w, op.cin = n, h, w, cin
     op.cout, op.kh, op.kw = cout, kh, kw
     op.stride, op.pad, op.dil = stride, pad, dil
@@ -241,6 +261,84 @@ def op_subsample(x, y):
     return op
 
 
+def _op_geom(op, x, cout, kh, kw, stride, pad, dil):
+    n, h, w, cin = x.shape
+    op.n, op.h, op.w, op.cin = n, h, w, cin
+    op.cout, op.kh, op.kw = cout, kh, kw
+    op.stride, op.pad, op.dil = stride, pad, dil
+    op.ho, op.wo = conv_out(h, kh, stride, pad, dil), conv_out(w, kw, stride, pad, dil)
+
+
+def op_wgrad(x, gy, dw, kh, kw, stride, pad, dil=1, scale=None):
+    """x: forward input ``Act``; gy: output-gradient ``Act`` (bf16); dw: fp32 tensor [cout][kh][kw][cin],
+    accumulated."""
+    op = _C.TdetOp()
+    op.kind = _C.OP_WGRAD
+    _op_geom(op, x, gy.shape[3], kh, kw, stride, pad, dil)
+    assert gy.shape == (op.n, op.ho, op.wo, op.cout), (gy.shape, (op.n, op.ho, op.wo, op.cout))
+    assert dw.dtype == torch.float32 and dw.numel() == op.cout * kh * kw * op.cin
+    op.x_dtype, op.gy_dtype = _TD[x.dtype], _TD[gy.dtype]
+    op.x, op.gy, op.dw = x.ptr, gy.ptr, dw.data_ptr()
+    op.x_meta = x.meta
+    op.scale = _ptr(scale)
+    return op
+
+
+def op_dw_unpack(src, dst, cout, cin, kh, kw):
+    op = _C.TdetOp()
+    op.kind = _C.OP_DW_UNPACK
+    op.cout, op.cin, op.kh, op.kw = cout, cin, kh, kw
+    op.x, op.y = src.data_ptr(), dst.data_ptr()
+    return op
+
+
+def op_colsum(x, dw):
+    n, h, w, c = x.shape
+    op = _C.TdetOp()
+    op.kind = _C.OP_COLSUM
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.x_dtype = _TD[x.dtype]
+    op.x, op.dw = x.ptr, dw.data_ptr()
+    return op
+
+
+def _op_eltwise(kind, x, y):
+    n, h, w, c = x.shape
+    op = _C.TdetOp()
+    op.kind = kind
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.cout = c
+    op.ho, op.wo = y.shape[1], y.shape[2]
+    op.x_dtype = op.y_dtype = _TD[x.dtype]
+    op.x, op.y = x.ptr, y.ptr
+    return op
+
+
+def op_sumpool2(x, y):
+    return _op_eltwise(_C.OP_SUMPOOL2, x, y)
+
+
+def op_dilate2(x, y):
+    return _op_eltwise(_C.OP_DILATE2, x, y)
+
+
+def op_add_mask(x, y, residual=None, mask=None):
+    op = _op_eltwise(_C.OP_ADD_MASK, x, y)
+    if residual is not None:
+        op.residual, op.residual_dtype = residual.ptr, _TD[residual.dtype]
+    if mask is not None:
+        op.mask = mask.ptr
+    return op
+
+
+def op_zero(t):
+    op = _C.TdetOp()
+    op.kind = _C.OP_ZERO
+    op.y = t.data_ptr()
+    op.x_stride[0] = t.numel() * t.element_size()
+    return op
+
+
 def run_op(op, device):
     """Runs one op immediately on the current stream of `device` (tests / debugging)."""
     idx = _index(device)
@@ -295,6 +393,12 @@ class Plan:
         with torch.cuda.device(self.index):
             _C.check(_C.lib().tdet_plan_run(self._handle, self._ext_array(ext), self.n_ext,
                                             _stream_ptr(self.device)))
+
+    def run_range(self, ext, first, last):
+        """Runs ops [first, last) only, so the caller can interleave stream work between segments."""
+        with torch.cuda.device(self.index):
+            _C.check(_C.lib().tdet_plan_run_range(self._handle, self._ext_array(ext), self.n_ext, first,
+                                                  last, _stream_ptr(self.device)))
 
     def run_timed(self, ext):
         """Per-launch device milliseconds (CUDA events between launches); measurement only."""
