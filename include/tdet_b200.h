@@ -91,8 +91,7 @@ enum {
   TDET_FLAG_SCALED_OUT = 2, /* y is stored with a device-chosen power-of-two exponent (needs y_meta,
                                x_meta and bound_consts) */
   TDET_FLAG_COARSE_PARITY = 4, /* coarse[i][j] is added at y[2i][2j] only (adjoint of a stride-2 1x1 conv,
-                                  resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */
-  TDET_FLAG_WGT_BF16 = 8    /* wgt is bf16 although x is fp16 (tcgen05 kind::f16 takes one format per
+                                  resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */  TDET_FLAG_WGT_BF16 = 8    /* wgt is bf16 although x is fp16 (tcgen05 kind::f16 takes one format per
                                operand); default: wgt has x's format */
 };
 
@@ -132,7 +131,8 @@ typedef struct tdet_tensor_meta {
  * TDET_OP_SUBSAMPLE y[n][i][j][:] = x[n][2i][2j][:]   (ho = (h-1)/2+1), any 16-bit dtype
  * TDET_OP_WGRAD     x: the conv's forward input [n][h][w][cin] (x_dtype, x_meta); gy: the gradient
  *                   w.r.t. the BN output of that conv (ReLU mask already applied)
- *                   [n][ho][wo][cout] of gy_dtype (BF16);
+ *                   [n][ho][wo][cout] of gy_dtype, which must equal x_dtype (tcgen05 kind::f16 rejects
+ *                   mixed fp16/bf16 operands: measured, illegal instruction);
  *                   dw: fp32 [cout][kh][kw][cin], ACCUMULATED (caller zeroes it):
  *                   dw[co][r][s][ci] += scale[co] * sum_{n,p,q} gy[n][p][q][co] * x[n][p*stride-pad+r*dil][..][ci]
  *                   (scale = folded BN scale or NULL = 1).  geometry fields as for the forward conv.

@@ -27,7 +27,6 @@ BF16, F32, F16 = 0, 1, 2
 FLAG_RELU = 1
 FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4
-FLAG_WGT_BF16 = 8
 
 
 class TdetOp(ctypes.Structure):

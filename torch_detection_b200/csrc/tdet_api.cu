@@ -334,8 +334,8 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   gp.Wc = o.wc;
   gp.has_res = o.residual ? 1 : 0;
   gp.ab_fp16 = o.x_dtype == TDET_F16;
-  const int w_dtype = (o.flags & TDET_FLAG_WGT_BF16) ? static_cast<int>(TDET_BF16) : o.x_dtype;
-  gp.b_fp16 = w_dtype == TDET_F16;
+  const int w_dtype = o.x_dtype;  // tcgen05 kind::f16 needs A and B in ONE format (mixing traps)
+  gp.b_fp16 = gp.ab_fp16;
   if (o.cout % 256 == 0) {
     l.bn = 256;
     l.stages = o.residual ? 3 : 4;
@@ -496,7 +496,8 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
   if (o.ho != out_dim(o.h, o.kh, o.stride, o.pad, o.dil) || o.wo != out_dim(o.w, o.kw, o.stride, o.pad, o.dil))
     return fail(TDET_ERR_INVALID_ARGUMENT, "wgrad output size %dx%d inconsistent with geometry", o.ho, o.wo);
   if (!o.x || !o.gy || !o.dw) return fail(TDET_ERR_INVALID_ARGUMENT, "wgrad: null tensor pointer");
-  if (!is16(o.x_dtype) || !is16(o.gy_dtype)) return fail(TDET_ERR_INVALID_ARGUMENT, "wgrad: 16-bit operands only");
+  if (!is16(o.x_dtype) || o.gy_dtype != o.x_dtype)
+    return fail(TDET_ERR_INVALID_ARGUMENT, "wgrad: x and gy must share one 16-bit format");
   const long long m_ll = static_cast<long long>(o.n) * o.ho * o.wo;
   if (m_ll <= 0 || m_ll > 0x7FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "M out of range");
   WgradParams& wp = l.wp;

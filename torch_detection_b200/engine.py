@@ -172,18 +172,16 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
             coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False):
-    """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype (or
-    bf16 with an fp16 x: the two MMA operand formats are independent)."""
+    """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype."""
     n, h, w, cin = x.shape
     cout = wgt.shape[0]
-    wgt_bf16 = wgt.dtype == torch.bfloat16 and x.dtype == torch.float16
-    if wgt.dtype != x.dtype and not wgt_bf16:
-        raise ValueError("conv weights must be packed in the input tensor's format or bf16 (%s vs %s)"
+    if wgt.dtype != x.dtype:
+        raise ValueError("conv weights must be packed in the input tensor's format (%s vs %s)"
                          % (wgt.dtype, x.dtype))
     op = _C.TdetOp()
     op.kind = _C.OP_CONV
     op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
-        (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_WGT_BF16 if wgt_bf16 else 0)
+        (_C.FLAG_COARSE_PARITY if coarse_parity else 0)
     if mask is not None:
         op.mask = mask.ptr
     op.n, op.h, op.w, op.cin = n, h, w, cin
