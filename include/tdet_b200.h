@@ -91,8 +91,7 @@ enum {
   TDET_FLAG_SCALED_OUT = 2, /* y is stored with a device-chosen power-of-two exponent (needs y_meta,
                                x_meta and bound_consts) */
   TDET_FLAG_COARSE_PARITY = 4, /* coarse[i][j] is added at y[2i][2j] only (adjoint of a stride-2 1x1 conv,
-                                  resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */  TDET_FLAG_WGT_BF16 = 8    /* wgt is bf16 although x is fp16 (tcgen05 kind::f16 takes one format per
-                               operand); default: wgt has x's format */
+                                  resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */
 };
 
 /* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
