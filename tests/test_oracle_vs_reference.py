@@ -88,3 +88,30 @@ def test_golden_fixtures_are_reproducible_from_reference():
             bb.load_state_dict(sd)
         assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
         assert helpers.state_hash(neck.state_dict()) == meta["neck_hash"]
+
+
+@pytest.mark.parametrize("depth", [18, 50])
+def test_gradient_oracle_matches_reference_autograd(depth):
+    """The gradient oracle (oracle/grad_oracle.plain_grads) against autograd through the live reference
+    modules: same ATen forward and backward ops in the same order -> identical parameter gradients."""
+    from oracle import grad_oracle
+    torch.set_num_threads(4)
+    bb, neck = reference_shim.build_pair(depth, seed=7)
+    sd = bb.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(17))
+    bb.load_state_dict(sd)
+    x = torch.randn(2, 3, 64, 96)
+    outs = neck(bb(x))
+    g = torch.Generator().manual_seed(1)
+    grads = [torch.randn(o.shape, generator=g) for o in outs]
+    torch.autograd.backward(list(outs), grads)
+    gb, gn, _, _ = grad_oracle.plain_grads(bb.state_dict(), neck.state_dict(), x, depth, grads,
+                                           train_from_stage=1)
+    ref_b = dict(bb.named_parameters())
+    ref_n = dict(neck.named_parameters())
+    assert len(gn) == 16
+    for k, v in gn.items():
+        assert torch.allclose(v, ref_n[k].grad, rtol=1e-5, atol=1e-7), k
+    assert gb and all(not k.startswith("layer1") for k in gb)
+    for k, v in gb.items():
+        assert torch.allclose(v, ref_b[k].grad, rtol=1e-5, atol=1e-7), k

@@ -87,21 +87,60 @@ class MetaArena(object):
 # operand preparation
 # --------------------------------------------------------------------------------------------
 
-def pack_conv_weight(w, dtype=torch.bfloat16):
+class OperandCache(object):
+    """Derived device operands (packed weights, folded BN, bound constants) of one module.
+
+    Every entry remembers how it is made and which parameters / buffers it depends on; `refresh()`
+    re-derives, IN PLACE, the entries whose dependencies changed (an optimizer step, a
+    load_state_dict), so device pointers -- and with them the compiled plans and their TMA
+    descriptors -- stay valid for the life of the module."""
+
+    def __init__(self):
+        self.store = {}
+
+    @staticmethod
+    def _versions(deps):
+        return tuple((p.data_ptr(), p._version) for p in deps)
+
+    def get(self, key, make, deps=()):
+        e = self.store.get(key)
+        if e is None:
+            e = [make(None), make, tuple(deps), self._versions(deps)]
+            self.store[key] = e
+        return e[0]
+
+    def value(self, key):
+        """Existing entry or None (optional operands such as a conv bias)."""
+        e = self.store.get(key)
+        return None if e is None else e[0]
+
+    def refresh(self):
+        n = 0
+        for e in self.store.values():
+            v = self._versions(e[2])
+            if v != e[3]:
+                e[1](e[0])
+                e[3] = v
+                n += 1
+        return n
+
+
+def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
     """fp32 OIHW parameter -> 16-bit [O][kh][kw][I] (tcgen05 B operand rows) in `dtype`."""
     require_cuda(w, "weight")
     w = w.detach()
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     o, i, kh, kw = w.shape
-    out = torch.empty((o, kh, kw, i), dtype=dtype, device=w.device)
+    if out is None:
+        out = torch.empty((o, kh, kw, i), dtype=dtype, device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_conv_weight(w.data_ptr(), out.data_ptr(), o, i, kh, kw,
                                                 _TD[dtype], _stream_ptr(w.device)))
     return out
 
 
-def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16):
+def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16, out=None):
     """fp32 OIHW parameter (+ folded BN scale per O) -> 16-bit [I][kh][kw][O] with the filter rotated by
     180 degrees: the B operand of the data-gradient conv (a conv over the output gradient)."""
     require_cuda(w, "weight")
@@ -109,14 +148,15 @@ def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16):
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     o, i, kh, kw = w.shape
-    out = torch.empty((i, kh, kw, o), dtype=dtype, device=w.device)
+    if out is None:
+        out = torch.empty((i, kh, kw, o), dtype=dtype, device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_dgrad_weight(w.data_ptr(), _ptr(scale), out.data_ptr(), o, i, kh, kw,
                                                  _TD[dtype], _stream_ptr(w.device)))
     return out
 
 
-def pack_stem_weight(w):
+def pack_stem_weight(w, out=None):
     """fp32 [64][3][7][7] -> bf16 [64][448] stem operand."""
     require_cuda(w, "weight")
     w = w.detach()
@@ -124,20 +164,24 @@ def pack_stem_weight(w):
         raise ValueError("stem weight must be (64,3,7,7)")
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
-    out = torch.empty((64, 448), dtype=torch.bfloat16, device=w.device)
+    if out is None:
+        out = torch.empty((64, 448), dtype=torch.bfloat16, device=w.device)
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_stem_weight(w.data_ptr(), out.data_ptr(), _stream_ptr(w.device)))
     return out
 
 
-def fold_bn(bn):
+def fold_bn(bn, out=None):
     """eval-mode nn.BatchNorm2d -> (scale, shift) fp32 device vectors."""
     g, b, m, v = (t.detach().float().contiguous() for t in
                   (bn.weight, bn.bias, bn.running_mean, bn.running_var))
     require_cuda(g, "BatchNorm parameters")
     ch = g.numel()
-    scale = torch.empty(ch, dtype=torch.float32, device=g.device)
-    shift = torch.empty(ch, dtype=torch.float32, device=g.device)
+    if out is None:
+        scale = torch.empty(ch, dtype=torch.float32, device=g.device)
+        shift = torch.empty(ch, dtype=torch.float32, device=g.device)
+    else:
+        scale, shift = out
     with torch.cuda.device(g.device):
         _C.check(_C.lib().tdet_fold_bn(g.data_ptr(), b.data_ptr(), m.data_ptr(), v.data_ptr(),
                                        ctypes.c_float(bn.eps), scale.data_ptr(), shift.data_ptr(),
@@ -145,11 +189,12 @@ def fold_bn(bn):
     return scale, shift
 
 
-def bound_consts(w_packed, scale, shift):
+def bound_consts(w_packed, scale, shift, out=None):
     """{G, max|shift|} with |conv(x)*scale + shift| <= G*max|x| + max|shift| (device, fp32[2])."""
     cout = w_packed.shape[0]
     k = w_packed.numel() // cout
-    out = torch.empty(2, dtype=torch.float32, device=w_packed.device)
+    if out is None:
+        out = torch.empty(2, dtype=torch.float32, device=w_packed.device)
     with torch.cuda.device(w_packed.device):
         _C.check(_C.lib().tdet_conv_bound_consts(w_packed.data_ptr(), _TD[w_packed.dtype], _ptr(scale),
                                                  _ptr(shift), cout, k, out.data_ptr(),

@@ -21,7 +21,7 @@ import os
 import torch
 import torch.nn as nn
 
-from ... import engine
+from ... import engine, training
 from ...registry import BACKBONES
 from ..utils import (conv1x1_group, conv3x3_group, conv7x7_group, norm_layer, kaiming_init,
                      constant_init, load_checkpoint)
@@ -201,18 +201,16 @@ class ResNet(nn.Module):
                     "only, as in the reference's configs): call .eval() or .train() with "
                     "bn_eval=True first")
 
-    def _param_key(self, device):
-        return (device,) + tuple((p.data_ptr(), p._version) for p in self.parameters()) + \
-            tuple((b.data_ptr(), b._version) for b in self.buffers())
-
     def _get_operands(self, device):
         """Lazy cache of derived operands (packed weights per format, folded BN vectors, bound
-        constants); dropped together with all plans whenever a parameter or buffer changes."""
-        key = self._param_key(device)
-        if self._operands is None or key != self._operand_key:
-            self._operands = _OperandCache()
-            self._operand_key = key
+        constants).  When a parameter or buffer changes the affected entries are re-derived in place
+        (engine.OperandCache.refresh): device pointers, hence the compiled plans, stay valid."""
+        if self._operands is None or self._operand_key != device:
+            self._operands = engine.OperandCache()
+            self._operand_key = device
             self._plans = {}
+        else:
+            self._operands.refresh()
         return self._operands
 
     def _segments(self, n):
@@ -231,8 +229,12 @@ class ResNet(nn.Module):
                 segs.append(([i], c))
         return segs
 
-    def _build_plan(self, x, cache):
+    def _build_plan(self, x, cache, train_from=None):
         """Compiles the topology for one input geometry into tdet_ops.
+
+        train_from (training path): index of the first trainable stage.  Activations are then plain
+        bf16 (the wgrad MMA needs the saved input and the bf16 gradient in one format), nothing from
+        that stage on is recycled, and the per-block records the backward plan needs are returned.
 
         Internal activations are fp16 significands with a per-tensor power-of-two exponent chosen on
         the device (TDET_FLAG_SCALED_OUT); stage outputs are plain bf16 (they are what the module
@@ -240,25 +242,30 @@ class ResNet(nn.Module):
         so each conv's weights are packed in its input's format."""
         n, _, h, w = x.shape
         dev = x.device
-        internal = INTERNAL_DTYPE
+        train = train_from is not None
+        internal = torch.bfloat16 if train else INTERNAL_DTYPE
         scaled = internal == torch.float16
         ops = []
         pool = _BufferPool(dev)
-        segs = self._segments(n)
+        segs = [(list(range(len(self.res_layers))), n)] if train else self._segments(n)
+        records = []
         max_chunks = max((n + c - 1) // c for _, c in segs)
         n_meta = 8 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
         meta = engine.MetaArena(n_meta, dev)
 
         def new_act(shape, dtype):
-            return engine.Act(pool.get(shape), shape, dtype, meta.new())
+            return engine.Act(pool.get(shape), shape, dtype, None if train else meta.new())
 
         def conv(name, module, bn, src, dst, residual=None, relu=True):
             k = module.kernel_size[0]
-            wgt = cache.get((name, "w", src.dtype), lambda: engine.pack_conv_weight(module.weight, src.dtype))
-            sc, sh = cache.get((name, "bn"), lambda: engine.fold_bn(bn))
+            wgt = cache.get((name, "w", src.dtype),
+                            lambda out: engine.pack_conv_weight(module.weight, src.dtype, out=out),
+                            deps=(module.weight,))
+            sc, sh = cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))
             is_scaled = scaled and dst.dtype == torch.float16
             consts = cache.get((name, "consts", src.dtype),
-                               lambda: engine.bound_consts(wgt, sc, sh)) if is_scaled else None
+                               lambda out: engine.bound_consts(wgt, sc, sh, out=out),
+                               deps=(module.weight,) + _bn_deps(bn)) if is_scaled else None
             ops.append(engine.op_conv(src, wgt, dst, k, k, module.stride[0], module.padding[0],
                                       module.dilation[0], scale=sc, shift=sh, residual=residual,
                                       relu=relu, consts=consts, scaled_out=is_scaled))
@@ -284,7 +291,7 @@ class ResNet(nn.Module):
                 outs.append(t)
             else:
                 t = pool.get((n, sh_, sw_, sc_))
-            boundary.append((t, meta.new()))
+            boundary.append((t, None if train else meta.new()))
 
         def boundary_act(li, i0, cn):
             t, m = boundary[li]
@@ -296,13 +303,18 @@ class ResNet(nn.Module):
                 cn = min(chunk, n - i0)
                 if stages[0] == 0:
                     staged = pool.get((cn,) + engine.stem_staging_dims(ho, wo) + (4,))
-                    staged_meta = meta.new()
+                    staged_meta = None if train else meta.new()
                     ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta))
                     stem_out = new_act((cn, ho, wo, 64), internal)
-                    stem_w = cache.get(("conv1", "w"), lambda: engine.pack_stem_weight(self.conv1.weight))
-                    sc, sh = cache.get(("conv1", "bn"), lambda: engine.fold_bn(getattr(self, self.norm_name)))
+                    stem_bn = getattr(self, self.norm_name)
+                    stem_w = cache.get(("conv1", "w"),
+                                       lambda out: engine.pack_stem_weight(self.conv1.weight, out=out),
+                                       deps=(self.conv1.weight,))
+                    sc, sh = cache.get(("conv1", "bn"), lambda out: engine.fold_bn(stem_bn, out=out),
+                                       deps=_bn_deps(stem_bn))
                     stem_consts = cache.get(("conv1", "consts"),
-                                            lambda: engine.bound_consts(stem_w, sc, sh)) if scaled else None
+                                            lambda out: engine.bound_consts(stem_w, sc, sh, out=out),
+                                            deps=(self.conv1.weight,) + _bn_deps(stem_bn)) if scaled else None
                     ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh,
                                               x_meta=staged_meta, consts=stem_consts, scaled_out=scaled))
                     pool.release(staged)
@@ -334,6 +346,8 @@ class ResNet(nn.Module):
                         nconv = len(unit.kernel_sizes)
                         src = cur
                         temps = []
+                        keep = train and li >= train_from
+                        acts = []
                         for ci, k in enumerate(unit.kernel_sizes):
                             module = getattr(unit, "conv%d" % (ci + 1))
                             oh = engine.conv_out(src.shape[1], k, module.stride[0], module.padding[0],
@@ -350,19 +364,34 @@ class ResNet(nn.Module):
                             conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src,
                                  dst, residual=residual if final else None)
                             src = dst
-                        for t in temps:
-                            pool.release(t.buf)
+                            acts.append(dst)
+                        if keep:
+                            # saved for backward: block input, every conv output (ReLU masks + wgrad operands)
+                            records.append(dict(li=li, bi=bi, pre=pre, unit=unit, xin=cur, acts=acts,
+                                                last=last))
+                        else:
+                            for t in temps:
+                                pool.release(t.buf)
+                            if cur_pooled:
+                                pool.release(cur.buf)
                         if shortcut is not None:
                             pool.release(shortcut.buf)
-                        if cur_pooled:
-                            pool.release(cur.buf)
                         cur = src
                         cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
         plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers], dev, meta=meta)
+        if train:
+            return plan, [tuple(o.shape) for o in outs], records, boundary, geo
         return plan, [tuple(o.shape) for o in outs]
 
     def forward(self, x):
         self._check_supported(x)
+        if self.training and torch.is_grad_enabled():
+            params = self._trainable_weights()
+            if params:
+                outs = training.PlanFunction.apply(self, 1, x, *params)
+                if x.dtype == torch.float32:
+                    outs = [_upcast(o) for o in outs]
+                return outs[0] if len(outs) == 1 else tuple(outs)
         cache = self._get_operands(x.device)
         key = (tuple(x.shape), x.dtype, tuple(x.stride()), x.device, INTERNAL_DTYPE)
         entry = self._plans.get(key)
@@ -378,6 +407,219 @@ class ResNet(nn.Module):
             outs = [_upcast(o) for o in outs]
         return outs[0] if len(outs) == 1 else tuple(outs)
 
+    # ------------------------------------------------------------------ training path (config 4)
+    def set_grad_sync(self, sync):
+        """Attach a ``training.BucketAllReduce``: backward then all-reduces one flat fp32 bucket per
+        stage (deepest first) as soon as that stage's wgrad kernels are enqueued."""
+        self._grad_sync = sync
+
+    def _trainable_weights(self):
+        """Conv weights that get gradients, in module order.  Supported configuration = the
+        reference's detector configs: frozen stem (frozen_stages >= 0), frozen BN affine parameters
+        (bn_frozen=True), a frozen prefix of stages and a fully trainable suffix."""
+        stem_norm = getattr(self, self.norm_name)
+        if any(p.requires_grad for p in list(self.conv1.parameters()) + list(stem_norm.parameters())):
+            raise NotImplementedError(
+                "training the stem (conv1/bn1) is not on the B200 path: use frozen_stages >= 0 and "
+                "call .train() (reference configs freeze the stem and stage 1)")
+        first = None
+        params = []
+        for li, lname in enumerate(self.res_layers):
+            stage = getattr(self, lname)
+            convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
+            flags = [m.weight.requires_grad for m in convs]
+            for m in stage.modules():
+                if isinstance(m, nn.BatchNorm2d) and any(p.requires_grad for p in m.parameters()) and any(flags):
+                    raise NotImplementedError(
+                        "BatchNorm affine gradients are not on the B200 path: build the backbone with "
+                        "bn_frozen=True (frozen BN, as the reference's configs do)")
+            if any(flags):
+                if not all(flags):
+                    raise NotImplementedError("partially frozen stage %s" % lname)
+                if first is None:
+                    first = li
+                params.extend(m.weight for m in convs)
+            elif first is not None:
+                raise NotImplementedError("frozen stage %s after a trainable one" % lname)
+        self._train_from = first
+        return params
+
+    def _train_forward(self, inputs, params):
+        (x,) = inputs
+        cache = self._get_operands(x.device)
+        key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from)
+        entry = self._plans.get(key)
+        if entry is None:
+            entry = self._build_plan(x, cache, train_from=self._train_from)
+            self._plans[key] = entry
+        plan, out_shapes, records, boundary, geo = entry
+        outs = [torch.empty(s, dtype=torch.bfloat16, device=x.device,
+                            memory_format=torch.channels_last) for s in out_shapes]
+        plan.run([x] + outs)
+        self._last_run = (plan, [x] + outs)
+        self._train_serial = getattr(self, "_train_serial", 0) + 1
+        state = dict(key=key, outs=outs, params=list(params), serial=self._train_serial, x=x)
+        return outs, state
+
+    def _build_bwd_plan(self, state, cache):
+        """Backward plan for the saved forward `state`: stages deepest first, blocks last to first."""
+        plan, out_shapes, records, boundary, geo = self._plans[state["key"]]
+        dev = state["x"].device
+        outs = state["outs"]
+        n = state["x"].shape[0]
+        bb = training.BackwardBuilder(dev, cache)
+        out_pos = {li: i for i, li in enumerate(sorted(self.out_indices))}
+        g_ext = [engine.nhwc_empty(*_nhwc_shape(o), dev) for o in outs]  # placeholders, re-bound per run
+
+        def stage_act(li):
+            """Forward output of stage li as an Act (an ext output or a static boundary buffer)."""
+            sh_, sw_, sc_ = geo[li]
+            if li in out_pos:
+                return engine.Act(outs[out_pos[li]], (n, sh_, sw_, sc_), torch.bfloat16)
+            return engine.Act(boundary[li][0], (n, sh_, sw_, sc_), torch.bfloat16)
+
+        def scale_of(name, bn):
+            return cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))[0]
+
+        nst = len(self.res_layers)
+        first = self._train_from
+        buckets = []
+        segments = []  # (first op, last op, bucket index)
+        by_stage = {}
+        for r in records:
+            by_stage.setdefault(r["li"], []).append(r)
+        if (nst - 1) not in out_pos:
+            raise NotImplementedError("training needs the last stage among out_indices")
+        g_cur = None  # masked gradient w.r.t. the output of the block being processed
+        for li in range(nst - 1, first - 1, -1):
+            seg_start = len(bb.ops)
+            stage = getattr(self, self.res_layers[li])
+            convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
+            bucket = training.GradBucket([m.weight for m in convs], dev)
+            buckets.append(bucket)
+            blocks = by_stage[li]
+            if li == nst - 1:
+                # gradient of the top stage output arrives from autograd only: apply its ReLU mask
+                top = stage_act(li)
+                g_cur = bb.new_act(top.shape)
+                bb.ops.append(engine.op_add_mask(engine.act_of(g_ext[out_pos[li]]), g_cur, mask=top))
+            for r in reversed(blocks):
+                unit, pre, xin, acts = r["unit"], r["pre"], r["xin"], r["acts"]
+                nconv = len(unit.kernel_sizes)
+                gM = g_cur
+                g = gM
+                for ci in range(nconv - 1, -1, -1):
+                    module = getattr(unit, "conv%d" % (ci + 1))
+                    name = pre + "conv%d" % (ci + 1)
+                    sc = scale_of(name, getattr(unit, unit.norm_names[ci]))
+                    x_ci = xin if ci == 0 else acts[ci - 1]
+                    bb.wgrad(name, module, sc, x_ci, g, bucket.view(bucket.index_of(module.weight)))
+                    if ci > 0:
+                        g_next = bb.dgrad(name, module, sc, g, acts[ci - 1].shape, mask=acts[ci - 1],
+                                          deps=_bn_deps(getattr(unit, unit.norm_names[ci])))
+                        if g is not gM:
+                            bb.release(g)
+                        g = g_next
+                ds = unit.downsample
+                if ds is not None:
+                    name = pre + "downsample"
+                    sc_ds = scale_of(name, ds[1])
+                    bb.wgrad(name, ds[0], sc_ds, xin, gM, bucket.view(bucket.index_of(ds[0].weight)))
+                # gradient w.r.t. the block input: needed unless the producer is frozen
+                is_first_block = r["bi"] == 0
+                need_gin = not (is_first_block and li == first)
+                g_in = None
+                if need_gin:
+                    module = unit.conv1
+                    name = pre + "conv1"
+                    sc = scale_of(name, getattr(unit, unit.norm_names[0]))
+                    residual, coarse, gd = None, None, None
+                    if ds is not None:
+                        name_ds = pre + "downsample"
+                        wd = bb.dgrad_weight(name_ds, ds[0], scale_of(name_ds, ds[1]), deps=_bn_deps(ds[1]))
+                        s_ds = ds[0].stride[0]
+                        if s_ds == 1:
+                            gd = bb.new_act(xin.shape)
+                        elif s_ds == 2:
+                            gd = bb.new_act((xin.shape[0], gM.shape[1], gM.shape[2], xin.shape[3]))
+                        else:
+                            raise NotImplementedError("shortcut stride %d" % s_ds)
+                        bb.ops.append(engine.op_conv(gM, wd, gd, 1, 1, 1, 0, 1))
+                        if s_ds == 1:
+                            residual = gd
+                        else:
+                            coarse = gd
+                    else:
+                        residual = gM
+                    merged = None
+                    if is_first_block and (li - 1) in out_pos:
+                        # the stage input is a returned feature map: add the gradient autograd hands in
+                        ext = engine.act_of(g_ext[out_pos[li - 1]])
+                        if residual is None:
+                            residual = ext
+                        else:
+                            merged = bb.new_act(xin.shape)
+                            bb.ops.append(engine.op_add_mask(residual, merged, residual=ext))
+                            residual = merged
+                    g_in = bb.dgrad(name, module, sc, g, xin.shape, residual=residual, coarse=coarse, mask=xin,
+                                    deps=_bn_deps(getattr(unit, unit.norm_names[0])))
+                    bb.release(gd)
+                    bb.release(merged)
+                if g is not gM:
+                    bb.release(g)
+                bb.release(gM)
+                g_cur = g_in
+            segments.append([seg_start, len(bb.ops), len(buckets) - 1])
+        ops, shift = bb.finalize()
+        # every bucket is re-zeroed at the start of the run (1x1 wgrads accumulate straight into it)
+        head = [engine.op_zero(b.flat) for b in buckets]
+        ops = head + ops
+        shift += len(head)
+        segments = [(a + shift, b + shift, k) for a, b, k in segments]
+        segments[0] = (0, segments[0][1], segments[0][2])
+        ext = g_ext + [outs[out_pos[li]] for li in sorted(out_pos)]
+        bplan = engine.Plan(ops, ext, [cache, bb.buffers, bb.acc_ws, [b.flat for b in buckets]], dev)
+        return bplan, buckets, segments
+
+    def _train_backward(self, state, gouts):
+        if state["serial"] != getattr(self, "_train_serial", 0):
+            raise RuntimeError("ResNet backward after a newer training forward of the same module: the "
+                               "saved activations live in the plan's static buffers (one forward per backward)")
+        cache = self._get_operands(state["x"].device)
+        bkey = ("bwd",) + state["key"]
+        entry = self._plans.get(bkey)
+        if entry is None:
+            entry = self._build_bwd_plan(state, cache)
+            self._plans[bkey] = entry
+        bplan, buckets, segments = entry
+        outs = state["outs"]
+        gs = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
+        ext = gs + outs
+        sync = getattr(self, "_grad_sync", None)
+        reduced = []
+        for a, b, k in segments:
+            if sync is not None:
+                sync.guard(buckets[k].flat)
+            bplan.run_range(ext, a, b)
+            # the plan's accumulators are reused by the next backward: autograd gets a copy, which is
+            # made (and all-reduced) on the side stream while the next segment computes
+            reduced.append(sync.reduce(buckets[k].flat) if sync is not None else buckets[k].flat.clone())
+        if sync is not None:
+            sync.module_done()
+        self._last_bwd_run = (bplan, ext)
+        lookup = {}
+        for (a, b, k), flat in zip(segments, reduced):
+            bucket = buckets[k]
+            for i, p in enumerate(bucket.params):
+                lookup[id(p)] = flat[bucket.offsets[i]:bucket.offsets[i] + p.numel()].view(p.shape)
+        grads = [lookup[id(p)] for p in state["params"]]
+        return [None], grads
+
+
+def _nhwc_shape(t):
+    n, c, h, w = t.shape
+    return n, h, w, c
+
 
 # Storage format of the backbone's internal activations: float16 = fp16 significand + per-tensor
 # power-of-two exponent (default; ~8x lower rounding error than bf16 at the same tensor-core rate),
@@ -389,14 +631,8 @@ INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16")
 DEFAULT_CHUNKS = "0"
 
 
-class _OperandCache(object):
-    def __init__(self):
-        self.store = {}
-
-    def get(self, key, make):
-        if key not in self.store:
-            self.store[key] = make()
-        return self.store[key]
+def _bn_deps(bn):
+    return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
 
 
 def _upcast(t):

@@ -16,7 +16,7 @@ merged lateral is written exactly once.  Like the reference, mismatching pyramid
 import torch
 import torch.nn as nn
 
-from ... import engine
+from ... import engine, training
 from ...registry import NECKS
 from ..utils import ConvModule, xavier_init, constant_init
 
@@ -75,19 +75,25 @@ class FPN(nn.Module):
 
     # ------------------------------------------------------------------ B200 execution
     def _get_operands(self, device):
-        key = (device,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._operands is not None and key == self._operand_key:
+        """Packed bf16 weights and fp32 biases; re-derived in place when a parameter changes
+        (engine.OperandCache), so plans and their TMA descriptors survive optimizer steps."""
+        if self._operands is not None and self._operand_key == device:
+            self._operands.refresh()
             return self._operands
-        ops = {}
+        cache = engine.OperandCache()
         for kind, convs in (("lat", self.lateral_convs), ("out", self.fpn_convs)):
             for j, cm in enumerate(convs):
-                ops["%s%d.w" % (kind, j)] = engine.pack_conv_weight(cm.conv.weight)
-                ops["%s%d.b" % (kind, j)] = cm.conv.bias.detach().float().contiguous() \
-                    if cm.conv.bias is not None else None
-        self._operands = ops
-        self._operand_key = key
+                conv = cm.conv
+                cache.get("%s%d.w" % (kind, j),
+                          lambda out, conv=conv: engine.pack_conv_weight(conv.weight, out=out),
+                          deps=(conv.weight,))
+                if conv.bias is not None:
+                    cache.get("%s%d.b" % (kind, j),
+                              lambda out, conv=conv: _bias_copy(conv.bias, out), deps=(conv.bias,))
+        self._operands = cache
+        self._operand_key = device
         self._plans = {}
-        return ops
+        return cache
 
     def _build_plan(self, feats, operands):
         dev = feats[0].device
@@ -110,15 +116,15 @@ class FPN(nn.Module):
             nb, h, w, c = shapes[j]
             lats[j] = engine.Act(torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev),
                                  (nb, h, w, co), torch.bfloat16)
-            ops.append(engine.op_conv(srcs[j], operands["lat%d.w" % j], lats[j], 1, 1, 1, 0, 1,
-                                      shift=operands["lat%d.b" % j],
+            ops.append(engine.op_conv(srcs[j], operands.value("lat%d.w" % j), lats[j], 1, 1, 1, 0, 1,
+                                      shift=operands.value("lat%d.b" % j),
                                       coarse=lats[j + 1] if j < nl - 1 else None))
         outs = []
         for j in range(nl):
             nb, h, w, _ = shapes[j]
             o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
-            ops.append(engine.op_conv(lats[j], operands["out%d.w" % j], o, 3, 3, 1, 1, 1,
-                                      shift=operands["out%d.b" % j]))
+            ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), o, 3, 3, 1, 1, 1,
+                                      shift=operands.value("out%d.b" % j)))
             outs.append(o)
         if self.num_outs > nl:
             if not self.add_extra_convs:
@@ -136,13 +142,14 @@ class FPN(nn.Module):
                     # the reference applies ReLU *in place* to P_j before the next extra conv
                     # (fpn.py:123-124), so every extra level that feeds another one is returned
                     # post-ReLU: fold that ReLU into the producing conv's epilogue.
-                    ops.append(engine.op_conv(src, operands["out%d.w" % j], o, 3, 3, 2, 1, 1,
-                                              shift=operands["out%d.b" % j],
+                    ops.append(engine.op_conv(src, operands.value("out%d.w" % j), o, 3, 3, 2, 1, 1,
+                                              shift=operands.value("out%d.b" % j),
                                               relu=(j < self.num_outs - 1)))
                     outs.append(o)
                     src = o
         ext = list(feats) + [o.buf for o in outs]
         plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats]], dev)
+        plan.lats = lats  # merged laterals: the saved activations of the training path
         return plan, [tuple(o.buf.shape) for o in outs]
 
     @staticmethod
@@ -158,6 +165,15 @@ class FPN(nn.Module):
 
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)
+        if self.training and torch.is_grad_enabled() and (
+                any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs)):
+            if self.add_extra_convs and self.num_outs > self.backbone_end_level - self.start_level:
+                raise NotImplementedError("training with add_extra_convs=True is not on the B200 path yet")
+            params = list(self.parameters())
+            return tuple(training.PlanFunction.apply(self, len(inputs), *(list(inputs) + params)))
+        return self._forward_infer(inputs)
+
+    def _forward_infer(self, inputs):
         want_fp32 = all(t.dtype == torch.float32 for t in inputs)
         feats = [self._as_bf16_nhwc(t) for t in inputs]
         for t, c in zip(feats, self.in_channels):
@@ -175,6 +191,120 @@ class FPN(nn.Module):
                 for s in out_shapes]
         plan.run(feats + outs)
         self._last_run = (plan, feats + outs)  # for profiling tools (bench.py)
+        self._last_feats = feats
         if want_fp32:
             outs = [o.float() for o in outs]
         return tuple(outs)
+
+    # ------------------------------------------------------------------ training path (config 4)
+    def set_grad_sync(self, sync):
+        """Attach a ``training.BucketAllReduce``: the neck's gradients form one flat fp32 bucket that is
+        all-reduced as soon as the neck's backward is enqueued (it overlaps the whole backbone backward)."""
+        self._grad_sync = sync
+
+    def _train_forward(self, inputs, params):
+        with torch.no_grad():
+            outs = self._forward_infer(inputs)
+        plan, ext = self._last_run
+        self._train_serial = getattr(self, "_train_serial", 0) + 1
+        state = dict(plan=plan, feats=self._last_feats, outs=list(ext[len(self._last_feats):]),
+                     in_dtypes=[t.dtype for t in inputs], params=list(params),
+                     serial=self._train_serial)
+        return outs, state
+
+    def _build_bwd_plan(self, state, operands):
+        plan, feats, outs = state["plan"], state["feats"], state["outs"]
+        dev = feats[0].device
+        used = feats[self.start_level:self.backbone_end_level]
+        nl = len(used)
+        bb = training.BackwardBuilder(dev, operands)
+        convs = [cm.conv for cm in self.lateral_convs] + [cm.conv for cm in self.fpn_convs]
+        plist = []
+        for c in convs:
+            plist.append(c.weight)
+            if c.bias is not None:
+                plist.append(c.bias)
+        bucket = training.GradBucket(plist, dev)
+        g_ext = [engine.nhwc_empty(o.shape[0], o.shape[2], o.shape[3], o.shape[1], dev) for o in outs]
+        gp = [engine.act_of(g) for g in g_ext]
+        # extra levels are stride-2 subsamples of the last output (fpn.py:114-116): scatter them back
+        for j in range(len(outs) - 1, nl - 1, -1):
+            up = bb.new_act(gp[j - 1].shape)
+            bb.ops.append(engine.op_dilate2(gp[j], up))
+            tot = bb.new_act(gp[j - 1].shape)
+            bb.ops.append(engine.op_add_mask(gp[j - 1], tot, residual=up))
+            bb.release(up)
+            gp[j - 1] = tot
+        d_feats = [engine.nhwc_empty(t.shape[0], t.shape[2], t.shape[3], t.shape[1], dev) for t in used]
+        pooled = None
+        for j in range(nl):
+            lat, out = self.lateral_convs[j].conv, self.fpn_convs[j].conv
+            L = plan.lats[j]
+            # output conv: dW, db, and dL_j = dgrad(dP_j) + 2x2 sum-pool of the finer level's dL
+            bb.wgrad("out%d" % j, out, None, L, gp[j], bucket.view(bucket.index_of(out.weight)))
+            if out.bias is not None:
+                bb.ops.append(engine.op_colsum(gp[j], bucket.view(bucket.index_of(out.bias))))
+            dL = bb.dgrad("out%d" % j, out, None, gp[j], L.shape, residual=pooled)
+            bb.release(pooled)
+            # lateral conv
+            bb.wgrad("lat%d" % j, lat, None, engine.act_of(used[j]), dL,
+                     bucket.view(bucket.index_of(lat.weight)))
+            if lat.bias is not None:
+                bb.ops.append(engine.op_colsum(dL, bucket.view(bucket.index_of(lat.bias))))
+            wd = bb.dgrad_weight("lat%d" % j, lat, None)
+            bb.ops.append(engine.op_conv(dL, wd, engine.act_of(d_feats[j]), 1, 1, 1, 0, 1))
+            if j + 1 < nl:
+                pooled = bb.new_act(plan.lats[j + 1].shape)
+                bb.ops.append(engine.op_sumpool2(dL, pooled))
+            else:
+                pooled = None
+            bb.release(dL)
+        ops, _ = bb.finalize()
+        ops = [engine.op_zero(bucket.flat)] + ops
+        ext = g_ext + list(feats) + d_feats
+        bplan = engine.Plan(ops, ext, [operands, bb.buffers, bb.acc_ws, bucket.flat], dev)
+        return bplan, bucket
+
+    def _train_backward(self, state, gouts):
+        if state["serial"] != getattr(self, "_train_serial", 0):
+            raise RuntimeError("FPN backward after a newer training forward of the same module "
+                               "(one forward per backward: saved laterals live in the plan)")
+        feats, outs = state["feats"], state["outs"]
+        dev = feats[0].device
+        operands = self._get_operands(dev)
+        key = ("bwd", id(state["plan"]))
+        entry = self._plans.get(key)
+        if entry is None:
+            entry = self._build_bwd_plan(state, operands)
+            self._plans[key] = entry
+        bplan, bucket = entry
+        gs = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
+        used = feats[self.start_level:self.backbone_end_level]
+        d_feats = [torch.empty_like(t, memory_format=torch.channels_last) for t in used]
+        ext = gs + list(feats) + d_feats
+        sync = getattr(self, "_grad_sync", None)
+        if sync is not None:
+            sync.guard(bucket.flat)
+        bplan.run(ext)
+        self._last_bwd_run = (bplan, ext)
+        if sync is not None:
+            flat = sync.reduce(bucket.flat)
+            sync.module_done()
+        else:
+            flat = bucket.flat.clone()
+        lookup = {id(p): flat[bucket.offsets[i]:bucket.offsets[i] + p.numel()].view(p.shape)
+                  for i, p in enumerate(bucket.params)}
+        g_params = [lookup[id(p)] for p in state["params"]]
+        g_inputs = [None] * len(feats)
+        for j, d in enumerate(d_feats):
+            i = self.start_level + j
+            g_inputs[i] = d if state["in_dtypes"][i] == torch.bfloat16 else d.to(state["in_dtypes"][i])
+        return g_inputs, g_params
+
+
+def _bias_copy(bias, out):
+    src = bias.detach().float()
+    if out is None:
+        return src.contiguous().clone()
+    out.copy_(src)
+    return out

@@ -1,0 +1,239 @@
+"""Training path shared by the ResNet and FPN modules (BASELINE.json config 4: frozen/eval BatchNorm,
+frozen stem + stage 1, hand-written dgrad / wgrad implicit-GEMM kernels, bucketed gradient all-reduce).
+
+The reference trains through torch autograd over nn.Conv2d / nn.BatchNorm2d (resnet.py:97-119,
+fpn.py:88-125); here each module owns ONE autograd.Function whose backward runs a pre-compiled plan
+of ``tdet_op`` descriptors on the caller's stream:
+
+    dgrad  = TDET_OP_CONV over the output gradient with the 180-degree-rotated, BN-scale-folded,
+             transposed weights (tdet_pack_dgrad_weight); the ReLU backward of the layer it feeds is
+             the conv's ``mask`` epilogue, residual / shortcut / external gradients are its
+             ``residual`` / ``coarse`` (parity scatter) operands, so every gradient tensor is
+             written exactly once.
+    wgrad  = TDET_OP_WGRAD (pixels are the contraction dimension) into fp32 accumulators that live
+             in one flat bucket per stage -- the all-reduce unit.
+
+Gradient tensors are plain bf16 (tcgen05 needs both MMA operands in one format, and the stage
+outputs that cross module boundaries are bf16), parameter gradients fp32.
+"""
+import torch
+
+from . import engine
+
+
+class BucketAllReduce(object):
+    """Sums (averages) flat gradient buckets across ranks, overlapped with the rest of backward.
+
+    ``reduce(bucket)`` is called by a module's backward as soon as the kernels writing that bucket
+    have been enqueued.  On a side stream that waits for exactly that point of the compute stream
+    the bucket is copied out (the plan re-zeroes its accumulators in the next step) and the copy is
+    all-reduced, so NCCL traffic over NVLink overlaps the remaining dgrad/wgrad kernels; the
+    returned tensor is what the module hands to autograd.  ``finish()`` makes the compute stream
+    wait for every outstanding bucket: modules call it at the end of their backward unless
+    ``defer=True``, in which case the training loop calls it once after ``backward()`` (then even
+    the neck's bucket overlaps the whole backbone backward).  With CPU tensors (gloo; host-logic
+    tests) or a single rank the collective runs inline.
+    """
+
+    def __init__(self, group=None, average=True, defer=False):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.average = average
+        self.defer = defer
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._streams = {}
+        self._pending = []
+        self._copied = {}  # bucket address -> event: its side-stream copy has completed
+        self.buckets_reduced = 0
+        self.bytes_reduced = 0
+
+    def _comm_stream(self, device):
+        s = self._streams.get(device)
+        if s is None:
+            s = torch.cuda.Stream(device=device)
+            self._streams[device] = s
+        return s
+
+    def guard(self, bucket):
+        """Before a plan overwrites `bucket`: wait until the previous step's copy of it is done."""
+        ev = self._copied.pop(bucket.data_ptr(), None)
+        if ev is not None:
+            torch.cuda.current_stream(bucket.device).wait_event(ev)
+
+    def reduce(self, bucket):
+        self.buckets_reduced += 1
+        self.bytes_reduced += bucket.numel() * bucket.element_size()
+        if not bucket.is_cuda:
+            out = bucket.clone()
+            if self.world > 1:
+                self.dist.all_reduce(out, group=self.group)
+                if self.average:
+                    out.div_(self.world)
+            return out
+        main = torch.cuda.current_stream(bucket.device)
+        comm = self._comm_stream(bucket.device)
+        comm.wait_stream(main)
+        with torch.cuda.stream(comm):
+            out = bucket.clone()
+            ev = torch.cuda.Event()
+            ev.record(comm)
+            if self.world > 1:
+                self.dist.all_reduce(out, group=self.group)
+                if self.average:
+                    out.div_(self.world)
+        out.record_stream(main)
+        self._copied[bucket.data_ptr()] = ev
+        self._pending.append((bucket.device, comm))
+        return out
+
+    def finish(self):
+        for device, comm in self._pending:
+            torch.cuda.current_stream(device).wait_stream(comm)
+        self._pending = []
+
+    def module_done(self):
+        if not self.defer:
+            self.finish()
+
+
+class GradBucket(object):
+    """Flat fp32 buffer holding the OIHW gradients of a list of parameters (one all-reduce unit)."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 63) // 64 * 64  # keep every view 256-byte aligned (vector reductions)
+        self.flat = torch.zeros(max(off, 64), dtype=torch.float32, device=device)
+
+    def view(self, i):
+        p = self.params[i]
+        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view(p.shape)
+
+    def index_of(self, param):
+        for i, p in enumerate(self.params):
+            if p is param:
+                return i
+        raise KeyError("parameter not in bucket")
+
+
+class BackwardBuilder(object):
+    """Emits the backward ops of conv layers into one op list, with a liveness-based pool for the
+    gradient tensors and one zero-initialised workspace for the k x k wgrad accumulators."""
+
+    def __init__(self, device, cache):
+        self.device = device
+        self.cache = cache     # operand cache of the owning module (rotated weights live there)
+        self.ops = []
+        self.free = {}
+        self.buffers = []
+        self.acc_jobs = []     # (conv name, cout, cin, kh, kw, destination view) of k x k convs
+        self.acc_ws = None
+
+    # ---- gradient tensors ---------------------------------------------------------------------
+    def new_act(self, shape):
+        numel = 1
+        for s in shape:
+            numel *= s
+        bucket = self.free.get(numel)
+        if bucket:
+            buf = bucket.pop()
+        else:
+            buf = torch.empty(numel, dtype=torch.bfloat16, device=self.device)
+            self.buffers.append(buf)
+        return engine.Act(buf, shape, torch.bfloat16)
+
+    def release(self, act):
+        if act is not None:
+            self.free.setdefault(act.buf.numel(), []).append(act.buf)
+
+    # ---- ops ------------------------------------------------------------------------------------
+    def dgrad_weight(self, name, module, scale, deps=()):
+        """`scale` is the folded-BN scale tensor of the conv (refreshed in place before this entry: the
+        cache keeps insertion order); `deps` = the BatchNorm parameters / buffers it derives from."""
+        return self.cache.get((name, "wd"),
+                              lambda out: engine.pack_dgrad_weight(module.weight, scale, out=out),
+                              deps=(module.weight,) + tuple(deps))
+
+    def dgrad(self, name, module, scale, g, in_shape, residual=None, coarse=None, mask=None, deps=()):
+        """Gradient w.r.t. the input (shape `in_shape`, NHWC) of conv `module` given g = dL/d(BN(conv))."""
+        k = module.kernel_size[0]
+        stride, pad, dil = module.stride[0], module.padding[0], module.dilation[0]
+        wd = self.dgrad_weight(name, module, scale, deps)
+        dx = self.new_act(in_shape)
+        src = g
+        tmp = None
+        if stride == 2:
+            # adjoint of the output subsampling: zero-insertion upsample, then the stride-1 dgrad
+            tmp = self.new_act((in_shape[0], in_shape[1] + 2 * pad - dil * (k - 1),
+                                in_shape[2] + 2 * pad - dil * (k - 1), g.shape[3]))
+            self.ops.append(engine.op_dilate2(g, tmp))
+            src = tmp
+        elif stride != 1:
+            raise NotImplementedError("dgrad for conv stride %d" % stride)
+        self.ops.append(engine.op_conv(src, wd, dx, k, k, 1, dil * (k - 1) - pad, dil, residual=residual,
+                                       coarse=coarse, coarse_parity=coarse is not None, mask=mask))
+        self.release(tmp)
+        return dx
+
+    def wgrad(self, name, module, scale, x, g, dst):
+        """dst: fp32 OIHW view inside a GradBucket."""
+        k = module.kernel_size[0]
+        cout, cin = module.out_channels, module.in_channels
+        stride, pad, dil = module.stride[0], module.padding[0], module.dilation[0]
+        if k == 1:
+            self.ops.append(engine.op_wgrad(x, g, dst, 1, 1, stride, pad, dil, scale=scale))
+        else:
+            self.acc_jobs.append((len(self.ops), name, cout, cin, k, stride, pad, dil, scale, x, g, dst))
+            self.ops.append(None)  # placeholder: resolved once the accumulator workspace exists
+            self.ops.append(None)
+
+    def finalize(self):
+        """Allocates the accumulator workspace, resolves the k x k wgrad ops and prepends its reset."""
+        total = sum(c[2] * c[3] * c[4] * c[4] for c in self.acc_jobs)
+        head = []
+        if total:
+            self.acc_ws = torch.zeros(total, dtype=torch.float32, device=self.device)
+            head.append(engine.op_zero(self.acc_ws))
+            off = 0
+            for (idx, name, cout, cin, k, stride, pad, dil, scale, x, g, dst) in self.acc_jobs:
+                n = cout * cin * k * k
+                acc = self.acc_ws[off:off + n]
+                off += n
+                self.ops[idx] = engine.op_wgrad(x, g, acc, k, k, stride, pad, dil, scale=scale)
+                self.ops[idx + 1] = engine.op_dw_unpack(acc, dst, cout, cin, k, k)
+        return head + self.ops, len(head)
+
+
+def as_grad_nhwc(g, like):
+    """Incoming autograd gradient -> dense NHWC bf16 (zero-copy when it already is)."""
+    if g is None:
+        return torch.zeros_like(like, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    if g.dtype == torch.bfloat16 and g.is_contiguous(memory_format=torch.channels_last):
+        return g
+    return g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+
+
+class PlanFunction(torch.autograd.Function):
+    """autograd bridge: forward/backward are the owning module's compiled plans.
+
+    apply(module, n_inputs, *inputs_then_params) -> tuple of outputs."""
+
+    @staticmethod
+    def forward(ctx, module, n_inputs, *args):
+        inputs, params = args[:n_inputs], args[n_inputs:]
+        outs, state = module._train_forward(inputs, params)
+        ctx.module = module
+        ctx.state = state
+        ctx.n_inputs = n_inputs
+        ctx.n_params = len(params)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        g_inputs, g_params = ctx.module._train_backward(ctx.state, gouts)
+        ctx.state = None
+        return (None, None) + tuple(g_inputs) + tuple(g_params)
