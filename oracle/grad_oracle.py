@@ -9,13 +9,15 @@ restatements, both plain CPU fp32 autograd over the oracle's forward:
                         reference's arithmetic, pinned bit-exact to the reference's forward by
                         tests/test_oracle_vs_reference.py; its backward is ATen's own autograd
                         formulas of the same ops).
-  teacher_forced_grads  the same graph with bf16 rounding placed where the CUDA training path rounds
-                        (conv weights, the image, every stored activation), passed straight through
-                        in backward.  ReLU masks then come from the bf16 forward -- the comparison
-                        SURVEY.md 8(c) calls "teacher-forced": bf16 flips a small fraction of ReLU
-                        decisions relative to fp32, which changes backbone gradients by O(0.1) in
-                        rel-L2 for ANY bf16 implementation (PyTorch's own included), so the gate
-                        for backbone gradients must match masks.
+  teacher_forced_grads  the same graph with every stored activation forced to the value the CUDA
+                        forward stored (downloaded through the modules' saved_activations() test
+                        API) and bf16-rounded conv weights, passed straight through in backward.
+                        ReLU masks and wgrad inputs are then the kernels' own -- the comparison
+                        SURVEY.md 8(c) calls "teacher-forced" / "mask-matched": any bf16 forward
+                        flips ~1% of the ReLU decisions of the fp32 forward (and of any OTHER bf16
+                        forward with a different accumulation order), which moves backbone gradients
+                        by O(0.1) in rel-L2 -- measured here for an independent bf16 emulation:
+                        0.07-0.18 -- for ANY bf16 implementation, PyTorch's own included.
 
 Gradients are returned for every conv weight of the trainable stages (frozen BN: no affine
 gradients; frozen stem / leading stages as in the reference's configs) and all FPN parameters.
@@ -66,57 +68,121 @@ def _ste(t):
     return t + (_r(t) - t).detach()
 
 
-def teacher_forced_grads(bb_sd, neck_sd, x, depth, grad_outs, train_from_stage=1, out_channels=256,
-                         num_outs=5):
+def _force(y, stored, relu):
+    """Forward value := the CUDA path's stored activation, ReLU decision := its sign pattern;
+    backward: the gradient of y under that decision."""
+    stored = stored.float()
+    if relu:
+        y = y * (stored > 0).to(y.dtype)
+    return y + (stored - y).detach()
+
+
+def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs, train_from_stage=1,
+                         out_channels=256, num_outs=5):
+    """fp32 autograd over the reference's graph with every stored activation (and hence every ReLU
+    mask and every conv / wgrad input) forced to the value the CUDA training forward stored:
+    `saved_bb` = ResNet.saved_activations(), `saved_neck` = FPN.saved_activations().  Conv weights are
+    bf16-rounded (straight-through), as the kernels' operands are.  What remains different from the
+    CUDA backward is arithmetic only: bf16 storage of the gradient tensors, the rounding of the
+    BN-scale-folded dgrad weights, fp32 accumulation order."""
     kind, counts = orc.ARCH[depth]
     bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage))
     neck = _leafify(neck_sd, lambda k: True)
 
-    def w(sd, k):
-        return _ste(sd[k])
-
-    def cbn(inp, wkey, bnp, stride=1, pad=0, relu=False, res=None):
-        y = F.conv2d(inp, w(bb, wkey), None, stride, pad)
+    def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None):
+        y = F.conv2d(inp, _ste(bb[wkey]), None, stride, pad)
         scale = bb[bnp + ".weight"] / torch.sqrt(bb[bnp + ".running_var"] + orc.BN_EPS)
         shift = bb[bnp + ".bias"] - bb[bnp + ".running_mean"] * scale
         y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res
-        if relu:
-            y = F.relu(y)
-        return _ste(y)
+        return y if stored is None else _force(y, stored, relu)
 
-    h = cbn(_r(x.float()), "conv1.weight", "bn1", 2, 3, relu=True)
-    h = F.max_pool2d(h, 3, 2, 1)
     feats = []
+    h = None
     for li, nblocks in enumerate(counts):
+        if li < train_from_stage:
+            feats.append(None)
+            continue
         for b in range(nblocks):
             p = "layer%d.%d" % (li + 1, b)
             s = 2 if (b == 0 and li > 0) else 1
+            if h is None:
+                h = saved_bb[p + ".in"].float()  # frozen producer: a constant
             res = h
             if (p + ".downsample.0.weight") in bb:
-                res = cbn(h, p + ".downsample.0.weight", p + ".downsample.1", s, 0)
+                # the shortcut branch is stored in bf16 and consumed by conv3's epilogue
+                res = _ste(cbn(h, p + ".downsample.0.weight", p + ".downsample.1", None, s, 0))
             if kind == "bottleneck":
-                o = cbn(h, p + ".conv1.weight", p + ".bn1", 1, 0, relu=True)
-                o = cbn(o, p + ".conv2.weight", p + ".bn2", s, 1, relu=True)
-                h = cbn(o, p + ".conv3.weight", p + ".bn3", 1, 0, relu=True, res=res)
+                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], 1, 0, relu=True)
+                o = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], s, 1, relu=True)
+                h = cbn(o, p + ".conv3.weight", p + ".bn3", saved_bb[p + ".conv3"], 1, 0, relu=True, res=res)
             else:
-                o = cbn(h, p + ".conv1.weight", p + ".bn1", s, 1, relu=True)
-                h = cbn(o, p + ".conv2.weight", p + ".bn2", 1, 1, relu=True, res=res)
+                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], s, 1, relu=True)
+                h = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], 1, 1, relu=True, res=res)
         feats.append(h)
     n = len(feats)
+    for j in range(n):
+        if feats[j] is None:
+            feats[j] = saved_neck["C%d" % j].float()  # frozen stage output: a constant for the neck
     lats = [None] * n
     for j in range(n - 1, -1, -1):
-        y = F.conv2d(feats[j], w(neck, "lateral_convs.%d.conv.weight" % j),
+        y = F.conv2d(feats[j], _ste(neck["lateral_convs.%d.conv.weight" % j]),
                      neck["lateral_convs.%d.conv.bias" % j])
         if j < n - 1:
             y = y + F.interpolate(lats[j + 1], scale_factor=2, mode="nearest")
-        lats[j] = _ste(y)
-    outs = [_ste(F.conv2d(lats[j], w(neck, "fpn_convs.%d.conv.weight" % j),
-                          neck["fpn_convs.%d.conv.bias" % j], 1, 1)) for j in range(n)]
+        lats[j] = _force(y, saved_neck["lat%d" % j], False)
+    outs = [F.conv2d(lats[j], _ste(neck["fpn_convs.%d.conv.weight" % j]),
+                     neck["fpn_convs.%d.conv.bias" % j], 1, 1) for j in range(n)]
     for _ in range(num_outs - n):
         outs.append(F.max_pool2d(outs[-1], 1, stride=2))
     torch.autograd.backward(list(outs), [g.float() for g in grad_outs])
     gb = {k: v.grad for k, v in bb.items() if v.requires_grad}
     gn = {k: v.grad for k, v in neck.items() if v.requires_grad}
     return gb, gn, feats, outs
+
+
+def oracle_saved_activations(bb_sd, neck_sd, x, depth):
+    """The activations the CUDA training forward stores, computed by the fp32 oracle itself, under the
+    names of ResNet.saved_activations() / FPN.saved_activations().  Forcing the oracle with its own
+    activations must reproduce plain_grads (tests/test_grad_oracle_cpu.py)."""
+    kind, counts = orc.ARCH[depth]
+    saved_bb, saved_neck = {}, {}
+    with torch.no_grad():
+        h = F.conv2d(x.float(), bb_sd["conv1.weight"], None, 2, 3)
+        h = F.relu(orc._bn(bb_sd, "bn1", h))
+        h = F.max_pool2d(h, 3, 2, 1)
+        feats = []
+        for li, nblocks in enumerate(counts):
+            for b in range(nblocks):
+                p = "layer%d.%d" % (li + 1, b)
+                s = 2 if (b == 0 and li > 0) else 1
+                saved_bb[p + ".in"] = h
+                res = h
+                if (p + ".downsample.0.weight") in bb_sd:
+                    res = orc._bn(bb_sd, p + ".downsample.1",
+                                  F.conv2d(h, bb_sd[p + ".downsample.0.weight"], None, s))
+                if kind == "bottleneck":
+                    o = F.relu(orc._bn(bb_sd, p + ".bn1", F.conv2d(h, bb_sd[p + ".conv1.weight"])))
+                    saved_bb[p + ".conv1"] = o
+                    o = F.relu(orc._bn(bb_sd, p + ".bn2", F.conv2d(o, bb_sd[p + ".conv2.weight"], None, s, 1)))
+                    saved_bb[p + ".conv2"] = o
+                    h = F.relu(orc._bn(bb_sd, p + ".bn3", F.conv2d(o, bb_sd[p + ".conv3.weight"])) + res)
+                    saved_bb[p + ".conv3"] = h
+                else:
+                    o = F.relu(orc._bn(bb_sd, p + ".bn1", F.conv2d(h, bb_sd[p + ".conv1.weight"], None, s, 1)))
+                    saved_bb[p + ".conv1"] = o
+                    h = F.relu(orc._bn(bb_sd, p + ".bn2", F.conv2d(o, bb_sd[p + ".conv2.weight"], None, 1, 1)) + res)
+                    saved_bb[p + ".conv2"] = h
+            feats.append(h)
+        n = len(feats)
+        lats = [None] * n
+        for j in range(n - 1, -1, -1):
+            y = F.conv2d(feats[j], neck_sd["lateral_convs.%d.conv.weight" % j],
+                         neck_sd["lateral_convs.%d.conv.bias" % j])
+            if j < n - 1:
+                y = y + F.interpolate(lats[j + 1], scale_factor=2, mode="nearest")
+            lats[j] = y
+            saved_neck["C%d" % j] = feats[j]
+            saved_neck["lat%d" % j] = y
+    return saved_bb, saved_neck

@@ -8,7 +8,9 @@ Gates (bf16 tolerance of north_star, rel-L2 <= 1e-2):
     TEACHER-FORCED oracle (fp32 autograd with bf16 rounding where the kernels round, so ReLU masks
     match);
   * the 16 FPN gradients also vs the plain fp32 oracle (<= 2e-2: the laterals' wgrad operand C_k
-    itself carries the forward's bf16 error);
+    itself carries the training forward's plain-bf16 error of ~1e-2);
+  * local consistency of the training forward: each P level vs an fp32 recomputation from the
+    kernels' own stored laterals (<= 4e-3, one bf16 rounding);
   * reported, not gated: backbone gradients vs the plain fp32 oracle (mask flips; expected 0.1-0.4,
     like PyTorch's own bf16) with their cosine similarity.
 """
@@ -60,14 +62,17 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
     got_b = {k: p.grad.detach().cpu() for k, p in bb.named_parameters() if p.grad is not None}
     got_n = {k: p.grad.detach().cpu() for k, p in neck.named_parameters() if p.grad is not None}
 
-    tb, tn, tf_feats, tf_outs = grad_oracle.teacher_forced_grads(bsd, nsd, x.float(), depth, grads,
+    saved_b, saved_n = bb.saved_activations(), neck.saved_activations()
+    tb, tn, tf_feats, tf_outs = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
                                                                  train_from_stage=frozen)
     pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen)
     assert set(got_b) == set(tb), (sorted(set(got_b) ^ set(tb))[:8])
     assert set(got_n) == set(tn) and len(got_n) == 16
-    # training-mode forward (plain bf16 activations) against its own emulation
-    for a, b in zip(outs, tf_outs):
-        assert orc.rel_l2(a.float(), b) <= 5e-3
+    # the forced forward reproduces the CUDA outputs up to ONE layer of arithmetic (fp32 conv of the
+    # kernels' own stored inputs): every stored tensor is locally consistent with its inputs
+    fwd = [orc.rel_l2(a.float(), b) for a, b in zip(outs, tf_outs)]
+    print("train-mode P levels vs one-layer fp32 recomputation:", ["%.2e" % e for e in fwd])
+    assert max(fwd) <= 4e-3
     errs_n = {k: orc.rel_l2(got_n[k], tn[k]) for k in tn}
     errs_b = {k: orc.rel_l2(got_b[k], tb[k]) for k in tb}
     plain_n = {k: orc.rel_l2(got_n[k], pn[k]) for k in pn}
@@ -113,7 +118,8 @@ def test_second_step_uses_updated_weights(cuda_device):
     torch.autograd.backward(list(outs), [t.to(dev).contiguous(memory_format=torch.channels_last) for t in grads])
     torch.cuda.synchronize()
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
-    tb, tn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, x.float().cpu(), 50, grads)
+    tb, tn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, bb.saved_activations(),
+                                                    neck.saved_activations(), 50, grads)
     for k, p in neck.named_parameters():
         assert orc.rel_l2(p.grad.cpu(), tn[k]) <= GATE, k
     for k, p in bb.named_parameters():

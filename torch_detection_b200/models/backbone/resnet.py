@@ -380,6 +380,8 @@ class ResNet(nn.Module):
                         cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
         plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers], dev, meta=meta)
         if train:
+            # records reference stage outputs through the plan's placeholder tensors: remember which
+            plan.out_placeholders = {id(t): i for i, t in enumerate(outs)}
             return plan, [tuple(o.shape) for o in outs], records, boundary, geo
         return plan, [tuple(o.shape) for o in outs]
 
@@ -444,6 +446,28 @@ class ResNet(nn.Module):
         self._train_from = first
         return params
 
+    def saved_activations(self):
+        """{name: fp32 NCHW CPU tensor} of what the last training forward saved for backward (block
+        inputs ``layerL.B.in`` and every conv's stored output ``layerL.B.convK``).  Test/debug API:
+        it is how the gradient tests teacher-force the oracle with the kernels' own ReLU masks."""
+        plan, out_shapes, records, boundary, geo = self._plans[self._train_state["key"]]
+        outs = self._train_state["outs"]
+
+        def fetch(act):
+            pos = plan.out_placeholders.get(id(act.buf))
+            if pos is not None:
+                return outs[pos].float().cpu()
+            n, h, w, c = act.shape
+            flat = act.buf[act.offset:act.offset + n * h * w * c]
+            return flat.view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()
+
+        saved = {}
+        for r in records:
+            saved[r["pre"] + "in"] = fetch(r["xin"])
+            for ci, a in enumerate(r["acts"]):
+                saved[r["pre"] + "conv%d" % (ci + 1)] = fetch(a)
+        return saved
+
     def _train_forward(self, inputs, params):
         (x,) = inputs
         cache = self._get_operands(x.device)
@@ -459,6 +483,7 @@ class ResNet(nn.Module):
         self._last_run = (plan, [x] + outs)
         self._train_serial = getattr(self, "_train_serial", 0) + 1
         state = dict(key=key, outs=outs, params=list(params), serial=self._train_serial, x=x)
+        self._train_state = state
         return outs, state
 
     def _build_bwd_plan(self, state, cache):
@@ -480,6 +505,14 @@ class ResNet(nn.Module):
 
         def scale_of(name, bn):
             return cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))[0]
+
+        def live(act):
+            """Saved activation as seen by this plan: stage outputs are the forward's returned tensors
+            (external, re-bound per run), everything else sits in the forward plan's static buffers."""
+            pos = plan.out_placeholders.get(id(act.buf))
+            if pos is None:
+                return act
+            return engine.Act(outs[pos], act.shape, act.dtype, None, act.offset)
 
         nst = len(self.res_layers)
         first = self._train_from
@@ -504,7 +537,8 @@ class ResNet(nn.Module):
                 g_cur = bb.new_act(top.shape)
                 bb.ops.append(engine.op_add_mask(engine.act_of(g_ext[out_pos[li]]), g_cur, mask=top))
             for r in reversed(blocks):
-                unit, pre, xin, acts = r["unit"], r["pre"], r["xin"], r["acts"]
+                unit, pre = r["unit"], r["pre"]
+                xin, acts = live(r["xin"]), [live(a) for a in r["acts"]]
                 nconv = len(unit.kernel_sizes)
                 gM = g_cur
                 g = gM

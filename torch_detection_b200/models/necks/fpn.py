@@ -202,6 +202,18 @@ class FPN(nn.Module):
         all-reduced as soon as the neck's backward is enqueued (it overlaps the whole backbone backward)."""
         self._grad_sync = sync
 
+    def saved_activations(self):
+        """{name: fp32 NCHW CPU tensor}: inputs ``C{j}`` and merged laterals ``lat{j}`` of the last training
+        forward (test/debug API, see ResNet.saved_activations)."""
+        state = self._train_state
+        saved = {}
+        used = state["feats"][self.start_level:self.backbone_end_level]
+        for j, (t, l) in enumerate(zip(used, state["plan"].lats)):
+            saved["C%d" % j] = t.float().cpu()
+            n, h, w, c = l.shape
+            saved["lat%d" % j] = l.buf[:n * h * w * c].view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()
+        return saved
+
     def _train_forward(self, inputs, params):
         with torch.no_grad():
             outs = self._forward_infer(inputs)
@@ -210,6 +222,7 @@ class FPN(nn.Module):
         state = dict(plan=plan, feats=self._last_feats, outs=list(ext[len(self._last_feats):]),
                      in_dtypes=[t.dtype for t in inputs], params=list(params),
                      serial=self._train_serial)
+        self._train_state = state
         return outs, state
 
     def _build_bwd_plan(self, state, operands):
