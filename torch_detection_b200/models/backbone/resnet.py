@@ -456,7 +456,7 @@ class ResNet(nn.Module):
         def fetch(act):
             pos = plan.out_placeholders.get(id(act.buf))
             if pos is not None:
-                return outs[pos].float().cpu()
+                return outs[pos].detach().float().cpu()
             n, h, w, c = act.shape
             flat = act.buf[act.offset:act.offset + n * h * w * c]
             return flat.view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()

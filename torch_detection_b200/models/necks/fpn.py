@@ -209,7 +209,7 @@ class FPN(nn.Module):
         saved = {}
         used = state["feats"][self.start_level:self.backbone_end_level]
         for j, (t, l) in enumerate(zip(used, state["plan"].lats)):
-            saved["C%d" % j] = t.float().cpu()
+            saved["C%d" % j] = t.detach().float().cpu()
             n, h, w, c = l.shape
             saved["lat%d" % j] = l.buf[:n * h * w * c].view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()
         return saved
