@@ -68,35 +68,83 @@ def _ste(t):
     return t + (_r(t) - t).detach()
 
 
-def _force(y, stored, relu):
+def _force(y, stored, relu, round_grad=False):
     """Forward value := the CUDA path's stored activation, ReLU decision := its sign pattern;
-    backward: the gradient of y under that decision."""
+    backward: the gradient of y under that decision.  round_grad: the total gradient w.r.t. the
+    stored tensor passes through one bf16 rounding, as the kernel that materialises it does."""
     stored = stored.float()
     if relu:
         y = y * (stored > 0).to(y.dtype)
-    return y + (stored - y).detach()
+    out = y + (stored - y).detach()
+    if round_grad and out.requires_grad:
+        out.register_hook(_r)
+    return out
+
+
+def _tap(t, round_grad):
+    """Identity whose gradient contribution is rounded to bf16 (a branch gradient the kernels store
+    before merging it: shortcut dgrad, 2x2 sum-pooled lateral gradient, dC_k handed to the backbone)."""
+    if not (round_grad and t.requires_grad):
+        return t
+    out = t * 1.0
+    out.register_hook(_r)
+    return out
+
+
+class _ConvBNKernelModel(torch.autograd.Function):
+    """conv + frozen BN with the CUDA path's operand rounding: forward uses bf16(w) and the fp32
+    scale/shift epilogue; the data gradient uses the BN-scale-folded operand bf16(scale * w)
+    (tdet_pack_dgrad_weight); the weight gradient is scale * (g (*) x) in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, shift, stride, pad):
+        ctx.save_for_backward(x, w, scale)
+        ctx.conf = (stride, pad)
+        y = F.conv2d(x, _r(w), None, stride, pad)
+        return y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, scale = ctx.saved_tensors
+        stride, pad = ctx.conf
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.nn.grad.conv2d_input(x.shape, _r(w * scale.view(-1, 1, 1, 1)), g, stride, pad)
+        if ctx.needs_input_grad[1]:
+            gw = torch.nn.grad.conv2d_weight(x, w.shape, g * scale.view(1, -1, 1, 1), stride, pad)
+        return gx, gw, None, None, None, None
 
 
 def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs, train_from_stage=1,
-                         out_channels=256, num_outs=5):
+                         out_channels=256, num_outs=5, kernel_rounding=False):
     """fp32 autograd over the reference's graph with every stored activation (and hence every ReLU
     mask and every conv / wgrad input) forced to the value the CUDA training forward stored:
     `saved_bb` = ResNet.saved_activations(), `saved_neck` = FPN.saved_activations().  Conv weights are
-    bf16-rounded (straight-through), as the kernels' operands are.  What remains different from the
-    CUDA backward is arithmetic only: bf16 storage of the gradient tensors, the rounding of the
-    BN-scale-folded dgrad weights, fp32 accumulation order."""
+    bf16-rounded (straight-through), as the kernels' operands are.
+
+    kernel_rounding=False: the backward is exact fp32 -- what remains different from the CUDA
+        backward is its bf16 storage of gradient tensors and dgrad operands (accumulates as
+        ~sqrt(depth) * 2^-9) plus fp32 accumulation order.
+    kernel_rounding=True: additionally one bf16 rounding at every point where the CUDA backward
+        stores a gradient tensor, and the scale-folded dgrad operand: "rounding hooks placed exactly
+        where the kernels round" (SURVEY.md 8c-2); what remains is fp32 accumulation order only, so
+        this is the tight gate on the kernels' arithmetic."""
     kind, counts = orc.ARCH[depth]
+    kr = kernel_rounding
     bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage))
     neck = _leafify(neck_sd, lambda k: True)
 
-    def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None):
-        y = F.conv2d(inp, _ste(bb[wkey]), None, stride, pad)
+    def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None, round_grad=False):
         scale = bb[bnp + ".weight"] / torch.sqrt(bb[bnp + ".running_var"] + orc.BN_EPS)
         shift = bb[bnp + ".bias"] - bb[bnp + ".running_mean"] * scale
-        y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+        if kr:
+            y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad)
+        else:
+            y = F.conv2d(inp, _ste(bb[wkey]), None, stride, pad)
+            y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res
-        return y if stored is None else _force(y, stored, relu)
+        return y if stored is None else _force(y, stored, relu, round_grad)
 
     feats = []
     h = None
@@ -111,15 +159,18 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
                 h = saved_bb[p + ".in"].float()  # frozen producer: a constant
             res = h
             if (p + ".downsample.0.weight") in bb:
-                # the shortcut branch is stored in bf16 and consumed by conv3's epilogue
-                res = _ste(cbn(h, p + ".downsample.0.weight", p + ".downsample.1", None, s, 0))
+                # the shortcut branch is stored in bf16 and consumed by conv3's epilogue; its data
+                # gradient is stored (bf16) before it is merged into the block-input gradient
+                res = _ste(cbn(_tap(h, kr), p + ".downsample.0.weight", p + ".downsample.1", None, s, 0))
             if kind == "bottleneck":
-                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], 1, 0, relu=True)
-                o = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], s, 1, relu=True)
-                h = cbn(o, p + ".conv3.weight", p + ".bn3", saved_bb[p + ".conv3"], 1, 0, relu=True, res=res)
+                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], 1, 0, relu=True, round_grad=kr)
+                o = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], s, 1, relu=True, round_grad=kr)
+                h = cbn(o, p + ".conv3.weight", p + ".bn3", saved_bb[p + ".conv3"], 1, 0, relu=True, res=res,
+                        round_grad=kr)
             else:
-                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], s, 1, relu=True)
-                h = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], 1, 1, relu=True, res=res)
+                o = cbn(h, p + ".conv1.weight", p + ".bn1", saved_bb[p + ".conv1"], s, 1, relu=True, round_grad=kr)
+                h = cbn(o, p + ".conv2.weight", p + ".bn2", saved_bb[p + ".conv2"], 1, 1, relu=True, res=res,
+                        round_grad=kr)
         feats.append(h)
     n = len(feats)
     for j in range(n):
@@ -127,13 +178,15 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
             feats[j] = saved_neck["C%d" % j].float()  # frozen stage output: a constant for the neck
     lats = [None] * n
     for j in range(n - 1, -1, -1):
-        y = F.conv2d(feats[j], _ste(neck["lateral_convs.%d.conv.weight" % j]),
+        y = F.conv2d(_tap(feats[j], kr), _ste(neck["lateral_convs.%d.conv.weight" % j]),
                      neck["lateral_convs.%d.conv.bias" % j])
         if j < n - 1:
-            y = y + F.interpolate(lats[j + 1], scale_factor=2, mode="nearest")
-        lats[j] = _force(y, saved_neck["lat%d" % j], False)
+            y = y + F.interpolate(_tap(lats[j + 1], kr), scale_factor=2, mode="nearest")
+        lats[j] = _force(y, saved_neck["lat%d" % j], False, kr)
     outs = [F.conv2d(lats[j], _ste(neck["fpn_convs.%d.conv.weight" % j]),
                      neck["fpn_convs.%d.conv.bias" % j], 1, 1) for j in range(n)]
+    if kr and num_outs > n and outs[-1].requires_grad:
+        outs[-1].register_hook(_r)  # dP of the coarsest level + scattered extra-level gradients: stored once
     for _ in range(num_outs - n):
         outs.append(F.max_pool2d(outs[-1], 1, stride=2))
     torch.autograd.backward(list(outs), [g.float() for g in grad_outs])

@@ -5,8 +5,15 @@ backward plans, against the CPU gradient oracle.
 
 Gates (bf16 tolerance of north_star, rel-L2 <= 1e-2):
   * all 16 FPN parameter gradients and every trainable backbone conv-weight gradient vs the
-    TEACHER-FORCED oracle (fp32 autograd with bf16 rounding where the kernels round, so ReLU masks
-    match);
+    TEACHER-FORCED oracle with rounding hooks where the kernels round (grad_oracle
+    kernel_rounding=True: fp32 autograd over the kernels' own stored activations / ReLU masks, one
+    bf16 rounding per stored gradient tensor, scale-folded bf16 dgrad operand).  What is left is
+    fp32 accumulation order, so the gate is tightened to 3e-3 (expected ~1e-3);
+  * the same gradients vs the teacher-forced oracle with an EXACT fp32 backward: gated at 1e-2 for
+    the 16 FPN gradients; for the backbone it is REPORTED and sanity-gated at 4e-2: bf16 storage of
+    the gradient chain accumulates ~sqrt(depth) * 2^-9 (measured 0.7-1.6e-2 on ResNet-50, the same
+    figure the oracle's own rounding model shows against its exact backward) -- DESIGN.md section 7
+    lists the fp16 block-exponent gradient chain that removes it;
   * the 16 FPN gradients also vs the plain fp32 oracle (<= 2e-2: the laterals' wgrad operand C_k
     itself carries the training forward's plain-bf16 error of ~1e-2);
   * local consistency of the training forward: each P level vs an fp32 recomputation from the
@@ -64,7 +71,9 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
 
     saved_b, saved_n = bb.saved_activations(), neck.saved_activations()
     tb, tn, tf_feats, tf_outs = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
-                                                                 train_from_stage=frozen)
+                                                                 train_from_stage=frozen, kernel_rounding=True)
+    xb, xn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
+                                                    train_from_stage=frozen)
     pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen)
     assert set(got_b) == set(tb), (sorted(set(got_b) ^ set(tb))[:8])
     assert set(got_n) == set(tn) and len(got_n) == 16
@@ -77,14 +86,22 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
     errs_b = {k: orc.rel_l2(got_b[k], tb[k]) for k in tb}
     plain_n = {k: orc.rel_l2(got_n[k], pn[k]) for k in pn}
     plain_b = {k: (orc.rel_l2(got_b[k], pb[k]), _cos(got_b[k], pb[k])) for k in pb}
-    print("FPN grads vs teacher-forced: max %.2e ; vs plain fp32: max %.2e" %
-          (max(errs_n.values()), max(plain_n.values())))
-    print("backbone grads (%d) vs teacher-forced: max %.2e median %.2e" %
-          (len(errs_b), max(errs_b.values()), sorted(errs_b.values())[len(errs_b) // 2]))
+    exact_n = {k: orc.rel_l2(got_n[k], xn[k]) for k in xn}
+    exact_b = {k: orc.rel_l2(got_b[k], xb[k]) for k in xb}
+    print("FPN grads vs teacher-forced (kernel rounding): max %.2e ; (exact backward): max %.2e ; vs plain "
+          "fp32: max %.2e" % (max(errs_n.values()), max(exact_n.values()), max(plain_n.values())))
+    print("backbone grads (%d) vs teacher-forced (kernel rounding): max %.2e median %.2e ; (exact backward): "
+          "max %.2e median %.2e" %
+          (len(errs_b), max(errs_b.values()), sorted(errs_b.values())[len(errs_b) // 2],
+           max(exact_b.values()), sorted(exact_b.values())[len(exact_b) // 2]))
     print("backbone grads vs plain fp32 (report only): max rel-L2 %.2e, min cosine %.4f" %
           (max(v[0] for v in plain_b.values()), min(v[1] for v in plain_b.values())))
-    bad = {k: v for k, v in list(errs_n.items()) + list(errs_b.items()) if not v <= GATE}
-    assert not bad, "gradients over the 1e-2 gate vs the teacher-forced oracle: %s" % bad
+    bad = {k: v for k, v in list(errs_n.items()) + list(errs_b.items()) if not v <= 3e-3}
+    assert not bad, "gradients over 3e-3 vs the teacher-forced oracle with kernel rounding: %s" % bad
+    bad = {k: v for k, v in exact_n.items() if not v <= GATE}
+    assert not bad, "FPN gradients over 1e-2 vs the exact teacher-forced backward: %s" % bad
+    bad = {k: v for k, v in exact_b.items() if not v <= 4e-2}
+    assert not bad, "backbone gradients over 4e-2 vs the exact teacher-forced backward: %s" % bad
     bad = {k: v for k, v in plain_n.items() if not v <= 2e-2}
     assert not bad, "FPN gradients over 2e-2 vs the plain fp32 oracle: %s" % bad
     # frozen parameters received nothing
@@ -119,12 +136,12 @@ def test_second_step_uses_updated_weights(cuda_device):
     torch.cuda.synchronize()
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
     tb, tn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, bb.saved_activations(),
-                                                    neck.saved_activations(), 50, grads)
+                                                    neck.saved_activations(), 50, grads, kernel_rounding=True)
     for k, p in neck.named_parameters():
-        assert orc.rel_l2(p.grad.cpu(), tn[k]) <= GATE, k
+        assert orc.rel_l2(p.grad.cpu(), tn[k]) <= 3e-3, k
     for k, p in bb.named_parameters():
         if p.grad is not None:
-            assert orc.rel_l2(p.grad.cpu(), tb[k]) <= GATE, k
+            assert orc.rel_l2(p.grad.cpu(), tb[k]) <= 3e-3, k
 
 
 def test_eval_mode_unchanged_and_unsupported_training_configs(cuda_device):
