@@ -168,6 +168,114 @@ def run_reference(args):
     return 0
 
 
+def run_train(args):
+    """Config 4 (secondary bench line): R50+FPN forward+backward with fixed random upstream gradients on
+    P2..P6, weights/images resident, per-stage flat fp32 gradient buckets all-reduced on a side stream."""
+    import torch.distributed as dist
+    from torch_detection_b200 import models, training
+    from torch_detection_b200.utils import obj_from_dict
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    exp = 4 if args.depth >= 50 else 1
+    bb = obj_from_dict(dict(type="ResNet", depth=args.depth, frozen_stages=1, bn_eval=True, bn_frozen=True),
+                       parent=models.backbone)
+    bb.init_weights()
+    neck = obj_from_dict(dict(type="FPN", in_channels=[64 * 2 ** i * exp for i in range(4)], out_channels=256,
+                              num_outs=5), parent=models.necks)
+    neck.init_weights()
+    bb, neck = bb.to(dev).train(), neck.to(dev).train()
+    sync = training.BucketAllReduce(defer=True)
+    bb.set_grad_sync(sync)
+    neck.set_grad_sync(sync)
+    B = args.batch if args.batch != 16 else 8
+    x = make_batch(B, args.height, args.width, 100 + rank, torch.bfloat16).to(dev)
+    params = [p for p in list(bb.parameters()) + list(neck.parameters()) if p.requires_grad]
+    outs = neck(bb(x))
+    g = torch.Generator().manual_seed(7)
+    grads = [(torch.randn(o.shape, generator=g) * 1e-3).to(torch.bfloat16).to(dev).contiguous(
+        memory_format=torch.channels_last) for o in outs]
+    del outs
+
+    def step():
+        for p in params:
+            p.grad = None
+        o = neck(bb(x))
+        torch.autograd.backward(list(o), grads)
+        sync.finish()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    if rank == 0:
+        from oracle import resnet_fpn_oracle as orc
+        Hp, Wp = x.shape[2], x.shape[3]
+        fwd = orc.conv_flops(args.depth, Hp, Wp)[0]
+        launches = {"fwd": bb._last_run[0].num_launches + neck._last_run[0].num_launches,
+                    "bwd": bb._last_bwd_run[0].num_launches + neck._last_bwd_run[0].num_launches}
+        bwd_fl = bb._last_bwd_run[0].flops + neck._last_bwd_run[0].flops
+        table = []
+        for mod in (neck, bb):
+            plan, ext = mod._last_bwd_run
+            info = plan.launch_info()
+            for inf, t in zip(info, plan.run_timed(ext)):
+                inf = dict(inf)
+                inf["module"] = type(mod).__name__ + ".backward"
+                inf["ms"] = t
+                table.append(inf)
+        if args.launch_table:
+            with open(args.launch_table, "w") as f:
+                json.dump(table, f, indent=1)
+        value = world * B * args.steps / (ms_total / 1e3)
+        wg = [t for t in table if t["kind"] == 5]
+        dg = [t for t in table if t["kind"] == 3]
+        print(json.dumps({
+            "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
+            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "config 4: ResNet-%d + FPN forward+backward, batch %d per GPU, %dx%d" %
+                                   (args.depth, B, Hp, Wp),
+                       "grad_allreduce": "%d flat fp32 buckets, %.1f MB per step, NCCL on a side stream" %
+                                         (sync.buckets_reduced // (args.steps + max(args.warmup, 3)),
+                                          sync.bytes_reduced / (args.steps + max(args.warmup, 3)) / 1e6)},
+            "gflop_per_image": {"forward": fwd / 1e9, "backward_executed": bwd_fl / B / 1e9},
+            "tflops_per_gpu": (value / world) * (fwd + bwd_fl / B) / 1e12,
+            "launches_per_step": launches, "gpu_launches": (launches["fwd"] + launches["bwd"]) * args.steps,
+            "backward_kernels": {
+                "wgrad": {"launches": len(wg), "ms": sum(t["ms"] for t in wg),
+                          "tflops": sum(t["flops"] for t in wg) / max(sum(t["ms"] for t in wg), 1e-9) / 1e9},
+                "dgrad": {"launches": len(dg), "ms": sum(t["ms"] for t in dg),
+                          "tflops": sum(t["flops"] for t in dg) / max(sum(t["ms"] for t in dg), 1e-9) / 1e9},
+                "other_ms": sum(t["ms"] for t in table if t["kind"] not in (3, 5))},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -180,9 +288,14 @@ def main():
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-table", default="", help="write the per-launch timing table (JSON) here")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train = BASELINE.json config 4: forward+backward, frozen BN, frozen stem+stage 1, "
+                         "batch 8 per GPU, bucketed NCCL gradient all-reduce overlapped with backward")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     import torch.distributed as dist
     from torch_detection_b200 import models
