@@ -18,8 +18,13 @@
 //                                         staging slab -> TMA store), overlapped with the next tile's
 //                                         main loop through tmem_full/empty.  A warp may only read
 //                                         TMEM lanes 32*(warp%4)..+31, so the 8 warps form two groups
-//                                         of four; group g converts the g-th 32-column half of every
-//                                         64-column slab (the epilogue is FMA/convert-issue bound).
+//                                         of four.  Group g OWNS accumulator buffer g: it drains every
+//                                         second tile of the CTA on its own named barrier, staging slabs
+//                                         and TMA-store queue, so the two groups run de-synchronised and
+//                                         hide each other's latency chain (tcgen05.ld -> LDS -> convert ->
+//                                         STS -> fence -> barrier -> store), which -- not issue rate and not
+//                                         DRAM -- bounded the memory-bound 1x1 convs (ncu: 67 % of cycles
+//                                         without an eligible warp at 55 % DRAM utilisation).
 //
 // Numerics: every stored activation tensor may carry a per-tensor power-of-two exponent
 // (TensorMeta::e, value = stored * 2^e) and its true |max| (TensorMeta::amax_bits).  A kernel picks
@@ -41,7 +46,7 @@ constexpr int kGemmThreads = 384;       // 12 warps; warp 11 is the B producer o
 constexpr int kEpiThreads = 256;         // 8 epilogue warps: two warps per TMEM lane quadrant
 constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
-constexpr int kOutSlabs = 2;             // staging double buffer for TMA stores
+constexpr int kEpiGroupThreads = 128;    // one epilogue group = 4 warps = all 128 TMEM lanes
 
 enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2, A_STEM2 = 3, A_PATCH = 4 };
 
@@ -106,7 +111,9 @@ struct ConvGemmParams {
 // BRES_KB > 0: the whole weight panel (up to BRES_KB k-blocks; requires a single n-tile) is loaded
 // once per CTA and stays resident in shared memory; only A tiles stream through the ring.
 // PATCH: A_PATCH pipeline (A ring of kPatchStages halo patches; STAGES then counts B tiles).
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH>
+// OSLABS: staging slabs per epilogue group (1: a group's stores serialise with its next slab; 2: double
+// buffered).
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
 struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kBSlots = BRES_KB > 0 ? BRES_KB : STAGES;
@@ -115,11 +122,11 @@ struct GemmSmem {
   static constexpr int kBOffset = kAStages * kAStageBytes;
   static constexpr int kResOffset = kBOffset + kBSlots * kBBytes;
   static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
-  static constexpr int kBarOffset = kOutOffset + kOutSlabs * kSlabBytes;
+  static constexpr int kBarOffset = kOutOffset + 2 * OSLABS * kSlabBytes;
   static constexpr int kNumBars = 2 * STAGES + 5 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1) + 2 * kPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
-  static constexpr int kDynamic = kParamOffset + 2 * BN * 4;
+  static constexpr int kDynamic = kParamOffset + 4 * BN * 4;  // scale/shift per epilogue group
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
 };
 
@@ -141,10 +148,10 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
   return pack_bf16x2(lo, hi);
 }
 
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH>
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
   constexpr int kSlabsPerTile = BN / 64;
@@ -169,8 +176,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + s); };
   auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + kPatchStages + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
-  float* s_scale = reinterpret_cast<float*>(smem + L::kParamOffset);
-  float* s_shift = s_scale + BN;
+  float* s_params = reinterpret_cast<float*>(smem + L::kParamOffset);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,7 +194,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 4);  // one arrive per warp of the epilogue group that owns buffer a
     }
     for (int s = 0; s < kRS; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -437,12 +443,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ epilogue (warps 3..10)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == TMEM lane == staging row
-    const int epi_tid = threadIdx.x - 96;  // 0..255
-    const int half = (warp - 3) >> 2;      // which 32-column half of each slab this warp converts
-    const bool issuer = epi_tid == 0;      // issues TMA stores, frees residual slabs
+    const int group = (warp - 3) >> 2;     // which accumulator buffer (every second tile) this warp drains
+    const int gtid = (threadIdx.x - 96) & (kEpiGroupThreads - 1);
+    const uint32_t gbar = 1u + group;      // the group's named barrier
+    const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
+    float* s_scale = s_params + group * 2 * BN;
+    float* s_shift = s_scale + BN;
+    const uint32_t smem_out_g = smem_out + group * OSLABS * kSlabBytes;
 
     // per-tensor exponents (all zero when no metadata is attached)
     const int e_in = p.in_meta ? p.in_meta->e : 0;
@@ -457,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       if (p.coarse_meta && has_coarse) bound += __uint_as_float(p.coarse_meta->amax_bits);
       if (bound > 0.0f && bound < 3.0e38f) e_out = ilogbf(bound) - 14;  // bound * 2^-e_out < 2^15
       e_out = max(-100, min(100, e_out));
-      if (blockIdx.x == 0 && epi_tid == 0) p.out_meta->e = e_out;
+      if (blockIdx.x == 0 && threadIdx.x == 96) p.out_meta->e = e_out;
     }
     const float mul_in = ldexpf(1.0f, e_in - e_out);
     const float mul_shift = ldexpf(1.0f, -e_out);
@@ -465,23 +475,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const float mul_co = ldexpf(1.0f, e_co - e_out);
     float amax_local = 0.0f;
 
-    int acc = 0;
-    uint32_t acc_phase = 0;
     int cur_n_tile = -1;
-    int rs = 0;
-    uint32_t rphase = 0;
     int ob = 0;  // staging buffer of the next slab
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int seq = 0; // CTA-local tile counter: tile seq accumulates in TMEM buffer seq & 1
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+      if ((seq & 1) != group) continue;
+      const int acc = group;
+      const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BN;
       if (n_tile != cur_n_tile) {
-        named_bar_sync(1, kEpiThreads);
-        for (int i = epi_tid; i < BN; i += kEpiThreads) {
+        named_bar_sync(gbar, kEpiGroupThreads);
+        for (int i = gtid; i < BN; i += kEpiGroupThreads) {
           s_scale[i] = (p.scale ? __ldg(p.scale + n0 + i) : 1.0f) * mul_in;
           s_shift[i] = (p.shift ? __ldg(p.shift + n0 + i) : 0.0f) * mul_shift;
         }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(gbar, kEpiGroupThreads);
         cur_n_tile = n_tile;
       }
       // output pixel of this thread's row
@@ -529,13 +539,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                               static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int slab = 0; slab < kSlabsPerTile; ++slab) {
-        // the staging buffer `ob` was last read by the TMA store issued two slabs ago
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // residual slabs are produced in tile order into one ring shared by both groups
+        const int ridx = seq * kSlabsPerTile + slab;
+        const int rs = ridx % kRS;
+        const uint32_t rphase = static_cast<uint32_t>(ridx / kRS) & 1u;
+        // the staging buffer `ob` was last read by the TMA store this group issued OSLABS slabs ago
+        if (issuer) {
+          if (OSLABS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
         if (has_res) mbar_wait(rfull_bar(rs), rphase);
-        named_bar_sync(1, kEpiThreads);
-        const uint32_t out_row = smem_out + ob * kSlabBytes + row * 128;
+        named_bar_sync(gbar, kEpiGroupThreads);
+        const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
-        {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_addr + slab * 64 + half * 32, v);
           uint4 rco[4];
@@ -636,9 +654,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         fence_proxy_async_smem();  // staging writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(gbar, kEpiGroupThreads);
         if (issuer) {
-          const uint32_t src = smem_out + ob * kSlabBytes;
+          const uint32_t src = smem_out_g + ob * kSlabBytes;
           if (p.a_mode >= A_STEM) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -655,13 +673,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           if (has_res) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
         }
-        ob ^= 1;
-        if (has_res) {
-          if (++rs == kRS) { rs = 0; rphase ^= 1u; }
-        }
+        if (OSLABS > 1) ob ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (p.out_meta) {

@@ -211,46 +211,48 @@ int encode_4d(CUtensorMap* tm, const void* ptr, int dt, int c, int w, int h, int
   return TDET_OK;
 }
 
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH = false>
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
 int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
   static bool attr_set[64] = {};
   int dev = 0;
   TDET_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH>,
+    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH><<<grid, kGemmThreads, L::kDynamic, st>>>(gp);
+  conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS><<<grid, kGemmThreads, L::kDynamic, st>>>(gp);
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }
 
+// Kernel variants: tile width / A-B ring depth / residual ring slabs / resident weight k-blocks /
+// staging slabs per epilogue group -- each sized to fill the 227 KiB of shared memory.
 int launch_gemm(const Launch& l, cudaStream_t st) {
   const int v = l.bn * 1000000 + l.stages * 10000 + l.res_slabs * 100 + l.bres_kb;
   if (l.patch) {
     switch (v) {
-      case 64 * 1000000 + 40209: return launch_gemm_t<64, 4, 2, 9, true>(l.gp, l.grid, st);
-      case 128 * 1000000 + 40200: return launch_gemm_t<128, 4, 2, 0, true>(l.gp, l.grid, st);
-      case 128 * 1000000 + 70000: return launch_gemm_t<128, 7, 0, 0, true>(l.gp, l.grid, st);
-      case 256 * 1000000 + 30000: return launch_gemm_t<256, 3, 0, 0, true>(l.gp, l.grid, st);
+      case 64 * 1000000 + 40209: return launch_gemm_t<64, 4, 2, 9, true, 1>(l.gp, l.grid, st);
+      case 128 * 1000000 + 40200: return launch_gemm_t<128, 4, 2, 0, true, 1>(l.gp, l.grid, st);
+      case 128 * 1000000 + 70000: return launch_gemm_t<128, 7, 0, 0, true, 1>(l.gp, l.grid, st);
+      case 256 * 1000000 + 30000: return launch_gemm_t<256, 3, 0, 0, true, 1>(l.gp, l.grid, st);
     }
     return fail(TDET_ERR_INVALID_ARGUMENT, "no patch-mode GEMM instantiation for tile %d/%d/%d/%d", l.bn,
                 l.stages, l.res_slabs, l.bres_kb);
   }
   switch (v) {
     // streaming weights
-    case 64 * 1000000 + 60200: return launch_gemm_t<64, 6, 2, 0>(l.gp, l.grid, st);
-    case 128 * 1000000 + 50200: return launch_gemm_t<128, 5, 2, 0>(l.gp, l.grid, st);
-    case 256 * 1000000 + 40000: return launch_gemm_t<256, 4, 0, 0>(l.gp, l.grid, st);
-    case 256 * 1000000 + 30300: return launch_gemm_t<256, 3, 3, 0>(l.gp, l.grid, st);
+    case 64 * 1000000 + 50200: return launch_gemm_t<64, 5, 2, 0, false, 2>(l.gp, l.grid, st);
+    case 128 * 1000000 + 40200: return launch_gemm_t<128, 4, 2, 0, false, 2>(l.gp, l.grid, st);
+    case 256 * 1000000 + 30000: return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
+    case 256 * 1000000 + 30200: return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
-    case 64 * 1000000 + 40007: return launch_gemm_t<64, 4, 0, 7>(l.gp, l.grid, st);    // stem
-    case 64 * 1000000 + 40209: return launch_gemm_t<64, 4, 2, 9>(l.gp, l.grid, st);
-    case 128 * 1000000 + 40204: return launch_gemm_t<128, 4, 2, 4>(l.gp, l.grid, st);
-    case 256 * 1000000 + 40301: return launch_gemm_t<256, 4, 3, 1>(l.gp, l.grid, st);
-    case 256 * 1000000 + 40004: return launch_gemm_t<256, 4, 0, 4>(l.gp, l.grid, st);
+    case 64 * 1000000 + 40007: return launch_gemm_t<64, 4, 0, 7, false, 2>(l.gp, l.grid, st);    // stem
+    case 64 * 1000000 + 30209: return launch_gemm_t<64, 3, 2, 9, false, 2>(l.gp, l.grid, st);
+    case 128 * 1000000 + 40204: return launch_gemm_t<128, 4, 2, 4, false, 2>(l.gp, l.grid, st);
+    case 256 * 1000000 + 30401: return launch_gemm_t<256, 3, 4, 1, false, 2>(l.gp, l.grid, st);
+    case 256 * 1000000 + 30004: return launch_gemm_t<256, 3, 0, 4, false, 1>(l.gp, l.grid, st);
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d", l.bn, l.stages,
               l.res_slabs, l.bres_kb);
@@ -338,15 +340,15 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   gp.b_fp16 = gp.ab_fp16;
   if (o.cout % 256 == 0) {
     l.bn = 256;
-    l.stages = o.residual ? 3 : 4;
-    l.res_slabs = o.residual ? 3 : 0;
+    l.stages = 3;
+    l.res_slabs = o.residual ? 2 : 0;
   } else if (o.cout % 128 == 0) {
     l.bn = 128;
-    l.stages = 5;
+    l.stages = 4;
     l.res_slabs = 2;
   } else {
     l.bn = 64;
-    l.stages = 6;
+    l.stages = 5;
     l.res_slabs = 2;
   }
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
@@ -387,13 +389,13 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     if (resident_b_enabled() && gp.num_n_tiles == 1 && gp.num_m_tiles >= 4 * di.num_sms) {
       // the weight panel fits beside the A ring: load it once per CTA instead of once per k-block
       if (l.bn == 64 && gp.num_kb_b <= 9) {
-        l.stages = 4; l.res_slabs = 2; l.bres_kb = 9;
+        l.stages = 3; l.res_slabs = 2; l.bres_kb = 9;
       } else if (l.bn == 128 && gp.num_kb_b <= 4) {
         l.stages = 4; l.res_slabs = 2; l.bres_kb = 4;
       } else if (l.bn == 256 && gp.num_kb_b <= 1) {
-        l.stages = 4; l.res_slabs = 3; l.bres_kb = 1;
+        l.stages = 3; l.res_slabs = 4; l.bres_kb = 1;
       } else if (l.bn == 256 && gp.num_kb_b <= 4 && !o.residual) {
-        l.stages = 4; l.res_slabs = 0; l.bres_kb = 4;
+        l.stages = 3; l.res_slabs = 0; l.bres_kb = 4;
       }
     }
   }
