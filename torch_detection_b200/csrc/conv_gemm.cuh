@@ -18,9 +18,12 @@
 //                                         staging slab -> TMA store), overlapped with the next tile's
 //                                         main loop through tmem_full/empty.  A warp may only read
 //                                         TMEM lanes 32*(warp%4)..+31, so the 8 warps form two groups
-//                                         of four.  Group g OWNS accumulator buffer g: it drains every
-//                                         second tile of the CTA on its own named barrier, staging slabs
-//                                         and TMA-store queue, so the two groups run de-synchronised and
+//                                         of four.  Group g converts every second 64-column slab of a
+//                                         tile (every second tile when a tile is one slab wide) on its
+//                                         own named barrier, staging slabs and TMA-store queue -- each
+//                                         residual-ring slot then has a single consumer, which keeps
+//                                         the mbarrier parity protocol sound -- so the two groups run
+//                                         de-synchronised and
 //                                         hide each other's latency chain (tcgen05.ld -> LDS -> convert ->
 //                                         STS -> fence -> barrier -> store), which -- not issue rate and not
 //                                         DRAM -- bounded the memory-bound 1x1 convs (ncu: 67 % of cycles
@@ -194,7 +197,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrive per warp of the epilogue group that owns buffer a
+      mbar_init(tempty_bar(a), kSlabsPerTile == 1 ? 4 : 8);  // one arrive per warp draining buffer a
     }
     for (int s = 0; s < kRS; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -443,7 +446,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ epilogue (warps 3..10)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == TMEM lane == staging row
-    const int group = (warp - 3) >> 2;     // which accumulator buffer (every second tile) this warp drains
+    const int group = (warp - 3) >> 2;     // epilogue group: slabs (or tiles) with index % 2 == group
+    constexpr bool kByTile = kSlabsPerTile == 1;
     const int gtid = (threadIdx.x - 96) & (kEpiGroupThreads - 1);
     const uint32_t gbar = 1u + group;      // the group's named barrier
     const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
@@ -479,8 +483,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int ob = 0;  // staging buffer of the next slab
     int seq = 0; // CTA-local tile counter: tile seq accumulates in TMEM buffer seq & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
-      if ((seq & 1) != group) continue;
-      const int acc = group;
+      if (kByTile && (seq & 1) != group) continue;
+      const int acc = seq & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -538,8 +542,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
-      for (int slab = 0; slab < kSlabsPerTile; ++slab) {
-        // residual slabs are produced in tile order into one ring shared by both groups
+      for (int slab = kByTile ? 0 : group; slab < kSlabsPerTile; slab += kByTile ? 1 : 2) {
+        // residual slabs are produced in tile order into one ring shared by both groups; consecutive
+        // slabs of a group are two ring positions apart, so with any ring depth >= 2 the previous fill of
+        // a slot has completed before the group waits for the next one (no parity aliasing)
         const int ridx = seq * kSlabsPerTile + slab;
         const int rs = ridx % kRS;
         const uint32_t rphase = static_cast<uint32_t>(ridx / kRS) & 1u;
@@ -647,8 +653,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                          : "memory");
           }
         }
-        if (slab == kSlabsPerTile - 1) {
-          // all TMEM reads of this accumulator are complete: hand it back to the MMA warp
+        if (slab + (kByTile ? 1 : 2) >= kSlabsPerTile) {
+          // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
