@@ -129,7 +129,10 @@ struct GemmSmem {
   static constexpr int kNumBars = 2 * STAGES + 5 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1) + 2 * kPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
-  static constexpr int kDynamic = kParamOffset + 4 * BN * 4;  // scale/shift per epilogue group
+  // scale/shift per epilogue group: a group only touches the columns of its own slabs (half of BN),
+  // except for one-slab tiles where the groups alternate tiles
+  static constexpr int kGroupCols = BN == 64 ? 64 : BN / 2;
+  static constexpr int kDynamic = kParamOffset + 2 * 2 * kGroupCols * 4;
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
 };
 
@@ -454,8 +457,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const bool has_res = RES_SLABS > 0 && p.has_res;
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
-    float* s_scale = s_params + group * 2 * BN;
-    float* s_shift = s_scale + BN;
+    float* s_scale = s_params + group * 2 * L::kGroupCols;
+    float* s_shift = s_scale + L::kGroupCols;
     const uint32_t smem_out_g = smem_out + group * OSLABS * kSlabBytes;
 
     // per-tensor exponents (all zero when no metadata is attached)
@@ -491,9 +494,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int n0 = n_tile * BN;
       if (n_tile != cur_n_tile) {
         named_bar_sync(gbar, kEpiGroupThreads);
-        for (int i = gtid; i < BN; i += kEpiGroupThreads) {
-          s_scale[i] = (p.scale ? __ldg(p.scale + n0 + i) : 1.0f) * mul_in;
-          s_shift[i] = (p.shift ? __ldg(p.shift + n0 + i) : 0.0f) * mul_shift;
+        for (int i = gtid; i < L::kGroupCols; i += kEpiGroupThreads) {
+          // local column i of this group = column (i & 63) of its (i >> 6)-th slab
+          const int col = kByTile ? i : (((i >> 6) * 2 + group) * 64 + (i & 63));
+          s_scale[i] = (p.scale ? __ldg(p.scale + n0 + col) : 1.0f) * mul_in;
+          s_shift[i] = (p.shift ? __ldg(p.shift + n0 + col) : 0.0f) * mul_shift;
         }
         named_bar_sync(gbar, kEpiGroupThreads);
         cur_n_tile = n_tile;
@@ -584,7 +589,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           tmem_ld_wait();
           float x[32];
-          const int cb = slab * 64 + half * 32;
+          const int cb = (kByTile ? slab : (slab >> 1)) * 64 + half * 32;  // group-local column
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + cb + j * 4);

@@ -124,7 +124,7 @@ struct Launch {
   bool has_ext = false;
   // conv / stem
   ConvGemmParams gp{};
-  int bn = 0, stages = 0, res_slabs = 0, bres_kb = 0;
+  int bn = 0, stages = 0, res_slabs = 0, bres_kb = 0, oslabs = 1;
   bool patch = false;
   bool no_patch = false;  // debugging hook: force the im2col loader
   // wgrad
@@ -171,6 +171,7 @@ bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
 // A_PATCH is used when the 8x16 spatial tiling wastes at most this many percent of the MMA rows.
 int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
+constexpr int kDefaultVariantSet = 32;
 
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
 
@@ -228,7 +229,12 @@ int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
 }
 
 // Kernel variants: tile width / A-B ring depth / residual ring slabs / resident weight k-blocks /
-// staging slabs per epilogue group -- each sized to fill the 227 KiB of shared memory.
+// staging slabs per epilogue group -- each sized to fill the 227 KiB of shared memory.  TDET_VARIANT_SET
+// selects between alternative allocations of that memory (measured A/B).
+constexpr int vkey(int bn, int stages, int res, int bres, int os) {
+  return (((bn * 16 + stages) * 16 + res) * 16 + bres) * 4 + os;
+}
+
 int launch_gemm(const Launch& l, cudaStream_t st) {
   const int v = l.bn * 1000000 + l.stages * 10000 + l.res_slabs * 100 + l.bres_kb;
   if (l.patch) {
@@ -241,21 +247,28 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     return fail(TDET_ERR_INVALID_ARGUMENT, "no patch-mode GEMM instantiation for tile %d/%d/%d/%d", l.bn,
                 l.stages, l.res_slabs, l.bres_kb);
   }
-  switch (v) {
+  switch (vkey(l.bn, l.stages, l.res_slabs, l.bres_kb, l.oslabs)) {
     // streaming weights
-    case 64 * 1000000 + 50200: return launch_gemm_t<64, 5, 2, 0, false, 2>(l.gp, l.grid, st);
-    case 128 * 1000000 + 40200: return launch_gemm_t<128, 4, 2, 0, false, 2>(l.gp, l.grid, st);
-    case 256 * 1000000 + 30000: return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
-    case 256 * 1000000 + 30200: return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(64, 6, 2, 0, 1): return launch_gemm_t<64, 6, 2, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(64, 5, 2, 0, 2): return launch_gemm_t<64, 5, 2, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(128, 5, 2, 0, 1): return launch_gemm_t<128, 5, 2, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(128, 4, 2, 0, 2): return launch_gemm_t<128, 4, 2, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 4, 0, 0, 1): return launch_gemm_t<256, 4, 0, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 3, 0, 0, 2): return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 3, 3, 0, 1): return launch_gemm_t<256, 3, 3, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 2, 4, 0, 2): return launch_gemm_t<256, 2, 4, 0, false, 2>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
-    case 64 * 1000000 + 40007: return launch_gemm_t<64, 4, 0, 7, false, 2>(l.gp, l.grid, st);    // stem
-    case 64 * 1000000 + 30209: return launch_gemm_t<64, 3, 2, 9, false, 2>(l.gp, l.grid, st);
-    case 128 * 1000000 + 40204: return launch_gemm_t<128, 4, 2, 4, false, 2>(l.gp, l.grid, st);
-    case 256 * 1000000 + 30401: return launch_gemm_t<256, 3, 4, 1, false, 2>(l.gp, l.grid, st);
-    case 256 * 1000000 + 30004: return launch_gemm_t<256, 3, 0, 4, false, 1>(l.gp, l.grid, st);
+    case vkey(64, 4, 0, 7, 2): return launch_gemm_t<64, 4, 0, 7, false, 2>(l.gp, l.grid, st);  // stem
+    case vkey(64, 4, 2, 9, 1): return launch_gemm_t<64, 4, 2, 9, false, 1>(l.gp, l.grid, st);
+    case vkey(64, 3, 2, 9, 2): return launch_gemm_t<64, 3, 2, 9, false, 2>(l.gp, l.grid, st);
+    case vkey(128, 4, 2, 4, 2): return launch_gemm_t<128, 4, 2, 4, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 4, 4, 1, 2): return launch_gemm_t<256, 4, 4, 1, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 4, 3, 1, 1): return launch_gemm_t<256, 4, 3, 1, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
   }
-  return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d", l.bn, l.stages,
-              l.res_slabs, l.bres_kb);
+  return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d/%d", l.bn, l.stages,
+              l.res_slabs, l.bres_kb, l.oslabs);
 }
 
 // Fills the epilogue / numerics part of the GEMM parameters shared by conv and stem.
@@ -338,18 +351,23 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   gp.ab_fp16 = o.x_dtype == TDET_F16;
   const int w_dtype = o.x_dtype;  // tcgen05 kind::f16 needs A and B in ONE format (mixing traps)
   gp.b_fp16 = gp.ab_fp16;
+  // bit i of TDET_VARIANT_SET picks the double-buffered-staging allocation for kernel family i
+  const int vs = env_int("TDET_VARIANT_SET", kDefaultVariantSet);
   if (o.cout % 256 == 0) {
     l.bn = 256;
-    l.stages = 3;
-    l.res_slabs = o.residual ? 2 : 0;
+    if (o.residual) {
+      if (vs & 1) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; } else { l.stages = 3; l.res_slabs = 3; l.oslabs = 1; }
+    } else {
+      if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; } else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
+    }
   } else if (o.cout % 128 == 0) {
     l.bn = 128;
-    l.stages = 4;
     l.res_slabs = 2;
+    if (vs & 4) { l.stages = 4; l.oslabs = 2; } else { l.stages = 5; l.oslabs = 1; }
   } else {
     l.bn = 64;
-    l.stages = 5;
     l.res_slabs = 2;
+    if (vs & 8) { l.stages = 5; l.oslabs = 2; } else { l.stages = 6; l.oslabs = 1; }
   }
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
   gp.num_n_tiles = o.cout / l.bn;
@@ -366,6 +384,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     const bool variant = (l.bn == 64 && gp.num_kb_b <= 9) || l.bn == 128 || (l.bn == 256 && !o.residual);
     if (fits && variant) {
       l.patch = true;
+      l.oslabs = 1;
       gp.a_mode = A_PATCH;
       gp.tile_bw = kPatchBW;
       gp.tile_bh = kPatchBH;
@@ -389,13 +408,16 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     if (resident_b_enabled() && gp.num_n_tiles == 1 && gp.num_m_tiles >= 4 * di.num_sms) {
       // the weight panel fits beside the A ring: load it once per CTA instead of once per k-block
       if (l.bn == 64 && gp.num_kb_b <= 9) {
-        l.stages = 3; l.res_slabs = 2; l.bres_kb = 9;
+        l.res_slabs = 2; l.bres_kb = 9;
+        if (vs & 16) { l.stages = 3; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
       } else if (l.bn == 128 && gp.num_kb_b <= 4) {
-        l.stages = 4; l.res_slabs = 2; l.bres_kb = 4;
+        l.stages = 4; l.res_slabs = 2; l.bres_kb = 4; l.oslabs = 2;
       } else if (l.bn == 256 && gp.num_kb_b <= 1) {
-        l.stages = 3; l.res_slabs = 4; l.bres_kb = 1;
+        l.stages = 4; l.bres_kb = 1;
+        if (vs & 32) { l.res_slabs = 4; l.oslabs = 2; } else { l.res_slabs = 3; l.oslabs = 1; }
       } else if (l.bn == 256 && gp.num_kb_b <= 4 && !o.residual) {
-        l.stages = 3; l.res_slabs = 0; l.bres_kb = 4;
+        l.res_slabs = 0; l.bres_kb = 4;
+        if (vs & 64) { l.stages = 2; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
       }
     }
   }
@@ -611,6 +633,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   l.stages = v2 ? 4 : 6;
   l.res_slabs = v2 ? 0 : 2;
   l.bres_kb = v2 ? 7 : 0;
+  l.oslabs = v2 ? 2 : 1;
   rc = encode_2d(&gp.tmap_b, o.wgt, TDET_BF16, 448, 64, 64, "stem weights");
   if (rc) return rc;
   if (v2) {
