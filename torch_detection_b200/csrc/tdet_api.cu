@@ -171,7 +171,7 @@ bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
 // A_PATCH is used when the 8x16 spatial tiling wastes at most this many percent of the MMA rows.
 int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
-constexpr int kDefaultVariantSet = 32;
+constexpr int kDefaultVariantSet = 0;
 
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
 
