@@ -33,6 +33,7 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+SM_RESERVE = int(os.environ.get("TDET_SM_RESERVE", "8"))  # SMs left to NCCL while gradients are all-reduced
 METRIC = "ResNet-50-FPN img/s @800x1333 bf16 at 1/2/4/8 B200; % tensor-pipe peak"
 FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
 
@@ -164,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -181,6 +182,9 @@ def run_train(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the all-reduce overlaps persistent one-CTA-per-SM kernels: keep NCCL on a few SMs and leave
+        # exactly those free (BucketAllReduce.sm_reserve), or every conv kernel would run a second wave
+        os.environ.setdefault("NCCL_MAX_CTAS", str(SM_RESERVE))
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     exp = 4 if args.depth >= 50 else 1
@@ -191,7 +195,7 @@ def run_train(args):
                               num_outs=5), parent=models.necks)
     neck.init_weights()
     bb, neck = bb.to(dev).train(), neck.to(dev).train()
-    sync = training.BucketAllReduce(defer=True)
+    sync = training.BucketAllReduce(defer=True, sm_reserve=SM_RESERVE if world > 1 else 0)
     bb.set_grad_sync(sync)
     neck.set_grad_sync(sync)
     B = args.batch if args.batch != 16 else 8
@@ -250,7 +254,7 @@ def run_train(args):
         value = world * B * args.steps / (ms_total / 1e3)
         wg = [t for t in table if t["kind"] == 5]
         dg = [t for t in table if t["kind"] == 3]
-        print(json.dumps({
+        emit(({
             "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
             "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -276,7 +280,27 @@ def run_train(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: route everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) to stderr and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -485,7 +509,7 @@ def main():
             "clocks": sampler.summary() if sampler else None,
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -185,6 +185,11 @@ const char* tdet_last_error(void);
 /* 0 if `device` is an sm_100 part this build can run on, else TDET_ERR_UNSUPPORTED_DEVICE. */
 int tdet_device_supported(int device);
 
+/* The GEMM kernels are persistent, one CTA per SM.  While another stream needs SMs of its own -- NCCL
+ * all-reducing gradient buckets under the backward pass -- a full-width grid would wait for them and
+ * run a second wave; plans built after this call size their grids to (SM count - sms). */
+int tdet_set_sm_reserve(int device, int sms);
+
 /* Geometry of the TDET_OP_PREP output for a stem output of ho x wo pixels: hp = 2*ho + 6 rows,
  * wp = 2*wo + 16 rounded up to a multiple of 16 pixels (the image sits at offset (3,3)). */
 int tdet_stem_staging_dims(int ho, int wo, int* hp, int* wp);

@@ -69,7 +69,7 @@ class TdetError(RuntimeError):
 
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
-    "tdet_stem_staging_dims",
+    "tdet_stem_staging_dims", "tdet_set_sm_reserve",
     "tdet_pack_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
     "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_range", "tdet_plan_run_timed",
@@ -94,6 +94,7 @@ def lib():
     L.tdet_abi_version.restype = i32
     L.tdet_last_error.restype = ctypes.c_char_p
     L.tdet_device_supported.argtypes = [i32]
+    L.tdet_set_sm_reserve.argtypes = [i32, i32]
     L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_dgrad_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]

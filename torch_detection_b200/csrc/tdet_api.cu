@@ -82,6 +82,7 @@ Driver& driver() {
 
 struct DeviceInfo {
   int num_sms = 0;
+  int sm_reserve = 0;  // SMs the persistent GEMM grids leave free (tdet_set_sm_reserve)
   int cc_major = 0, cc_minor = 0;
   bool queried = false;
 };
@@ -473,7 +474,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
       reinterpret_cast<unsigned long long*>(&gp.tmap_a)[1] &= ~(1ull << 21);
   }
   const int num_tiles = gp.num_m_tiles * gp.num_n_tiles;
-  int g = di.num_sms;
+  int g = di.num_sms - di.sm_reserve;
   if (g > num_tiles) g = num_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) * o.kh * o.kw);
@@ -694,7 +695,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
     if (r != CUDA_SUCCESS)
       return fail(TDET_ERR_DRIVER, "cuTensorMapEncodeTiled(stem out) failed: %d", static_cast<int>(r));
   }
-  int g = di.num_sms;
+  int g = di.num_sms - di.sm_reserve;
   if (g > gp.num_m_tiles) g = gp.num_m_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.flops = 2.0 * static_cast<double>(o.n) * o.ho * o.wo * 64.0 * 147.0;
@@ -933,6 +934,15 @@ const char* tdet_last_error(void) { return g_err; }
 int tdet_device_supported(int device) {
   DeviceInfo* di = nullptr;
   return require_sm100(device, &di);
+}
+
+int tdet_set_sm_reserve(int device, int sms) {
+  DeviceInfo* di = nullptr;
+  int rc = device_info(device, &di);
+  if (rc) return rc;
+  if (sms < 0 || sms >= di->num_sms) return fail(TDET_ERR_INVALID_ARGUMENT, "sm_reserve %d out of range", sms);
+  di->sm_reserve = sms;
+  return TDET_OK;
 }
 
 int tdet_stem_staging_dims(int ho, int wo, int* hp, int* wp) {

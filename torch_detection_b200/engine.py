@@ -32,6 +32,11 @@ def conv_out(v, k, s, p, d=1):
     return (v + 2 * p - d * (k - 1) - 1) // s + 1
 
 
+def set_sm_reserve(device, sms):
+    """Plans built afterwards leave `sms` SMs free (for NCCL kernels overlapping the backward pass)."""
+    _C.check(_C.lib().tdet_set_sm_reserve(_index(device), sms))
+
+
 def stem_staging_dims(ho, wo):
     """(hp, wp) of the padded NHWC4 staging buffer TDET_OP_PREP writes for a stem output ho x wo."""
     hp, wp = ctypes.c_int32(), ctypes.c_int32()

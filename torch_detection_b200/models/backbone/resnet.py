@@ -414,6 +414,8 @@ class ResNet(nn.Module):
         """Attach a ``training.BucketAllReduce``: backward then all-reduces one flat fp32 bucket per
         stage (deepest first) as soon as that stage's wgrad kernels are enqueued."""
         self._grad_sync = sync
+        if sync is not None:
+            sync.attach(self, next(self.parameters()).device)
 
     def _trainable_weights(self):
         """Conv weights that get gradients, in module order.  Supported configuration = the

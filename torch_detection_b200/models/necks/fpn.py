@@ -201,6 +201,8 @@ class FPN(nn.Module):
         """Attach a ``training.BucketAllReduce``: the neck's gradients form one flat fp32 bucket that is
         all-reduced as soon as the neck's backward is enqueued (it overlaps the whole backbone backward)."""
         self._grad_sync = sync
+        if sync is not None:
+            sync.attach(self, next(self.parameters()).device)
 
     def saved_activations(self):
         """{name: fp32 NCHW CPU tensor}: inputs ``C{j}`` and merged laterals ``lat{j}`` of the last training

@@ -35,18 +35,26 @@ class BucketAllReduce(object):
     tests) or a single rank the collective runs inline.
     """
 
-    def __init__(self, group=None, average=True, defer=False):
+    def __init__(self, group=None, average=True, defer=False, sm_reserve=0):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.average = average
         self.defer = defer
+        # SMs the modules' persistent GEMM grids leave to the NCCL kernels (pair with NCCL_MAX_CTAS)
+        self.sm_reserve = sm_reserve
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._streams = {}
         self._pending = []
         self._copied = {}  # bucket address -> event: its side-stream copy has completed
         self.buckets_reduced = 0
         self.bytes_reduced = 0
+
+    def attach(self, module, device):
+        """Called by module.set_grad_sync: re-size the module's grids if SMs are reserved for NCCL."""
+        if self.sm_reserve and self.world > 1 and device.type == "cuda":
+            engine.set_sm_reserve(device, self.sm_reserve)
+            module._plans = {}
 
     def _comm_stream(self, device):
         s = self._streams.get(device)
