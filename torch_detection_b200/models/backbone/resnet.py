@@ -451,7 +451,7 @@ class ResNet(nn.Module):
     def saved_activations(self):
         """{name: fp32 NCHW CPU tensor} of what the last training forward saved for backward (block
         inputs ``layerL.B.in`` and every conv's stored output ``layerL.B.convK``).  Test/debug API:
-        it is how the gradient tests teacher-force the oracle with the kernels' own ReLU masks."""
+        the gradient tests feed these to their fp32 checker so that ReLU masks match the kernels'."""
         plan, out_shapes, records, boundary, geo = self._plans[self._train_state["key"]]
         outs = self._train_state["outs"]
 
