@@ -221,6 +221,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Launched with programmatic stream serialisation: everything above (barrier init, TMEM allocation,
+  // descriptor prefetch) overlaps the tail of the previous kernel; its outputs are read only below.
+  grid_dependency_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kb = p.kh * p.kw * p.k_chunks;

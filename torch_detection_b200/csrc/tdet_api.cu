@@ -213,6 +213,26 @@ int encode_4d(CUtensorMap* tm, const void* ptr, int dt, int c, int w, int h, int
   return TDET_OK;
 }
 
+// GEMM kernels are launched with programmatic stream serialisation (PDL): a kernel's CTAs may start --
+// and run their set-up up to griddepcontrol.wait -- as soon as the previous kernel's CTAs leave the SMs,
+// instead of after the whole grid has drained and the launch latency has elapsed.  TDET_PDL=0 disables.
+template <typename Params>
+int launch_pdl(void (*kernel)(Params), dim3 grid, int threads, int smem, cudaStream_t st, const Params& prm) {
+  static const bool pdl = env_int("TDET_PDL", 1) != 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(static_cast<unsigned>(threads), 1, 1);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TDET_CUDA(cudaLaunchKernelEx(&cfg, kernel, prm));
+  return TDET_OK;
+}
+
 template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
 int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
@@ -224,9 +244,8 @@ int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS><<<grid, kGemmThreads, L::kDynamic, st>>>(gp);
-  TDET_CUDA(cudaGetLastError());
-  return TDET_OK;
+  return launch_pdl(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>, grid, kGemmThreads,
+                    L::kDynamic, st, gp);
 }
 
 // Kernel variants: tile width / A-B ring depth / residual ring slabs / resident weight k-blocks /
@@ -498,9 +517,7 @@ int launch_wgrad_t(const WgradParams& wp, dim3 grid, cudaStream_t st) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  wgrad_gemm_kernel<NB, PIX, STAGES><<<grid, kWgThreads, L::kDynamic, st>>>(wp);
-  TDET_CUDA(cudaGetLastError());
-  return TDET_OK;
+  return launch_pdl(wgrad_gemm_kernel<NB, PIX, STAGES>, grid, kWgThreads, L::kDynamic, st, wp);
 }
 
 int launch_wgrad(const Launch& l, cudaStream_t st) {

@@ -8,8 +8,9 @@
 // consumed with a_major = b_major = MN: 64 channels contiguous per row, 8-pixel groups 1024 B apart
 // (SBO), the next 64 channels in the next slab (LBO = PIX*128 B).  X is gathered by the same kind of
 // tensor map the forward A operand uses (tiled 2D for 1x1 stride 1, im2col 4D otherwise), so padding
-// and stride semantics are the forward kernel's by construction.  g (bf16) and X (bf16, or fp16 with a
-// per-tensor exponent) may differ in format: kind::f16 takes the A and B formats independently.
+// and stride semantics are the forward kernel's by construction.  g and X must share one 16-bit format
+// (bf16, or fp16 with per-tensor exponents applied in the epilogue): tcgen05 kind::f16 traps on mixed
+// fp16/bf16 operands (measured).
 //
 // One CTA = one (128-channel Cout tile, filter tap, NB-wide Cin group) and one slice of the pixel
 // range (split-K over blockIdx.y); partial sums are combined with vectorised fp32 reductions
@@ -114,6 +115,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  grid_dependency_wait();
 
   if (nkb > 0) {
     if (warp == 0) {
