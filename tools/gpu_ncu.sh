@@ -1,11 +1,18 @@
 #!/bin/bash
-# ncu: launch list of one step + full-set captures of representative GEMM launches.
+# ncu: launch lists of one warm inference step and one warm training step (NVTX range "tdet_step"), then
+# full-set captures of representative GEMM launches.  Each ncu command runs only after the plain command exited 0.
 mkdir -p gpurun_out
-python tools/profile_step.py --steps 2 > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 64 -c 64 --csv --log-file gpurun_out/launches.csv python tools/profile_step.py --steps 2 > gpurun_out/ncu1.log 2>&1
-echo "ncu list exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 0 -c 5 -f -o gpurun_out/prof_layer1 python tools/profile_step.py --steps 1 > gpurun_out/ncu2.log 2>&1
+R=${1:-r1s3}
+python tools/profile_step.py --steps 3 > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
+python tools/profile_train.py --steps 3 > gpurun_out/plain_train.log 2>&1 || { tail -5 gpurun_out/plain_train.log; exit 1; }
+ncu --nvtx --nvtx-include "tdet_step/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_infer_$R.csv python tools/profile_step.py --steps 3 > gpurun_out/ncu1.log 2>&1
+echo "ncu infer list exit $?"
+ncu --nvtx --nvtx-include "tdet_step/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_$R.csv python tools/profile_train.py --steps 3 > gpurun_out/ncu1t.log 2>&1
+echo "ncu train list exit $?"
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 0 -c 5 -f -o gpurun_out/prof_layer1_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu2.log 2>&1
 echo "ncu layer1 exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 56 -c 2 -f -o gpurun_out/prof_fpn python tools/profile_step.py --steps 1 > gpurun_out/ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 56 -c 2 -f -o gpurun_out/prof_fpn_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu3.log 2>&1
 echo "ncu fpn exit $?"
+ncu --set full --clock-control none --import-source on -k regex:wgrad_gemm -s 0 -c 3 -f -o gpurun_out/prof_wgrad_$R python tools/profile_train.py --steps 1 > gpurun_out/ncu4.log 2>&1
+echo "ncu wgrad exit $?"
 ls -la gpurun_out/*.ncu-rep

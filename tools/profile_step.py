@@ -25,7 +25,11 @@ neck.init_weights()
 bb, neck = bb.to(dev).eval(), neck.to(dev).eval()
 x = make_batch(args.batch, 800, 1333, 0, torch.bfloat16).to(dev)
 with torch.no_grad():
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        if i == args.steps - 1:
+            torch.cuda.synchronize()
+            torch.cuda.nvtx.range_push("tdet_step")  # ncu --nvtx --nvtx-include "tdet_step/" = one warm step
         outs = neck(bb(x))
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
 print("ok", [tuple(o.shape) for o in outs])
