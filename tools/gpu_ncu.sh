@@ -7,7 +7,7 @@ python tools/profile_step.py --steps 3 > gpurun_out/plain.log 2>&1 || { tail -5 
 python tools/profile_train.py --steps 3 > gpurun_out/plain_train.log 2>&1 || { tail -5 gpurun_out/plain_train.log; exit 1; }
 ncu --nvtx --nvtx-include "tdet_step/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_infer_$R.csv python tools/profile_step.py --steps 3 > gpurun_out/ncu1.log 2>&1
 echo "ncu infer list exit $?"
-ncu --nvtx --nvtx-include "tdet_step/" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_$R.csv python tools/profile_train.py --steps 3 > gpurun_out/ncu1t.log 2>&1
+ncu --nvtx --nvtx-include "tdet_step" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_$R.csv python tools/profile_train.py --steps 3 > gpurun_out/ncu1t.log 2>&1
 echo "ncu train list exit $?"
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 0 -c 5 -f -o gpurun_out/prof_layer1_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu2.log 2>&1
 echo "ncu layer1 exit $?"

@@ -39,7 +39,7 @@ def raw_page(rep):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rep", action="append", default=[])
-    ap.add_argument("--launches", default="")
+    ap.add_argument("--launches", action="append", default=[])
     ap.add_argument("--out", required=True)
     ap.add_argument("--title", default="ncu summary")
     ap.add_argument("--note", action="append", default=[])
@@ -66,24 +66,27 @@ def main():
                 vals.append("%s %s" % (v, u) if u and u != "%" else v)
             md.append("| %d | `%s` | " % (j, kn) + " | ".join(vals) + " |")
         md.append("")
-    if a.launches:
-        rows = [r for r in csv.reader(open(a.launches)) if len(r) > 10 and r[0].isdigit()]
-        tot = sum(float(r[-1]) for r in rows)
-        agg = OrderedDict()
-        for r in rows:
-            k = r[4].split("(")[0].replace("void ", "")
-            agg.setdefault(k, [0, 0.0])
-            agg[k][0] += 1
-            agg[k][1] += float(r[-1])
-        md += ["## launch list `%s` (gpu__time_duration.sum, one step, cold-cache/serialised: compare shares)" % a.launches, "",
-               "| kernel | launches | total us | share of step |", "|---|---|---|---|"]
-        for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            md.append("| `%s` | %d | %.1f | %.1f%% |" % (k, c, t / 1e3, 100 * t / tot))
-        md += ["", "total %d launches, %.1f us" % (len(rows), tot / 1e3), "", "<details><summary>every launch</summary>", "",
-               "| id | kernel | grid | ns |", "|---|---|---|---|"]
-        for r in rows:
-            md.append("| %s | `%s` | %s | %s |" % (r[0], r[4].split("(")[0].replace("void ", ""), r[8], r[-1]))
-        md += ["", "</details>", ""]
+    for launches in a.launches:
+            allrows = [r for r in csv.reader(open(launches)) if len(r) > 10]
+            hdr = next(r for r in allrows if r[0] == "ID")
+            ik, ig = hdr.index("Kernel Name"), hdr.index("Grid Size")
+            rows = [r for r in allrows if r[0].isdigit()]
+            tot = sum(float(r[-1]) for r in rows)
+            agg = OrderedDict()
+            for r in rows:
+                k = r[ik].split("(")[0].replace("void ", "")
+                agg.setdefault(k, [0, 0.0])
+                agg[k][0] += 1
+                agg[k][1] += float(r[-1])
+            md += ["## launch list `%s` (gpu__time_duration.sum, one step, cold-cache/serialised: compare shares)" % launches, "",
+                   "| kernel | launches | total us | share of step |", "|---|---|---|---|"]
+            for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                md.append("| `%s` | %d | %.1f | %.1f%% |" % (k, c, t / 1e3, 100 * t / tot))
+            md += ["", "total %d launches, %.1f us" % (len(rows), tot / 1e3), "", "<details><summary>every launch</summary>", "",
+                   "| id | kernel | grid | ns |", "|---|---|---|---|"]
+            for r in rows:
+                md.append("| %s | `%s` | %s | %s |" % (r[0], r[ik].split("(")[0].replace("void ", ""), r[ig], r[-1]))
+            md += ["", "</details>", ""]
     open(a.out, "w").write("\n".join(md))
     print("wrote", a.out)
 

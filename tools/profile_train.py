@@ -28,7 +28,8 @@ grads = None
 for i in range(args.steps):
     if i == args.steps - 1 and i > 0:
         torch.cuda.synchronize()
-        torch.cuda.nvtx.range_push("tdet_step")  # ncu --nvtx --nvtx-include "tdet_step/" = one warm step
+        # start/end (process-wide) range: backward kernels are launched from autograd's own thread
+        rng = torch.cuda.nvtx.range_start("tdet_step")  # ncu --nvtx --nvtx-include "tdet_step" = one warm step
     for p in list(bb.parameters()) + list(neck.parameters()):
         p.grad = None
     outs = neck(bb(x))
@@ -38,5 +39,5 @@ for i in range(args.steps):
     torch.autograd.backward(list(outs), grads)
 torch.cuda.synchronize()
 if args.steps > 1:
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_end(rng)
 print("ok")

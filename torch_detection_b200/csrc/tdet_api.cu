@@ -591,7 +591,9 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
       reinterpret_cast<unsigned long long*>(&wp.tmap_x)[1] &= ~(1ull << 21);
   }
   const int tiles = ((o.cout + 127) / 128) * o.kh * o.kw * wp.ci_groups;
-  int splits = (2 * di.num_sms + tiles - 1) / tiles;
+  // one CTA per SM (shared memory): aim at exactly two full waves, never a partial third one
+  const int sms = di.num_sms - di.sm_reserve;
+  int splits = (2 * sms) / tiles;
   if (splits > wp.kblocks) splits = wp.kblocks;
   if (splits < 1) splits = 1;
   wp.kb_per_cta = (wp.kblocks + splits - 1) / splits;
