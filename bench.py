@@ -460,9 +460,17 @@ def main():
         gemm_fl = sum(l["flops"] for l in gemm)
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_s3_traffic.json")
+        if os.path.isfile(tpath) and args.depth == 50 and args.batch == 16:
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["roofline_traffic_bytes"]
+            traffic_note = ("DRAM read+write of the family's largest launch (FPN P2 3x3, algorithmic 1102.2 MB) from "
+                            + tj["source"])
         roof = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
             "kernel": "conv_gemm_kernel<256,4> (all launches of one step: %d launches, %.1f%% of step time)"
                       % (len(dom), 100.0 * dom_ms / all_ms),
             "peak_source": peaks["_source"] + ", sustained bf16 (kernel timed inside a long step)",
