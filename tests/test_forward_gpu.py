@@ -165,3 +165,26 @@ def test_cpu_tensor_and_train_mode_bn_are_refused(cuda_device):
     bb.train()
     with pytest.raises(NotImplementedError):
         bb(torch.randn(1, 3, 64, 64, device=cuda_device))
+
+
+@pytest.mark.parametrize("depth,hw,batch", [
+    (18, (512, 512), 2),
+    (34, (608, 1024), 1),
+    (50, (512, 512), 3),
+    (101, (608, 1024), 2),
+    (101, (1024, 1024), 1),
+])
+def test_config5_sweep_depth_by_size(cuda_device, depth, hw, batch):
+    """BASELINE.json config 5 (depth x input size x batch sweep) and config 3's ResNet-101: every FPN level of
+    every depth at detector-sized inputs against the CPU oracle (image 0; the other images are covered by
+    the batch-independence property)."""
+    bb, neck = helpers.build_product_pair(depth, seed=13, bnstats=True)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    g = torch.Generator().manual_seed(depth)
+    xb = torch.randn(batch, 3, hw[0], hw[1], generator=g).to(torch.bfloat16)
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, xb[:1].float(), depth)
+    feats, outs = _run_product(bb, neck, xb, cuda_device)
+    assert all(t.shape[0] == batch for t in feats + outs)
+    _check_levels([t[:1] for t in feats], want_f, ["C2", "C3", "C4", "C5"])
+    e = _check_levels([t[:1] for t in outs], want_p, ["P2", "P3", "P4", "P5", "P6"])
+    print("rel-L2 sweep", depth, hw, batch, e)
