@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 5
+#define TDET_ABI_VERSION 6
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -81,7 +81,8 @@ typedef enum tdet_op_kind {
   TDET_OP_SUMPOOL2 = 8,  /* adjoint of the nearest-x2 upsample (fpn.py:100-101): 2x2 sum pool */
   TDET_OP_DILATE2 = 9,   /* adjoint of a stride-2 subsample: zero-insertion upsample to (ho, wo) */
   TDET_OP_ADD_MASK = 10, /* y = (x + residual) * (mask > 0): gradient merge / ReLU backward */
-  TDET_OP_ZERO = 11      /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
+  TDET_OP_ZERO = 11,     /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
+  TDET_OP_AMAX = 12      /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2 } tdet_dtype;
@@ -141,7 +142,13 @@ typedef struct tdet_tensor_meta {
  *                   fp32 accumulation
  * TDET_OP_DILATE2   y[n][u][v][:] = (u,v even) ? x[n][u/2][v/2][:] : 0; y is (ho, wo) with
  *                   h == (ho+1)/2, w == (wo+1)/2
- * TDET_OP_ADD_MASK  y = (x + residual) * (mask != 0); residual and mask optional; all [n][h][w][cin] bf16
+ * TDET_OP_ADD_MASK  y = (x + residual) * (mask != 0); residual and mask optional; all [n][h][w][cin] 16-bit of
+ *                   x_dtype / residual_dtype / y_dtype with optional x_meta / residual_meta exponents.  With
+ *                   TDET_FLAG_SCALED_OUT (y_dtype F16, needs y_meta and the inputs' metas with valid amax) the
+ *                   output exponent is chosen from amax(x) + amax(residual) and that bound is recorded as
+ *                   y's amax.  Without inputs to add or mask it is the format conversion fp16*2^e -> bf16.
+ * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;
+ *                   its exponent field is left untouched)
  * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled
  */
 typedef struct tdet_op {
@@ -175,6 +182,7 @@ typedef struct tdet_op {
   int32_t gy_dtype;
   int32_t reserved0;
   float* dw;                 /* WGRAD / COLSUM: fp32 accumulator */
+  const tdet_tensor_meta* gy_meta; /* WGRAD: exponent of gy (NULL = 0) */
 } tdet_op;
 
 typedef struct tdet_plan tdet_plan; /* opaque */

@@ -59,13 +59,13 @@ def plain_grads(bb_sd, neck_sd, x, depth, grad_outs, train_from_stage=1, out_cha
     return gb, gn, feats, outs
 
 
-def _r(t):
-    return t.to(torch.bfloat16).to(torch.float32)
+def _r(t, dtype=torch.bfloat16):
+    return t.to(dtype).to(torch.float32)
 
 
-def _ste(t):
-    """bf16 rounding in forward, identity in backward."""
-    return t + (_r(t) - t).detach()
+def _ste(t, dtype=torch.bfloat16):
+    """16-bit rounding in forward, identity in backward."""
+    return t + (_r(t, dtype) - t).detach()
 
 
 def _force(y, stored, relu, round_grad=False):
@@ -97,30 +97,31 @@ class _ConvBNKernelModel(torch.autograd.Function):
     (tdet_pack_dgrad_weight); the weight gradient is scale * (g (*) x) in fp32."""
 
     @staticmethod
-    def forward(ctx, x, w, scale, shift, stride, pad):
+    def forward(ctx, x, w, scale, shift, stride, pad, wdtype):
         ctx.save_for_backward(x, w, scale)
-        ctx.conf = (stride, pad)
-        y = F.conv2d(x, _r(w), None, stride, pad)
+        ctx.conf = (stride, pad, wdtype)
+        y = F.conv2d(x, _r(w, wdtype), None, stride, pad)
         return y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
 
     @staticmethod
     def backward(ctx, g):
         x, w, scale = ctx.saved_tensors
-        stride, pad = ctx.conf
+        stride, pad, wdtype = ctx.conf
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = torch.nn.grad.conv2d_input(x.shape, _r(w * scale.view(-1, 1, 1, 1)), g, stride, pad)
+            gx = torch.nn.grad.conv2d_input(x.shape, _r(w * scale.view(-1, 1, 1, 1), wdtype), g, stride, pad)
         if ctx.needs_input_grad[1]:
             gw = torch.nn.grad.conv2d_weight(x, w.shape, g * scale.view(1, -1, 1, 1), stride, pad)
-        return gx, gw, None, None, None, None
+        return gx, gw, None, None, None, None, None
 
 
 def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs, train_from_stage=1,
-                         out_channels=256, num_outs=5, kernel_rounding=False):
+                         out_channels=256, num_outs=5, kernel_rounding=False, bb_weight_dtype=torch.bfloat16):
     """fp32 autograd over the reference's graph with every stored activation (and hence every ReLU
     mask and every conv / wgrad input) forced to the value the CUDA training forward stored:
     `saved_bb` = ResNet.saved_activations(), `saved_neck` = FPN.saved_activations().  Conv weights are
-    bf16-rounded (straight-through), as the kernels' operands are.
+    rounded to the kernels' operand format (straight-through): `bb_weight_dtype` for the backbone (fp16 with
+    the default block-exponent activations, bf16 with TDET_INTERNAL_DTYPE=bf16), bf16 for the neck.
 
     kernel_rounding=False: the backward is exact fp32 -- what remains different from the CUDA
         backward is its bf16 storage of gradient tensors and dgrad operands (accumulates as
@@ -138,9 +139,9 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
         scale = bb[bnp + ".weight"] / torch.sqrt(bb[bnp + ".running_var"] + orc.BN_EPS)
         shift = bb[bnp + ".bias"] - bb[bnp + ".running_mean"] * scale
         if kr:
-            y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad)
+            y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad, bb_weight_dtype)
         else:
-            y = F.conv2d(inp, _ste(bb[wkey]), None, stride, pad)
+            y = F.conv2d(inp, _ste(bb[wkey], bb_weight_dtype), None, stride, pad)
             y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res

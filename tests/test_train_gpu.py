@@ -46,6 +46,11 @@ def _train_pair(depth, seed, dev, bnstats, frozen_stages=1):
     return bb, neck, bsd, nsd
 
 
+def _backbone_weight_dtype():
+    from torch_detection_b200.models.backbone import resnet
+    return resnet.INTERNAL_DTYPE
+
+
 def _cos(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
@@ -73,10 +78,12 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
     got_n = {k: p.grad.detach().cpu() for k, p in neck.named_parameters() if p.grad is not None}
 
     saved_b, saved_n = bb.saved_activations(), neck.saved_activations()
+    wdt = _backbone_weight_dtype()
     tb, tn, tf_feats, tf_outs = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
-                                                                 train_from_stage=frozen, kernel_rounding=True)
+                                                                 train_from_stage=frozen, kernel_rounding=True,
+                                                                 bb_weight_dtype=wdt)
     xb, xn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
-                                                    train_from_stage=frozen)
+                                                    train_from_stage=frozen, bb_weight_dtype=wdt)
     pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen)
     assert set(got_b) == set(tb), (sorted(set(got_b) ^ set(tb))[:8])
     assert set(got_n) == set(tn) and len(got_n) == 16
@@ -146,7 +153,8 @@ def test_second_step_uses_updated_weights(cuda_device):
     torch.cuda.synchronize()
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
     tb, tn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, bb.saved_activations(),
-                                                    neck.saved_activations(), 50, grads, kernel_rounding=True)
+                                                    neck.saved_activations(), 50, grads, kernel_rounding=True,
+                                                    bb_weight_dtype=_backbone_weight_dtype())
     for k, p in neck.named_parameters():
         assert orc.rel_l2(p.grad.cpu(), tn[k]) <= 1.5e-3, k
     for k, p in bb.named_parameters():

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # tdet_status
 OK = 0
@@ -22,6 +22,7 @@ ERR_OUT_OF_MEMORY = -6
 # tdet_op_kind
 OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO = 5, 6, 7, 8, 9, 10, 11
+OP_AMAX = 12
 # tdet_dtype
 BF16, F32, F16 = 0, 1, 2
 FLAG_RELU = 1
@@ -49,7 +50,7 @@ class TdetOp(ctypes.Structure):
         ("bound_consts", ctypes.c_void_p),
         ("mask", ctypes.c_void_p), ("gy", ctypes.c_void_p),
         ("gy_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
-        ("dw", ctypes.c_void_p),
+        ("dw", ctypes.c_void_p), ("gy_meta", ctypes.c_void_p),
     ]
 
 

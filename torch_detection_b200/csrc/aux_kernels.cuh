@@ -300,29 +300,79 @@ dilate2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
   }
 }
 
-__device__ __forceinline__ uint32_t add_mask_bf16x2(uint32_t a, uint32_t b, uint32_t m) {
-  float lo = bf16_lo(a) + bf16_lo(b), hi = bf16_hi(a) + bf16_hi(b);
-  if ((m & 0x00007FFFu) == 0u) lo = 0.0f;
-  if ((m & 0x7FFF0000u) == 0u) hi = 0.0f;
-  return pack_bf16x2(lo, hi);
+// y = (x * 2^ex + res * 2^er) * (mask != 0), stored as y_dtype * 2^ey.  Formats are per tensor (bf16 or fp16);
+// ey is either 0 or, when y_meta/scaled is set, chosen so that amax(x) + amax(res) < 2^15 (fp16-safe), in which
+// case that bound is also recorded as y's amax (an upper bound is all downstream exponent choices need).
+struct AddMaskParams {
+  const uint4* x;
+  const uint4* res;
+  const uint4* mask;
+  uint4* y;
+  long long total;  // uint4 groups
+  int x_fp16, res_fp16, y_fp16, scaled;
+  const TensorMeta* x_meta;
+  const TensorMeta* res_meta;
+  TensorMeta* y_meta;
+};
+
+__global__ void __launch_bounds__(256)
+add_mask_kernel(const AddMaskParams p) {
+  const int ex = p.x_meta ? p.x_meta->e : 0;
+  const int er = (p.res && p.res_meta) ? p.res_meta->e : 0;
+  int ey = 0;
+  if (p.scaled) {
+    float bound = p.x_meta ? __uint_as_float(p.x_meta->amax_bits) : 0.0f;
+    if (p.res && p.res_meta) bound += __uint_as_float(p.res_meta->amax_bits);
+    if (bound > 0.0f && bound < 3.0e38f) ey = ilogbf(bound) - 14;
+    ey = max(-100, min(100, ey));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      p.y_meta->e = ey;
+      p.y_meta->amax_bits = __float_as_uint(bound);
+    }
+  }
+  const float mx = ldexpf(1.0f, ex - ey), mr = ldexpf(1.0f, er - ey);
+  const bool xf = p.x_fp16 != 0, rf = p.res_fp16 != 0, yf = p.y_fp16 != 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < p.total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = __ldg(p.x + i);
+    const uint4 b = p.res ? __ldg(p.res + i) : make_uint4(0u, 0u, 0u, 0u);
+    const uint4 m = p.mask ? __ldg(p.mask + i) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, mw[4] = {m.x, m.y, m.z, m.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float alo, ahi, blo, bhi;
+      unpack16x2(aw[j], xf, alo, ahi);
+      unpack16x2(bw[j], rf, blo, bhi);
+      float lo = fmaf(blo, mr, alo * mx), hi = fmaf(bhi, mr, ahi * mx);
+      if ((mw[j] & 0x00007FFFu) == 0u) lo = 0.0f;
+      if ((mw[j] & 0x7FFF0000u) == 0u) hi = 0.0f;
+      ow[j] = pack16x2(lo, hi, yf);
+    }
+    p.y[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
 }
 
-// y = (x + residual) * (mask != 0); residual / mask nullable
+// meta->amax_bits = max |x| * 2^e_x  (atomicMax on the bit pattern; the plan zeroes the arena first)
 __global__ void __launch_bounds__(256)
-add_mask_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, const uint4* __restrict__ mask,
-                uint4* __restrict__ y, long long total) {
+amax_kernel(const uint4* __restrict__ x, long long total, int x_fp16, const TensorMeta* x_meta, TensorMeta* meta) {
+  float amax = 0.0f;
+  const bool xf = x_fp16 != 0;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 a = __ldg(x + i);
-    const uint4 b = res ? __ldg(res + i) : make_uint4(0u, 0u, 0u, 0u);
-    const uint4 m = mask ? __ldg(mask + i) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
-    uint4 o;
-    o.x = add_mask_bf16x2(a.x, b.x, m.x);
-    o.y = add_mask_bf16x2(a.y, b.y, m.y);
-    o.z = add_mask_bf16x2(a.z, b.z, m.z);
-    o.w = add_mask_bf16x2(a.w, b.w, m.w);
-    y[i] = o;
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      unpack16x2(aw[j], xf, lo, hi);
+      amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
+    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0 && amax > 0.0f)
+    atomicMax(&meta->amax_bits, __float_as_uint(ldexpf(amax, x_meta ? x_meta->e : 0)));
 }
 
 }  // namespace tdet

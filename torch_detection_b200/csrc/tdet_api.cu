@@ -563,7 +563,7 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
   wp.dw = o.dw;
   wp.scale = o.scale;
   wp.x_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
-  wp.g_meta = nullptr;
+  wp.g_meta = reinterpret_cast<const TensorMeta*>(o.gy_meta);
   const bool tiled = (o.kh == 1 && o.kw == 1 && o.stride == 1 && o.pad == 0);
   wp.x_im2col = tiled ? 0 : 1;
   int rc = encode_2d(&wp.tmap_g, o.gy, o.gy_dtype, o.cout, wp.M, l.wg_pix, "output gradient");
@@ -769,13 +769,21 @@ int build_launch(Launch& l, const DeviceInfo& di) {
       l.bytes = 2.0 * o.n * o.cin * (static_cast<double>(o.h) * o.w + static_cast<double>(o.ho) * o.wo);
       return TDET_OK;
     case TDET_OP_ADD_MASK:
-      if (o.cin % 8 || !o.x || !o.y || o.x_dtype != TDET_BF16)
+      if (o.cin % 8 || !o.x || !o.y || !is16(o.x_dtype) || !is16(o.y_dtype) || (o.residual && !is16(o.residual_dtype)))
         return fail(TDET_ERR_INVALID_ARGUMENT, "add_mask: bad arguments");
+      if ((o.flags & TDET_FLAG_SCALED_OUT) &&
+          (o.y_dtype != TDET_F16 || !o.y_meta || !o.x_meta || (o.residual && !o.residual_meta)))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "add_mask: SCALED_OUT needs an F16 y with y_meta and input metas");
       l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w * (2 + (o.residual ? 1 : 0) + (o.mask ? 1 : 0));
       return TDET_OK;
     case TDET_OP_ZERO:
       if (!o.y || o.x_stride[0] <= 0) return fail(TDET_ERR_INVALID_ARGUMENT, "zero: bad arguments");
       l.bytes = static_cast<double>(o.x_stride[0]);
+      return TDET_OK;
+    case TDET_OP_AMAX:
+      if (o.cin % 8 || !o.x || !o.y_meta || !is16(o.x_dtype))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "amax: bad arguments");
+      l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w;
       return TDET_OK;
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
@@ -867,10 +875,28 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       return TDET_OK;
     }
     case TDET_OP_ADD_MASK: {
+      AddMaskParams ap{};
+      ap.x = static_cast<const uint4*>(o.x);
+      ap.res = static_cast<const uint4*>(o.residual);
+      ap.mask = static_cast<const uint4*>(o.mask);
+      ap.y = static_cast<uint4*>(o.y);
+      ap.total = static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8);
+      ap.x_fp16 = o.x_dtype == TDET_F16;
+      ap.res_fp16 = o.residual_dtype == TDET_F16;
+      ap.y_fp16 = o.y_dtype == TDET_F16;
+      ap.scaled = (o.flags & TDET_FLAG_SCALED_OUT) ? 1 : 0;
+      ap.x_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
+      ap.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+      ap.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+      add_mask_kernel<<<grid_for(ap.total, di.num_sms), 256, 0, st>>>(ap);
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
+    case TDET_OP_AMAX: {
       const long long total = static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8);
-      add_mask_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(
-          static_cast<const uint4*>(o.x), static_cast<const uint4*>(o.residual),
-          static_cast<const uint4*>(o.mask), static_cast<uint4*>(o.y), total);
+      amax_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(
+          static_cast<const uint4*>(o.x), total, o.x_dtype == TDET_F16 ? 1 : 0,
+          reinterpret_cast<const TensorMeta*>(o.x_meta), reinterpret_cast<TensorMeta*>(o.y_meta));
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

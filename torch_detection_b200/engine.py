@@ -327,7 +327,7 @@ def op_wgrad(x, gy, dw, kh, kw, stride, pad, dil=1, scale=None):
     assert dw.dtype == torch.float32 and dw.numel() == op.cout * kh * kw * op.cin
     op.x_dtype, op.gy_dtype = _TD[x.dtype], _TD[gy.dtype]
     op.x, op.gy, op.dw = x.ptr, gy.ptr, dw.data_ptr()
-    op.x_meta = x.meta
+    op.x_meta, op.gy_meta = x.meta, gy.meta
     op.scale = _ptr(scale)
     return op
 
@@ -357,7 +357,7 @@ def _op_eltwise(kind, x, y):
     op.n, op.h, op.w, op.cin = n, h, w, c
     op.cout = c
     op.ho, op.wo = y.shape[1], y.shape[2]
-    op.x_dtype = op.y_dtype = _TD[x.dtype]
+    op.x_dtype, op.y_dtype = _TD[x.dtype], _TD[y.dtype]
     op.x, op.y = x.ptr, y.ptr
     return op
 
@@ -370,12 +370,28 @@ def op_dilate2(x, y):
     return _op_eltwise(_C.OP_DILATE2, x, y)
 
 
-def op_add_mask(x, y, residual=None, mask=None):
+def op_add_mask(x, y, residual=None, mask=None, scaled_out=False):
+    """y = (x + residual) * (mask != 0) across 16-bit formats / per-tensor exponents; scaled_out: y (fp16)
+    gets an exponent chosen from the inputs' recorded |max| (their metas must carry it)."""
     op = _op_eltwise(_C.OP_ADD_MASK, x, y)
+    op.x_meta, op.y_meta = x.meta, y.meta
+    if scaled_out:
+        op.flags = _C.FLAG_SCALED_OUT
     if residual is not None:
-        op.residual, op.residual_dtype = residual.ptr, _TD[residual.dtype]
+        op.residual, op.residual_dtype, op.residual_meta = residual.ptr, _TD[residual.dtype], residual.meta
     if mask is not None:
         op.mask = mask.ptr
+    return op
+
+
+def op_amax(x, meta):
+    """meta.amax = max |x| (true values); `meta` = device address of a tdet_tensor_meta."""
+    n, h, w, c = x.shape
+    op = _C.TdetOp()
+    op.kind = _C.OP_AMAX
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.x_dtype = _TD[x.dtype]
+    op.x, op.x_meta, op.y_meta = x.ptr, x.meta, meta
     return op
 
 

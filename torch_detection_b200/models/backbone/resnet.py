@@ -232,9 +232,10 @@ class ResNet(nn.Module):
     def _build_plan(self, x, cache, train_from=None):
         """Compiles the topology for one input geometry into tdet_ops.
 
-        train_from (training path): index of the first trainable stage.  Activations are then plain
-        bf16 (the wgrad MMA needs the saved input and the bf16 gradient in one format), nothing from
-        that stage on is recycled, and the per-block records the backward plan needs are returned.
+        train_from (training path): index of the first trainable stage.  Nothing from that stage on is
+        recycled, stage outputs are kept in the internal format too (the returned bf16 tensors are
+        converted copies: the wgrad MMA needs the saved input and the gradient in ONE format), and the
+        per-block records the backward plan needs are returned.
 
         Internal activations are fp16 significands with a per-tensor power-of-two exponent chosen on
         the device (TDET_FLAG_SCALED_OUT); stage outputs are plain bf16 (they are what the module
@@ -243,18 +244,18 @@ class ResNet(nn.Module):
         n, _, h, w = x.shape
         dev = x.device
         train = train_from is not None
-        internal = torch.bfloat16 if train else INTERNAL_DTYPE
+        internal = INTERNAL_DTYPE
         scaled = internal == torch.float16
         ops = []
         pool = _BufferPool(dev)
         segs = [(list(range(len(self.res_layers))), n)] if train else self._segments(n)
         records = []
         max_chunks = max((n + c - 1) // c for _, c in segs)
-        n_meta = 8 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
+        n_meta = 16 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
         meta = engine.MetaArena(n_meta, dev)
 
         def new_act(shape, dtype):
-            return engine.Act(pool.get(shape), shape, dtype, None if train else meta.new())
+            return engine.Act(pool.get(shape), shape, dtype, meta.new())
 
         def conv(name, module, bn, src, dst, residual=None, relu=True):
             k = module.kernel_size[0]
@@ -291,9 +292,14 @@ class ResNet(nn.Module):
                 outs.append(t)
             else:
                 t = pool.get((n, sh_, sw_, sc_))
-            boundary.append((t, None if train else meta.new()))
+            boundary.append((t, meta.new()))
+        # training: stage outputs in the internal format (saved for backward, feed the next stage)
+        cints = [engine.Act(pool.get((n, sh_, sw_, sc_)), (n, sh_, sw_, sc_), internal, meta.new())
+                 for (sh_, sw_, sc_) in geo] if train else None
 
         def boundary_act(li, i0, cn):
+            if train:
+                return cints[li]
             t, m = boundary[li]
             sh_, sw_, sc_ = geo[li]
             return engine.Act(t, (cn, sh_, sw_, sc_), torch.bfloat16, m, offset=i0 * sh_ * sw_ * sc_)
@@ -303,7 +309,7 @@ class ResNet(nn.Module):
                 cn = min(chunk, n - i0)
                 if stages[0] == 0:
                     staged = pool.get((cn,) + engine.stem_staging_dims(ho, wo) + (4,))
-                    staged_meta = None if train else meta.new()
+                    staged_meta = meta.new()
                     ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta))
                     stem_out = new_act((cn, ho, wo, 64), internal)
                     stem_bn = getattr(self, self.norm_name)
@@ -378,11 +384,14 @@ class ResNet(nn.Module):
                             pool.release(shortcut.buf)
                         cur = src
                         cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
+                    if train and li in self.out_indices:
+                        # the returned feature map: plain bf16 copy of the internal stage output
+                        t, m = boundary[li]
+                        ops.append(engine.op_add_mask(cints[li], engine.Act(t, cints[li].shape, torch.bfloat16, m)))
         plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers], dev, meta=meta)
         if train:
             # records reference stage outputs through the plan's placeholder tensors: remember which
-            plan.out_placeholders = {id(t): i for i, t in enumerate(outs)}
-            return plan, [tuple(o.shape) for o in outs], records, boundary, geo
+            return plan, [tuple(o.shape) for o in outs], records, cints, geo
         return plan, [tuple(o.shape) for o in outs]
 
     def forward(self, x):
@@ -452,16 +461,15 @@ class ResNet(nn.Module):
         """{name: fp32 NCHW CPU tensor} of what the last training forward saved for backward (block
         inputs ``layerL.B.in`` and every conv's stored output ``layerL.B.convK``).  Test/debug API:
         the gradient tests feed these to their fp32 checker so that ReLU masks match the kernels'."""
-        plan, out_shapes, records, boundary, geo = self._plans[self._train_state["key"]]
-        outs = self._train_state["outs"]
+        plan, out_shapes, records, cints, geo = self._plans[self._train_state["key"]]
+        raw = plan.meta.tensor.cpu()
+        base = plan.meta.tensor.data_ptr()
 
         def fetch(act):
-            pos = plan.out_placeholders.get(id(act.buf))
-            if pos is not None:
-                return outs[pos].detach().float().cpu()
             n, h, w, c = act.shape
-            flat = act.buf[act.offset:act.offset + n * h * w * c]
-            return flat.view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()
+            flat = act.buf[act.offset:act.offset + n * h * w * c].view(act.dtype)
+            e = int(raw[(act.meta - base) // 8, 0]) if act.meta is not None else 0
+            return flat.view(n, h, w, c).permute(0, 3, 1, 2).float().cpu() * (2.0 ** e)
 
         saved = {}
         for r in records:
@@ -490,31 +498,38 @@ class ResNet(nn.Module):
 
     def _build_bwd_plan(self, state, cache):
         """Backward plan for the saved forward `state`: stages deepest first, blocks last to first."""
-        plan, out_shapes, records, boundary, geo = self._plans[state["key"]]
+        plan, out_shapes, records, cints, geo = self._plans[state["key"]]
         dev = state["x"].device
         outs = state["outs"]
-        n = state["x"].shape[0]
-        bb = training.BackwardBuilder(dev, cache)
+        scaled = INTERNAL_DTYPE == torch.float16
+        # gradient tensors are stored in the format of the saved activations (one format per MMA): fp16
+        # significands with a per-tensor exponent chosen on the device (8x finer than bf16), or plain bf16
+        n_blocks = sum(len(getattr(self, l)) for l in self.res_layers)
+        meta = engine.MetaArena(16 + 8 * n_blocks, dev) if scaled else None
+        bb = training.BackwardBuilder(dev, cache, INTERNAL_DTYPE, meta)
         out_pos = {li: i for i, li in enumerate(sorted(self.out_indices))}
         g_ext = [engine.nhwc_empty(*_nhwc_shape(o), dev) for o in outs]  # placeholders, re-bound per run
+        ext_acts = {}
+
+        def ext_grad(li):
+            """Gradient autograd hands in for returned stage li (plain bf16); its |max| is measured once so
+            that the consuming kernel can bound its own output."""
+            if li not in ext_acts:
+                m = meta.new() if scaled else None
+                a = engine.Act(g_ext[out_pos[li]], cints[li].shape, torch.bfloat16, m)
+                if scaled:
+                    bb.ops.append(engine.op_amax(engine.Act(a.buf, a.shape, a.dtype, None), m))
+                ext_acts[li] = a
+            return ext_acts[li]
 
         def stage_act(li):
-            """Forward output of stage li as an Act (an ext output or a static boundary buffer)."""
-            sh_, sw_, sc_ = geo[li]
-            if li in out_pos:
-                return engine.Act(outs[out_pos[li]], (n, sh_, sw_, sc_), torch.bfloat16)
-            return engine.Act(boundary[li][0], (n, sh_, sw_, sc_), torch.bfloat16)
+            return cints[li]
 
         def scale_of(name, bn):
             return cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))[0]
 
         def live(act):
-            """Saved activation as seen by this plan: stage outputs are the forward's returned tensors
-            (external, re-bound per run), everything else sits in the forward plan's static buffers."""
-            pos = plan.out_placeholders.get(id(act.buf))
-            if pos is None:
-                return act
-            return engine.Act(outs[pos], act.shape, act.dtype, None, act.offset)
+            return act
 
         nst = len(self.res_layers)
         first = self._train_from
@@ -537,7 +552,7 @@ class ResNet(nn.Module):
                 # gradient of the top stage output arrives from autograd only: apply its ReLU mask
                 top = stage_act(li)
                 g_cur = bb.new_act(top.shape)
-                bb.ops.append(engine.op_add_mask(engine.act_of(g_ext[out_pos[li]]), g_cur, mask=top))
+                bb.ops.append(engine.op_add_mask(ext_grad(li), g_cur, mask=top, scaled_out=scaled))
             for r in reversed(blocks):
                 unit, pre = r["unit"], r["pre"]
                 xin, acts = live(r["xin"]), [live(a) for a in r["acts"]]
@@ -580,7 +595,7 @@ class ResNet(nn.Module):
                             gd = bb.new_act((xin.shape[0], gM.shape[1], gM.shape[2], xin.shape[3]))
                         else:
                             raise NotImplementedError("shortcut stride %d" % s_ds)
-                        bb.ops.append(engine.op_conv(gM, wd, gd, 1, 1, 1, 0, 1))
+                        bb.conv_dgrad_op(name_ds, ds[0], wd, gM, gd, 1, 0, 1, deps=_bn_deps(ds[1]))
                         if s_ds == 1:
                             residual = gd
                         else:
@@ -590,12 +605,12 @@ class ResNet(nn.Module):
                     merged = None
                     if is_first_block and (li - 1) in out_pos:
                         # the stage input is a returned feature map: add the gradient autograd hands in
-                        ext = engine.act_of(g_ext[out_pos[li - 1]])
+                        ext = ext_grad(li - 1)
                         if residual is None:
                             residual = ext
                         else:
                             merged = bb.new_act(xin.shape)
-                            bb.ops.append(engine.op_add_mask(residual, merged, residual=ext))
+                            bb.ops.append(engine.op_add_mask(residual, merged, residual=ext, scaled_out=scaled))
                             residual = merged
                     g_in = bb.dgrad(name, module, sc, g, xin.shape, residual=residual, coarse=coarse, mask=xin,
                                     deps=_bn_deps(getattr(unit, unit.norm_names[0])))
@@ -613,8 +628,7 @@ class ResNet(nn.Module):
         shift += len(head)
         segments = [(a + shift, b + shift, k) for a, b, k in segments]
         segments[0] = (0, segments[0][1], segments[0][2])
-        ext = g_ext + [outs[out_pos[li]] for li in sorted(out_pos)]
-        bplan = engine.Plan(ops, ext, [cache, bb.buffers, bb.acc_ws, [b.flat for b in buckets]], dev)
+        bplan = engine.Plan(ops, g_ext, [cache, bb.buffers, bb.acc_ws, [b.flat for b in buckets]], dev, meta=meta)
         return bplan, buckets, segments
 
     def _train_backward(self, state, gouts):
@@ -629,8 +643,7 @@ class ResNet(nn.Module):
             self._plans[bkey] = entry
         bplan, buckets, segments = entry
         outs = state["outs"]
-        gs = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
-        ext = gs + outs
+        ext = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
         sync = getattr(self, "_grad_sync", None)
         reduced = []
         for a, b, k in segments:

@@ -132,9 +132,12 @@ class BackwardBuilder(object):
     """Emits the backward ops of conv layers into one op list, with a liveness-based pool for the
     gradient tensors and one zero-initialised workspace for the k x k wgrad accumulators."""
 
-    def __init__(self, device, cache):
+    def __init__(self, device, cache, dtype=torch.bfloat16, meta=None):
         self.device = device
         self.cache = cache     # operand cache of the owning module (rotated weights live there)
+        self.dtype = dtype     # storage format of the gradient tensors (= format of the saved activations)
+        self.meta = meta       # engine.MetaArena: gradient tensors carry a per-tensor power-of-two exponent
+        self.scaled = meta is not None
         self.ops = []
         self.free = {}
         self.buffers = []
@@ -142,7 +145,7 @@ class BackwardBuilder(object):
         self.acc_ws = None
 
     # ---- gradient tensors ---------------------------------------------------------------------
-    def new_act(self, shape):
+    def new_act(self, shape, meta="new"):
         numel = 1
         for s in shape:
             numel *= s
@@ -150,9 +153,11 @@ class BackwardBuilder(object):
         if bucket:
             buf = bucket.pop()
         else:
-            buf = torch.empty(numel, dtype=torch.bfloat16, device=self.device)
+            buf = torch.empty(numel, dtype=torch.bfloat16, device=self.device)  # raw 16-bit storage
             self.buffers.append(buf)
-        return engine.Act(buf, shape, torch.bfloat16)
+        if meta == "new":
+            meta = self.meta.new() if self.scaled else None
+        return engine.Act(buf, shape, self.dtype, meta)
 
     def release(self, act):
         if act is not None:
@@ -162,9 +167,20 @@ class BackwardBuilder(object):
     def dgrad_weight(self, name, module, scale, deps=()):
         """`scale` is the folded-BN scale tensor of the conv (refreshed in place before this entry: the
         cache keeps insertion order); `deps` = the BatchNorm parameters / buffers it derives from."""
-        return self.cache.get((name, "wd"),
-                              lambda out: engine.pack_dgrad_weight(module.weight, scale, out=out),
+        return self.cache.get((name, "wd", self.dtype),
+                              lambda out: engine.pack_dgrad_weight(module.weight, scale, dtype=self.dtype, out=out),
                               deps=(module.weight,) + tuple(deps))
+
+    def dgrad_consts(self, name, module, wd, deps=()):
+        """{G, 0} with |dgrad(g)| <= G * max|g|: the bound the kernel picks the output exponent from."""
+        if not self.scaled:
+            return None
+        return self.cache.get((name, "wdc", self.dtype), lambda out: engine.bound_consts(wd, None, None, out=out),
+                              deps=(module.weight,) + tuple(deps))
+
+    def conv_dgrad_op(self, name, module, wd, src, dx, k, pad, dil, deps=(), **kw):
+        self.ops.append(engine.op_conv(src, wd, dx, k, k, 1, pad, dil, consts=self.dgrad_consts(name, module, wd, deps),
+                                       scaled_out=self.scaled, **kw))
 
     def dgrad(self, name, module, scale, g, in_shape, residual=None, coarse=None, mask=None, deps=()):
         """Gradient w.r.t. the input (shape `in_shape`, NHWC) of conv `module` given g = dL/d(BN(conv))."""
@@ -176,14 +192,15 @@ class BackwardBuilder(object):
         tmp = None
         if stride == 2:
             # adjoint of the output subsampling: zero-insertion upsample, then the stride-1 dgrad
+            # (zero insertion keeps the exponent and the |max|: the metadata is shared)
             tmp = self.new_act((in_shape[0], in_shape[1] + 2 * pad - dil * (k - 1),
-                                in_shape[2] + 2 * pad - dil * (k - 1), g.shape[3]))
+                                in_shape[2] + 2 * pad - dil * (k - 1), g.shape[3]), meta=g.meta)
             self.ops.append(engine.op_dilate2(g, tmp))
             src = tmp
         elif stride != 1:
             raise NotImplementedError("dgrad for conv stride %d" % stride)
-        self.ops.append(engine.op_conv(src, wd, dx, k, k, 1, dil * (k - 1) - pad, dil, residual=residual,
-                                       coarse=coarse, coarse_parity=coarse is not None, mask=mask))
+        self.conv_dgrad_op(name, module, wd, src, dx, k, dil * (k - 1) - pad, dil, deps, residual=residual,
+                           coarse=coarse, coarse_parity=coarse is not None, mask=mask)
         self.release(tmp)
         return dx
 
