@@ -179,7 +179,10 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
             feats[j] = saved_neck["C%d" % j].float()  # frozen stage output: a constant for the neck
     lats = [None] * n
     for j in range(n - 1, -1, -1):
-        y = F.conv2d(_tap(feats[j], kr), _ste(neck["lateral_convs.%d.conv.weight" % j]),
+        # the neck consumes the returned bf16 feature map (a converted copy of the backbone's internal
+        # stage output): forward value = what the neck stored, gradient straight through to the backbone
+        cj = _force(feats[j], saved_neck["C%d" % j], False) if feats[j].requires_grad else feats[j]
+        y = F.conv2d(_tap(cj, kr), _ste(neck["lateral_convs.%d.conv.weight" % j]),
                      neck["lateral_convs.%d.conv.bias" % j])
         if j < n - 1:
             y = y + F.interpolate(_tap(lats[j + 1], kr), scale_factor=2, mode="nearest")

@@ -5,24 +5,19 @@ backward plans, against the CPU gradient oracle.
 
 Gates (bf16 tolerance of north_star, rel-L2 <= 1e-2), all against the TEACHER-FORCED oracle = fp32
 autograd over the kernels' own stored activations / ReLU masks (grad_oracle.teacher_forced_grads):
-  * the 16 FPN parameter gradients and the conv-weight gradients of the LAST backbone stage vs the
-    exact fp32 backward: <= 1e-2 (measured 4-9e-3);
-  * arithmetic check where the rounding chain is still short: the FPN gradients and the last block's
-    conv3 vs the oracle with rounding hooks where the kernels round (kernel_rounding=True):
-    <= 1.5e-3 (measured 2-8e-4: fp32 accumulation order + the few bf16 near-ties it flips);
-  * every other backbone gradient vs the exact fp32 backward: REPORTED and sanity-gated at 4e-2.
-    The gradient chain is stored in bf16, so the deviation random-walks with one 2^-9 rounding per
-    stored tensor and per scale-folded dgrad operand: ~sqrt(2*depth)*1.7e-3 = 0.8-1.9e-2 at
-    ResNet-50 depth (tools/diag_grads.py: the oracle's own rounding model shows the same curve
-    against its exact backward, and kernel-vs-model decorrelates after a few layers because a 1e-3
-    input difference already changes bf16 rounding decisions).  DESIGN.md section 7: an fp16
-    block-exponent gradient chain (8x finer) is the remedy;
-  * the 16 FPN gradients also vs the plain fp32 oracle (<= 2e-2: the laterals' wgrad operand C_k
-    itself carries the training forward's plain-bf16 error of ~1e-2);
+  * EVERY parameter gradient -- the 16 of the FPN and every trainable backbone conv weight (42 for
+    ResNet-50 with a frozen stage 1, 80 for ResNet-101 from stage 3) -- vs the exact fp32 backward:
+    <= 1e-2.  Measured 4.1-6.8e-3 with the default fp16 block-exponent gradient chain (the plain-bf16
+    chain of TDET_INTERNAL_DTYPE=bf16 random-walks to 1.1-2.6e-2 at this depth: one 2^-9 rounding per
+    stored gradient tensor and per scale-folded dgrad operand, tools/diag_grads.py);
+  * arithmetic check of the neck (its gradient chain is plain bf16 and short): the 16 FPN gradients
+    vs the oracle with rounding hooks where the kernels round (kernel_rounding=True): <= 1.5e-3
+    (measured 2-4e-4: fp32 accumulation order + the few bf16 near-ties it flips);
+  * the 16 FPN gradients also vs the plain fp32 oracle (<= 2e-2; measured ~5e-3);
   * local consistency of the training forward: each P level vs an fp32 recomputation from the
     kernels' own stored laterals (<= 4e-3, one bf16 rounding);
-  * reported, not gated: backbone gradients vs the plain fp32 oracle (ReLU mask flips; 0.2-0.6, like
-    PyTorch's own bf16) with their cosine similarity.
+  * reported, not gated: backbone gradients vs the plain fp32 oracle (ReLU mask flips of the 16-bit
+    forward; 0.1-0.25, cosine >= 0.97 -- PyTorch's own bf16 autocast is worse) .
 """
 import pytest
 import torch
@@ -106,19 +101,10 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
            max(exact_b.values()), sorted(exact_b.values())[len(exact_b) // 2]))
     print("backbone grads vs plain fp32 (report only): max rel-L2 %.2e, min cosine %.4f" %
           (max(v[0] for v in plain_b.values()), min(v[1] for v in plain_b.values())))
-    last_stage = max(int(k[5]) for k in exact_b)
-    last_block = max(int(k.split(".")[1]) for k in exact_b if int(k[5]) == last_stage)
-    top = "layer%d.%d.conv%d.weight" % (last_stage, last_block, 3 if depth >= 50 else 2)
-    arith = dict(errs_n)
-    arith[top] = errs_b[top]
-    bad = {k: v for k, v in arith.items() if not v <= 1.5e-3}
-    assert not bad, "over 1.5e-3 vs the teacher-forced oracle with kernel rounding: %s" % bad
-    bad = {k: v for k, v in exact_n.items() if not v <= GATE}
-    assert not bad, "FPN gradients over 1e-2 vs the exact teacher-forced backward: %s" % bad
-    bad = {k: v for k, v in exact_b.items() if int(k[5]) == last_stage and not v <= GATE}
-    assert not bad, "last-stage gradients over 1e-2 vs the exact teacher-forced backward: %s" % bad
-    bad = {k: v for k, v in exact_b.items() if not v <= 4e-2}
-    assert not bad, "backbone gradients over 4e-2 vs the exact teacher-forced backward: %s" % bad
+    bad = {k: v for k, v in errs_n.items() if not v <= 1.5e-3}
+    assert not bad, "FPN gradients over 1.5e-3 vs the teacher-forced oracle with kernel rounding: %s" % bad
+    bad = {k: v for k, v in list(exact_n.items()) + list(exact_b.items()) if not v <= GATE}
+    assert not bad, "gradients over 1e-2 vs the exact teacher-forced backward: %s" % bad
     bad = {k: v for k, v in plain_n.items() if not v <= 2e-2}
     assert not bad, "FPN gradients over 2e-2 vs the plain fp32 oracle: %s" % bad
     # frozen parameters received nothing
@@ -157,9 +143,11 @@ def test_second_step_uses_updated_weights(cuda_device):
                                                     bb_weight_dtype=_backbone_weight_dtype())
     for k, p in neck.named_parameters():
         assert orc.rel_l2(p.grad.cpu(), tn[k]) <= 1.5e-3, k
+    xb, _, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, bb.saved_activations(), neck.saved_activations(),
+                                                   50, grads, bb_weight_dtype=_backbone_weight_dtype())
     for k, p in bb.named_parameters():
         if p.grad is not None:
-            assert orc.rel_l2(p.grad.cpu(), tb[k]) <= 4e-2, k
+            assert orc.rel_l2(p.grad.cpu(), xb[k]) <= GATE, k
 
 
 def test_eval_mode_unchanged_and_unsupported_training_configs(cuda_device):
