@@ -85,7 +85,7 @@ typedef enum tdet_op_kind {
   TDET_OP_AMAX = 12      /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
 } tdet_op_kind;
 
-typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2 } tdet_dtype;
+typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
 
 enum {
   TDET_FLAG_RELU = 1,       /* ReLU after scale/shift/residual (resnet.py:48,58,103,108,118) */
@@ -106,8 +106,11 @@ typedef struct tdet_tensor_meta {
 /*
  * One step of the path.  Unused fields must be zero / NULL.
  *
- * TDET_OP_PREP      x: logical (n, 3, h, w) image batch of x_dtype (F32/BF16) with element strides
- *                   x_stride[] = {n, c, h, w} (NCHW-contiguous or channels_last both work)
+ * TDET_OP_PREP      x: logical (n, 3, hc, wc) image batch of x_dtype (F32/BF16/U8) with element strides
+ *                   x_stride[] = {n, c, h, w} (NCHW-contiguous, channels_last, or an HWC uint8 batch viewed
+ *                   as NCHW all work); hc/wc = valid extent (0 = h/w), zero-padded to the (h, w) the stem
+ *                   sees (pad-to-size-divisor); optional scale/shift[3]: v*scale[c] + shift[c], the data
+ *                   layer's (v - mean)/std (datasets/dataset_transforms.py:29-44 steps 2 and 5).
  *                   y: bf16 [n][hp][wp][4] with (hp, wp) = tdet_stem_staging_dims(ho, wo) (ho/wo = stem output
  *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
  *                   y_meta (optional): receives the image's |max| (exponent 0).

@@ -230,6 +230,40 @@ def fpn_forward(sd, inputs, in_channels, out_channels, num_outs, start_level=0, 
     return tuple(outs)
 
 
+def pafpn_forward(sd, inputs, in_channels, out_channels, num_outs, start_level=0, end_level=-1,
+                  add_extra_convs=False, activation=None):
+    """PAFPN.forward (models/necks/pafpn.py:108-148), normalize=None: the FPN pyramid P, then the
+    bottom-up path N_i = pa_convs2[i-1](P_i + pa_convs1[i-1](N_{i-1})) (:131-134); `activation` is the
+    ConvModule activation of the pa convs (None or 'relu', applied to each conv's output)."""
+    assert len(inputs) == len(in_channels)
+    lo, hi = fpn_level_range(len(in_channels), start_level, end_level)
+    n = hi - lo
+    act = (lambda t: F.relu(t, inplace=True)) if activation == "relu" else (lambda t: t)
+    lats = [F.conv2d(inputs[lo + j], sd["lateral_convs.%d.conv.weight" % j],
+                     sd["lateral_convs.%d.conv.bias" % j]) for j in range(n)]
+    for j in range(n - 1, 0, -1):
+        lats[j - 1] += F.interpolate(lats[j], scale_factor=2, mode="nearest")
+    outs = [F.conv2d(lats[j], sd["fpn_convs.%d.conv.weight" % j],
+                     sd["fpn_convs.%d.conv.bias" % j], 1, 1) for j in range(n)]
+    for j in range(1, n):
+        down = act(F.conv2d(outs[j - 1], sd["pa_convs1.%d.conv.weight" % (j - 1)],
+                            sd["pa_convs1.%d.conv.bias" % (j - 1)], 2, 1))
+        outs[j] = act(F.conv2d(outs[j] + down, sd["pa_convs2.%d.conv.weight" % (j - 1)],
+                               sd["pa_convs2.%d.conv.bias" % (j - 1)], 1, 1))
+    if num_outs > len(outs):
+        if not add_extra_convs:
+            for _ in range(num_outs - n):
+                outs.append(F.max_pool2d(outs[-1], 1, stride=2))
+        else:
+            outs.append(F.conv2d(inputs[hi - 1], sd["fpn_convs.%d.conv.weight" % n],
+                                 sd["fpn_convs.%d.conv.bias" % n], 2, 1))
+            for j in range(n + 1, num_outs):
+                outs.append(F.conv2d(F.relu(outs[-1], inplace=True),
+                                     sd["fpn_convs.%d.conv.weight" % j],
+                                     sd["fpn_convs.%d.conv.bias" % j], 2, 1))
+    return tuple(outs)
+
+
 def resnet_fpn_forward(bb_sd, neck_sd, x, depth, out_channels=256, num_outs=5):
     kind, _ = ARCH[depth]
     in_ch = [64 * 2 ** i * EXPANSION[kind] for i in range(4)]

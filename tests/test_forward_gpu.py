@@ -188,3 +188,63 @@ def test_config5_sweep_depth_by_size(cuda_device, depth, hw, batch):
     _check_levels([t[:1] for t in feats], want_f, ["C2", "C3", "C4", "C5"])
     e = _check_levels([t[:1] for t in outs], want_p, ["P2", "P3", "P4", "P5", "P6"])
     print("rel-L2 sweep", depth, hw, batch, e)
+
+
+@pytest.mark.parametrize("activation", [None, "relu"])
+def test_pafpn_neck(cuda_device, activation):
+    """PAFPN (bottom-up path fused as conv + residual) against the CPU oracle."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    dev = cuda_device
+    bb, _ = helpers.build_product_pair(50, seed=6, bnstats=True)
+    torch.manual_seed(6)
+    neck = obj_from_dict(dict(type="PAFPN", in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5,
+                              activation=activation), parent=models.necks)
+    neck.init_weights()
+    neck.eval()
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(2, 3, 160, 224, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    wf = orc.resnet_forward(bsd, x.float(), 50)
+    wp = orc.pafpn_forward(nsd, [f.clone() for f in wf], [256, 512, 1024, 2048], 256, 5, activation=activation)
+    feats, outs = _run_product(bb, neck, x, dev)
+    assert len(outs) == 5 and all(o.dtype == torch.bfloat16 for o in outs)
+    e = _check_levels(outs, wp, ["N2", "N3", "N4", "N5", "N6"])
+    print("rel-L2 PAFPN", activation, e)
+    neck.train()
+    with pytest.raises(NotImplementedError):
+        neck(feats)
+
+
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32])
+def test_input_transform_normalise_and_pad_in_the_loader(cuda_device, dtype):
+    """the data layer's (v - mean)/std and pad-to-size-divisor (reference
+    datasets/dataset_transforms.py:29-44) folded into TDET_OP_PREP: raw HWC uint8 (or NCHW fp32) batch in,
+    features of the normalised, zero-padded image out."""
+    dev = cuda_device
+    bb, neck = helpers.build_product_pair(50, seed=3, bnstats=True)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    means, stds = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    g = torch.Generator().manual_seed(2)
+    raw = torch.randint(0, 256, (2, 150, 200, 3), generator=g, dtype=torch.uint8)  # N, H, W, C as decoded
+    x = raw.permute(0, 3, 1, 2)                                                     # zero-copy NCHW view
+    if dtype == torch.float32:
+        x = x.float().contiguous()
+    norm = (raw.permute(0, 3, 1, 2).float() - torch.tensor(means).view(1, 3, 1, 1)) / torch.tensor(stds).view(1, 3, 1, 1)
+    padded = torch.zeros(2, 3, 160, 224)
+    padded[:, :, :150, :200] = norm
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, padded.to(torch.bfloat16).float(), 50)
+    bb.set_input_transform(means, stds, size_divisor=32)
+    bb, neck = bb.to(dev).eval(), neck.to(dev).eval()
+    with torch.no_grad():
+        feats = bb(x.to(dev))
+        outs = neck(feats)
+    torch.cuda.synchronize()
+    assert tuple(feats[0].shape) == (2, 256, 40, 56)
+    feats = [f.float() for f in feats]
+    outs = [o.float() for o in outs]
+    _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
+    _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"])
+    bb.set_input_transform(None)
+    with torch.no_grad():
+        plain = bb(padded.to(torch.bfloat16).to(dev))
+    assert orc.rel_l2(plain[0].float(), feats[0]) <= 2e-3   # same staged image either way

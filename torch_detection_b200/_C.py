@@ -24,7 +24,7 @@ OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO = 5, 6, 7, 8, 9, 10, 11
 OP_AMAX = 12
 # tdet_dtype
-BF16, F32, F16 = 0, 1, 2
+BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1
 FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4

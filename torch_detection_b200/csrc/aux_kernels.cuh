@@ -8,15 +8,26 @@
 
 namespace tdet {
 
-// (n,3,h,w) fp32/bf16 with arbitrary element strides -> [n][hp][wp][4] bf16, image at (3,3), zero
-// border, zero 4th channel.  One thread per staged pixel (8-byte store, coalesced along wp).
-// Optionally records the image's |max| (of the bf16-rounded values) in `meta`.
+// (n,3,h,w) uint8/fp32/bf16 with arbitrary element strides (NCHW, channels_last or an HWC image batch
+// viewed as NCHW) -> [n][hp][wp][4] bf16, image at (3,3), zero border, zero 4th channel.  One thread per
+// staged pixel (8-byte store, coalesced along wp).  Optional per-channel affine `v * scale[c] + shift[c]`
+// (the data layer's normalisation, scale = 1/std, shift = -mean/std) and zero padding beyond the valid
+// (hv, wv) extent (pad-to-size-divisor): the reference's ImageTransforms steps 2 and 5
+// (datasets/dataset_transforms.py:29-44) folded into the stem's loader.  Optionally records the staged
+// image's |max| (of the bf16-rounded values) in `meta`.
+template <typename T>
+__device__ __forceinline__ float prep_load(const T* p) { return static_cast<float>(*p); }
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
-                  int n, int h, int w, int hp, int wp, uint2* __restrict__ y, TensorMeta* meta) {
+                  int n, int hv, int wv, int hp, int wp, const float* __restrict__ scale,
+                  const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta) {
   const long long total = static_cast<long long>(n) * hp * wp;
   float amax = 0.0f;
+  float s0 = 1.0f, s1 = 1.0f, s2 = 1.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+  if (scale) { s0 = scale[0]; s1 = scale[1]; s2 = scale[2]; }
+  if (shift) { b0 = shift[0]; b1 = shift[1]; b2 = shift[2]; }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int xw = static_cast<int>(i % wp);
@@ -25,11 +36,11 @@ prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long
     const int img = static_cast<int>(t / hp);
     const int iw = xw - 3, ih = yh - 3;
     uint2 o = make_uint2(0u, 0u);
-    if (iw >= 0 && iw < w && ih >= 0 && ih < h) {
+    if (iw >= 0 && iw < wv && ih >= 0 && ih < hv) {
       const T* px = x + img * sn + ih * sh + iw * sw;
-      const float c0 = static_cast<float>(px[0]);
-      const float c1 = static_cast<float>(px[sc]);
-      const float c2 = static_cast<float>(px[2 * sc]);
+      const float c0 = fmaf(prep_load(px), s0, b0);
+      const float c1 = fmaf(prep_load(px + sc), s1, b1);
+      const float c2 = fmaf(prep_load(px + 2 * sc), s2, b2);
       o.x = pack_bf16x2(c0, c1);
       o.y = pack_bf16x2(c2, 0.0f);
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(bf16_lo(o.x)), fabsf(bf16_hi(o.x))), fabsf(bf16_lo(o.y))));

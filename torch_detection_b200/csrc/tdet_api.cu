@@ -731,9 +731,13 @@ int build_launch(Launch& l, const DeviceInfo& di) {
     case TDET_OP_STEM: return build_stem(l, di);
     case TDET_OP_PREP:
       if (o.cin != 3 || !o.x || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad arguments");
-      if (o.x_dtype != TDET_BF16 && o.x_dtype != TDET_F32)
+      if (o.x_dtype != TDET_BF16 && o.x_dtype != TDET_F32 && o.x_dtype != TDET_U8)
         return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad dtype");
-      l.bytes = static_cast<double>(o.n) * o.h * o.w * 3 * (o.x_dtype == TDET_F32 ? 4 : 2) +
+      if (o.hc < 0 || o.hc > o.h || o.wc < 0 || o.wc > o.w)
+        return fail(TDET_ERR_INVALID_ARGUMENT, "prep: valid extent %dx%d exceeds the padded size %dx%d", o.hc,
+                    o.wc, o.h, o.w);
+      l.bytes = static_cast<double>(o.n) * (o.hc ? o.hc : o.h) * (o.wc ? o.wc : o.w) * 3 *
+                    (o.x_dtype == TDET_F32 ? 4 : o.x_dtype == TDET_U8 ? 1 : 2) +
                 static_cast<double>(o.n) * stem_hp(o.ho) * stem_wp(o.wo) * 8;
       return TDET_OK;
     case TDET_OP_MAXPOOL:
@@ -807,14 +811,19 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       const long long total = static_cast<long long>(o.n) * hp * wp;
       const int g = grid_for(total, di.num_sms);
       TensorMeta* meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+      const int hv = o.hc ? o.hc : o.h, wv = o.wc ? o.wc : o.w;  // valid extent; the rest is zero padding
       if (o.x_dtype == TDET_F32)
         prep_image_kernel<float><<<g, 256, 0, st>>>(static_cast<const float*>(o.x), o.x_stride[0],
-                                                    o.x_stride[1], o.x_stride[2], o.x_stride[3], o.n,
-                                                    o.h, o.w, hp, wp, static_cast<uint2*>(o.y), meta);
+                                                    o.x_stride[1], o.x_stride[2], o.x_stride[3], o.n, hv, wv,
+                                                    hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta);
+      else if (o.x_dtype == TDET_U8)
+        prep_image_kernel<uint8_t><<<g, 256, 0, st>>>(static_cast<const uint8_t*>(o.x), o.x_stride[0],
+                                                      o.x_stride[1], o.x_stride[2], o.x_stride[3], o.n, hv, wv,
+                                                      hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta);
       else
         prep_image_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(o.x), o.x_stride[0], o.x_stride[1], o.x_stride[2],
-            o.x_stride[3], o.n, o.h, o.w, hp, wp, static_cast<uint2*>(o.y), meta);
+            o.x_stride[3], o.n, hv, wv, hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta);
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

@@ -11,7 +11,7 @@ from . import _C
 
 BN_EPS = 1e-5  # nn.BatchNorm2d default (reference models/utils/layers.py:50-54)
 
-_TD = {torch.bfloat16: _C.BF16, torch.float16: _C.F16, torch.float32: _C.F32}
+_TD = {torch.bfloat16: _C.BF16, torch.float16: _C.F16, torch.float32: _C.F32, torch.uint8: _C.U8}
 
 
 def _stream_ptr(device):
@@ -252,19 +252,26 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
     return op
 
 
-def op_prep(x, y, ho, wo, y_meta=None):
+def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None):
+    """x: logical (n, 3, h, w) image batch (fp32 / bf16 / uint8, any strides: an HWC batch viewed as NCHW is
+    fine); scale/shift: optional fp32[3] device vectors of the per-channel normalisation v*scale + shift;
+    padded_hw: the (H, W) >= (h, w) the network sees, the difference is zero padding (size divisor)."""
     n, c, h, w = x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_PREP
-    op.n, op.h, op.w, op.cin = n, h, w, c
+    ph, pw = padded_hw if padded_hw is not None else (h, w)
+    op.n, op.h, op.w, op.cin = n, ph, pw, c
+    if (ph, pw) != (h, w):
+        op.hc, op.wc = h, w
     op.ho, op.wo = ho, wo
-    if x.dtype not in (torch.float32, torch.bfloat16):
-        raise NotImplementedError("input dtype %s (supported: float32, bfloat16)" % x.dtype)
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+        raise NotImplementedError("input dtype %s (supported: float32, bfloat16, uint8)" % x.dtype)
     op.x_dtype = _TD[x.dtype]
     for i, s in enumerate(x.stride()):
         op.x_stride[i] = s
     op.x, op.y = _ptr(x), _ptr(y)
     op.y_meta = y_meta
+    op.scale, op.shift = _ptr(scale), _ptr(shift)
     return op
 
 

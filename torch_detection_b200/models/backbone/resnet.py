@@ -190,6 +190,21 @@ class ResNet(nn.Module):
         return self
 
     # ------------------------------------------------------------------ B200 execution
+    def set_input_transform(self, img_means=(0., 0., 0.), img_stds=(1., 1., 1.), size_divisor=None):
+        """Fold the data layer's per-channel normalisation and pad-to-size-divisor (reference
+        ``ImageTransforms`` steps 2 and 5, datasets/dataset_transforms.py:29-44) into
+        the stem's loader kernel: ``forward`` then takes the RAW resized batch -- logical (N,3,h,w), uint8 /
+        fp32 / bf16, any strides (an HWC uint8 batch viewed with ``.permute(0, 3, 1, 2)`` is zero-copy) --
+        and the returned feature maps are those of the normalised image zero-padded to multiples of
+        ``size_divisor``.  ``set_input_transform(None)`` removes it."""
+        if img_means is None:
+            self._input_tf = None
+        else:
+            means, stds = tuple(float(v) for v in img_means), tuple(float(v) for v in img_stds)
+            assert len(means) == 3 and len(stds) == 3 and all(s != 0 for s in stds)
+            self._input_tf = (means, stds, int(size_divisor) if size_divisor else None)
+        self._plans = {}
+
     def _check_supported(self, x):
         engine.require_cuda(x, "ResNet input")
         if x.dim() != 4 or x.shape[1] != 3:
@@ -241,8 +256,18 @@ class ResNet(nn.Module):
         the device (TDET_FLAG_SCALED_OUT); stage outputs are plain bf16 (they are what the module
         returns and what crosses chunk boundaries).  tcgen05 needs both MMA operands in one format,
         so each conv's weights are packed in its input's format."""
-        n, _, h, w = x.shape
+        n, _, h_in, w_in = x.shape
         dev = x.device
+        tf = getattr(self, "_input_tf", None)
+        h, w = h_in, w_in
+        tf_scale = tf_shift = None
+        if tf is not None:
+            means, stds, div = tf
+            if div:
+                h, w = (h_in + div - 1) // div * div, (w_in + div - 1) // div * div
+            tf_scale, tf_shift = cache.get(("input_tf", tf), lambda out: (
+                torch.tensor([1.0 / s for s in stds], dtype=torch.float32, device=dev),
+                torch.tensor([-m / s for m, s in zip(means, stds)], dtype=torch.float32, device=dev)))
         train = train_from is not None
         internal = INTERNAL_DTYPE
         scaled = internal == torch.float16
@@ -310,7 +335,8 @@ class ResNet(nn.Module):
                 if stages[0] == 0:
                     staged = pool.get((cn,) + engine.stem_staging_dims(ho, wo) + (4,))
                     staged_meta = meta.new()
-                    ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta))
+                    ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta, scale=tf_scale,
+                                              shift=tf_shift, padded_hw=(h, w)))
                     stem_out = new_act((cn, ho, wo, 64), internal)
                     stem_bn = getattr(self, self.norm_name)
                     stem_w = cache.get(("conv1", "w"),
@@ -404,7 +430,7 @@ class ResNet(nn.Module):
                     outs = [_upcast(o) for o in outs]
                 return outs[0] if len(outs) == 1 else tuple(outs)
         cache = self._get_operands(x.device)
-        key = (tuple(x.shape), x.dtype, tuple(x.stride()), x.device, INTERNAL_DTYPE)
+        key = (tuple(x.shape), x.dtype, tuple(x.stride()), x.device, INTERNAL_DTYPE, getattr(self, "_input_tf", None))
         entry = self._plans.get(key)
         if entry is None:
             entry = self._build_plan(x, cache)
@@ -481,7 +507,8 @@ class ResNet(nn.Module):
     def _train_forward(self, inputs, params):
         (x,) = inputs
         cache = self._get_operands(x.device)
-        key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from)
+        key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from,
+               getattr(self, "_input_tf", None))
         entry = self._plans.get(key)
         if entry is None:
             entry = self._build_plan(x, cache, train_from=self._train_from)

@@ -81,7 +81,7 @@ class FPN(nn.Module):
             self._operands.refresh()
             return self._operands
         cache = engine.OperandCache()
-        for kind, convs in (("lat", self.lateral_convs), ("out", self.fpn_convs)):
+        for kind, convs in self._conv_groups():
             for j, cm in enumerate(convs):
                 conv = cm.conv
                 cache.get("%s%d.w" % (kind, j),
@@ -94,6 +94,9 @@ class FPN(nn.Module):
         self._operand_key = device
         self._plans = {}
         return cache
+
+    def _conv_groups(self):
+        return (("lat", self.lateral_convs), ("out", self.fpn_convs))
 
     def _build_plan(self, feats, operands):
         dev = feats[0].device
@@ -119,13 +122,7 @@ class FPN(nn.Module):
             ops.append(engine.op_conv(srcs[j], operands.value("lat%d.w" % j), lats[j], 1, 1, 1, 0, 1,
                                       shift=operands.value("lat%d.b" % j),
                                       coarse=lats[j + 1] if j < nl - 1 else None))
-        outs = []
-        for j in range(nl):
-            nb, h, w, _ = shapes[j]
-            o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
-            ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), o, 3, 3, 1, 1, 1,
-                                      shift=operands.value("out%d.b" % j)))
-            outs.append(o)
+        outs, keep = self._emit_outputs(ops, operands, lats, shapes, dev)
         if self.num_outs > nl:
             if not self.add_extra_convs:
                 for _ in range(self.num_outs - nl):
@@ -148,9 +145,22 @@ class FPN(nn.Module):
                     outs.append(o)
                     src = o
         ext = list(feats) + [o.buf for o in outs]
-        plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats]], dev)
+        plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats], keep], dev)
         plan.lats = lats  # merged laterals: the saved activations of the training path
         return plan, [tuple(o.buf.shape) for o in outs]
+
+    def _emit_outputs(self, ops, operands, lats, shapes, dev):
+        """P_j = conv3x3(merged lateral j) + bias (fpn.py:106-108).  Returns (output Acts, buffers to keep
+        alive); subclasses extend the pyramid here."""
+        co = self.out_channels
+        outs = []
+        for j in range(len(lats)):
+            nb, h, w, _ = shapes[j]
+            o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
+            ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), o, 3, 3, 1, 1, 1,
+                                      shift=operands.value("out%d.b" % j)))
+            outs.append(o)
+        return outs, []
 
     @staticmethod
     def _as_bf16_nhwc(t):
