@@ -46,6 +46,7 @@ constexpr int kBM = 128;         // UMMA M (cta_group::1)
 constexpr int kBK = 64;          // 16-bit elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
 constexpr int kGemmThreads = 384;       // 12 warps; warp 11 is the B producer of the patch mode
+constexpr int kGemmThreadsNoPatch = 352; // 11 warps otherwise: 186 instead of 170 registers per thread
 constexpr int kEpiThreads = 256;         // 8 epilogue warps: two warps per TMEM lane quadrant
 constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
@@ -75,6 +76,7 @@ struct ConvGemmParams {
   CUtensorMap tmap_b;
   CUtensorMap tmap_out;   // 2D (Cout, M) box (64,128); A_STEM: 4D (64, Wo, Ho, N) box (64,bw,bh,1)
   CUtensorMap tmap_res;   // 2D (Cout, M) box (64,128) over the residual tensor (if any)
+  CUtensorMap tmap_mask;  // same geometry over the ReLU-mask tensor (if mask_tma)
   int M;            // valid output rows (pixels); for A_STEM rows are masked per pixel instead
   int N;            // Cout
   int num_m_tiles;
@@ -104,6 +106,8 @@ struct ConvGemmParams {
                                   //    stride-2 1x1 shortcut); 0: nearest-x2 upsample-add (FPN)
   const void* mask_src;           // nullable 16-bit [M][N] tensor: output is zeroed where it is <= 0
                                   //    (ReLU backward against the stored forward activation)
+  int mask_tma;                   // 1: the mask streams through the residual ring by TMA (tmap_mask), one
+                                  //    slab after the residual's; 0: read with global loads in the epilogue
   const TensorMeta* in_meta;      // nullable
   const TensorMeta* res_meta;     // nullable
   const TensorMeta* coarse_meta;  // nullable
@@ -155,13 +159,14 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
 }
 
 template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                  : (2 * BN <= 256) ? 256 : 512;
   constexpr int kSlabsPerTile = BN / 64;
   constexpr int kRS = RES_SLABS > 0 ? RES_SLABS : 1;
+  static_assert(RES_SLABS % 2 == 0, "two epilogue groups: the residual ring depth must be even");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
@@ -192,6 +197,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tma_prefetch_desc(&p.tmap_b);
     tma_prefetch_desc(&p.tmap_out);
     if (p.has_res) tma_prefetch_desc(&p.tmap_res);
+    if (p.mask_tma) tma_prefetch_desc(&p.tmap_mask);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -402,29 +408,36 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ TMA producer (residual)
-    if (RES_SLABS > 0 && p.has_res) {
+    // ------------------------------------------------------------------ TMA producer (residual, mask)
+    // Per 64-column output slab the ring receives the residual slab (if any), then the mask slab (if it
+    // is TMA-staged).  The epilogue groups alternate slabs, so with a ring depth that is a multiple of
+    // 2 * (operands per slab) every slot has ONE consumer group -- required: an mbarrier parity wait is
+    // only sound if the previous fill of the slot has completed before the consumer waits for the next.
+    const int nload = (p.has_res ? 1 : 0) + (p.mask_tma ? 1 : 0);
+    if (RES_SLABS > 0 && nload > 0) {
       int rs = 0;
       uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
         for (int s = 0; s < kSlabsPerTile; ++s) {
-          mbar_wait(rempty_bar(rs), rphase ^ 1u);
-          if (lane == 0) {
-            mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
-            if (p.a_mode >= A_STEM) {
-              const int tw = m_tile % p.tiles_w;
-              const int t = m_tile / p.tiles_w;
-              tma_load_4d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
-                          tw * p.tile_bw, (t % p.tiles_h) * p.tile_bh, t / p.tiles_h);
-            } else {
-              tma_load_2d(smem_res + rs * kSlabBytes, &p.tmap_res, rfull_bar(rs), n_tile * BN + s * 64,
-                          m_tile * kBM);
+          for (int j = 0; j < nload; ++j) {
+            const CUtensorMap* tm = (j == 0 && p.has_res) ? &p.tmap_res : &p.tmap_mask;
+            mbar_wait(rempty_bar(rs), rphase ^ 1u);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
+              if (p.a_mode >= A_STEM) {
+                const int tw = m_tile % p.tiles_w;
+                const int t = m_tile / p.tiles_w;
+                tma_load_4d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), n_tile * BN + s * 64,
+                            tw * p.tile_bw, (t % p.tiles_h) * p.tile_bh, t / p.tiles_h);
+              } else {
+                tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), n_tile * BN + s * 64, m_tile * kBM);
+              }
             }
+            __syncwarp();
+            if (++rs == kRS) { rs = 0; rphase ^= 1u; }
           }
-          __syncwarp();
-          if (++rs == kRS) { rs = 0; rphase ^= 1u; }
         }
       }
     }
@@ -458,6 +471,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t gbar = 1u + group;      // the group's named barrier
     const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
+    const bool mask_tma = RES_SLABS > 0 && p.mask_tma != 0;
+    const int nload = (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
     float* s_scale = s_params + group * 2 * L::kGroupCols;
@@ -542,7 +557,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                        (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
       }
       const uint8_t* mask_row = nullptr;
-      if (valid && p.mask_src)
+      if (valid && p.mask_src && !mask_tma)
         mask_row = static_cast<const uint8_t*>(p.mask_src) + (pix * p.N + n0) * 2;
 
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -554,18 +569,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // residual slabs are produced in tile order into one ring shared by both groups; consecutive
         // slabs of a group are two ring positions apart, so with any ring depth >= 2 the previous fill of
         // a slot has completed before the group waits for the next one (no parity aliasing)
-        const int ridx = seq * kSlabsPerTile + slab;
+        const int ridx = (seq * kSlabsPerTile + slab) * nload;
         const int rs = ridx % kRS;
         const uint32_t rphase = static_cast<uint32_t>(ridx / kRS) & 1u;
+        const int midx = ridx + (has_res ? 1 : 0);
+        const int ms = midx % kRS;
+        const uint32_t mphase = static_cast<uint32_t>(midx / kRS) & 1u;
         // the staging buffer `ob` was last read by the TMA store this group issued OSLABS slabs ago
         if (issuer) {
           if (OSLABS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         if (has_res) mbar_wait(rfull_bar(rs), rphase);
+        if (mask_tma) mbar_wait(rfull_bar(ms), mphase);
         named_bar_sync(gbar, kEpiGroupThreads);
         const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
+        const uint32_t mk_row = smem_res + ms * kSlabBytes + row * 128;
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
@@ -576,7 +596,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
           }
           uint4 rmk[4];
-          if (mask_row) {
+          if (mask_tma) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = mk_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rmk[j].x), "=r"(rmk[j].y), "=r"(rmk[j].z), "=r"(rmk[j].w)
+                           : "r"(a));
+            }
+          } else if (mask_row) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) rmk[j] = ldg_nc_v4(mask_row + (slab * 64 + half * 32 + j * 8) * 2);
           }
@@ -632,7 +660,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
           }
-          if (mask_row) {
+          if (mask_tma ? valid : (mask_row != nullptr)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t w4[4] = {rmk[j].x, rmk[j].y, rmk[j].z, rmk[j].w};
@@ -686,6 +714,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           if (has_res) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
+          if (mask_tma) mbar_arrive(rempty_bar(ms));
         }
         if (OSLABS > 1) ob ^= 1;
       }

@@ -244,8 +244,8 @@ int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  return launch_pdl(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>, grid, kGemmThreads,
-                    L::kDynamic, st, gp);
+  return launch_pdl(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>, grid,
+                    PATCH ? kGemmThreads : kGemmThreadsNoPatch, L::kDynamic, st, gp);
 }
 
 // Kernel variants: tile width / A-B ring depth / residual ring slabs / resident weight k-blocks /
@@ -271,19 +271,23 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     // streaming weights
     case vkey(64, 6, 2, 0, 1): return launch_gemm_t<64, 6, 2, 0, false, 1>(l.gp, l.grid, st);
     case vkey(64, 5, 2, 0, 2): return launch_gemm_t<64, 5, 2, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(64, 5, 4, 0, 1): return launch_gemm_t<64, 5, 4, 0, false, 1>(l.gp, l.grid, st);
     case vkey(128, 5, 2, 0, 1): return launch_gemm_t<128, 5, 2, 0, false, 1>(l.gp, l.grid, st);
     case vkey(128, 4, 2, 0, 2): return launch_gemm_t<128, 4, 2, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(128, 4, 4, 0, 1): return launch_gemm_t<128, 4, 4, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 0, 1): return launch_gemm_t<256, 4, 0, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 3, 0, 0, 2): return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
-    case vkey(256, 3, 3, 0, 1): return launch_gemm_t<256, 3, 3, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 3, 2, 0, 1): return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 4, 0, 2): return launch_gemm_t<256, 2, 4, 0, false, 2>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
     case vkey(64, 4, 0, 7, 2): return launch_gemm_t<64, 4, 0, 7, false, 2>(l.gp, l.grid, st);  // stem
     case vkey(64, 4, 2, 9, 1): return launch_gemm_t<64, 4, 2, 9, false, 1>(l.gp, l.grid, st);
     case vkey(64, 3, 2, 9, 2): return launch_gemm_t<64, 3, 2, 9, false, 2>(l.gp, l.grid, st);
+    case vkey(64, 3, 4, 9, 1): return launch_gemm_t<64, 3, 4, 9, false, 1>(l.gp, l.grid, st);
     case vkey(128, 4, 2, 4, 2): return launch_gemm_t<128, 4, 2, 4, false, 2>(l.gp, l.grid, st);
+    case vkey(128, 3, 4, 4, 1): return launch_gemm_t<128, 3, 4, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 4, 1, 2): return launch_gemm_t<256, 4, 4, 1, false, 2>(l.gp, l.grid, st);
-    case vkey(256, 4, 3, 1, 1): return launch_gemm_t<256, 4, 3, 1, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 4, 4, 1, 1): return launch_gemm_t<256, 4, 4, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
   }
@@ -371,23 +375,27 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   gp.ab_fp16 = o.x_dtype == TDET_F16;
   const int w_dtype = o.x_dtype;  // tcgen05 kind::f16 needs A and B in ONE format (mixing traps)
   gp.b_fp16 = gp.ab_fp16;
-  // bit i of TDET_VARIANT_SET picks the double-buffered-staging allocation for kernel family i
+  // bit i of TDET_VARIANT_SET picks the double-buffered-staging allocation for kernel family i.
+  // naux = operands that stream through the residual ring beside the accumulator: residual and/or the
+  // ReLU-backward mask; the ring depth must be a multiple of 2 * (operands per slab) (conv_gemm.cuh).
   const int vs = env_int("TDET_VARIANT_SET", kDefaultVariantSet);
+  const int naux = (o.residual ? 1 : 0) + (o.mask ? 1 : 0);
   if (o.cout % 256 == 0) {
     l.bn = 256;
-    if (o.residual) {
-      if (vs & 1) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; } else { l.stages = 3; l.res_slabs = 3; l.oslabs = 1; }
-    } else {
-      if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; } else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
-    }
+    if (naux == 2 || (naux == 1 && (vs & 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
+    else if (naux == 1) { l.stages = 3; l.res_slabs = 2; l.oslabs = 1; }
+    else if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; }
+    else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
   } else if (o.cout % 128 == 0) {
     l.bn = 128;
-    l.res_slabs = 2;
-    if (vs & 4) { l.stages = 4; l.oslabs = 2; } else { l.stages = 5; l.oslabs = 1; }
+    if (naux == 2) { l.stages = 4; l.res_slabs = 4; l.oslabs = 1; }
+    else if (vs & 4) { l.stages = 4; l.res_slabs = 2; l.oslabs = 2; }
+    else { l.stages = 5; l.res_slabs = 2; l.oslabs = 1; }
   } else {
     l.bn = 64;
-    l.res_slabs = 2;
-    if (vs & 8) { l.stages = 5; l.oslabs = 2; } else { l.stages = 6; l.oslabs = 1; }
+    if (naux == 2) { l.stages = 5; l.res_slabs = 4; l.oslabs = 1; }
+    else if (vs & 8) { l.stages = 5; l.res_slabs = 2; l.oslabs = 2; }
+    else { l.stages = 6; l.res_slabs = 2; l.oslabs = 1; }
   }
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
   gp.num_n_tiles = o.cout / l.bn;
@@ -402,6 +410,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     const double rows = static_cast<double>(o.n) * tw * th * kBM;
     const bool fits = rows <= 0x7FFFFF00LL && rows * 100.0 <= real_rows * (100.0 + patch_max_waste_pct());
     const bool variant = (l.bn == 64 && gp.num_kb_b <= 9) || l.bn == 128 || (l.bn == 256 && !o.residual);
+    // (ring depth 2 in the patch variants: with a residual AND a mask, the mask is read by global loads)
     if (fits && variant) {
       l.patch = true;
       l.oslabs = 1;
@@ -417,7 +426,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
       } else if (l.bn == 128) {
         // 16 KiB weight tiles are consumed every 256 MMA cycles: without a residual operand the
         // freed shared memory buys a deeper B ring
-        if (o.residual) { l.stages = 4; l.res_slabs = 2; } else { l.stages = 7; l.res_slabs = 0; }
+        if (naux > 0) { l.stages = 4; l.res_slabs = 2; } else { l.stages = 7; l.res_slabs = 0; }
       } else {
         l.stages = 3; l.res_slabs = 0;
       }
@@ -428,20 +437,28 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     if (resident_b_enabled() && gp.num_n_tiles == 1 && gp.num_m_tiles >= 4 * di.num_sms) {
       // the weight panel fits beside the A ring: load it once per CTA instead of once per k-block
       if (l.bn == 64 && gp.num_kb_b <= 9) {
-        l.res_slabs = 2; l.bres_kb = 9;
-        if (vs & 16) { l.stages = 3; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
+        l.bres_kb = 9;
+        if (naux == 2) { l.stages = 3; l.res_slabs = 4; l.oslabs = 1; }
+        else if (vs & 16) { l.stages = 3; l.res_slabs = 2; l.oslabs = 2; }
+        else { l.stages = 4; l.res_slabs = 2; l.oslabs = 1; }
       } else if (l.bn == 128 && gp.num_kb_b <= 4) {
-        l.stages = 4; l.res_slabs = 2; l.bres_kb = 4; l.oslabs = 2;
+        l.bres_kb = 4;
+        if (naux == 2) { l.stages = 3; l.res_slabs = 4; l.oslabs = 1; }
+        else { l.stages = 4; l.res_slabs = 2; l.oslabs = 2; }
       } else if (l.bn == 256 && gp.num_kb_b <= 1) {
-        l.stages = 4; l.bres_kb = 1;
-        if (vs & 32) { l.res_slabs = 4; l.oslabs = 2; } else { l.res_slabs = 3; l.oslabs = 1; }
-      } else if (l.bn == 256 && gp.num_kb_b <= 4 && !o.residual) {
+        l.stages = 4; l.bres_kb = 1; l.res_slabs = 4;
+        l.oslabs = (vs & 32) ? 2 : 1;
+      } else if (l.bn == 256 && gp.num_kb_b <= 4 && naux == 0) {
         l.res_slabs = 0; l.bres_kb = 4;
         if (vs & 64) { l.stages = 2; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
       }
     }
   }
 
+  {
+    const int nload = (o.residual ? 1 : 0) + 1;
+    gp.mask_tma = (o.mask && l.res_slabs > 0 && l.res_slabs % (2 * nload) == 0) ? 1 : 0;
+  }
   rc = encode_2d(&gp.tmap_b, o.wgt, w_dtype, static_cast<long long>(o.kh) * o.kw * o.cin, o.cout,
                  l.bn, "weights");
   if (rc) return rc;
@@ -453,6 +470,11 @@ int build_conv(Launch& l, const DeviceInfo& di) {
                      kPatchBH, "residual");
       if (rc) return rc;
     }
+    if (gp.mask_tma) {
+      // (the mask is only tested for zero: its 16-bit format does not matter to the TMA or the kernel)
+      rc = encode_4d(&gp.tmap_mask, o.mask, TDET_BF16, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "mask");
+      if (rc) return rc;
+    }
     rc = encode_4d(&gp.tmap_a, o.x, o.x_dtype, o.cin, o.w, o.h, o.n, kPatchPW, kPatchPH, "halo patch");
     if (rc) return rc;
   } else {
@@ -460,6 +482,10 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     if (rc) return rc;
     if (o.residual) {
       rc = encode_2d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout, gp.M, kBM, "residual");
+      if (rc) return rc;
+    }
+    if (gp.mask_tma) {
+      rc = encode_2d(&gp.tmap_mask, o.mask, TDET_BF16, o.cout, gp.M, kBM, "mask");
       if (rc) return rc;
     }
   }
