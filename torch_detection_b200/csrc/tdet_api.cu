@@ -173,6 +173,8 @@ bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
 int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
 constexpr int kDefaultVariantSet = 0;
+constexpr int kDefaultResVariant = 0;  // residual convs with streamed weights: 0 (256,3,2) 1 (256,2,4,os2) 2 BN=128 3 (256,2,6)
+constexpr int kDefaultRes1Ring = 4;
 
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
 
@@ -279,6 +281,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(256, 3, 0, 0, 2): return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
     case vkey(256, 3, 2, 0, 1): return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 4, 0, 2): return launch_gemm_t<256, 2, 4, 0, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 2, 6, 0, 1): return launch_gemm_t<256, 2, 6, 0, false, 1>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
     case vkey(64, 4, 0, 7, 2): return launch_gemm_t<64, 4, 0, 7, false, 2>(l.gp, l.grid, st);  // stem
     case vkey(64, 4, 2, 9, 1): return launch_gemm_t<64, 4, 2, 9, false, 1>(l.gp, l.grid, st);
@@ -288,6 +291,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(128, 3, 4, 4, 1): return launch_gemm_t<128, 3, 4, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 4, 1, 2): return launch_gemm_t<256, 4, 4, 1, false, 2>(l.gp, l.grid, st);
     case vkey(256, 4, 4, 1, 1): return launch_gemm_t<256, 4, 4, 1, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 4, 6, 1, 1): return launch_gemm_t<256, 4, 6, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
   }
@@ -380,15 +384,17 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   // ReLU-backward mask; the ring depth must be a multiple of 2 * (operands per slab) (conv_gemm.cuh).
   const int vs = env_int("TDET_VARIANT_SET", kDefaultVariantSet);
   const int naux = (o.residual ? 1 : 0) + (o.mask ? 1 : 0);
-  if (o.cout % 256 == 0) {
+  const int resv = env_int("TDET_RES_VARIANT", kDefaultResVariant);
+  if (o.cout % 256 == 0 && !(resv == 2 && naux >= 1)) {
     l.bn = 256;
-    if (naux == 2 || (naux == 1 && (vs & 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
+    if (naux == 2 || (naux == 1 && (resv == 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
+    else if (naux == 1 && resv == 3) { l.stages = 2; l.res_slabs = 6; l.oslabs = 1; }
     else if (naux == 1) { l.stages = 3; l.res_slabs = 2; l.oslabs = 1; }
     else if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; }
     else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
   } else if (o.cout % 128 == 0) {
     l.bn = 128;
-    if (naux == 2) { l.stages = 4; l.res_slabs = 4; l.oslabs = 1; }
+    if (naux == 2 || (o.cout % 256 == 0)) { l.stages = 4; l.res_slabs = 4; l.oslabs = 1; }
     else if (vs & 4) { l.stages = 4; l.res_slabs = 2; l.oslabs = 2; }
     else { l.stages = 5; l.res_slabs = 2; l.oslabs = 1; }
   } else {
@@ -446,8 +452,10 @@ int build_conv(Launch& l, const DeviceInfo& di) {
         if (naux == 2) { l.stages = 3; l.res_slabs = 4; l.oslabs = 1; }
         else { l.stages = 4; l.res_slabs = 2; l.oslabs = 2; }
       } else if (l.bn == 256 && gp.num_kb_b <= 1) {
-        l.stages = 4; l.bres_kb = 1; l.res_slabs = 4;
+        l.bres_kb = 1;
         l.oslabs = (vs & 32) ? 2 : 1;
+        if (env_int("TDET_RES1_RING", kDefaultRes1Ring) == 6 && l.oslabs == 1) { l.stages = 4; l.res_slabs = 6; }
+        else { l.stages = 4; l.res_slabs = 4; }
       } else if (l.bn == 256 && gp.num_kb_b <= 4 && naux == 0) {
         l.res_slabs = 0; l.bres_kb = 4;
         if (vs & 64) { l.stages = 2; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
