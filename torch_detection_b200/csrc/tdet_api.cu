@@ -174,7 +174,7 @@ int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
 constexpr int kDefaultVariantSet = 0;
 constexpr int kDefaultResVariant = 0;  // residual convs with streamed weights: 0 (256,3,2) 1 (256,2,4,os2) 2 BN=128 3 (256,2,6)
-constexpr int kDefaultRes1Ring = 4;
+constexpr int kDefaultRes1Ring = 3;
 
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
 
@@ -279,7 +279,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(128, 4, 4, 0, 1): return launch_gemm_t<128, 4, 4, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 0, 1): return launch_gemm_t<256, 4, 0, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 3, 0, 0, 2): return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
-    case vkey(256, 3, 2, 0, 1): return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 3, 3, 0, 1): return launch_gemm_t<256, 3, 3, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 4, 0, 2): return launch_gemm_t<256, 2, 4, 0, false, 2>(l.gp, l.grid, st);
     case vkey(256, 2, 6, 0, 1): return launch_gemm_t<256, 2, 6, 0, false, 1>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
@@ -292,6 +292,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(256, 4, 4, 1, 2): return launch_gemm_t<256, 4, 4, 1, false, 2>(l.gp, l.grid, st);
     case vkey(256, 4, 4, 1, 1): return launch_gemm_t<256, 4, 4, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 6, 1, 1): return launch_gemm_t<256, 4, 6, 1, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 4, 3, 1, 1): return launch_gemm_t<256, 4, 3, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
   }
@@ -389,7 +390,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     l.bn = 256;
     if (naux == 2 || (naux == 1 && (resv == 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
     else if (naux == 1 && resv == 3) { l.stages = 2; l.res_slabs = 6; l.oslabs = 1; }
-    else if (naux == 1) { l.stages = 3; l.res_slabs = 2; l.oslabs = 1; }
+    else if (naux == 1) { l.stages = 3; l.res_slabs = 3; l.oslabs = 1; }
     else if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; }
     else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
   } else if (o.cout % 128 == 0) {
@@ -454,8 +455,9 @@ int build_conv(Launch& l, const DeviceInfo& di) {
       } else if (l.bn == 256 && gp.num_kb_b <= 1) {
         l.bres_kb = 1;
         l.oslabs = (vs & 32) ? 2 : 1;
-        if (env_int("TDET_RES1_RING", kDefaultRes1Ring) == 6 && l.oslabs == 1) { l.stages = 4; l.res_slabs = 6; }
-        else { l.stages = 4; l.res_slabs = 4; }
+        const int ring = env_int("TDET_RES1_RING", kDefaultRes1Ring);
+        l.stages = 4;
+        l.res_slabs = (naux == 2 || l.oslabs == 2) ? 4 : (ring == 6 ? 6 : ring == 4 ? 4 : 3);
       } else if (l.bn == 256 && gp.num_kb_b <= 4 && naux == 0) {
         l.res_slabs = 0; l.bres_kb = 4;
         if (vs & 64) { l.stages = 2; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
@@ -465,7 +467,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
 
   {
     const int nload = (o.residual ? 1 : 0) + 1;
-    gp.mask_tma = (o.mask && l.res_slabs > 0 && l.res_slabs % (2 * nload) == 0) ? 1 : 0;
+    gp.mask_tma = (o.mask && l.res_slabs >= 2 * nload) ? 1 : 0;
   }
   rc = encode_2d(&gp.tmap_b, o.wgt, w_dtype, static_cast<long long>(o.kh) * o.kw * o.cin, o.cout,
                  l.bn, "weights");
