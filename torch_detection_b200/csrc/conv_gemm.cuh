@@ -187,8 +187,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + s); };
   auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + kPatchStages + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
-  // highest residual-ring index each epilogue group has obtained so far (see the epilogue)
-  volatile int* ring_progress = reinterpret_cast<volatile int*>(smem + L::kTmemPtrOffset + 8);
+  // highest residual-ring index the producer has issued so far (see the epilogue)
+  volatile int* ring_issued = reinterpret_cast<volatile int*>(smem + L::kTmemPtrOffset + 8);
   float* s_params = reinterpret_cast<float*>(smem + L::kParamOffset);
 
   const int warp = threadIdx.x >> 5;
@@ -215,8 +215,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(rempty_bar(s), 1);
     }
     mbar_init(bres_bar, 1);
-    ring_progress[0] = -1;
-    ring_progress[1] = -1;
+    *ring_issued = -1;
     for (int s = 0; s < kPatchStages; ++s) {
       mbar_init(afull_bar(s), 1);
       mbar_init(aempty_bar(s), 1);
@@ -420,6 +419,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int nload = (p.has_res ? 1 : 0) + (p.mask_tma ? 1 : 0);
     if (RES_SLABS > 0 && nload > 0) {
       int rs = 0;
+      int issued = 0;
       uint32_t rphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
@@ -438,7 +438,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               } else {
                 tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), n_tile * BN + s * 64, m_tile * kBM);
               }
+              *ring_issued = issued;  // this fill's predecessor in the slot has been consumed, hence completed
             }
+            ++issued;
             __syncwarp();
             if (++rs == kRS) { rs = 0; rphase ^= 1u; }
           }
@@ -586,25 +588,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         // An mbarrier parity wait is only sound if the PREVIOUS fill of the slot (ring index - kRS) has
         // completed before the consumer waits for this one -- otherwise the barrier is still one phase
-        // behind and the wait falls through.  A single in-order consumer has that for free; with two
-        // groups the previous fill may belong to the other group, so wait until that group reports having
-        // obtained it (ring_progress: a fill it obtained has, by definition, completed).
+        // behind and the wait falls through.  A single in-order consumer has that for free; with two groups
+        // the previous fill may belong to the other group.  The producer issues a fill only after its
+        // predecessor was consumed, so "the producer has issued ring index r" implies it: wait for that
+        // first (no extra coupling: the data cannot arrive before it is requested).
         if (nload > 0) {
-          const int prev = ridx - kRS;
-          if (prev >= 0) {
-            const int prev_item = prev / nload;
-            const int owner = kByTile ? (prev_item & 1) : ((prev_item % kSlabsPerTile) & 1);
-            if (owner != group) {
-              uint32_t spins = 0;
-              while (ring_progress[owner] < prev + (nload - 1)) {
-                if (++spins > (1u << 24)) __trap();
-              }
-            }
+          uint32_t spins = 0;
+          while (*ring_issued < ridx + nload - 1) {
+            if (++spins > (1u << 24)) __trap();
           }
         }
         if (has_res) mbar_wait(rfull_bar(rs), rphase);
         if (mask_tma) mbar_wait(rfull_bar(ms), mphase);
-        if (issuer && nload > 0) ring_progress[group] = ridx + nload - 1;
         named_bar_sync(gbar, kEpiGroupThreads);
         const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
