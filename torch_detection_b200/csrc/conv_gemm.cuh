@@ -158,7 +158,8 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
   return pack_bf16x2(lo, hi);
 }
 
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
+// MASKED: the kernel carries the ReLU-backward mask path (dgrad); forward instantiations compile it out.
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED>
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
@@ -416,7 +417,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // is TMA-staged), in tile order; the two epilogue groups consume alternate slabs from this ONE ring
     // (sharing it lets the faster group borrow slots; two private rings of half the depth measured 15 %
     // slower on the residual convs).
-    const int nload = (p.has_res ? 1 : 0) + (p.mask_tma ? 1 : 0);
+    const int nload = (p.has_res ? 1 : 0) + ((MASKED && p.mask_tma) ? 1 : 0);
     if (RES_SLABS > 0 && nload > 0) {
       int rs = 0;
       int issued = 0;
@@ -477,7 +478,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t gbar = 1u + group;      // the group's named barrier
     const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
-    const bool mask_tma = RES_SLABS > 0 && p.mask_tma != 0;
+    const bool mask_tma = MASKED && RES_SLABS > 0 && p.mask_tma != 0;
     const int nload = (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
@@ -563,7 +564,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                        (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
       }
       const uint8_t* mask_row = nullptr;
-      if (valid && p.mask_src && !mask_tma)
+      if (MASKED && valid && p.mask_src && !mask_tma)
         mask_row = static_cast<const uint8_t*>(p.mask_src) + (pix * p.N + n0) * 2;
 
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -614,7 +615,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
           }
           uint4 rmk[4];
-          if (mask_tma) {
+          if (!MASKED) {
+          } else if (mask_tma) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t a = mk_row + ((((half << 2) | j) ^ (row & 7)) << 4);
@@ -678,7 +680,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
           }
-          if (mask_tma ? valid : (mask_row != nullptr)) {
+          if (MASKED && (mask_tma ? valid : (mask_row != nullptr))) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t w4[4] = {rmk[j].x, rmk[j].y, rmk[j].z, rmk[j].w};

@@ -235,19 +235,26 @@ int launch_pdl(void (*kernel)(Params), dim3 grid, int threads, int smem, cudaStr
   return TDET_OK;
 }
 
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
-int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED>
+int launch_gemm_m(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
   static bool attr_set[64] = {};
   int dev = 0;
   TDET_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>,
+    TDET_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, MASKED>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     attr_set[dev] = true;
   }
-  return launch_pdl(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>, grid,
+  return launch_pdl(conv_gemm_kernel<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, MASKED>, grid,
                     PATCH ? kGemmThreads : kGemmThreadsNoPatch, L::kDynamic, st, gp);
+}
+
+// forward convs never carry a ReLU-backward mask: they get the instantiation without that code path
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
+int launch_gemm_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
+  if (gp.mask_src) return launch_gemm_m<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, true>(gp, grid, st);
+  return launch_gemm_m<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, false>(gp, grid, st);
 }
 
 // Kernel variants: tile width / A-B ring depth / residual ring slabs / resident weight k-blocks /
