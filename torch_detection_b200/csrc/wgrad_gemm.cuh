@@ -12,9 +12,12 @@
 // (bf16, or fp16 with per-tensor exponents applied in the epilogue): tcgen05 kind::f16 traps on mixed
 // fp16/bf16 operands (measured).
 //
-// One CTA = one (128-channel Cout tile, filter tap, NB-wide Cin group) and one slice of the pixel
+// One CTA = one (MT x 128-channel Cout tile, filter tap, NB-wide Cin group) and one slice of the pixel
 // range (split-K over blockIdx.y); partial sums are combined with vectorised fp32 reductions
 // (red.global.add.v4.f32) into the [Cout][kh][kw][Cin] accumulator, which the caller zeroes.
+// MT = 2 keeps two accumulators (2 x NB TMEM columns) that share every X tile: the kernel is bound by
+// L2->SM operand traffic (ncu: tensor pipe 53 % active at 27 % L2, 9 % DRAM), and 256 x 256 output tiles
+// need 64 B per tensor cycle instead of the 96 B of 128 x 256.
 //   warp 0  TMA producer      warp 1  tcgen05.mma issuer      warps 2..5  epilogue (TMEM -> red.add)
 #pragma once
 #include "conv_gemm.cuh"
@@ -56,21 +59,22 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
                : "memory");
 }
 
-template <int NB, int PIX, int STAGES>
+template <int NB, int PIX, int STAGES, int MT>
 struct WgradSmem {
   static constexpr int kSlab = PIX * 128;
-  static constexpr int kStageBytes = (2 + NB / 64) * kSlab;
+  static constexpr int kStageBytes = (2 * MT + NB / 64) * kSlab;
   static constexpr int kBarOffset = STAGES * kStageBytes;
   static constexpr int kDynamic = kBarOffset + (2 * STAGES + 1) * 8 + 16;
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
   static_assert(kSlab % 1024 == 0, "slabs must keep the 1024-byte swizzle alignment");
 };
 
-template <int NB, int PIX, int STAGES>
+template <int NB, int PIX, int STAGES, int MT>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
-  using L = WgradSmem<NB, PIX, STAGES>;
-  constexpr uint32_t kTmemCols = NB < 32 ? 32 : NB;
+  using L = WgradSmem<NB, PIX, STAGES, MT>;
+  constexpr uint32_t kTmemCols = MT * NB < 32 ? 32 : MT * NB;
+  static_assert(MT * NB <= 512 && (MT * NB & (MT * NB - 1)) == 0, "TMEM allocation: power of two <= 512 columns");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0u) __trap();
@@ -127,10 +131,11 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t fb = full_bar(stage);
           mbar_arrive_expect_tx(fb, L::kStageBytes);
           const uint32_t a = base + stage * L::kStageBytes;
-          const uint32_t b = a + 2 * L::kSlab;
+          const uint32_t b = a + 2 * MT * L::kSlab;
           const int m0 = kb * PIX;
-          tma_load_2d(a, &p.tmap_g, fb, co_tile * 128, m0);
-          tma_load_2d(a + L::kSlab, &p.tmap_g, fb, co_tile * 128 + 64, m0);
+#pragma unroll
+          for (int j = 0; j < 2 * MT; ++j)
+            tma_load_2d(a + j * L::kSlab, &p.tmap_g, fb, co_tile * 128 * MT + j * 64, m0);
           if (p.x_im2col) {
             const int q0 = m0 % p.Wo;
             const int tt = m0 / p.Wo;
@@ -159,13 +164,16 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a = base + stage * L::kStageBytes;
-          const uint32_t b = a + 2 * L::kSlab;
+          const uint32_t b = a + 2 * MT * L::kSlab;
 #pragma unroll
           for (int k = 0; k < PIX / kUmmaK; ++k) {
             // 16 pixels per MMA = two 8-row groups = 2048 B further down each slab
-            const uint64_t da = make_smem_desc_mn_sw128(a + k * 2048, L::kSlab);
             const uint64_t db = make_smem_desc_mn_sw128(b + k * 2048, L::kSlab);
-            umma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t da = make_smem_desc_mn_sw128(a + mt * 2 * L::kSlab + k * 2048, L::kSlab);
+              umma_bf16_ss(tmem_base + mt * NB, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));
           if (kb == nkb - 1) umma_commit(done_bar);
@@ -175,25 +183,28 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       }
     } else {
       const int quad = warp & 3;
-      const int co = co_tile * 128 + quad * 32 + lane;
-      float sc = (co < p.cout && p.scale) ? __ldg(p.scale + co) : 1.0f;
       int e = 0;
       if (p.x_meta) e += p.x_meta->e;
       if (p.g_meta) e += p.g_meta->e;
-      sc = ldexpf(sc, e);
       mbar_wait(done_bar, 0);
       tc_fence_after();
-      float* dst_row = p.dw + (static_cast<long long>(co) * taps + tap) * p.cin + cig * NB;
 #pragma unroll 1
-      for (int c = 0; c < NB / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
-        if (co < p.cout) {
+      for (int mt = 0; mt < MT; ++mt) {
+        const int co = (co_tile * MT + mt) * 128 + quad * 32 + lane;
+        float sc = (co < p.cout && p.scale) ? __ldg(p.scale + co) : 1.0f;
+        sc = ldexpf(sc, e);
+        float* dst_row = p.dw + (static_cast<long long>(co) * taps + tap) * p.cin + cig * NB;
+#pragma unroll 1
+        for (int c = 0; c < NB / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + mt * NB + c * 32, v);
+          tmem_ld_wait();
+          if (co < p.cout) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(dst_row + c * 32 + j * 4, __uint_as_float(v[4 * j]) * sc, __uint_as_float(v[4 * j + 1]) * sc,
-                       __uint_as_float(v[4 * j + 2]) * sc, __uint_as_float(v[4 * j + 3]) * sc);
+            for (int j = 0; j < 8; ++j)
+              red_add_v4(dst_row + c * 32 + j * 4, __uint_as_float(v[4 * j]) * sc, __uint_as_float(v[4 * j + 1]) * sc,
+                         __uint_as_float(v[4 * j + 2]) * sc, __uint_as_float(v[4 * j + 3]) * sc);
+          }
         }
       }
     }
