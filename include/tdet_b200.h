@@ -82,7 +82,8 @@ typedef enum tdet_op_kind {
   TDET_OP_DILATE2 = 9,   /* adjoint of a stride-2 subsample: zero-insertion upsample to (ho, wo) */
   TDET_OP_ADD_MASK = 10, /* y = (x + residual) * (mask > 0): gradient merge / ReLU backward */
   TDET_OP_ZERO = 11,     /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
-  TDET_OP_AMAX = 12      /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
+  TDET_OP_AMAX = 12,     /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
+  TDET_OP_BN_AFFINE_GRAD = 13 /* gamma / beta gradients of a frozen-statistics BatchNorm from stored tensors */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -150,6 +151,12 @@ typedef struct tdet_tensor_meta {
  *                   TDET_FLAG_SCALED_OUT (y_dtype F16, needs y_meta and the inputs' metas with valid amax) the
  *                   output exponent is chosen from amax(x) + amax(residual) and that bound is recorded as
  *                   y's amax.  Without inputs to add or mask it is the format conversion fp16*2^e -> bf16.
+ * TDET_OP_BN_AFFINE_GRAD  gy: masked gradient w.r.t. the BN output y [n][h][w][cin] (gy_dtype, gy_meta); x: the
+ *                   stored activation that equals y wherever gy != 0 (x_dtype, x_meta); residual (optional):
+ *                   tensor to subtract (the block's residual operand, y = x - residual); scale = gamma,
+ *                   shift = beta (fp32 [cin]); dw: fp32 [2*cin] accumulator {dgamma[cin], dbeta[cin]}
+ *                   (caller zeroes it).  norm_layer / nn.BatchNorm2d in eval mode with trainable affine
+ *                   parameters (bn_frozen=False, resnet.py:272-281).
  * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;
  *                   its exponent field is left untouched)
  * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled

@@ -38,19 +38,22 @@ def _leafify(sd, wanted):
     return out
 
 
-def trainable_backbone_key(train_from_stage):
-    """Conv weights of layer{train_from_stage+1..4} (0-based stage index), BN frozen."""
+def trainable_backbone_key(train_from_stage, bn_affine=False):
+    """Conv weights of layer{train_from_stage+1..4} (0-based stage index); with bn_affine also the
+    weight / bias of their (eval-mode) BatchNorms (the reference's bn_frozen=False)."""
     def wanted(k):
-        if not k.startswith("layer") or not k.endswith(".weight"):
+        if not k.startswith("layer") or int(k[5]) - 1 < train_from_stage:
             return False
-        if ".bn" in k or ".downsample.1." in k:
-            return False
-        return int(k[5]) - 1 >= train_from_stage
+        is_bn = ".bn" in k or ".downsample.1." in k
+        if is_bn:
+            return bn_affine and (k.endswith(".weight") or k.endswith(".bias"))
+        return k.endswith(".weight")
     return wanted
 
 
-def plain_grads(bb_sd, neck_sd, x, depth, grad_outs, train_from_stage=1, out_channels=256, num_outs=5):
-    bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage))
+def plain_grads(bb_sd, neck_sd, x, depth, grad_outs, train_from_stage=1, out_channels=256, num_outs=5,
+                bn_affine=False):
+    bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage, bn_affine))
     neck = _leafify(neck_sd, lambda k: True)
     feats, outs = orc.resnet_fpn_forward(bb, neck, x.float(), depth, out_channels, num_outs)
     torch.autograd.backward(list(outs), [g.float() for g in grad_outs])
@@ -116,7 +119,8 @@ class _ConvBNKernelModel(torch.autograd.Function):
 
 
 def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs, train_from_stage=1,
-                         out_channels=256, num_outs=5, kernel_rounding=False, bb_weight_dtype=torch.bfloat16):
+                         out_channels=256, num_outs=5, kernel_rounding=False, bb_weight_dtype=torch.bfloat16,
+                         bn_affine=False):
     """fp32 autograd over the reference's graph with every stored activation (and hence every ReLU
     mask and every conv / wgrad input) forced to the value the CUDA training forward stored:
     `saved_bb` = ResNet.saved_activations(), `saved_neck` = FPN.saved_activations().  Conv weights are
@@ -132,7 +136,8 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
         this is the tight gate on the kernels' arithmetic."""
     kind, counts = orc.ARCH[depth]
     kr = kernel_rounding
-    bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage))
+    assert not (kr and bn_affine), "the kernel-rounding model covers conv weights only"
+    bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage, bn_affine))
     neck = _leafify(neck_sd, lambda k: True)
 
     def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None, round_grad=False):

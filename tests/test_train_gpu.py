@@ -30,9 +30,9 @@ pytestmark = pytest.mark.gpu
 GATE = 1e-2
 
 
-def _train_pair(depth, seed, dev, bnstats, frozen_stages=1):
+def _train_pair(depth, seed, dev, bnstats, frozen_stages=1, bn_frozen=True):
     bb, neck = helpers.build_product_pair(depth, seed=seed, bnstats=bnstats, frozen_stages=frozen_stages,
-                                          bn_eval=True, bn_frozen=True)
+                                          bn_eval=True, bn_frozen=bn_frozen)
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
     bb = bb.to(dev)
     neck = neck.to(dev)
@@ -51,16 +51,19 @@ def _cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("depth,shape,bnstats,frozen", [
-    (50, (2, 3, 128, 160), False, 1),
-    (50, (2, 3, 96, 128), True, 1),
-    (50, (1, 3, 128, 128), True, 0),
-    (18, (2, 3, 128, 160), True, 1),
-    (101, (1, 3, 64, 96), False, 2),
+@pytest.mark.parametrize("depth,shape,bnstats,frozen,bn_frozen", [
+    (50, (2, 3, 128, 160), False, 1, True),
+    (50, (2, 3, 96, 128), True, 1, True),
+    (50, (1, 3, 128, 128), True, 0, True),
+    (18, (2, 3, 128, 160), True, 1, True),
+    (101, (1, 3, 64, 96), False, 2, True),
+    (50, (2, 3, 128, 160), True, 1, False),   # the reference's default bn_frozen=False: BN affine gradients
+    (18, (2, 3, 96, 128), True, 0, False),
 ])
-def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
+def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen, bn_frozen):
     dev = cuda_device
-    bb, neck, bsd, nsd = _train_pair(depth, 21, dev, bnstats, frozen)
+    bb, neck, bsd, nsd = _train_pair(depth, 21, dev, bnstats, frozen, bn_frozen)
+    bn_affine = not bn_frozen
     g = torch.Generator().manual_seed(5)
     x = torch.randn(*shape, generator=g).to(torch.bfloat16)
     feats = bb(x.to(dev))
@@ -78,9 +81,14 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
                                                                  train_from_stage=frozen, kernel_rounding=True,
                                                                  bb_weight_dtype=wdt)
     xb, xn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
-                                                    train_from_stage=frozen, bb_weight_dtype=wdt)
-    pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen)
-    assert set(got_b) == set(tb), (sorted(set(got_b) ^ set(tb))[:8])
+                                                    train_from_stage=frozen, bb_weight_dtype=wdt, bn_affine=bn_affine)
+    pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen,
+                                           bn_affine=bn_affine)
+    assert set(got_b) == set(xb), (sorted(set(got_b) ^ set(xb))[:8])
+    if bn_affine:
+        bnk = [k for k in xb if ".bn" in k or ".downsample.1." in k]
+        worst = max(bnk, key=lambda k: orc.rel_l2(got_b[k], xb[k]))
+        print("BN affine grads (%d): max rel-L2 %.2e (%s)" % (len(bnk), orc.rel_l2(got_b[worst], xb[worst]), worst))
     assert set(got_n) == set(tn) and len(got_n) == 16
     # the forced forward reproduces the CUDA outputs up to ONE layer of arithmetic (fp32 conv of the
     # kernels' own stored inputs): every stored tensor is locally consistent with its inputs
@@ -88,7 +96,7 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen):
     print("train-mode P levels vs one-layer fp32 recomputation:", ["%.2e" % e for e in fwd])
     assert max(fwd) <= 4e-3
     errs_n = {k: orc.rel_l2(got_n[k], tn[k]) for k in tn}
-    errs_b = {k: orc.rel_l2(got_b[k], tb[k]) for k in tb}
+    errs_b = {k: orc.rel_l2(got_b[k], tb[k]) for k in tb if k in got_b}
     plain_n = {k: orc.rel_l2(got_n[k], pn[k]) for k in pn}
     plain_b = {k: (orc.rel_l2(got_b[k], pb[k]), _cos(got_b[k], pb[k])) for k in pb}
     exact_n = {k: orc.rel_l2(got_n[k], xn[k]) for k in xn}
@@ -160,7 +168,7 @@ def test_eval_mode_unchanged_and_unsupported_training_configs(cuda_device):
     bb.train()                                   # frozen_stages=-1: the stem would need gradients
     with pytest.raises(NotImplementedError):
         bb(x)
-    bb2, _ = helpers.build_product_pair(50, seed=0, frozen_stages=1, bn_eval=True, bn_frozen=False)
+    bb2, _ = helpers.build_product_pair(50, seed=0, frozen_stages=1, bn_eval=False)
     bb2 = bb2.to(dev).train()
-    with pytest.raises(NotImplementedError):   # BN affine gradients
+    with pytest.raises(NotImplementedError):   # batch-statistics BatchNorm
         bb2(x)

@@ -23,6 +23,7 @@ ERR_OUT_OF_MEMORY = -6
 OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO = 5, 6, 7, 8, 9, 10, 11
 OP_AMAX = 12
+OP_BN_AFFINE_GRAD = 13
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1

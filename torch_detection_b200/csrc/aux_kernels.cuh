@@ -263,6 +263,81 @@ colsum_kernel(const uint4* __restrict__ x, float* __restrict__ dw, long long row
   }
 }
 
+// Frozen-statistics BatchNorm affine gradients from stored tensors (training with bn_frozen=False):
+//   y = gamma * xhat + beta  =>  dbeta[c] += sum_m g[m][c],  dgamma[c] += sum_m g[m][c] * (y[m][c] - beta[c]) / gamma[c]
+// where g is the (ReLU-masked) gradient w.r.t. y.  y itself is not stored, but wherever g != 0 it equals the
+// stored activation `a` (ReLU passed) minus, for the block's last conv, the residual operand `b`:
+// y = a - b.  One pass over g, a (and b); per-tensor exponents applied.  Channels with gamma == 0 get
+// dgamma = 0 (xhat cannot be recovered from y there).
+struct BnAffineParams {
+  const uint4* g;
+  const uint4* a;
+  const uint4* b;   // nullable
+  long long rows;
+  int c8, rows_per_block;
+  int g_fp16, a_fp16, b_fp16;
+  const TensorMeta* g_meta;
+  const TensorMeta* a_meta;
+  const TensorMeta* b_meta;
+  const float* gamma;
+  const float* beta;
+  float* dgamma;
+  float* dbeta;
+};
+
+__global__ void __launch_bounds__(256)
+bn_affine_grad_kernel(const BnAffineParams p) {
+  const int cg = threadIdx.x & 7;
+  const int rl = threadIdx.x >> 3;
+  const long long r0 = static_cast<long long>(blockIdx.x) * p.rows_per_block;
+  const long long r1 = min(p.rows, r0 + p.rows_per_block);
+  const float mg = ldexpf(1.0f, p.g_meta ? p.g_meta->e : 0);
+  const float ma = ldexpf(1.0f, p.a_meta ? p.a_meta->e : 0);
+  const float mb = ldexpf(1.0f, (p.b && p.b_meta) ? p.b_meta->e : 0);
+  const bool gf = p.g_fp16 != 0, af = p.a_fp16 != 0, bf = p.b_fp16 != 0;
+  float dot[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long r = r0 + rl; r < r1; r += 32) {
+    const long long idx = r * p.c8 + blockIdx.y * 8 + cg;
+    const uint4 vg = __ldg(p.g + idx);
+    const uint4 va = __ldg(p.a + idx);
+    const uint4 vb = p.b ? __ldg(p.b + idx) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t wg[4] = {vg.x, vg.y, vg.z, vg.w}, wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g0, g1, a0, a1, b0, b1;
+      unpack16x2(wg[j], gf, g0, g1);
+      unpack16x2(wa[j], af, a0, a1);
+      unpack16x2(wb[j], bf, b0, b1);
+      const float y0 = fmaf(a0, ma, -b0 * mb), y1 = fmaf(a1, ma, -b1 * mb);
+      dot[2 * j] = fmaf(g0, y0, dot[2 * j]);
+      dot[2 * j + 1] = fmaf(g1, y1, dot[2 * j + 1]);
+      sum[2 * j] += g0;
+      sum[2 * j + 1] += g1;
+    }
+  }
+  __shared__ float red[2][32][65];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][rl][cg * 8 + j] = dot[j];
+    red[1][rl][cg * 8 + j] = sum[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float d = 0.0f, s = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      d += red[0][i][threadIdx.x];
+      s += red[1][i][threadIdx.x];
+    }
+    const int c = blockIdx.y * 64 + threadIdx.x;
+    d *= mg;
+    s *= mg;
+    const float gm = __ldg(p.gamma + c);
+    atomicAdd(p.dbeta + c, s);
+    if (gm != 0.0f) atomicAdd(p.dgamma + c, (d - __ldg(p.beta + c) * s) / gm);
+  }
+}
+
 __device__ __forceinline__ uint32_t add4_bf16x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return pack_bf16x2(bf16_lo(a) + bf16_lo(b) + bf16_lo(c) + bf16_lo(d),
                      bf16_hi(a) + bf16_hi(b) + bf16_hi(c) + bf16_hi(d));

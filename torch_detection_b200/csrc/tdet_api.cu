@@ -836,6 +836,12 @@ int build_launch(Launch& l, const DeviceInfo& di) {
         return fail(TDET_ERR_INVALID_ARGUMENT, "amax: bad arguments");
       l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w;
       return TDET_OK;
+    case TDET_OP_BN_AFFINE_GRAD:
+      if (o.cin <= 0 || o.cin % 64 || !o.x || !o.gy || !o.dw || !o.scale || !o.shift || !is16(o.x_dtype) ||
+          !is16(o.gy_dtype) || (o.residual && !is16(o.residual_dtype)))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "bn_affine_grad: bad arguments");
+      l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w * (2 + (o.residual ? 1 : 0));
+      return TDET_OK;
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "unknown op kind %d", o.kind);
 }
@@ -945,6 +951,32 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       ap.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
       ap.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
       add_mask_kernel<<<grid_for(ap.total, di.num_sms), 256, 0, st>>>(ap);
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
+    case TDET_OP_BN_AFFINE_GRAD: {
+      BnAffineParams bp{};
+      bp.g = static_cast<const uint4*>(o.gy);
+      bp.a = static_cast<const uint4*>(o.x);
+      bp.b = static_cast<const uint4*>(o.residual);
+      bp.rows = static_cast<long long>(o.n) * o.h * o.w;
+      bp.c8 = o.cin / 8;
+      long long strips = (bp.rows + 1023) / 1024;
+      const long long cap = static_cast<long long>(di.num_sms) * 8;
+      if (strips > cap) strips = cap;
+      bp.rows_per_block = static_cast<int>((bp.rows + strips - 1) / strips);
+      strips = (bp.rows + bp.rows_per_block - 1) / bp.rows_per_block;
+      bp.g_fp16 = o.gy_dtype == TDET_F16;
+      bp.a_fp16 = o.x_dtype == TDET_F16;
+      bp.b_fp16 = o.residual_dtype == TDET_F16;
+      bp.g_meta = reinterpret_cast<const TensorMeta*>(o.gy_meta);
+      bp.a_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
+      bp.b_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+      bp.gamma = o.scale;
+      bp.beta = o.shift;
+      bp.dgamma = o.dw;
+      bp.dbeta = o.dw + o.cin;
+      bn_affine_grad_kernel<<<dim3(static_cast<unsigned>(strips), static_cast<unsigned>(o.cin / 64), 1), 256, 0, st>>>(bp);
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

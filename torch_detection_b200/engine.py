@@ -391,6 +391,23 @@ def op_add_mask(x, y, residual=None, mask=None, scaled_out=False):
     return op
 
 
+def op_bn_affine_grad(g, a, gamma, beta, dw, b=None):
+    """dw[0:C] += dgamma, dw[C:2C] += dbeta of a frozen-statistics BatchNorm: g = masked gradient w.r.t. its
+    output, a (minus b, if given) = the stored tensor that equals the BN output wherever g != 0."""
+    n, h, w, c = g.shape
+    assert a.shape == g.shape and dw.numel() == 2 * c and dw.dtype == torch.float32
+    op = _C.TdetOp()
+    op.kind = _C.OP_BN_AFFINE_GRAD
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.gy, op.gy_dtype, op.gy_meta = g.ptr, _TD[g.dtype], g.meta
+    op.x, op.x_dtype, op.x_meta = a.ptr, _TD[a.dtype], a.meta
+    if b is not None:
+        op.residual, op.residual_dtype, op.residual_meta = b.ptr, _TD[b.dtype], b.meta
+    op.scale, op.shift = gamma.data_ptr(), beta.data_ptr()
+    op.dw = dw.data_ptr()
+    return op
+
+
 def op_amax(x, meta):
     """meta.amax = max |x| (true values); `meta` = device address of a tdet_tensor_meta."""
     n, h, w, c = x.shape

@@ -400,14 +400,14 @@ class ResNet(nn.Module):
                         if keep:
                             # saved for backward: block input, every conv output (ReLU masks + wgrad operands)
                             records.append(dict(li=li, bi=bi, pre=pre, unit=unit, xin=cur, acts=acts,
-                                                last=last))
+                                                last=last, shortcut=shortcut))
                         else:
                             for t in temps:
                                 pool.release(t.buf)
                             if cur_pooled:
                                 pool.release(cur.buf)
-                        if shortcut is not None:
-                            pool.release(shortcut.buf)
+                        if shortcut is not None and not keep:
+                            pool.release(shortcut.buf)  # (kept in training: BatchNorm affine gradients need it)
                         cur = src
                         cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
                     if train and li in self.out_indices:
@@ -453,34 +453,42 @@ class ResNet(nn.Module):
             sync.attach(self, next(self.parameters()).device)
 
     def _trainable_weights(self):
-        """Conv weights that get gradients, in module order.  Supported configuration = the
-        reference's detector configs: frozen stem (frozen_stages >= 0), frozen BN affine parameters
-        (bn_frozen=True), a frozen prefix of stages and a fully trainable suffix."""
+        """Parameters that get gradients, in module order: the conv weights of the trainable stages and --
+        with bn_frozen=False -- the affine parameters of their (eval-mode) BatchNorms.  Supported: a frozen
+        stem (frozen_stages >= 0), a frozen prefix of stages and a fully trainable suffix; per stage the BN
+        affine parameters are either all trainable or all frozen."""
         stem_norm = getattr(self, self.norm_name)
-        if any(p.requires_grad for p in list(self.conv1.parameters()) + list(stem_norm.parameters())):
+        if self.conv1.weight.requires_grad:
             raise NotImplementedError(
-                "training the stem (conv1/bn1) is not on the B200 path: use frozen_stages >= 0 and "
-                "call .train() (reference configs freeze the stem and stage 1)")
+                "training the stem (conv1) is not on the B200 path: use frozen_stages >= 0 and call "
+                ".train() (reference configs freeze the stem and stage 1)")
         first = None
         params = []
+        bn_train = []
         for li, lname in enumerate(self.res_layers):
             stage = getattr(self, lname)
             convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
+            bns = [m for m in stage.modules() if isinstance(m, nn.BatchNorm2d)]
             flags = [m.weight.requires_grad for m in convs]
-            for m in stage.modules():
-                if isinstance(m, nn.BatchNorm2d) and any(p.requires_grad for p in m.parameters()) and any(flags):
-                    raise NotImplementedError(
-                        "BatchNorm affine gradients are not on the B200 path: build the backbone with "
-                        "bn_frozen=True (frozen BN, as the reference's configs do)")
+            bflags = [p.requires_grad for m in bns for p in (m.weight, m.bias)]
             if any(flags):
                 if not all(flags):
                     raise NotImplementedError("partially frozen stage %s" % lname)
+                if any(bflags) and not all(bflags):
+                    raise NotImplementedError("partially frozen BatchNorm parameters in stage %s" % lname)
                 if first is None:
                     first = li
                 params.extend(m.weight for m in convs)
-            elif first is not None:
-                raise NotImplementedError("frozen stage %s after a trainable one" % lname)
+                if all(bflags) and bflags:
+                    for m in bns:
+                        params.extend((m.weight, m.bias))
+                bn_train.append(bool(bflags) and all(bflags))
+            else:
+                if first is not None:
+                    raise NotImplementedError("frozen stage %s after a trainable one" % lname)
+                bn_train.append(False)
         self._train_from = first
+        self._train_bn = tuple(bn_train)
         return params
 
     def saved_activations(self):
@@ -507,7 +515,7 @@ class ResNet(nn.Module):
     def _train_forward(self, inputs, params):
         (x,) = inputs
         cache = self._get_operands(x.device)
-        key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from,
+        key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from, self._train_bn,
                getattr(self, "_input_tf", None))
         entry = self._plans.get(key)
         if entry is None:
@@ -572,8 +580,23 @@ class ResNet(nn.Module):
             seg_start = len(bb.ops)
             stage = getattr(self, self.res_layers[li])
             convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
-            bucket = training.GradBucket([m.weight for m in convs], dev)
+            bn_on = self._train_bn[li]
+            bparams = [m.weight for m in convs]
+            if bn_on:
+                for m in stage.modules():
+                    if isinstance(m, nn.BatchNorm2d):
+                        bparams.extend((m.weight, m.bias))  # adjacent: {dgamma[C], dbeta[C]} is one accumulator
+            bucket = training.GradBucket(bparams, dev)
             buckets.append(bucket)
+
+            def bn_grad(name, bn, g, a, b=None, bucket=bucket):
+                """dgamma / dbeta of an eval-mode BatchNorm with trainable affine parameters."""
+                i = bucket.index_of(bn.weight)
+                c = bn.weight.numel()
+                dw = bucket.flat[bucket.offsets[i]:bucket.offsets[i] + 2 * c]
+                assert bucket.offsets[i + 1] == bucket.offsets[i] + c
+                gamma, beta = cache.get((name, "affine"), lambda out: _affine_copy(bn, out), deps=(bn.weight, bn.bias))
+                bb.ops.append(engine.op_bn_affine_grad(g, a, gamma, beta, dw, b=b))
             blocks = by_stage[li]
             if li == nst - 1:
                 # gradient of the top stage output arrives from autograd only: apply its ReLU mask
@@ -592,6 +615,13 @@ class ResNet(nn.Module):
                     sc = scale_of(name, getattr(unit, unit.norm_names[ci]))
                     x_ci = xin if ci == 0 else acts[ci - 1]
                     bb.wgrad(name, module, sc, x_ci, g, bucket.view(bucket.index_of(module.weight)))
+                    if bn_on:
+                        if ci == nconv - 1:
+                            # y = out - residual operand wherever the (masked) gradient is non-zero
+                            res_op = live(r["shortcut"]) if unit.downsample is not None else xin
+                            bn_grad(name, getattr(unit, unit.norm_names[ci]), g, acts[ci], b=res_op)
+                        else:
+                            bn_grad(name, getattr(unit, unit.norm_names[ci]), g, acts[ci])
                     if ci > 0:
                         g_next = bb.dgrad(name, module, sc, g, acts[ci - 1].shape, mask=acts[ci - 1],
                                           deps=_bn_deps(getattr(unit, unit.norm_names[ci])))
@@ -603,6 +633,8 @@ class ResNet(nn.Module):
                     name = pre + "downsample"
                     sc_ds = scale_of(name, ds[1])
                     bb.wgrad(name, ds[0], sc_ds, xin, gM, bucket.view(bucket.index_of(ds[0].weight)))
+                    if bn_on:
+                        bn_grad(name, ds[1], gM, live(r["shortcut"]))
                 # gradient w.r.t. the block input: needed unless the producer is frozen
                 is_first_block = r["bi"] == 0
                 need_gin = not (is_first_block and li == first)
@@ -705,6 +737,16 @@ INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16")
 
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
+
+
+def _affine_copy(bn, out):
+    """fp32 device copies of an eval-mode BatchNorm's (gamma, beta), refreshed in place."""
+    g, b = bn.weight.detach().float(), bn.bias.detach().float()
+    if out is None:
+        return g.contiguous().clone(), b.contiguous().clone()
+    out[0].copy_(g)
+    out[1].copy_(b)
+    return out
 
 
 def _bn_deps(bn):
