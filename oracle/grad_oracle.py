@@ -52,10 +52,14 @@ def trainable_backbone_key(train_from_stage, bn_affine=False):
 
 
 def plain_grads(bb_sd, neck_sd, x, depth, grad_outs, train_from_stage=1, out_channels=256, num_outs=5,
-                bn_affine=False):
+                bn_affine=False, start_level=0, add_extra_convs=False):
     bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage, bn_affine))
     neck = _leafify(neck_sd, lambda k: True)
-    feats, outs = orc.resnet_fpn_forward(bb, neck, x.float(), depth, out_channels, num_outs)
+    kind, _ = orc.ARCH[depth]
+    in_ch = [64 * 2 ** i * orc.EXPANSION[kind] for i in range(4)]
+    feats = orc.resnet_forward(bb, x.float(), depth)
+    outs = orc.fpn_forward(neck, feats, in_ch, out_channels, num_outs, start_level=start_level,
+                           add_extra_convs=add_extra_convs)
     torch.autograd.backward(list(outs), [g.float() for g in grad_outs])
     gb = {k: v.grad for k, v in bb.items() if v.requires_grad}
     gn = {k: v.grad for k, v in neck.items() if v.requires_grad}

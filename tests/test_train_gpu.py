@@ -172,3 +172,43 @@ def test_eval_mode_unchanged_and_unsupported_training_configs(cuda_device):
     bb2 = bb2.to(dev).train()
     with pytest.raises(NotImplementedError):   # batch-statistics BatchNorm
         bb2(x)
+
+
+def test_retinanet_style_neck_gradients(cuda_device):
+    """FPN(start_level=1, add_extra_convs=True): extra stride-2 convs on C5 with the reference's in-place ReLU
+    between them (fpn.py:118-124); all neck gradients and the backbone's vs the plain fp32 oracle's FPN part
+    (no ReLU inside the neck except that one) and the mask-matched backbone check through C-level agreement."""
+    from torch_detection_b200.models.necks import FPN
+    dev = cuda_device
+    bb, _ = helpers.build_product_pair(50, seed=9, bnstats=True, frozen_stages=1, bn_eval=True, bn_frozen=True)
+    torch.manual_seed(9)
+    neck = FPN([256, 512, 1024, 2048], 256, 5, start_level=1, add_extra_convs=True)
+    neck.init_weights()
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    bb, neck = bb.to(dev).train(), neck.to(dev).train()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 128, 160, generator=g).to(torch.bfloat16)
+    feats = bb(x.to(dev))
+    outs = neck(feats)
+    assert len(outs) == 5
+    grads = [torch.randn(o.shape, generator=g).to(torch.bfloat16) for o in outs]
+    torch.autograd.backward(list(outs), [t.to(dev).contiguous(memory_format=torch.channels_last) for t in grads])
+    torch.cuda.synchronize()
+    # neck-only oracle on the kernels' own C levels: fp32 autograd of the reference's FPN forward
+    cs = [f.detach().float().cpu().requires_grad_(True) for f in feats]
+    leaf = {k: v.clone().float().requires_grad_(True) for k, v in nsd.items()}
+    ref_outs = orc.fpn_forward(leaf, [c for c in cs], [256, 512, 1024, 2048], 256, 5, start_level=1,
+                               add_extra_convs=True)
+    torch.autograd.backward(list(ref_outs), [t.float() for t in grads])
+    for k, p in neck.named_parameters():
+        e = orc.rel_l2(p.grad.cpu(), leaf[k].grad)
+        assert e <= GATE, (k, e)
+    # the gradient handed to the backbone for C3..C5 (C2 is unused with start_level=1): check through layer4
+    got = {k: p.grad.detach().cpu() for k, p in bb.named_parameters() if p.grad is not None}
+    pb, _, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), 50, grads, train_from_stage=1, start_level=1,
+                                          add_extra_convs=True)
+    assert set(got) == set(pb)
+    cos = min(torch.nn.functional.cosine_similarity(got[k].flatten().double(), pb[k].flatten().double(), dim=0).item()
+              for k in pb if k.startswith("layer4"))
+    print("RetinaNet-style neck: layer4 gradient cosine vs plain fp32 oracle >= %.4f" % cos)
+    assert cos >= 0.97

@@ -177,8 +177,6 @@ class FPN(nn.Module):
         assert len(inputs) == len(self.in_channels)
         if self.training and torch.is_grad_enabled() and (
                 any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs)):
-            if self.add_extra_convs and self.num_outs > self.backbone_end_level - self.start_level:
-                raise NotImplementedError("training with add_extra_convs=True is not on the B200 path yet")
             params = list(self.parameters())
             return tuple(training.PlanFunction.apply(self, len(inputs), *(list(inputs) + params)))
         return self._forward_infer(inputs)
@@ -252,14 +250,37 @@ class FPN(nn.Module):
         bucket = training.GradBucket(plist, dev)
         g_ext = [engine.nhwc_empty(o.shape[0], o.shape[2], o.shape[3], o.shape[1], dev) for o in outs]
         gp = [engine.act_of(g) for g in g_ext]
-        # extra levels are stride-2 subsamples of the last output (fpn.py:114-116): scatter them back
-        for j in range(len(outs) - 1, nl - 1, -1):
-            up = bb.new_act(gp[j - 1].shape)
-            bb.ops.append(engine.op_dilate2(gp[j], up))
-            tot = bb.new_act(gp[j - 1].shape)
-            bb.ops.append(engine.op_add_mask(gp[j - 1], tot, residual=up))
-            bb.release(up)
-            gp[j - 1] = tot
+        extra_dc = None  # gradient of the extra stride-2 convs w.r.t. the top backbone level
+        out_acts = [engine.act_of(o) for o in outs]  # the forward's returned tensors (external, re-bound)
+        if not self.add_extra_convs:
+            # extra levels are stride-2 subsamples of the last output (fpn.py:114-116): scatter them back
+            for j in range(len(outs) - 1, nl - 1, -1):
+                up = bb.new_act(gp[j - 1].shape)
+                bb.ops.append(engine.op_dilate2(gp[j], up))
+                tot = bb.new_act(gp[j - 1].shape)
+                bb.ops.append(engine.op_add_mask(gp[j - 1], tot, residual=up))
+                bb.release(up)
+                gp[j - 1] = tot
+        elif len(outs) > nl:
+            # RetinaNet-style extra levels (fpn.py:118-124): o_nl = conv(C_top), o_j = conv(relu_(o_{j-1})); every
+            # level that feeds another one is RETURNED post-ReLU (in place), so its incoming gradient and the
+            # next conv's data gradient are merged and masked in that dgrad conv's epilogue
+            top = engine.act_of(feats[self.backbone_end_level - 1])
+            g = gp[len(outs) - 1]
+            for j in range(len(outs) - 1, nl - 1, -1):
+                conv = self.fpn_convs[j].conv
+                x_j = top if j == nl else out_acts[j - 1]
+                bb.wgrad("out%d" % j, conv, None, x_j, g, bucket.view(bucket.index_of(conv.weight)))
+                if conv.bias is not None:
+                    bb.ops.append(engine.op_colsum(g, bucket.view(bucket.index_of(conv.bias))))
+                if j > nl:
+                    g_prev = bb.dgrad("out%d" % j, conv, None, g, x_j.shape, residual=gp[j - 1], mask=out_acts[j - 1])
+                else:
+                    g_prev = bb.dgrad("out%d" % j, conv, None, g, x_j.shape)
+                if g is not gp[len(outs) - 1]:
+                    bb.release(g)
+                g = g_prev
+            extra_dc = g
         d_feats = [engine.nhwc_empty(t.shape[0], t.shape[2], t.shape[3], t.shape[1], dev) for t in used]
         pooled = None
         for j in range(nl):
@@ -277,7 +298,8 @@ class FPN(nn.Module):
             if lat.bias is not None:
                 bb.ops.append(engine.op_colsum(dL, bucket.view(bucket.index_of(lat.bias))))
             wd = bb.dgrad_weight("lat%d" % j, lat, None)
-            bb.ops.append(engine.op_conv(dL, wd, engine.act_of(d_feats[j]), 1, 1, 1, 0, 1))
+            bb.ops.append(engine.op_conv(dL, wd, engine.act_of(d_feats[j]), 1, 1, 1, 0, 1,
+                                         residual=extra_dc if (j == nl - 1 and extra_dc is not None) else None))
             if j + 1 < nl:
                 pooled = bb.new_act(plan.lats[j + 1].shape)
                 bb.ops.append(engine.op_sumpool2(dL, pooled))
@@ -286,7 +308,7 @@ class FPN(nn.Module):
             bb.release(dL)
         ops, _ = bb.finalize()
         ops = [engine.op_zero(bucket.flat)] + ops
-        ext = g_ext + list(feats) + d_feats
+        ext = g_ext + list(feats) + d_feats + list(outs)
         bplan = engine.Plan(ops, ext, [operands, bb.buffers, bb.acc_ws, bucket.flat], dev)
         return bplan, bucket
 
@@ -306,7 +328,7 @@ class FPN(nn.Module):
         gs = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
         used = feats[self.start_level:self.backbone_end_level]
         d_feats = [torch.empty_like(t, memory_format=torch.channels_last) for t in used]
-        ext = gs + list(feats) + d_feats
+        ext = gs + list(feats) + d_feats + list(outs)
         sync = getattr(self, "_grad_sync", None)
         if sync is not None:
             sync.guard(bucket.flat)
