@@ -197,9 +197,15 @@ def test_retinanet_style_neck_gradients(cuda_device):
     # neck-only oracle on the kernels' own C levels: fp32 autograd of the reference's FPN forward
     cs = [f.detach().float().cpu().requires_grad_(True) for f in feats]
     leaf = {k: v.clone().float().requires_grad_(True) for k, v in nsd.items()}
-    ref_outs = orc.fpn_forward(leaf, [c for c in cs], [256, 512, 1024, 2048], 256, 5, start_level=1,
-                               add_extra_convs=True)
-    torch.autograd.backward(list(ref_outs), [t.float() for t in grads])
+    ref_outs = list(orc.fpn_forward(leaf, [c for c in cs], [256, 512, 1024, 2048], 256, 3, start_level=1))
+    # extra levels with the ReLU decision of the kernels' own returned P6 (mask-matched, as for the backbone)
+    p6 = torch.nn.functional.conv2d(cs[3], leaf["fpn_convs.3.conv.weight"], leaf["fpn_convs.3.conv.bias"], 2, 1)
+    p6 = grad_oracle._force(p6, outs[3].detach().float().cpu(), True)
+    p7 = torch.nn.functional.conv2d(p6, leaf["fpn_convs.4.conv.weight"], leaf["fpn_convs.4.conv.bias"], 2, 1)
+    ref_outs += [p6, p7]
+    for a, b in zip(outs, ref_outs):
+        assert orc.rel_l2(a.float(), b) <= 4e-3
+    torch.autograd.backward(ref_outs, [t.float() for t in grads])
     for k, p in neck.named_parameters():
         e = orc.rel_l2(p.grad.cpu(), leaf[k].grad)
         assert e <= GATE, (k, e)
