@@ -204,7 +204,7 @@ def test_retinanet_style_neck_gradients(cuda_device):
     p7 = torch.nn.functional.conv2d(p6, leaf["fpn_convs.4.conv.weight"], leaf["fpn_convs.4.conv.bias"], 2, 1)
     ref_outs += [p6, p7]
     for a, b in zip(outs, ref_outs):
-        assert orc.rel_l2(a.float(), b) <= 4e-3
+        assert orc.rel_l2(a.float(), b) <= GATE   # two stored bf16 tensors + bf16 weights deep
     torch.autograd.backward(ref_outs, [t.float() for t in grads])
     for k, p in neck.named_parameters():
         e = orc.rel_l2(p.grad.cpu(), leaf[k].grad)
