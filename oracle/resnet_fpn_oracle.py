@@ -204,29 +204,33 @@ def resnet_forward(sd, x, depth, num_stages=4, strides=(1, 2, 2, 2), dilations=(
     return outs[0] if len(outs) == 1 else tuple(outs)
 
 
+def _cm(sd, prefix, x, stride=1, pad=0):
+    """ConvModule.forward with activate_last=True and no activation (layers.py:120-127): conv (+bias), then the
+    norm layer if the module has one (eval-mode BatchNorm2d)."""
+    y = F.conv2d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"), stride, pad)
+    if (prefix + ".norm.weight") in sd:
+        y = _bn(sd, prefix + ".norm", y)
+    return y
+
+
 def fpn_forward(sd, inputs, in_channels, out_channels, num_outs, start_level=0, end_level=-1,
                 add_extra_convs=False):
     """FPN.forward (models/necks/fpn.py:88-125), normalize=None (conv + bias only)."""
     assert len(inputs) == len(in_channels)
     lo, hi = fpn_level_range(len(in_channels), start_level, end_level)
     n = hi - lo
-    lats = [F.conv2d(inputs[lo + j], sd["lateral_convs.%d.conv.weight" % j],
-                     sd["lateral_convs.%d.conv.bias" % j]) for j in range(n)]
+    lats = [_cm(sd, "lateral_convs.%d" % j, inputs[lo + j]) for j in range(n)]
     for j in range(n - 1, 0, -1):
         lats[j - 1] += F.interpolate(lats[j], scale_factor=2, mode="nearest")
-    outs = [F.conv2d(lats[j], sd["fpn_convs.%d.conv.weight" % j],
-                     sd["fpn_convs.%d.conv.bias" % j], 1, 1) for j in range(n)]
+    outs = [_cm(sd, "fpn_convs.%d" % j, lats[j], 1, 1) for j in range(n)]
     if num_outs > len(outs):
         if not add_extra_convs:
             for _ in range(num_outs - n):
                 outs.append(F.max_pool2d(outs[-1], 1, stride=2))
         else:
-            outs.append(F.conv2d(inputs[hi - 1], sd["fpn_convs.%d.conv.weight" % n],
-                                 sd["fpn_convs.%d.conv.bias" % n], 2, 1))
+            outs.append(_cm(sd, "fpn_convs.%d" % n, inputs[hi - 1], 2, 1))
             for j in range(n + 1, num_outs):
-                outs.append(F.conv2d(F.relu(outs[-1], inplace=True),
-                                     sd["fpn_convs.%d.conv.weight" % j],
-                                     sd["fpn_convs.%d.conv.bias" % j], 2, 1))
+                outs.append(_cm(sd, "fpn_convs.%d" % j, F.relu(outs[-1], inplace=True), 2, 1))
     return tuple(outs)
 
 
@@ -239,28 +243,21 @@ def pafpn_forward(sd, inputs, in_channels, out_channels, num_outs, start_level=0
     lo, hi = fpn_level_range(len(in_channels), start_level, end_level)
     n = hi - lo
     act = (lambda t: F.relu(t, inplace=True)) if activation == "relu" else (lambda t: t)
-    lats = [F.conv2d(inputs[lo + j], sd["lateral_convs.%d.conv.weight" % j],
-                     sd["lateral_convs.%d.conv.bias" % j]) for j in range(n)]
+    lats = [_cm(sd, "lateral_convs.%d" % j, inputs[lo + j]) for j in range(n)]
     for j in range(n - 1, 0, -1):
         lats[j - 1] += F.interpolate(lats[j], scale_factor=2, mode="nearest")
-    outs = [F.conv2d(lats[j], sd["fpn_convs.%d.conv.weight" % j],
-                     sd["fpn_convs.%d.conv.bias" % j], 1, 1) for j in range(n)]
+    outs = [_cm(sd, "fpn_convs.%d" % j, lats[j], 1, 1) for j in range(n)]
     for j in range(1, n):
-        down = act(F.conv2d(outs[j - 1], sd["pa_convs1.%d.conv.weight" % (j - 1)],
-                            sd["pa_convs1.%d.conv.bias" % (j - 1)], 2, 1))
-        outs[j] = act(F.conv2d(outs[j] + down, sd["pa_convs2.%d.conv.weight" % (j - 1)],
-                               sd["pa_convs2.%d.conv.bias" % (j - 1)], 1, 1))
+        down = act(_cm(sd, "pa_convs1.%d" % (j - 1), outs[j - 1], 2, 1))
+        outs[j] = act(_cm(sd, "pa_convs2.%d" % (j - 1), outs[j] + down, 1, 1))
     if num_outs > len(outs):
         if not add_extra_convs:
             for _ in range(num_outs - n):
                 outs.append(F.max_pool2d(outs[-1], 1, stride=2))
         else:
-            outs.append(F.conv2d(inputs[hi - 1], sd["fpn_convs.%d.conv.weight" % n],
-                                 sd["fpn_convs.%d.conv.bias" % n], 2, 1))
+            outs.append(_cm(sd, "fpn_convs.%d" % n, inputs[hi - 1], 2, 1))
             for j in range(n + 1, num_outs):
-                outs.append(F.conv2d(F.relu(outs[-1], inplace=True),
-                                     sd["fpn_convs.%d.conv.weight" % j],
-                                     sd["fpn_convs.%d.conv.bias" % j], 2, 1))
+                outs.append(_cm(sd, "fpn_convs.%d" % j, F.relu(outs[-1], inplace=True), 2, 1))
     return tuple(outs)
 
 

@@ -248,3 +248,32 @@ def test_input_transform_normalise_and_pad_in_the_loader(cuda_device, dtype):
     with torch.no_grad():
         plain = bb(padded.to(torch.bfloat16).to(dev))
     assert orc.rel_l2(plain[0].float(), feats[0]) <= 2e-3   # same staged image either way
+
+
+@pytest.mark.parametrize("neck_type", ["FPN", "PAFPN"])
+def test_neck_with_folded_batchnorm(cuda_device, neck_type):
+    """necks built with normalize=... -- the eval-mode BatchNorm after every neck conv is
+    folded into the GEMM epilogue (scale/shift), including under the fused upsample-add."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    dev = cuda_device
+    bb, _ = helpers.build_product_pair(18, seed=12, bnstats=True)
+    torch.manual_seed(12)
+    neck = obj_from_dict(dict(type=neck_type, in_channels=[64, 128, 256, 512], out_channels=256, num_outs=5,
+                              normalize=dict(type="BN")), parent=models.necks)
+    neck.init_weights()
+    sd = neck.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(7))
+    neck.load_state_dict(sd)
+    neck.eval()
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(2, 3, 128, 192, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    wf = orc.resnet_forward(bsd, x.float(), 18)
+    fwd = orc.fpn_forward if neck_type == "FPN" else orc.pafpn_forward
+    wp = fwd(nsd, [f.clone() for f in wf], [64, 128, 256, 512], 256, 5)
+    feats, outs = _run_product(bb, neck, x, dev)
+    e = _check_levels(outs, wp, ["L2", "L3", "L4", "L5", "L6"])
+    print("rel-L2 %s + BN" % neck_type, e)
+    neck.train()
+    with pytest.raises(NotImplementedError):
+        neck(feats)

@@ -142,3 +142,33 @@ def test_pafpn_oracle_and_mirror_match_reference(activation):
                                 activation=activation)
     assert len(ref) == len(got) == 5
     assert all(torch.equal(x, y) for x, y in zip(ref, got))
+
+
+@pytest.mark.parametrize("neck_type", ["FPN", "PAFPN"])
+def test_neck_with_batchnorm_matches_reference(neck_type):
+    """Row f4: normalize=... puts an (eval-mode) BatchNorm after every neck conv (layers.py:57-135); the oracle
+    and the product's parameter mirror against the live reference with randomised running statistics."""
+    from torch_detection_b200 import models as b200
+    from torch_detection_b200.utils import obj_from_dict as b200_build
+    ref_backbone, ref_necks, obj_from_dict = reference_shim.load()
+    cfg = dict(type=neck_type, in_channels=[64, 128, 256, 512], out_channels=256, num_outs=5,
+               normalize=dict(type="BN"))
+    torch.manual_seed(4)
+    neck = obj_from_dict(dict(cfg), parent=ref_necks)
+    neck.init_weights()
+    neck.eval()
+    torch.manual_seed(4)
+    mine = b200_build(dict(cfg), parent=b200.necks)
+    mine.init_weights()
+    sd = neck.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(6))
+    neck.load_state_dict(sd)
+    mine.load_state_dict(sd)
+    assert list(sd.keys()) == list(mine.state_dict().keys())
+    g = torch.Generator().manual_seed(3)
+    feats = [torch.randn(2, c, 64 // 2 ** i, 96 // 2 ** i, generator=g) for i, c in enumerate([64, 128, 256, 512])]
+    fwd = orc.fpn_forward if neck_type == "FPN" else orc.pafpn_forward
+    with torch.no_grad():
+        ref = neck([f.clone() for f in feats])
+        got = fwd(sd, [f.clone() for f in feats], [64, 128, 256, 512], 256, 5)
+    assert all(torch.equal(x, y) for x, y in zip(ref, got))

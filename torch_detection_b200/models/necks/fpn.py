@@ -87,7 +87,14 @@ class FPN(nn.Module):
                 cache.get("%s%d.w" % (kind, j),
                           lambda out, conv=conv: engine.pack_conv_weight(conv.weight, out=out),
                           deps=(conv.weight,))
-                if conv.bias is not None:
+                if cm.with_norm:
+                    # eval-mode BatchNorm folded to the epilogue's scale / shift (a conv bias folds into shift)
+                    norm = cm.norm
+                    cache.get("%s%d.bn" % (kind, j),
+                              lambda out, conv=conv, norm=norm: _fold_conv_bn(conv, norm, out),
+                              deps=tuple(t for t in (norm.weight, norm.bias, norm.running_mean, norm.running_var,
+                                                     conv.bias) if t is not None))
+                elif conv.bias is not None:
                     cache.get("%s%d.b" % (kind, j),
                               lambda out, conv=conv: _bias_copy(conv.bias, out), deps=(conv.bias,))
         self._operands = cache
@@ -120,7 +127,7 @@ class FPN(nn.Module):
             lats[j] = engine.Act(torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev),
                                  (nb, h, w, co), torch.bfloat16)
             ops.append(engine.op_conv(srcs[j], operands.value("lat%d.w" % j), lats[j], 1, 1, 1, 0, 1,
-                                      shift=operands.value("lat%d.b" % j),
+                                      **_epi(operands, "lat%d" % j),
                                       coarse=lats[j + 1] if j < nl - 1 else None))
         outs, keep = self._emit_outputs(ops, operands, lats, shapes, dev)
         if self.num_outs > nl:
@@ -140,7 +147,7 @@ class FPN(nn.Module):
                     # (fpn.py:123-124), so every extra level that feeds another one is returned
                     # post-ReLU: fold that ReLU into the producing conv's epilogue.
                     ops.append(engine.op_conv(src, operands.value("out%d.w" % j), o, 3, 3, 2, 1, 1,
-                                              shift=operands.value("out%d.b" % j),
+                                              **_epi(operands, "out%d" % j),
                                               relu=(j < self.num_outs - 1)))
                     outs.append(o)
                     src = o
@@ -158,7 +165,7 @@ class FPN(nn.Module):
             nb, h, w, _ = shapes[j]
             o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
             ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), o, 3, 3, 1, 1, 1,
-                                      shift=operands.value("out%d.b" % j)))
+                                      **_epi(operands, "out%d" % j)))
             outs.append(o)
         return outs, []
 
@@ -177,6 +184,10 @@ class FPN(nn.Module):
         assert len(inputs) == len(self.in_channels)
         if self.training and torch.is_grad_enabled() and (
                 any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs)):
+            if any(getattr(m, "with_norm", False) for m in self.modules()):
+                raise NotImplementedError(
+                    "training a neck with normalize=... means batch-statistics BatchNorm (the reference does not "
+                    "freeze it): not on the B200 path; eval() runs with the norm folded into the conv epilogue")
             params = list(self.parameters())
             return tuple(training.PlanFunction.apply(self, len(inputs), *(list(inputs) + params)))
         return self._forward_infer(inputs)
@@ -347,6 +358,22 @@ class FPN(nn.Module):
             i = self.start_level + j
             g_inputs[i] = d if state["in_dtypes"][i] == torch.bfloat16 else d.to(state["in_dtypes"][i])
         return g_inputs, g_params
+
+
+def _epi(operands, key):
+    """Epilogue operands of conv `key`: folded BatchNorm scale/shift if it has a norm layer, else its bias."""
+    bn = operands.value(key + ".bn")
+    if bn is not None:
+        return dict(scale=bn[0], shift=bn[1])
+    return dict(shift=operands.value(key + ".b"))
+
+
+def _fold_conv_bn(conv, norm, out):
+    """(scale, shift) of conv(+bias) -> eval BatchNorm: y = scale * conv_nobias(x) + shift."""
+    sc, sh = engine.fold_bn(norm, out=out)
+    if conv.bias is not None:
+        sh.add_(conv.bias.detach().float() * sc)   # BN(conv + b) = scale*conv + (shift + scale*b)
+    return sc, sh
 
 
 def _bias_copy(bias, out):

@@ -19,7 +19,7 @@ import torch.nn as nn
 from ... import engine
 from ...registry import NECKS
 from ..utils import ConvModule
-from .fpn import FPN
+from .fpn import FPN, _epi
 
 
 @NECKS.register_module
@@ -93,7 +93,7 @@ class PAFPN(FPN):
             # P_j: the returned N_0 for the finest level, a temporary otherwise
             p = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev)) if j == 0 else temp((nb, h, w, co))
             ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), p, 3, 3, 1, 1, 1,
-                                      shift=operands.value("out%d.b" % j)))
+                                      **_epi(operands, "out%d" % j)))
             if j == 0:
                 prev = p
                 outs.append(p)
@@ -105,14 +105,14 @@ class PAFPN(FPN):
                 # relu(conv + b) first, then + P_j (ConvModule applies the activation before the add)
                 t = temp((nb, h, w, co))
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), t, 3, 3, 2, 1, 1,
-                                          shift=operands.value("pa1_%d.b" % (j - 1)), relu=True))
+                                          **_epi(operands, "pa1_%d" % (j - 1)), relu=True))
                 ops.append(engine.op_add_mask(t, s, residual=p))
             else:
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), s, 3, 3, 2, 1, 1,
-                                          shift=operands.value("pa1_%d.b" % (j - 1)), residual=p))
+                                          **_epi(operands, "pa1_%d" % (j - 1)), residual=p))
             nj = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
             ops.append(engine.op_conv(s, operands.value("pa2_%d.w" % (j - 1)), nj, 3, 3, 1, 1, 1,
-                                      shift=operands.value("pa2_%d.b" % (j - 1)), relu=relu))
+                                      **_epi(operands, "pa2_%d" % (j - 1)), relu=relu))
             outs.append(nj)
             prev = nj
         return outs, keep
@@ -127,8 +127,5 @@ class PAFPN(FPN):
 
 def _pa_conv(channels, stride, normalize, bias, use_gn, activation):
     """3x3 ConvModule of the bottom-up path; the activation is applied by the owning plan."""
-    cm = ConvModule(channels, channels, 3, stride=stride, padding=1, normalize=normalize, bias=bias,
-                    use_gn=use_gn)
-    cm.activation = activation
-    cm.with_activation = activation is not None
-    return cm
+    return ConvModule(channels, channels, 3, stride=stride, padding=1, normalize=normalize, bias=bias,
+                      use_gn=use_gn, activation=activation)

@@ -40,19 +40,22 @@ def norm_layer(planes, use_gn=False):
 
 
 class ConvModule(nn.Module):
-    """conv (+bias) container used by the neck (layers.py:57-135).  Only the configuration the FPN
-    path uses is accepted: no norm, no activation (``normalize=None``)."""
+    """conv (+bias) (+BatchNorm) (+ReLU) parameter container used by the necks (layers.py:57-135).  The
+    owning neck's plan executes it: an eval-mode BatchNorm (``normalize`` not None, ``use_gn=False``) is
+    folded into the conv's fp32 epilogue; GroupNorm, ``activate_last=False`` and ReLU6 are refused."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, normalize=None, use_gn=False, activation=None,
                  activate_last=True):
         super(ConvModule, self).__init__()
-        if normalize is not None or use_gn:
-            raise NotImplementedError("ConvModule with a norm layer is not on the B200 FPN path")
-        if activation is not None:
-            raise NotImplementedError("ConvModule activation is not on the B200 FPN path")
-        self.with_norm = False
-        self.with_activation = False
+        if use_gn and normalize is not None:
+            raise NotImplementedError("GroupNorm cannot be folded into a GEMM epilogue (B200 neck path)")
+        if activation not in (None, "relu"):
+            raise NotImplementedError("ConvModule activation %r is not on the B200 neck path" % (activation,))
+        if not activate_last:
+            raise NotImplementedError("ConvModule(activate_last=False) is not on the B200 neck path")
+        self.with_norm = normalize is not None
+        self.with_activation = activation is not None
         self.with_bias = bias
         self.activation = activation
         self.activate_last = activate_last
@@ -63,6 +66,10 @@ class ConvModule(nn.Module):
         for attr in ("in_channels", "out_channels", "kernel_size", "stride", "padding", "dilation",
                      "groups"):
             setattr(self, attr, getattr(self.conv, attr))
+        if self.with_norm:
+            self.norm = norm_layer(out_channels, use_gn=False)   # created after the conv, as in the reference
+        if self.with_activation:
+            self.activate = nn.ReLU(inplace=True)
 
     def forward(self, x):
         raise NotImplementedError(
