@@ -190,7 +190,8 @@ typedef struct tdet_op {
   const void* mask;          /* CONV / ADD_MASK: forward activation to mask the result against */
   const void* gy;            /* WGRAD: output gradient */
   int32_t gy_dtype;
-  int32_t reserved0;
+  int32_t groups;            /* CONV: 0/1 = dense; > 1 = grouped conv (cin == cout, 64 % (cin/groups) == 0) over
+                                weights from tdet_pack_grouped_conv_weight (ResNeXt, resnext.py:84-87) */
   float* dw;                 /* WGRAD / COLSUM: fp32 accumulator */
   const tdet_tensor_meta* gy_meta; /* WGRAD: exponent of gy (NULL = 0) */
 } tdet_op;
@@ -223,6 +224,11 @@ int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
 int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
                  float eps, float* scale, float* shift, int channels, void* stream);
+/* Grouped conv weights: fp32 [cout][cin/groups][kh][kw] -> DENSE 16-bit [cout][kh][kw][cin], zero outside each
+ * output channel's group (block-diagonal): the GEMM kernel then contracts, per 64-wide tile of output
+ * channels, only the 64 input channels of the same range. */
+int tdet_pack_grouped_conv_weight(const float* w, void* w_packed, int cout, int cin, int kh, int kw, int groups,
+                                  int dtype, void* stream);
 /* Operand of the data-gradient conv: out[ci][kh-1-r][kw-1-s][co] = scale[co] * w[co][ci][r][s]
  * (scale = folded BN scale of the forward conv, NULL = 1), 16-bit, round-to-nearest-even. */
 int tdet_pack_dgrad_weight(const float* w_oihw, const float* scale, void* w_packed, int cout, int cin,

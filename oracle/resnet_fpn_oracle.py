@@ -170,7 +170,9 @@ def _block(sd, p, x, kind, stride, dilation):
     if kind == "bottleneck":  # resnet.py:97-119 ; stride on the 3x3 (:75)
         out = F.conv2d(x, sd[p + ".conv1.weight"])
         out = F.relu_(_bn(sd, p + ".bn1", out))
-        out = F.conv2d(out, sd[p + ".conv2.weight"], None, stride, dilation, dilation)
+        # groups > 1 for ResNeXt (models/backbone/resnext.py:84-87): inferred from the parameter's shape
+        w2 = sd[p + ".conv2.weight"]
+        out = F.conv2d(out, w2, None, stride, dilation, dilation, out.shape[1] // w2.shape[1])
         out = F.relu_(_bn(sd, p + ".bn2", out))
         out = F.conv2d(out, sd[p + ".conv3.weight"])
         out = _bn(sd, p + ".bn3", out)

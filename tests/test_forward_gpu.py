@@ -277,3 +277,31 @@ def test_neck_with_folded_batchnorm(cuda_device, neck_type):
     neck.train()
     with pytest.raises(NotImplementedError):
         neck(feats)
+
+
+@pytest.mark.parametrize("base_width,cardinality", [(4, 32), (8, 32)])
+def test_resnext_backbone(cuda_device, base_width, cardinality):
+    """ResNeXt-50 (grouped 3x3 as a 64-channel band on the dense GEMM kernel) + FPN."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    dev = cuda_device
+    torch.manual_seed(5)
+    bb = obj_from_dict(dict(type="ResNeXt", depth=50, base_width=base_width, cardinality=cardinality),
+                       parent=models.backbone)
+    bb.init_weights()
+    sd = bb.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(3))
+    bb.load_state_dict(sd)
+    bb.eval()
+    _, neck = helpers.build_product_pair(50, seed=5)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(2, 3, 128, 160, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    wf = orc.resnet_forward(bsd, x.float(), 50)
+    wp = orc.fpn_forward(nsd, [f.clone() for f in wf], [256, 512, 1024, 2048], 256, 5)
+    feats, outs = _run_product(bb, neck, x, dev)
+    _check_levels(feats, wf, ["C2", "C3", "C4", "C5"])
+    e = _check_levels(outs, wp, ["P2", "P3", "P4", "P5", "P6"])
+    print("rel-L2 ResNeXt-50 %dx%dd" % (cardinality, base_width), e)
+    bb.train()
+    with pytest.raises(NotImplementedError):
+        bb(x.to(dev))

@@ -172,3 +172,27 @@ def test_neck_with_batchnorm_matches_reference(neck_type):
         ref = neck([f.clone() for f in feats])
         got = fwd(sd, [f.clone() for f in feats], [64, 128, 256, 512], 256, 5)
     assert all(torch.equal(x, y) for x, y in zip(ref, got))
+
+
+def test_resnext_oracle_and_mirror_match_reference():
+    """Row f4: ResNeXt-50 32x4d -- the product module mirrors the reference's parameters for the same seed and
+    the oracle (grouped conv2 inferred from the parameter shape) is bit-identical to the live reference."""
+    from torch_detection_b200 import models as b200
+    from torch_detection_b200.utils import obj_from_dict as b200_build
+    ref_backbone, ref_necks, obj_from_dict = reference_shim.load()
+    cfg = dict(type="ResNeXt", depth=50, base_width=4, cardinality=32)
+    torch.manual_seed(1)
+    ref = obj_from_dict(dict(cfg), parent=ref_backbone)
+    ref.init_weights()
+    ref.eval()
+    torch.manual_seed(1)
+    mine = b200_build(dict(cfg), parent=b200.backbone)
+    mine.init_weights()
+    a, b = ref.state_dict(), mine.state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+    assert mine.resX_layers == ["layer1", "layer2", "layer3", "layer4"] and mine.feat_dim == ref.feat_dim
+    x = torch.randn(1, 3, 64, 96)
+    with torch.no_grad():
+        want = ref(x)
+        got = orc.resnet_forward(a, x, 50)
+    assert all(torch.equal(u, v) for u, v in zip(want, got))

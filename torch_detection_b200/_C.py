@@ -50,7 +50,7 @@ class TdetOp(ctypes.Structure):
         ("coarse_meta", ctypes.c_void_p), ("y_meta", ctypes.c_void_p),
         ("bound_consts", ctypes.c_void_p),
         ("mask", ctypes.c_void_p), ("gy", ctypes.c_void_p),
-        ("gy_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("gy_dtype", ctypes.c_int32), ("groups", ctypes.c_int32),
         ("dw", ctypes.c_void_p), ("gy_meta", ctypes.c_void_p),
     ]
 
@@ -72,7 +72,7 @@ class TdetError(RuntimeError):
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
     "tdet_stem_staging_dims", "tdet_set_sm_reserve",
-    "tdet_pack_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
+    "tdet_pack_conv_weight", "tdet_pack_grouped_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
     "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_range", "tdet_plan_run_timed",
     "tdet_plan_num_launches", "tdet_plan_launch_info",
@@ -98,6 +98,7 @@ def lib():
     L.tdet_device_supported.argtypes = [i32]
     L.tdet_set_sm_reserve.argtypes = [i32, i32]
     L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.tdet_pack_grouped_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_dgrad_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
     L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]

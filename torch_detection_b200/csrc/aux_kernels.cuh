@@ -143,6 +143,28 @@ pack_weight_kernel(const float* __restrict__ w, W* __restrict__ out, int cout, i
   }
 }
 
+// grouped fp32 [O][I/g][kh][kw] -> dense 16-bit [O][kh][kw][I], zero outside the output channel's group
+template <typename W>
+__global__ void __launch_bounds__(256)
+pack_grouped_weight_kernel(const float* __restrict__ w, W* __restrict__ out, int cout, int cin, int kh, int kw,
+                           int groups) {
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  const int cig = cin / groups, cog = cout / groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    long long t = i / cin;
+    const int s = static_cast<int>(t % kw);
+    t /= kw;
+    const int r = static_cast<int>(t % kh);
+    const int co = static_cast<int>(t / kh);
+    const int g = co / cog;
+    float v = 0.0f;
+    if (ci / cig == g) v = w[((static_cast<long long>(co) * cig + (ci - g * cig)) * kh + r) * kw + s];
+    out[i] = to_w16<W>(v);
+  }
+}
+
 // fp32 [64][3][7][7] -> bf16 [64][448], k = r*64 + s*4 + c for s < 7, c < 3 (zero elsewhere): one
 // 64-wide k-block per filter row, matching the 16-pixel x 4-channel window rows the stem loads.
 __global__ void __launch_bounds__(256)

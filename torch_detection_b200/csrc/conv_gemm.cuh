@@ -82,6 +82,7 @@ struct ConvGemmParams {
   int num_m_tiles;
   int num_n_tiles;
   int k_chunks;     // Cin / 64 (A_STEM: 1)
+  int grouped;      // grouped conv as a 64-channel band: n-tile j (BN = 64) contracts only channel chunk j
   int kh, kw, dil;
   int cin;          // B column offset of tap (r,s) is (r*kw + s)*cin
   int a_mode;
@@ -236,7 +237,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   grid_dependency_wait();
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kb = p.kh * p.kw * p.k_chunks;
+  // grouped convs (group width divides 64): output channels [64j, 64j+64) only see input channels of the
+  // same range, so each 64-wide n-tile runs ONE channel chunk per filter tap over the densely packed,
+  // block-diagonal weight matrix
+  const int kcn = p.grouped ? 1 : p.k_chunks;
+  const int num_kb = p.kh * p.kw * kcn;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (A, B)
@@ -256,7 +261,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int t = m_tile / p.tiles_w;
         const int th = t % p.tiles_h;
         const int img = t / p.tiles_h;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(aempty_bar(stage), phase ^ 1u);
           if (lane == 0) {
             mbar_arrive_expect_tx(afull_bar(stage), kPatchBytes);
@@ -290,9 +296,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         cw = tw * p.tile_bw;
         ch = th * p.tile_bh;
       }
+      const int kc_lo = p.grouped ? n_tile : 0;
       for (int r = 0; r < p.kh; ++r) {
         for (int s = 0; s < p.kw; ++s) {
-          for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
               const uint32_t fb = full_bar(stage);
@@ -338,7 +345,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(afull_bar(as), aphase);
           tc_fence_after();
           const uint32_t a0 = smem_a + as * kPatchStageBytes;
@@ -354,11 +362,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                   smem_b + (BRES_KB > 0 ? tap * p.k_chunks + kc : stage) * L::kBBytes);
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k)
-                umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kc - kc_lo) | tap | k) != 0 ? 1u : 0u);
               if (BRES_KB == 0) umma_commit(empty_bar(stage));
               if (tap == 8) {
                 umma_commit(aempty_bar(as));
-                if (kc == p.k_chunks - 1) umma_commit(tfull_bar(acc));
+                if (kc == kc_lo + kcn - 1) umma_commit(tfull_bar(acc));
               }
             }
             __syncwarp();
@@ -455,7 +463,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.num_n_tiles) * BN;
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {

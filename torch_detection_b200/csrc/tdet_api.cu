@@ -393,14 +393,22 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   const int vs = env_int("TDET_VARIANT_SET", kDefaultVariantSet);
   const int naux = (o.residual ? 1 : 0) + (o.mask ? 1 : 0);
   const int resv = env_int("TDET_RES_VARIANT", kDefaultResVariant);
-  if (o.cout % 256 == 0 && !(resv == 2 && naux >= 1)) {
+  const bool grouped = o.groups > 1;
+  if (grouped) {
+    if (o.cin != o.cout || o.cin % o.groups || 64 % (o.cin / o.groups))
+      return fail(TDET_ERR_UNSUPPORTED_SHAPE,
+                  "grouped conv needs cin == cout and a group width dividing 64 (cin %d, cout %d, groups %d)",
+                  o.cin, o.cout, o.groups);
+    gp.grouped = 1;
+  }
+  if (o.cout % 256 == 0 && !grouped && !(resv == 2 && naux >= 1)) {
     l.bn = 256;
     if (naux == 2 || (naux == 1 && (resv == 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
     else if (naux == 1 && resv == 3) { l.stages = 2; l.res_slabs = 6; l.oslabs = 1; }
     else if (naux == 1) { l.stages = 3; l.res_slabs = 3; l.oslabs = 1; }
     else if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; }
     else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
-  } else if (o.cout % 128 == 0) {
+  } else if (o.cout % 128 == 0 && !grouped) {
     l.bn = 128;
     if (naux == 2 || (o.cout % 256 == 0)) { l.stages = 4; l.res_slabs = 4; l.oslabs = 1; }
     else if (vs & 4) { l.stages = 4; l.res_slabs = 2; l.oslabs = 2; }
@@ -539,9 +547,9 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   int g = di.num_sms - di.sm_reserve;
   if (g > num_tiles) g = num_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
-  l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) * o.kh * o.kw);
+  l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) / (grouped ? o.groups : 1) * o.kh * o.kw);
   l.bytes = 2.0 * (static_cast<double>(o.n) * o.h * o.w * o.cin +
-                   static_cast<double>(o.cout) * o.cin * o.kh * o.kw +
+                   static_cast<double>(o.cout) * o.cin / (grouped ? o.groups : 1) * o.kh * o.kw +
                    real_rows * o.cout * (1 + (o.residual ? 1 : 0)) +
                    (o.mask ? real_rows * o.cout : 0.0) +
                    (o.coarse ? static_cast<double>(o.n) * o.hc * o.wc * o.cout : 0.0));
@@ -1097,6 +1105,23 @@ int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin
   else
     pack_weight_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
                                                          cout, cin, kh, kw);
+  TDET_CUDA(cudaGetLastError());
+  return TDET_OK;
+}
+
+int tdet_pack_grouped_conv_weight(const float* w, void* w_packed, int cout, int cin, int kh, int kw, int groups,
+                                  int dtype, void* stream) {
+  if (!w || !w_packed || cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0 || groups < 1 || cin % groups ||
+      cout % groups || !is16(dtype))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "pack_grouped_conv_weight: bad arguments");
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  const int g = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TDET_F16)
+    pack_grouped_weight_kernel<__half><<<g, 256, 0, st>>>(w, static_cast<__half*>(w_packed), cout, cin, kh, kw, groups);
+  else
+    pack_grouped_weight_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), cout,
+                                                                 cin, kh, kw, groups);
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }

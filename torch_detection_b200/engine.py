@@ -145,6 +145,22 @@ def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
     return out
 
 
+def pack_grouped_conv_weight(w, groups, dtype=torch.bfloat16, out=None):
+    """fp32 [O][I/groups][kh][kw] grouped parameter -> dense block-diagonal 16-bit [O][kh][kw][I]."""
+    require_cuda(w, "weight")
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    o, ig, kh, kw = w.shape
+    i = ig * groups
+    if out is None:
+        out = torch.empty((o, kh, kw, i), dtype=dtype, device=w.device)
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().tdet_pack_grouped_conv_weight(w.data_ptr(), out.data_ptr(), o, i, kh, kw, groups,
+                                                        _TD[dtype], _stream_ptr(w.device)))
+    return out
+
+
 def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16, out=None):
     """fp32 OIHW parameter (+ folded BN scale per O) -> 16-bit [I][kh][kw][O] with the filter rotated by
     180 degrees: the B operand of the data-gradient conv (a conv over the output gradient)."""
@@ -221,7 +237,7 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
-            coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False):
+            coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1):
     """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype."""
     n, h, w, cin = x.shape
     cout = wgt.shape[0]
@@ -234,6 +250,7 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
         (_C.FLAG_COARSE_PARITY if coarse_parity else 0)
     if mask is not None:
         op.mask = mask.ptr
+    op.groups = groups
     op.n, op.h, op.w, op.cin = n, h, w, cin
     op.cout, op.kh, op.kw = cout, kh, kw
     op.stride, op.pad, op.dil = stride, pad, dil

@@ -32,6 +32,8 @@ class _ResidualUnit(nn.Module):
     ``state_dict`` keys match (``convK``, ``bnK``, ``downsample.{0,1}``)."""
     expansion = 1
     kernel_sizes = ()
+    groups = 1          # ResNeXt: cardinality of the grouped 3x3 (resnext.py:84-87)
+    grouped_conv = -1   # index of the grouped conv
 
     def __init__(self, inplanes, planes, stride=1, dilation=1, use_gn=False, downsample=None):
         super(_ResidualUnit, self).__init__()
@@ -43,7 +45,8 @@ class _ResidualUnit(nn.Module):
                 convs.append(conv1x1_group(cin, cout))
             else:
                 convs.append(conv3x3_group(cin, cout, stride if strided else 1,
-                                           dilation if (strided or self.all_dilated) else 1))
+                                           dilation if (strided or self.all_dilated) else 1,
+                                           groups=self.groups if idx == self.grouped_conv else 1))
         for idx, conv in enumerate(convs):
             self.add_module("conv%d" % (idx + 1), conv)
         self.norm_names = ["bn%d" % (i + 1) for i in range(len(convs))]
@@ -284,9 +287,15 @@ class ResNet(nn.Module):
 
         def conv(name, module, bn, src, dst, residual=None, relu=True):
             k = module.kernel_size[0]
-            wgt = cache.get((name, "w", src.dtype),
-                            lambda out: engine.pack_conv_weight(module.weight, src.dtype, out=out),
-                            deps=(module.weight,))
+            if module.groups > 1:
+                wgt = cache.get((name, "w", src.dtype),
+                                lambda out: engine.pack_grouped_conv_weight(module.weight, module.groups, src.dtype,
+                                                                            out=out),
+                                deps=(module.weight,))
+            else:
+                wgt = cache.get((name, "w", src.dtype),
+                                lambda out: engine.pack_conv_weight(module.weight, src.dtype, out=out),
+                                deps=(module.weight,))
             sc, sh = cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))
             is_scaled = scaled and dst.dtype == torch.float16
             consts = cache.get((name, "consts", src.dtype),
@@ -294,7 +303,7 @@ class ResNet(nn.Module):
                                deps=(module.weight,) + _bn_deps(bn)) if is_scaled else None
             ops.append(engine.op_conv(src, wgt, dst, k, k, module.stride[0], module.padding[0],
                                       module.dilation[0], scale=sc, shift=sh, residual=residual,
-                                      relu=relu, consts=consts, scaled_out=is_scaled))
+                                      relu=relu, consts=consts, scaled_out=is_scaled, groups=module.groups))
 
         # geometry of every stage output, and the full-batch bf16 tensors that hold them
         ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
@@ -470,6 +479,8 @@ class ResNet(nn.Module):
             convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
             bns = [m for m in stage.modules() if isinstance(m, nn.BatchNorm2d)]
             flags = [m.weight.requires_grad for m in convs]
+            if any(flags) and any(m.groups > 1 for m in convs):
+                raise NotImplementedError("training grouped convolutions (ResNeXt) is not on the B200 path yet")
             bflags = [p.requires_grad for m in bns for p in (m.weight, m.bias)]
             if any(flags):
                 if not all(flags):

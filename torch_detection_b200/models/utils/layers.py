@@ -11,8 +11,6 @@ import torch.nn as nn
 
 
 def _conv(cin, cout, k, stride, padding, dilation, groups, bias):
-    if groups != 1:
-        raise NotImplementedError("grouped convolution is outside the B200 ResNet/FPN path")
     return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=padding, dilation=dilation,
                      groups=groups, bias=bias)
 
