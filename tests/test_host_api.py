@@ -71,7 +71,8 @@ def test_constructor_errors():
     with pytest.raises(NotImplementedError):
         ResNet(50, use_gn=True)
     with pytest.raises(NotImplementedError):
-        FPN([256, 512], 256, 2, normalize=dict(type="BN"))
+        FPN([256, 512], 256, 2, normalize=dict(type="GN"), use_gn=True)   # GroupNorm cannot be folded
+    assert FPN([256, 512], 256, 2, normalize=dict(type="BN")).lateral_convs[0].with_norm
     with pytest.raises(TypeError):
         ResNet(18).init_weights(pretrained=3)
 
