@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 6
+#define TDET_ABI_VERSION 7
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -83,7 +83,8 @@ typedef enum tdet_op_kind {
   TDET_OP_ADD_MASK = 10, /* y = (x + residual) * (mask > 0): gradient merge / ReLU backward */
   TDET_OP_ZERO = 11,     /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
   TDET_OP_AMAX = 12,     /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
-  TDET_OP_BN_AFFINE_GRAD = 13 /* gamma / beta gradients of a frozen-statistics BatchNorm from stored tensors */
+  TDET_OP_BN_AFFINE_GRAD = 13, /* gamma / beta gradients of a frozen-statistics BatchNorm from stored tensors */
+  TDET_OP_SPLIT_COMBINE = 14 /* y (fp32 [n][h][w][cin]) = hi + lo of a split-precision tensor x ([n][h][w][2*cin] bf16) */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -94,6 +95,12 @@ enum {
                                x_meta and bound_consts) */
   TDET_FLAG_COARSE_PARITY = 4, /* coarse[i][j] is added at y[2i][2j] only (adjoint of a stride-2 1x1 conv,
                                   resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */
+  TDET_FLAG_SPLIT = 8       /* split precision (the fp32-I/O mode, <= 1e-4 vs the fp32 reference): every
+                               activation tensor is a bf16 pair value = hi + lo stored as 2*C channels
+                               [hi | lo] (PREP / STEM staging: two image planes), conv weights come from
+                               tdet_pack_conv_weight_split; the GEMM accumulates hi*hi + lo*hi + hi*lo in
+                               fp32 and the epilogue splits its fp32 result again.  cin / cout stay the
+                               LOGICAL channel counts.  Valid on PREP, STEM, MAXPOOL, CONV. */
 };
 
 /* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
@@ -224,6 +231,11 @@ int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
 int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,
                  float eps, float* scale, float* shift, int channels, void* stream);
+/* Split-precision operands: fp32 OIHW -> bf16 [cout][kh][kw][2*cin], per filter tap the cin hi values
+ * bf16(w) followed by the cin lo values bf16(w - hi).  Stem: fp32 [64][3][7][7] -> bf16 [64][896] (the 448-column
+ * layout of tdet_pack_stem_weight for hi, then for lo). */
+int tdet_pack_conv_weight_split(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw, void* stream);
+int tdet_pack_stem_weight_split(const float* w_oihw, void* w_packed, void* stream);
 /* Grouped conv weights: fp32 [cout][cin/groups][kh][kw] -> DENSE 16-bit [cout][kh][kw][cin], zero outside each
  * output channel's group (block-diagonal): the GEMM kernel then contracts, per 64-wide tile of output
  * channels, only the 64 input channels of the same range. */

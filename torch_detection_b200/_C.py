@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # tdet_status
 OK = 0
@@ -24,11 +24,13 @@ OP_PREP, OP_STEM, OP_MAXPOOL, OP_CONV, OP_SUBSAMPLE = 0, 1, 2, 3, 4
 OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO = 5, 6, 7, 8, 9, 10, 11
 OP_AMAX = 12
 OP_BN_AFFINE_GRAD = 13
+OP_SPLIT_COMBINE = 14
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1
 FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4
+FLAG_SPLIT = 8
 
 
 class TdetOp(ctypes.Structure):
@@ -72,7 +74,8 @@ class TdetError(RuntimeError):
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
     "tdet_stem_staging_dims", "tdet_set_sm_reserve",
-    "tdet_pack_conv_weight", "tdet_pack_grouped_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
+    "tdet_pack_conv_weight", "tdet_pack_conv_weight_split", "tdet_pack_stem_weight_split",
+    "tdet_pack_grouped_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
     "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_range", "tdet_plan_run_timed",
     "tdet_plan_num_launches", "tdet_plan_launch_info",
@@ -98,6 +101,8 @@ def lib():
     L.tdet_device_supported.argtypes = [i32]
     L.tdet_set_sm_reserve.argtypes = [i32, i32]
     L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.tdet_pack_conv_weight_split.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.tdet_pack_stem_weight_split.argtypes = [vp, vp, vp]
     L.tdet_pack_grouped_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_dgrad_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]

@@ -22,7 +22,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
                   int n, int hv, int wv, int hp, int wp, const float* __restrict__ scale,
-                  const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta) {
+                  const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta, int split) {
   const long long total = static_cast<long long>(n) * hp * wp;
   float amax = 0.0f;
   float s0 = 1.0f, s1 = 1.0f, s2 = 1.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
@@ -44,6 +44,15 @@ prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long
       o.x = pack_bf16x2(c0, c1);
       o.y = pack_bf16x2(c2, 0.0f);
       amax = fmaxf(amax, fmaxf(fmaxf(fabsf(bf16_lo(o.x)), fabsf(bf16_hi(o.x))), fabsf(bf16_lo(o.y))));
+      if (split) {
+        // lo plane of the split-precision staging: the batch's second half [n .. 2n)
+        uint2 l;
+        l.x = pack_bf16x2(c0 - bf16_lo(o.x), c1 - bf16_hi(o.x));
+        l.y = pack_bf16x2(c2 - bf16_lo(o.y), 0.0f);
+        y[total + i] = l;
+      }
+    } else if (split) {
+      y[total + i] = make_uint2(0u, 0u);
     }
     y[i] = o;
   }
@@ -140,6 +149,110 @@ pack_weight_kernel(const float* __restrict__ w, W* __restrict__ out, int cout, i
     const int r = static_cast<int>(t % kh);
     const int co = static_cast<int>(t / kh);
     out[i] = to_w16<W>(w[((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s]);
+  }
+}
+
+// split precision: fp32 OIHW -> bf16 [O][kh][kw][2*I]: per tap I hi values then I lo values
+__global__ void __launch_bounds__(256)
+pack_weight_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int kh, int kw) {
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    long long t = i / cin;
+    const int s = static_cast<int>(t % kw);
+    t /= kw;
+    const int r = static_cast<int>(t % kh);
+    const int co = static_cast<int>(t / kh);
+    const float v = w[((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const long long base = ((static_cast<long long>(co) * kh + r) * kw + s) * (2 * cin);
+    out[base + ci] = hi;
+    out[base + cin + ci] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// split-precision stem weights: [64][896] = {448 hi | 448 lo}, each in the pack_stem_weight layout
+__global__ void __launch_bounds__(256)
+pack_stem_weight_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 448) return;
+  const int co = i / 448;
+  const int k = i - co * 448;
+  const int r = k >> 6;
+  const int s = (k & 63) >> 2;
+  const int c = k & 3;
+  float v = 0.0f;
+  if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[co * 896 + k] = hi;
+  out[co * 896 + 448 + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// split-precision 3x3/2 max-pool on [n][h][w][2*C] (hi | lo): the max is taken on hi + lo, the winning pair kept
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_split_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int c8,
+                          int ho, int wo) {
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int ow = static_cast<int>(t % wo);
+    t /= wo;
+    const int oh = static_cast<int>(t % ho);
+    const int img = static_cast<int>(t / ho);
+    float best[8];
+    uint32_t bh[4] = {0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -3.0e38f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int ih = 2 * oh - 1 + dy;
+      if (ih < 0 || ih >= h) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int iw = 2 * ow - 1 + dx;
+        if (iw < 0 || iw >= w) continue;
+        const uint4* px = x + ((static_cast<long long>(img) * h + ih) * w + iw) * (2 * c8);
+        const uint4 vh = __ldg(px + cg), vl = __ldg(px + c8 + cg);
+        const uint32_t wh[4] = {vh.x, vh.y, vh.z, vh.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v0 = bf16_lo(wh[j]) + bf16_lo(wl[j]), v1 = bf16_hi(wh[j]) + bf16_hi(wl[j]);
+          if (v0 > best[2 * j]) {
+            best[2 * j] = v0;
+            bh[j] = (bh[j] & 0xFFFF0000u) | (wh[j] & 0xFFFFu);
+            bl[j] = (bl[j] & 0xFFFF0000u) | (wl[j] & 0xFFFFu);
+          }
+          if (v1 > best[2 * j + 1]) {
+            best[2 * j + 1] = v1;
+            bh[j] = (bh[j] & 0xFFFFu) | (wh[j] & 0xFFFF0000u);
+            bl[j] = (bl[j] & 0xFFFFu) | (wl[j] & 0xFFFF0000u);
+          }
+        }
+      }
+    }
+    uint4* py = y + ((static_cast<long long>(img) * ho + oh) * wo + ow) * (2 * c8);
+    py[cg] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+    py[c8 + cg] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+  }
+}
+
+// fp32 y[m][c] = hi + lo of a split-precision tensor x[m][2c]
+__global__ void __launch_bounds__(256)
+split_combine_kernel(const uint4* __restrict__ x, float4* __restrict__ y, long long rows, int c8) {
+  const long long total = rows * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long m = i / c8;
+    const int cg = static_cast<int>(i - m * c8);
+    const uint4 vh = __ldg(x + m * (2 * c8) + cg), vl = __ldg(x + m * (2 * c8) + c8 + cg);
+    float4* dst = y + i * 2;
+    dst[0] = make_float4(bf16_lo(vh.x) + bf16_lo(vl.x), bf16_hi(vh.x) + bf16_hi(vl.x),
+                         bf16_lo(vh.y) + bf16_lo(vl.y), bf16_hi(vh.y) + bf16_hi(vl.y));
+    dst[1] = make_float4(bf16_lo(vh.z) + bf16_lo(vl.z), bf16_hi(vh.z) + bf16_hi(vl.z),
+                         bf16_lo(vh.w) + bf16_lo(vl.w), bf16_hi(vh.w) + bf16_hi(vl.w));
   }
 }
 

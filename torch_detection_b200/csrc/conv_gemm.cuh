@@ -83,6 +83,13 @@ struct ConvGemmParams {
   int num_n_tiles;
   int k_chunks;     // Cin / 64 (A_STEM: 1)
   int grouped;      // grouped conv as a 64-channel band: n-tile j (BN = 64) contracts only channel chunk j
+  // Split precision (fp32-I/O mode): every tensor is a bf16 pair value = hi + lo stored as 2*C channels
+  // [hi | lo]; the GEMM runs the three significant products hi*hi + lo*hi + hi*lo as a 3x longer K loop
+  // (pure producer-side indexing), the epilogue splits its fp32 result into hi/lo again.
+  int split;
+  int b_tap_stride; // weight columns per filter tap (cin, or 2*cin in split mode; stem: 64)
+  int b_lo_off;     // split mode: column offset of the lo weights inside a tap (cin; stem: 448)
+  int a_lo_img;     // split mode, stem: image-index offset of the lo plane of the staged batch
   int kh, kw, dil;
   int cin;          // B column offset of tap (r,s) is (r*kw + s)*cin
   int a_mode;
@@ -160,7 +167,8 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
 }
 
 // MASKED: the kernel carries the ReLU-backward mask path (dgrad); forward instantiations compile it out.
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED>
+// SPLIT: split-precision epilogue (hi/lo outputs, hi/lo residual and coarse operands); needs OSLABS == 2.
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false>
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
@@ -241,7 +249,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   // same range, so each 64-wide n-tile runs ONE channel chunk per filter tap over the densely packed,
   // block-diagonal weight matrix
   const int kcn = p.grouped ? 1 : p.k_chunks;
-  const int num_kb = p.kh * p.kw * kcn;
+  const int nv = (SPLIT && p.split) ? 3 : 1;  // virtual K passes: hi*hi, lo*hi, hi*lo
+  const int num_kb = p.kh * p.kw * kcn * nv;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (A, B)
@@ -299,6 +308,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int kc_lo = p.grouped ? n_tile : 0;
       for (int r = 0; r < p.kh; ++r) {
         for (int s = 0; s < p.kw; ++s) {
+         for (int v = 0; v < nv; ++v) {
           for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
@@ -306,26 +316,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               mbar_arrive_expect_tx(fb, stage_tx);
               const uint32_t dst_a = smem_a + stage * kABytes;
               const uint32_t dst_b = smem_b + stage * L::kBBytes;
+              const int ka = (kc + (v == 1 ? p.k_chunks : 0)) * kBK;  // lo activations sit C channels further
               if (p.a_mode == A_TILED) {
-                tma_load_2d(dst_a, &p.tmap_a, fb, kc * kBK, m_tile * kBM);
+                tma_load_2d(dst_a, &p.tmap_a, fb, ka, m_tile * kBM);
               } else if (p.a_mode == A_IM2COL) {
-                tma_load_im2col_4d(dst_a, &p.tmap_a, fb, kc * kBK, cw, ch, cn,
+                tma_load_im2col_4d(dst_a, &p.tmap_a, fb, ka, cw, ch, cn,
                                    static_cast<uint16_t>(s * p.dil),
                                    static_cast<uint16_t>(r * p.dil));
               } else if (p.a_mode == A_STEM) {
                 // filter row r of the 7x7 window = staged image row 2*(ho + r/2) + (r & 1)
-                tma_load_5d(dst_a, &p.tmap_a, fb, 0, r & 1, cw, ch + (r >> 1), cn);
+                tma_load_5d(dst_a, &p.tmap_a, fb, 0, r & 1, cw, ch + (r >> 1), cn + (v == 1 ? p.a_lo_img : 0));
               } else {
                 // A_STEM2: the 7 staged image rows x 272 pixels all windows of this tile live in,
                 // copied linearly (no swizzle); coordinates (64-element chunk, chunk index, row, image)
                 tma_load_4d(dst_a, &p.tmap_a, fb, 0, cw >> 3, 2 * ch, cn);
               }
               if (BRES_KB == 0)
-                tma_load_2d(dst_b, &p.tmap_b, fb, (r * p.kw + s) * p.cin + kc * kBK, n0);
+                tma_load_2d(dst_b, &p.tmap_b, fb,
+                            (r * p.kw + s) * p.b_tap_stride + (v == 2 ? p.b_lo_off : 0) + kc * kBK, n0);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
+         }
         }
       }
     }
@@ -425,7 +438,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // is TMA-staged), in tile order; the two epilogue groups consume alternate slabs from this ONE ring
     // (sharing it lets the faster group borrow slots; two private rings of half the depth measured 15 %
     // slower on the residual convs).
-    const int nload = (p.has_res ? 1 : 0) + ((MASKED && p.mask_tma) ? 1 : 0);
+    const bool rsplit = SPLIT && p.split && p.has_res;
+    const int nload = rsplit ? 2 : (p.has_res ? 1 : 0) + ((MASKED && p.mask_tma) ? 1 : 0);
     if (RES_SLABS > 0 && nload > 0) {
       int rs = 0;
       int issued = 0;
@@ -435,17 +449,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int n_tile = tile - m_tile * p.num_n_tiles;
         for (int s = 0; s < kSlabsPerTile; ++s) {
           for (int j = 0; j < nload; ++j) {
-            const CUtensorMap* tm = (j == 0 && p.has_res) ? &p.tmap_res : &p.tmap_mask;
+            const CUtensorMap* tm = (rsplit || (j == 0 && p.has_res)) ? &p.tmap_res : &p.tmap_mask;
+            const int cres = n_tile * BN + s * 64 + ((rsplit && j == 1) ? p.N : 0);  // lo half: N channels on
             mbar_wait(rempty_bar(rs), rphase ^ 1u);
             if (lane == 0) {
               mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
               if (p.a_mode >= A_STEM) {
                 const int tw = m_tile % p.tiles_w;
                 const int t = m_tile / p.tiles_w;
-                tma_load_4d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), n_tile * BN + s * 64,
+                tma_load_4d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres,
                             tw * p.tile_bw, (t % p.tiles_h) * p.tile_bh, t / p.tiles_h);
               } else {
-                tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), n_tile * BN + s * 64, m_tile * kBM);
+                tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres, m_tile * kBM);
               }
               *ring_issued = issued;  // this fill's predecessor in the slot has been consumed, hence completed
             }
@@ -469,7 +484,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
               mbar_arrive_expect_tx(full_bar(stage), L::kBBytes);
-              tma_load_2d(smem_b + stage * L::kBBytes, &p.tmap_b, full_bar(stage), tap * p.cin + kc * kBK, n0);
+              tma_load_2d(smem_b + stage * L::kBBytes, &p.tmap_b, full_bar(stage), tap * p.b_tap_stride + kc * kBK, n0);
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -488,7 +503,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
     const bool mask_tma = MASKED && RES_SLABS > 0 && p.mask_tma != 0;
-    const int nload = (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
+    const bool split = SPLIT && p.split != 0;
+    static_assert(!SPLIT || OSLABS == 2, "split precision stages the hi and the lo slab side by side");
+    // split mode: the residual's lo slab rides in the ring slot the mask would use
+    const int nload = (split && has_res) ? 2 : (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
     float* s_scale = s_params + group * 2 * L::kGroupCols;
@@ -570,7 +588,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int img = t / p.Ho;
         if (!(p.coarse_parity && ((pp | q) & 1)))
           coarse_row = static_cast<const uint8_t*>(p.coarse) +
-                       (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) * p.N + n0) * 2;
+                       (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) *
+                            (split ? 2 * p.N : p.N) + n0) * 2;
       }
       const uint8_t* mask_row = nullptr;
       if (MASKED && valid && p.mask_src && !mask_tma)
@@ -593,7 +612,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t mphase = static_cast<uint32_t>(midx / kRS) & 1u;
         // the staging buffer `ob` was last read by the TMA store this group issued OSLABS slabs ago
         if (issuer) {
-          if (OSLABS == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (OSLABS == 1 || split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         // An mbarrier parity wait is only sound if the PREVIOUS fill of the slot (ring index - kRS) has
@@ -609,8 +628,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         if (has_res) mbar_wait(rfull_bar(rs), rphase);
-        if (mask_tma) mbar_wait(rfull_bar(ms), mphase);
+        if (mask_tma || (split && has_res)) mbar_wait(rfull_bar(ms), mphase);
         named_bar_sync(gbar, kEpiGroupThreads);
+        if (split) ob = 0;
         const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
         const uint32_t mk_row = smem_res + ms * kSlabBytes + row * 128;
@@ -671,6 +691,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 x[8 * j + 2 * e + 1] = fmaf(hi, mul_res, x[8 * j + 2 * e + 1]);
               }
             }
+            if (SPLIT && split) {
+              // lo half of the residual pair (next ring slot)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t a = mk_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+                uint4 r2;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r2.x), "=r"(r2.y), "=r"(r2.z), "=r"(r2.w)
+                             : "r"(a));
+                const uint32_t w4[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[8 * j + 2 * e] += bf16_lo(w4[e]);
+                  x[8 * j + 2 * e + 1] += bf16_hi(w4[e]);
+                }
+              }
+            }
           }
           if (coarse_row) {
 #pragma unroll
@@ -682,6 +719,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 unpack16x2(w4[e], co_fp16, lo, hi);
                 x[8 * j + 2 * e] = fmaf(lo, mul_co, x[8 * j + 2 * e]);
                 x[8 * j + 2 * e + 1] = fmaf(hi, mul_co, x[8 * j + 2 * e + 1]);
+              }
+            }
+            if (SPLIT && split) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 c2 = ldg_nc_v4(coarse_row + (p.N + slab * 64 + half * 32 + j * 8) * 2);
+                const uint32_t w4[4] = {c2.x, c2.y, c2.z, c2.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  x[8 * j + 2 * e] += bf16_lo(w4[e]);
+                  x[8 * j + 2 * e + 1] += bf16_hi(w4[e]);
+                }
               }
             }
           }
@@ -716,6 +765,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
                          "r"(o.z), "r"(o.w)
                          : "memory");
+            if (SPLIT && split) {
+              // lo = bf16(x - hi): the second staging slab of the group
+              uint4 l;
+              l.x = pack_bf16x2(x[8 * j + 0] - bf16_lo(o.x), x[8 * j + 1] - bf16_hi(o.x));
+              l.y = pack_bf16x2(x[8 * j + 2] - bf16_lo(o.y), x[8 * j + 3] - bf16_hi(o.y));
+              l.z = pack_bf16x2(x[8 * j + 4] - bf16_lo(o.z), x[8 * j + 5] - bf16_hi(o.z));
+              l.w = pack_bf16x2(x[8 * j + 6] - bf16_lo(o.w), x[8 * j + 7] - bf16_hi(o.w));
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a + kSlabBytes), "r"(l.x), "r"(l.y),
+                           "r"(l.z), "r"(l.w)
+                           : "memory");
+            }
           }
         }
         if (slab + (kByTile ? 1 : 2) >= kSlabsPerTile) {
@@ -741,11 +801,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 "r"(st_c1)
                 : "memory");
           }
+          if (SPLIT && split) {
+            if (p.a_mode >= A_STEM) {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src + kSlabBytes), "r"(p.N + n0 + slab * 64),
+                  "r"(st_c1), "r"(st_c2), "r"(st_c3)
+                  : "memory");
+            } else {
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src + kSlabBytes), "r"(p.N + n0 + slab * 64),
+                  "r"(st_c1)
+                  : "memory");
+            }
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           if (has_res) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
-          if (mask_tma) mbar_arrive(rempty_bar(ms));
+          if (mask_tma || (split && has_res)) mbar_arrive(rempty_bar(ms));
         }
-        if (OSLABS > 1) ob ^= 1;
+        if (OSLABS > 1 && !split) ob ^= 1;
       }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");

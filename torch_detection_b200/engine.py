@@ -145,6 +145,34 @@ def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
     return out
 
 
+def pack_conv_weight_split(w, out=None):
+    """fp32 OIHW -> bf16 [O][kh][kw][2*I]: per tap the hi halves bf16(w), then the lo halves bf16(w - hi)."""
+    require_cuda(w, "weight")
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    o, i, kh, kw = w.shape
+    if out is None:
+        out = torch.empty((o, kh, kw, 2 * i), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().tdet_pack_conv_weight_split(w.data_ptr(), out.data_ptr(), o, i, kh, kw,
+                                                      _stream_ptr(w.device)))
+    return out
+
+
+def pack_stem_weight_split(w, out=None):
+    """fp32 [64][3][7][7] -> bf16 [64][896]: the stem operand layout for hi, then for lo."""
+    require_cuda(w, "weight")
+    w = w.detach().float().contiguous()
+    if tuple(w.shape) != (64, 3, 7, 7):
+        raise ValueError("stem weight must be (64,3,7,7)")
+    if out is None:
+        out = torch.empty((64, 896), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().tdet_pack_stem_weight_split(w.data_ptr(), out.data_ptr(), _stream_ptr(w.device)))
+    return out
+
+
 def pack_grouped_conv_weight(w, groups, dtype=torch.bfloat16, out=None):
     """fp32 [O][I/groups][kh][kw] grouped parameter -> dense block-diagonal 16-bit [O][kh][kw][I]."""
     require_cuda(w, "weight")
@@ -237,8 +265,11 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
-            coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1):
-    """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype."""
+            coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1,
+            split=False):
+    """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype.
+    split: split-precision tensors (bf16 hi|lo pairs, 2x the logical channels in memory); Act shapes stay
+    logical."""
     n, h, w, cin = x.shape
     cout = wgt.shape[0]
     if wgt.dtype != x.dtype:
@@ -247,7 +278,7 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
     op = _C.TdetOp()
     op.kind = _C.OP_CONV
     op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
-        (_C.FLAG_COARSE_PARITY if coarse_parity else 0)
+        (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_SPLIT if split else 0)
     if mask is not None:
         op.mask = mask.ptr
     op.groups = groups
@@ -269,7 +300,7 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
     return op
 
 
-def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None):
+def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, split=False):
     """x: logical (n, 3, h, w) image batch (fp32 / bf16 / uint8, any strides: an HWC batch viewed as NCHW is
     fine); scale/shift: optional fp32[3] device vectors of the per-channel normalisation v*scale + shift;
     padded_hw: the (H, W) >= (h, w) the network sees, the difference is zero padding (size divisor)."""
@@ -278,6 +309,7 @@ def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None):
     op.kind = _C.OP_PREP
     ph, pw = padded_hw if padded_hw is not None else (h, w)
     op.n, op.h, op.w, op.cin = n, ph, pw, c
+    op.flags = _C.FLAG_SPLIT if split else 0   # y then holds 2n staged planes: hi then lo
     if (ph, pw) != (h, w):
         op.hc, op.wc = h, w
     op.ho, op.wo = ho, wo
@@ -292,11 +324,12 @@ def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None):
     return op
 
 
-def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False):
+def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False, split=False):
     """x: staged image buffer (bf16); y: ``Act`` of shape (n, ho, wo, 64)."""
     op = _C.TdetOp()
     op.kind = _C.OP_STEM
-    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0)
+    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
+        (_C.FLAG_SPLIT if split else 0)
     op.n, op.h, op.w, op.cin = n, h, w, 3
     op.cout, op.kh, op.kw = 64, 7, 7
     op.stride, op.pad, op.dil = 2, 3, 1
@@ -309,10 +342,11 @@ def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=Non
     return op
 
 
-def op_maxpool(x, y):
+def op_maxpool(x, y, split=False):
     n, h, w, c = x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_MAXPOOL
+    op.flags = _C.FLAG_SPLIT if split else 0
     op.n, op.h, op.w, op.cin = n, h, w, c
     op.cout, op.kh, op.kw, op.stride, op.pad, op.dil = c, 3, 3, 2, 1, 1
     op.ho, op.wo = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
@@ -321,8 +355,21 @@ def op_maxpool(x, y):
     return op
 
 
-def op_subsample(x, y):
+def op_split_combine(x, y):
+    """y (fp32 NHWC tensor) = hi + lo of the split-precision activation x (logical shape (n, h, w, c))."""
     n, h, w, c = x.shape
+    assert y.dtype == torch.float32 and y.numel() == n * h * w * c
+    op = _C.TdetOp()
+    op.kind = _C.OP_SPLIT_COMBINE
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.x, op.y = x.ptr, y.data_ptr()
+    return op
+
+
+def op_subsample(x, y, split=False):
+    n, h, w, c = x.shape
+    if split:
+        c = 2 * c   # a pure copy: the physical channel count is what matters
     op = _C.TdetOp()
     op.kind = _C.OP_SUBSAMPLE
     op.n, op.h, op.w, op.cin = n, h, w, c
