@@ -13,6 +13,7 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 
 BF16_GATE = 1e-2
+FP32_GATE = 1e-4   # fp32 I/O: split-precision kernels (north_star tolerance)
 
 
 def _run_product(bb, neck, x, dev):
@@ -45,8 +46,10 @@ def test_golden_vectors(cuda_device, name, dtype):
     assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
     feats, outs = _run_product(bb, neck, arrays["x"].to(dtype), cuda_device)
     assert all(t.dtype == dtype for t in feats + outs)
-    _check_levels(feats, [arrays["C%d" % i] for i in range(2, 6)], ["C2", "C3", "C4", "C5"])
-    _check_levels(outs, [arrays["P%d" % i] for i in range(2, 7)], ["P2", "P3", "P4", "P5", "P6"])
+    gate = FP32_GATE if dtype == torch.float32 else BF16_GATE
+    _check_levels(feats, [arrays["C%d" % i] for i in range(2, 6)], ["C2", "C3", "C4", "C5"], gate)
+    e = _check_levels(outs, [arrays["P%d" % i] for i in range(2, 7)], ["P2", "P3", "P4", "P5", "P6"], gate)
+    print("golden %s %s" % (name, dtype), e)
 
 
 @pytest.mark.parametrize("depth,shape,bnstats", [

@@ -107,3 +107,46 @@ def test_split_lateral_with_upsample_add_and_combine(cuda_device):
     ref = F.conv2d(x, wt, bias) + F.interpolate(co, scale_factor=2, mode="nearest")
     assert torch.equal(out, combine(y))
     assert rel_l2(out, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("depth,shape,bnstats", [
+    (18, (2, 3, 128, 160), True),
+    (50, (2, 3, 128, 160), False),
+    (50, (1, 3, 224, 320), True),
+    (101, (1, 3, 128, 128), True),
+])
+def test_fp32_io_end_to_end(cuda_device, depth, shape, bnstats):
+    """north_star: with fp32 I/O every FPN level (and C2..C5) within rel-L2 <= 1e-4 of the fp32 reference."""
+    from oracle import resnet_fpn_oracle as orc
+    from tests import helpers
+    bb, neck = helpers.build_product_pair(depth, seed=11, bnstats=bnstats)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(5))
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, x, depth)
+    bb, neck = bb.to(cuda_device).eval(), neck.to(cuda_device).eval()
+    with torch.no_grad():
+        feats = bb(x.to(cuda_device))
+        outs = neck(feats)
+    torch.cuda.synchronize()
+    assert all(t.dtype == torch.float32 for t in tuple(feats) + tuple(outs))
+    errs = [orc.rel_l2(a, b) for a, b in zip(tuple(feats) + tuple(outs), tuple(want_f) + tuple(want_p))]
+    print("fp32 I/O R%d %s rel-L2: C %s  P %s" % (depth, shape, ["%.1e" % e for e in errs[:4]], ["%.1e" % e for e in errs[4:]]))
+    assert max(errs) <= 1e-4, errs
+
+
+def test_fp32_io_full_size_image(cuda_device):
+    """BASELINE geometry in fp32-I/O mode: one 800x1333 image zero-padded to 800x1344."""
+    from oracle import resnet_fpn_oracle as orc
+    from tests import helpers
+    bb, neck = helpers.build_product_pair(50, seed=0)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.zeros(1, 3, 800, 1344)
+    x[:, :, :, :1333] = torch.randn(1, 3, 800, 1333, generator=torch.Generator().manual_seed(0))
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, x, 50)
+    bb, neck = bb.to(cuda_device).eval(), neck.to(cuda_device).eval()
+    with torch.no_grad():
+        outs = neck(bb(x.to(cuda_device)))
+    torch.cuda.synchronize()
+    errs = [orc.rel_l2(a, b) for a, b in zip(outs, want_p)]
+    print("fp32 I/O full size rel-L2", ["%.1e" % e for e in errs])
+    assert max(errs) <= 1e-4

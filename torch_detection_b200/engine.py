@@ -108,6 +108,7 @@ class OperandCache(object):
         return tuple((p.data_ptr(), p._version) for p in deps)
 
     def get(self, key, make, deps=()):
+        """Existing entry, or make(None) (remembered together with how to re-derive it in place)."""
         e = self.store.get(key)
         if e is None:
             e = [make(None), make, tuple(deps), self._versions(deps)]

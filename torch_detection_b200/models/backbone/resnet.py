@@ -272,22 +272,31 @@ class ResNet(nn.Module):
                 torch.tensor([1.0 / s for s in stds], dtype=torch.float32, device=dev),
                 torch.tensor([-m / s for m, s in zip(means, stds)], dtype=torch.float32, device=dev)))
         train = train_from is not None
-        internal = INTERNAL_DTYPE
+        # fp32 input in eval mode = the fp32-I/O mode: split-precision tensors (bf16 hi|lo pairs, 2x the
+        # channels in memory, every conv a 3-pass hi/lo GEMM) and fp32 outputs within 1e-4 of the fp32 reference
+        split = (x.dtype == torch.float32) and not train and FP32_IO_SPLIT
+        cs = 2 if split else 1
+        internal = torch.bfloat16 if split else INTERNAL_DTYPE
         scaled = internal == torch.float16
         ops = []
         pool = _BufferPool(dev)
-        segs = [(list(range(len(self.res_layers))), n)] if train else self._segments(n)
+        segs = [(list(range(len(self.res_layers))), n)] if (train or split) else self._segments(n)
         records = []
         max_chunks = max((n + c - 1) // c for _, c in segs)
         n_meta = 16 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
         meta = engine.MetaArena(n_meta, dev)
 
         def new_act(shape, dtype):
-            return engine.Act(pool.get(shape), shape, dtype, meta.new())
+            return engine.Act(pool.get(shape[:3] + (shape[3] * cs,)), shape, dtype, None if split else meta.new())
 
         def conv(name, module, bn, src, dst, residual=None, relu=True):
             k = module.kernel_size[0]
-            if module.groups > 1:
+            if split:
+                if module.groups > 1:
+                    raise NotImplementedError("grouped convolutions have no split-precision (fp32-I/O) path yet")
+                wgt = cache.get((name, "wsplit"), lambda out: engine.pack_conv_weight_split(module.weight, out=out),
+                                deps=(module.weight,))
+            elif module.groups > 1:
                 wgt = cache.get((name, "w", src.dtype),
                                 lambda out: engine.pack_grouped_conv_weight(module.weight, module.groups, src.dtype,
                                                                             out=out),
@@ -303,7 +312,8 @@ class ResNet(nn.Module):
                                deps=(module.weight,) + _bn_deps(bn)) if is_scaled else None
             ops.append(engine.op_conv(src, wgt, dst, k, k, module.stride[0], module.padding[0],
                                       module.dilation[0], scale=sc, shift=sh, residual=residual,
-                                      relu=relu, consts=consts, scaled_out=is_scaled, groups=module.groups))
+                                      relu=relu, consts=consts, scaled_out=is_scaled, groups=module.groups,
+                                      split=split))
 
         # geometry of every stage output, and the full-batch bf16 tensors that hold them
         ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
@@ -319,14 +329,17 @@ class ResNet(nn.Module):
             cout = getattr(last, "conv%d" % len(last.kernel_sizes)).out_channels
             geo.append((hh, ww, cout))
         outs = []
+        outs_f32 = []  # split mode: the returned fp32 tensors (hi + lo of the split stage outputs in `outs`)
         boundary = []
         for li, (sh_, sw_, sc_) in enumerate(geo):
             if li in self.out_indices:
-                t = engine.nhwc_empty(n, sh_, sw_, sc_, dev)  # placeholder, re-bound at run time
+                t = engine.nhwc_empty(n, sh_, sw_, sc_ * cs, dev)  # placeholder, re-bound at run time
                 outs.append(t)
+                if split:
+                    outs_f32.append(engine.nhwc_empty(n, sh_, sw_, sc_, dev, torch.float32))
             else:
-                t = pool.get((n, sh_, sw_, sc_))
-            boundary.append((t, meta.new()))
+                t = pool.get((n, sh_, sw_, sc_ * cs))
+            boundary.append((t, None if split else meta.new()))
         # training: stage outputs in the internal format (saved for backward, feed the next stage)
         cints = [engine.Act(pool.get((n, sh_, sw_, sc_)), (n, sh_, sw_, sc_), internal, meta.new())
                  for (sh_, sw_, sc_) in geo] if train else None
@@ -342,26 +355,31 @@ class ResNet(nn.Module):
             for i0 in range(0, n, chunk):
                 cn = min(chunk, n - i0)
                 if stages[0] == 0:
-                    staged = pool.get((cn,) + engine.stem_staging_dims(ho, wo) + (4,))
-                    staged_meta = meta.new()
+                    staged = pool.get((cn * cs,) + engine.stem_staging_dims(ho, wo) + (4,))
+                    staged_meta = None if split else meta.new()
                     ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta, scale=tf_scale,
-                                              shift=tf_shift, padded_hw=(h, w)))
+                                              shift=tf_shift, padded_hw=(h, w), split=split))
                     stem_out = new_act((cn, ho, wo, 64), internal)
                     stem_bn = getattr(self, self.norm_name)
-                    stem_w = cache.get(("conv1", "w"),
-                                       lambda out: engine.pack_stem_weight(self.conv1.weight, out=out),
-                                       deps=(self.conv1.weight,))
+                    if split:
+                        stem_w = cache.get(("conv1", "wsplit"),
+                                           lambda out: engine.pack_stem_weight_split(self.conv1.weight, out=out),
+                                           deps=(self.conv1.weight,))
+                    else:
+                        stem_w = cache.get(("conv1", "w"),
+                                           lambda out: engine.pack_stem_weight(self.conv1.weight, out=out),
+                                           deps=(self.conv1.weight,))
                     sc, sh = cache.get(("conv1", "bn"), lambda out: engine.fold_bn(stem_bn, out=out),
                                        deps=_bn_deps(stem_bn))
                     stem_consts = cache.get(("conv1", "consts"),
                                             lambda out: engine.bound_consts(stem_w, sc, sh, out=out),
                                             deps=(self.conv1.weight,) + _bn_deps(stem_bn)) if scaled else None
                     ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh,
-                                              x_meta=staged_meta, consts=stem_consts, scaled_out=scaled))
+                                              x_meta=staged_meta, consts=stem_consts, scaled_out=scaled, split=split))
                     pool.release(staged)
                     # max-pool commutes with the (positive) per-tensor scale: metadata passes through
-                    cur = engine.Act(pool.get((cn, hq, wq, 64)), (cn, hq, wq, 64), internal, stem_out.meta)
-                    ops.append(engine.op_maxpool(stem_out, cur))
+                    cur = engine.Act(pool.get((cn, hq, wq, 64 * cs)), (cn, hq, wq, 64), internal, stem_out.meta)
+                    ops.append(engine.op_maxpool(stem_out, cur, split=split))
                     pool.release(stem_out.buf)
                     cur_pooled = True
                 else:
@@ -419,11 +437,16 @@ class ResNet(nn.Module):
                             pool.release(shortcut.buf)  # (kept in training: BatchNorm affine gradients need it)
                         cur = src
                         cur_pooled = not last  # stage outputs live in boundary tensors, never pooled
+                    if split and li in self.out_indices:
+                        ops.append(engine.op_split_combine(boundary_act(li, 0, n),
+                                                           outs_f32[sorted(self.out_indices).index(li)]))
                     if train and li in self.out_indices:
                         # the returned feature map: plain bf16 copy of the internal stage output
                         t, m = boundary[li]
                         ops.append(engine.op_add_mask(cints[li], engine.Act(t, cints[li].shape, torch.bfloat16, m)))
-        plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers], dev, meta=meta)
+        plan = engine.Plan(ops, [x] + outs + outs_f32, [cache, pool.all_buffers], dev, meta=meta)
+        if split:
+            return plan, [tuple(o.shape) for o in outs], [tuple(o.shape) for o in outs_f32]
         if train:
             # records reference stage outputs through the plan's placeholder tensors: remember which
             return plan, [tuple(o.shape) for o in outs], records, cints, geo
@@ -444,6 +467,19 @@ class ResNet(nn.Module):
         if entry is None:
             entry = self._build_plan(x, cache)
             self._plans[key] = entry
+        if len(entry) == 3:
+            # fp32-I/O mode: split-precision stage outputs (kept on the returned tensors for a following B200
+            # neck) and their fp32 sums
+            plan, split_shapes, f32_shapes = entry
+            souts = [torch.empty(s, dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+                     for s in split_shapes]
+            outs = [torch.empty(s, dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+                    for s in f32_shapes]
+            plan.run([x] + souts + outs)
+            self._last_run = (plan, [x] + souts + outs)
+            for o, so in zip(outs, souts):
+                o._tdet_split = so
+            return outs[0] if len(outs) == 1 else tuple(outs)
         plan, out_shapes = entry
         outs = [torch.empty(s, dtype=torch.bfloat16, device=x.device,
                             memory_format=torch.channels_last) for s in out_shapes]
@@ -745,6 +781,10 @@ def _nhwc_shape(t):
 # bfloat16 = plain bf16 everywhere (TDET_INTERNAL_DTYPE=bf16).
 INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16").lower() in (
     "bf16", "bfloat16") else torch.float16
+
+# fp32 inputs in eval mode run the split-precision path (fp32-I/O tolerance 1e-4, ~3x the MMA work and 2x the
+# bytes); TDET_FP32_IO=bf16 keeps fp32 tensors at the module boundary only (bf16-accurate, fast).
+FP32_IO_SPLIT = os.environ.get("TDET_FP32_IO", "split").lower() == "split"
 
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"

@@ -105,12 +105,23 @@ class FPN(nn.Module):
     def _conv_groups(self):
         return (("lat", self.lateral_convs), ("out", self.fpn_convs))
 
-    def _build_plan(self, feats, operands):
+    def _build_plan(self, feats, operands, split=False):
+        """split: fp32-I/O mode -- `feats` are split-precision tensors (bf16 hi|lo pairs, 2x channels), every conv
+        runs the 3-pass hi/lo GEMM and the returned tensors are the fp32 sums of split outputs."""
         dev = feats[0].device
         n = feats[0].shape[0]
+        cs = 2 if split else 1
         used = feats[self.start_level:self.backbone_end_level]
         nl = len(used)
-        shapes = [(t.shape[0], t.shape[2], t.shape[3], t.shape[1]) for t in used]  # n,h,w,c
+        shapes = [(t.shape[0], t.shape[2], t.shape[3], t.shape[1] // cs) for t in used]  # n,h,w,c (logical)
+
+        def wkey(key):
+            if not split:
+                return operands.value(key + ".w")
+            kind, j = ("lat", int(key[3:])) if key.startswith("lat") else ("out", int(key[3:]))
+            conv = (self.lateral_convs if kind == "lat" else self.fpn_convs)[j].conv
+            return operands.get(key + ".wsplit", lambda out: engine.pack_conv_weight_split(conv.weight, out=out),
+                                deps=(conv.weight,))
         for j in range(nl - 1, 0, -1):
             for dim, a, b in ((2, shapes[j - 1][1], 2 * shapes[j][1]), (3, shapes[j - 1][2], 2 * shapes[j][2])):
                 if a != b:
@@ -120,52 +131,67 @@ class FPN(nn.Module):
                         "non-singleton dimension %d" % (a, b, dim))
         co = self.out_channels
         ops = []
-        srcs = [engine.act_of(t) for t in used]
+        srcs = [engine.Act(t, shapes[j], torch.bfloat16) for j, t in enumerate(used)]
         lats = [None] * nl
         for j in range(nl - 1, -1, -1):
             nb, h, w, c = shapes[j]
-            lats[j] = engine.Act(torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev),
+            lats[j] = engine.Act(torch.empty(nb * h * w * co * cs, dtype=torch.bfloat16, device=dev),
                                  (nb, h, w, co), torch.bfloat16)
-            ops.append(engine.op_conv(srcs[j], operands.value("lat%d.w" % j), lats[j], 1, 1, 1, 0, 1,
+            ops.append(engine.op_conv(srcs[j], wkey("lat%d" % j), lats[j], 1, 1, 1, 0, 1,
                                       **_epi(operands, "lat%d" % j),
-                                      coarse=lats[j + 1] if j < nl - 1 else None))
-        outs, keep = self._emit_outputs(ops, operands, lats, shapes, dev)
+                                      coarse=lats[j + 1] if j < nl - 1 else None, split=split))
+        if split:
+            outs, keep = FPN._emit_outputs(self, ops, operands, lats, shapes, dev, wkey=wkey, split=True)
+        else:
+            outs, keep = self._emit_outputs(ops, operands, lats, shapes, dev)
         if self.num_outs > nl:
             if not self.add_extra_convs:
                 for _ in range(self.num_outs - nl):
                     nb, h, w, _ = outs[-1].shape
-                    o = engine.act_of(engine.nhwc_empty(nb, (h - 1) // 2 + 1, (w - 1) // 2 + 1, co, dev))
-                    ops.append(engine.op_subsample(outs[-1], o))
+                    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                    o = engine.Act(engine.nhwc_empty(nb, oh, ow, co * cs, dev), (nb, oh, ow, co), torch.bfloat16)
+                    ops.append(engine.op_subsample(outs[-1], o, split=split))
                     outs.append(o)
             else:
-                src = engine.act_of(feats[self.backbone_end_level - 1])
+                top = feats[self.backbone_end_level - 1]
+                src = engine.Act(top, (top.shape[0], top.shape[2], top.shape[3], top.shape[1] // cs), torch.bfloat16)
                 for j in range(nl, self.num_outs):
                     nb, h, w, c = src.shape
                     oh, ow = engine.conv_out(h, 3, 2, 1), engine.conv_out(w, 3, 2, 1)
-                    o = engine.act_of(engine.nhwc_empty(nb, oh, ow, co, dev))
+                    o = engine.Act(engine.nhwc_empty(nb, oh, ow, co * cs, dev), (nb, oh, ow, co), torch.bfloat16)
                     # the reference applies ReLU *in place* to P_j before the next extra conv
                     # (fpn.py:123-124), so every extra level that feeds another one is returned
                     # post-ReLU: fold that ReLU into the producing conv's epilogue.
-                    ops.append(engine.op_conv(src, operands.value("out%d.w" % j), o, 3, 3, 2, 1, 1,
+                    ops.append(engine.op_conv(src, wkey("out%d" % j), o, 3, 3, 2, 1, 1,
                                               **_epi(operands, "out%d" % j),
-                                              relu=(j < self.num_outs - 1)))
+                                              relu=(j < self.num_outs - 1), split=split))
                     outs.append(o)
                     src = o
-        ext = list(feats) + [o.buf for o in outs]
+        f32 = []
+        if split:
+            for o in outs:
+                nb, h, w, c = o.shape
+                t = engine.nhwc_empty(nb, h, w, c, dev, torch.float32)
+                ops.append(engine.op_split_combine(o, t))
+                f32.append(t)
+        ext = list(feats) + [o.buf for o in outs] + f32
         plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats], keep], dev)
         plan.lats = lats  # merged laterals: the saved activations of the training path
+        if split:
+            return plan, [tuple(o.buf.shape) for o in outs], [tuple(t.shape) for t in f32]
         return plan, [tuple(o.buf.shape) for o in outs]
 
-    def _emit_outputs(self, ops, operands, lats, shapes, dev):
+    def _emit_outputs(self, ops, operands, lats, shapes, dev, wkey=None, split=False):
         """P_j = conv3x3(merged lateral j) + bias (fpn.py:106-108).  Returns (output Acts, buffers to keep
         alive); subclasses extend the pyramid here."""
         co = self.out_channels
+        cs = 2 if split else 1
         outs = []
         for j in range(len(lats)):
             nb, h, w, _ = shapes[j]
-            o = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
-            ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), o, 3, 3, 1, 1, 1,
-                                      **_epi(operands, "out%d" % j)))
+            o = engine.Act(engine.nhwc_empty(nb, h, w, co * cs, dev), (nb, h, w, co), torch.bfloat16)
+            wgt = wkey("out%d" % j) if wkey is not None else operands.value("out%d.w" % j)
+            ops.append(engine.op_conv(lats[j], wgt, o, 3, 3, 1, 1, 1, **_epi(operands, "out%d" % j), split=split))
             outs.append(o)
         return outs, []
 
@@ -194,6 +220,8 @@ class FPN(nn.Module):
 
     def _forward_infer(self, inputs):
         want_fp32 = all(t.dtype == torch.float32 for t in inputs)
+        if type(self) is FPN and all(getattr(t, "_tdet_split", None) is not None for t in inputs):
+            return self._forward_split([t._tdet_split for t in inputs])
         feats = [self._as_bf16_nhwc(t) for t in inputs]
         for t, c in zip(feats, self.in_channels):
             if t.dim() != 4 or t.shape[1] != c:
@@ -213,6 +241,29 @@ class FPN(nn.Module):
         self._last_feats = feats
         if want_fp32:
             outs = [o.float() for o in outs]
+        return tuple(outs)
+
+    def _forward_split(self, feats):
+        """fp32-I/O mode: the backbone handed over split-precision stage outputs (bf16 hi|lo pairs)."""
+        for t, c in zip(feats, self.in_channels):
+            if t.dim() != 4 or t.shape[1] != 2 * c:
+                raise ValueError("FPN split-precision input with %s channels, expected 2*%d" % (tuple(t.shape), c))
+        dev = feats[0].device
+        operands = self._get_operands(dev)
+        key = ("split",) + tuple(tuple(t.shape) for t in feats) + (dev,)
+        entry = self._plans.get(key)
+        if entry is None:
+            entry = self._build_plan(feats, operands, split=True)
+            self._plans[key] = entry
+        plan, split_shapes, f32_shapes = entry
+        souts = [torch.empty(s, dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+                 for s in split_shapes]
+        outs = [torch.empty(s, dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+                for s in f32_shapes]
+        plan.run(list(feats) + souts + outs)
+        self._last_run = (plan, list(feats) + souts + outs)
+        for o, so in zip(outs, souts):
+            o._tdet_split = so
         return tuple(outs)
 
     # ------------------------------------------------------------------ training path (config 4)
