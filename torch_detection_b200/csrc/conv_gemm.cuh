@@ -172,8 +172,16 @@ template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
-  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                 : (2 * BN <= 256) ? 256 : 512;
+  // Split precision keeps TWO accumulators per tile: hi*hi in one, the small cross terms lo*hi + hi*lo in the
+  // other, summed in fp32 by the epilogue.  tcgen05's fp32 accumulation is not exact -- measured ~0.17 ulp of
+  // systematic loss per MMA step, which over the 3x longer K loop and ~50 layers was the dominant error of
+  // the fp32-I/O mode (1.0e-4 at P2 vs 1.7e-5 for the scheme with exact accumulation); keeping the main chain
+  // a third as long and the cross terms (2^-8 of the magnitude) apart cuts it ~3x.
+  constexpr int kAccStride = SPLIT ? 2 * BN : BN;            // TMEM columns per accumulator buffer
+  constexpr int kAccBufs = (SPLIT && BN == 256) ? 1 : 2;      // 2 x 256 columns leave no room to double-buffer
+  constexpr uint32_t kAccCols = kAccStride * kAccBufs;
+  constexpr uint32_t kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128
+                                 : (kAccCols <= 256) ? 256 : 512;
   constexpr int kSlabsPerTile = BN / 64;
   constexpr int kRS = RES_SLABS > 0 ? RES_SLABS : 1;
 
@@ -357,7 +365,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
         const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(afull_bar(as), aphase);
@@ -396,10 +404,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * kAccStride);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
+        // split precision: pass v of this k-block (0 hi*hi -> main accumulator, 1/2 cross terms -> the second)
+        const int v = (nv == 3) ? (kb / kcn) % 3 : 0;
+        const uint32_t d_tmem = d_main + (v != 0 ? static_cast<uint32_t>(BN) : 0u);
+        const int kb_first = (v != 0) ? kcn : 0;  // first k-block that writes this accumulator
         if (lane == 0) {
           if (BRES_KB > 0 && p.a_mode == A_STEM2) {
             // Row i of the A operand is the 8-pixel x 4-channel window starting at staged pixel 2*i:
@@ -420,7 +432,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
-              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kb - kb_first) | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(stage));
@@ -429,7 +441,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      acc ^= 1;
+      if (kAccBufs == 2) acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp == 2) {
@@ -539,8 +551,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int seq = 0; // CTA-local tile counter: tile seq accumulates in TMEM buffer seq & 1
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
       if (kByTile && (seq & 1) != group) continue;
-      const int acc = seq & 1;
-      const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
+      const int acc = kAccBufs == 2 ? (seq & 1) : 0;
+      const uint32_t acc_phase = static_cast<uint32_t>(kAccBufs == 2 ? (seq >> 1) : seq) & 1u;
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BN;
@@ -598,7 +610,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                              static_cast<uint32_t>(acc * BN);
+                              static_cast<uint32_t>(acc * kAccStride);
 #pragma unroll 1
       for (int slab = kByTile ? 0 : group; slab < kSlabsPerTile; slab += kByTile ? 1 : 2) {
         // residual slabs are produced in tile order into one ring shared by both groups; consecutive
@@ -669,6 +681,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           tmem_ld_wait();
           float x[32];
+          if (SPLIT && split) {
+            // main (hi*hi) + cross (lo*hi + hi*lo) accumulators, summed in fp32
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+            tmem_ld_32x32b_x32(t_addr + BN + slab * 64 + half * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(x[i] + __uint_as_float(v[i]));
+          }
           const int cb = (kByTile ? slab : (slab >> 1)) * 64 + half * 32;  // group-local column
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
