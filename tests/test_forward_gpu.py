@@ -235,7 +235,10 @@ def test_input_transform_normalise_and_pad_in_the_loader(cuda_device, dtype):
     norm = (raw.permute(0, 3, 1, 2).float() - torch.tensor(means).view(1, 3, 1, 1)) / torch.tensor(stds).view(1, 3, 1, 1)
     padded = torch.zeros(2, 3, 160, 224)
     padded[:, :, :150, :200] = norm
-    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, padded.to(torch.bfloat16).float(), 50)
+    # uint8 in -> bf16 path (the staged image is bf16); fp32 in -> the fp32-I/O (split-precision) path
+    ref_in = padded if dtype == torch.float32 else padded.to(torch.bfloat16).float()
+    gate = FP32_GATE if dtype == torch.float32 else BF16_GATE
+    want_f, want_p = orc.resnet_fpn_forward(bsd, nsd, ref_in, 50)
     bb.set_input_transform(means, stds, size_divisor=32)
     bb, neck = bb.to(dev).eval(), neck.to(dev).eval()
     with torch.no_grad():
@@ -245,12 +248,12 @@ def test_input_transform_normalise_and_pad_in_the_loader(cuda_device, dtype):
     assert tuple(feats[0].shape) == (2, 256, 40, 56)
     feats = [f.float() for f in feats]
     outs = [o.float() for o in outs]
-    _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
-    _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"])
+    _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"], gate)
+    _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"], gate)
     bb.set_input_transform(None)
     with torch.no_grad():
         plain = bb(padded.to(torch.bfloat16).to(dev))
-    assert orc.rel_l2(plain[0].float(), feats[0]) <= 2e-3   # same staged image either way
+    assert orc.rel_l2(plain[0].float(), feats[0]) <= 5e-3   # the same image without the fused transform
 
 
 @pytest.mark.parametrize("neck_type", ["FPN", "PAFPN"])
