@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--launch-table", default="", help="write the per-launch timing table (JSON) here")
+    ap.add_argument("--io-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="fp32 = the fp32-I/O mode (split-precision kernels, <= 1e-4 vs the fp32 reference); secondary line")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="train = BASELINE.json config 4: forward+backward, frozen BN, frozen stem+stage 1, "
                          "batch 8 per GPU, bucketed NCCL gradient all-reduce overlapped with backward")
@@ -352,7 +354,8 @@ def main():
     neck = neck.to(dev).eval()
 
     B, H, W = args.batch, args.height, args.width
-    x_host = make_batch(B, H, W, 100 + rank, torch.bfloat16).pin_memory()
+    io_dtype = torch.float32 if args.io_dtype == "fp32" else torch.bfloat16
+    x_host = make_batch(B, H, W, 100 + rank, io_dtype).pin_memory()
     x_dev = x_host.to(dev)
     Hp, Wp = x_host.shape[2], x_host.shape[3]
 
@@ -391,7 +394,7 @@ def main():
     stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    p6_host = torch.empty((B, 256, outs[-1].shape[2], outs[-1].shape[3]), dtype=torch.bfloat16).contiguous(
+    p6_host = torch.empty((B, 256, outs[-1].shape[2], outs[-1].shape[3]), dtype=io_dtype).contiguous(
         memory_format=torch.channels_last).pin_memory()
     main_stream = torch.cuda.current_stream(dev)
 
@@ -499,10 +502,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.io_dtype == "bf16" else "bf16 hi+lo pairs (split precision, fp32 I/O)",
             "data": "synthetic",
             "config": {"workload": "ResNet-%d + FPN forward, batch %d per GPU, %dx%d zero-padded to %dx%d, "
-                                   "bf16 NCHW in, P2..P6 bf16 out" % (args.depth, B, H, W, Hp, Wp),
+                                   "%s NCHW in, P2..P6 %s out" % (args.depth, B, H, W, Hp, Wp, args.io_dtype,
+                                                                   args.io_dtype),
                        "images_per_gpu": B, "global_batch": B * world, "gflop_per_image": flops_img / 1e9,
                        "parallelism": "batch sharded, no data-path collective",
                        "l2": "per-step working set (~1.4 GB/img of activations) >> 126 MB L2, no explicit flush"},
