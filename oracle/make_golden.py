@@ -34,6 +34,40 @@ def state_hash(sd):
     return h.hexdigest()
 
 
+def grad_signature(g):
+    """Compact fingerprint of a gradient tensor: L2 norm, sum, a fixed pseudo-random projection, first 8 values."""
+    g = g.detach().double().flatten()
+    idx = torch.arange(g.numel(), dtype=torch.float64)
+    proj = torch.cos(0.37 * idx + 0.11)
+    return np.array([float(g.norm()), float(g.sum()), float((g * proj).sum())] + [float(v) for v in g[:8]])
+
+
+def make_gradient_golden(out_dir):
+    """tests/golden/r18_fpn_64x64_grads.npz: the REFERENCE's own autograd (training config: frozen BN statistics,
+    stage 1 frozen) on the r18 fixture's input with seeded upstream gradients; one fingerprint per parameter."""
+    depth, seed = 18, 0
+    bb, neck = reference_shim.build_pair(depth, seed=seed)
+    sd = bb.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(1000 + seed))
+    bb.load_state_dict(sd)
+    g = torch.Generator().manual_seed(77 + seed)
+    x = torch.randn(1, 3, 64, 64, generator=g)
+    outs = neck(bb(x))
+    gg = torch.Generator().manual_seed(99)
+    grads = [torch.randn(o.shape, generator=gg) for o in outs]
+    torch.autograd.backward(list(outs), grads)
+    arrays = {}
+    for prefix, mod in (("bb.", bb), ("neck.", neck)):
+        for k, p in mod.named_parameters():
+            if p.grad is not None and not (prefix == "bb." and (k.startswith("layer1") or not k.startswith("layer"))):
+                arrays[prefix + k] = grad_signature(p.grad)
+    meta = dict(depth=depth, seed=seed, input_seed=77 + seed, grad_seed=99,
+                bb_hash=state_hash(bb.state_dict()), neck_hash=state_hash(neck.state_dict()))
+    np.savez(os.path.join(out_dir, "r18_fpn_64x64_grads.npz"), **arrays,
+             **{"meta_" + k: np.array(v) for k, v in meta.items()})
+    print("r18_fpn_64x64_grads", len(arrays), "parameter gradients")
+
+
 def main():
     assert reference_shim.available(), "needs /root/reference"
     torch.set_num_threads(1)  # fixed reduction order
@@ -61,6 +95,7 @@ def main():
         np.savez(os.path.join(out_dir, name + ".npz"),
                  **arrays, **{"meta_" + k: np.array(v) for k, v in meta.items()})
         print(name, {k: v.shape for k, v in arrays.items()})
+    make_gradient_golden(out_dir)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,7 @@
 """Oracle vs the committed golden vectors (produced by the reference itself, oracle/make_golden.py).
 CPU-only; runs on the GPU box too, where the reference tree is absent."""
+import os
+
 import pytest
 import torch
 
@@ -40,3 +42,29 @@ def test_bf16_emulation_is_within_gate():
     _, emu = orc.resnet_fpn_forward_bf16_emulated(bsd, nsd, arrays["x"], 50)
     errs = [orc.rel_l2(a, b) for a, b in zip(emu, outs)]
     assert max(errs) < 1.5e-2, errs
+
+
+def test_gradient_oracle_reproduces_reference_gradient_fixture():
+    """tests/golden/r18_fpn_64x64_grads.npz holds fingerprints of the REFERENCE's own autograd gradients
+    (oracle/make_golden.py, dev container).  The gradient oracle must reproduce them anywhere -- this is what
+    pins oracle/grad_oracle.py on the GPU box, where the reference tree does not exist."""
+    import numpy as np
+    from oracle import grad_oracle, make_golden
+    z = np.load(os.path.join(helpers.GOLDEN_DIR, "r18_fpn_64x64_grads.npz"))
+    seed = int(z["meta_seed"])
+    bb, neck = helpers.build_product_pair(18, seed=seed, bnstats=True)
+    assert helpers.state_hash(bb.state_dict()) == str(z["meta_bb_hash"])
+    assert helpers.state_hash(neck.state_dict()) == str(z["meta_neck_hash"])
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    x = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(int(z["meta_input_seed"])))
+    with torch.no_grad():
+        _, outs = orc.resnet_fpn_forward(bsd, nsd, x, 18)
+    gg = torch.Generator().manual_seed(int(z["meta_grad_seed"]))
+    grads = [torch.randn(o.shape, generator=gg) for o in outs]
+    gb, gn, _, _ = grad_oracle.plain_grads(bsd, nsd, x, 18, grads, train_from_stage=1, bn_affine=True)
+    keys = [k for k in z.files if not k.startswith("meta_")]
+    assert len(keys) >= 40
+    for k in keys:
+        got = (gb if k.startswith("bb.") else gn)[k.split(".", 1)[1]]
+        sig = make_golden.grad_signature(got)
+        assert np.allclose(sig, z[k], rtol=2e-4, atol=1e-6 * abs(z[k][0])), (k, sig[:3], z[k][:3])
