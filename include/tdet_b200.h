@@ -84,7 +84,9 @@ typedef enum tdet_op_kind {
   TDET_OP_ZERO = 11,     /* cudaMemsetAsync(y, 0, x_stride[0] bytes): gradient accumulators */
   TDET_OP_AMAX = 12,     /* y_meta->amax_bits = max |x| (true values): bound input for tensors produced elsewhere */
   TDET_OP_BN_AFFINE_GRAD = 13, /* gamma / beta gradients of a frozen-statistics BatchNorm from stored tensors */
-  TDET_OP_SPLIT_COMBINE = 14 /* y (fp32 [n][h][w][cin]) = hi + lo of a split-precision tensor x ([n][h][w][2*cin] bf16) */
+  TDET_OP_SPLIT_COMBINE = 14, /* y (fp32 [n][h][w][cin]) = hi + lo of a split-precision tensor x ([n][h][w][2*cin] bf16) */
+  TDET_OP_MAXPOOL_BWD = 15,  /* backward of MaxPool2d(3, 2, 1) fused with the ReLU backward of its input (stem) */
+  TDET_OP_STEM_WGRAD = 16    /* weight gradient of the 7x7/2 stem conv from the staged image */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -164,6 +166,13 @@ typedef struct tdet_tensor_meta {
  *                   shift = beta (fp32 [cin]); dw: fp32 [2*cin] accumulator {dgamma[cin], dbeta[cin]}
  *                   (caller zeroes it).  norm_layer / nn.BatchNorm2d in eval mode with trainable affine
  *                   parameters (bn_frozen=False, resnet.py:272-281).
+ * TDET_OP_MAXPOOL_BWD  x: the max-pool's input S [n][h][w][cin] (post-ReLU stem output, x_dtype); gy: gradient
+ *                   w.r.t. the pooled tensor [n][ho][wo][cin] (gy_dtype, gy_meta); y: bf16 [n][h][w][cin] =
+ *                   (S > 0) * scatter of gy to each window's first maximum (aten max_pool2d tie rule)
+ *                   (resnet.py:257-258 backward).
+ * TDET_OP_STEM_WGRAD  x: the TDET_OP_PREP staging of the batch (bf16 NHWC4); gy: bf16 [n][ho][wo][64] gradient
+ *                   w.r.t. bn1's output; scale: folded bn1 scale (or NULL); dw: fp32 [64][3][7][7], accumulated.
+ *                   h, w = image size as for TDET_OP_STEM.
  * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;
  *                   its exponent field is left untouched)
  * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled

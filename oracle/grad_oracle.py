@@ -42,7 +42,9 @@ def trainable_backbone_key(train_from_stage, bn_affine=False):
     """Conv weights of layer{train_from_stage+1..4} (0-based stage index); with bn_affine also the
     weight / bias of their (eval-mode) BatchNorms (the reference's bn_frozen=False)."""
     def wanted(k):
-        if not k.startswith("layer") or int(k[5]) - 1 < train_from_stage:
+        if train_from_stage < 0 and (k == "conv1.weight" or (bn_affine and k in ("bn1.weight", "bn1.bias"))):
+            return True   # the stem trains too (the reference's frozen_stages = -1)
+        if not k.startswith("layer") or int(k[5]) - 1 < max(train_from_stage, 0):
             return False
         is_bn = ".bn" in k or ".downsample.1." in k
         if is_bn:
@@ -124,7 +126,7 @@ class _ConvBNKernelModel(torch.autograd.Function):
 
 def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs, train_from_stage=1,
                          out_channels=256, num_outs=5, kernel_rounding=False, bb_weight_dtype=torch.bfloat16,
-                         bn_affine=False):
+                         bn_affine=False, x=None):
     """fp32 autograd over the reference's graph with every stored activation (and hence every ReLU
     mask and every conv / wgrad input) forced to the value the CUDA training forward stored:
     `saved_bb` = ResNet.saved_activations(), `saved_neck` = FPN.saved_activations().  Conv weights are
@@ -144,13 +146,14 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
     bb = _leafify(bb_sd, trainable_backbone_key(train_from_stage, bn_affine))
     neck = _leafify(neck_sd, lambda k: True)
 
-    def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None, round_grad=False):
+    def cbn(inp, wkey, bnp, stored, stride=1, pad=0, relu=False, res=None, round_grad=False, wdtype=None):
+        wdtype = wdtype or bb_weight_dtype
         scale = bb[bnp + ".weight"] / torch.sqrt(bb[bnp + ".running_var"] + orc.BN_EPS)
         shift = bb[bnp + ".bias"] - bb[bnp + ".running_mean"] * scale
         if kr:
-            y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad, bb_weight_dtype)
+            y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad, wdtype)
         else:
-            y = F.conv2d(inp, _ste(bb[wkey], bb_weight_dtype), None, stride, pad)
+            y = F.conv2d(inp, _ste(bb[wkey], wdtype), None, stride, pad)
             y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res
@@ -158,6 +161,12 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
 
     feats = []
     h = None
+    if train_from_stage < 0:
+        # trainable stem (frozen_stages = -1): bf16 image and bf16 stem weights, stem output forced to the stored
+        # tensor; the max-pool then sees exactly the values the CUDA max-pool saw (same maxima, same tie rule)
+        s_out = cbn(_r(x.float()), "conv1.weight", "bn1", saved_bb["stem.out"], 2, 3, relu=True, round_grad=kr,
+                    wdtype=torch.bfloat16)
+        h = F.max_pool2d(s_out, 3, 2, 1)
     for li, nblocks in enumerate(counts):
         if li < train_from_stage:
             feats.append(None)

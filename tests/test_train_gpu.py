@@ -59,6 +59,8 @@ def _cos(a, b):
     (101, (1, 3, 64, 96), False, 2, True),
     (50, (2, 3, 128, 160), True, 1, False),   # the reference's default bn_frozen=False: BN affine gradients
     (18, (2, 3, 96, 128), True, 0, False),
+    (50, (2, 3, 96, 128), True, -1, False),   # the reference's constructor defaults: everything trains, stem included
+    (18, (1, 3, 128, 160), True, -1, True),
 ])
 def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen, bn_frozen):
     dev = cuda_device
@@ -79,9 +81,10 @@ def test_gradients_match_oracle(cuda_device, depth, shape, bnstats, frozen, bn_f
     wdt = _backbone_weight_dtype()
     tb, tn, tf_feats, tf_outs = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
                                                                  train_from_stage=frozen, kernel_rounding=True,
-                                                                 bb_weight_dtype=wdt)
+                                                                 bb_weight_dtype=wdt, x=x.float())
     xb, xn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, saved_b, saved_n, depth, grads,
-                                                    train_from_stage=frozen, bb_weight_dtype=wdt, bn_affine=bn_affine)
+                                                    train_from_stage=frozen, bb_weight_dtype=wdt, bn_affine=bn_affine,
+                                                    x=x.float())
     pb, pn, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), depth, grads, train_from_stage=frozen,
                                            bn_affine=bn_affine)
     assert set(got_b) == set(xb), (sorted(set(got_b) ^ set(xb))[:8])
@@ -165,9 +168,8 @@ def test_eval_mode_unchanged_and_unsupported_training_configs(cuda_device):
     x = torch.randn(1, 3, 64, 64).to(dev)
     bb.eval()
     assert not bb(x)[0].requires_grad          # eval mode never builds a graph
-    bb.train()                                   # frozen_stages=-1: the stem would need gradients
-    with pytest.raises(NotImplementedError):
-        bb(x)
+    bb.train()                                   # frozen_stages=-1 (the reference default): the stem trains too
+    assert bb(x)[0].requires_grad
     bb2, _ = helpers.build_product_pair(50, seed=0, frozen_stages=1, bn_eval=False)
     bb2 = bb2.to(dev).train()
     with pytest.raises(NotImplementedError):   # batch-statistics BatchNorm

@@ -25,6 +25,7 @@ OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO
 OP_AMAX = 12
 OP_BN_AFFINE_GRAD = 13
 OP_SPLIT_COMBINE = 14
+OP_MAXPOOL_BWD, OP_STEM_WGRAD = 15, 16
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1

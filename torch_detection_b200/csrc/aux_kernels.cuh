@@ -473,6 +473,157 @@ bn_affine_grad_kernel(const BnAffineParams p) {
   }
 }
 
+// Backward of the stem's max-pool (3x3 / stride 2 / pad 1) fused with the ReLU backward of the stem output:
+//   dS[n][ih][iw][c] = (S > 0) * sum over the (up to four) pooling windows whose FIRST maximum (row-major
+//   scan, the tie rule of aten::max_pool2d_with_indices) is (ih, iw) of g[window]
+// S: stem output [n][h][w][C] (16-bit, any common exponent: only compared), g: gradient w.r.t. the pooled tensor
+// [n][ho][wo][C] (16-bit, exponent from g_meta), dS: bf16 true values.  One thread per (input pixel, 8 channels).
+struct MaxpoolBwdParams {
+  const uint4* s;
+  const uint4* g;
+  uint4* ds;
+  int n, h, w, c8, ho, wo;
+  int s_fp16, g_fp16;
+  const TensorMeta* g_meta;
+};
+
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_bwd_kernel(const MaxpoolBwdParams p) {
+  const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c8;
+  const float mg = ldexpf(1.0f, p.g_meta ? p.g_meta->e : 0);
+  const bool sf = p.s_fp16 != 0, gf = p.g_fp16 != 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    long long t = i / p.c8;
+    const int iw = static_cast<int>(t % p.w);
+    t /= p.w;
+    const int ih = static_cast<int>(t % p.h);
+    const int img = static_cast<int>(t / p.h);
+    const uint4 self = __ldg(p.s + i);
+    const uint32_t sw[4] = {self.x, self.y, self.z, self.w};
+    float me[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unpack16x2(sw[j], sf, me[2 * j], me[2 * j + 1]);
+      acc[2 * j] = acc[2 * j + 1] = 0.0f;
+    }
+    // windows (oh, ow) that contain (ih, iw): 2*oh - 1 <= ih <= 2*oh + 1
+    for (int oh = (ih >> 1); oh <= ((ih + 1) >> 1); ++oh) {
+      if (oh < 0 || oh >= p.ho) continue;
+      for (int ow = (iw >> 1); ow <= ((iw + 1) >> 1); ++ow) {
+        if (ow < 0 || ow >= p.wo) continue;
+        // is (ih, iw) the first maximum of this window, per channel?
+        bool win[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) win[j] = true;
+        for (int dy = 0; dy < 3; ++dy) {
+          const int yh = 2 * oh - 1 + dy;
+          if (yh < 0 || yh >= p.h) continue;
+          for (int dx = 0; dx < 3; ++dx) {
+            const int xw = 2 * ow - 1 + dx;
+            if (xw < 0 || xw >= p.w || (yh == ih && xw == iw)) continue;
+            const bool before = (yh < ih) || (yh == ih && xw < iw);  // scanned earlier: wins ties
+            const uint4 o = __ldg(p.s + ((static_cast<long long>(img) * p.h + yh) * p.w + xw) * p.c8 + cg);
+            const uint32_t ow4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a, b;
+              unpack16x2(ow4[j], sf, a, b);
+              if (before ? (a >= me[2 * j]) : (a > me[2 * j])) win[2 * j] = false;
+              if (before ? (b >= me[2 * j + 1]) : (b > me[2 * j + 1])) win[2 * j + 1] = false;
+            }
+          }
+        }
+        const uint4 gv = __ldg(p.g + ((static_cast<long long>(img) * p.ho + oh) * p.wo + ow) * p.c8 + cg);
+        const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a, b;
+          unpack16x2(gw[j], gf, a, b);
+          if (win[2 * j]) acc[2 * j] += a;
+          if (win[2 * j + 1]) acc[2 * j + 1] += b;
+        }
+      }
+    }
+    uint32_t o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o4[j] = pack_bf16x2(me[2 * j] > 0.0f ? acc[2 * j] * mg : 0.0f, me[2 * j + 1] > 0.0f ? acc[2 * j + 1] * mg : 0.0f);
+    p.ds[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
+
+// Weight gradient of the 7x7 / stride 2 / pad 3 stem conv (3 -> 64 channels; CUDA cores: 40 GFLOP per batch of 8):
+//   dW[co][c][r][s] += scale[co] * sum_{n,p,q} g[n][p][q][co] * img[n][2p-3+r][2q-3+s][c]
+// img = the padded NHWC4 bf16 staging TDET_OP_PREP wrote (pixel (ih, iw) at (ih+3, iw+3)), g = bf16 [n][ho][wo][64].
+// A block walks tiles of 4 x 64 output pixels, staging the g tile and the (13 x 133)-pixel image patch in shared
+// memory as fp32; thread (co = t & 63, grp = t >> 6) accumulates the 37 filter taps k = grp + 4j of channel co.
+constexpr int kSwTileH = 4, kSwTileW = 64;
+constexpr int kSwPatchH = 2 * kSwTileH + 5, kSwPatchW = 2 * kSwTileW + 5;
+constexpr int kSwSmemBytes = (kSwTileH * kSwTileW * 64 + kSwPatchH * kSwPatchW * 4) * 4;
+
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const uint2* __restrict__ img, const __nv_bfloat16* __restrict__ g, const float* __restrict__ scale,
+                  float* __restrict__ dw, int n, int ho, int wo, int hp, int wp) {
+  extern __shared__ float sw_smem[];
+  float* sg = sw_smem;                               // [256 pixels][64 channels]
+  float* si = sw_smem + kSwTileH * kSwTileW * 64;    // [13][133][4]
+  const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  int koff[37];
+  float acc[37];
+#pragma unroll
+  for (int j = 0; j < 37; ++j) {
+    const int k = grp + 4 * j;  // index into [c][r][s] (147 valid)
+    const int c = k / 49, r = (k % 49) / 7, s = k % 7;
+    koff[j] = k < 147 ? (r * kSwPatchW + s) * 4 + c : 0;
+    acc[j] = 0.0f;
+  }
+  const int tiles_w = (wo + kSwTileW - 1) / kSwTileW, tiles_h = (ho + kSwTileH - 1) / kSwTileH;
+  const long long tiles = static_cast<long long>(n) * tiles_h * tiles_w;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    long long t = tile / tiles_w;
+    const int th = static_cast<int>(t % tiles_h);
+    const int im = static_cast<int>(t / tiles_h);
+    const int p0 = th * kSwTileH, q0 = tw * kSwTileW;
+    __syncthreads();
+    // g tile (zero beyond the image)
+    for (int i = threadIdx.x; i < kSwTileH * kSwTileW * 64; i += 256) {
+      const int c = i & 63, pix = i >> 6;
+      const int pl = pix / kSwTileW, ql = pix - pl * kSwTileW;
+      const int pp = p0 + pl, qq = q0 + ql;
+      sg[i] = (pp < ho && qq < wo)
+                  ? __bfloat162float(g[((static_cast<long long>(im) * ho + pp) * wo + qq) * 64 + c]) : 0.0f;
+    }
+    // image patch: staged rows 2*p0 .. 2*p0 + 12, columns 2*q0 .. 2*q0 + 132 (zero beyond the staging)
+    for (int i = threadIdx.x; i < kSwPatchH * kSwPatchW; i += 256) {
+      const int yl = i / kSwPatchW, xl = i - yl * kSwPatchW;
+      const int y = 2 * p0 + yl, x = 2 * q0 + xl;
+      uint2 v = make_uint2(0u, 0u);
+      if (y < hp && x < wp) v = __ldg(img + (static_cast<long long>(im) * hp + y) * wp + x);
+      si[4 * i + 0] = bf16_lo(v.x);
+      si[4 * i + 1] = bf16_hi(v.x);
+      si[4 * i + 2] = bf16_lo(v.y);
+      si[4 * i + 3] = 0.0f;
+    }
+    __syncthreads();
+    for (int pix = 0; pix < kSwTileH * kSwTileW; ++pix) {
+      const int pl = pix / kSwTileW, ql = pix - pl * kSwTileW;
+      const float gv = sg[pix * 64 + co];
+      const float* base = si + (2 * pl * kSwPatchW + 2 * ql) * 4;
+#pragma unroll
+      for (int j = 0; j < 37; ++j) acc[j] = fmaf(gv, base[koff[j]], acc[j]);
+    }
+  }
+  const float sc = scale ? scale[co] : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 37; ++j) {
+    const int k = grp + 4 * j;
+    if (k < 147) atomicAdd(dw + co * 147 + k, acc[j] * sc);
+  }
+}
+
 __device__ __forceinline__ uint32_t add4_bf16x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return pack_bf16x2(bf16_lo(a) + bf16_lo(b) + bf16_lo(c) + bf16_lo(d),
                      bf16_hi(a) + bf16_hi(b) + bf16_hi(c) + bf16_hi(d));

@@ -895,6 +895,19 @@ int build_launch(Launch& l, const DeviceInfo& di) {
         return fail(TDET_ERR_INVALID_ARGUMENT, "amax: bad arguments");
       l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w;
       return TDET_OK;
+    case TDET_OP_MAXPOOL_BWD:
+      if (o.cin % 8 || !o.x || !o.gy || !o.y || o.ho != out_dim(o.h, 3, 2, 1, 1) || o.wo != out_dim(o.w, 3, 2, 1, 1) ||
+          !is16(o.x_dtype) || !is16(o.gy_dtype))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "maxpool_bwd: bad arguments");
+      l.bytes = 2.0 * o.n * o.cin * (2.0 * o.h * o.w + static_cast<double>(o.ho) * o.wo);
+      return TDET_OK;
+    case TDET_OP_STEM_WGRAD:
+      if (!o.x || !o.gy || !o.dw || o.gy_dtype != TDET_BF16 || o.ho != out_dim(o.h, 7, 2, 3, 1) ||
+          o.wo != out_dim(o.w, 7, 2, 3, 1))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "stem_wgrad: bad arguments");
+      l.flops = 2.0 * static_cast<double>(o.n) * o.ho * o.wo * 64.0 * 147.0;
+      l.bytes = 2.0 * o.n * (static_cast<double>(stem_hp(o.ho)) * stem_wp(o.wo) * 4 + static_cast<double>(o.ho) * o.wo * 64);
+      return TDET_OK;
     case TDET_OP_SPLIT_COMBINE:
       if (o.cin % 8 || !o.x || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "split_combine: bad arguments");
       l.bytes = 8.0 * o.n * o.cin * static_cast<double>(o.h) * o.w;
@@ -1018,6 +1031,38 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       ap.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
       ap.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
       add_mask_kernel<<<grid_for(ap.total, di.num_sms), 256, 0, st>>>(ap);
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
+    case TDET_OP_MAXPOOL_BWD: {
+      MaxpoolBwdParams mp{};
+      mp.s = static_cast<const uint4*>(o.x);
+      mp.g = static_cast<const uint4*>(o.gy);
+      mp.ds = static_cast<uint4*>(o.y);
+      mp.n = o.n; mp.h = o.h; mp.w = o.w; mp.c8 = o.cin / 8; mp.ho = o.ho; mp.wo = o.wo;
+      mp.s_fp16 = o.x_dtype == TDET_F16;
+      mp.g_fp16 = o.gy_dtype == TDET_F16;
+      mp.g_meta = reinterpret_cast<const TensorMeta*>(o.gy_meta);
+      const long long total = static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8);
+      maxpool3x3s2_bwd_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(mp);
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
+    case TDET_OP_STEM_WGRAD: {
+      static bool attr_set[64] = {};
+      int dev = 0;
+      TDET_CUDA(cudaGetDevice(&dev));
+      if (!attr_set[dev]) {
+        TDET_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSwSmemBytes));
+        attr_set[dev] = true;
+      }
+      const long long tiles = static_cast<long long>(o.n) * ((o.ho + kSwTileH - 1) / kSwTileH) *
+                              ((o.wo + kSwTileW - 1) / kSwTileW);
+      long long g = 2LL * di.num_sms;
+      if (g > tiles) g = tiles;
+      stem_wgrad_kernel<<<static_cast<unsigned>(g), 256, kSwSmemBytes, st>>>(
+          static_cast<const uint2*>(o.x), static_cast<const __nv_bfloat16*>(o.gy), o.scale, o.dw, o.n, o.ho, o.wo,
+          stem_hp(o.ho), stem_wp(o.wo));
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

@@ -473,6 +473,31 @@ def op_bn_affine_grad(g, a, gamma, beta, dw, b=None):
     return op
 
 
+def op_maxpool_bwd(s, g, ds):
+    """ds (bf16) = (s > 0) * scatter of g to each 3x3/2 window's first maximum of s (max-pool + ReLU backward)."""
+    n, h, w, c = s.shape
+    op = _C.TdetOp()
+    op.kind = _C.OP_MAXPOOL_BWD
+    op.n, op.h, op.w, op.cin = n, h, w, c
+    op.ho, op.wo = g.shape[1], g.shape[2]
+    op.x, op.x_dtype = s.ptr, _TD[s.dtype]
+    op.gy, op.gy_dtype, op.gy_meta = g.ptr, _TD[g.dtype], g.meta
+    op.y, op.y_dtype = ds.ptr, _C.BF16
+    return op
+
+
+def op_stem_wgrad(n, h, w, staged, g, dw, scale=None):
+    """dw (fp32 [64][3][7][7]) += scale * wgrad of the stem conv; staged = TDET_OP_PREP output, g bf16 (n, ho, wo, 64)."""
+    op = _C.TdetOp()
+    op.kind = _C.OP_STEM_WGRAD
+    op.n, op.h, op.w, op.cin, op.cout = n, h, w, 3, 64
+    op.ho, op.wo = g.shape[1], g.shape[2]
+    op.x, op.gy, op.gy_dtype = _ptr(staged), g.ptr, _TD[g.dtype]
+    op.scale = _ptr(scale)
+    op.dw = dw.data_ptr()
+    return op
+
+
 def op_amax(x, meta):
     """meta.amax = max |x| (true values); `meta` = device address of a tdet_tensor_meta."""
     n, h, w, c = x.shape

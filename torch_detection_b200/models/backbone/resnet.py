@@ -282,6 +282,7 @@ class ResNet(nn.Module):
         pool = _BufferPool(dev)
         segs = [(list(range(len(self.res_layers))), n)] if (train or split) else self._segments(n)
         records = []
+        stem_rec = None
         max_chunks = max((n + c - 1) // c for _, c in segs)
         n_meta = 16 + (2 + 4 * sum(len(getattr(self, l)) for l in self.res_layers)) * max_chunks
         meta = engine.MetaArena(n_meta, dev)
@@ -376,11 +377,16 @@ class ResNet(nn.Module):
                                             deps=(self.conv1.weight,) + _bn_deps(stem_bn)) if scaled else None
                     ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh,
                                               x_meta=staged_meta, consts=stem_consts, scaled_out=scaled, split=split))
-                    pool.release(staged)
+                    keep_stem = train and getattr(self, "_train_stem", False)
+                    if not keep_stem:
+                        pool.release(staged)
                     # max-pool commutes with the (positive) per-tensor scale: metadata passes through
                     cur = engine.Act(pool.get((cn, hq, wq, 64 * cs)), (cn, hq, wq, 64), internal, stem_out.meta)
                     ops.append(engine.op_maxpool(stem_out, cur, split=split))
-                    pool.release(stem_out.buf)
+                    if keep_stem:
+                        stem_rec = dict(staged=staged, stem_out=stem_out, h=h, w=w)  # saved for the stem's backward
+                    else:
+                        pool.release(stem_out.buf)
                     cur_pooled = True
                 else:
                     cur = boundary_act(stages[0] - 1, i0, cn)
@@ -448,7 +454,7 @@ class ResNet(nn.Module):
         if split:
             return plan, [tuple(o.shape) for o in outs], [tuple(o.shape) for o in outs_f32]
         if train:
-            # records reference stage outputs through the plan's placeholder tensors: remember which
+            plan.stem_rec = stem_rec
             return plan, [tuple(o.shape) for o in outs], records, cints, geo
         return plan, [tuple(o.shape) for o in outs]
 
@@ -503,10 +509,6 @@ class ResNet(nn.Module):
         stem (frozen_stages >= 0), a frozen prefix of stages and a fully trainable suffix; per stage the BN
         affine parameters are either all trainable or all frozen."""
         stem_norm = getattr(self, self.norm_name)
-        if self.conv1.weight.requires_grad:
-            raise NotImplementedError(
-                "training the stem (conv1) is not on the B200 path: use frozen_stages >= 0 and call "
-                ".train() (reference configs freeze the stem and stage 1)")
         first = None
         params = []
         bn_train = []
@@ -534,6 +536,18 @@ class ResNet(nn.Module):
                 if first is not None:
                     raise NotImplementedError("frozen stage %s after a trainable one" % lname)
                 bn_train.append(False)
+        # the stem (frozen_stages = -1): 7x7 wgrad + max-pool/ReLU backward, only below a trainable stage 1
+        stem_bn_flags = [stem_norm.weight.requires_grad, stem_norm.bias.requires_grad]
+        self._train_stem = bool(self.conv1.weight.requires_grad)
+        self._train_stem_bn = all(stem_bn_flags)
+        if self._train_stem or any(stem_bn_flags):
+            if first != 0:
+                raise NotImplementedError("a trainable stem below a frozen stage 1")
+            if not self._train_stem or (any(stem_bn_flags) and not all(stem_bn_flags)):
+                raise NotImplementedError("partially frozen stem (conv1 / bn1)")
+            params.append(self.conv1.weight)
+            if self._train_stem_bn:
+                params.extend((stem_norm.weight, stem_norm.bias))
         self._train_from = first
         self._train_bn = tuple(bn_train)
         return params
@@ -553,6 +567,8 @@ class ResNet(nn.Module):
             return flat.view(n, h, w, c).permute(0, 3, 1, 2).float().cpu() * (2.0 ** e)
 
         saved = {}
+        if getattr(plan, "stem_rec", None) is not None:
+            saved["stem.out"] = fetch(plan.stem_rec["stem_out"])
         for r in records:
             saved[r["pre"] + "in"] = fetch(r["xin"])
             for ci, a in enumerate(r["acts"]):
@@ -563,7 +579,7 @@ class ResNet(nn.Module):
         (x,) = inputs
         cache = self._get_operands(x.device)
         key = ("train", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, self._train_from, self._train_bn,
-               getattr(self, "_input_tf", None))
+               self._train_stem, self._train_stem_bn, getattr(self, "_input_tf", None))
         entry = self._plans.get(key)
         if entry is None:
             entry = self._build_plan(x, cache, train_from=self._train_from)
@@ -684,7 +700,7 @@ class ResNet(nn.Module):
                         bn_grad(name, ds[1], gM, live(r["shortcut"]))
                 # gradient w.r.t. the block input: needed unless the producer is frozen
                 is_first_block = r["bi"] == 0
-                need_gin = not (is_first_block and li == first)
+                need_gin = not (is_first_block and li == first) or (li == 0 and self._train_stem)
                 g_in = None
                 if need_gin:
                     module = unit.conv1
@@ -726,6 +742,28 @@ class ResNet(nn.Module):
                     bb.release(g)
                 bb.release(gM)
                 g_cur = g_in
+            segments.append([seg_start, len(bb.ops), len(buckets) - 1])
+        if self._train_stem:
+            # stem: max-pool + ReLU backward (scatter to the window maxima), bn1 affine gradients, 7x7 wgrad
+            seg_start = len(bb.ops)
+            rec = plan.stem_rec
+            stem_bn = getattr(self, self.norm_name)
+            sparams = [self.conv1.weight] + ([stem_bn.weight, stem_bn.bias] if self._train_stem_bn else [])
+            bucket = training.GradBucket(sparams, dev)
+            buckets.append(bucket)
+            s_out = rec["stem_out"]
+            d_s = engine.Act(torch.empty(s_out.shape[0] * s_out.shape[1] * s_out.shape[2] * 64, dtype=torch.bfloat16,
+                                         device=dev), s_out.shape, torch.bfloat16)
+            bb.buffers.append(d_s.buf)
+            bb.ops.append(engine.op_maxpool_bwd(s_out, g_cur, d_s))
+            if self._train_stem_bn:
+                gamma, beta = cache.get(("conv1", "affine"), lambda out: _affine_copy(stem_bn, out),
+                                        deps=(stem_bn.weight, stem_bn.bias))
+                c = stem_bn.weight.numel()
+                dwb = bucket.flat[bucket.offsets[1]:bucket.offsets[1] + 2 * c]
+                bb.ops.append(engine.op_bn_affine_grad(d_s, s_out, gamma, beta, dwb))
+            bb.ops.append(engine.op_stem_wgrad(s_out.shape[0], rec["h"], rec["w"], rec["staged"], d_s, bucket.view(0),
+                                               scale=scale_of("conv1", stem_bn)))
             segments.append([seg_start, len(bb.ops), len(buckets) - 1])
         ops, shift = bb.finalize()
         # every bucket is re-zeroed at the start of the run (1x1 wgrads accumulate straight into it)
