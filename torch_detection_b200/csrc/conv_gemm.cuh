@@ -616,14 +616,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // residual slabs are produced in tile order into one ring shared by both groups; consecutive
         // slabs of a group are two ring positions apart, so with any ring depth >= 2 the previous fill of
         // a slot has completed before the group waits for the next one (no parity aliasing)
-        // coarse operand (global loads): requested a whole pipeline step ahead of its use -- half 0 here, before
-        // the group's waits and barriers, half 1 while half 0 is being packed -- so that its L2 latency is covered
-        // (ncu showed 20 % of all stall samples on the first use of these registers when loaded just in time)
-        uint4 rco[4];
-        if (coarse_row) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + j * 8) * 2);
-        }
         const int ridx = (seq * kSlabsPerTile + slab) * nload;
         const int rs = ridx % kRS;
         const uint32_t rphase = static_cast<uint32_t>(ridx / kRS) & 1u;
@@ -658,6 +650,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int half = 0; half < 2; ++half) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_addr + slab * 64 + half * 32, v);
+          uint4 rco[4];
+          if (coarse_row) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
+          }
           uint4 rmk[4];
           if (!MASKED) {
           } else if (mask_tma) {
@@ -744,10 +741,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 x[8 * j + 2 * e] = fmaf(lo, mul_co, x[8 * j + 2 * e]);
                 x[8 * j + 2 * e + 1] = fmaf(hi, mul_co, x[8 * j + 2 * e + 1]);
               }
-            }
-            if (half == 0) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + 32 + j * 8) * 2);
             }
             if (SPLIT && split) {
 #pragma unroll
