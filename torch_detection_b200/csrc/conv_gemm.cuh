@@ -52,7 +52,14 @@ constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
 constexpr int kEpiGroupThreads = 128;    // one epilogue group = 4 warps = all 128 TMEM lanes
 
-enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2, A_STEM2 = 3, A_PATCH = 4 };
+enum AMode : int { A_TILED = 0, A_IM2COL = 1, A_STEM = 2, A_STEM2 = 3, A_PATCH = 4, A_SPATIAL = 5 };
+
+// A_SPATIAL (1x1, stride 1, with a coarse operand and nothing else in the ring: the FPN laterals): an M tile is
+// 8 x 16 output pixels (one 4D tiled TMA load per 64-channel chunk, a standard K-major tile), so the coarse
+// pixels the tile's epilogue adds form ONE 4 x 8-pixel box that TMA stages in shared memory -- a quarter-size
+// slot of the residual ring -- instead of 16-byte global loads whose latency the epilogue cannot hide.
+constexpr int kCoarseSlotBytes = 4 * 8 * 128;  // 4096: 32 coarse pixels x 64 channels
+constexpr int kRingSplit = 4;                  // coarse slots per 16 KiB residual slab
 
 // A_PATCH (3x3, stride 1, pad 1, dil 1): an M tile is 8 x 16 output pixels; per 64-channel chunk ONE
 // tiled TMA load deposits the (8+2) x (16+2) pixel halo patch (180 rows of 128 B, SWIZZLE_128B) and the
@@ -77,6 +84,8 @@ struct ConvGemmParams {
   CUtensorMap tmap_out;   // 2D (Cout, M) box (64,128); A_STEM: 4D (64, Wo, Ho, N) box (64,bw,bh,1)
   CUtensorMap tmap_res;   // 2D (Cout, M) box (64,128) over the residual tensor (if any)
   CUtensorMap tmap_mask;  // same geometry over the ReLU-mask tensor (if mask_tma)
+  CUtensorMap tmap_coarse; // A_SPATIAL: 4D (C, Wc, Hc, N) box (64, 4, 8, 1) over the coarse operand
+  int coarse_tma;
   int M;            // valid output rows (pixels); for A_STEM rows are masked per pixel instead
   int N;            // Cout
   int num_m_tiles;
@@ -138,7 +147,10 @@ struct GemmSmem {
   static constexpr int kResOffset = kBOffset + kBSlots * kBBytes;
   static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
   static constexpr int kBarOffset = kOutOffset + 2 * OSLABS * kSlabBytes;
-  static constexpr int kNumBars = 2 * STAGES + 5 + 2 * (RES_SLABS > 0 ? RES_SLABS : 1) + 2 * kPatchStages;
+  // the coarse-staging variants (BN 256, ring of 1 or 2 slabs) cut each slab into quarter-size slots
+  static constexpr bool kCoarseRing = BN == 256 && !PATCH && OSLABS == 1 && (RES_SLABS == 1 || RES_SLABS == 2);
+  static constexpr int kRingBars = kCoarseRing ? kRingSplit * RES_SLABS : (RES_SLABS > 0 ? RES_SLABS : 1);
+  static constexpr int kNumBars = 2 * STAGES + 5 + 2 * kRingBars + 2 * kPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;  // + 8: ring progress of the two groups
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
   // scale/shift per epilogue group: a group only touches the columns of its own slabs (half of BN),
@@ -200,10 +212,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
   auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
-  auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kRS + s); };
-  const uint32_t bres_bar = bar0 + 8u * (2 * STAGES + 4 + 2 * kRS);
-  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + s); };
-  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRS + kPatchStages + s); };
+  constexpr int kRB = L::kRingBars;
+  auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kRB + s); };
+  const uint32_t bres_bar = bar0 + 8u * (2 * STAGES + 4 + 2 * kRB);
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRB + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 5 + 2 * kRB + kPatchStages + s); };
+  // ring geometry: 16 KiB residual / mask slabs, or quarter-size coarse boxes (A_SPATIAL)
+  const bool coarse_tma = L::kCoarseRing && !MASKED && !SPLIT && p.coarse_tma != 0;
+  const int rdepth = coarse_tma ? kRingSplit * kRS : kRS;
+  const uint32_t rslot = coarse_tma ? kCoarseSlotBytes : kSlabBytes;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
   // highest residual-ring index the producer has issued so far (see the epilogue)
   volatile int* ring_issued = reinterpret_cast<volatile int*>(smem + L::kTmemPtrOffset + 8);
@@ -218,6 +235,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tma_prefetch_desc(&p.tmap_out);
     if (p.has_res) tma_prefetch_desc(&p.tmap_res);
     if (p.mask_tma) tma_prefetch_desc(&p.tmap_mask);
+    if (p.coarse_tma) tma_prefetch_desc(&p.tmap_coarse);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -228,7 +246,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), kSlabsPerTile == 1 ? 4 : 8);  // one arrive per warp draining buffer a
     }
-    for (int s = 0; s < kRS; ++s) {
+    for (int s = 0; s < kRB; ++s) {
       mbar_init(rfull_bar(s), 1);
       mbar_init(rempty_bar(s), 1);
     }
@@ -331,6 +349,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 tma_load_im2col_4d(dst_a, &p.tmap_a, fb, ka, cw, ch, cn,
                                    static_cast<uint16_t>(s * p.dil),
                                    static_cast<uint16_t>(r * p.dil));
+              } else if (p.a_mode == A_SPATIAL) {
+                tma_load_4d(dst_a, &p.tmap_a, fb, ka, cw, ch, cn);
               } else if (p.a_mode == A_STEM) {
                 // filter row r of the 7x7 window = staged image row 2*(ho + r/2) + (r & 1)
                 tma_load_5d(dst_a, &p.tmap_a, fb, 0, r & 1, cw, ch + (r >> 1), cn + (v == 1 ? p.a_lo_img : 0));
@@ -451,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // (sharing it lets the faster group borrow slots; two private rings of half the depth measured 15 %
     // slower on the residual convs).
     const bool rsplit = SPLIT && p.split && p.has_res;
-    const int nload = rsplit ? 2 : (p.has_res ? 1 : 0) + ((MASKED && p.mask_tma) ? 1 : 0);
+    const int nload = coarse_tma ? 1 : rsplit ? 2 : (p.has_res ? 1 : 0) + ((MASKED && p.mask_tma) ? 1 : 0);
     if (RES_SLABS > 0 && nload > 0) {
       int rs = 0;
       int issued = 0;
@@ -465,8 +485,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int cres = n_tile * BN + s * 64 + ((rsplit && j == 1) ? p.N : 0);  // lo half: N channels on
             mbar_wait(rempty_bar(rs), rphase ^ 1u);
             if (lane == 0) {
-              mbar_arrive_expect_tx(rfull_bar(rs), kSlabBytes);
-              if (p.a_mode >= A_STEM) {
+              mbar_arrive_expect_tx(rfull_bar(rs), rslot);
+              if (coarse_tma) {
+                // the 4 x 8 coarse pixels under this 8 x 16 tile
+                const int tw = m_tile % p.tiles_w;
+                const int t = m_tile / p.tiles_w;
+                tma_load_4d(smem_res + rs * rslot, &p.tmap_coarse, rfull_bar(rs), cres, tw * (p.tile_bw >> 1),
+                            (t % p.tiles_h) * (p.tile_bh >> 1), t / p.tiles_h);
+              } else if (p.a_mode >= A_STEM) {
                 const int tw = m_tile % p.tiles_w;
                 const int t = m_tile / p.tiles_w;
                 tma_load_4d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres,
@@ -478,7 +504,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             ++issued;
             __syncwarp();
-            if (++rs == kRS) { rs = 0; rphase ^= 1u; }
+            if (++rs == rdepth) { rs = 0; rphase ^= 1u; }
           }
         }
       }
@@ -518,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const bool split = SPLIT && p.split != 0;
     static_assert(!SPLIT || OSLABS == 2, "split precision stages the hi and the lo slab side by side");
     // split mode: the residual's lo slab rides in the ring slot the mask would use
-    const int nload = (split && has_res) ? 2 : (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
+    const int nload = coarse_tma ? 1 : (split && has_res) ? 2 : (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
     const bool has_coarse = p.coarse != nullptr;
     const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
     float* s_scale = s_params + group * 2 * L::kGroupCols;
@@ -592,7 +618,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         st_c1 = m_tile * kBM;
       }
       const uint8_t* coarse_row = nullptr;
-      if (valid && has_coarse) {
+      // TMA-staged coarse operand: this thread's pixel (hl, wl) of the 8 x 16 tile reads coarse box row
+      // (hl/2)*4 + wl/2; parity mode only adds at even pixels
+      int crow = -1;
+      if (coarse_tma && valid) {
+        const int hl = row / p.tile_bw, wl = row - hl * p.tile_bw;
+        if (!(p.coarse_parity && ((hl | wl) & 1))) crow = (hl >> 1) * (p.tile_bw >> 1) + (wl >> 1);
+      }
+      if (valid && has_coarse && !coarse_tma) {
         const int m = static_cast<int>(pix);
         const int q = m % p.Wo;
         const int t = m / p.Wo;
@@ -617,11 +650,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         // slabs of a group are two ring positions apart, so with any ring depth >= 2 the previous fill of
         // a slot has completed before the group waits for the next one (no parity aliasing)
         const int ridx = (seq * kSlabsPerTile + slab) * nload;
-        const int rs = ridx % kRS;
-        const uint32_t rphase = static_cast<uint32_t>(ridx / kRS) & 1u;
+        const int rs = ridx % rdepth;
+        const uint32_t rphase = static_cast<uint32_t>(ridx / rdepth) & 1u;
         const int midx = ridx + (has_res ? 1 : 0);
-        const int ms = midx % kRS;
-        const uint32_t mphase = static_cast<uint32_t>(midx / kRS) & 1u;
+        const int ms = midx % rdepth;
+        const uint32_t mphase = static_cast<uint32_t>(midx / rdepth) & 1u;
         // the staging buffer `ob` was last read by the TMA store this group issued OSLABS slabs ago
         if (issuer) {
           if (OSLABS == 1 || split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -639,7 +672,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (++spins > (1u << 24)) __trap();
           }
         }
-        if (has_res) mbar_wait(rfull_bar(rs), rphase);
+        if (has_res || coarse_tma) mbar_wait(rfull_bar(rs), rphase);
         if (mask_tma || (split && has_res)) mbar_wait(rfull_bar(ms), mphase);
         named_bar_sync(gbar, kEpiGroupThreads);
         if (split) ob = 0;
@@ -755,6 +788,25 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
             }
           }
+          if (crow >= 0) {
+            const uint32_t cbase = smem_res + rs * rslot + crow * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = cbase + ((((half << 2) | j) ^ (crow & 7)) << 4);
+              uint4 c4;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(c4.x), "=r"(c4.y), "=r"(c4.z), "=r"(c4.w)
+                           : "r"(a));
+              const uint32_t w4[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float lo, hi;
+                unpack16x2(w4[e], co_fp16, lo, hi);
+                x[8 * j + 2 * e] = fmaf(lo, mul_co, x[8 * j + 2 * e]);
+                x[8 * j + 2 * e + 1] = fmaf(hi, mul_co, x[8 * j + 2 * e + 1]);
+              }
+            }
+          }
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
@@ -838,7 +890,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (has_res) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
+          if (has_res || coarse_tma) mbar_arrive(rempty_bar(rs));  // every thread passed the barrier: slab consumed
           if (mask_tma || (split && has_res)) mbar_arrive(rempty_bar(ms));
         }
         if (OSLABS > 1 && !split) ob ^= 1;

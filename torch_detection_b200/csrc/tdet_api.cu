@@ -312,6 +312,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(256, 4, 0, 0, 1): return launch_gemm_t<256, 4, 0, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 3, 0, 0, 2): return launch_gemm_t<256, 3, 0, 0, false, 2>(l.gp, l.grid, st);
     case vkey(256, 3, 3, 0, 1): return launch_gemm_t<256, 3, 3, 0, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 3, 2, 0, 1): return launch_gemm_t<256, 3, 2, 0, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 4, 0, 2): return launch_gemm_t<256, 2, 4, 0, false, 2>(l.gp, l.grid, st);
     case vkey(256, 2, 6, 0, 1): return launch_gemm_t<256, 2, 6, 0, false, 1>(l.gp, l.grid, st);
     // resident weights (single n-tile, small K)
@@ -326,6 +327,7 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(256, 4, 6, 1, 1): return launch_gemm_t<256, 4, 6, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 3, 1, 1): return launch_gemm_t<256, 4, 3, 1, false, 1>(l.gp, l.grid, st);
     case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
+    case vkey(256, 3, 1, 4, 1): return launch_gemm_t<256, 3, 1, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d/%d", l.bn, l.stages,
@@ -523,6 +525,31 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     }
   }
 
+  // FPN laterals (1x1 + nearest-x2 coarse add, nothing else in the ring): 8 x 16 spatial tiles, so the coarse
+  // pixels under a tile are one TMA box staged in shared memory (A_SPATIAL, conv_gemm.cuh)
+  bool spatial = false;
+  if (tiled && o.coarse && !o.residual && !o.mask && !split && !grouped && l.bn == 256 && !l.no_patch &&
+      env_int("TDET_COARSE_TMA", 1)) {
+    const int tw = (o.wo + kPatchBW - 1) / kPatchBW, th = (o.ho + kPatchBH - 1) / kPatchBH;
+    const double rows = static_cast<double>(o.n) * tw * th * kBM;
+    if (rows <= 0x7FFFFF00LL && rows * 100.0 <= real_rows * 115.0) {
+      spatial = true;
+      gp.a_mode = A_SPATIAL;
+      gp.coarse_tma = 1;
+      gp.tile_bw = kPatchBW;
+      gp.tile_bh = kPatchBH;
+      gp.tiles_w = tw;
+      gp.tiles_h = th;
+      gp.num_m_tiles = o.n * tw * th;
+      l.oslabs = 1;
+      if (resident_b_enabled() && gp.num_n_tiles == 1 && gp.num_kb_b <= 4 && gp.num_m_tiles >= 4 * di.num_sms) {
+        l.stages = 3; l.res_slabs = 1; l.bres_kb = 4;
+      } else {
+        l.stages = 3; l.res_slabs = 2; l.bres_kb = 0;
+      }
+    }
+  }
+
   {
     const int nload = (o.residual ? 1 : 0) + 1;
     gp.mask_tma = (o.mask && l.res_slabs >= 2 * nload) ? 1 : 0;
@@ -531,7 +558,15 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   rc = encode_2d(&gp.tmap_b, o.wgt, w_dtype, static_cast<long long>(o.kh) * o.kw * o.cin * csplit, o.cout,
                  l.bn, "weights");
   if (rc) return rc;
-  if (l.patch) {
+  if (spatial) {
+    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
+    if (rc) return rc;
+    rc = encode_4d(&gp.tmap_a, o.x, o.x_dtype, o.cin, o.w, o.h, o.n, kPatchBW, kPatchBH, "activation tile");
+    if (rc) return rc;
+    rc = encode_4d(&gp.tmap_coarse, o.coarse, o.coarse_dtype, o.cout, o.wc, o.hc, o.n, kPatchBW / 2, kPatchBH / 2,
+                   "coarse level");
+    if (rc) return rc;
+  } else if (l.patch) {
     rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
     if (rc) return rc;
     if (o.residual) {
@@ -558,7 +593,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
       if (rc) return rc;
     }
   }
-  if (l.patch) {
+  if (l.patch || spatial) {
   } else if (tiled) {
     rc = encode_2d(&gp.tmap_a, o.x, o.x_dtype, o.cin * csplit, gp.M, kBM, "activations");
     if (rc) return rc;
