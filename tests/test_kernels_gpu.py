@@ -135,27 +135,56 @@ def test_conv_op(cuda_device, case, epi, dtype):
     assert err <= TOL[dtype], "rel-L2 %.3e" % err
 
 
-def test_conv_upsample_add(cuda_device):
-    """FPN lateral: 1x1 + bias + nearest-x2 upsample of the coarser level (fpn.py:92-101)."""
+PAIR_CASES = [c for c in CONV_CASES if c[5] % 256 == 0] + [
+    ("1x1_1024_256_long_k", 2, 50, 84, 1024, 256, 1, 1, 0, 1),     # 66 m-tiles: the default pair selection
+    ("3x3_256_256_odd_tiles", 1, 25, 42, 256, 512, 3, 1, 1, 1),    # 9 m-tiles x 2 n-tiles: padding tile in a pair
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+@pytest.mark.parametrize("epi", ["bn_relu", "bn_res_relu"])
+def test_conv_op_cta_pairs(cuda_device, case, epi, monkeypatch):
+    """Every eligible conv forced onto the CTA-pair kernel (clusters of two, cta_group::2 MMAs)."""
+    from torch_detection_b200 import engine
+    monkeypatch.setenv("TDET_PAIR", "2")
+    name, n, h, w, cin, cout, k, stride, pad, dil = case
+    dev = cuda_device
+    xb = engine.nhwc_empty(n, h, w, cin, dev)
+    ho, wo = engine.conv_out(h, k, stride, pad, dil), engine.conv_out(w, k, stride, pad, dil)
+    y = engine.nhwc_empty(n, ho, wo, cout, dev)
+    wp = engine.pack_conv_weight(torch.zeros(cout, cin, k, k, device=dev))
+    plan = engine.Plan([engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), k, k, stride, pad, dil)], [],
+                       [xb, y, wp], dev)
+    info = plan.launch_info()[0]
+    if n * ho * wo > 128:
+        assert info["variant"] & 8192, "conv was not scheduled on the pair kernel: %r" % (info,)
+    test_conv_op(cuda_device, case, epi, torch.bfloat16)
+
+
+@pytest.mark.parametrize("shape", [(2, 26, 44), (2, 32, 40), (1, 30, 38), (3, 64, 16)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_conv_upsample_add(cuda_device, shape, dtype):
+    """FPN lateral: 1x1 + bias + nearest-x2 upsample of the coarser level (fpn.py:92-101).  The shapes
+    cover the global-load path (ragged 8x16 tiling) and the TMA-staged coarse box (spatial tiles)."""
     from torch_detection_b200 import engine
     dev = cuda_device
     g = torch.Generator().manual_seed(7)
-    n, h, w, cin, cout = 2, 26, 44, 512, 256
+    (n, h, w), cin, cout = shape, 512, 256
     x = torch.randn(n, cin, h, w, generator=g).to(dev)
     wt = (torch.randn(cout, cin, 1, 1, generator=g) * (1.0 / cin) ** 0.5).to(dev)
     bias = (0.1 * torch.randn(cout, generator=g)).to(dev)
-    coarse = _nhwc(torch.randn(n, cout, h // 2, w // 2, generator=g).to(dev))
-    xb = _nhwc(x)
-    wp = engine.pack_conv_weight(wt)
-    y = engine.nhwc_empty(n, h, w, cout, dev)
+    coarse = _nhwc(torch.randn(n, cout, h // 2, w // 2, generator=g).to(dev), dtype)
+    xb = _nhwc(x, dtype)
+    wp = engine.pack_conv_weight(wt, dtype)
+    y = engine.nhwc_empty(n, h, w, cout, dev, dtype)
     op = engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), 1, 1, 1, 0, 1, shift=bias,
                         coarse=engine.act_of(coarse))
     engine.run_op(op, dev)
     torch.cuda.synchronize()
-    ref = F.conv2d(xb.float(), wt.to(torch.bfloat16).float(), bias)
+    ref = F.conv2d(xb.float(), wt.to(dtype).float(), bias)
     ref = ref + F.interpolate(coarse.float(), scale_factor=2, mode="nearest")
     err = rel_l2(y.float(), ref)
-    assert err <= TOL[torch.bfloat16], "rel-L2 %.3e" % err
+    assert err <= TOL[dtype], "rel-L2 %.3e" % err
 
 
 @pytest.mark.parametrize("magnitude", [1.0, 3.0e4, 2.0e-5])

@@ -137,9 +137,10 @@ struct ConvGemmParams {
 // PATCH: A_PATCH pipeline (A ring of kPatchStages halo patches; STAGES then counts B tiles).
 // OSLABS: staging slabs per epilogue group (1: a group's stores serialise with its next slab; 2: double
 // buffered).
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS>
+// PAIR: CTA pair (cta_group::2): each CTA stages only its half of the weight tile's N rows.
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool PAIR = false>
 struct GemmSmem {
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 2;
   static constexpr int kBSlots = BRES_KB > 0 ? BRES_KB : STAGES;
   static constexpr int kAStages = PATCH ? kPatchStages : STAGES;
   static constexpr int kAStageBytes = PATCH ? kPatchStageBytes : kABytes;
@@ -148,7 +149,7 @@ struct GemmSmem {
   static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
   static constexpr int kBarOffset = kOutOffset + 2 * OSLABS * kSlabBytes;
   // the coarse-staging variants (BN 256, ring of 1 or 2 slabs) cut each slab into quarter-size slots
-  static constexpr bool kCoarseRing = BN == 256 && !PATCH && OSLABS == 1 && (RES_SLABS == 1 || RES_SLABS == 2);
+  static constexpr bool kCoarseRing = BN == 256 && !PATCH && !PAIR && OSLABS == 1 && (RES_SLABS == 1 || RES_SLABS == 2);
   static constexpr int kRingBars = kCoarseRing ? kRingSplit * RES_SLABS : (RES_SLABS > 0 ? RES_SLABS : 1);
   static constexpr int kNumBars = 2 * STAGES + 5 + 2 * kRingBars + 2 * kPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;  // + 8: ring progress of the two groups
@@ -180,10 +181,17 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
 
 // MASKED: the kernel carries the ReLU-backward mask path (dgrad); forward instantiations compile it out.
 // SPLIT: split-precision epilogue (hi/lo outputs, hi/lo residual and coarse operands); needs OSLABS == 2.
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false>
+// PAIR: launched as clusters of two CTAs (one TPC); the pair computes two vertically adjacent 128-row tiles of one
+// n-tile with M = 256 cta_group::2 MMAs issued by the leader.  Each CTA loads its own A tile and HALF of the weight
+// tile (the MMA reads both halves across the pair), so the L2 -> SM operand traffic per MMA cycle drops by a third
+// -- the streamed-weight kernels are bound by exactly that traffic -- and each weight tile is fetched once per 256
+// output rows.  Accumulators, residual ring and epilogue stay per-CTA.
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false,
+          bool PAIR = false>
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, PAIR>;
+  static_assert(!PAIR || (BN == 256 && !PATCH && BRES_KB == 0 && !SPLIT), "CTA pairs: streamed 256-wide tiles only");
   // Split precision keeps TWO accumulators per tile: hi*hi in one, the small cross terms lo*hi + hi*lo in the
   // other, summed in fp32 by the epilogue.  tcgen05's fp32 accumulation is not exact -- measured ~0.17 ulp of
   // systematic loss per MMA step, which over the 3x longer K loop and ~50 layers was the dominant error of
@@ -244,7 +252,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kSlabsPerTile == 1 ? 4 : 8);  // one arrive per warp draining buffer a
+      // one arrive per warp draining buffer a (the leader's barrier collects both CTAs of a pair)
+      mbar_init(tempty_bar(a), (kSlabsPerTile == 1 ? 4 : 8) * (PAIR ? 2 : 1));
     }
     for (int s = 0; s < kRB; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -258,19 +267,33 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     fence_mbar_init();
   }
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   if (warp == 3) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Launched with programmatic stream serialisation: everything above (barrier init, TMEM allocation,
   // descriptor prefetch) overlaps the tail of the previous kernel; its outputs are read only below.
   grid_dependency_wait();
 
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tile schedule: CTA (or pair) t takes tiles t, t + step, ...; a pair's tile is two consecutive m-tiles, the
+  // rank picks one (the last pair of an odd count re-loads the last valid tile and stores nothing)
+  const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = (PAIR ? (p.num_m_tiles + 1) >> 1 : p.num_m_tiles) * p.num_n_tiles;
+  auto m_tile_of = [&](int tile) {
+    const int mt = tile / p.num_n_tiles;
+    return PAIR ? 2 * mt + static_cast<int>(cta_rank) : mt;
+  };
   // grouped convs (group width divides 64): output channels [64j, 64j+64) only see input channels of the
   // same range, so each 64-wide n-tile runs ONE channel chunk per filter tap over the densely packed,
   // block-diagonal weight matrix
@@ -290,7 +313,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_stage_bytes) + (BRES_KB > 0 ? 0u : L::kBBytes);
     if (PATCH) {
       // one halo patch per (tile, 64-channel chunk); OOB pixels (the conv padding) are zero-filled
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_tile = tile / p.num_n_tiles;
         const int tw = m_tile % p.tiles_w;
         const int t = m_tile / p.tiles_w;
@@ -309,14 +332,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_tile = m_tile_of(tile);
+      const int n_tile = tile % p.num_n_tiles;
       const int n0 = n_tile * BN;
+      const int m_ld = PAIR ? min(m_tile, p.num_m_tiles - 1) : m_tile;
       // tile origin in the A coordinate space
       int cw = 0, ch = 0, cn = 0;
       if (p.a_mode == A_IM2COL) {
-        const int m0 = m_tile * kBM;
+        const int m0 = m_ld * kBM;
         const int q0 = m0 % p.Wo;
         const int t = m0 / p.Wo;
         const int p0 = t % p.Ho;
@@ -338,12 +362,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
-              const uint32_t fb = full_bar(stage);
-              mbar_arrive_expect_tx(fb, stage_tx);
               const uint32_t dst_a = smem_a + stage * kABytes;
               const uint32_t dst_b = smem_b + stage * L::kBBytes;
               const int ka = (kc + (v == 1 ? p.k_chunks : 0)) * kBK;  // lo activations sit C channels further
-              if (p.a_mode == A_TILED) {
+              if (PAIR) {
+                // both CTAs' bytes are counted on the leader's barrier, which the (leader's) MMA warp waits on
+                if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
+                const uint32_t lb = mapa_shared(full_bar(stage), 0);
+                if (p.a_mode == A_TILED) {
+                  tma_load_2d_pair(dst_a, &p.tmap_a, lb, ka, m_ld * kBM);
+                } else {
+                  tma_load_im2col_4d_pair(dst_a, &p.tmap_a, lb, ka, cw, ch, cn, static_cast<uint16_t>(s * p.dil),
+                                          static_cast<uint16_t>(r * p.dil));
+                }
+                tma_load_2d_pair(dst_b, &p.tmap_b, lb, (r * p.kw + s) * p.b_tap_stride + kc * kBK,
+                                 n0 + static_cast<int>(cta_rank) * (BN / 2));
+              }
+              const uint32_t fb = full_bar(stage);
+              if (!PAIR) mbar_arrive_expect_tx(fb, stage_tx);
+              if (PAIR) {
+              } else if (p.a_mode == A_TILED) {
                 tma_load_2d(dst_a, &p.tmap_a, fb, ka, m_tile * kBM);
               } else if (p.a_mode == A_IM2COL) {
                 tma_load_im2col_4d(dst_a, &p.tmap_a, fb, ka, cw, ch, cn,
@@ -359,7 +397,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 // copied linearly (no swizzle); coordinates (64-element chunk, chunk index, row, image)
                 tma_load_4d(dst_a, &p.tmap_a, fb, 0, cw >> 3, 2 * ch, cn);
               }
-              if (BRES_KB == 0)
+              if (BRES_KB == 0 && !PAIR)
                 tma_load_2d(dst_b, &p.tmap_b, fb,
                             (r * p.kw + s) * p.b_tap_stride + (v == 2 ? p.b_lo_off : 0) + kc * kBK, n0);
             }
@@ -372,7 +410,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_f16kind(kBM, BN, p.ab_fp16 ? kFmtF16 : kFmtBF16,
+    const uint32_t idesc = make_idesc_f16kind(PAIR ? 2 * kBM : kBM, BN, p.ab_fp16 ? kFmtF16 : kFmtBF16,
                                               p.b_fp16 ? kFmtF16 : kFmtBF16);
     int stage = 0;
     uint32_t phase = 0;
@@ -382,7 +420,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH) {
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
@@ -420,8 +458,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-    } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    } else if (!PAIR || cta_rank == 0)
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_main = tmem_base + static_cast<uint32_t>(acc * kAccStride);
@@ -452,11 +490,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
-              umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kb - kb_first) | k) != 0 ? 1u : 0u);
+              if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kb - kb_first) | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (PAIR) {
+            // frees the stage / publishes the accumulator in both CTAs
+            umma_commit_pair(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -476,9 +521,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int rs = 0;
       int issued = 0;
       uint32_t rphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_tile = m_tile_of(tile);
+        const int n_tile = tile % p.num_n_tiles;
         for (int s = 0; s < kSlabsPerTile; ++s) {
           for (int j = 0; j < nload; ++j) {
             const CUtensorMap* tm = (rsplit || (j == 0 && p.has_res)) ? &p.tmap_res : &p.tmap_mask;
@@ -498,7 +543,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 tma_load_4d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres,
                             tw * p.tile_bw, (t % p.tiles_h) * p.tile_bh, t / p.tiles_h);
               } else {
-                tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres, m_tile * kBM);
+                tma_load_2d(smem_res + rs * kSlabBytes, tm, rfull_bar(rs), cres,
+                            (PAIR ? min(m_tile, p.num_m_tiles - 1) : m_tile) * kBM);
               }
               *ring_issued = issued;  // this fill's predecessor in the slot has been consumed, hence completed
             }
@@ -514,7 +560,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH && BRES_KB == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
@@ -575,12 +621,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int cur_n_tile = -1;
     int ob = 0;  // staging buffer of the next slab
     int seq = 0; // CTA-local tile counter: tile seq accumulates in TMEM buffer seq & 1
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++seq) {
       if (kByTile && (seq & 1) != group) continue;
       const int acc = kAccBufs == 2 ? (seq & 1) : 0;
       const uint32_t acc_phase = static_cast<uint32_t>(kAccBufs == 2 ? (seq >> 1) : seq) & 1u;
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m_tile = m_tile_of(tile);
+      const int n_tile = tile % p.num_n_tiles;
       const int n0 = n_tile * BN;
       if (n_tile != cur_n_tile) {
         named_bar_sync(gbar, kEpiGroupThreads);
@@ -855,13 +901,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         fence_proxy_async_smem();  // staging writes -> visible to the TMA (async proxy)
         named_bar_sync(gbar, kEpiGroupThreads);
         if (issuer) {
           const uint32_t src = smem_out_g + ob * kSlabBytes;
-          if (p.a_mode >= A_STEM) {
+          if (PAIR && m_tile >= p.num_m_tiles) {
+            // the odd pair's padding tile: nothing to store
+          } else if (p.a_mode >= A_STEM) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),
@@ -906,10 +957,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // (pair: the peer may still signal this CTA's barriers)
   if (warp == 3) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
