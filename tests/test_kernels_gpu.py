@@ -138,6 +138,9 @@ def test_conv_op(cuda_device, case, epi, dtype):
 PAIR_CASES = [c for c in CONV_CASES if c[5] % 256 == 0] + [
     ("1x1_1024_256_long_k", 2, 50, 84, 1024, 256, 1, 1, 0, 1),     # 66 m-tiles: the default pair selection
     ("3x3_256_256_odd_tiles", 1, 25, 42, 256, 512, 3, 1, 1, 1),    # 9 m-tiles x 2 n-tiles: padding tile in a pair
+    ("3x3_128_128_patch", 3, 32, 40, 128, 128, 3, 1, 1, 1),        # halo-patch loader, 15 spatial tiles (odd)
+    ("3x3_256_256_patch", 1, 48, 32, 256, 256, 3, 1, 1, 1),
+    ("3x3_128_256_patch_ragged", 2, 30, 38, 128, 256, 3, 1, 1, 1),
 ]
 
 
@@ -146,7 +149,7 @@ PAIR_CASES = [c for c in CONV_CASES if c[5] % 256 == 0] + [
 def test_conv_op_cta_pairs(cuda_device, case, epi, monkeypatch):
     """Every eligible conv forced onto the CTA-pair kernel (clusters of two, cta_group::2 MMAs)."""
     from torch_detection_b200 import engine
-    monkeypatch.setenv("TDET_PAIR", "2")
+    monkeypatch.setenv("TDET_PAIR", "15")
     name, n, h, w, cin, cout, k, stride, pad, dil = case
     dev = cuda_device
     xb = engine.nhwc_empty(n, h, w, cin, dev)

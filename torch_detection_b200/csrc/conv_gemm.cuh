@@ -191,7 +191,7 @@ template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, PAIR>;
-  static_assert(!PAIR || (BN == 256 && !PATCH && BRES_KB == 0 && !SPLIT), "CTA pairs: streamed 256-wide tiles only");
+  static_assert(!PAIR || (BN >= 128 && BRES_KB == 0 && !SPLIT), "CTA pairs: streamed weight tiles, 128/256 wide");
   // Split precision keeps TWO accumulators per tile: hi*hi in one, the small cross terms lo*hi + hi*lo in the
   // other, summed in fp32 by the epilogue.  tcgen05's fp32 accumulation is not exact -- measured ~0.17 ulp of
   // systematic loss per MMA step, which over the 3x longer K loop and ~50 layers was the dominant error of
@@ -314,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH) {
       // one halo patch per (tile, 64-channel chunk); OOB pixels (the conv padding) are zero-filled
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_tile = tile / p.num_n_tiles;
+        const int m_tile = PAIR ? min(m_tile_of(tile), p.num_m_tiles - 1) : m_tile_of(tile);
         const int tw = m_tile % p.tiles_w;
         const int t = m_tile / p.tiles_w;
         const int th = t % p.tiles_h;
@@ -323,9 +323,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(aempty_bar(stage), phase ^ 1u);
           if (lane == 0) {
-            mbar_arrive_expect_tx(afull_bar(stage), kPatchBytes);
-            tma_load_4d(smem_a + stage * kPatchStageBytes, &p.tmap_a, afull_bar(stage), kc * kBK,
-                        tw * kPatchBW - 1, th * kPatchBH - 1, img);
+            if (PAIR) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(afull_bar(stage), 2 * kPatchBytes);
+              tma_load_4d_pair(smem_a + stage * kPatchStageBytes, &p.tmap_a, mapa_shared(afull_bar(stage), 0),
+                               kc * kBK, tw * kPatchBW - 1, th * kPatchBH - 1, img);
+            } else {
+              mbar_arrive_expect_tx(afull_bar(stage), kPatchBytes);
+              tma_load_4d(smem_a + stage * kPatchStageBytes, &p.tmap_a, afull_bar(stage), kc * kBK,
+                          tw * kPatchBW - 1, th * kPatchBH - 1, img);
+            }
           }
           __syncwarp();
           if (++stage == kPatchStages) { stage = 0; phase ^= 1u; }
@@ -420,6 +426,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH) {
       int as = 0;
       uint32_t aphase = 0;
+      if (!PAIR || cta_rank == 0)
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -440,12 +447,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               const uint64_t db = make_smem_desc_sw128(
                   smem_b + (BRES_KB > 0 ? tap * p.k_chunks + kc : stage) * L::kBBytes);
 #pragma unroll
-              for (int k = 0; k < kBK / kUmmaK; ++k)
-                umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kc - kc_lo) | tap | k) != 0 ? 1u : 0u);
-              if (BRES_KB == 0) umma_commit(empty_bar(stage));
-              if (tap == 8) {
-                umma_commit(aempty_bar(as));
-                if (kc == kc_lo + kcn - 1) umma_commit(tfull_bar(acc));
+              for (int k = 0; k < kBK / kUmmaK; ++k) {
+                if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kc - kc_lo) | tap | k) != 0 ? 1u : 0u);
+                else umma_bf16_ss(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kc - kc_lo) | tap | k) != 0 ? 1u : 0u);
+              }
+              if (PAIR) {
+                umma_commit_pair(empty_bar(stage));
+                if (tap == 8) {
+                  umma_commit_pair(aempty_bar(as));
+                  if (kc == kc_lo + kcn - 1) umma_commit_pair(tfull_bar(acc));
+                }
+              } else {
+                if (BRES_KB == 0) umma_commit(empty_bar(stage));
+                if (tap == 8) {
+                  umma_commit(aempty_bar(as));
+                  if (kc == kc_lo + kcn - 1) umma_commit(tfull_bar(acc));
+                }
               }
             }
             __syncwarp();
@@ -567,8 +584,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             if (lane == 0) {
-              mbar_arrive_expect_tx(full_bar(stage), L::kBBytes);
-              tma_load_2d(smem_b + stage * L::kBBytes, &p.tmap_b, full_bar(stage), tap * p.b_tap_stride + kc * kBK, n0);
+              if (PAIR) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * L::kBBytes);
+                tma_load_2d_pair(smem_b + stage * L::kBBytes, &p.tmap_b, mapa_shared(full_bar(stage), 0),
+                                 tap * p.b_tap_stride + kc * kBK, n0 + static_cast<int>(cta_rank) * (BN / 2));
+              } else {
+                mbar_arrive_expect_tx(full_bar(stage), L::kBBytes);
+                tma_load_2d(smem_b + stage * L::kBBytes, &p.tmap_b, full_bar(stage), tap * p.b_tap_stride + kc * kBK, n0);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -652,7 +675,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int wl = row - hl * p.tile_bw;
         const int ho = th * p.tile_bh + hl;
         const int wo = tw * p.tile_bw + wl;
-        valid = (ho < p.Ho) && (wo < p.Wo);
+        valid = (ho < p.Ho) && (wo < p.Wo) && !(PAIR && m_tile >= p.num_m_tiles);
         pix = (static_cast<long long>(img) * p.Ho + ho) * p.Wo + wo;
         st_c1 = tw * p.tile_bw;
         st_c2 = th * p.tile_bh;

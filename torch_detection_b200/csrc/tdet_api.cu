@@ -174,6 +174,7 @@ bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
 int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
 constexpr int kDefaultVariantSet = 0;
+constexpr int kDefaultPairMode = 9;  // measured: long-K streamed convs 5-9 %, 256-wide halo-patch 3x3 6 % faster; others lose
 constexpr int kDefaultResVariant = 0;  // residual convs with streamed weights: 0 (256,3,2) 1 (256,2,4,os2) 2 BN=128 3 (256,2,6)
 constexpr int kDefaultRes1Ring = 3;
 
@@ -278,21 +279,22 @@ int launch_gemm_split(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
                     L::kDynamic, st, gp);
 }
 
-// CTA-pair variants (clusters of two CTAs, cta_group::2 MMAs): streamed 256-wide tiles
-template <int STAGES, int RES_SLABS, int OSLABS, bool MASKED>
+// CTA-pair variants (clusters of two CTAs, cta_group::2 MMAs): streamed weight tiles
+template <int BN, int STAGES, int RES_SLABS, bool PATCH, int OSLABS, bool MASKED>
 int launch_gemm_pair_m(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
-  using L = GemmSmem<256, STAGES, RES_SLABS, 0, false, OSLABS, true>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, 0, PATCH, OSLABS, true>;
   static int max_clusters[64] = {};  // co-resident pairs on the device (0 = not queried yet)
   int dev = 0;
   TDET_CUDA(cudaGetDevice(&dev));
-  auto kernel = conv_gemm_kernel<256, STAGES, RES_SLABS, 0, false, OSLABS, MASKED, false, true>;
+  auto kernel = conv_gemm_kernel<BN, STAGES, RES_SLABS, 0, PATCH, OSLABS, MASKED, false, true>;
+  constexpr int kThreads = PATCH ? kGemmThreads : kGemmThreadsNoPatch;
   if (!max_clusters[dev]) {
     TDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     // the grid is persistent with a static tile stride: it must not exceed what is resident at once (a TPC
     // with one SM fused off hosts no pair)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * 74, 1, 1);
-    cfg.blockDim = dim3(kGemmThreadsNoPatch, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = L::kDynamic;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -307,12 +309,12 @@ int launch_gemm_pair_m(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
     max_clusters[dev] = n;
   }
   if (grid.x > 2u * static_cast<unsigned>(max_clusters[dev])) grid.x = 2u * static_cast<unsigned>(max_clusters[dev]);
-  return launch_pdl(kernel, grid, kGemmThreadsNoPatch, L::kDynamic, st, gp, 2);
+  return launch_pdl(kernel, grid, kThreads, L::kDynamic, st, gp, 2);
 }
-template <int STAGES, int RES_SLABS, int OSLABS>
+template <int BN, int STAGES, int RES_SLABS, bool PATCH, int OSLABS>
 int launch_gemm_pair(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
-  if (gp.mask_src) return launch_gemm_pair_m<STAGES, RES_SLABS, OSLABS, true>(gp, grid, st);
-  return launch_gemm_pair_m<STAGES, RES_SLABS, OSLABS, false>(gp, grid, st);
+  if (gp.mask_src) return launch_gemm_pair_m<BN, STAGES, RES_SLABS, PATCH, OSLABS, true>(gp, grid, st);
+  return launch_gemm_pair_m<BN, STAGES, RES_SLABS, PATCH, OSLABS, false>(gp, grid, st);
 }
 
 // forward convs never carry a ReLU-backward mask: they get the instantiation without that code path
@@ -342,9 +344,12 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
                 l.stages, l.res_slabs);
   }
   if (l.pair) {
-    switch (vkey(l.bn, l.stages, l.res_slabs, 0, l.oslabs)) {
-      case vkey(256, 6, 0, 0, 1): return launch_gemm_pair<6, 0, 1>(l.gp, l.grid, st);
-      case vkey(256, 4, 3, 0, 1): return launch_gemm_pair<4, 3, 1>(l.gp, l.grid, st);
+    switch (vkey(l.bn, l.stages, l.res_slabs, l.patch ? 1 : 0, l.oslabs)) {
+      case vkey(256, 6, 0, 0, 1): return launch_gemm_pair<256, 6, 0, false, 1>(l.gp, l.grid, st);
+      case vkey(256, 4, 3, 0, 1): return launch_gemm_pair<256, 4, 3, false, 1>(l.gp, l.grid, st);
+      case vkey(256, 6, 0, 1, 1): return launch_gemm_pair<256, 6, 0, true, 1>(l.gp, l.grid, st);
+      case vkey(128, 7, 0, 1, 1): return launch_gemm_pair<128, 7, 0, true, 1>(l.gp, l.grid, st);
+      case vkey(128, 4, 2, 1, 1): return launch_gemm_pair<128, 4, 2, true, 1>(l.gp, l.grid, st);
     }
     return fail(TDET_ERR_INVALID_ARGUMENT, "no CTA-pair GEMM instantiation for tile %d/%d/%d", l.bn, l.stages,
                 l.res_slabs);
@@ -612,13 +617,21 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   // operand traffic per MMA cycle and a deeper ring in the same shared memory.  Measured (R50 batch 16): 5-9 %
   // faster from K = 1024 up; short-K / epilogue-bound convs (conv3 + residual, stride-2 shortcuts) lose 10-15 % to
   // the lock-step of the two epilogues, so they stay single-CTA (TDET_PAIR=2 forces pairs wherever they apply).
+  // TDET_PAIR bits: 1 long-K streamed convs, 2 every streamed 256-wide conv, 4 / 8 halo-patch 3x3 convs with
+  // 128- / 256-wide tiles (the MMA of a pair reads a third less shared memory per cycle: 128-wide SS MMAs alone
+  // saturate the 128 B/clk of one SM).
   l.pair = false;
-  const int pair_mode = env_int("TDET_PAIR", 1);
+  const int pair_mode = env_int("TDET_PAIR", kDefaultPairMode);
   if (!l.patch && !spatial && l.bn == 256 && l.bres_kb == 0 && !split && naux <= 1 && !l.no_patch &&
-      gp.num_m_tiles >= 2 && pair_mode && (pair_mode == 2 || (naux == 0 && gp.num_kb_b >= 16))) {
+      gp.num_m_tiles >= 2 && ((pair_mode & 2) || ((pair_mode & 1) && naux == 0 && gp.num_kb_b >= 16))) {
     l.pair = true;
     l.oslabs = 1;
     if (naux == 1) { l.stages = 4; l.res_slabs = 3; } else { l.stages = 6; l.res_slabs = 0; }
+  }
+  if (l.patch && l.bres_kb == 0 && gp.num_m_tiles >= 2 && !grouped &&
+      ((l.bn == 128 && (pair_mode & 4)) || (l.bn == 256 && (pair_mode & 8)))) {
+    l.pair = true;
+    if (l.bn == 256) l.stages = 6;
   }
 
   {
