@@ -814,11 +814,26 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
       reinterpret_cast<unsigned long long*>(&wp.tmap_x)[1] &= ~(1ull << 21);
   }
   const int tiles = ((o.cout + 128 * l.wg_mt - 1) / (128 * l.wg_mt)) * o.kh * o.kw * wp.ci_groups;
-  // one CTA per SM (shared memory): aim at exactly two full waves, never a partial third one
+  // One CTA per SM (shared memory).  Split-K trades main-loop length against the fp32 reduction traffic every
+  // CTA adds (a whole tile of red.add per CTA, ~3 TB/s device-wide measured): pick half a wave, one or two full
+  // waves -- never a partial extra one -- by a two-term cost model (TDET_WGRAD_WAVES=1/2 forces one).
   const int sms = di.num_sms - di.sm_reserve;
-  int splits = (2 * sms) / tiles;
-  if (splits > wp.kblocks) splits = wp.kblocks;
-  if (splits < 1) splits = 1;
+  const double t_kb = 0.15 * l.wg_mt * (l.wg_pix / 16) * (l.wg_nb / 256.0);  // us per k-block (measured ~50 % pipe)
+  const double tile_bytes = 128.0 * l.wg_mt * l.wg_nb * 4.0;
+  const int force_waves = env_int("TDET_WGRAD_WAVES", 0);
+  int splits = 1;
+  double best = 1e30;
+  for (int target : {sms / 2, sms, 2 * sms}) {
+    if (force_waves && target != force_waves * sms) continue;
+    int sp = target / tiles;
+    if (sp > wp.kblocks) sp = wp.kblocks;
+    if (sp < 1) sp = 1;
+    const int ctas = tiles * sp;
+    const int waves = (ctas + sms - 1) / sms;
+    const int conc = ctas < sms ? ctas : sms;
+    const double t = waves * ((wp.kblocks + sp - 1) / sp * t_kb + conc * tile_bytes / 3.0e6);
+    if (t < best) { best = t; splits = sp; }
+  }
   wp.kb_per_cta = (wp.kblocks + splits - 1) / splits;
   splits = (wp.kblocks + wp.kb_per_cta - 1) / wp.kb_per_cta;
   l.grid = dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits), 1);
