@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 7
+#define TDET_ABI_VERSION 8
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -97,12 +97,16 @@ enum {
                                x_meta and bound_consts) */
   TDET_FLAG_COARSE_PARITY = 4, /* coarse[i][j] is added at y[2i][2j] only (adjoint of a stride-2 1x1 conv,
                                   resnet.py:129-136) instead of nearest-x2 upsampled; hc = (ho+1)/2 */
-  TDET_FLAG_SPLIT = 8       /* split precision (the fp32-I/O mode, <= 1e-4 vs the fp32 reference): every
+  TDET_FLAG_SPLIT = 8,      /* split precision (the fp32-I/O mode, <= 1e-4 vs the fp32 reference): every
                                activation tensor is a bf16 pair value = hi + lo stored as 2*C channels
                                [hi | lo] (PREP / STEM staging: two image planes), conv weights come from
                                tdet_pack_conv_weight_split; the GEMM accumulates hi*hi + lo*hi + hi*lo in
                                fp32 and the epilogue splits its fp32 result again.  cin / cout stay the
                                LOGICAL channel counts.  Valid on PREP, STEM, MAXPOOL, CONV. */
+  TDET_FLAG_POOL = 16       /* TDET_OP_STEM only: the kernel also applies the 3x3/2 p1 max-pool that follows the
+                               stem (resnet.py:218,258) and y is the POOLED tensor [n][hp][wp][64], hp =
+                               (ho - 1) / 2 + 1; the stem's own output never reaches memory.  Needs
+                               TDET_FLAG_RELU (out-of-image window positions are taken as 0). */
 };
 
 /* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
@@ -125,7 +129,8 @@ typedef struct tdet_tensor_meta {
  *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
  *                   y_meta (optional): receives the image's |max| (exponent 0).
  * TDET_OP_STEM      x: the PREP output (bf16); wgt: tdet_pack_stem_weight output (bf16 [64][448]);
- *                   scale/shift: folded bn1; y: [n][ho][wo][64] of y_dtype.  h,w = image size.
+ *                   scale/shift: folded bn1; y: [n][ho][wo][64] of y_dtype (with TDET_FLAG_POOL: the max-pooled
+ *                   [n][(ho-1)/2+1][(wo-1)/2+1][64]).  h,w = image size.
  * TDET_OP_MAXPOOL   x: [n][h][w][cin] of x_dtype; y: [n][ho][wo][cin] same dtype; 3x3, stride 2,
  *                   pad 1.  (Metadata passes through unchanged: the caller aliases it.)
  * TDET_OP_CONV      x: [n][h][w][cin] of x_dtype; wgt: [cout][kh][kw][cin] of the SAME dtype;

@@ -275,6 +275,40 @@ def test_prep_and_stem(cuda_device, shape, dtype):
     ref = F.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     err = rel_l2(y.float(), ref)
     assert err <= TOL[torch.bfloat16], "rel-L2 %.3e" % err
+    # the same kernel with the 3x3/2 max-pool in its epilogue (TDET_FLAG_POOL): bit-identical to pooling its output
+    hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
+    yp = engine.nhwc_empty(n, hq, wq, 64, dev)
+    yp.fill_(-1.0)
+    engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(yp), scale, shift, pool=True), dev)
+    torch.cuda.synchronize()
+    assert torch.equal(yp, F.max_pool2d(y, 3, 2, 1)), "fused stem + max-pool differs from pooling the stem output"
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 500), (2, 99, 250), (1, 18, 14)])
+def test_stem_pool_strips(cuda_device, shape):
+    """Fused stem + max-pool over several column strips, odd sizes, and ranges that span images."""
+    from torch_detection_b200 import engine
+    dev = cuda_device
+    n, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, 3, h, w, generator=g).to(dev)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * (2.0 / (64 * 49)) ** 0.5).to(dev)
+    scale = (0.5 + torch.rand(64, generator=g)).to(dev)
+    shift = (0.3 * torch.randn(64, generator=g)).to(dev)
+    ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
+    hp, wp_ = engine.stem_staging_dims(ho, wo)
+    staged = torch.empty((n, hp, wp_, 4), dtype=torch.bfloat16, device=dev)
+    engine.run_op(engine.op_prep(x, staged, ho, wo), dev)
+    wpk = engine.pack_stem_weight(wt)
+    for dtype in (torch.bfloat16, torch.float16):
+        y = engine.nhwc_empty(n, ho, wo, 64, dev, dtype)
+        engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(y), scale, shift), dev)
+        hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
+        yp = engine.nhwc_empty(n, hq, wq, 64, dev, dtype)
+        yp.fill_(-1.0)
+        engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(yp), scale, shift, pool=True), dev)
+        torch.cuda.synchronize()
+        assert torch.equal(yp, F.max_pool2d(y.float(), 3, 2, 1).to(dtype)), "fused stem + max-pool mismatch (%s)" % dtype
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 32, 48), (1, 64, 35, 51), (2, 128, 9, 7)])

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # tdet_status
 OK = 0
@@ -32,6 +32,7 @@ FLAG_RELU = 1
 FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4
 FLAG_SPLIT = 8
+FLAG_POOL = 16
 
 
 class TdetOp(ctypes.Structure):

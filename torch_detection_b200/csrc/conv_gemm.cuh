@@ -109,6 +109,8 @@ struct ConvGemmParams {
   int a_stage_bytes;     // bytes one A load deposits per stage (kABytes except A_STEM2)
   int num_kb_b;          // number of 64-wide k-blocks of the weight matrix (resident-B kernels)
   int stem_row_bytes;    // A_STEM2: shared-memory pitch of one staged image row segment
+  int pool_h, pool_w;    // POOL kernels: size of the 3x3/2 max-pooled output the stem writes instead of its own
+  void* pool_out;        //   [n][pool_h][pool_w][64], 16-bit
   int Hc, Wc;       // coarse level size (upsample-add)
   int relu;
   int has_res;
@@ -186,10 +188,22 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
 // tile (the MMA reads both halves across the pair), so the L2 -> SM operand traffic per MMA cycle drops by a third
 // -- the streamed-weight kernels are bound by exactly that traffic -- and each weight tile is fetched once per 256
 // output rows.  Accumulators, residual ring and epilogue stay per-CTA.
+// POOL (stem, A_STEM2 only): the epilogue max-pools (3x3, stride 2, pad 1: resnet.py:218) before anything reaches
+// HBM.  A CTA walks DOWN consecutive conv rows of one 128-pixel column strip; each epilogue group owns 32 of the 64
+// channels of EVERY row (pooling is per channel, so the groups never talk), keeps the last three post-ReLU rows
+// in shared memory and, after every odd row 2p+1, writes pooled row p = max over rows 2p-1..2p+1 x columns
+// 2q-1..2q+1.  Strips start at conv column 112 j - 8 and produce pooled columns 56 j .. 56 j + 55 (12.5 % of the
+// MMA rows overlap, as many tiles as before); out-of-image positions hold 0, which equals the -inf padding of the
+// reference because every window has a valid element and post-ReLU values are >= 0.  This removes the write and
+// the re-read of the 64 x H/2 x W/2 stem output (1.1 GB per batch of 16 at 800x1344) and the pooling launch.
+constexpr int kPoolStep = 56;  // pooled columns per strip
+
 template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false,
-          bool PAIR = false>
+          bool PAIR = false, bool POOL = false>
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  static_assert(!POOL || (BN == 64 && BRES_KB > 0 && !PATCH && !SPLIT && !PAIR && !MASKED && RES_SLABS == 0),
+                "POOL: the stem kernel only");
   using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, PAIR>;
   static_assert(!PAIR || (BN >= 128 && BRES_KB == 0 && !SPLIT), "CTA pairs: streamed weight tiles, 128/256 wide");
   // Split precision keeps TWO accumulators per tile: hi*hi in one, the small cross terms lo*hi + hi*lo in the
@@ -240,7 +254,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_a);
     tma_prefetch_desc(&p.tmap_b);
-    tma_prefetch_desc(&p.tmap_out);
+    if (!POOL) tma_prefetch_desc(&p.tmap_out);
     if (p.has_res) tma_prefetch_desc(&p.tmap_res);
     if (p.mask_tma) tma_prefetch_desc(&p.tmap_mask);
     if (p.coarse_tma) tma_prefetch_desc(&p.tmap_coarse);
@@ -253,7 +267,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       // one arrive per warp draining buffer a (the leader's barrier collects both CTAs of a pair)
-      mbar_init(tempty_bar(a), (kSlabsPerTile == 1 ? 4 : 8) * (PAIR ? 2 : 1));
+      mbar_init(tempty_bar(a), ((kSlabsPerTile == 1 && !POOL) ? 4 : 8) * (PAIR ? 2 : 1));
     }
     for (int s = 0; s < kRB; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -287,9 +301,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
   // tile schedule: CTA (or pair) t takes tiles t, t + step, ...; a pair's tile is two consecutive m-tiles, the
   // rank picks one (the last pair of an odd count re-loads the last valid tile and stores nothing)
-  const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int num_tiles = (PAIR ? (p.num_m_tiles + 1) >> 1 : p.num_m_tiles) * p.num_n_tiles;
+  // POOL: this CTA's contiguous range [pool_g0, pool_g1) of (image, strip, pooled row) units; a run of pooled rows
+  // [pa, pb) of one strip takes the conv rows 2 pa - 1 .. 2 pb - 1 in order (one tile each)
+  int pool_g0 = 0, pool_g1 = 0, pool_tiles = 0;
+  if (POOL) {
+    const long long total = static_cast<long long>(p.num_m_tiles);  // = images * strips * pool_h
+    pool_g0 = static_cast<int>(total * blockIdx.x / gridDim.x);
+    pool_g1 = static_cast<int>(total * (blockIdx.x + 1) / gridDim.x);
+    for (int g = pool_g0; g < pool_g1;) {
+      const int pa = g % p.pool_h;
+      const int len = min(p.pool_h - pa, pool_g1 - g);
+      pool_tiles += 2 * len + 1;
+      g += len;
+    }
+  }
+  const int tile0 = POOL ? 0 : PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = POOL ? 1 : PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int num_tiles = POOL ? pool_tiles : (PAIR ? (p.num_m_tiles + 1) >> 1 : p.num_m_tiles) * p.num_n_tiles;
   auto m_tile_of = [&](int tile) {
     const int mt = tile / p.num_n_tiles;
     return PAIR ? 2 * mt + static_cast<int>(cta_rank) : mt;
@@ -336,6 +364,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           __syncwarp();
           if (++stage == kPatchStages) { stage = 0; phase ^= 1u; }
         }
+      }
+    } else if (POOL) {
+      for (int g = pool_g0; g < pool_g1;) {
+        const int unit = g / p.pool_h;
+        const int pa = g - unit * p.pool_h;
+        const int len = min(p.pool_h - pa, pool_g1 - g);
+        const int img = unit / p.tiles_w;
+        const int strip = unit - img * p.tiles_w;
+        for (int r = 2 * pa - 1; r <= 2 * (pa + len) - 1; ++r) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full_bar(stage), stage_tx);
+            // 7 staged rows x 272 px from staged pixel 2 * (112 strip - 8), staged row 2 r (out of range: zeros)
+            tma_load_4d(smem_a + stage * kABytes, &p.tmap_a, full_bar(stage), 0, 2 * kPoolStep / 8 * strip - 1, 2 * r,
+                        img);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        g += len;
       }
     } else
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -488,18 +536,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t d_tmem = d_main + (v != 0 ? static_cast<uint32_t>(BN) : 0u);
         const int kb_first = (v != 0) ? kcn : 0;  // first k-block that writes this accumulator
         if (lane == 0) {
-          if (BRES_KB > 0 && p.a_mode == A_STEM2) {
+          if (BRES_KB == 7 && p.a_mode == A_STEM2) {  // (the stem's seven filter rows are its resident k-blocks)
             // Row i of the A operand is the 8-pixel x 4-channel window starting at staged pixel 2*i:
             // an un-swizzled K-major view whose rows are 16 bytes apart and OVERLAP (the second
             // 8-element K chunk of row i is the first chunk of row i+1): LBO = 16 B, SBO = 128 B.
-            const uint32_t a0 = smem_a + stage * kABytes;
-            for (int r = 0; r < p.num_kb_b; ++r) {
-              const uint64_t db = make_smem_desc_sw128(smem_b + r * L::kBBytes);
+            // (one thread issues 14 MMAs of ~32 tensor cycles each: the descriptors are base + constant, so that
+            // the issue loop stays shorter than the MMAs it feeds)
+            const uint64_t da0 = make_smem_desc_nosw(smem_a + stage * kABytes, 16, 128);
+            const uint64_t db0 = make_smem_desc_sw128(smem_b);
+            const uint32_t row16 = static_cast<uint32_t>(p.stem_row_bytes) >> 4;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const uint64_t da = make_smem_desc_nosw(a0 + r * p.stem_row_bytes + k * 32, 16, 128);
-                umma_bf16_ss(d_tmem, da, db + 2u * k, idesc, (r | k) != 0 ? 1u : 0u);
-              }
+            for (int r = 0; r < 7; ++r) {
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_bf16_ss(d_tmem, da0 + (r * row16 + 2u * k), db0 + (r * (L::kBBytes >> 4) + 2u * k), idesc,
+                             (r | k) != 0 ? 1u : 0u);
             }
           } else {
             const uint64_t da = make_smem_desc_sw128(smem_a + stage * kABytes);
@@ -641,10 +692,127 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const float mul_co = ldexpf(1.0f, e_co - e_out);
     float amax_local = 0.0f;
 
+    if (POOL) {
+      // ---- stem + 3x3/2 max-pool: this group owns channels [32 group, 32 group + 32) of every conv row.
+      // Vertical max in registers (each thread keeps the packed previous two rows of its own pixel), horizontal
+      // max through one shared-memory row (double buffered: one named barrier per pooled row).
+      const uint32_t vbuf = smem_out_g;  // two 128 px x 64 B rows (the group's staging slabs are free)
+      for (int i = gtid; i < 64; i += kEpiGroupThreads) {
+        s_scale[i] = (p.scale ? __ldg(p.scale + i) : 1.0f) * mul_in;
+        s_shift[i] = (p.shift ? __ldg(p.shift + i) : 0.0f) * mul_shift;
+      }
+      named_bar_sync(gbar, kEpiGroupThreads);
+      uint8_t* const out = static_cast<uint8_t*>(p.pool_out);
+      uint32_t amax_pk = 0;  // running max of the packed (non-negative) outputs, both 16-bit halves
+      int pseq = 0;
+      int vb = 0;
+      // Accumulator rows are fetched one tile ahead (two register buffers): the TMEM read latency and the wait for
+      // the MMA hide behind the arithmetic of the previous row, and the accumulator is handed back early.
+      int ld_acc = 0;
+      auto issue_ld = [&](uint32_t (&v)[32]) {
+        ld_acc = pseq & 1;
+        mbar_wait(tfull_bar(ld_acc), static_cast<uint32_t>(pseq >> 1) & 1u);
+        ++pseq;
+        tc_fence_after();
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(ld_acc * kAccStride + group * 32), v);
+      };
+      auto finish_ld = [&]() {
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(ld_acc));
+      };
+      // one conv row of this thread's pixel: BN + ReLU, packed to 16 x (2 x 16 bit); zeros outside the image
+      auto conv_row = [&](const uint32_t (&v)[32], int r, int col, uint32_t (&o)[16]) {
+        if (r >= 0 && r < p.Ho && col >= 0 && col < p.Wo) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + group * 32 + 4 * j);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + group * 32 + 4 * j);
+            // (PTX max: max(-0, +0) = +0, so the packed values order like unsigned integers)
+            o[2 * j] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.0f),
+                                fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.0f), out_fp16);
+            o[2 * j + 1] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.0f),
+                                    fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.0f), out_fp16);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = 0u;
+        }
+      };
+      for (int g = pool_g0; g < pool_g1;) {
+        const int unit = g / p.pool_h;
+        const int pa = g - unit * p.pool_h;
+        const int len = min(p.pool_h - pa, pool_g1 - g);
+        const int img = unit / p.tiles_w;
+        const int strip = unit - img * p.tiles_w;
+        const int col = 2 * kPoolStep * strip - 8 + row;  // conv column of this thread's accumulator row
+        uint32_t va[32], vb2[32];
+        uint32_t prev[16], vm[16];
+        issue_ld(va);                 // row 2 pa - 1
+        finish_ld();
+        issue_ld(vb2);                // row 2 pa
+        conv_row(va, 2 * pa - 1, col, prev);
+        for (int pr = pa; pr < pa + len; ++pr) {
+          finish_ld();
+          issue_ld(va);               // row 2 pr + 1
+          conv_row(vb2, 2 * pr, col, vm);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) vm[j] = __vmaxu2(vm[j], prev[j]);
+          finish_ld();
+          if (pr + 1 < pa + len) issue_ld(vb2);  // row 2 pr + 2
+          conv_row(va, 2 * pr + 1, col, prev);
+          const uint32_t dst = vbuf + static_cast<uint32_t>(vb) * 8192u + row * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 m;
+            m.x = __vmaxu2(vm[4 * j], prev[4 * j]);
+            m.y = __vmaxu2(vm[4 * j + 1], prev[4 * j + 1]);
+            m.z = __vmaxu2(vm[4 * j + 2], prev[4 * j + 2]);
+            m.w = __vmaxu2(vm[4 * j + 3], prev[4 * j + 3]);
+            amax_pk = __vmaxu2(amax_pk, __vmaxu2(__vmaxu2(m.x, m.y), __vmaxu2(m.z, m.w)));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ ((row >> 1) & 3)) << 4)),
+                         "r"(m.x), "r"(m.y), "r"(m.z), "r"(m.w)
+                         : "memory");
+          }
+          named_bar_sync(gbar, kEpiGroupThreads);
+          // pooled row pr: horizontal max over conv columns 2q-1 .. 2q+1 (this strip's rows 2 ql + 7 .. + 9)
+          const uint32_t rb = vbuf + static_cast<uint32_t>(vb) * 8192u;
+          for (int it = gtid; it < kPoolStep * 4; it += kEpiGroupThreads) {
+            const int ql = it >> 2, c = it & 3;
+            const int q = kPoolStep * strip + ql;
+            if (q < p.pool_w) {
+              uint4 t[3];
+#pragma unroll
+              for (int dc = 0; dc < 3; ++dc) {
+                const int i = 2 * ql + 7 + dc;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(t[dc].x), "=r"(t[dc].y), "=r"(t[dc].z), "=r"(t[dc].w)
+                             : "r"(rb + i * 64 + ((c ^ ((i >> 1) & 3)) << 4)));
+              }
+              uint4 m;
+              m.x = __vmaxu2(__vmaxu2(t[0].x, t[1].x), t[2].x);
+              m.y = __vmaxu2(__vmaxu2(t[0].y, t[1].y), t[2].y);
+              m.z = __vmaxu2(__vmaxu2(t[0].z, t[1].z), t[2].z);
+              m.w = __vmaxu2(__vmaxu2(t[0].w, t[1].w), t[2].w);
+              stg_v4(out + ((static_cast<long long>(img) * p.pool_h + pr) * p.pool_w + q) * 128 + group * 64 + c * 16, m);
+            }
+          }
+          vb ^= 1;  // (the other buffer was last read before this row's barrier)
+        }
+        g += len;
+      }
+      {
+        float lo, hi;
+        unpack16x2(amax_pk, out_fp16, lo, hi);
+        amax_local = fmaxf(lo, hi);
+      }
+    }
     int cur_n_tile = -1;
     int ob = 0;  // staging buffer of the next slab
     int seq = 0; // CTA-local tile counter: tile seq accumulates in TMEM buffer seq & 1
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, ++seq) {
+    for (int tile = POOL ? num_tiles : tile0; tile < num_tiles; tile += tile_step, ++seq) {
       if (kByTile && (seq & 1) != group) continue;
       const int acc = kAccBufs == 2 ? (seq & 1) : 0;
       const uint32_t acc_phase = static_cast<uint32_t>(kAccBufs == 2 ? (seq >> 1) : seq) & 1u;

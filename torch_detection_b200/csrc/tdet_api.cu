@@ -128,6 +128,7 @@ struct Launch {
   int bn = 0, stages = 0, res_slabs = 0, bres_kb = 0, oslabs = 1;
   bool patch = false;
   bool pair = false;      // CTA-pair kernel (clusters of 2)
+  bool pool = false;      // stem kernel with the fused max-pool
   bool no_patch = false;  // debugging hook: force the im2col loader
   // wgrad
   WgradParams wp{};
@@ -331,8 +332,27 @@ constexpr int vkey(int bn, int stages, int res, int bres, int os) {
   return (((bn * 16 + stages) * 16 + res) * 16 + bres) * 4 + os;
 }
 
+template <int STAGES>
+int launch_gemm_pool_t(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
+  using L = GemmSmem<64, STAGES, 0, 7, false, 1>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  TDET_CUDA(cudaGetDevice(&dev));
+  auto kernel = conv_gemm_kernel<64, STAGES, 0, 7, false, 1, false, false, false, true>;
+  if (!attr_set[dev]) {
+    TDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    attr_set[dev] = true;
+  }
+  return launch_pdl(kernel, grid, kGemmThreadsNoPatch, L::kDynamic, st, gp);
+}
+int launch_gemm_pool(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
+  // (ring depth 4 vs 8 measured equal: the kernel is bound by the ~80 cycles every N = 64 MMA instruction takes)
+  return launch_gemm_pool_t<8>(gp, grid, st);
+}
+
 int launch_gemm(const Launch& l, cudaStream_t st) {
   const int v = l.bn * 1000000 + l.stages * 10000 + l.res_slabs * 100 + l.bres_kb;
+  if (l.pool) return launch_gemm_pool(l.gp, l.grid, st);
   if (l.gp.split) {
     switch (vkey(l.bn, l.stages, l.res_slabs, 0, 2)) {
       case vkey(64, 5, 2, 0, 2): return launch_gemm_split<64, 5, 2>(l.gp, l.grid, st);
@@ -864,6 +884,10 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
   const bool split = (o.flags & TDET_FLAG_SPLIT) != 0;  // staged batch = 2n planes (hi, lo); y = 128 channels (hi | lo)
   const bool v2 = stem_version() >= 2 && !split;        // split precision streams the weights: window-gather path
+  const bool pool = (o.flags & TDET_FLAG_POOL) != 0;
+  if (pool && (!v2 || !(o.flags & TDET_FLAG_RELU) || !is16(o.y_dtype)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "stem: TDET_FLAG_POOL needs the linear-row kernel (no split precision), "
+                                            "TDET_FLAG_RELU and a 16-bit output");
   const int bw = v2 ? kStem2BW : kStemBW, bh = v2 ? 1 : kStemBH;
   ConvGemmParams& gp = l.gp;
   memset(&gp, 0, sizeof(gp));
@@ -889,6 +913,15 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   gp.num_m_tiles = o.n * gp.tiles_w * gp.tiles_h;
   gp.num_n_tiles = 1;
   gp.M = gp.num_m_tiles * kBM;
+  if (pool) {
+    // work units = (image, 56-pooled-column strip, pooled row); the kernel derives the conv-row tiles of its range
+    gp.pool_h = out_dim(o.ho, 3, 2, 1, 1);
+    gp.pool_w = out_dim(o.wo, 3, 2, 1, 1);
+    gp.pool_out = o.y;
+    gp.tiles_w = (gp.pool_w + kPoolStep - 1) / kPoolStep;
+    gp.num_m_tiles = o.n * gp.tiles_w * gp.pool_h;
+  }
+  l.pool = pool;
   gp.ab_fp16 = 0;
   gp.num_kb_b = 7;
   gp.a_stage_bytes = kABytes;
@@ -943,7 +976,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
       return fail(TDET_ERR_DRIVER, "cuTensorMapEncodeTiled(stem A) failed: %d", static_cast<int>(r));
   }
   // output [n][ho][wo][64] as (c, w, h, n); a 128-row staging slab is a (64, 32, 4, 1) box
-  {
+  if (!pool) {
     const cuuint64_t cb = split ? 256 : 128;  // bytes per output pixel: 64 channels, or 64 hi + 64 lo
     cuuint64_t dims[4] = {cb / 2, static_cast<cuuint64_t>(o.wo), static_cast<cuuint64_t>(o.ho),
                           static_cast<cuuint64_t>(o.n)};
@@ -963,7 +996,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.flops = 2.0 * static_cast<double>(o.n) * o.ho * o.wo * 64.0 * 147.0;
   l.bytes = 2.0 * (static_cast<double>(o.n) * hp * wp * 4 + 64.0 * 448 +
-                   static_cast<double>(o.n) * o.ho * o.wo * 64);
+                   static_cast<double>(o.n) * (pool ? gp.pool_h * gp.pool_w : o.ho * o.wo) * 64);
   return TDET_OK;
 }
 

@@ -325,12 +325,14 @@ def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, s
     return op
 
 
-def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False, split=False):
-    """x: staged image buffer (bf16); y: ``Act`` of shape (n, ho, wo, 64)."""
+def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False, split=False,
+            pool=False):
+    """x: staged image buffer (bf16); y: ``Act`` of shape (n, ho, wo, 64) -- with ``pool`` the kernel also
+    applies the 3x3/2 max-pool and y is the pooled (n, (ho-1)//2+1, (wo-1)//2+1, 64)."""
     op = _C.TdetOp()
     op.kind = _C.OP_STEM
     op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
-        (_C.FLAG_SPLIT if split else 0)
+        (_C.FLAG_SPLIT if split else 0) | (_C.FLAG_POOL if pool else 0)
     op.n, op.h, op.w, op.cin = n, h, w, 3
     op.cout, op.kh, op.kw = 64, 7, 7
     op.stride, op.pad, op.dil = 2, 3, 1

@@ -360,7 +360,11 @@ class ResNet(nn.Module):
                     staged_meta = None if split else meta.new()
                     ops.append(engine.op_prep(x[i0:i0 + cn], staged, ho, wo, y_meta=staged_meta, scale=tf_scale,
                                               shift=tf_shift, padded_hw=(h, w), split=split))
-                    stem_out = new_act((cn, ho, wo, 64), internal)
+                    keep_stem = train and getattr(self, "_train_stem", False)
+                    # the stem kernel max-pools in its epilogue unless the pre-pool activation is needed
+                    # (stem training) or the tensors are bf16 pairs (fp32-I/O mode)
+                    fuse_pool = FUSE_STEM_POOL and not split and not keep_stem
+                    stem_out = None if fuse_pool else new_act((cn, ho, wo, 64), internal)
                     stem_bn = getattr(self, self.norm_name)
                     if split:
                         stem_w = cache.get(("conv1", "wsplit"),
@@ -375,18 +379,23 @@ class ResNet(nn.Module):
                     stem_consts = cache.get(("conv1", "consts"),
                                             lambda out: engine.bound_consts(stem_w, sc, sh, out=out),
                                             deps=(self.conv1.weight,) + _bn_deps(stem_bn)) if scaled else None
-                    ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh,
-                                              x_meta=staged_meta, consts=stem_consts, scaled_out=scaled, split=split))
-                    keep_stem = train and getattr(self, "_train_stem", False)
-                    if not keep_stem:
+                    if fuse_pool:
+                        cur = engine.Act(pool.get((cn, hq, wq, 64)), (cn, hq, wq, 64), internal, meta.new())
+                        ops.append(engine.op_stem(cn, h, w, staged, stem_w, cur, sc, sh, x_meta=staged_meta,
+                                                  consts=stem_consts, scaled_out=scaled, pool=True))
                         pool.release(staged)
-                    # max-pool commutes with the (positive) per-tensor scale: metadata passes through
-                    cur = engine.Act(pool.get((cn, hq, wq, 64 * cs)), (cn, hq, wq, 64), internal, stem_out.meta)
-                    ops.append(engine.op_maxpool(stem_out, cur, split=split))
-                    if keep_stem:
-                        stem_rec = dict(staged=staged, stem_out=stem_out, h=h, w=w)  # saved for the stem's backward
                     else:
-                        pool.release(stem_out.buf)
+                        ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh, x_meta=staged_meta,
+                                                  consts=stem_consts, scaled_out=scaled, split=split))
+                        if not keep_stem:
+                            pool.release(staged)
+                        # max-pool commutes with the (positive) per-tensor scale: metadata passes through
+                        cur = engine.Act(pool.get((cn, hq, wq, 64 * cs)), (cn, hq, wq, 64), internal, stem_out.meta)
+                        ops.append(engine.op_maxpool(stem_out, cur, split=split))
+                        if keep_stem:
+                            stem_rec = dict(staged=staged, stem_out=stem_out, h=h, w=w)  # saved for the stem's backward
+                        else:
+                            pool.release(stem_out.buf)
                     cur_pooled = True
                 else:
                     cur = boundary_act(stages[0] - 1, i0, cn)
@@ -823,6 +832,8 @@ INTERNAL_DTYPE = torch.bfloat16 if os.environ.get("TDET_INTERNAL_DTYPE", "fp16")
 # fp32 inputs in eval mode run the split-precision path (fp32-I/O tolerance 1e-4, ~3x the MMA work and 2x the
 # bytes); TDET_FP32_IO=bf16 keeps fp32 tensors at the module boundary only (bf16-accurate, fast).
 FP32_IO_SPLIT = os.environ.get("TDET_FP32_IO", "split").lower() == "split"
+# the stem kernel applies the 3x3/2 max-pool in its epilogue (TDET_FLAG_POOL); 0 = separate TDET_OP_MAXPOOL launch
+FUSE_STEM_POOL = os.environ.get("TDET_STEM_POOL", "1") != "0"
 
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
