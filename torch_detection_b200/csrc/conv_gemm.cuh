@@ -198,6 +198,10 @@ __device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool fp16) {
 // the re-read of the 64 x H/2 x W/2 stem output (1.1 GB per batch of 16 at 800x1344) and the pooling launch.
 constexpr int kPoolStep = 56;  // pooled columns per strip
 
+#ifndef TDET_MMA_SINGLE_THREAD
+#define TDET_MMA_SINGLE_THREAD 0
+#endif
+
 template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false,
           bool PAIR = false, bool POOL = false>
 __global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
@@ -464,6 +468,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // kSingle: ONE thread runs the whole issue loop (no per-step warp reconvergence on the critical path)
+    constexpr bool kSingle = TDET_MMA_SINGLE_THREAD != 0;
+    if (!kSingle || lane == 0) {
     const uint32_t idesc = make_idesc_f16kind(PAIR ? 2 * kBM : kBM, BN, p.ab_fp16 ? kFmtF16 : kFmtBF16,
                                               p.b_fp16 ? kFmtF16 : kFmtBF16);
     int stage = 0;
@@ -471,6 +478,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     if (BRES_KB > 0) mbar_wait(bres_bar, 0);
+    // descriptor bases: an operand tile at byte offset x is base + (x >> 4)
+    const uint64_t da0 = make_smem_desc_sw128(smem_a);
+    const uint64_t db0 = make_smem_desc_sw128(smem_b);
+    const uint64_t da_patch0 = make_smem_desc_sw128_sbo(smem_a, kPatchPW * 128);
     if (PATCH) {
       int as = 0;
       uint32_t aphase = 0;
@@ -483,17 +494,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(afull_bar(as), aphase);
           tc_fence_after();
-          const uint32_t a0 = smem_a + as * kPatchStageBytes;
+          // (the issuing thread must stay ahead of 128-/64-wide MMAs of 64 / 32 tensor cycles: descriptors are
+          // base + immediate, the tap loop is unrolled)
+          const uint64_t da_patch = da_patch0 + static_cast<uint32_t>(as * (kPatchStageBytes >> 4));
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             if (BRES_KB == 0) {
               mbar_wait(full_bar(stage), phase);
               tc_fence_after();
             }
-            if (lane == 0) {
-              const int r = tap / 3, sx = tap - 3 * r;
-              const uint64_t da = make_smem_desc_sw128_sbo(a0 + (r * kPatchPW + sx) * 128, kPatchPW * 128);
-              const uint64_t db = make_smem_desc_sw128(
-                  smem_b + (BRES_KB > 0 ? tap * p.k_chunks + kc : stage) * L::kBBytes);
+            if (kSingle || lane == 0) {
+              const uint64_t da = da_patch + static_cast<uint32_t>(((tap / 3) * kPatchPW + tap % 3) * 8);
+              const uint64_t db = db0 + static_cast<uint32_t>((BRES_KB > 0 ? tap * p.k_chunks + kc : stage) *
+                                                              (L::kBBytes >> 4));
 #pragma unroll
               for (int k = 0; k < kBK / kUmmaK; ++k) {
                 if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2u * k, db + 2u * k, idesc, ((kc - kc_lo) | tap | k) != 0 ? 1u : 0u);
@@ -513,7 +526,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 }
               }
             }
-            __syncwarp();
+            if (!kSingle) __syncwarp();
             if (BRES_KB == 0) {
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -535,7 +548,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int v = (nv == 3) ? (kb / kcn) % 3 : 0;
         const uint32_t d_tmem = d_main + (v != 0 ? static_cast<uint32_t>(BN) : 0u);
         const int kb_first = (v != 0) ? kcn : 0;  // first k-block that writes this accumulator
-        if (lane == 0) {
+        if (kSingle || lane == 0) {
           if (BRES_KB == 7 && p.a_mode == A_STEM2) {  // (the stem's seven filter rows are its resident k-blocks)
             // Row i of the A operand is the 8-pixel x 4-channel window starting at staged pixel 2*i:
             // an un-swizzled K-major view whose rows are 16 bytes apart and OVERLAP (the second
@@ -553,8 +566,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                              (r | k) != 0 ? 1u : 0u);
             }
           } else {
-            const uint64_t da = make_smem_desc_sw128(smem_a + stage * kABytes);
-            const uint64_t db = make_smem_desc_sw128(smem_b + (BRES_KB > 0 ? kb : stage) * L::kBBytes);
+            const uint64_t da = da0 + static_cast<uint32_t>(stage * (kABytes >> 4));
+            const uint64_t db = db0 + static_cast<uint32_t>((BRES_KB > 0 ? kb : stage) * (L::kBBytes >> 4));
 #pragma unroll
             for (int k = 0; k < kBK / kUmmaK; ++k) {
               // advance 32 bytes (16 elements) along K inside the 128-byte swizzle row: +2 (16-byte units)
@@ -571,12 +584,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
           }
         }
-        __syncwarp();
+        if (!kSingle) __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if (kAccBufs == 2) acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    }
+    __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ TMA producer (residual, mask)
     // Per 64-column output slab the ring receives the residual slab (if any), then the mask slab (if it
