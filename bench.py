@@ -464,7 +464,7 @@ def main():
         peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
         traffic, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_s3_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r1_s5_traffic.json")
         if os.path.isfile(tpath) and args.depth == 50 and args.batch == 16:
             with open(tpath) as f:
                 tj = json.load(f)

@@ -9,10 +9,10 @@ ncu --nvtx --nvtx-include "tdet_step/" --metrics gpu__time_duration.sum --clock-
 echo "ncu infer list exit $?"
 ncu --nvtx --nvtx-include "tdet_step" --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_train_$R.csv python tools/profile_train.py --steps 3 > gpurun_out/ncu1t.log 2>&1
 echo "ncu train list exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 0 -c 5 -f -o gpurun_out/prof_layer1_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 0 -c 4 -f -o gpurun_out/prof_layer1_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu2.log 2>&1
 echo "ncu layer1 exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 56 -c 2 -f -o gpurun_out/prof_fpn_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_gemm -s 56 -c 4 -f -o gpurun_out/prof_fpn_$R python tools/profile_step.py --steps 1 > gpurun_out/ncu3.log 2>&1
 echo "ncu fpn exit $?"
-ncu --set full --clock-control none --import-source on -k regex:wgrad_gemm -s 0 -c 3 -f -o gpurun_out/prof_wgrad_$R python tools/profile_train.py --steps 1 > gpurun_out/ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wgrad_gemm -s 0 -c 2 -f -o gpurun_out/prof_wgrad_$R python tools/profile_train.py --steps 1 > gpurun_out/ncu4.log 2>&1
 echo "ncu wgrad exit $?"
 ls -la gpurun_out/*.ncu-rep
