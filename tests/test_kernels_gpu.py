@@ -150,6 +150,7 @@ def test_conv_op_cta_pairs(cuda_device, case, epi, monkeypatch):
     """Every eligible conv forced onto the CTA-pair kernel (clusters of two, cta_group::2 MMAs)."""
     from torch_detection_b200 import engine
     monkeypatch.setenv("TDET_PAIR", "15")
+    monkeypatch.setenv("TDET_SWAP", "0")
     name, n, h, w, cin, cout, k, stride, pad, dil = case
     dev = cuda_device
     xb = engine.nhwc_empty(n, h, w, cin, dev)
@@ -162,6 +163,32 @@ def test_conv_op_cta_pairs(cuda_device, case, epi, monkeypatch):
     if n * ho * wo > 128:
         assert info["variant"] & 8192, "conv was not scheduled on the pair kernel: %r" % (info,)
     test_conv_op(cuda_device, case, epi, torch.bfloat16)
+
+
+SWAP_CASES = [c for c in CONV_CASES if c[5] in (64, 128)] + [
+    ("1x1_256_128_ragged", 3, 37, 29, 256, 128, 1, 1, 0, 1),
+    ("3x3_128_128_two_images", 2, 40, 24, 128, 128, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", SWAP_CASES, ids=[c[0] for c in SWAP_CASES])
+@pytest.mark.parametrize("epi", ["plain", "bn_relu", "bias"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_conv_op_swapped_operands(cuda_device, case, epi, dtype, monkeypatch):
+    """Every eligible narrow conv forced onto the operand-swapped kernel (weights as the M operand, 256 pixels as N)."""
+    from torch_detection_b200 import engine
+    monkeypatch.setenv("TDET_SWAP", "3")
+    name, n, h, w, cin, cout, k, stride, pad, dil = case
+    dev = cuda_device
+    xb = engine.nhwc_empty(n, h, w, cin, dev, dtype)
+    ho, wo = engine.conv_out(h, k, stride, pad, dil), engine.conv_out(w, k, stride, pad, dil)
+    y = engine.nhwc_empty(n, ho, wo, cout, dev, dtype)
+    wp = engine.pack_conv_weight(torch.zeros(cout, cin, k, k, device=dev), dtype)
+    plan = engine.Plan([engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), k, k, stride, pad, dil)], [],
+                       [xb, y, wp], dev)
+    info = plan.launch_info()[0]
+    assert info["variant"] & 16384, "conv was not scheduled on the operand-swapped kernel: %r" % (info,)
+    test_conv_op(cuda_device, case, epi, dtype)
 
 
 @pytest.mark.parametrize("shape", [(2, 26, 44), (2, 32, 40), (1, 30, 38), (3, 64, 16)])

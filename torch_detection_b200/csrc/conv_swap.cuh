@@ -1,0 +1,258 @@
+// Operand-swapped implicit-GEMM conv for narrow outputs (Cout = 64 or 128; SURVEY.md section 8 rows a3/a5: conv1 and
+// conv2 of the bottlenecks of layer1/layer2, resnet.py:97-108).
+//
+// Measured on B200: one tcgen05.mma of M = 128, K = 16 takes ~115-145 SM cycles whatever its
+// N, because the 128 x 32 B A-operand fetch from shared memory is the fixed part.  With the output channels as N a
+// 64- or 128-wide conv therefore runs the tensor pipe at 25-50 %.  Here the roles are swapped:
+//
+//     D^T[Cout (M = 128 lanes), 256 pixels (N)] = W[Cout, K] * A[256 pixels, K]^T
+//
+// so every MMA is the full-rate 128 x 256 x 16 shape (Cout = 64: the weight tile's upper 64 rows are TMA zero fill).
+// The accumulator arrives transposed -- TMEM lane = output channel, column = pixel -- which makes the epilogue's
+// per-channel scale/shift two registers per thread; each thread converts its channel for 32 pixels at a time
+// (tcgen05.ld 32x32b.x32) and scatters 16-bit values into the [pixel][channel] 128B-swizzled staging slab (a warp's 32
+// lanes = 32 consecutive channels = 64 contiguous bytes of one pixel row: conflict-free), which leaves by TMA store.
+//
+//   warp 0      TMA producer: pixel tile (256 rows x 128 B; tiled 2D for 1x1 s1, im2col otherwise) + weight tile
+//   warp 1      one thread issues tcgen05.mma (4 per stage), commits free the stage / publish the accumulator
+//   warps 2..9  epilogue, two groups of four warps (a warp reads only TMEM lanes 32*(warp%4)..+31): group g converts
+//               pixel columns [128 g, 128 g + 128) of every tile
+// Epilogue: scale/shift (folded BN or bias), optional ReLU, 16-bit output with the optional per-tensor exponent
+// (conv_gemm.cuh header).  No residual / coarse / mask operands: the convs that need them are 256 wide.
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace tdet {
+
+constexpr int kSwapPix = 256;      // pixels per tile = UMMA N
+constexpr int kSwapThreads = 320;  // 10 warps
+
+template <int STAGES>
+struct SwapSmem {
+  static constexpr int kPixBytes = kSwapPix * 128;  // 32 KiB
+  static constexpr int kWBytes = 128 * 128;         // 16 KiB: 128 weight rows x 64 K elements
+  static constexpr int kStageBytes = kPixBytes + kWBytes;
+  static constexpr int kOutOffset = STAGES * kStageBytes;
+  static constexpr int kOutBytes = 2 * 2 * kSlabBytes;  // two groups x two 64-channel slabs of 128 pixels
+  static constexpr int kBarOffset = kOutOffset + kOutBytes;
+  static constexpr int kNumBars = 2 * STAGES + 4;
+  static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
+  static constexpr int kDynamic = kTmemPtrOffset + 16;
+  static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kSwapThreads, 1)
+conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
+  using L = SwapSmem<STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t base = smem_u32(smem);
+  if ((base & 1023u) != 0u) __trap();
+  const uint32_t smem_out = base + L::kOutOffset;
+  const uint32_t bar0 = base + L::kBarOffset;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmap_a);
+    tma_prefetch_desc(&p.tmap_b);
+    tma_prefetch_desc(&p.tmap_out);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  grid_dependency_wait();
+
+  const int num_tiles = p.num_m_tiles;  // 256-pixel tiles
+  const int num_kb = p.kh * p.kw * p.k_chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int cw = 0, ch = 0, cn = 0;
+      if (p.a_mode == A_IM2COL) {
+        const int m0 = tile * kSwapPix;
+        const int q0 = m0 % p.Wo;
+        const int t = m0 / p.Wo;
+        cn = t / p.Ho;
+        cw = q0 * p.stride - p.pad;
+        ch = (t % p.Ho) * p.stride - p.pad;
+      }
+      for (int r = 0; r < p.kh; ++r) {
+        for (int s = 0; s < p.kw; ++s) {
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (lane == 0) {
+              const uint32_t fb = full_bar(stage);
+              mbar_arrive_expect_tx(fb, L::kStageBytes);
+              const uint32_t dst = base + stage * L::kStageBytes;
+              if (p.a_mode == A_TILED)
+                tma_load_2d(dst, &p.tmap_a, fb, kc * kBK, tile * kSwapPix);
+              else
+                tma_load_im2col_4d(dst, &p.tmap_a, fb, kc * kBK, cw, ch, cn, static_cast<uint16_t>(s * p.dil),
+                                   static_cast<uint16_t>(r * p.dil));
+              // rows >= Cout of the 128-row box lie outside the weight matrix: zero fill
+              tma_load_2d(dst + L::kPixBytes, &p.tmap_b, fb, (r * p.kw + s) * p.b_tap_stride + kc * kBK, 0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      // A operand = weights (M = 128 rows), B operand = pixels (N = 256 rows); both K-major SWIZZLE_128B tiles
+      const uint32_t idesc = make_idesc_f16kind(128, kSwapPix, p.b_fp16 ? kFmtF16 : kFmtBF16,
+                                                p.ab_fp16 ? kFmtF16 : kFmtBF16);
+      const uint64_t dpix0 = make_smem_desc_sw128(base);
+      const uint64_t dw0 = make_smem_desc_sw128(base + L::kPixBytes);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kSwapPix);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t off = static_cast<uint32_t>(stage * (L::kStageBytes >> 4));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_bf16_ss(d_tmem, dw0 + (off + 2u * k), dpix0 + (off + 2u * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may access
+    const int group = (warp - 2) >> 2;      // pixel columns [128 group, 128 group + 128) of every tile
+    const int gtid = (threadIdx.x - 64) & (kEpiGroupThreads - 1);
+    const uint32_t gbar = 1u + group;
+    const bool issuer = gtid == 0;
+    const int c = quad * 32 + lane;         // output channel of this thread
+    const bool active = quad * 32 < p.N;    // warp-uniform: channels [32 quad, 32 quad + 32) exist
+    const bool out_fp16 = p.out_fp16 != 0;
+    const int slabs = p.N / 64;             // 1 or 2 staging slabs per group
+    const uint32_t stage_g = smem_out + group * 2 * kSlabBytes;
+
+    const int e_in = p.in_meta ? p.in_meta->e : 0;
+    int e_out = 0;
+    if (p.out_scaled) {
+      float bound = p.bound_consts[1];
+      const float a_in = p.in_meta ? __uint_as_float(p.in_meta->amax_bits) : 0.0f;
+      bound += p.bound_consts[0] * a_in;
+      if (bound > 0.0f && bound < 3.0e38f) e_out = ilogbf(bound) - 14;
+      e_out = max(-100, min(100, e_out));
+      if (blockIdx.x == 0 && threadIdx.x == 64) p.out_meta->e = e_out;
+    }
+    const float sc = active ? (p.scale ? __ldg(p.scale + c) : 1.0f) * ldexpf(1.0f, e_in - e_out) : 0.0f;
+    const float sh = active ? (p.shift ? __ldg(p.shift + c) : 0.0f) * ldexpf(1.0f, -e_out) : 0.0f;
+    // staging address of (pixel row 0, this channel): slab c/64, 16-byte chunk (c%64)/8 (XOR-swizzled per row)
+    const uint32_t st_base = stage_g + (c >> 6) * kSlabBytes + (c & 7) * 2;
+    const int chunk16 = (c & 63) >> 3;
+    float amax_local = 0.0f;
+
+    int seq = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+      const int acc = seq & 1;
+      const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
+      const int m0 = tile * kSwapPix + group * 128;  // first pixel of this group's half
+      // the staging slabs were last read by the TMA store of the previous tile
+      if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      named_bar_sync(gbar, kEpiGroupThreads);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (active) {
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                static_cast<uint32_t>(acc * kSwapPix + group * 128);
+#pragma unroll 1
+        for (int ck = 0; ck < 4; ++ck) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + ck * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int pr = ck * 32 + i;  // pixel row inside the group's 128
+            float y = fmaf(__uint_as_float(v[i]), sc, sh);
+            if (p.relu) y = fmaxf(y, 0.0f);
+            if (m0 + pr < p.M) amax_local = fmaxf(amax_local, fabsf(y));
+            uint16_t h;
+            if (out_fp16) {
+              const __half hh = __float2half_rn(y);
+              h = *reinterpret_cast<const uint16_t*>(&hh);
+            } else {
+              const __nv_bfloat16 bb = __float2bfloat16_rn(y);
+              h = *reinterpret_cast<const uint16_t*>(&bb);
+            }
+            const uint32_t a = st_base + pr * 128 + ((chunk16 ^ (pr & 7)) << 4);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete: hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      fence_proxy_async_smem();
+      named_bar_sync(gbar, kEpiGroupThreads);
+      if (issuer && m0 < p.M) {
+        for (int s = 0; s < slabs; ++s)
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(stage_g + s * kSlabBytes), "r"(s * 64),
+                       "r"(m0)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (p.out_meta) {
+      float a = amax_local;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+      if (lane == 0) atomicMax(&p.out_meta->amax_bits, __float_as_uint(ldexpf(a, e_out)));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace tdet
