@@ -168,6 +168,9 @@ def test_conv_op_cta_pairs(cuda_device, case, epi, monkeypatch):
 SWAP_CASES = [c for c in CONV_CASES if c[5] in (64, 128)] + [
     ("1x1_256_128_ragged", 3, 37, 29, 256, 128, 1, 1, 0, 1),
     ("3x3_128_128_two_images", 2, 40, 24, 128, 128, 3, 1, 1, 1),
+    ("3x3_64_64_halo_patch", 2, 64, 40, 64, 64, 3, 1, 1, 1),           # 8 x 32 spatial tiles, no waste
+    ("3x3_128_128_halo_patch_ragged", 1, 60, 38, 128, 128, 3, 1, 1, 1),  # 12 % waste, clipped stores
+    ("3x3_256_128_halo_patch", 3, 32, 16, 256, 128, 3, 1, 1, 1),       # four channel chunks per tile
 ]
 
 

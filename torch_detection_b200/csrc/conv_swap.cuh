@@ -19,32 +19,44 @@
 //               pixel columns [128 g, 128 g + 128) of every tile
 // Epilogue: scale/shift (folded BN or bias), optional ReLU, 16-bit output with the optional per-tensor exponent
 // (conv_gemm.cuh header).  No residual / coarse / mask operands: the convs that need them are 256 wide.
+//
+// PATCH (3x3, stride 1, pad 1): a tile is 8 x 32 output pixels; ONE (8+2) x (32+2)-pixel halo patch per 64-channel
+// chunk is loaded (4D tiled TMA, zero-filled padding) and the nine taps are nine shifted pixel-operand descriptors
+// over it (8-pixel row groups 10 rows apart: SBO = 1280 B), so the activations are read 1.3x instead of 9x; the
+// weight tiles stream through their own ring.
 #pragma once
 #include "conv_gemm.cuh"
 
 namespace tdet {
 
 constexpr int kSwapPix = 256;      // pixels per tile = UMMA N
-constexpr int kSwapThreads = 320;  // 10 warps
+constexpr int kSwapThreads = 352;  // 11 warps (warp 10: weight producer of the PATCH mode)
+constexpr int kSwapPW = 8, kSwapPH = 32;                     // PATCH: output pixels per tile
+constexpr int kSwapHaloW = kSwapPW + 2, kSwapHaloH = kSwapPH + 2;
+constexpr int kSwapPatchBytes = kSwapHaloW * kSwapHaloH * 128;                  // 43 520
+constexpr int kSwapPatchStage = (kSwapPatchBytes + 1023) / 1024 * 1024;         // 44 032
+constexpr int kSwapPatchStages = 2;
 
-template <int STAGES>
+// !PATCH: STAGES x (pixel tile + weight tile).  PATCH: two halo patches, then STAGES weight tiles.
+template <int STAGES, bool PATCH>
 struct SwapSmem {
   static constexpr int kPixBytes = kSwapPix * 128;  // 32 KiB
   static constexpr int kWBytes = 128 * 128;         // 16 KiB: 128 weight rows x 64 K elements
-  static constexpr int kStageBytes = kPixBytes + kWBytes;
-  static constexpr int kOutOffset = STAGES * kStageBytes;
+  static constexpr int kStageBytes = PATCH ? kWBytes : kPixBytes + kWBytes;
+  static constexpr int kWOffset = PATCH ? kSwapPatchStages * kSwapPatchStage : kPixBytes;  // first weight tile
+  static constexpr int kOutOffset = (PATCH ? kSwapPatchStages * kSwapPatchStage : 0) + STAGES * kStageBytes;
   static constexpr int kOutBytes = 2 * 2 * kSlabBytes;  // two groups x two 64-channel slabs of 128 pixels
   static constexpr int kBarOffset = kOutOffset + kOutBytes;
-  static constexpr int kNumBars = 2 * STAGES + 4;
+  static constexpr int kNumBars = 2 * STAGES + 4 + 2 * kSwapPatchStages;
   static constexpr int kTmemPtrOffset = kBarOffset + kNumBars * 8;
   static constexpr int kDynamic = kTmemPtrOffset + 16;
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
 };
 
-template <int STAGES>
+template <int STAGES, bool PATCH = false>
 __global__ void __launch_bounds__(kSwapThreads, 1)
 conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = SwapSmem<STAGES>;
+  using L = SwapSmem<STAGES, PATCH>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t base = smem_u32(smem);
   if ((base & 1023u) != 0u) __trap();
@@ -54,6 +66,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+  auto afull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
+  auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kSwapPatchStages + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kTmemPtrOffset);
 
   const int warp = threadIdx.x >> 5;
@@ -72,6 +86,10 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);  // one arrive per epilogue warp
+    }
+    for (int s = 0; s < kSwapPatchStages; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
     }
     fence_mbar_init();
   }
@@ -92,6 +110,26 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    if (PATCH) {
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tw = tile % p.tiles_w;
+        const int t = tile / p.tiles_w;
+        const int th = t % p.tiles_h;
+        const int img = t / p.tiles_h;
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(aempty_bar(as), aphase ^ 1u);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(afull_bar(as), kSwapPatchBytes);
+            tma_load_4d(base + as * kSwapPatchStage, &p.tmap_a, afull_bar(as), kc * kBK, tw * kSwapPW - 1,
+                        th * kSwapPH - 1, img);
+          }
+          __syncwarp();
+          if (++as == kSwapPatchStages) { as = 0; aphase ^= 1u; }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int cw = 0, ch = 0, cn = 0;
       if (p.a_mode == A_IM2COL) {
@@ -124,6 +162,27 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ TMA producer (weights, PATCH mode): its own
+    // warp, so that the next tile's halo patch is requested a whole tile ahead instead of behind nine weight tiles
+    if (PATCH) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(full_bar(stage), L::kWBytes);
+              tma_load_2d(base + L::kWOffset + stage * L::kStageBytes, &p.tmap_b, full_bar(stage),
+                          tap * p.b_tap_stride + kc * kBK, 0);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
@@ -136,6 +195,41 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (PATCH) {
+        const uint64_t dpatch0 = make_smem_desc_sw128_sbo(base, kSwapHaloW * 128);
+        const uint64_t dwp0 = make_smem_desc_sw128(base + L::kWOffset);
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kSwapPix);
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(afull_bar(as), aphase);
+            tc_fence_after();
+            const uint64_t dpatch = dpatch0 + static_cast<uint32_t>(as * (kSwapPatchStage >> 4));
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(full_bar(stage), phase);
+              tc_fence_after();
+              const uint64_t dpx = dpatch + static_cast<uint32_t>(((tap / 3) * kSwapHaloW + tap % 3) * 8);
+              const uint64_t dw = dwp0 + static_cast<uint32_t>(stage * (L::kStageBytes >> 4));
+#pragma unroll
+              for (int k = 0; k < kBK / kUmmaK; ++k)
+                umma_bf16_ss(d_tmem, dw + 2u * k, dpx + 2u * k, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              umma_commit(empty_bar(stage));
+              if (tap == 8) {
+                umma_commit(aempty_bar(as));
+                if (kc == p.k_chunks - 1) umma_commit(tfull_bar(acc));
+              }
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (++as == kSwapPatchStages) { as = 0; aphase ^= 1u; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      } else
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
@@ -191,6 +285,15 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
       const int acc = seq & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
       const int m0 = tile * kSwapPix + group * 128;  // first pixel of this group's half
+      // PATCH: this group's half is rows [16 group, 16 group + 16) x 8 columns of the 8 x 32 spatial tile
+      int ptw = 0, pth = 0, pimg = 0;
+      if (PATCH) {
+        ptw = tile % p.tiles_w;
+        const int t = tile / p.tiles_w;
+        pth = t % p.tiles_h;
+        pimg = t / p.tiles_h;
+      }
+      const int h0 = pth * kSwapPH + group * 16, w0 = ptw * kSwapPW;
       // the staging slabs were last read by the TMA store of the previous tile
       if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       named_bar_sync(gbar, kEpiGroupThreads);
@@ -209,7 +312,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
             const int pr = ck * 32 + i;  // pixel row inside the group's 128
             float y = fmaf(__uint_as_float(v[i]), sc, sh);
             if (p.relu) y = fmaxf(y, 0.0f);
-            if (m0 + pr < p.M) amax_local = fmaxf(amax_local, fabsf(y));
+            const bool ok = PATCH ? (h0 + (pr >> 3) < p.Ho && w0 + (pr & 7) < p.Wo) : (m0 + pr < p.M);
+            if (ok) amax_local = fmaxf(amax_local, fabsf(y));
             uint16_t h;
             if (out_fp16) {
               const __half hh = __float2half_rn(y);
@@ -229,12 +333,19 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       fence_proxy_async_smem();
       named_bar_sync(gbar, kEpiGroupThreads);
-      if (issuer && m0 < p.M) {
-        for (int s = 0; s < slabs; ++s)
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                       ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(stage_g + s * kSlabBytes), "r"(s * 64),
-                       "r"(m0)
-                       : "memory");
+      if (issuer && (PATCH ? h0 < p.Ho : m0 < p.M)) {
+        for (int s = 0; s < slabs; ++s) {
+          if (PATCH)
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(stage_g + s * kSlabBytes), "r"(s * 64),
+                         "r"(w0), "r"(h0), "r"(pimg)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                         ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(stage_g + s * kSlabBytes), "r"(s * 64),
+                         "r"(m0)
+                         : "memory");
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
