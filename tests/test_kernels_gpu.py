@@ -334,11 +334,14 @@ def test_stem_pool_strips(cuda_device, shape):
         y = engine.nhwc_empty(n, ho, wo, 64, dev, dtype)
         engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(y), scale, shift), dev)
         hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
-        yp = engine.nhwc_empty(n, hq, wq, 64, dev, dtype)
-        yp.fill_(-1.0)
+        # the pooled rows leave by plain global stores (not clipped by a tensor map): guard bands on both sides
+        guard = 4096
+        flat = torch.full((guard + n * hq * wq * 64 + guard,), -1.0, dtype=dtype, device=dev)
+        yp = flat[guard:guard + n * hq * wq * 64].view(n, hq, wq, 64).permute(0, 3, 1, 2)
         engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(yp), scale, shift, pool=True), dev)
         torch.cuda.synchronize()
         assert torch.equal(yp, F.max_pool2d(y.float(), 3, 2, 1).to(dtype)), "fused stem + max-pool mismatch (%s)" % dtype
+        assert bool((flat[:guard] == -1).all()) and bool((flat[-guard:] == -1).all()), "write outside the pooled tensor"
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 32, 48), (1, 64, 35, 51), (2, 128, 9, 7)])
