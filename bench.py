@@ -474,7 +474,8 @@ def main():
         roof = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-            "kernel": "conv_gemm_kernel<256,4> (all launches of one step: %d launches, %.1f%% of step time)"
+            "kernel": "256-wide tcgen05 implicit-GEMM launches (conv_gemm_kernel<256,...> incl. CTA pairs, and "
+                      "conv_swap_kernel: 128x256x16 MMAs; all launches of one step: %d launches, %.1f%% of step time)"
                       % (len(dom), 100.0 * dom_ms / all_ms),
             "peak_source": peaks["_source"] + ", sustained bf16 (kernel timed inside a long step)",
             "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
