@@ -18,43 +18,52 @@ namespace tdet {
 template <typename T>
 __device__ __forceinline__ float prep_load(const T* p) { return static_cast<float>(*p); }
 
+// One thread stages TWO horizontally adjacent pixels (the pitch is a multiple of 16 pixels): one 16-byte store, and
+// the (image, row, column) decode runs in 32-bit arithmetic per pair -- the staged batch has < 2^31 pixels, and the
+// 64-bit div/mod per pixel of the first version cost more than the memory traffic (0.10 ms -> see DESIGN 3.3).
 template <typename T>
 __global__ void __launch_bounds__(256)
 prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
                   int n, int hv, int wv, int hp, int wp, const float* __restrict__ scale,
                   const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta, int split) {
   const long long total = static_cast<long long>(n) * hp * wp;
+  const unsigned pairs = static_cast<unsigned>(total >> 1);
+  const unsigned wp2 = static_cast<unsigned>(wp) >> 1;
   float amax = 0.0f;
   float s0 = 1.0f, s1 = 1.0f, s2 = 1.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
   if (scale) { s0 = scale[0]; s1 = scale[1]; s2 = scale[2]; }
   if (shift) { b0 = shift[0]; b1 = shift[1]; b2 = shift[2]; }
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int xw = static_cast<int>(i % wp);
-    const long long t = i / wp;
-    const int yh = static_cast<int>(t % hp);
-    const int img = static_cast<int>(t / hp);
-    const int iw = xw - 3, ih = yh - 3;
-    uint2 o = make_uint2(0u, 0u);
-    if (iw >= 0 && iw < wv && ih >= 0 && ih < hv) {
-      const T* px = x + img * sn + ih * sh + iw * sw;
-      const float c0 = fmaf(prep_load(px), s0, b0);
-      const float c1 = fmaf(prep_load(px + sc), s1, b1);
-      const float c2 = fmaf(prep_load(px + 2 * sc), s2, b2);
-      o.x = pack_bf16x2(c0, c1);
-      o.y = pack_bf16x2(c2, 0.0f);
-      amax = fmaxf(amax, fmaxf(fmaxf(fabsf(bf16_lo(o.x)), fabsf(bf16_hi(o.x))), fabsf(bf16_lo(o.y))));
-      if (split) {
-        // lo plane of the split-precision staging: the batch's second half [n .. 2n)
-        uint2 l;
-        l.x = pack_bf16x2(c0 - bf16_lo(o.x), c1 - bf16_hi(o.x));
-        l.y = pack_bf16x2(c2 - bf16_lo(o.y), 0.0f);
-        y[total + i] = l;
+  uint4* __restrict__ y4 = reinterpret_cast<uint4*>(y);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += gridDim.x * blockDim.x) {
+    const unsigned t = i / wp2;
+    const int xw = static_cast<int>(i - t * wp2) * 2;
+    const unsigned img = t / static_cast<unsigned>(hp);
+    const int ih = static_cast<int>(t - img * static_cast<unsigned>(hp)) - 3;
+    uint2 o[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    uint2 lo[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+    if (ih >= 0 && ih < hv) {
+      const T* row = x + img * sn + ih * sh;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int iw = xw + k - 3;
+        if (iw >= 0 && iw < wv) {
+          const T* px = row + iw * sw;
+          const float c0 = fmaf(prep_load(px), s0, b0);
+          const float c1 = fmaf(prep_load(px + sc), s1, b1);
+          const float c2 = fmaf(prep_load(px + 2 * sc), s2, b2);
+          o[k].x = pack_bf16x2(c0, c1);
+          o[k].y = pack_bf16x2(c2, 0.0f);
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(bf16_lo(o[k].x)), fabsf(bf16_hi(o[k].x))), fabsf(bf16_lo(o[k].y))));
+          if (split) {
+            lo[k].x = pack_bf16x2(c0 - bf16_lo(o[k].x), c1 - bf16_hi(o[k].x));
+            lo[k].y = pack_bf16x2(c2 - bf16_lo(o[k].y), 0.0f);
+          }
+        }
       }
-    } else if (split) {
-      y[total + i] = make_uint2(0u, 0u);
     }
-    y[i] = o;
+    y4[i] = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+    // lo plane of the split-precision staging: the batch's second half [n .. 2n)
+    if (split) y4[pairs + i] = make_uint4(lo[0].x, lo[0].y, lo[1].x, lo[1].y);
   }
   if (meta) {
 #pragma unroll

@@ -1232,7 +1232,8 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
     case TDET_OP_PREP: {
       const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
       const long long total = static_cast<long long>(o.n) * hp * wp;
-      const int g = grid_for(total, di.num_sms);
+      if (total >= (1ll << 31)) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "prep: staged batch of %lld pixels", total);
+      const int g = grid_for(total / 2, di.num_sms);  // one thread per pixel pair
       TensorMeta* meta = reinterpret_cast<TensorMeta*>(o.y_meta);
       const int hv = o.hc ? o.hc : o.h, wv = o.wc ? o.wc : o.w;  // valid extent; the rest is zero padding
       const int split = (o.flags & TDET_FLAG_SPLIT) ? 1 : 0;     // y then holds 2n staged images: hi planes, lo planes
