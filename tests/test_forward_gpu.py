@@ -89,6 +89,25 @@ def test_full_size_r50_fpn_single_image(cuda_device):
     print("rel-L2 full size", e1, e2)
 
 
+def test_full_batch16_equals_single_image(cuda_device):
+    """BASELINE config 2 at its full size (batch 16 @800x1344): every image of a batch of 16 copies reproduces the
+    single-image result -- which `test_full_size_r50_fpn_single_image` checks against the oracle -- bit for bit.
+    Size-independent property covering the whole-batch tile schedules (CTA pairs, fused stem + max-pool ranges that
+    span images, 8 400-tile persistent grids)."""
+    bb, neck = helpers.build_product_pair(50, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x1 = torch.zeros(1, 3, 800, 1344)
+    x1[:, :, :, :1333] = torch.randn(1, 3, 800, 1333, generator=g)
+    x1 = x1.to(torch.bfloat16)
+    f1, p1 = _run_product(bb, neck, x1, cuda_device)
+    f16, p16 = _run_product(bb, neck, x1.expand(16, -1, -1, -1).contiguous(), cuda_device)
+    for a, b in zip(f1 + p1, f16 + p16):
+        assert b.shape[0] == 16
+        for i in (0, 7, 15):
+            assert torch.equal(a[0], b[i]), "image %d of the batch differs from the single-image run" % i
+        assert torch.equal(b, b[0:1].expand_as(b))
+
+
 def test_batch_independence_and_determinism(cuda_device):
     """Images are independent units (eval BN): batch of 3 == three batches of 1, bit for bit, and a
     second run reproduces the first exactly (size-independent property)."""
