@@ -7,7 +7,12 @@
 //   A_TILED  : 1x1 stride-1 conv -> A is the activation matrix itself (2D tiled tensor map)
 //   A_IM2COL : kxk / strided conv -> 4D im2col tensor map, one load per (filter tap, 64-ch chunk)
 //   A_STEM   : 7x7/2 stem on the padded NHWC4 staging -> 5D tiled map with overlapping windows
+//   A_STEM2  : the stem from linear staged rows (un-swizzled overlapping descriptors); POOL fuses the max-pool
+//   A_PATCH  : 3x3 stride-1 conv -> one halo patch per tile, the nine taps are shifted descriptors over it
+//   A_SPATIAL: 1x1 conv over 8x16-pixel tiles with the coarse FPN level staged by TMA (laterals)
 // W is pre-packed [Cout][kh][kw][Cin], i.e. K-major rows, loaded by a 2D tiled map.
+// Variants: PAIR (clusters of two CTAs, cta_group::2 MMAs of M = 256), SPLIT (split-precision fp32-I/O mode),
+// MASKED (ReLU-backward mask operand: dgrad), POOL (stem + max-pool); narrow outputs run in conv_swap.cuh.
 //
 // Persistent, warp-specialised CTA (352 threads), every global<->shared transfer is asynchronous:
 //   warp 0      TMA producer for A/B     (full/empty mbarrier ring, STAGES deep)
