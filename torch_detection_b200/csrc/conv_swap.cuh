@@ -1,13 +1,15 @@
 // Operand-swapped implicit-GEMM conv for narrow outputs (Cout = 64 or 128; SURVEY.md section 8 rows a3/a5: conv1 and
 // conv2 of the bottlenecks of layer1/layer2, resnet.py:97-108).
 //
-// Measured on B200: one tcgen05.mma of M = 128, K = 16 takes ~115-145 SM cycles whatever its
-// N, because the 128 x 32 B A-operand fetch from shared memory is the fixed part.  With the output channels as N a
-// 64- or 128-wide conv therefore runs the tensor pipe at 25-50 %.  Here the roles are swapped:
+// Measured on B200 (tools/probe_umma_m64.cu): a 128 x 128 x 16 MMA reads 8 KB of operands per
+// 64 cycles -- all of the SM's shared-memory bandwidth -- so inside a conv kernel, where TMA fills and the epilogue
+// share that bandwidth, 128-wide tiles reach ~45 % of the tensor rate (145 cycles per MMA), while the 256-wide shape
+// (12 KB per 128 cycles) runs at its math rate.  Here the roles are swapped:
 //
 //     D^T[Cout (M = 128 lanes), 256 pixels (N)] = W[Cout, K] * A[256 pixels, K]^T
 //
-// so every MMA is the full-rate 128 x 256 x 16 shape (Cout = 64: the weight tile's upper 64 rows are TMA zero fill).
+// so every MMA is the 128 x 256 x 16 shape (Cout = 64: the weight tile's upper 64 rows are TMA zero fill; an M = 64
+// MMA takes the same 128 cycles, so narrower weight operands gain nothing).
 // The accumulator arrives transposed -- TMEM lane = output channel, column = pixel -- which makes the epilogue's
 // per-channel scale/shift two registers per thread; each thread converts its channel for 32 pixels at a time
 // (tcgen05.ld 32x32b.x32) and scatters 16-bit values into the [pixel][channel] 128B-swizzled staging slab (a warp's 32
