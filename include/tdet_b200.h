@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 8
+#define TDET_ABI_VERSION 9
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -86,7 +86,8 @@ typedef enum tdet_op_kind {
   TDET_OP_BN_AFFINE_GRAD = 13, /* gamma / beta gradients of a frozen-statistics BatchNorm from stored tensors */
   TDET_OP_SPLIT_COMBINE = 14, /* y (fp32 [n][h][w][cin]) = hi + lo of a split-precision tensor x ([n][h][w][2*cin] bf16) */
   TDET_OP_MAXPOOL_BWD = 15,  /* backward of MaxPool2d(3, 2, 1) fused with the ReLU backward of its input (stem) */
-  TDET_OP_STEM_WGRAD = 16    /* weight gradient of the 7x7/2 stem conv from the staged image */
+  TDET_OP_STEM_WGRAD = 16,   /* weight gradient of the 7x7/2 stem conv from the staged image */
+  TDET_OP_PARITY_MERGE = 17  /* interleave the four parity-class results of a stride-2 3x3 dgrad (+ ReLU mask) */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -175,6 +176,12 @@ typedef struct tdet_tensor_meta {
  *                   w.r.t. the pooled tensor [n][ho][wo][cin] (gy_dtype, gy_meta); y: bf16 [n][h][w][cin] =
  *                   (S > 0) * scatter of gy to each window's first maximum (aten max_pool2d tie rule)
  *                   (resnet.py:257-258 backward).
+ * TDET_OP_PARITY_MERGE  input gradient of a 3x3 / stride 2 / pad 1 conv (resnet.py:75,99) from four stride-1 convs
+ *                   over the coarse gradient g [n][hc][wc][.] with the parity classes of the rotated kernel:
+ *                   x = p00 [n][hc][wc][cin] (1x1, tap (1,1)), residual = p01 [n][hc+2][wc+1][cin] (1x2, pad 1, taps
+ *                   (1,0),(1,2)), coarse = p10 [n][hc+1][wc+2][cin] (2x1, pad 1), gy = p11 [n][hc+1][wc+1][cin] (2x2,
+ *                   pad 1), all of x_dtype with their metas; y [n][h][w][cin]: y[2i+a][2j+b] = p_ab[i+o][j+o] (o = 1
+ *                   for the padded classes), zeroed where mask (nullable, [n][h][w][cin]) is not positive.
  * TDET_OP_STEM_WGRAD  x: the TDET_OP_PREP staging of the batch (bf16 NHWC4); gy: bf16 [n][ho][wo][64] gradient
  *                   w.r.t. bn1's output; scale: folded bn1 scale (or NULL); dw: fp32 [64][3][7][7], accumulated.
  *                   h, w = image size as for TDET_OP_STEM.

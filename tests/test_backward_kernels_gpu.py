@@ -98,6 +98,51 @@ def test_dgrad_3x3_stride2(cuda_device, case):
     assert err <= 4e-3
 
 
+@pytest.mark.parametrize("case", [("3x3s2_128", 2, 21, 27, 128, 128), ("3x3s2_512", 1, 25, 42, 512, 512),
+                                  ("3x3s2_even", 2, 20, 28, 256, 256), ("3x3s2_64_128", 3, 32, 16, 64, 128)],
+                         ids=lambda c: c[0])
+@pytest.mark.parametrize("scaled", [False, True], ids=["bf16", "fp16_scaled"])
+def test_dgrad_3x3_stride2_parity_classes(cuda_device, case, scaled):
+    """The training path's stride-2 dgrad: four parity-class convs over the coarse gradient + TDET_OP_PARITY_MERGE
+    (training.BackwardBuilder), against autograd of the strided conv with the same 16-bit-rounded weights."""
+    from torch_detection_b200 import engine, training
+    name, n, h, w, cin, cout = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(13)
+    ho, wo = engine.conv_out(h, 3, 2, 1), engine.conv_out(w, 3, 2, 1)
+    conv = torch.nn.Conv2d(cin, cout, 3, 2, 1, bias=False).to(dev)
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5).to(dev))
+    scale = (0.5 + torch.rand(cout, generator=g)).to(dev)
+    dtype = torch.float16 if scaled else torch.bfloat16
+    gy = _nhwc(torch.randn(n, cout, ho, wo, generator=g).to(dev), dtype)
+    mask = _nhwc(F.relu(torch.randn(n, cin, h, w, generator=g)).to(dev))
+    meta = engine.MetaArena(16, dev) if scaled else None
+    bb = training.BackwardBuilder(dev, engine.OperandCache(), dtype=dtype, meta=meta)
+    assert training.S2_DGRAD_PARITY
+    g_act = engine.Act(gy, (n, ho, wo, cout), dtype, meta.new() if scaled else None)
+    if scaled:
+        bb.ops.append(engine.op_amax(g_act, g_act.meta))  # the producer of g would have recorded its |max|
+    dx = bb.dgrad("c", conv, scale, g_act, (n, h, w, cin), mask=engine.act_of(mask))
+    ops, _ = bb.finalize()
+    kinds = [o.kind for o in ops]
+    assert kinds.count(17) == 1 and 9 not in kinds, "expected the parity path, got op kinds %r" % (kinds,)
+    plan = engine.Plan(ops, [], [gy, mask] + bb.buffers, dev, meta=meta)
+    plan.run([])
+    torch.cuda.synchronize()
+    x = torch.zeros(n, cin, h, w, device=dev, requires_grad=True)
+    wq = (conv.weight.detach() * scale.view(-1, 1, 1, 1)).to(dtype).float()
+    (ref,) = torch.autograd.grad(F.conv2d(x, wq, None, 2, 1, 1), x, gy.float())
+    ref = ref * (mask.float() > 0)
+    got = dx.buf[:n * h * w * cin].view(dtype).view(n, h, w, cin).permute(0, 3, 1, 2).float()
+    if scaled:
+        e_dx = meta.read()[(dx.meta - meta.tensor.data_ptr()) // 8][0]
+        got = got * 2.0 ** e_dx
+    err = rel_l2(got, ref)
+    print("parity dgrad %s rel-L2 %.3e" % (name, err))
+    assert err <= 4e-3
+
+
 @pytest.mark.parametrize("hw", [(20, 28), (25, 42)])
 def test_dgrad_shortcut_parity_add(cuda_device, hw):
     """Block-input gradient of a strided bottleneck: dgrad(conv1)(g1) + scatter of the stride-2 1x1

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # tdet_status
 OK = 0
@@ -25,7 +25,7 @@ OP_WGRAD, OP_DW_UNPACK, OP_COLSUM, OP_SUMPOOL2, OP_DILATE2, OP_ADD_MASK, OP_ZERO
 OP_AMAX = 12
 OP_BN_AFFINE_GRAD = 13
 OP_SPLIT_COMBINE = 14
-OP_MAXPOOL_BWD, OP_STEM_WGRAD = 15, 16
+OP_MAXPOOL_BWD, OP_STEM_WGRAD, OP_PARITY_MERGE = 15, 16, 17
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1

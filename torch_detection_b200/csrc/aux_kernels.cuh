@@ -734,6 +734,75 @@ add_mask_kernel(const AddMaskParams p) {
   }
 }
 
+// Stride-2 3x3 dgrad as four parity classes (TDET_OP_PARITY_MERGE): dx[2i+a][2j+b] only receives the filter taps of
+// matching parity, so the input gradient is four small stride-1 convs over the COARSE gradient g --
+//   (0,0): 1x1, tap (1,1)      (0,1): 1x2, taps (1,0),(1,2)      (1,0): 2x1, taps (0,1),(2,1)      (1,1): 2x2, the corners
+// of the rotated kernel -- a quarter of the MMAs of a 3x3 conv over the zero-inserted gradient.  The multi-tap classes
+// run with pad 1 (symmetric padding is all the conv op has), which shifts their outputs by one pixel and adds a
+// border: p01 is [n][hc+2][wc+1], p10 [n][hc+1][wc+2], p11 [n][hc+1][wc+1], p00 [n][hc][wc].  This kernel interleaves
+// the four results into dx [n][h][w][c], applies the ReLU-backward mask and converts formats / exponents.
+struct ParityMergeParams {
+  const uint4* p[4];         // p00, p01, p10, p11
+  const TensorMeta* pm[4];   // nullable
+  const uint4* mask;         // nullable, [n][h][w][c]
+  uint4* y;
+  TensorMeta* y_meta;
+  int n, h, w, c8, hc, wc;
+  int p_fp16, y_fp16, scaled;
+};
+
+__global__ void __launch_bounds__(256)
+parity_merge_kernel(const ParityMergeParams q) {
+  int e[4];
+  float bound = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    e[k] = q.pm[k] ? q.pm[k]->e : 0;
+    if (q.pm[k]) bound = fmaxf(bound, __uint_as_float(q.pm[k]->amax_bits));
+  }
+  int ey = 0;
+  if (q.scaled) {
+    if (bound > 0.0f && bound < 3.0e38f) ey = ilogbf(bound) - 14;
+    ey = max(-100, min(100, ey));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      q.y_meta->e = ey;
+      q.y_meta->amax_bits = __float_as_uint(bound);
+    }
+  }
+  float mul[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) mul[k] = ldexpf(1.0f, e[k] - ey);
+  const bool pf = q.p_fp16 != 0, yf = q.y_fp16 != 0;
+  const unsigned total = static_cast<unsigned>(q.n) * q.h * q.w * q.c8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % q.c8;
+    unsigned t = i / q.c8;
+    const int v = static_cast<int>(t % q.w);
+    t /= q.w;
+    const int u = static_cast<int>(t % q.h);
+    const int img = static_cast<int>(t / q.h);
+    const int a = u & 1, b = v & 1, k = 2 * a + b;
+    const int off = k ? 1 : 0;                                       // the padded classes are shifted by one pixel
+    const int ph = q.hc + (k == 1 ? 2 : k ? 1 : 0), pw = q.wc + (k == 2 ? 2 : k ? 1 : 0);
+    const long long src = ((static_cast<long long>(img) * ph + (u >> 1) + off) * pw + (v >> 1) + off) * q.c8 + cg;
+    const uint4 x = __ldg(q.p[k] + src);
+    const uint4 m = q.mask ? __ldg(q.mask + i) : make_uint4(0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu, 0x7FFF7FFFu);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, mw[4] = {m.x, m.y, m.z, m.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      unpack16x2(xw[j], pf, lo, hi);
+      lo *= mul[k];
+      hi *= mul[k];
+      if ((mw[j] & 0x00007FFFu) == 0u) lo = 0.0f;
+      if ((mw[j] & 0x7FFF0000u) == 0u) hi = 0.0f;
+      ow[j] = pack16x2(lo, hi, yf);
+    }
+    q.y[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 // meta->amax_bits = max |x| * 2^e_x  (atomicMax on the bit pattern; the plan zeroes the arena first)
 __global__ void __launch_bounds__(256)
 amax_kernel(const uint4* __restrict__ x, long long total, int x_fp16, const TensorMeta* x_meta, TensorMeta* meta) {

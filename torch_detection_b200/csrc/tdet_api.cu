@@ -1180,6 +1180,16 @@ int build_launch(Launch& l, const DeviceInfo& di) {
         return fail(TDET_ERR_INVALID_ARGUMENT, "add_mask: SCALED_OUT needs an F16 y with y_meta and input metas");
       l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w * (2 + (o.residual ? 1 : 0) + (o.mask ? 1 : 0));
       return TDET_OK;
+    case TDET_OP_PARITY_MERGE:
+      if (o.cin % 8 || !o.x || !o.residual || !o.coarse || !o.gy || !o.y || !is16(o.x_dtype) || !is16(o.y_dtype) ||
+          o.hc != out_dim(o.h, 3, 2, 1, 1) || o.wc != out_dim(o.w, 3, 2, 1, 1) ||
+          static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8) >= (1ll << 32))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "parity_merge: bad arguments");
+      if ((o.flags & TDET_FLAG_SCALED_OUT) &&
+          (o.y_dtype != TDET_F16 || !o.y_meta || !o.x_meta || !o.residual_meta || !o.coarse_meta || !o.gy_meta))
+        return fail(TDET_ERR_INVALID_ARGUMENT, "parity_merge: SCALED_OUT needs an F16 y with y_meta and input metas");
+      l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w * (2 + (o.mask ? 1 : 0));
+      return TDET_OK;
     case TDET_OP_ZERO:
       if (!o.y || o.x_stride[0] <= 0) return fail(TDET_ERR_INVALID_ARGUMENT, "zero: bad arguments");
       l.bytes = static_cast<double>(o.x_stride[0]);
@@ -1326,6 +1336,28 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       ap.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
       ap.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
       add_mask_kernel<<<grid_for(ap.total, di.num_sms), 256, 0, st>>>(ap);
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
+    case TDET_OP_PARITY_MERGE: {
+      ParityMergeParams q{};
+      q.p[0] = static_cast<const uint4*>(o.x);
+      q.p[1] = static_cast<const uint4*>(o.residual);
+      q.p[2] = static_cast<const uint4*>(o.coarse);
+      q.p[3] = static_cast<const uint4*>(o.gy);
+      q.pm[0] = reinterpret_cast<const TensorMeta*>(o.x_meta);
+      q.pm[1] = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+      q.pm[2] = reinterpret_cast<const TensorMeta*>(o.coarse_meta);
+      q.pm[3] = reinterpret_cast<const TensorMeta*>(o.gy_meta);
+      q.mask = static_cast<const uint4*>(o.mask);
+      q.y = static_cast<uint4*>(o.y);
+      q.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+      q.n = o.n; q.h = o.h; q.w = o.w; q.c8 = o.cin / 8; q.hc = o.hc; q.wc = o.wc;
+      q.p_fp16 = o.x_dtype == TDET_F16;
+      q.y_fp16 = o.y_dtype == TDET_F16;
+      q.scaled = (o.flags & TDET_FLAG_SCALED_OUT) ? 1 : 0;
+      const long long total = static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8);
+      parity_merge_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(q);
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

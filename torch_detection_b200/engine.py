@@ -458,6 +458,28 @@ def op_add_mask(x, y, residual=None, mask=None, scaled_out=False):
     return op
 
 
+def op_parity_merge(parts, y, hc, wc, mask=None, scaled_out=False):
+    """y[2i+a][2j+b] = parts[2a+b][i+o][j+o] * (mask != 0): interleaves the four parity-class results of a stride-2
+    3x3 dgrad (TDET_OP_PARITY_MERGE; o = 1 for the three pad-1 classes).  hc, wc = size of the coarse gradient."""
+    n, h, w, c = y.shape
+    p00, p01, p10, p11 = parts
+    assert p00.shape == (n, hc, wc, c) and p01.shape == (n, hc + 2, wc + 1, c)
+    assert p10.shape == (n, hc + 1, wc + 2, c) and p11.shape == (n, hc + 1, wc + 1, c)
+    op = _C.TdetOp()
+    op.kind = _C.OP_PARITY_MERGE
+    op.n, op.h, op.w, op.cin, op.hc, op.wc = n, h, w, c, hc, wc
+    op.x_dtype = op.residual_dtype = op.coarse_dtype = op.gy_dtype = _TD[p00.dtype]
+    op.y_dtype = _TD[y.dtype]
+    op.x, op.residual, op.coarse, op.gy = p00.ptr, p01.ptr, p10.ptr, p11.ptr
+    op.x_meta, op.residual_meta, op.coarse_meta, op.gy_meta = p00.meta, p01.meta, p10.meta, p11.meta
+    op.y, op.y_meta = y.ptr, y.meta
+    if mask is not None:
+        op.mask = mask.ptr
+    if scaled_out:
+        op.flags = _C.FLAG_SCALED_OUT
+    return op
+
+
 def op_bn_affine_grad(g, a, gamma, beta, dw, b=None):
     """dw[0:C] += dgamma, dw[C:2C] += dbeta of a frozen-statistics BatchNorm: g = masked gradient w.r.t. its
     output, a (minus b, if given) = the stored tensor that equals the BN output wherever g != 0."""

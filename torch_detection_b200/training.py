@@ -9,7 +9,8 @@ of ``tdet_op`` descriptors on the caller's stream:
              transposed weights (tdet_pack_dgrad_weight); the ReLU backward of the layer it feeds is
              the conv's ``mask`` epilogue, residual / shortcut / external gradients are its
              ``residual`` / ``coarse`` (parity scatter) operands, so every gradient tensor is
-             written exactly once.
+             written exactly once.  A stride-2 3x3 conv's dgrad is four parity-class convs over the
+             coarse gradient + TDET_OP_PARITY_MERGE (no zero insertion).
     wgrad  = TDET_OP_WGRAD (pixels are the contraction dimension) into fp32 accumulators that live
              in one flat bucket per stage -- the all-reduce unit.
 
@@ -187,6 +188,9 @@ class BackwardBuilder(object):
         k = module.kernel_size[0]
         stride, pad, dil = module.stride[0], module.padding[0], module.dilation[0]
         wd = self.dgrad_weight(name, module, scale, deps)
+        if (stride == 2 and k == 3 and pad == 1 and dil == 1 and residual is None and coarse is None
+                and S2_DGRAD_PARITY):
+            return self._dgrad_s2_parity(name, module, wd, g, in_shape, mask, deps)
         dx = self.new_act(in_shape)
         src = g
         tmp = None
@@ -202,6 +206,43 @@ class BackwardBuilder(object):
         self.conv_dgrad_op(name, module, wd, src, dx, k, dil * (k - 1) - pad, dil, deps, residual=residual,
                            coarse=coarse, coarse_parity=coarse is not None, mask=mask)
         self.release(tmp)
+        return dx
+
+    def _dgrad_s2_parity(self, name, module, wd, g, in_shape, mask, deps):
+        """3x3 / stride 2 / pad 1 dgrad without zero insertion: dx[2i+a][2j+b] only sees the taps of the rotated
+        kernel whose parity matches (a, b), so it is four small stride-1 convs over the coarse gradient (1x1, 1x2,
+        2x1, 2x2: a quarter of the MMAs of the 3x3 conv over the zero-inserted gradient) and one interleaving pass
+        that also applies the ReLU-backward mask (TDET_OP_PARITY_MERGE)."""
+        n, hc, wc, _ = g.shape
+        cin = in_shape[3]
+        parts = []
+        for a in (0, 1):
+            for b in (0, 1):
+                rs = [1] if a == 0 else [0, 2]
+                ss = [1] if b == 0 else [0, 2]
+                kh, kw = len(rs), len(ss)
+                pad = 1 if (a or b) else 0
+
+                def make(out, rs=rs, ss=ss):
+                    sub = wd[:, rs][:, :, ss]
+                    if out is None:
+                        return sub.contiguous()
+                    out.copy_(sub)
+                    return out
+
+                w_ab = self.cache.get((name, "wd%d%d" % (a, b), self.dtype), make, deps=(module.weight,) + tuple(deps))
+                consts = None
+                if self.scaled:
+                    consts = self.cache.get((name, "wdc%d%d" % (a, b), self.dtype),
+                                            lambda out, w_ab=w_ab: engine.bound_consts(w_ab, None, None, out=out),
+                                            deps=(module.weight,) + tuple(deps))
+                part = self.new_act((n, hc + 2 * pad - kh + 1, wc + 2 * pad - kw + 1, cin))
+                self.ops.append(engine.op_conv(g, w_ab, part, kh, kw, 1, pad, 1, consts=consts, scaled_out=self.scaled))
+                parts.append(part)
+        dx = self.new_act(in_shape)
+        self.ops.append(engine.op_parity_merge(parts, dx, hc, wc, mask=mask, scaled_out=self.scaled))
+        for part in parts:
+            self.release(part)
         return dx
 
     def wgrad(self, name, module, scale, x, g, dst):
@@ -231,6 +272,10 @@ class BackwardBuilder(object):
                 self.ops[idx] = engine.op_wgrad(x, g, acc, k, k, stride, pad, dil, scale=scale)
                 self.ops[idx + 1] = engine.op_dw_unpack(acc, dst, cout, cin, k, k)
         return head + self.ops, len(head)
+
+
+# stride-2 3x3 dgrad as four parity-class convs (default) instead of a 3x3 conv over the zero-inserted gradient
+S2_DGRAD_PARITY = __import__("os").environ.get("TDET_S2_DGRAD", "parity").lower() != "dilate"
 
 
 def as_grad_nhwc(g, like):
