@@ -774,6 +774,7 @@ parity_merge_kernel(const ParityMergeParams q) {
   for (int k = 0; k < 4; ++k) mul[k] = ldexpf(1.0f, e[k] - ey);
   const bool pf = q.p_fp16 != 0, yf = q.y_fp16 != 0;
   const unsigned total = static_cast<unsigned>(q.n) * q.h * q.w * q.c8;
+#pragma unroll 4
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const unsigned cg = i % q.c8;
     unsigned t = i / q.c8;
