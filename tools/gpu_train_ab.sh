@@ -3,8 +3,6 @@
 mkdir -p gpurun_out
 run() {
   echo -n "$1 : "
-  env $2 python bench.py --mode train --steps 10 --warmup 3 --no-cpu-baseline --launch-table gpurun_out/lt_train_$1.json 2>gpurun_out/abt_$1.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.1f img/s  %.3f ms/step' % (d['value'], d['ms_per_step']), d['backward_kernels'])" || tail -5 gpurun_out/abt_$1.err
+  env $2 python bench.py --mode train --steps 10 --warmup 3 --no-cpu-baseline --launch-table gpurun_out/lt_train_$1.json 2>gpurun_out/abt_$1.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.1f img/s  %.3f ms/step' % (d['value'], d['ms_per_step']), d['backward_kernels']['wgrad'])" || tail -5 gpurun_out/abt_$1.err
 }
-for rep in 1 2; do
-run dilate_$rep "TDET_S2_DGRAD=dilate"; run parity_$rep "TDET_S2_DGRAD=parity"
-done
+run st0 "TDET_WGRAD_SMALL_TILE=0"; run st1 "TDET_WGRAD_SMALL_TILE=1"; run st0b "TDET_WGRAD_SMALL_TILE=0"; run st1b "TDET_WGRAD_SMALL_TILE=1"

@@ -912,6 +912,44 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
   // two Cout tiles per CTA (two accumulators sharing every X tile) whenever Cout allows: less L2->SM traffic
   l.wg_mt = (o.cout % 256 == 0 && l.wg_nb >= 128 && env_int("TDET_WGRAD_MT", 2) >= 2) ? 2 : 1;
   l.wg_pix = (l.wg_nb == 256 || l.wg_mt == 2) ? 64 : 128;
+  // Split-K trades main-loop length against the fp32 reduction traffic every CTA adds (a whole tile of red.add per
+  // CTA, ~2-3 TB/s device-wide measured).  Two-term cost model over {one, two full waves} -- never a partial extra
+  // one -- and, for layers with few pixels (layer3/4: reduction-bound), over the 128 x 128 tile as well:
+  // a quarter of the reduction bytes per CTA for MMAs that run at half the rate.  Calibration (measured): a
+  // 128x256x16 MMA 0.075 us, a 128x128x16 one 0.076 us (shared-memory bound), 2 TB/s of reductions.
+  const int sms = di.num_sms - di.sm_reserve;
+  const int force_waves = env_int("TDET_WGRAD_WAVES", 0);
+  auto estimate = [&](int nb, int mt, int pix, int* splits_out) {
+    const long long kblocks = (m_ll + pix - 1) / pix;
+    const int tiles = ((o.cout + 128 * mt - 1) / (128 * mt)) * o.kh * o.kw * (o.cin / nb);
+    const double t_kb = mt * (pix / 16) * (nb == 256 ? 0.075 : nb == 128 ? 0.076 : 0.06);
+    const double tile_bytes = 128.0 * mt * nb * 4.0;
+    double best = 1e30;
+    for (int target : {sms, 2 * sms}) {  // (half a wave measured slower than one wherever the model preferred it)
+      if (force_waves && target != force_waves * sms) continue;
+      long long sp = target / tiles;
+      if (sp > kblocks) sp = kblocks;
+      if (sp < 1) sp = 1;
+      const long long ctas = tiles * sp;
+      const long long waves = (ctas + sms - 1) / sms;
+      const double conc = static_cast<double>(ctas < sms ? ctas : sms);
+      const double t = waves * ((kblocks + sp - 1) / sp * t_kb + conc * tile_bytes / 2.0e6);
+      if (t < best) { best = t; *splits_out = static_cast<int>(sp); }
+    }
+    return best;
+  };
+  int splits = 1;
+  {
+    const double t_default = estimate(l.wg_nb, l.wg_mt, l.wg_pix, &splits);
+    int splits_small = 1;
+    if (l.wg_nb >= 128 && env_int("TDET_WGRAD_SMALL_TILE", 1) &&
+        estimate(128, 1, 128, &splits_small) < t_default) {
+      l.wg_nb = 128;
+      l.wg_mt = 1;
+      l.wg_pix = 128;
+      splits = splits_small;
+    }
+  }
   wp.M = static_cast<int>(m_ll);
   wp.cout = o.cout;
   wp.cin = o.cin;
@@ -957,26 +995,6 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
       reinterpret_cast<unsigned long long*>(&wp.tmap_x)[1] &= ~(1ull << 21);
   }
   const int tiles = ((o.cout + 128 * l.wg_mt - 1) / (128 * l.wg_mt)) * o.kh * o.kw * wp.ci_groups;
-  // One CTA per SM (shared memory).  Split-K trades main-loop length against the fp32 reduction traffic every
-  // CTA adds (a whole tile of red.add per CTA, ~3 TB/s device-wide measured): pick half a wave, one or two full
-  // waves -- never a partial extra one -- by a two-term cost model (TDET_WGRAD_WAVES=1/2 forces one).
-  const int sms = di.num_sms - di.sm_reserve;
-  const double t_kb = 0.15 * l.wg_mt * (l.wg_pix / 16) * (l.wg_nb / 256.0);  // us per k-block (measured ~50 % pipe)
-  const double tile_bytes = 128.0 * l.wg_mt * l.wg_nb * 4.0;
-  const int force_waves = env_int("TDET_WGRAD_WAVES", 0);
-  int splits = 1;
-  double best = 1e30;
-  for (int target : {sms / 2, sms, 2 * sms}) {
-    if (force_waves && target != force_waves * sms) continue;
-    int sp = target / tiles;
-    if (sp > wp.kblocks) sp = wp.kblocks;
-    if (sp < 1) sp = 1;
-    const int ctas = tiles * sp;
-    const int waves = (ctas + sms - 1) / sms;
-    const int conc = ctas < sms ? ctas : sms;
-    const double t = waves * ((wp.kblocks + sp - 1) / sp * t_kb + conc * tile_bytes / 3.0e6);
-    if (t < best) { best = t; splits = sp; }
-  }
   wp.kb_per_cta = (wp.kblocks + splits - 1) / splits;
   splits = (wp.kblocks + wp.kb_per_cta - 1) / wp.kb_per_cta;
   l.grid = dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(splits), 1);
