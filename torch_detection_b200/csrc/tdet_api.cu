@@ -916,7 +916,8 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
   // CTA, ~2-3 TB/s device-wide measured).  Two-term cost model over {one, two full waves} -- never a partial extra
   // one -- and, for layers with few pixels (layer3/4: reduction-bound), over the 128 x 128 tile as well:
   // a quarter of the reduction bytes per CTA for MMAs that run at half the rate.  Calibration (measured): a
-  // 128x256x16 MMA 0.075 us, a 128x128x16 one 0.076 us (shared-memory bound), 2 TB/s of reductions.
+  // 128x256x16 MMA 0.075 us, a 128x128x16 one 0.076 us (shared-memory bound), 1 TB/s of effective reduction
+  // throughput (fitted: 57 us for 74 x 2 CTAs x 256 KB + 17 us of MMAs; 47 us for 144 CTAs x 64 KB + 36 us).
   const int sms = di.num_sms - di.sm_reserve;
   const int force_waves = env_int("TDET_WGRAD_WAVES", 0);
   auto estimate = [&](int nb, int mt, int pix, int* splits_out) {
@@ -933,7 +934,7 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
       const long long ctas = tiles * sp;
       const long long waves = (ctas + sms - 1) / sms;
       const double conc = static_cast<double>(ctas < sms ? ctas : sms);
-      const double t = waves * ((kblocks + sp - 1) / sp * t_kb + conc * tile_bytes / 2.0e6);
+      const double t = waves * ((kblocks + sp - 1) / sp * t_kb + conc * tile_bytes / 1.0e6);
       if (t < best) { best = t; *splits_out = static_cast<int>(sp); }
     }
     return best;
