@@ -913,7 +913,7 @@ int build_wgrad(Launch& l, const DeviceInfo& di) {
   l.wg_mt = (o.cout % 256 == 0 && l.wg_nb >= 128 && env_int("TDET_WGRAD_MT", 2) >= 2) ? 2 : 1;
   l.wg_pix = (l.wg_nb == 256 || l.wg_mt == 2) ? 64 : 128;
   // Split-K trades main-loop length against the fp32 reduction traffic every CTA adds (a whole tile of red.add per
-  // CTA, ~2-3 TB/s device-wide measured).  Two-term cost model over {one, two full waves} -- never a partial extra
+  // CTA, ~1 TB/s effective when the split-K partners of a tile finish together).  Two-term cost model over {one, two full waves} -- never a partial extra
   // one -- and, for layers with few pixels (layer3/4: reduction-bound), over the 128 x 128 tile as well:
   // a quarter of the reduction bytes per CTA for MMAs that run at half the rate.  Calibration (measured): a
   // 128x256x16 MMA 0.075 us, a 128x128x16 one 0.076 us (shared-memory bound), 1 TB/s of effective reduction

@@ -15,9 +15,10 @@
 // One CTA = one (MT x 128-channel Cout tile, filter tap, NB-wide Cin group) and one slice of the pixel
 // range (split-K over blockIdx.y); partial sums are combined with vectorised fp32 reductions
 // (red.global.add.v4.f32) into the [Cout][kh][kw][Cin] accumulator, which the caller zeroes.
-// MT = 2 keeps two accumulators (2 x NB TMEM columns) that share every X tile: the kernel is bound by
-// L2->SM operand traffic (ncu: tensor pipe 53 % active at 27 % L2, 9 % DRAM), and 256 x 256 output tiles
-// need 64 B per tensor cycle instead of the 96 B of 128 x 256.
+// MT = 2 keeps two accumulators (2 x NB TMEM columns) that share every X tile: 256 x 256 output tiles need 64 B of
+// operands per tensor cycle instead of the 96 B of 128 x 256 (big layers: tensor pipe 85 % of elapsed cycles).  The
+// split-K factor and, for layers with few pixels, the tile shape come from a cost model in build_wgrad (tdet_api.cu):
+// such layers are bound by the reduction traffic (CTAs x tile bytes at ~1 TB/s), not by the main loop.
 //   warp 0  TMA producer      warp 1  tcgen05.mma issuer      warps 2..5  epilogue (TMEM -> red.add)
 #pragma once
 #include "conv_gemm.cuh"
