@@ -9,15 +9,23 @@ N > 1 is launched by the driver as `python -m torch.distributed.run --nproc-per-
 sharded across ranks with NO data-path collective ("scaling": "weak": 16 images per GPU);
 torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the device time.
 
-Prints ONE JSON line (rank 0).  `value` = whole-job images/s with inputs resident in HBM;
-`e2e` = the same through the public module API from pinned HOST buffers (H2D copy of every step's
-batch and a D2H read of the coarsest pyramid level inside the timed region);
-`roofline` = the tcgen05 implicit-GEMM kernel family, per-launch device time measured live with CUDA
-events (tdet_plan_run_timed) against MEASURED_PEAKS.json; `cpu_baseline` = the oracle (the reference's
-algorithm, CPU fp32) timed on this box's host cores on a bounded sample (rank 0, N=1 only).
+Prints ONE JSON line (rank 0).  Headline keys (BASELINE.json config 2):
+  `value`     whole-job images/s with inputs resident in HBM (device events, max over ranks)
+  `e2e`       the same through the public module API from pinned HOST buffers: H2D copy of every step's batch and
+              a D2H read of the coarsest pyramid level inside the timed region (the consumers of P2..P5 -- the
+              detection heads -- live on the device); `e2e_full_copy` also copies ALL five levels back
+  `roofline`  the tcgen05 implicit-GEMM kernel family, per-launch device time measured live with CUDA events
+              (tdet_plan_run_timed) against the BURST bf16 peak of MEASURED_PEAKS.json
+  `sustained` the same step looped for >= 3 s (power-capped clocks) with the median SM clock
+  `cpu_baseline` the reference's algorithm (CPU fp32) timed on this box's host cores on a bounded sample
+Secondary legs in the SAME line, so that the driver's 1/2/4/8-GPU runs carry them:
+  `r101_b64`  BASELINE.json config 3: ResNet-101 + FPN forward, batch 64 sharded over the N GPUs
+  `train`     BASELINE.json config 4: ResNet-50 + FPN forward+backward (frozen BN, stem + stage 1 frozen),
+              batch 8 per GPU, per-stage gradient buckets all-reduced by NCCL under the backward kernels
 
-`--impl reference` times the reference's CPU implementation of the path (the oracle port: the
-reference tree itself cannot travel to the GPU box) with all host threads on the same config.
+`--impl reference` times the reference's CPU implementation of the path with all host threads on the same
+config: the UNMODIFIED reference through oracle/reference_shim.py where its tree exists (the dev container),
+else the bit-identical oracle port (the reference is pure Python and cannot travel to the GPU box).
 """
 import argparse
 import json
@@ -97,16 +105,20 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
 
-    def summary(self):
-        sm, mx, reasons = [], [], set()
+    def mark(self):
+        return len(self.samples)
+
+    def summary(self, first=0, last=None):
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[first:last]:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
             except ValueError:
                 continue
             for name, val in zip(names, parts[3:7]):
@@ -116,32 +128,59 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw)}
 
 
-def time_cpu_oracle(depth, h, w, with_fpn, iters, warmup, threads):
-    """Reference algorithm (oracle port) on host cores: fp32, eval, no_grad."""
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the reference's algorithm on the host cores)
+# ---------------------------------------------------------------------------------------------------
+
+def cpu_forward_fn(depth, with_fpn):
+    """(callable(x) -> outputs, kind): the unmodified reference modules where the tree is importable
+    (oracle/reference_shim.py: /root/reference, dev container only), else the bit-identical oracle port."""
+    from oracle import reference_shim
     from oracle import resnet_fpn_oracle as orc
-    torch.set_num_threads(threads)
+    if reference_shim.available():
+        try:
+            pair = reference_shim.build_pair(depth, seed=0)
+            if pair is not None:
+                bb, neck = pair
+                if with_fpn:
+                    return (lambda x: neck(bb(x))), "reference"
+                return (lambda x: bb(x)), "reference"
+        except Exception as e:  # a broken tree must not take the bench down: fall back to the port
+            sys.stderr.write("reference shim failed (%s): timing the oracle port\n" % (e,))
     g = torch.Generator().manual_seed(0)
     bsd = orc.make_resnet_state(depth, generator=g)
     exp = orc.EXPANSION[orc.ARCH[depth][0]]
-    in_ch = [64 * 2 ** i * exp for i in range(4)]
-    nsd = orc.make_fpn_state(in_ch, 256, 5, generator=g)
-    x = make_batch(1, h, w, 0, torch.float32) if with_fpn else \
-        torch.randn(1, 3, h, w, generator=g)
+    nsd = orc.make_fpn_state([64 * 2 ** i * exp for i in range(4)], 256, 5, generator=g)
+    if with_fpn:
+        return (lambda x: orc.resnet_fpn_forward(bsd, nsd, x, depth)), "port"
+    return (lambda x: orc.resnet_forward(bsd, x, depth)), "port"
+
+
+def time_cpu(depth, h, w, with_fpn, iters, warmup, threads):
+    """Per-iteration seconds of the CPU forward: fp32, eval, no_grad.  with_fpn: the
+    R-depth + FPN path on the image padded to a multiple of 32; else BASELINE.json config 1 exactly (backbone
+    only, raw h x w)."""
+    torch.set_num_threads(threads)
+    fn, kind = cpu_forward_fn(depth, with_fpn)
+    g = torch.Generator().manual_seed(0)
+    x = make_batch(1, h, w, 0, torch.float32) if with_fpn else torch.randn(1, 3, h, w, generator=g)
     times = []
     with torch.no_grad():
         for i in range(warmup + iters):
             t0 = time.perf_counter()
-            if with_fpn:
-                orc.resnet_fpn_forward(bsd, nsd, x, depth)
-            else:
-                orc.resnet_forward(bsd, x, depth)
+            fn(x)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return times
+    return times, kind
+
+
+def median(v):
+    s = sorted(v)
+    return s[len(s) // 2] if len(s) % 2 else 0.5 * (s[len(s) // 2 - 1] + s[len(s) // 2])
 
 
 def run_reference(args):
@@ -150,9 +189,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    times = time_cpu_oracle(args.depth, args.height, args.width, True, args.steps, args.warmup, threads)
+    times, kind = time_cpu(args.depth, args.height, args.width, True, max(args.steps, 1), max(args.warmup, 1), threads)
     total = sum(times)
     value = len(times) / total
+    med = 1.0 / median(times)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "img/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -160,8 +200,11 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ResNet-%d + FPN forward, 800x1333 (padded 800x1344)" % args.depth,
                    "sample": "each step = 1 image on the host CPU (bounded sample of the batch-16 workload)"},
-        "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": "port",
-                         "sample": "%d x (1 image 3x800x1344 fp32, oracle port of resnet.py+fpn.py)" % len(times)},
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": threads, "kind": kind,
+                         "median_img_s": med, "best_img_s": 1.0 / min(times),
+                         "sample": "%d x (1 image 3x800x1344 fp32, %s, %d threads)" % (
+                             len(times), "unmodified reference modules" if kind == "reference"
+                             else "oracle port of resnet.py+fpn.py", threads)},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -169,37 +212,163 @@ def run_reference(args):
     return 0
 
 
-def run_train(args):
-    """Config 4 (secondary bench line): R50+FPN forward+backward with fixed random upstream gradients on
-    P2..P6, weights/images resident, per-stage flat fp32 gradient buckets all-reduced on a side stream."""
-    import torch.distributed as dist
-    from torch_detection_b200 import models, training
+# ---------------------------------------------------------------------------------------------------
+# GPU legs
+# ---------------------------------------------------------------------------------------------------
+
+def build_pair(depth, dev, train=False):
+    from torch_detection_b200 import models
     from torch_detection_b200.utils import obj_from_dict
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the all-reduce overlaps persistent one-CTA-per-SM kernels: keep NCCL on a few SMs and leave
-        # exactly those free (BucketAllReduce.sm_reserve), or every conv kernel would run a second wave
-        os.environ.setdefault("NCCL_MAX_CTAS", str(SM_RESERVE))
-        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    exp = 4 if args.depth >= 50 else 1
-    bb = obj_from_dict(dict(type="ResNet", depth=args.depth, frozen_stages=1, bn_eval=True, bn_frozen=True),
-                       parent=models.backbone)
+    exp = 4 if depth >= 50 else 1
+    kw = dict(frozen_stages=1, bn_eval=True, bn_frozen=True) if train else {}
+    bb = obj_from_dict(dict(type="ResNet", depth=depth, **kw), parent=models.backbone)
     bb.init_weights()
     neck = obj_from_dict(dict(type="FPN", in_channels=[64 * 2 ** i * exp for i in range(4)], out_channels=256,
                               num_outs=5), parent=models.necks)
     neck.init_weights()
-    bb, neck = bb.to(dev).train(), neck.to(dev).train()
+    bb, neck = bb.to(dev), neck.to(dev)
+    if train:
+        return bb.train(), neck.train()
+    return bb.eval(), neck.eval()
+
+
+class Ctx(object):
+    """Rank / device / collective plumbing of one bench process."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, self.world))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # the training leg's all-reduce overlaps persistent one-CTA-per-SM kernels: NCCL stays on a few SMs
+            # and exactly those are left free (BucketAllReduce.sm_reserve), or every conv would run a second wave
+            os.environ.setdefault("NCCL_MAX_CTAS", str(SM_RESERVE))
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = torch.tensor(list(values), device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_steps(ctx, fn, steps, warmup):
+    """W untimed steps, then exactly `steps` steps between barrier + synchronize, device events, max over ranks."""
+    for _ in range(max(warmup, 3)):
+        fn()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    ctx.barrier()
+    return ctx.max_over_ranks([e0.elapsed_time(e1)])[0], out
+
+
+def sustained_leg(ctx, fn, images_per_step, min_seconds, sampler):
+    """Loops the step until >= min_seconds of device time have passed (the power cap then sets the clock)."""
+    fn()
+    ctx.barrier()
+    first = sampler.mark() if sampler else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    steps = 0
+    while True:
+        for _ in range(20):
+            fn()
+        steps += 20
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
+    clocks = sampler.summary(first, sampler.mark()) if sampler else None
+    return {"value": ctx.world * images_per_step * steps / (ms / 1e3), "unit": "img/s", "seconds": ms / 1e3,
+            "steps": steps, "ms_per_step": ms / steps, "clocks": clocks}
+
+
+def e2e_leg(ctx, step, x_host, x_dev, out_like, steps, copy_levels):
+    """End to end from pinned host memory: double-buffered H2D on a copy stream, forward, D2H of the listed
+    pyramid levels.  Returns (img/s, h2d bytes, d2h bytes)."""
+    dev = ctx.dev
+    B = x_host.shape[0]
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    host_out = [torch.empty(out_like[i].shape, dtype=out_like[i].dtype).contiguous(
+        memory_format=torch.channels_last).pin_memory() for i in copy_levels]
+    main_stream = torch.cuda.current_stream(dev)
+
+    def loop(n_steps):
+        for b in range(2):
+            consumed[b].record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[0])
+            stage[0].copy_(x_host, non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n_steps):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < n_steps:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[nxt])
+                    stage[nxt].copy_(x_host, non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            main_stream.wait_event(ready[cur])
+            o = step(stage[cur])
+            consumed[cur].record(main_stream)
+            for h, lvl in zip(host_out, copy_levels):
+                h.copy_(o[lvl], non_blocking=True)
+
+    loop(3)
+    ctx.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    f0.record()
+    loop(steps)
+    f1.record()
+    ctx.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = max(ctx.max_over_ranks([max(f0.elapsed_time(f1), 0.0), t_wall * 1e3]))  # events vs wall clock: the slower
+    return (ctx.world * B * steps / (ms / 1e3), x_host.numel() * x_host.element_size(),
+            sum(h.numel() * h.element_size() for h in host_out))
+
+
+def train_leg(ctx, args, steps, warmup, launch_table=""):
+    """BASELINE.json config 4: R50+FPN forward+backward with fixed random upstream gradients on P2..P6,
+    weights/images resident, per-stage flat fp32 gradient buckets all-reduced on a side stream."""
+    from torch_detection_b200 import training
+    from oracle import resnet_fpn_oracle as orc  # FLOP model only
+    dev, world = ctx.dev, ctx.world
+    bb, neck = build_pair(args.depth, dev, train=True)
     sync = training.BucketAllReduce(defer=True, sm_reserve=SM_RESERVE if world > 1 else 0)
     bb.set_grad_sync(sync)
     neck.set_grad_sync(sync)
-    B = args.batch if args.batch != 16 else 8
-    x = make_batch(B, args.height, args.width, 100 + rank, torch.bfloat16).to(dev)
+    B = args.train_batch
+    x = make_batch(B, args.height, args.width, 100 + ctx.rank, torch.bfloat16).to(dev)
     params = [p for p in list(bb.parameters()) + list(neck.parameters()) if p.requires_grad]
     outs = neck(bb(x))
     g = torch.Generator().manual_seed(7)
@@ -214,70 +383,94 @@ def run_train(args):
         torch.autograd.backward(list(o), grads)
         sync.finish()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    ms_total, _ = timed_steps(ctx, step, steps, warmup)
+    b0, n0 = sync.bytes_reduced, sync.buckets_reduced
+    step()
+    allreduce_mb = (sync.bytes_reduced - b0) / 1e6
+    buckets = sync.buckets_reduced - n0
+    # cost of the collective: the same steps with the all-reduce switched off (buckets still copied out), and
+    # the device time of the collectives themselves on the side stream
+    exposed_ms = coll_ms = None
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    if rank == 0:
-        from oracle import resnet_fpn_oracle as orc
+        sync.profile(True)
+        for _ in range(3):
+            step()
+        coll_ms = sync.collective_ms() / 3.0
+        sync.profile(False)
+        sync.enabled = False
+        ms_off, _ = timed_steps(ctx, step, steps, 2)
+        sync.enabled = True
+        exposed_ms = ms_total / steps - ms_off / steps
+        coll_ms = ctx.max_over_ranks([coll_ms])[0]
+    res = None
+    if ctx.rank == 0:
         Hp, Wp = x.shape[2], x.shape[3]
         fwd = orc.conv_flops(args.depth, Hp, Wp)[0]
         launches = {"fwd": bb._last_run[0].num_launches + neck._last_run[0].num_launches,
                     "bwd": bb._last_bwd_run[0].num_launches + neck._last_bwd_run[0].num_launches}
         bwd_fl = bb._last_bwd_run[0].flops + neck._last_bwd_run[0].flops
-        table = []
-        for mod in (neck, bb):
-            plan, ext = mod._last_bwd_run
-            info = plan.launch_info()
-            for inf, t in zip(info, plan.run_timed(ext)):
-                inf = dict(inf)
-                inf["module"] = type(mod).__name__ + ".backward"
-                inf["ms"] = t
-                table.append(inf)
-        if args.launch_table:
-            with open(args.launch_table, "w") as f:
-                json.dump(table, f, indent=1)
-        value = world * B * args.steps / (ms_total / 1e3)
-        wg = [t for t in table if t["kind"] == 5]
-        dg = [t for t in table if t["kind"] == 3]
-        emit(({
+        value = world * B * steps / (ms_total / 1e3)
+        res = {
             "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
-            "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "config 4: ResNet-%d + FPN forward+backward, batch %d per GPU, %dx%d" %
-                                   (args.depth, B, Hp, Wp),
-                       "grad_allreduce": "%d flat fp32 buckets, %.1f MB per step, NCCL on a side stream" %
-                                         (sync.buckets_reduced // (args.steps + max(args.warmup, 3)),
-                                          sync.bytes_reduced / (args.steps + max(args.warmup, 3)) / 1e6)},
+            "img_s": value, "value": value, "unit": "img/s", "n_gpus": world, "steps": steps,
+            "ms_per_step": ms_total / steps, "batch_per_gpu": B,
+            "allreduce_mb": allreduce_mb if world > 1 else 0.0, "buckets_per_step": buckets,
+            "allreduce_device_ms": coll_ms, "allreduce_exposed_ms": exposed_ms,
+            "overlap_ms": (coll_ms - max(exposed_ms, 0.0)) if coll_ms is not None else None,
+            "sm_reserve": SM_RESERVE if world > 1 else 0,
             "gflop_per_image": {"forward": fwd / 1e9, "backward_executed": bwd_fl / B / 1e9},
             "tflops_per_gpu": (value / world) * (fwd + bwd_fl / B) / 1e12,
-            "launches_per_step": launches, "gpu_launches": (launches["fwd"] + launches["bwd"]) * args.steps,
-            "backward_kernels": {
+            "launches_per_step": launches,
+            "gpu_launches": (launches["fwd"] + launches["bwd"]) * steps,
+        }
+        if launch_table:
+            table = []
+            for mod in (neck, bb):
+                plan, ext = mod._last_bwd_run
+                for inf, t in zip(plan.launch_info(), plan.run_timed(ext)):
+                    inf = dict(inf)
+                    inf["module"] = type(mod).__name__ + ".backward"
+                    inf["ms"] = t
+                    table.append(inf)
+            with open(launch_table, "w") as f:
+                json.dump(table, f, indent=1)
+            wg = [t for t in table if t["kind"] == 5]
+            dg = [t for t in table if t["kind"] == 3]
+            res["backward_kernels"] = {
                 "wgrad": {"launches": len(wg), "ms": sum(t["ms"] for t in wg),
                           "tflops": sum(t["flops"] for t in wg) / max(sum(t["ms"] for t in wg), 1e-9) / 1e9},
                 "dgrad": {"launches": len(dg), "ms": sum(t["ms"] for t in dg),
                           "tflops": sum(t["flops"] for t in dg) / max(sum(t["ms"] for t in dg), 1e-9) / 1e9},
-                "other_ms": sum(t["ms"] for t in table if t["kind"] not in (3, 5))},
-        }))
+                "other_ms": sum(t["ms"] for t in table if t["kind"] not in (3, 5))}
+    del bb, neck, sync, x, grads, params
+    torch.cuda.empty_cache()
+    from torch_detection_b200 import engine
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+        engine.set_sm_reserve(dev, 0)
+    return res
+
+
+def r101_leg(ctx, args, steps, warmup):
+    """BASELINE.json config 3: ResNet-101 + FPN forward, batch 64 sharded over the N GPUs (64 / N per GPU)."""
+    from oracle import resnet_fpn_oracle as orc  # FLOP model only
+    per_gpu = max(64 // ctx.world, 1)
+    bb, neck = build_pair(101, ctx.dev)
+    x = make_batch(per_gpu, args.height, args.width, 300 + ctx.rank, torch.bfloat16).to(ctx.dev)
+
+    def step():
+        with torch.no_grad():
+            return neck(bb(x))
+
+    ms, _ = timed_steps(ctx, step, steps, warmup)
+    value = ctx.world * per_gpu * steps / (ms / 1e3)
+    flops = orc.conv_flops(101, x.shape[2], x.shape[3])[0]
+    res = {"img_s": value, "unit": "img/s", "global_batch": per_gpu * ctx.world, "batch_per_gpu": per_gpu,
+           "ms_per_step": ms / steps, "steps": steps, "tflops_per_gpu": (value / ctx.world) * flops / 1e12,
+           "workload": "config 3: ResNet-101 + FPN forward, batch 64 sharded over %d GPU(s), %dx%d" % (
+               ctx.world, x.shape[2], x.shape[3])}
+    del bb, neck, x
+    torch.cuda.empty_cache()
+    return res
 
 
 _REAL_STDOUT = None
@@ -307,52 +500,42 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--train-batch", type=int, default=8, help="images per GPU of the training leg (config 4)")
     ap.add_argument("--depth", type=int, default=50)
     ap.add_argument("--height", type=int, default=800)
     ap.add_argument("--width", type=int, default=1333)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true",
+                    help="skip the sustained / full-copy / R101 batch-64 / training legs (quick A/B runs)")
     ap.add_argument("--launch-table", default="", help="write the per-launch timing table (JSON) here")
     ap.add_argument("--io-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="fp32 = the fp32-I/O mode (split-precision kernels, <= 1e-4 vs the fp32 reference); secondary line")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="train = BASELINE.json config 4: forward+backward, frozen BN, frozen stem+stage 1, "
+                    help="train = BASELINE.json config 4 alone: forward+backward, frozen BN, frozen stem+stage 1, "
                          "batch 8 per GPU, bucketed NCCL gradient all-reduce overlapped with backward")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.mode == "train":
-        return run_train(args)
 
-    import torch.distributed as dist
-    from torch_detection_b200 import models
-    from torch_detection_b200.utils import obj_from_dict
     from oracle import resnet_fpn_oracle as orc  # FLOP model + cpu_baseline only
+    ctx = Ctx(args)
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    if args.mode == "train":
+        if args.batch != 16:
+            args.train_batch = args.batch
+        res = train_leg(ctx, args, args.steps, args.warmup, args.launch_table)
+        if rank == 0:
+            res.update({"warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                        "dtype": "bf16", "data": "synthetic",
+                        "config": {"workload": "config 4: ResNet-%d + FPN forward+backward, batch %d per GPU, 800x1344"
+                                               % (args.depth, args.train_batch)}})
+            emit(res)
+        ctx.close()
+        return 0
 
     # ---- model (reference build API, reference init, seed 0) -------------------------------------
-    torch.manual_seed(0)
-    exp = 4 if args.depth >= 50 else 1
-    in_ch = [64 * 2 ** i * exp for i in range(4)]
-    bb = obj_from_dict(dict(type="ResNet", depth=args.depth), parent=models.backbone)
-    bb.init_weights()
-    neck = obj_from_dict(dict(type="FPN", in_channels=in_ch, out_channels=256, num_outs=5),
-                         parent=models.necks)
-    neck.init_weights()
-    bb = bb.to(dev).eval()
-    neck = neck.to(dev).eval()
-
+    bb, neck = build_pair(args.depth, dev)
     B, H, W = args.batch, args.height, args.width
     io_dtype = torch.float32 if args.io_dtype == "fp32" else torch.bfloat16
     x_host = make_batch(B, H, W, 100 + rank, io_dtype).pin_memory()
@@ -363,77 +546,28 @@ def main():
         with torch.no_grad():
             return neck(bb(x))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput ------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- device-resident throughput (the headline `value`) ---------------------------------------------
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        outs = step(x_dev)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    ctx.barrier()
+    c_first = sampler.mark() if sampler else 0
+    ms_total, outs = timed_steps(ctx, lambda: step(x_dev), args.steps, 0)
     value = world * B * args.steps / (ms_total / 1e3)
 
-    # ---- end to end from pinned host buffers (double-buffered H2D on a copy stream) --------------------
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    p6_host = torch.empty((B, 256, outs[-1].shape[2], outs[-1].shape[3]), dtype=io_dtype).contiguous(
-        memory_format=torch.channels_last).pin_memory()
-    main_stream = torch.cuda.current_stream(dev)
-
-    def e2e_loop(n_steps):
-        for b in range(2):
-            consumed[b].record(main_stream)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[0])
-            stage[0].copy_(x_host, non_blocking=True)
-            ready[0].record(copy_stream)
-        for i in range(n_steps):
-            cur, nxt = i % 2, (i + 1) % 2
-            if i + 1 < n_steps:
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(consumed[nxt])
-                    stage[nxt].copy_(x_host, non_blocking=True)
-                    ready[nxt].record(copy_stream)
-            main_stream.wait_event(ready[cur])
-            o = step(stage[cur])
-            consumed[cur].record(main_stream)
-            p6_host.copy_(o[-1], non_blocking=True)
-        return o
-
-    e2e_loop(3)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    f0.record()
-    e2e_loop(args.steps)
-    f1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    ms2 = torch.tensor([max(f0.elapsed_time(f1), 0.0), t_wall * 1e3], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(ms2.max().item())  # device events vs wall clock: take the slower
-    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
-    if sampler:
-        sampler.stop()
+    # ---- end to end from pinned host buffers -----------------------------------------------------------
+    e2e_value, h2d, d2h = e2e_leg(ctx, step, x_host, x_dev, outs, args.steps, [len(outs) - 1])
+    c_last = sampler.mark() if sampler else 0
+    full = None
+    sustained = None
+    if not args.no_extra_legs:
+        fv, fh, fd = e2e_leg(ctx, step, x_host, x_dev, outs, max(args.steps // 2, 5), list(range(len(outs))))
+        full = {"value": fv, "unit": "img/s", "h2d_bytes_per_step": fh, "d2h_bytes_per_step": fd,
+                "note": "as e2e, but ALL of P2..P6 are copied back to pinned host memory every step (PCIe-bound)"}
+        sustained = sustained_leg(ctx, lambda: step(x_dev), B, 3.0, sampler)
 
     # ---- roofline of the tcgen05 GEMM kernel family, measured live with CUDA events --------------------
     roof = None
@@ -461,44 +595,65 @@ def main():
         all_ms = sum(l["ms"] for l in launches)
         gemm_ms = sum(l["ms"] for l in gemm)
         gemm_fl = sum(l["flops"] for l in gemm)
-        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        peak = float(peaks["bf16_tflops"])  # burst: the denominator BASELINE.md section 3 names
         achieved = dom_fl / (dom_ms * 1e-3) / 1e12
         traffic, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_s5_traffic.json")
-        if os.path.isfile(tpath) and args.depth == 50 and args.batch == 16:
-            with open(tpath) as f:
-                tj = json.load(f)
-            traffic = tj["roofline_traffic_bytes"]
-            traffic_note = ("DRAM read+write of the family's largest launch (FPN P2 3x3, algorithmic 1102.2 MB) from "
-                            + tj["source"])
+        for tname in ("r2_traffic.json", "r1_s5_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.isfile(tpath) and args.depth == 50 and args.batch == 16:
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic = tj["roofline_traffic_bytes"]
+                traffic_note = ("DRAM read+write of the family's largest launch (FPN P2 3x3, algorithmic 1102.2 MB) from "
+                                + tj["source"])
+                break
+        whole = (value / world) * orc.conv_flops(args.depth, Hp, Wp)[0] / 1e12
         roof = {
             "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-            "kernel": "256-wide tcgen05 implicit-GEMM launches (conv_gemm_kernel<256,...> incl. CTA pairs, and "
-                      "conv_swap_kernel: 128x256x16 MMAs; all launches of one step: %d launches, %.1f%% of step time)"
+            "kernel": "256-wide tcgen05 implicit-GEMM launches (conv_gemm_kernel<256,...> incl. CTA pairs and dual-source, "
+                      "and conv_swap_kernel: 128x256x16 MMAs; all launches of one step: %d launches, %.1f%% of step time)"
                       % (len(dom), 100.0 * dom_ms / all_ms),
-            "peak_source": peaks["_source"] + ", sustained bf16 (kernel timed inside a long step)",
-            "frac_of_burst_peak": achieved / float(peaks["bf16_tflops"]),
+            "peak_source": peaks["_source"] + ", burst bf16 (cuBLAS 8192^3, best of 10)",
+            "frac_of_sustained_peak": achieved / float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])),
             "all_gemm_launches": {"tflops": gemm_fl / (gemm_ms * 1e-3) / 1e12, "ms": gemm_ms,
                                   "share_of_step": gemm_ms / all_ms},
-            "whole_step_tflops": (value / world) * orc.conv_flops(args.depth, Hp, Wp)[0] / 1e12,
+            "whole_step_tflops": whole, "whole_step_frac": whole / peak,
             "launch_ms_sum": all_ms,
         }
         if args.launch_table:
             with open(args.launch_table, "w") as f:
                 json.dump(launches, f, indent=1)
+    n_launch = bb._last_run[0].num_launches + neck._last_run[0].num_launches
+    del bb, neck, outs, x_dev
+    torch.cuda.empty_cache()
+
+    # ---- secondary legs: config 3 (R101, batch 64 sharded) and config 4 (training, NCCL all-reduce) ------
+    r101 = train = None
+    if not args.no_extra_legs and args.io_dtype == "bf16":
+        r101 = r101_leg(ctx, args, 5, 3)
+        train = train_leg(ctx, args, 10, 3)
+    if sampler:
+        sampler.stop()
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only) ------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times = time_cpu_oracle(args.depth, H, W, True, 6, 1, threads)
-        cpu = {"value": len(times) / sum(times), "unit": "img/s", "cores": threads, "kind": "port",
-               "sample": "6 x (1 image 3x%dx%d fp32, ResNet-%d+FPN, oracle port, %d threads); best %.3f s"
-                         % (Hp, Wp, args.depth, threads, min(times))}
+        t_fpn, kind = time_cpu(args.depth, H, W, True, 10, 2, threads)
+        t_bb, _ = time_cpu(args.depth, H, W, False, 10, 2, threads)
+        t_one, _ = time_cpu(args.depth, H, W, False, 2, 1, 1)
+        gf_fpn = orc.conv_flops(args.depth, Hp, Wp)[0] / 1e9
+        cpu = {"value": 1.0 / median(t_fpn), "unit": "img/s", "cores": threads, "kind": kind,
+               "best_img_s": 1.0 / min(t_fpn), "gflops": gf_fpn / median(t_fpn),
+               "sample": "median of 10 x (1 image 3x%dx%d fp32, ResNet-%d+FPN, %s, %d threads) after 2 warm-up"
+                         % (Hp, Wp, args.depth, "unmodified reference" if kind == "reference" else "oracle port", threads),
+               "config1_backbone_only": {
+                   "workload": "BASELINE.json config 1: ResNet-%d backbone, 1x3x%dx%d fp32" % (args.depth, H, W),
+                   "median_img_s": 1.0 / median(t_bb), "best_img_s": 1.0 / min(t_bb), "cores": threads, "iters": len(t_bb),
+                   "one_thread_img_s": 1.0 / median(t_one), "one_thread_iters": len(t_one)}}
 
     if rank == 0:
-        n_launch = bb._last_run[0].num_launches + neck._last_run[0].num_launches
         flops_img = orc.conv_flops(args.depth, Hp, Wp)[0]
         line = {
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
@@ -513,20 +668,20 @@ def main():
                        "parallelism": "batch sharded, no data-path collective",
                        "l2": "per-step working set (~1.4 GB/img of activations) >> 126 MB L2, no explicit flush"},
             "tflops_per_gpu": (value / world) * flops_img / 1e12,
-            "e2e": {"value": e2e_value, "unit": "img/s",
-                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
-                    "d2h_bytes_per_step": p6_host.numel() * p6_host.element_size(),
-                    "note": "public API neck(backbone(x)); pinned bf16 host batch -> H2D (copy stream, "
-                            "double buffered) -> forward -> D2H of P6"},
+            "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "public API neck(backbone(x)); pinned host batch -> H2D (copy stream, double buffered) -> "
+                            "forward -> D2H of P6; P2..P5 stay on the device, where their consumers (the detection "
+                            "heads) run -- e2e_full_copy moves all five levels"},
+            "e2e_full_copy": full,
+            "sustained": sustained,
             "gpu_launches": n_launch * args.steps,
             "launches_per_step": n_launch,
-            "clocks": sampler.summary() if sampler else None,
+            "clocks": sampler.summary(c_first, c_last) if sampler else None,
             "roofline": roof, "cpu_baseline": cpu,
+            "r101_b64": r101, "train": train,
         }
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
     return 0
 
 

@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 9
+#define TDET_ABI_VERSION 10
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -104,10 +104,19 @@ enum {
                                tdet_pack_conv_weight_split; the GEMM accumulates hi*hi + lo*hi + hi*lo in
                                fp32 and the epilogue splits its fp32 result again.  cin / cout stay the
                                LOGICAL channel counts.  Valid on PREP, STEM, MAXPOOL, CONV. */
-  TDET_FLAG_POOL = 16       /* TDET_OP_STEM only: the kernel also applies the 3x3/2 p1 max-pool that follows the
+  TDET_FLAG_POOL = 16,      /* TDET_OP_STEM only: the kernel also applies the 3x3/2 p1 max-pool that follows the
                                stem (resnet.py:218,258) and y is the POOLED tensor [n][hp][wp][64], hp =
                                (ho - 1) / 2 + 1; the stem's own output never reaches memory.  Needs
                                TDET_FLAG_RELU (out-of-image window positions are taken as 0). */
+  TDET_FLAG_DUAL = 32       /* TDET_OP_CONV, 1x1 / stride 1 / cout % 256 == 0 only: a SECOND input,
+                               y = act( ([x | x2'] * wgt^T) * scale + shift ),  x2' = x2 sampled with stride2,
+                               i.e. wgt is the K-concatenation [cout][cin + cin2] of two 1x1 weight matrices and both
+                               GEMMs run in one launch into one accumulator.  This is a stage's first Bottleneck:
+                               conv3 + bn3 and the projection shortcut downsample(x) + its BN + the residual add +
+                               ReLU (resnet.py:110-118 with :129-136) without the shortcut tensor ever reaching memory
+                               (tdet_pack_conv_weight_scaled folds each BatchNorm's scale into its half of wgt, `shift`
+                               is the sum of the two BN shifts, scale = NULL).  x and x2 are plain tensors of ONE
+                               16-bit format (exponent 0; their metas only carry |max|); no residual / coarse / mask. */
 };
 
 /* Per-tensor metadata living in device memory (8 bytes): true value = stored * 2^e; amax_bits is
@@ -222,6 +231,12 @@ typedef struct tdet_op {
                                 weights from tdet_pack_grouped_conv_weight (ResNeXt, resnext.py:84-87) */
   float* dw;                 /* WGRAD / COLSUM: fp32 accumulator */
   const tdet_tensor_meta* gy_meta; /* WGRAD: exponent of gy (NULL = 0) */
+  /* ---- second input (TDET_FLAG_DUAL) ---- */
+  const void* x2;            /* [n][h2][w2][cin2] of x2_dtype == x_dtype; ho == (h2-1)/stride2+1, wo likewise */
+  const tdet_tensor_meta* x2_meta;
+  int32_t cin2, stride2, h2, w2;
+  int32_t x2_dtype;
+  int32_t reserved0;
 } tdet_op;
 
 typedef struct tdet_plan tdet_plan; /* opaque */
@@ -246,6 +261,11 @@ int tdet_stem_staging_dims(int ho, int wo, int* hp, int* wp);
  * dtype = TDET_BF16 or TDET_F16. */
 int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin, int kh, int kw,
                           int dtype, void* stream);
+/* Same with a per-output-channel factor (a folded BatchNorm scale) multiplied in before rounding, written into a
+ * row-pitched destination: w_packed[co * ld + (r*kw + s)*cin + ci] = round16(scale[co] * w[co][ci][r][s]).
+ * ld >= kh*kw*cin lets two matrices be packed side by side ([W | W2], TDET_FLAG_DUAL). */
+int tdet_pack_conv_weight_scaled(const float* w_oihw, const float* scale, void* w_packed, int cout, int cin, int kh,
+                                 int kw, int ld, int dtype, void* stream);
 /* fp32 [64][3][7][7] -> bf16 [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
 int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
 /* eval-mode BatchNorm2d -> per-channel fp32 scale = gamma/sqrt(var+eps), shift = beta-mean*scale

@@ -220,6 +220,93 @@ def test_conv_upsample_add(cuda_device, shape, dtype):
     assert err <= TOL[dtype], "rel-L2 %.3e" % err
 
 
+DUAL_CASES = [
+    # name, n, h2, w2, cin (main), cin2 (shortcut input), cout, stride2
+    ("layer1.0", 2, 20, 28, 64, 64, 256, 1),
+    ("layer2.0", 2, 21, 27, 128, 256, 512, 2),
+    ("layer3.0", 1, 26, 42, 256, 512, 1024, 2),
+    ("layer4.0_long_k", 2, 25, 42, 512, 1024, 2048, 2),      # 24 k-blocks: the CTA-pair kernel
+    ("many_tiles", 3, 100, 84, 64, 64, 256, 1),               # resident weight panel
+    ("many_tiles_s2", 2, 101, 83, 128, 256, 512, 2),
+]
+
+
+def _dual_reference(x, x2, w_a, w_b, sc_a, sc_b, sh_a, sh_b, s2, dtype):
+    """fp32 reference on the kernel's operands: the BatchNorm scales are folded into the 16-bit weights."""
+    wa = (w_a * sc_a.view(-1, 1, 1, 1)).to(dtype).float()
+    wb = (w_b * sc_b.view(-1, 1, 1, 1)).to(dtype).float()
+    ref = F.conv2d(x.float(), wa) + F.conv2d(x2.float(), wb, None, s2) + (sh_a + sh_b).view(1, -1, 1, 1)
+    return F.relu(ref)
+
+
+@pytest.mark.parametrize("case", DUAL_CASES, ids=[c[0] for c in DUAL_CASES])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_conv_dual_source(cuda_device, case, dtype):
+    """TDET_FLAG_DUAL: conv3 + bn3 and the projection shortcut (1x1 / stride s + BN) + add + ReLU of a stage's
+    first bottleneck in ONE launch (resnet.py:110-118, :129-136): one GEMM over [x | x2] with the K-concatenated,
+    scale-folded weights, against the two fp32 convs."""
+    from torch_detection_b200 import engine
+    name, n, h2, w2, cin, cin2, cout, s2 = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    ho, wo = (h2 - 1) // s2 + 1, (w2 - 1) // s2 + 1
+    x = _nhwc(torch.randn(n, cin, ho, wo, generator=g).to(dev), dtype)
+    x2 = _nhwc(torch.randn(n, cin2, h2, w2, generator=g).to(dev), dtype)
+    w_a = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(dev)
+    w_b = (torch.randn(cout, cin2, 1, 1, generator=g) * (2.0 / cin2) ** 0.5).to(dev)
+    sc_a, sc_b = ((0.5 + torch.rand(cout, generator=g)).to(dev) for _ in range(2))
+    sh_a, sh_b = ((0.3 * torch.randn(cout, generator=g)).to(dev) for _ in range(2))
+    wcat = engine.pack_dual_weight(w_a, sc_a, w_b, sc_b, dtype)
+    assert torch.equal(wcat[:, :cin].float(), (w_a * sc_a.view(-1, 1, 1, 1)).to(dtype).float().view(cout, cin))
+    assert torch.equal(wcat[:, cin:].float(), (w_b * sc_b.view(-1, 1, 1, 1)).to(dtype).float().view(cout, cin2))
+    y = engine.nhwc_empty(n, ho, wo, cout, dev, dtype)
+    op = engine.op_conv(engine.act_of(x), wcat, engine.act_of(y), 1, 1, 1, 0, 1, shift=sh_a + sh_b, relu=True,
+                        dual=(engine.act_of(x2), s2))
+    engine.run_op(op, dev)
+    torch.cuda.synchronize()
+    ref = _dual_reference(x, x2, w_a, w_b, sc_a, sc_b, sh_a, sh_b, s2, dtype)
+    err = rel_l2(y.float(), ref)
+    print("dual %s %s rel-L2 %.3e" % (name, dtype, err))
+    assert err <= TOL[dtype], "rel-L2 %.3e" % err
+
+
+def test_conv_dual_source_scaled_output(cuda_device):
+    """A dual conv writes an fp16 output with a device-chosen exponent: the bound uses the larger |max| of its two
+    (plain bf16) inputs, whose magnitudes differ by orders of magnitude here."""
+    from torch_detection_b200 import engine
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    n, h2, w2, cin, cin2, cout, s2 = 2, 30, 44, 128, 256, 512, 2
+    ho, wo = (h2 - 1) // s2 + 1, (w2 - 1) // s2 + 1
+    for mags in ((1.0, 1.0), (3.0e3, 2.0e-2), (1.0e-3, 40.0)):
+        arena = engine.MetaArena(3, dev)
+        m_x, m_x2, m_y = arena.new(), arena.new(), arena.new()
+        x = _nhwc((torch.randn(n, cin, ho, wo, generator=g) * mags[0]).to(dev))
+        x2 = _nhwc((torch.randn(n, cin2, h2, w2, generator=g) * mags[1]).to(dev))
+        arena.tensor[0, 1] = x.float().abs().max().view(torch.int32)
+        arena.tensor[1, 1] = x2.float().abs().max().view(torch.int32)
+        w_a = (torch.randn(cout, cin, 1, 1, generator=g) * (2.0 / cin) ** 0.5).to(dev)
+        w_b = (torch.randn(cout, cin2, 1, 1, generator=g) * (2.0 / cin2) ** 0.5).to(dev)
+        sc_a, sc_b = ((0.5 + torch.rand(cout, generator=g)).to(dev) for _ in range(2))
+        sh = (0.3 * mags[0] * torch.randn(cout, generator=g)).to(dev)
+        wcat = engine.pack_dual_weight(w_a, sc_a, w_b, sc_b, torch.bfloat16)
+        y = engine.Act(torch.empty(n * ho * wo * cout, dtype=torch.float16, device=dev), (n, ho, wo, cout),
+                       torch.float16, m_y)
+        op = engine.op_conv(engine.Act(x, (n, ho, wo, cin), torch.bfloat16, m_x), wcat, y, 1, 1, 1, 0, 1, shift=sh,
+                            relu=True, consts=engine.bound_consts(wcat, None, sh), scaled_out=True,
+                            dual=(engine.Act(x2, (n, h2, w2, cin2), torch.bfloat16, m_x2), s2))
+        engine.run_op(op, dev)
+        torch.cuda.synchronize()
+        e_y, amax_y = arena.read()[2]
+        y_true = (y.buf.view(n, ho, wo, cout).float() * 2.0 ** e_y).permute(0, 3, 1, 2)
+        ref = _dual_reference(x, x2, w_a, w_b, sc_a, sc_b, sh, torch.zeros_like(sh), s2, torch.bfloat16)
+        err = rel_l2(y_true, ref)
+        print("dual scaled mags %s: e_y=%d rel-L2 %.2e" % (mags, e_y, err))
+        assert torch.isfinite(y_true).all() and err <= TOL[torch.float16]
+        assert abs(amax_y - float(ref.abs().max())) <= 2e-3 * amax_y
+        assert float(y.buf.float().abs().max()) < 2.0 ** 15
+
+
 @pytest.mark.parametrize("magnitude", [1.0, 3.0e4, 2.0e-5])
 def test_scaled_fp16_chain(cuda_device, magnitude):
     """Per-tensor power-of-two exponents: conv -> (conv + residual) with device-chosen output

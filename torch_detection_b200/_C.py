@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # tdet_status
 OK = 0
@@ -33,6 +33,7 @@ FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4
 FLAG_SPLIT = 8
 FLAG_POOL = 16
+FLAG_DUAL = 32
 
 
 class TdetOp(ctypes.Structure):
@@ -56,6 +57,9 @@ class TdetOp(ctypes.Structure):
         ("mask", ctypes.c_void_p), ("gy", ctypes.c_void_p),
         ("gy_dtype", ctypes.c_int32), ("groups", ctypes.c_int32),
         ("dw", ctypes.c_void_p), ("gy_meta", ctypes.c_void_p),
+        ("x2", ctypes.c_void_p), ("x2_meta", ctypes.c_void_p),
+        ("cin2", ctypes.c_int32), ("stride2", ctypes.c_int32), ("h2", ctypes.c_int32), ("w2", ctypes.c_int32),
+        ("x2_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -76,7 +80,7 @@ class TdetError(RuntimeError):
 EXPORTS = [
     "tdet_abi_version", "tdet_last_error", "tdet_device_supported",
     "tdet_stem_staging_dims", "tdet_set_sm_reserve",
-    "tdet_pack_conv_weight", "tdet_pack_conv_weight_split", "tdet_pack_stem_weight_split",
+    "tdet_pack_conv_weight", "tdet_pack_conv_weight_scaled", "tdet_pack_conv_weight_split", "tdet_pack_stem_weight_split",
     "tdet_pack_grouped_conv_weight", "tdet_pack_dgrad_weight", "tdet_pack_stem_weight", "tdet_fold_bn",
     "tdet_conv_bound_consts",
     "tdet_op_run", "tdet_plan_create", "tdet_plan_run", "tdet_plan_run_range", "tdet_plan_run_timed",
@@ -103,6 +107,7 @@ def lib():
     L.tdet_device_supported.argtypes = [i32]
     L.tdet_set_sm_reserve.argtypes = [i32, i32]
     L.tdet_pack_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.tdet_pack_conv_weight_scaled.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_conv_weight_split.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     L.tdet_pack_stem_weight_split.argtypes = [vp, vp, vp]
     L.tdet_pack_grouped_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]

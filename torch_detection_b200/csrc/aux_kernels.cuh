@@ -161,6 +161,26 @@ pack_weight_kernel(const float* __restrict__ w, W* __restrict__ out, int cout, i
   }
 }
 
+// fp32 OIHW -> 16-bit out[co * ld + (r*kw + s)*cin + ci] = round16(scale[co] * w): a folded BatchNorm scale multiplied
+// into the rows, written with a row pitch so that two matrices can sit side by side ([W | W2], TDET_FLAG_DUAL)
+template <typename W>
+__global__ void __launch_bounds__(256)
+pack_weight_scaled_kernel(const float* __restrict__ w, const float* __restrict__ scale, W* __restrict__ out, int cout,
+                          int cin, int kh, int kw, int ld) {
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    long long t = i / cin;
+    const int s = static_cast<int>(t % kw);
+    t /= kw;
+    const int r = static_cast<int>(t % kh);
+    const int co = static_cast<int>(t / kh);
+    const float v = w[((static_cast<long long>(co) * cin + ci) * kh + r) * kw + s] * (scale ? scale[co] : 1.0f);
+    out[static_cast<long long>(co) * ld + (static_cast<long long>(r) * kw + s) * cin + ci] = to_w16<W>(v);
+  }
+}
+
 // split precision: fp32 OIHW -> bf16 [O][kh][kw][2*I]: per tap I hi values then I lo values
 __global__ void __launch_bounds__(256)
 pack_weight_split_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin, int kh, int kw) {

@@ -137,6 +137,15 @@ struct ConvGemmParams {
   const TensorMeta* coarse_meta;  // nullable
   TensorMeta* out_meta;           // nullable; when set the true |max| of the output is recorded
   const float* bound_consts;      // {G, max|shift|}, required iff out_scaled
+  // DUAL (1x1 / stride-1 convs): a SECOND A source -- a stage's projection shortcut, 1x1 with stride2 over x2 --
+  // is contracted after the main K loop into the SAME accumulator: the weight matrix is the K-concatenation
+  // [W (cin) | W2 (cin2)] with both BatchNorm scales folded into its rows, so the shortcut tensor never exists in
+  // memory.  Both sources are plain tensors of one format (exponent 0).
+  CUtensorMap tmap_a2;            // 2D tiled (stride2 == 1) or 4D im2col (stride2 > 1) view of x2
+  int dual;
+  int k_chunks2;
+  int stride2;
+  const TensorMeta* in2_meta;     // nullable
 };
 
 // BRES_KB > 0: the whole weight panel (up to BRES_KB k-blocks; requires a single n-tile) is loaded
@@ -267,6 +276,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (p.has_res) tma_prefetch_desc(&p.tmap_res);
     if (p.mask_tma) tma_prefetch_desc(&p.tmap_mask);
     if (p.coarse_tma) tma_prefetch_desc(&p.tmap_coarse);
+    if (p.dual) tma_prefetch_desc(&p.tmap_a2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -336,7 +346,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   // block-diagonal weight matrix
   const int kcn = p.grouped ? 1 : p.k_chunks;
   const int nv = (SPLIT && p.split) ? 3 : 1;  // virtual K passes: hi*hi, lo*hi, hi*lo
-  const int num_kb = p.kh * p.kw * kcn * nv;
+  const int num_kb = p.kh * p.kw * kcn * nv + (p.dual ? p.k_chunks2 : 0);  // DUAL: + the second source's k-blocks
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (A, B)
@@ -468,6 +478,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
          }
+        }
+      }
+      if (!SPLIT && p.dual) {
+        // second source: 1x1 / stride2 over x2 on this conv's output pixel grid; its weights are columns
+        // [cin, cin + cin2) of the concatenated matrix
+        const int m0 = m_ld * kBM;
+        const int q0 = m0 % p.Wo;
+        const int t2 = m0 / p.Wo;
+        const int p0 = t2 % p.Ho;
+        const int n2 = t2 / p.Ho;
+        for (int kc = 0; kc < p.k_chunks2; ++kc) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (lane == 0) {
+            const uint32_t dst_a = smem_a + stage * kABytes;
+            const uint32_t dst_b = smem_b + stage * L::kBBytes;
+            const int kcol = p.cin + kc * kBK;
+            if (PAIR) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_tx);
+              const uint32_t lb = mapa_shared(full_bar(stage), 0);
+              if (p.stride2 == 1) tma_load_2d_pair(dst_a, &p.tmap_a2, lb, kc * kBK, m0);
+              else tma_load_im2col_4d_pair(dst_a, &p.tmap_a2, lb, kc * kBK, q0 * p.stride2, p0 * p.stride2, n2, 0, 0);
+              tma_load_2d_pair(dst_b, &p.tmap_b, lb, kcol, n0 + static_cast<int>(cta_rank) * (BN / 2));
+            } else {
+              const uint32_t fb = full_bar(stage);
+              mbar_arrive_expect_tx(fb, stage_tx);
+              if (p.stride2 == 1) tma_load_2d(dst_a, &p.tmap_a2, fb, kc * kBK, m0);
+              else tma_load_im2col_4d(dst_a, &p.tmap_a2, fb, kc * kBK, q0 * p.stride2, p0 * p.stride2, n2, 0, 0);
+              if (BRES_KB == 0) tma_load_2d(dst_b, &p.tmap_b, fb, kcol, n0);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -698,7 +740,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int e_out = 0;
     if (p.out_scaled) {
       float bound = p.bound_consts[1];
-      const float a_in = p.in_meta ? __uint_as_float(p.in_meta->amax_bits) : 0.0f;
+      float a_in = p.in_meta ? __uint_as_float(p.in_meta->amax_bits) : 0.0f;
+      if (p.dual && p.in2_meta) a_in = fmaxf(a_in, __uint_as_float(p.in2_meta->amax_bits));  // (G of [W | W2])
       bound += p.bound_consts[0] * a_in;
       if (p.res_meta && p.has_res) bound += __uint_as_float(p.res_meta->amax_bits);
       if (p.coarse_meta && has_coarse) bound += __uint_as_float(p.coarse_meta->amax_bits);

@@ -23,6 +23,7 @@ namespace {
 using namespace tdet;
 
 static_assert(sizeof(tdet_tensor_meta) == sizeof(TensorMeta), "metadata layout mismatch");
+static_assert(sizeof(tdet_op) == 288, "tdet_op layout changed: bump TDET_ABI_VERSION and the ctypes mirror (_C.TdetOp)");
 
 thread_local char g_err[512] = "";
 
@@ -117,12 +118,12 @@ int require_sm100(int device, DeviceInfo** out) {
 }
 
 // ---- launch records ----------------------------------------------------------------------------
-constexpr int kExtFields = 8;
+constexpr int kExtFields = 9;
 struct Launch {
   int kind = 0;  // tdet_op_kind
   tdet_op op{};
-  int ext_slot[kExtFields] = {-1, -1, -1, -1, -1, -1, -1, -1};  // x, wgt, y, residual, coarse, mask, gy, dw
-  long long ext_offset[kExtFields] = {0, 0, 0, 0, 0, 0, 0, 0};  // byte offset of the field inside its external tensor
+  int ext_slot[kExtFields] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};  // x, wgt, y, residual, coarse, mask, gy, dw, x2
+  long long ext_offset[kExtFields] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // byte offset of the field inside its external tensor
   bool has_ext = false;
   // conv / stem
   ConvGemmParams gp{};
@@ -149,7 +150,8 @@ const void* get_field(const tdet_op& o, int f) {
     case 4: return o.coarse;
     case 5: return o.mask;
     case 6: return o.gy;
-    default: return o.dw;
+    case 7: return o.dw;
+    default: return o.x2;
   }
 }
 
@@ -162,7 +164,8 @@ void set_field(tdet_op& o, int f, const void* p) {
     case 4: o.coarse = p; break;
     case 5: o.mask = p; break;
     case 6: o.gy = p; break;
-    default: o.dw = static_cast<float*>(const_cast<void*>(p)); break;
+    case 7: o.dw = static_cast<float*>(const_cast<void*>(p)); break;
+    default: o.x2 = p; break;
   }
 }
 
@@ -628,6 +631,23 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   const int resv = env_int("TDET_RES_VARIANT", kDefaultResVariant);
   const bool grouped = o.groups > 1;
   const bool split = (o.flags & TDET_FLAG_SPLIT) != 0;
+  const bool dual = (o.flags & TDET_FLAG_DUAL) != 0;
+  if (dual) {
+    if (split || grouped || o.residual || o.coarse || o.mask || o.kh != 1 || o.kw != 1 || o.stride != 1 || o.pad != 0 ||
+        o.cout % 256 || !o.x2 || o.cin2 <= 0 || o.cin2 % 64 || o.stride2 < 1 || o.x2_dtype != o.x_dtype ||
+        o.ho != (o.h2 - 1) / o.stride2 + 1 || o.wo != (o.w2 - 1) / o.stride2 + 1)
+      return fail(TDET_ERR_INVALID_ARGUMENT,
+                  "dual-source conv: 1x1/stride-1 main conv with cout %% 256 == 0, no residual/coarse/mask/split/groups, "
+                  "and a second source [n][h2][w2][cin2] of x_dtype whose 1x1/stride2 output matches %dx%d", o.ho, o.wo);
+    if (o.x_meta || o.x2_meta) {
+      // both sources are contracted into ONE accumulator: they must be plain tensors (exponent 0); their metas
+      // only carry the recorded |max| for the output bound
+    }
+    gp.dual = 1;
+    gp.k_chunks2 = o.cin2 / 64;
+    gp.stride2 = o.stride2;
+    gp.in2_meta = reinterpret_cast<const TensorMeta*>(o.x2_meta);
+  }
   if (split) {
     if (o.x_dtype != TDET_BF16 || o.y_dtype != TDET_BF16 || (o.residual && o.residual_dtype != TDET_BF16) ||
         (o.coarse && o.coarse_dtype != TDET_BF16) || (o.flags & TDET_FLAG_SCALED_OUT) || o.mask || grouped)
@@ -672,7 +692,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   gp.num_m_tiles = (gp.M + kBM - 1) / kBM;
   gp.num_n_tiles = o.cout / l.bn;
   gp.a_stage_bytes = kABytes;
-  gp.num_kb_b = o.kh * o.kw * gp.k_chunks;
+  gp.num_kb_b = o.kh * o.kw * gp.k_chunks + (dual ? o.cin2 / 64 : 0);
   l.bres_kb = 0;
   l.patch = false;
   const double real_rows = static_cast<double>(gp.M);
@@ -782,9 +802,21 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     gp.mask_tma = (o.mask && l.res_slabs >= 2 * nload) ? 1 : 0;
   }
   const int csplit = split ? 2 : 1;  // physical channels per logical channel
-  rc = encode_2d(&gp.tmap_b, o.wgt, w_dtype, static_cast<long long>(o.kh) * o.kw * o.cin * csplit, o.cout,
-                 l.pair ? l.bn / 2 : l.bn, "weights");
+  rc = encode_2d(&gp.tmap_b, o.wgt, w_dtype, static_cast<long long>(o.kh) * o.kw * o.cin * csplit + (dual ? o.cin2 : 0),
+                 o.cout, l.pair ? l.bn / 2 : l.bn, "weights");
   if (rc) return rc;
+  if (dual) {
+    if (o.stride2 == 1) {
+      rc = encode_2d(&gp.tmap_a2, o.x2, o.x_dtype, o.cin2, gp.M, kBM, "second source");
+      if (rc) return rc;
+    } else {
+      tdet_op o2 = o;  // 1x1 / stride2 / pad 0 view of x2
+      o2.x = o.x2; o2.cin = o.cin2; o2.h = o.h2; o2.w = o.w2; o2.kh = o2.kw = 1; o2.pad = 0; o2.dil = 1;
+      o2.stride = o.stride2;
+      rc = encode_im2col(&gp.tmap_a2, o2, kBM);
+      if (rc) return rc;
+    }
+  }
   if (spatial) {
     rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
     if (rc) return rc;
@@ -858,8 +890,10 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   }
   if (g > num_tiles) g = num_tiles;
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
-  l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) / (grouped ? o.groups : 1) * o.kh * o.kw);
+  l.flops = 2.0 * real_rows * o.cout * (static_cast<double>(o.cin) / (grouped ? o.groups : 1) * o.kh * o.kw +
+                                        (dual ? o.cin2 : 0));
   l.bytes = 2.0 * (static_cast<double>(o.n) * o.h * o.w * o.cin +
+                   (dual ? real_rows * o.cin2 + static_cast<double>(o.cout) * o.cin2 : 0.0) +
                    static_cast<double>(o.cout) * o.cin / (grouped ? o.groups : 1) * o.kh * o.kw +
                    real_rows * o.cout * (1 + (o.residual ? 1 : 0)) +
                    (o.mask ? real_rows * o.cout : 0.0) +
@@ -1562,6 +1596,23 @@ int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin
   else
     pack_weight_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(w_oihw, static_cast<__nv_bfloat16*>(w_packed),
                                                          cout, cin, kh, kw);
+  TDET_CUDA(cudaGetLastError());
+  return TDET_OK;
+}
+
+int tdet_pack_conv_weight_scaled(const float* w_oihw, const float* scale, void* w_packed, int cout, int cin, int kh,
+                                 int kw, int ld, int dtype, void* stream) {
+  if (!w_oihw || !w_packed || cout <= 0 || cin <= 0 || kh <= 0 || kw <= 0 || ld < kh * kw * cin || !is16(dtype))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "pack_conv_weight_scaled: bad arguments");
+  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+  const int g = static_cast<int>((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == TDET_F16)
+    pack_weight_scaled_kernel<__half><<<g, 256, 0, st>>>(w_oihw, scale, static_cast<__half*>(w_packed), cout, cin, kh,
+                                                         kw, ld);
+  else
+    pack_weight_scaled_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(w_oihw, scale, static_cast<__nv_bfloat16*>(w_packed),
+                                                                cout, cin, kh, kw, ld);
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }

@@ -3,7 +3,9 @@
 torch is plumbing here: it owns device memory and the current stream.  Every arithmetic step of the
 path runs in ``libtdet_b200.so``; nothing in this module computes on tensors with torch ops.
 """
+import collections
 import ctypes
+import os
 
 import torch
 
@@ -120,15 +122,61 @@ class OperandCache(object):
         e = self.store.get(key)
         return None if e is None else e[0]
 
-    def refresh(self):
+    def refresh(self, force=False):
+        """Re-derives the entries whose dependencies changed.  Changes are detected through
+        ``(data_ptr, tensor._version)``; in-place updates made THROUGH ``.data`` (``p.data.add_``: legacy
+        optimizers, EMA, weight clamping) do not bump ``_version`` -- after such an update call
+        ``module.invalidate_operands()`` (or set ``TDET_REFRESH_EVERY_STEP=1``), which passes ``force=True``
+        and re-derives every entry that depends on a parameter or buffer."""
         n = 0
         for e in self.store.values():
             v = self._versions(e[2])
-            if v != e[3]:
+            if v != e[3] or (force and e[2]):
                 e[1](e[0])
                 e[3] = v
                 n += 1
         return n
+
+
+REFRESH_EVERY_STEP = os.environ.get("TDET_REFRESH_EVERY_STEP", "0") != "0"
+
+
+class PlanCache(object):
+    """Bounded LRU of compiled plans.  Entries are grouped (a training forward plan and its backward plan share a
+    group and are evicted together); at most ``capacity`` groups stay alive (``TDET_PLAN_CACHE``, default 4).  A plan
+    pins its whole static activation arena -- for training every saved activation plus the gradient pool -- and
+    the reference's loader pads per batch, so detection training can see many distinct H x W: an unbounded cache
+    would grow by gigabytes per new shape until the allocator fails.  Evicted plans are rebuilt on demand (fixed
+    padded shapes avoid the rebuilds)."""
+
+    def __init__(self, capacity=None):
+        self.capacity = capacity if capacity is not None else max(1, int(os.environ.get("TDET_PLAN_CACHE", "4")))
+        self.groups = collections.OrderedDict()
+
+    def get(self, key, group=None):
+        g = key if group is None else group
+        d = self.groups.get(g)
+        if d is None or key not in d:
+            return None
+        self.groups.move_to_end(g)
+        return d[key]
+
+    def put(self, key, entry, group=None):
+        g = key if group is None else group
+        self.groups.setdefault(g, {})[key] = entry
+        self.groups.move_to_end(g)
+        while len(self.groups) > self.capacity:
+            self.groups.popitem(last=False)
+        return entry
+
+    def __setitem__(self, key, entry):
+        self.put(key, entry)
+
+    def __len__(self):
+        return sum(len(d) for d in self.groups.values())
+
+    def clear(self):
+        self.groups.clear()
 
 
 def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
@@ -143,6 +191,25 @@ def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
     with torch.cuda.device(w.device):
         _C.check(_C.lib().tdet_pack_conv_weight(w.data_ptr(), out.data_ptr(), o, i, kh, kw,
                                                 _TD[dtype], _stream_ptr(w.device)))
+    return out
+
+
+def pack_dual_weight(w, scale, w2, scale2, dtype=torch.bfloat16, out=None):
+    """[cout][cin + cin2] 16-bit operand of a dual-source 1x1 conv: [scale * w | scale2 * w2] (each BatchNorm scale
+    folded into its half before the one rounding)."""
+    require_cuda(w, "weight")
+    ws = [t.detach().float().contiguous() for t in (w, w2)]
+    cout, cin = ws[0].shape[0], ws[0].shape[1]
+    cin2 = ws[1].shape[1]
+    assert ws[0].shape[2:] == (1, 1) and ws[1].shape[2:] == (1, 1) and ws[1].shape[0] == cout
+    if out is None:
+        out = torch.empty((cout, cin + cin2), dtype=dtype, device=w.device)
+    es = out.element_size()
+    with torch.cuda.device(w.device):
+        _C.check(_C.lib().tdet_pack_conv_weight_scaled(ws[0].data_ptr(), _ptr(scale), out.data_ptr(), cout, cin, 1, 1,
+                                                       cin + cin2, _TD[dtype], _stream_ptr(w.device)))
+        _C.check(_C.lib().tdet_pack_conv_weight_scaled(ws[1].data_ptr(), _ptr(scale2), out.data_ptr() + es * cin, cout,
+                                                       cin2, 1, 1, cin + cin2, _TD[dtype], _stream_ptr(w.device)))
     return out
 
 
@@ -267,12 +334,17 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
             coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1,
-            split=False):
+            split=False, dual=None):
     """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype.
     split: split-precision tensors (bf16 hi|lo pairs, 2x the logical channels in memory); Act shapes stay
-    logical."""
+    logical.
+    dual: (x2 Act, stride2) -- second input of a 1x1 conv (TDET_FLAG_DUAL: the projection shortcut of a stage's
+    first bottleneck contracted in the same launch); wgt is then the K-concatenation [cout][cin + cin2] from
+    ``pack_dual_weight`` and x, x2 are plain tensors of one format."""
     n, h, w, cin = x.shape
     cout = wgt.shape[0]
+    if dual is not None and wgt.numel() != cout * (cin + dual[0].shape[3]):
+        raise ValueError("dual-source conv: weights must be the [cout][cin + cin2] concatenation")
     if wgt.dtype != x.dtype:
         raise ValueError("conv weights must be packed in the input tensor's format (%s vs %s)"
                          % (wgt.dtype, x.dtype))
@@ -298,6 +370,13 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
         op.coarse, op.coarse_dtype, op.coarse_meta = coarse.ptr, _TD[coarse.dtype], coarse.meta
         op.hc, op.wc = coarse.shape[1], coarse.shape[2]
     op.bound_consts = _ptr(consts)
+    if dual is not None:
+        x2, stride2 = dual
+        if x2.dtype != x.dtype:
+            raise ValueError("dual-source conv: both inputs share one 16-bit format")
+        op.flags |= _C.FLAG_DUAL
+        op.x2, op.x2_meta, op.x2_dtype = x2.ptr, x2.meta, _TD[x2.dtype]
+        op.cin2, op.stride2, op.h2, op.w2 = x2.shape[3], stride2, x2.shape[1], x2.shape[2]
     return op
 
 

@@ -154,7 +154,7 @@ class ResNet(nn.Module):
             self.res_layers.append(name)
         self.feat_dim = block.expansion * 64 * 2 ** (len(stage_blocks) - 1)
 
-        self._plans = {}
+        self._plans = engine.PlanCache()
         self._operands = None
         self._operand_key = None
 
@@ -206,7 +206,7 @@ class ResNet(nn.Module):
             means, stds = tuple(float(v) for v in img_means), tuple(float(v) for v in img_stds)
             assert len(means) == 3 and len(stds) == 3 and all(s != 0 for s in stds)
             self._input_tf = (means, stds, int(size_divisor) if size_divisor else None)
-        self._plans = {}
+        self._plans = engine.PlanCache()
 
     def _check_supported(self, x):
         engine.require_cuda(x, "ResNet input")
@@ -219,6 +219,12 @@ class ResNet(nn.Module):
                     "only, as in the reference's configs): call .eval() or .train() with "
                     "bn_eval=True first")
 
+    def invalidate_operands(self):
+        """Re-derive every packed weight / folded BatchNorm operand at the next forward.  Needed only after
+        in-place parameter updates made through ``.data`` (they do not bump ``tensor._version``, which is how
+        changes are detected otherwise: optimizer steps through ``torch.optim`` and ``load_state_dict`` are seen)."""
+        self._operands_stale = True
+
     def _get_operands(self, device):
         """Lazy cache of derived operands (packed weights per format, folded BN vectors, bound
         constants).  When a parameter or buffer changes the affected entries are re-derived in place
@@ -226,9 +232,11 @@ class ResNet(nn.Module):
         if self._operands is None or self._operand_key != device:
             self._operands = engine.OperandCache()
             self._operand_key = device
-            self._plans = {}
+            self._plans = engine.PlanCache()
         else:
-            self._operands.refresh()
+            force = getattr(self, "_operands_stale", False) or (engine.REFRESH_EVERY_STEP and self.training)
+            self._operands.refresh(force=force)
+        self._operands_stale = False
         return self._operands
 
     def _segments(self, n):
@@ -290,8 +298,27 @@ class ResNet(nn.Module):
         def new_act(shape, dtype):
             return engine.Act(pool.get(shape[:3] + (shape[3] * cs,)), shape, dtype, None if split else meta.new())
 
-        def conv(name, module, bn, src, dst, residual=None, relu=True):
+        def conv(name, module, bn, src, dst, residual=None, relu=True, shortcut=None):
+            """shortcut = (name, conv, bn, input Act): the block's projection shortcut, contracted by this launch
+            (TDET_FLAG_DUAL) instead of a launch of its own whose output comes back as `residual`."""
             k = module.kernel_size[0]
+            if shortcut is not None:
+                # one GEMM over [src | shortcut input] with the K-concatenated weights [scale*W | scale_s*W_s]: the
+                # two BatchNorm scales are folded into the rows, the shifts are summed
+                sname, smod, sbn, sx = shortcut
+                sc, sh = cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))
+                sc2, sh2 = cache.get((sname, "bn"), lambda out: engine.fold_bn(sbn, out=out), deps=_bn_deps(sbn))
+                deps = (module.weight, smod.weight) + _bn_deps(bn) + _bn_deps(sbn)
+                wgt = cache.get((name, "wdual", src.dtype),
+                                lambda out: engine.pack_dual_weight(module.weight, sc, smod.weight, sc2, src.dtype, out=out),
+                                deps=deps)
+                shs = cache.get((name, "shift_dual"), lambda out: _sum_into(sh, sh2, out), deps=_bn_deps(bn) + _bn_deps(sbn))
+                is_scaled = scaled and dst.dtype == torch.float16
+                consts = cache.get((name, "consts_dual", src.dtype),
+                                   lambda out: engine.bound_consts(wgt, None, shs, out=out), deps=deps) if is_scaled else None
+                ops.append(engine.op_conv(src, wgt, dst, 1, 1, 1, 0, 1, shift=shs, relu=relu, consts=consts,
+                                          scaled_out=is_scaled, dual=(sx, smod.stride[0])))
+                return
             if split:
                 if module.groups > 1:
                     raise NotImplementedError("grouped convolutions have no split-precision (fp32-I/O) path yet")
@@ -379,10 +406,16 @@ class ResNet(nn.Module):
                     stem_consts = cache.get(("conv1", "consts"),
                                             lambda out: engine.bound_consts(stem_w, sc, sh, out=out),
                                             deps=(self.conv1.weight,) + _bn_deps(stem_bn)) if scaled else None
+                    # a fused projection shortcut contracts the stage input and conv2's output in ONE accumulator:
+                    # both are then plain bf16 (exponent 0), so the pooled stem output is stored that way too
+                    first_unit = getattr(self, self.res_layers[0])[0]
+                    stem_plain = fuse_pool and not train and _fuses_shortcut(first_unit)
                     if fuse_pool:
-                        cur = engine.Act(pool.get((cn, hq, wq, 64)), (cn, hq, wq, 64), internal, meta.new())
+                        cur = engine.Act(pool.get((cn, hq, wq, 64)), (cn, hq, wq, 64),
+                                         torch.bfloat16 if stem_plain else internal, meta.new())
                         ops.append(engine.op_stem(cn, h, w, staged, stem_w, cur, sc, sh, x_meta=staged_meta,
-                                                  consts=stem_consts, scaled_out=scaled, pool=True))
+                                                  consts=None if stem_plain else stem_consts,
+                                                  scaled_out=scaled and not stem_plain, pool=True))
                         pool.release(staged)
                     else:
                         ops.append(engine.op_stem(cn, h, w, staged, stem_w, stem_out, sc, sh, x_meta=staged_meta,
@@ -411,7 +444,10 @@ class ResNet(nn.Module):
                         wn = engine.conv_out(wb, 3, unit.stride, unit.dilation, unit.dilation)
                         residual = cur
                         shortcut = None
-                        if unit.downsample is not None:
+                        # a bottleneck's projection shortcut runs inside its conv3 launch (second accumulator):
+                        # the shortcut tensor is never written or re-read (inference plans)
+                        fuse_sc = (not train and not split and cur.dtype == torch.bfloat16 and _fuses_shortcut(unit))
+                        if unit.downsample is not None and not fuse_sc:
                             cd = unit.downsample[0].out_channels
                             shortcut = new_act((nb, hn, wn, cd), internal)
                             conv(pre + "downsample", unit.downsample[0], unit.downsample[1], cur, shortcut,
@@ -432,11 +468,17 @@ class ResNet(nn.Module):
                             if final and last:
                                 dst = boundary_act(li, i0, cn)  # stage output: plain bf16
                             else:
-                                dst = new_act((nb, oh, ow, module.out_channels), internal)
+                                # (the input of a dual-source conv3 is a plain bf16 tensor, see above)
+                                dst = new_act((nb, oh, ow, module.out_channels),
+                                              torch.bfloat16 if (fuse_sc and ci == nconv - 2) else internal)
                                 if not final:
                                     temps.append(dst)
-                            conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src,
-                                 dst, residual=residual if final else None)
+                            if final and fuse_sc:
+                                conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src, dst,
+                                     shortcut=(pre + "downsample", unit.downsample[0], unit.downsample[1], cur))
+                            else:
+                                conv(pre + "conv%d" % (ci + 1), module, getattr(unit, unit.norm_names[ci]), src,
+                                     dst, residual=residual if final else None)
                             src = dst
                             acts.append(dst)
                         if keep:
@@ -565,7 +607,7 @@ class ResNet(nn.Module):
         """{name: fp32 NCHW CPU tensor} of what the last training forward saved for backward (block
         inputs ``layerL.B.in`` and every conv's stored output ``layerL.B.convK``).  Test/debug API:
         the gradient tests feed these to their fp32 checker so that ReLU masks match the kernels'."""
-        plan, out_shapes, records, cints, geo = self._plans[self._train_state["key"]]
+        plan, out_shapes, records, cints, geo = self._train_state["entry"]
         raw = plan.meta.tensor.cpu()
         base = plan.meta.tensor.data_ptr()
 
@@ -599,13 +641,13 @@ class ResNet(nn.Module):
         plan.run([x] + outs)
         self._last_run = (plan, [x] + outs)
         self._train_serial = getattr(self, "_train_serial", 0) + 1
-        state = dict(key=key, outs=outs, params=list(params), serial=self._train_serial, x=x)
+        state = dict(key=key, entry=entry, outs=outs, params=list(params), serial=self._train_serial, x=x)
         self._train_state = state
         return outs, state
 
     def _build_bwd_plan(self, state, cache):
         """Backward plan for the saved forward `state`: stages deepest first, blocks last to first."""
-        plan, out_shapes, records, cints, geo = self._plans[state["key"]]
+        plan, out_shapes, records, cints, geo = state["entry"]
         dev = state["x"].device
         outs = state["outs"]
         scaled = INTERNAL_DTYPE == torch.float16
@@ -790,10 +832,9 @@ class ResNet(nn.Module):
                                "saved activations live in the plan's static buffers (one forward per backward)")
         cache = self._get_operands(state["x"].device)
         bkey = ("bwd",) + state["key"]
-        entry = self._plans.get(bkey)
+        entry = self._plans.get(bkey, group=state["key"])
         if entry is None:
-            entry = self._build_bwd_plan(state, cache)
-            self._plans[bkey] = entry
+            entry = self._plans.put(bkey, self._build_bwd_plan(state, cache), group=state["key"])
         bplan, buckets, segments = entry
         outs = state["outs"]
         ext = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
@@ -805,7 +846,7 @@ class ResNet(nn.Module):
             bplan.run_range(ext, a, b)
             # the plan's accumulators are reused by the next backward: autograd gets a copy, which is
             # made (and all-reduced) on the side stream while the next segment computes
-            reduced.append(sync.reduce(buckets[k].flat) if sync is not None else buckets[k].flat.clone())
+            reduced.append(sync.reduce(buckets[k].flat, buckets[k].params) if sync is not None else buckets[k].flat.clone())
         if sync is not None:
             sync.module_done()
         self._last_bwd_run = (bplan, ext)
@@ -835,8 +876,29 @@ FP32_IO_SPLIT = os.environ.get("TDET_FP32_IO", "split").lower() == "split"
 # the stem kernel applies the 3x3/2 max-pool in its epilogue (TDET_FLAG_POOL); 0 = separate TDET_OP_MAXPOOL launch
 FUSE_STEM_POOL = os.environ.get("TDET_STEM_POOL", "1") != "0"
 
+# a stage's projection shortcut is contracted inside the first bottleneck's conv3 launch (TDET_FLAG_DUAL)
+FUSE_SHORTCUT = os.environ.get("TDET_FUSE_SHORTCUT", "1") != "0"
+
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
+
+
+def _fuses_shortcut(unit):
+    """True if the unit's projection shortcut can run inside its last conv's launch (TDET_FLAG_DUAL): a bottleneck
+    whose last conv is a dense 1x1 with a multiple of 256 output channels and whose shortcut is a 1x1 conv."""
+    if not FUSE_SHORTCUT or unit.downsample is None or len(unit.kernel_sizes) < 2 or unit.kernel_sizes[-1] != 1:
+        return False
+    last = getattr(unit, "conv%d" % len(unit.kernel_sizes))
+    ds = unit.downsample[0]
+    return (last.out_channels % 256 == 0 and last.groups == 1 and last.stride[0] == 1 and
+            ds.kernel_size[0] == 1 and ds.padding[0] == 0 and ds.groups == 1 and ds.in_channels % 64 == 0)
+
+
+def _sum_into(a, b, out):
+    if out is None:
+        return (a + b).contiguous()
+    torch.add(a, b, out=out)
+    return out
 
 
 def _affine_copy(bn, out):

@@ -19,6 +19,7 @@ import math
 
 import torch.nn as nn
 
+from ... import engine
 from ...registry import BACKBONES
 from ..utils import conv7x7_group, norm_layer
 from .resnet import ResNet, Bottleneck, _make_res_layer
@@ -100,6 +101,6 @@ class ResNeXt(ResNet):
         self.resX_layers = self.res_layers  # the reference's attribute name (resnext.py:246)
         self.feat_dim = block.expansion * 64 * 2 ** (len(stage_blocks) - 1)
 
-        self._plans = {}
+        self._plans = engine.PlanCache()
         self._operands = None
         self._operand_key = None

@@ -62,7 +62,7 @@ class FPN(nn.Module):
                 self.fpn_convs.append(ConvModule(cin, out_channels, 3, stride=2, padding=1,
                                                  normalize=normalize, bias=self.with_bias,
                                                  use_gn=use_gn))
-        self._plans = {}
+        self._plans = engine.PlanCache()
         self._operands = None
         self._operand_key = None
 
@@ -78,7 +78,9 @@ class FPN(nn.Module):
         """Packed bf16 weights and fp32 biases; re-derived in place when a parameter changes
         (engine.OperandCache), so plans and their TMA descriptors survive optimizer steps."""
         if self._operands is not None and self._operand_key == device:
-            self._operands.refresh()
+            force = getattr(self, "_operands_stale", False) or (engine.REFRESH_EVERY_STEP and self.training)
+            self._operands.refresh(force=force)
+            self._operands_stale = False
             return self._operands
         cache = engine.OperandCache()
         for kind, convs in self._conv_groups():
@@ -99,8 +101,12 @@ class FPN(nn.Module):
                               lambda out, conv=conv: _bias_copy(conv.bias, out), deps=(conv.bias,))
         self._operands = cache
         self._operand_key = device
-        self._plans = {}
+        self._plans = engine.PlanCache()
         return cache
+
+    def invalidate_operands(self):
+        """See ResNet.invalidate_operands: call after in-place parameter updates made through ``.data``."""
+        self._operands_stale = True
 
     def _conv_groups(self):
         return (("lat", self.lateral_convs), ("out", self.fpn_convs))
@@ -218,9 +224,11 @@ class FPN(nn.Module):
             return tuple(training.PlanFunction.apply(self, len(inputs), *(list(inputs) + params)))
         return self._forward_infer(inputs)
 
-    def _forward_infer(self, inputs):
+    def _forward_infer(self, inputs, allow_split=True):
         want_fp32 = all(t.dtype == torch.float32 for t in inputs)
-        if type(self) is FPN and all(getattr(t, "_tdet_split", None) is not None for t in inputs):
+        # (the training path saves bf16 laterals for its backward plan: it never takes the split-precision path,
+        # also when a frozen / eval backbone handed over fp32-I/O stage outputs)
+        if allow_split and type(self) is FPN and all(getattr(t, "_tdet_split", None) is not None for t in inputs):
             return self._forward_split([t._tdet_split for t in inputs])
         feats = [self._as_bf16_nhwc(t) for t in inputs]
         for t, c in zip(feats, self.in_channels):
@@ -239,6 +247,7 @@ class FPN(nn.Module):
         plan.run(feats + outs)
         self._last_run = (plan, feats + outs)  # for profiling tools (bench.py)
         self._last_feats = feats
+        self._last_key = key
         if want_fp32:
             outs = [o.float() for o in outs]
         return tuple(outs)
@@ -288,12 +297,12 @@ class FPN(nn.Module):
 
     def _train_forward(self, inputs, params):
         with torch.no_grad():
-            outs = self._forward_infer(inputs)
+            outs = self._forward_infer(inputs, allow_split=False)
         plan, ext = self._last_run
         self._train_serial = getattr(self, "_train_serial", 0) + 1
         state = dict(plan=plan, feats=self._last_feats, outs=list(ext[len(self._last_feats):]),
                      in_dtypes=[t.dtype for t in inputs], params=list(params),
-                     serial=self._train_serial)
+                     serial=self._train_serial, key=self._last_key)
         self._train_state = state
         return outs, state
 
@@ -382,10 +391,9 @@ class FPN(nn.Module):
         dev = feats[0].device
         operands = self._get_operands(dev)
         key = ("bwd", id(state["plan"]))
-        entry = self._plans.get(key)
+        entry = self._plans.get(key, group=state["key"])
         if entry is None:
-            entry = self._build_bwd_plan(state, operands)
-            self._plans[key] = entry
+            entry = self._plans.put(key, self._build_bwd_plan(state, operands), group=state["key"])
         bplan, bucket = entry
         gs = [training.as_grad_nhwc(g, o) for g, o in zip(gouts, outs)]
         used = feats[self.start_level:self.backbone_end_level]
@@ -397,7 +405,7 @@ class FPN(nn.Module):
         bplan.run(ext)
         self._last_bwd_run = (bplan, ext)
         if sync is not None:
-            flat = sync.reduce(bucket.flat)
+            flat = sync.reduce(bucket.flat, bucket.params)
             sync.module_done()
         else:
             flat = bucket.flat.clone()

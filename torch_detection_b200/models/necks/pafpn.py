@@ -67,7 +67,7 @@ class PAFPN(FPN):
                 cin = in_channels[self.backbone_end_level - 1] if i == 0 else out_channels
                 self.fpn_convs.append(ConvModule(cin, out_channels, 3, stride=2, padding=1, normalize=normalize,
                                                  bias=self.with_bias, use_gn=use_gn))
-        self._plans = {}
+        self._plans = engine.PlanCache()
         self._operands = None
         self._operand_key = None
 

@@ -25,15 +25,22 @@ from . import engine
 class BucketAllReduce(object):
     """Sums (averages) flat gradient buckets across ranks, overlapped with the rest of backward.
 
-    ``reduce(bucket)`` is called by a module's backward as soon as the kernels writing that bucket
+    ``reduce(bucket, params)`` is called by a module's backward as soon as the kernels writing that bucket
     have been enqueued.  On a side stream that waits for exactly that point of the compute stream
     the bucket is copied out (the plan re-zeroes its accumulators in the next step) and the copy is
-    all-reduced, so NCCL traffic over NVLink overlaps the remaining dgrad/wgrad kernels; the
-    returned tensor is what the module hands to autograd.  ``finish()`` makes the compute stream
-    wait for every outstanding bucket: modules call it at the end of their backward unless
-    ``defer=True``, in which case the training loop calls it once after ``backward()`` (then even
-    the neck's bucket overlaps the whole backbone backward).  With CPU tensors (gloo; host-logic
-    tests) or a single rank the collective runs inline.
+    all-reduced (``ReduceOp.AVG``: no separate division pass), so NCCL traffic over NVLink overlaps the
+    remaining dgrad/wgrad kernels; the returned tensor is what the module hands to autograd.
+    ``finish()`` makes the compute stream wait for every outstanding bucket: modules call it at the end of
+    their backward unless ``defer=True``, in which case the training loop calls it once after ``backward()``
+    and BEFORE anything reads ``p.grad`` (then even the neck's bucket overlaps the whole backbone backward).
+
+    Deferred hand-over is only sound while autograd merely *adopts* the returned views (``p.grad is None``:
+    AccumulateGrad stores the tensor without launching a kernel).  When a parameter of the bucket already
+    holds a gradient (gradient accumulation, ``zero_grad(set_to_none=False)``) autograd would run
+    ``p.grad += g`` on the compute stream, racing the side stream -- for such buckets the compute stream
+    waits for the collective before the views are handed over (correct, that bucket just does not overlap).
+    The world size is queried when first needed, so the object may be built before ``init_process_group``.
+    With CPU tensors (gloo; host-logic tests) or a single rank the collective runs inline.
     """
 
     def __init__(self, group=None, average=True, defer=False, sm_reserve=0):
@@ -44,18 +51,24 @@ class BucketAllReduce(object):
         self.defer = defer
         # SMs the modules' persistent GEMM grids leave to the NCCL kernels (pair with NCCL_MAX_CTAS)
         self.sm_reserve = sm_reserve
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.enabled = True   # False: copy the buckets out but skip the collective (bench A/B of its cost)
         self._streams = {}
         self._pending = []
         self._copied = {}  # bucket address -> event: its side-stream copy has completed
+        self._timing = None  # list of (start, end) events around each collective while profiling
         self.buckets_reduced = 0
         self.bytes_reduced = 0
+        self.buckets_not_overlapped = 0
+
+    @property
+    def world(self):
+        return self.dist.get_world_size(self.group) if self.dist.is_initialized() else 1
 
     def attach(self, module, device):
         """Called by module.set_grad_sync: re-size the module's grids if SMs are reserved for NCCL."""
         if self.sm_reserve and self.world > 1 and device.type == "cuda":
             engine.set_sm_reserve(device, self.sm_reserve)
-            module._plans = {}
+            module._plans = engine.PlanCache()
 
     def _comm_stream(self, device):
         s = self._streams.get(device)
@@ -70,15 +83,27 @@ class BucketAllReduce(object):
         if ev is not None:
             torch.cuda.current_stream(bucket.device).wait_event(ev)
 
-    def reduce(self, bucket):
+    def profile(self, on=True):
+        """Record CUDA events around every collective (side stream) until profile(False)."""
+        self._timing = [] if on else None
+
+    def collective_ms(self):
+        """Sum of the device time of the collectives recorded since profile(True) (synchronises)."""
+        if not self._timing:
+            return 0.0
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self._timing)
+
+    def reduce(self, bucket, params=()):
         self.buckets_reduced += 1
         self.bytes_reduced += bucket.numel() * bucket.element_size()
+        world = self.world
         if not bucket.is_cuda:
             out = bucket.clone()
-            if self.world > 1:
+            if world > 1 and self.enabled:
                 self.dist.all_reduce(out, group=self.group)
                 if self.average:
-                    out.div_(self.world)
+                    out.div_(world)
             return out
         main = torch.cuda.current_stream(bucket.device)
         comm = self._comm_stream(bucket.device)
@@ -87,13 +112,24 @@ class BucketAllReduce(object):
             out = bucket.clone()
             ev = torch.cuda.Event()
             ev.record(comm)
-            if self.world > 1:
-                self.dist.all_reduce(out, group=self.group)
-                if self.average:
-                    out.div_(self.world)
+            if world > 1 and self.enabled:
+                t0 = t1 = None
+                if self._timing is not None:
+                    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    t0.record(comm)
+                op = self.dist.ReduceOp.AVG if self.average else self.dist.ReduceOp.SUM
+                self.dist.all_reduce(out, op=op, group=self.group)
+                if t1 is not None:
+                    t1.record(comm)
+                    self._timing.append((t0, t1))
         out.record_stream(main)
         self._copied[bucket.data_ptr()] = ev
-        self._pending.append((bucket.device, comm))
+        if any(p.grad is not None for p in params):
+            # autograd will accumulate into existing gradients on the compute stream: order it after the collective
+            main.wait_stream(comm)
+            self.buckets_not_overlapped += 1
+        else:
+            self._pending.append((bucket.device, comm))
         return out
 
     def finish(self):
