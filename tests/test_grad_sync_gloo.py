@@ -33,7 +33,7 @@ def _worker(rank, world, port, out):
             bucket.view(i).fill_(float(rank + 1) * (i + 1))
         sync = training.BucketAllReduce(average=True, defer=True)
         assert sync.world == world
-        red = sync.reduce(bucket.flat)
+        red = sync.reduce(bucket.flat, bucket.params)
         sync.finish()
         # the plan's accumulator is left untouched (it is re-zeroed by the next backward); the copy is reduced
         assert float(bucket.view(0).flatten()[0]) == float(rank + 1)
@@ -72,3 +72,19 @@ def test_bucket_allreduce_single_process():
     out = sync.reduce(b.flat)
     sync.module_done()
     assert out.data_ptr() != b.flat.data_ptr() and float(out[0]) == 3.0
+
+
+def test_world_size_is_queried_lazily():
+    """The object may be constructed before init_process_group (it used to sample the world size in __init__ and
+    silently skip the collective)."""
+    from torch_detection_b200 import training
+    assert not dist.is_initialized()
+    sync = training.BucketAllReduce(defer=True)
+    assert sync.world == 1
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(_free_port())
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        assert sync.world == dist.get_world_size() == 1
+    finally:
+        dist.destroy_process_group()

@@ -161,3 +161,49 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_plan_cache_is_a_bounded_lru():
+    """Plans pin their activation arenas; the cache keeps at most `capacity` groups (a training forward plan and its
+    backward plan form one group and leave together), least recently used first."""
+    from torch_detection_b200.engine import PlanCache
+    c = PlanCache(capacity=2)
+    c["a"] = 1
+    c.put(("bwd", "a"), 11, group="a")
+    c["b"] = 2
+    assert c.get("a") == 1 and c.get(("bwd", "a"), group="a") == 11 and len(c) == 3
+    c["c"] = 3                      # evicts the least recently used group: b
+    assert c.get("b") is None and c.get("a") == 1 and c.get("c") == 3
+    c["d"] = 4                      # a (forward AND backward entry) is now the oldest
+    assert c.get("a") is None and c.get(("bwd", "a"), group="a") is None and len(c) == 2
+    c.clear()
+    assert len(c) == 0
+    assert PlanCache().capacity >= 1
+    assert isinstance(ResNet(18)._plans, PlanCache) and isinstance(FPN([64, 128, 256, 512], 256, 5)._plans, PlanCache)
+
+
+def test_operand_cache_force_refresh():
+    """OperandCache.refresh(force=True) re-derives every entry with dependencies (what invalidate_operands() uses
+    after in-place updates through .data, which do not bump tensor._version)."""
+    from torch_detection_b200.engine import OperandCache
+    w = nn.Parameter(torch.ones(4))
+    cache = OperandCache()
+    calls = []
+
+    def make(out):
+        calls.append(out is None)
+        if out is None:
+            return w.detach().clone()
+        out.copy_(w.detach())
+        return out
+
+    v = cache.get("w", make, deps=(w,))
+    const = cache.get("const", lambda out: torch.zeros(1))
+    assert cache.refresh() == 0
+    w.data.mul_(2.0)                         # invisible to the version check
+    assert cache.refresh() == 0 and float(v[0]) == 1.0
+    assert cache.refresh(force=True) == 1 and float(v[0]) == 2.0 and const is cache.value("const")
+    with torch.no_grad():
+        w.mul_(2.0)                          # a normal in-place update is seen
+    assert cache.refresh() == 1 and float(v[0]) == 4.0
+    assert calls == [True, False, False]

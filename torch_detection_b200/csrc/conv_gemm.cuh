@@ -142,6 +142,11 @@ struct ConvGemmParams {
   // [W (cin) | W2 (cin2)] with both BatchNorm scales folded into its rows, so the shortcut tensor never exists in
   // memory.  Both sources are plain tensors of one format (exponent 0).
   CUtensorMap tmap_a2;            // 2D tiled (stride2 == 1) or 4D im2col (stride2 > 1) view of x2
+  // warp_stores: every epilogue warp stages and TMA-stores its OWN 32 rows of a slab (tmap_out then has 32-row boxes)
+  // and tracks its own bulk groups, so a slab costs two warp-level syncs instead of two 128-thread named barriers and
+  // the eight warps run fully de-synchronised (0: one 128-row store per slab, issued by the group's first thread)
+  int warp_stores;
+  int res_prefetch;               // residual / mask slabs are prefetched into L2 this many tiles ahead (0 = off)
   int dual;
   int k_chunks2;
   int stride2;
@@ -290,7 +295,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int s = 0; s < kRB; ++s) {
       mbar_init(rfull_bar(s), 1);
-      mbar_init(rempty_bar(s), 1);
+      mbar_init(rempty_bar(s), (p.warp_stores && !POOL) ? 4 : 1);  // per-warp consumers: one arrive per warp of the group
     }
     mbar_init(bres_bar, 1);
     *ring_issued = -1;
@@ -654,6 +659,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_tile = m_tile_of(tile);
         const int n_tile = tile % p.num_n_tiles;
+        // The ring only looks ~one slab ahead of the epilogue, far less than the HBM latency under load: pull the
+        // residual / mask tile of a later tile into L2 now (128 rows x BN columns; 2D operands only)
+        if (p.res_prefetch > 0 && !coarse_tma && p.a_mode < A_STEM && lane == 0) {
+          const int ptile = tile + p.res_prefetch * tile_step;
+          if (ptile < num_tiles) {
+            const int pm = PAIR ? min(m_tile_of(ptile), p.num_m_tiles - 1) : m_tile_of(ptile);
+            const int pn = (ptile % p.num_n_tiles) * BN;
+            for (int s = 0; s < kSlabsPerTile; ++s) {
+              if (p.has_res) tma_prefetch_l2_2d(&p.tmap_res, pn + s * 64, pm * kBM);
+              if (MASKED && p.mask_tma) tma_prefetch_l2_2d(&p.tmap_mask, pn + s * 64, pm * kBM);
+            }
+          }
+        }
         for (int s = 0; s < kSlabsPerTile; ++s) {
           for (int j = 0; j < nload; ++j) {
             const CUtensorMap* tm = (rsplit || (j == 0 && p.has_res)) ? &p.tmap_res : &p.tmap_mask;
@@ -720,7 +738,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     constexpr bool kByTile = kSlabsPerTile == 1;
     const int gtid = (threadIdx.x - 96) & (kEpiGroupThreads - 1);
     const uint32_t gbar = 1u + group;      // the group's named barrier
-    const bool issuer = gtid == 0;         // issues the group's TMA stores, frees residual slabs
+    const bool ws = p.warp_stores != 0 && !POOL;
+    const bool issuer = ws ? (lane == 0) : (gtid == 0);  // issues the TMA stores (its warp's / its group's), frees residual slabs
     const bool has_res = RES_SLABS > 0 && p.has_res;
     const bool mask_tma = MASKED && RES_SLABS > 0 && p.mask_tma != 0;
     const bool split = SPLIT && p.split != 0;
@@ -955,11 +974,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int midx = ridx + (has_res ? 1 : 0);
         const int ms = midx % rdepth;
         const uint32_t mphase = static_cast<uint32_t>(midx / rdepth) & 1u;
-        // the staging buffer `ob` was last read by the TMA store this group issued OSLABS slabs ago
+        // the staging buffer `ob` was last read by the TMA store this group (warp) issued OSLABS slabs ago
         if (issuer) {
           if (OSLABS == 1 || split) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
+        if (ws) __syncwarp();
         // An mbarrier parity wait is only sound if the PREVIOUS fill of the slot (ring index - kRS) has
         // completed before the consumer waits for this one -- otherwise the barrier is still one phase
         // behind and the wait falls through.  A single in-order consumer has that for free; with two groups
@@ -974,7 +994,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         if (has_res || coarse_tma) mbar_wait(rfull_bar(rs), rphase);
         if (mask_tma || (split && has_res)) mbar_wait(rfull_bar(ms), mphase);
-        named_bar_sync(gbar, kEpiGroupThreads);
+        if (!ws) named_bar_sync(gbar, kEpiGroupThreads);
         if (split) ob = 0;
         const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
@@ -1161,22 +1181,33 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         fence_proxy_async_smem();  // staging writes -> visible to the TMA (async proxy)
-        named_bar_sync(gbar, kEpiGroupThreads);
+        if (ws) __syncwarp(); else named_bar_sync(gbar, kEpiGroupThreads);
         if (issuer) {
-          const uint32_t src = smem_out_g + ob * kSlabBytes;
+          // warp_stores: rows [32 quad, 32 quad + 32) of the slab = a (64, 32)-row box, or the sub-box of the spatial
+          // tile those rows cover
+          const uint32_t src = smem_out_g + ob * kSlabBytes + (ws ? quad * 4096 : 0);
+          int c1 = st_c1, c2 = st_c2;
+          if (ws) {
+            if (p.a_mode >= A_STEM) {
+              c1 += (quad * 32) % p.tile_bw;
+              c2 += (quad * 32) / p.tile_bw;
+            } else {
+              c1 += quad * 32;
+            }
+          }
           if (PAIR && m_tile >= p.num_m_tiles) {
             // the odd pair's padding tile: nothing to store
           } else if (p.a_mode >= A_STEM) {
             asm volatile(
                 "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),
-                "r"(st_c1), "r"(st_c2), "r"(st_c3)
+                "r"(c1), "r"(c2), "r"(st_c3)
                 : "memory");
           } else {
             asm volatile(
                 "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                 ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src), "r"(n0 + slab * 64),
-                "r"(st_c1)
+                "r"(c1)
                 : "memory");
           }
           if (SPLIT && split) {
@@ -1184,13 +1215,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               asm volatile(
                   "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                   ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src + kSlabBytes), "r"(p.N + n0 + slab * 64),
-                  "r"(st_c1), "r"(st_c2), "r"(st_c3)
+                  "r"(c1), "r"(c2), "r"(st_c3)
                   : "memory");
             } else {
               asm volatile(
                   "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                   ::"l"(reinterpret_cast<uint64_t>(&p.tmap_out)), "r"(src + kSlabBytes), "r"(p.N + n0 + slab * 64),
-                  "r"(st_c1)
+                  "r"(c1)
                   : "memory");
             }
           }

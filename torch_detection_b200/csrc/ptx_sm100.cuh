@@ -97,6 +97,18 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       "r"(c3), "r"(c4)
       : "memory");
 }
+// L2 prefetch of a tile (no shared-memory destination, no completion tracking): brings data the CTA will TMA-load
+// a few tiles later from HBM into L2, where a shallow ring can cover the remaining latency
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // im2col mode, NHWC tensor seen as (c, w, h, n); (off_w, off_h) = filter tap offset (s*dil, r*dil)
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* tmap, uint32_t bar,
                                                    int c, int w, int h, int n, uint16_t off_w,

@@ -176,6 +176,9 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 bool resident_b_enabled() { return env_int("TDET_RESIDENT_B", 1) != 0; }
+// per-warp output stores (conv_gemm.cuh, ConvGemmParams::warp_stores): output tensor maps get 32-row boxes
+bool warp_stores_enabled() { return env_int("TDET_WARP_STORES", 1) != 0; }
+constexpr int kWarpRows = 32;
 // A_PATCH is used when the 8x16 spatial tiling wastes at most this many percent of the MMA rows.
 int patch_max_waste_pct() { return env_int("TDET_PATCH_MAX_WASTE", 15); }
 int stem_version() { return env_int("TDET_STEM", 2); }
@@ -817,8 +820,14 @@ int build_conv(Launch& l, const DeviceInfo& di) {
       if (rc) return rc;
     }
   }
+  // per-warp stores pay where the epilogue bounds the kernel (short K); long-K kernels measured ~2 % slower with them
+  const int ws_mode = env_int("TDET_WARP_STORES", 1);
+  const bool wst = ws_mode == 2 || (ws_mode == 1 && gp.num_kb_b <= 8);
+  gp.warp_stores = wst ? 1 : 0;
+  gp.res_prefetch = (o.residual || o.mask) ? env_int("TDET_RES_PREFETCH", 0) : 0;
+  const int out_bh = wst ? kWarpRows / kPatchBW : kPatchBH;  // spatial tiles: rows of the output box
   if (spatial) {
-    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
+    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, out_bh, "output");
     if (rc) return rc;
     rc = encode_4d(&gp.tmap_a, o.x, o.x_dtype, o.cin, o.w, o.h, o.n, kPatchBW, kPatchBH, "activation tile");
     if (rc) return rc;
@@ -826,7 +835,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
                    "coarse level");
     if (rc) return rc;
   } else if (l.patch) {
-    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, kPatchBH, "output");
+    rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, out_bh, "output");
     if (rc) return rc;
     if (o.residual) {
       rc = encode_4d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW,
@@ -841,7 +850,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     rc = encode_4d(&gp.tmap_a, o.x, o.x_dtype, o.cin, o.w, o.h, o.n, kPatchPW, kPatchPH, "halo patch");
     if (rc) return rc;
   } else {
-    rc = encode_2d(&gp.tmap_out, o.y, o.y_dtype, o.cout * csplit, gp.M, kBM, "output");
+    rc = encode_2d(&gp.tmap_out, o.y, o.y_dtype, o.cout * csplit, gp.M, wst ? kWarpRows : kBM, "output");
     if (rc) return rc;
     if (o.residual) {
       rc = encode_2d(&gp.tmap_res, o.residual, o.residual_dtype, o.cout * csplit, gp.M, kBM, "residual");
@@ -1158,7 +1167,11 @@ int build_stem(Launch& l, const DeviceInfo& di) {
                           static_cast<cuuint64_t>(o.n)};
     cuuint64_t strides[3] = {cb, static_cast<cuuint64_t>(o.wo) * cb,
                              static_cast<cuuint64_t>(o.ho) * o.wo * cb};
-    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(bw), static_cast<cuuint32_t>(bh), 1};
+    const bool wst = warp_stores_enabled();
+    gp.warp_stores = wst ? 1 : 0;
+    const int obw = wst ? (bw < kWarpRows ? bw : kWarpRows) : bw;  // per-warp stores: the 32 rows of one warp
+    const int obh = wst ? kWarpRows / obw : bh;
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(obw), static_cast<cuuint32_t>(obh), 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = driver().encode_tiled(&gp.tmap_out, tm_dtype(o.y_dtype), 4, o.y, dims, strides, box, es,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

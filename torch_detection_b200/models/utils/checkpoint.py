@@ -57,15 +57,30 @@ def _from_modelzoo(name):
     return weights.get_state_dict(progress=False)
 
 
-def load_checkpoint(model, filename, map_location=None, strict=False, logger=None):
+def _trusted(flag):
+    return flag or os.environ.get("TDET_TRUSTED_CHECKPOINTS", "0") != "0"
+
+
+def load_checkpoint(model, filename, map_location=None, strict=False, logger=None, trusted=False):
+    """Same signature as the reference plus `trusted`: files are unpickled with ``weights_only=True`` (tensors and
+    plain containers, which is all save_checkpoint and the reference write for weights/meta); a checkpoint that
+    carries arbitrary pickled objects is only loaded with ``trusted=True`` (or TDET_TRUSTED_CHECKPOINTS=1) --
+    unpickling an untrusted file executes code."""
     if filename.startswith("modelzoo://"):
         checkpoint = _from_modelzoo(filename[len("modelzoo://"):])
     elif filename.startswith(("http://", "https://")):
-        checkpoint = torch.hub.load_state_dict_from_url(filename, map_location=map_location)
+        checkpoint = torch.hub.load_state_dict_from_url(filename, map_location=map_location,
+                                                        weights_only=not _trusted(trusted))
     else:
         if not os.path.isfile(filename):
             raise IOError("{} is not a checkpoint file".format(filename))
-        checkpoint = torch.load(filename, map_location=map_location, weights_only=False)
+        try:
+            checkpoint = torch.load(filename, map_location=map_location, weights_only=True)
+        except Exception as exc:
+            if not _trusted(trusted):
+                raise RuntimeError("{} holds more than tensors and plain containers ({}); pass trusted=True to "
+                                   "unpickle it if you trust its source".format(filename, exc))
+            checkpoint = torch.load(filename, map_location=map_location, weights_only=False)
     if isinstance(checkpoint, dict) and "state_dict" in checkpoint:
         state_dict = checkpoint["state_dict"]
     elif isinstance(checkpoint, dict):  # OrderedDict of tensors
