@@ -507,6 +507,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true",
                     help="skip the sustained / full-copy / R101 batch-64 / training legs (quick A/B runs)")
+    ap.add_argument("--legs", default="full,sustained,r101,train",
+                    help="which of the extra legs run (comma list of full, sustained, r101, train)")
     ap.add_argument("--launch-table", default="", help="write the per-launch timing table (JSON) here")
     ap.add_argument("--io-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="fp32 = the fp32-I/O mode (split-precision kernels, <= 1e-4 vs the fp32 reference); secondary line")
@@ -563,10 +565,12 @@ def main():
     c_last = sampler.mark() if sampler else 0
     full = None
     sustained = None
-    if not args.no_extra_legs:
+    legs = set() if args.no_extra_legs else set(v.strip() for v in args.legs.split(",") if v.strip())
+    if "full" in legs:
         fv, fh, fd = e2e_leg(ctx, step, x_host, x_dev, outs, max(args.steps // 2, 5), list(range(len(outs))))
         full = {"value": fv, "unit": "img/s", "h2d_bytes_per_step": fh, "d2h_bytes_per_step": fd,
                 "note": "as e2e, but ALL of P2..P6 are copied back to pinned host memory every step (PCIe-bound)"}
+    if "sustained" in legs:
         sustained = sustained_leg(ctx, lambda: step(x_dev), B, 3.0, sampler)
 
     # ---- roofline of the tcgen05 GEMM kernel family, measured live with CUDA events --------------------
@@ -630,8 +634,9 @@ def main():
 
     # ---- secondary legs: config 3 (R101, batch 64 sharded) and config 4 (training, NCCL all-reduce) ------
     r101 = train = None
-    if not args.no_extra_legs and args.io_dtype == "bf16":
+    if "r101" in legs and args.io_dtype == "bf16":
         r101 = r101_leg(ctx, args, 5, 3)
+    if "train" in legs and args.io_dtype == "bf16":
         train = train_leg(ctx, args, 10, 3)
     if sampler:
         sampler.stop()

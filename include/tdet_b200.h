@@ -87,7 +87,8 @@ typedef enum tdet_op_kind {
   TDET_OP_SPLIT_COMBINE = 14, /* y (fp32 [n][h][w][cin]) = hi + lo of a split-precision tensor x ([n][h][w][2*cin] bf16) */
   TDET_OP_MAXPOOL_BWD = 15,  /* backward of MaxPool2d(3, 2, 1) fused with the ReLU backward of its input (stem) */
   TDET_OP_STEM_WGRAD = 16,   /* weight gradient of the 7x7/2 stem conv from the staged image */
-  TDET_OP_PARITY_MERGE = 17  /* interleave the four parity-class results of a stride-2 3x3 dgrad (+ ReLU mask) */
+  TDET_OP_PARITY_MERGE = 17, /* interleave the four parity-class results of a stride-2 3x3 dgrad (+ ReLU mask) */
+  TDET_OP_BOTTLENECK_TAIL = 18 /* fused conv2 (3x3) -> conv3 (1x1) + residual + ReLU [-> the next block's conv1] */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -108,6 +109,7 @@ enum {
                                stem (resnet.py:218,258) and y is the POOLED tensor [n][hp][wp][64], hp =
                                (ho - 1) / 2 + 1; the stem's own output never reaches memory.  Needs
                                TDET_FLAG_RELU (out-of-image window positions are taken as 0). */
+  TDET_FLAG_SCALED_OUT2 = 64, /* TDET_OP_BOTTLENECK_TAIL: y2 is stored with a device-chosen exponent (needs y2_meta) */
   TDET_FLAG_DUAL = 32       /* TDET_OP_CONV, 1x1 / stride 1 / cout % 256 == 0 only: a SECOND input,
                                y = act( ([x | x2'] * wgt^T) * scale + shift ),  x2' = x2 sampled with stride2,
                                i.e. wgt is the K-concatenation [cout][cin + cin2] of two 1x1 weight matrices and both
@@ -194,6 +196,17 @@ typedef struct tdet_tensor_meta {
  * TDET_OP_STEM_WGRAD  x: the TDET_OP_PREP staging of the batch (bf16 NHWC4); gy: bf16 [n][ho][wo][64] gradient
  *                   w.r.t. bn1's output; scale: folded bn1 scale (or NULL); dw: fp32 [64][3][7][7], accumulated.
  *                   h, w = image size as for TDET_OP_STEM.
+ * TDET_OP_BOTTLENECK_TAIL  the tail of an identity-shortcut Bottleneck with planes = 64 (layer1; resnet.py:105-118) and,
+ *                   optionally, the head of the next one (resnet.py:101-103), in ONE kernel:
+ *                     z2 = relu(conv3x3(x) * scale + shift)                 x = this block's conv1 output [n][h][w][64],
+ *                                                                           wgt [64][3][3][64], 3x3 / stride 1 / pad 1
+ *                     y  = relu(conv1x1(z2) * scale2 + shift2 + residual)   wgt2 [256][64]; residual, y [n][h][w][256]
+ *                     y2 = relu(conv1x1(y) * scale3 + shift3)               wgt3 [64][256] or NULL; y2 [n][h][w][64]
+ *                   z2 never reaches memory and y is not re-read.  x, wgt, wgt2 share x_dtype; wgt3 has y_dtype.
+ *                   cin == cout2 == 64 (cout2 = channels of z2), cout == 256, cout3 == 64 (or 0 without wgt3).
+ *                   TDET_FLAG_SCALED_OUT: y (F16) gets a device-chosen exponent; TDET_FLAG_SCALED_OUT2: y2 likewise.  The
+ *                   exponents come from the chained bounds of bound_consts (conv2), bound_consts2 (conv3) and
+ *                   bound_consts3 (next conv1); z2 is scaled like x (an F16 x with x_meta).
  * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;
  *                   its exponent field is left untouched)
  * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled
@@ -237,6 +250,20 @@ typedef struct tdet_op {
   int32_t cin2, stride2, h2, w2;
   int32_t x2_dtype;
   int32_t reserved0;
+  /* ---- TDET_OP_BOTTLENECK_TAIL: conv3 and the next block's conv1 ---- */
+  const void* wgt2;           /* conv3 weights [cout][cout2] of x_dtype */
+  const float* scale2;
+  const float* shift2;
+  const float* bound_consts2;
+  const void* wgt3;           /* next conv1 weights [cout3][cout] of y_dtype, or NULL */
+  const float* scale3;
+  const float* shift3;
+  const float* bound_consts3;
+  void* y2;                   /* [n][h][w][cout3] of y2_dtype */
+  tdet_tensor_meta* y2_meta;
+  int32_t cout2, cout3;
+  int32_t y2_dtype;
+  int32_t reserved1;
 } tdet_op;
 
 typedef struct tdet_plan tdet_plan; /* opaque */

@@ -532,3 +532,27 @@ def test_plans_built_under_an_sm_reserve(cuda_device):
     _check_levels(p1, want_p, ["P2", "P3", "P4", "P5", "P6"])
     for a, b in zip(f0 + p0, f1 + p1):
         assert torch.equal(a, b)
+
+
+def test_cuda_graph_replay_equals_eager(cuda_device):
+    """graphs.GraphedFeatureExtractor: the whole launch sequence of neck(backbone(x)) captured into one CUDA graph
+    replays the plans' own kernels: outputs equal the eager run bit for bit, for every new input."""
+    from torch_detection_b200.graphs import GraphedFeatureExtractor
+    dev = cuda_device
+    bb, neck = helpers.build_product_pair(50, seed=7, bnstats=True)
+    bb, neck = bb.to(dev).eval(), neck.to(dev).eval()
+    g = torch.Generator().manual_seed(3)
+    xs = [torch.randn(1, 3, 256, 320, generator=g).to(torch.bfloat16).to(dev) for _ in range(3)]
+    graphed = GraphedFeatureExtractor(bb, neck, xs[0])
+    for x in xs:
+        with torch.no_grad():
+            want = [o.clone() for o in neck(bb(x))]
+        got = graphed(x)
+        torch.cuda.synchronize()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        graphed(torch.zeros(2, 3, 256, 320, dtype=torch.bfloat16, device=dev))
+    bb.train()
+    with pytest.raises(NotImplementedError):
+        GraphedFeatureExtractor(bb, neck, xs[0])

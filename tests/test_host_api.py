@@ -144,7 +144,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert _C.lib().tdet_abi_version() == _C.ABI_VERSION
-    assert ctypes.sizeof(_C.TdetOp) == 288  # static_assert(sizeof(tdet_op) == 288) in tdet_api.cu
+    assert ctypes.sizeof(_C.TdetOp) == 384  # static_assert(sizeof(tdet_op) == 384) in tdet_api.cu
 
 
 def test_no_gpu_calls_fail_cleanly_without_device():

@@ -307,6 +307,116 @@ def test_conv_dual_source_scaled_output(cuda_device):
         assert float(y.buf.float().abs().max()) < 2.0 ** 15
 
 
+def _tail_reference(x, xres, w2, w3, w1n, bn2, bn3, bn1n, dtype, ydtype):
+    """fp32 reference of the fused bottleneck tail on the kernel's operands, rounding z2 and y where the kernel does."""
+    def bn(t, p):
+        return t * p[0].view(1, -1, 1, 1) + p[1].view(1, -1, 1, 1)
+    z2 = F.relu(bn(F.conv2d(x.float(), w2.to(dtype).float(), None, 1, 1), bn2)).to(dtype).float()
+    y = F.relu(bn(F.conv2d(z2, w3.to(dtype).float()), bn3) + xres.float())
+    y2 = None
+    if w1n is not None:
+        y2 = F.relu(bn(F.conv2d(y.to(ydtype).float(), w1n.to(ydtype).float()), bn1n))
+    return y, y2
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40), (1, 50, 84), (3, 100, 84), (2, 37, 29)],
+                         ids=["2x24x40", "1x50x84", "3x100x84_many_tiles", "2x37x29_ragged"])
+@pytest.mark.parametrize("fuse_next", [True, False], ids=["next_conv1", "tail_only"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_bottleneck_tail(cuda_device, shape, fuse_next, dtype):
+    """TDET_OP_BOTTLENECK_TAIL: conv2 3x3 -> conv3 1x1 + residual + ReLU (-> the next block's conv1) of a layer1
+    bottleneck (resnet.py:101-118) in one kernel, against fp32 convs of the same rounded operands."""
+    from torch_detection_b200 import engine
+    dev = cuda_device
+    n, h, w = shape
+    g = torch.Generator().manual_seed(h * w + n)
+    x = _nhwc(torch.randn(n, 64, h, w, generator=g).to(dev), dtype)
+    xres = _nhwc(torch.randn(n, 256, h, w, generator=g).to(dev), dtype)
+    w2 = (torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5).to(dev)
+    w3 = (torch.randn(256, 64, 1, 1, generator=g) * (2.0 / 64) ** 0.5).to(dev)
+    w1n = (torch.randn(64, 256, 1, 1, generator=g) * (2.0 / 256) ** 0.5).to(dev)
+    bns = [((0.5 + torch.rand(c, generator=g)).to(dev), (0.3 * torch.randn(c, generator=g)).to(dev)) for c in (64, 256, 64)]
+    y = engine.nhwc_empty(n, h, w, 256, dev, dtype)
+    y2 = engine.nhwc_empty(n, h, w, 64, dev, dtype)
+    y2.zero_()
+    nxt = dict(w=engine.pack_conv_weight(w1n, dtype), bn=bns[2], y=engine.act_of(y2)) if fuse_next else None
+    op = engine.op_bottleneck_tail(engine.act_of(x), engine.pack_conv_weight(w2, dtype), engine.act_of(y),
+                                   engine.act_of(xres), engine.pack_conv_weight(w3, dtype), bns[0], bns[1], nxt=nxt)
+    engine.run_op(op, dev)
+    torch.cuda.synchronize()
+    ref_y, ref_y2 = _tail_reference(x, xres, w2, w3, w1n if fuse_next else None, bns[0], bns[1], bns[2], dtype, dtype)
+    err = rel_l2(y.float(), ref_y)
+    print("bottleneck tail %s %s next=%s: y rel-L2 %.3e" % (shape, dtype, fuse_next, err))
+    assert err <= TOL[dtype], "y rel-L2 %.3e" % err
+    if fuse_next:
+        # y2 is computed from the kernel's own 16-bit y: reference it on that
+        ref2 = F.relu(F.conv2d(y.float(), w1n.to(dtype).float()) * bns[2][0].view(1, -1, 1, 1) + bns[2][1].view(1, -1, 1, 1))
+        err2 = rel_l2(y2.float(), ref2)
+        assert err2 <= TOL[dtype], "y2 rel-L2 %.3e" % err2
+        assert rel_l2(y2.float(), ref_y2) <= 3 * TOL[dtype]
+    # the op equals the three unfused launches bit for bit (same arithmetic, same rounding points)
+    z2 = engine.nhwc_empty(n, h, w, 64, dev, dtype)
+    yb = engine.nhwc_empty(n, h, w, 256, dev, dtype)
+    engine.run_op(engine.op_conv(engine.act_of(x), engine.pack_conv_weight(w2, dtype), engine.act_of(z2), 3, 3, 1, 1, 1,
+                                 scale=bns[0][0], shift=bns[0][1], relu=True), dev)
+    engine.run_op(engine.op_conv(engine.act_of(z2), engine.pack_conv_weight(w3, dtype), engine.act_of(yb), 1, 1, 1, 0, 1,
+                                 scale=bns[1][0], shift=bns[1][1], residual=engine.act_of(xres), relu=True), dev)
+    torch.cuda.synchronize()
+    assert torch.equal(y, yb), "fused tail differs from conv2 -> conv3 + residual launched separately"
+
+
+def test_bottleneck_tail_scaled(cuda_device):
+    """Per-tensor exponents through the fused tail: fp16 input with an exponent, fp16 outputs whose exponents the
+    kernel derives from the chained bounds; true values against fp32."""
+    from torch_detection_b200 import engine
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    n, h, w = 2, 40, 56
+    for mag in (1.0, 2.0e3, 3.0e-4):
+        arena = engine.MetaArena(4, dev)
+        m_x, m_r, m_y, m_y2 = (arena.new() for _ in range(4))
+
+        def scaled(shape, row):
+            t = torch.randn(*shape, generator=g).abs() * mag
+            e = int(torch.floor(torch.log2(t.abs().max())).item()) - 13
+            stored = _nhwc((t * 2.0 ** (-e)).to(dev), torch.float16)
+            arena.tensor[row, 0] = e
+            arena.tensor[row, 1] = (stored.float().abs().max() * 2.0 ** e).view(torch.int32)
+            return stored, e
+
+        x, e_x = scaled((n, 64, h, w), 0)
+        xres, e_r = scaled((n, 256, h, w), 1)
+        w2 = (torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5).to(dev)
+        w3 = (torch.randn(256, 64, 1, 1, generator=g) * (2.0 / 64) ** 0.5).to(dev)
+        w1n = (torch.randn(64, 256, 1, 1, generator=g) * (2.0 / 256) ** 0.5).to(dev)
+        bns = [((0.5 + torch.rand(c, generator=g)).to(dev), (0.3 * mag * torch.randn(c, generator=g)).to(dev))
+               for c in (64, 256, 64)]
+        w2p, w3p, w1p = (engine.pack_conv_weight(t, torch.float16) for t in (w2, w3, w1n))
+        y = engine.Act(torch.empty(n * h * w * 256, dtype=torch.float16, device=dev), (n, h, w, 256), torch.float16, m_y)
+        y2 = engine.Act(torch.empty(n * h * w * 64, dtype=torch.float16, device=dev), (n, h, w, 64), torch.float16, m_y2)
+        nxt = dict(w=w1p, bn=bns[2], y=y2, consts=engine.bound_consts(w1p, *bns[2]), scaled_out=True)
+        op = engine.op_bottleneck_tail(engine.Act(x, (n, h, w, 64), torch.float16, m_x), w2p, y,
+                                       engine.Act(xres, (n, h, w, 256), torch.float16, m_r), w3p, bns[0], bns[1],
+                                       consts2=engine.bound_consts(w2p, *bns[0]), consts3=engine.bound_consts(w3p, *bns[1]),
+                                       scaled_out=True, nxt=nxt)
+        engine.run_op(op, dev)
+        torch.cuda.synchronize()
+        metas = arena.read()
+        (e_y, amax_y), (e_y2, amax_y2) = metas[2], metas[3]
+        y_true = (y.buf.view(n, h, w, 256).float() * 2.0 ** e_y).permute(0, 3, 1, 2)
+        y2_true = (y2.buf.view(n, h, w, 64).float() * 2.0 ** e_y2).permute(0, 3, 1, 2)
+        ref_y, _ = _tail_reference(x.float() * 2.0 ** e_x, xres.float() * 2.0 ** e_r, w2, w3, None, bns[0], bns[1], bns[2],
+                                   torch.float16, torch.float16)
+        ref_y2 = F.relu(F.conv2d(y_true, w1n.half().float()) * bns[2][0].view(1, -1, 1, 1) + bns[2][1].view(1, -1, 1, 1))
+        e1, e2 = rel_l2(y_true, ref_y), rel_l2(y2_true, ref_y2)
+        print("bottleneck tail scaled mag %g: e_y=%d e_y2=%d rel-L2 %.2e %.2e" % (mag, e_y, e_y2, e1, e2))
+        # (z2 is rounded to fp16 inside the kernel with ITS exponent; the reference rounds the true values: allow 2x)
+        assert torch.isfinite(y_true).all() and e1 <= 2 * TOL[torch.float16] and e2 <= TOL[torch.float16]
+        assert abs(amax_y - float(y_true.abs().max())) <= 1e-3 * amax_y
+        assert abs(amax_y2 - float(y2_true.abs().max())) <= 1e-3 * amax_y2
+        assert float(y.buf.float().abs().max()) < 2.0 ** 15 and float(y2.buf.float().abs().max()) < 2.0 ** 15
+
+
 @pytest.mark.parametrize("magnitude", [1.0, 3.0e4, 2.0e-5])
 def test_scaled_fp16_chain(cuda_device, magnitude):
     """Per-tensor power-of-two exponents: conv -> (conv + residual) with device-chosen output

@@ -26,6 +26,7 @@ OP_AMAX = 12
 OP_BN_AFFINE_GRAD = 13
 OP_SPLIT_COMBINE = 14
 OP_MAXPOOL_BWD, OP_STEM_WGRAD, OP_PARITY_MERGE = 15, 16, 17
+OP_BOTTLENECK_TAIL = 18
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1
@@ -34,6 +35,7 @@ FLAG_COARSE_PARITY = 4
 FLAG_SPLIT = 8
 FLAG_POOL = 16
 FLAG_DUAL = 32
+FLAG_SCALED_OUT2 = 64
 
 
 class TdetOp(ctypes.Structure):
@@ -60,6 +62,12 @@ class TdetOp(ctypes.Structure):
         ("x2", ctypes.c_void_p), ("x2_meta", ctypes.c_void_p),
         ("cin2", ctypes.c_int32), ("stride2", ctypes.c_int32), ("h2", ctypes.c_int32), ("w2", ctypes.c_int32),
         ("x2_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("wgt2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("shift2", ctypes.c_void_p),
+        ("bound_consts2", ctypes.c_void_p),
+        ("wgt3", ctypes.c_void_p), ("scale3", ctypes.c_void_p), ("shift3", ctypes.c_void_p),
+        ("bound_consts3", ctypes.c_void_p),
+        ("y2", ctypes.c_void_p), ("y2_meta", ctypes.c_void_p),
+        ("cout2", ctypes.c_int32), ("cout3", ctypes.c_int32), ("y2_dtype", ctypes.c_int32), ("reserved1", ctypes.c_int32),
     ]
 
 

@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: no-ops unless a profiler (ncu --nvtx, nsys) is attached
 
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include "conv_gemm.cuh"
 #include "wgrad_gemm.cuh"
 #include "conv_swap.cuh"
+#include "bottleneck_fused.cuh"
 #include "aux_kernels.cuh"
 
 namespace {
@@ -23,7 +25,7 @@ namespace {
 using namespace tdet;
 
 static_assert(sizeof(tdet_tensor_meta) == sizeof(TensorMeta), "metadata layout mismatch");
-static_assert(sizeof(tdet_op) == 288, "tdet_op layout changed: bump TDET_ABI_VERSION and the ctypes mirror (_C.TdetOp)");
+static_assert(sizeof(tdet_op) == 384, "tdet_op layout changed: bump TDET_ABI_VERSION and the ctypes mirror (_C.TdetOp)");
 
 thread_local char g_err[512] = "";
 
@@ -133,6 +135,9 @@ struct Launch {
   bool pool = false;      // stem kernel with the fused max-pool
   bool swap = false;      // operand-swapped kernel for Cout <= 128 (conv_swap.cuh)
   bool no_patch = false;  // debugging hook: force the im2col loader
+  // fused bottleneck tail
+  FbParams fb{};
+  int fb_n3 = 0;
   // wgrad
   WgradParams wp{};
   int wg_nb = 0, wg_pix = 0, wg_mt = 1;
@@ -1189,11 +1194,104 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   return TDET_OK;
 }
 
+// ---- fused bottleneck tail (bottleneck_fused.cuh) --------------------------------------------------------------
+template <int N3>
+int launch_fb_t(const FbParams& fp, dim3 grid, cudaStream_t st) {
+  using L = FbSmem<N3>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  TDET_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    TDET_CUDA(cudaFuncSetAttribute(bottleneck_tail_kernel<N3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    attr_set[dev] = true;
+  }
+  return launch_pdl(bottleneck_tail_kernel<N3>, grid, kFbThreads, L::kDynamic, st, fp);
+}
+
+int build_bottleneck_tail(Launch& l, const DeviceInfo& di) {
+  const tdet_op& o = l.op;
+  if (o.cin != 64 || o.cout2 != 64 || o.cout != 256 || (o.wgt3 && o.cout3 != 64) || (!o.wgt3 && o.cout3 != 0))
+    return fail(TDET_ERR_UNSUPPORTED_SHAPE,
+                "bottleneck tail: 64 -> 64 (3x3) -> 256 (1x1) [-> 64 (1x1)] only (got %d -> %d -> %d -> %d)", o.cin,
+                o.cout2, o.cout, o.cout3);
+  if (o.kh != 3 || o.kw != 3 || o.stride != 1 || o.pad != 1 || o.dil != 1 || o.ho != o.h || o.wo != o.w)
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: conv2 must be 3x3 / stride 1 / pad 1");
+  if (!o.x || !o.wgt || !o.wgt2 || !o.y || !o.residual || (o.wgt3 && !o.y2))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: null tensor pointer");
+  if (!is16(o.x_dtype) || !is16(o.y_dtype) || !is16(o.residual_dtype) || (o.wgt3 && !is16(o.y2_dtype)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: 16-bit tensors only");
+  if (o.coarse || o.mask || o.groups > 1 || (o.flags & (TDET_FLAG_SPLIT | TDET_FLAG_DUAL | TDET_FLAG_COARSE_PARITY)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: no coarse / mask / groups / split / dual operands");
+  const bool out_scaled = (o.flags & TDET_FLAG_SCALED_OUT) != 0;
+  const bool y2_scaled = o.wgt3 && (o.flags & TDET_FLAG_SCALED_OUT2) != 0;
+  const bool z2_scaled = o.x_dtype == TDET_F16 && o.x_meta && o.bound_consts;
+  if ((out_scaled && (o.y_dtype != TDET_F16 || !o.y_meta)) || (y2_scaled && (o.y2_dtype != TDET_F16 || !o.y2_meta)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: a scaled output must be F16 with a meta");
+  if ((out_scaled || y2_scaled) && (!o.bound_consts || !o.bound_consts2 || !o.x_meta || !o.residual_meta ||
+                                    (y2_scaled && !o.bound_consts3)))
+    return fail(TDET_ERR_INVALID_ARGUMENT,
+                "bottleneck tail: scaled outputs need x_meta, residual_meta and the bound constants of every conv");
+  const long long m_ll = static_cast<long long>(o.n) * o.h * o.w;
+  if (m_ll <= 0 || m_ll > 0x7FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "M out of range");
+  FbParams& fp = l.fb;
+  memset(&fp, 0, sizeof(fp));
+  fp.H = o.h;
+  fp.W = o.w;
+  fp.tiles_w = (o.w + kPatchBW - 1) / kPatchBW;
+  fp.tiles_h = (o.h + kPatchBH - 1) / kPatchBH;
+  const long long tiles = static_cast<long long>(o.n) * fp.tiles_w * fp.tiles_h;
+  if (tiles > 0x7FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "too many tiles");
+  fp.num_tiles = static_cast<int>(tiles);
+  fp.x_fp16 = o.x_dtype == TDET_F16;
+  fp.out_fp16 = o.y_dtype == TDET_F16;
+  fp.res_fp16 = o.residual_dtype == TDET_F16;
+  fp.z1o_fp16 = o.y2_dtype == TDET_F16;
+  fp.z2_scaled = z2_scaled ? 1 : 0;
+  fp.out_scaled = out_scaled ? 1 : 0;
+  fp.z1o_scaled = y2_scaled ? 1 : 0;
+  fp.scale2 = o.scale; fp.shift2 = o.shift;
+  fp.scale3 = o.scale2; fp.shift3 = o.shift2;
+  fp.scale1n = o.scale3; fp.shift1n = o.shift3;
+  fp.consts2 = o.bound_consts; fp.consts3 = o.bound_consts2; fp.consts1n = o.bound_consts3;
+  fp.z1_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
+  fp.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+  fp.out_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+  fp.z1o_meta = reinterpret_cast<TensorMeta*>(o.y2_meta);
+  fp.res_prefetch = env_int("TDET_TAIL_PREFETCH", 1);
+  fp.trace = reinterpret_cast<unsigned long long*>(o.dw);  // debugging aid: cycle trace of CTA 0 (NULL in normal runs)
+  int rc = encode_4d(&fp.tmap_z1, o.x, o.x_dtype, 64, o.w, o.h, o.n, kPatchPW, kPatchPH, "conv2 halo patch");
+  if (rc) return rc;
+  rc = encode_2d(&fp.tmap_w2, o.wgt, o.x_dtype, 9 * 64, 64, 64, "conv2 weights");
+  if (rc) return rc;
+  rc = encode_2d(&fp.tmap_w3, o.wgt2, o.x_dtype, 64, 256, 256, "conv3 weights");
+  if (rc) return rc;
+  rc = encode_4d(&fp.tmap_res, o.residual, o.residual_dtype, 256, o.w, o.h, o.n, kPatchBW, kPatchBH, "residual");
+  if (rc) return rc;
+  rc = encode_4d(&fp.tmap_out, o.y, o.y_dtype, 256, o.w, o.h, o.n, kPatchBW, kPatchBH, "block output");
+  if (rc) return rc;
+  l.fb_n3 = o.wgt3 ? 64 : 0;
+  if (o.wgt3) {
+    rc = encode_2d(&fp.tmap_w1n, o.wgt3, o.y_dtype, 256, 64, 64, "next conv1 weights");
+    if (rc) return rc;
+    rc = encode_4d(&fp.tmap_z1o, o.y2, o.y2_dtype, 64, o.w, o.h, o.n, kPatchBW, kPatchBH, "next conv1 output");
+    if (rc) return rc;
+  }
+  int g = di.num_sms - di.sm_reserve;
+  if (g > fp.num_tiles) g = fp.num_tiles;
+  l.grid = dim3(static_cast<unsigned>(g), 1, 1);
+  l.bn = 256;
+  const double rows = static_cast<double>(m_ll);
+  l.flops = 2.0 * rows * (64.0 * 576 + 256.0 * 64 + (o.wgt3 ? 64.0 * 256 : 0.0));
+  l.bytes = 2.0 * (rows * (64 + 256 + 256 + (o.wgt3 ? 64 : 0)) + 64.0 * 576 + 256.0 * 64 + (o.wgt3 ? 64.0 * 256 : 0.0));
+  return TDET_OK;
+}
+
 int build_launch(Launch& l, const DeviceInfo& di) {
   const tdet_op& o = l.op;
   l.kind = o.kind;
   switch (o.kind) {
     case TDET_OP_CONV: return build_conv(l, di);
+    case TDET_OP_BOTTLENECK_TAIL: return build_bottleneck_tail(l, di);
     case TDET_OP_STEM: return build_stem(l, di);
     case TDET_OP_PREP:
       if (o.cin != 3 || !o.x || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "prep: bad arguments");
@@ -1305,6 +1403,8 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
   switch (l.kind) {
     case TDET_OP_CONV:
     case TDET_OP_STEM: return launch_gemm(l, st);
+    case TDET_OP_BOTTLENECK_TAIL:
+      return l.fb_n3 ? launch_fb_t<64>(l.fb, l.grid, st) : launch_fb_t<0>(l.fb, l.grid, st);
     case TDET_OP_PREP: {
       const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
       const long long total = static_cast<long long>(o.n) * hp * wp;
@@ -1505,6 +1605,36 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       return TDET_OK;
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "unknown op kind %d", l.kind);
+}
+
+// NVTX ranges: one range per plan run ("tdet:plan[n ops]") and, with TDET_NVTX=2, one per launch
+// named after the op kind and its GEMM shape, so that profiler timelines and `ncu --nvtx-include` can address a stage.
+int nvtx_level() {
+  static const int level = env_int("TDET_NVTX", 1);
+  return level;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name, bool enable) : on(enable) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() {
+    if (on) nvtxRangePop();
+  }
+};
+const char* kind_name(int kind) {
+  static const char* names[] = {"prep", "stem", "maxpool", "conv", "subsample", "wgrad", "dw_unpack", "colsum", "sumpool2",
+                                "dilate2", "add_mask", "zero", "amax", "bn_affine_grad", "split_combine", "maxpool_bwd",
+                                "stem_wgrad", "parity_merge", "bottleneck_tail"};
+  return (kind >= 0 && kind < static_cast<int>(sizeof(names) / sizeof(names[0]))) ? names[kind] : "op";
+}
+int run_launch_traced(const Launch& l, const DeviceInfo& di, cudaStream_t st, int index) {
+  if (nvtx_level() < 2) return run_launch(l, di, st);
+  char name[96];
+  snprintf(name, sizeof(name), "tdet:%d:%s %dx%d k%d n%d", index, kind_name(l.kind), l.op.ho, l.op.wo,
+           l.op.cin * (l.op.kh > 0 ? l.op.kh * l.op.kw : 1), l.op.cout);
+  NvtxRange r(name, true);
+  return run_launch(l, di, st);
 }
 
 struct DeviceGuard {
@@ -1792,8 +1922,12 @@ int tdet_plan_run(tdet_plan* plan, const void* const* ext_ptrs, int n_ext, void*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rc = plan_begin(plan, st);
   if (rc) return rc;
+  char name[48];
+  snprintf(name, sizeof(name), "tdet:plan[%d ops]", static_cast<int>(plan->launches.size()));
+  NvtxRange range(name, nvtx_level() >= 1);
+  int index = 0;
   for (const Launch& l : plan->launches) {
-    rc = run_launch(l, *plan->di, st);
+    rc = run_launch_traced(l, *plan->di, st, index++);
     if (rc) return rc;
   }
   return TDET_OK;
@@ -1817,8 +1951,11 @@ int tdet_plan_run_range(tdet_plan* plan, const void* const* ext_ptrs, int n_ext,
     rc = plan_begin(plan, st);
     if (rc) return rc;
   }
+  char name[64];
+  snprintf(name, sizeof(name), "tdet:plan[%d..%d of %d ops]", first, last, static_cast<int>(plan->launches.size()));
+  NvtxRange range(name, nvtx_level() >= 1);
   for (int i = first; i < last; ++i) {
-    rc = run_launch(plan->launches[i], *plan->di, st);
+    rc = run_launch_traced(plan->launches[i], *plan->di, st, i);
     if (rc) return rc;
   }
   return TDET_OK;
@@ -1869,6 +2006,18 @@ int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* ou
     out->n = l.wp.cin * l.wp.kh * l.wp.kw;
     out->k = l.wp.M;
     out->variant = l.wg_pix * 10 + l.wg_mt;
+    out->flops = l.flops;
+    out->bytes = l.bytes;
+    return TDET_OK;
+  }
+  if (l.kind == TDET_OP_BOTTLENECK_TAIL) {
+    out->tile_n = 256;
+    out->grid = static_cast<int32_t>(l.grid.x);
+    out->a_mode = A_PATCH;
+    out->m = l.fb.num_tiles * kBM;
+    out->n = 256;
+    out->k = 576 + 64 + l.fb_n3 * 4;
+    out->variant = 32768 + l.fb_n3;
     out->flops = l.flops;
     out->bytes = l.bytes;
     return TDET_OK;

@@ -380,6 +380,41 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
     return op
 
 
+def op_bottleneck_tail(x, w2, y, residual, w3, bn2, bn3, consts2=None, consts3=None, scaled_out=False, nxt=None):
+    """TDET_OP_BOTTLENECK_TAIL: z2 = relu(bn2(conv3x3(x))), y = relu(bn3(conv1x1(z2)) + residual) and -- with
+    nxt = dict(w=[64][256] in y's dtype, bn=(scale, shift), y=Act, consts=, scaled_out=) -- the next block's
+    y2 = relu(bn1(conv1x1(y))), in one kernel.  x: Act [n][h][w][64]; w2 [64][3][3][64], w3 [256][64] in x's dtype;
+    bn2 / bn3: (scale, shift) fp32 device vectors."""
+    n, h, w, cin = x.shape
+    if w2.dtype != x.dtype or w3.dtype != x.dtype:
+        raise ValueError("bottleneck tail: conv2 / conv3 weights must be packed in the input tensor's format")
+    op = _C.TdetOp()
+    op.kind = _C.OP_BOTTLENECK_TAIL
+    op.flags = _C.FLAG_RELU | (_C.FLAG_SCALED_OUT if scaled_out else 0)
+    op.n, op.h, op.w, op.cin = n, h, w, cin
+    op.cout, op.cout2, op.kh, op.kw = w3.shape[0], w2.shape[0], 3, 3
+    op.stride, op.pad, op.dil = 1, 1, 1
+    op.ho, op.wo = h, w
+    assert y.shape == (n, h, w, op.cout) and residual.shape == y.shape
+    op.x_dtype, op.y_dtype, op.residual_dtype = _TD[x.dtype], _TD[y.dtype], _TD[residual.dtype]
+    op.x, op.wgt, op.y, op.residual = x.ptr, w2.data_ptr(), y.ptr, residual.ptr
+    op.x_meta, op.y_meta, op.residual_meta = x.meta, y.meta, residual.meta
+    op.scale, op.shift = _ptr(bn2[0]), _ptr(bn2[1])
+    op.wgt2, op.scale2, op.shift2 = w3.data_ptr(), _ptr(bn3[0]), _ptr(bn3[1])
+    op.bound_consts, op.bound_consts2 = _ptr(consts2), _ptr(consts3)
+    if nxt is not None:
+        y2 = nxt["y"]
+        if nxt["w"].dtype != y.dtype:
+            raise ValueError("bottleneck tail: the next conv1's weights must be packed in y's format")
+        assert y2.shape == (n, h, w, nxt["w"].shape[0])
+        op.wgt3, op.scale3, op.shift3 = nxt["w"].data_ptr(), _ptr(nxt["bn"][0]), _ptr(nxt["bn"][1])
+        op.bound_consts3 = _ptr(nxt.get("consts"))
+        op.y2, op.y2_meta, op.y2_dtype, op.cout3 = y2.ptr, y2.meta, _TD[y2.dtype], nxt["w"].shape[0]
+        if nxt.get("scaled_out"):
+            op.flags |= _C.FLAG_SCALED_OUT2
+    return op
+
+
 def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, split=False):
     """x: logical (n, 3, h, w) image batch (fp32 / bf16 / uint8, any strides: an HWC batch viewed as NCHW is
     fine); scale/shift: optional fp32[3] device vectors of the per-channel normalisation v*scale + shift;

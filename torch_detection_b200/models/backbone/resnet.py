@@ -343,6 +343,27 @@ class ResNet(nn.Module):
                                       relu=relu, consts=consts, scaled_out=is_scaled, groups=module.groups,
                                       split=split))
 
+        def tail(pre, unit, z1, xin, dst, head, head_pre):
+            """Emits the fused tail of `unit` (input z1 = its conv1 output, residual xin, output dst) and returns the
+            conv1 output of the following block `head` if that is computed by the same kernel (else None)."""
+            def operands(name, module, bn, dtype):
+                wgt = cache.get((name, "w", dtype), lambda out: engine.pack_conv_weight(module.weight, dtype, out=out),
+                                deps=(module.weight,))
+                sc, sh = cache.get((name, "bn"), lambda out: engine.fold_bn(bn, out=out), deps=_bn_deps(bn))
+                consts = cache.get((name, "consts", dtype), lambda out: engine.bound_consts(wgt, sc, sh, out=out),
+                                   deps=(module.weight,) + _bn_deps(bn)) if scaled else None
+                return wgt, (sc, sh), consts
+            w2, bn2, c2 = operands(pre + "conv2", unit.conv2, getattr(unit, unit.norm_names[1]), z1.dtype)
+            w3, bn3, c3 = operands(pre + "conv3", unit.conv3, getattr(unit, unit.norm_names[2]), z1.dtype)
+            nxt, y2 = None, None
+            if head is not None:
+                w1, bn1, c1 = operands(head_pre + "conv1", head.conv1, getattr(head, head.norm_names[0]), dst.dtype)
+                y2 = new_act(z1.shape, internal)
+                nxt = dict(w=w1, bn=bn1, y=y2, consts=c1, scaled_out=scaled and y2.dtype == torch.float16)
+            ops.append(engine.op_bottleneck_tail(z1, w2, dst, xin, w3, bn2, bn3, consts2=c2, consts3=c3,
+                                                 scaled_out=scaled and dst.dtype == torch.float16, nxt=nxt))
+            return y2
+
         # geometry of every stage output, and the full-batch bf16 tensors that hold them
         ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
         hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
@@ -436,10 +457,27 @@ class ResNet(nn.Module):
                 for li in stages:
                     lname = self.res_layers[li]
                     stage = getattr(self, lname)
+                    pending_z1 = None  # conv1 output of the next block, already produced by a fused bottleneck tail
                     for bi, unit in enumerate(stage):
                         pre = "%s.%d." % (lname, bi)
                         last = bi == len(stage) - 1
                         nb, hb, wb, _ = cur.shape
+                        if not train and not split and _fuses_tail(unit):
+                            # TDET_OP_BOTTLENECK_TAIL: conv2 -> conv3 + residual + ReLU (-> the next block's conv1) in
+                            # one kernel; z2 never reaches memory and the block output is not re-read
+                            z1 = pending_z1
+                            if z1 is None:
+                                z1 = new_act((nb, hb, wb, unit.conv1.out_channels), internal)
+                                conv(pre + "conv1", unit.conv1, getattr(unit, unit.norm_names[0]), cur, z1)
+                            dst = boundary_act(li, i0, cn) if last else new_act((nb, hb, wb, unit.conv3.out_channels), internal)
+                            head = stage[bi + 1] if (FUSE_TAIL_NEXT and not last and _fuses_tail(stage[bi + 1])) else None
+                            pending_z1 = tail(pre, unit, z1, cur, dst, head, "%s.%d." % (lname, bi + 1))
+                            pool.release(z1.buf)
+                            if cur_pooled:
+                                pool.release(cur.buf)
+                            cur = dst
+                            cur_pooled = not last
+                            continue
                         hn = engine.conv_out(hb, 3, unit.stride, unit.dilation, unit.dilation)
                         wn = engine.conv_out(wb, 3, unit.stride, unit.dilation, unit.dilation)
                         residual = cur
@@ -879,6 +917,12 @@ FUSE_STEM_POOL = os.environ.get("TDET_STEM_POOL", "1") != "0"
 # a stage's projection shortcut is contracted inside the first bottleneck's conv3 launch (TDET_FLAG_DUAL)
 FUSE_SHORTCUT = os.environ.get("TDET_FUSE_SHORTCUT", "1") != "0"
 
+# conv2 -> conv3 + residual -> next conv1 of the identity-shortcut bottlenecks of layer1 as one kernel
+FUSE_TAIL = os.environ.get("TDET_FUSE_TAIL", "1") != "0"
+# ... and the next block's conv1 in the same kernel (measured: no faster than the tail-only kernel + a separate conv1,
+# the tail-only variant keeps W2 resident; kept as an experiment switch)
+FUSE_TAIL_NEXT = os.environ.get("TDET_FUSE_TAIL_NEXT", "0") != "0"
+
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
 
@@ -892,6 +936,18 @@ def _fuses_shortcut(unit):
     ds = unit.downsample[0]
     return (last.out_channels % 256 == 0 and last.groups == 1 and last.stride[0] == 1 and
             ds.kernel_size[0] == 1 and ds.padding[0] == 0 and ds.groups == 1 and ds.in_channels % 64 == 0)
+
+
+def _fuses_tail(unit):
+    """True if conv2 -> conv3 + residual (-> the next block's conv1) of this unit run as ONE kernel
+    (TDET_OP_BOTTLENECK_TAIL): an identity-shortcut bottleneck with planes = 64 (layer1 of ResNet-50/101/152)."""
+    if not FUSE_TAIL or unit.downsample is not None or tuple(unit.kernel_sizes) != (1, 3, 1):
+        return False
+    c1, c2, c3 = unit.conv1, unit.conv2, unit.conv3
+    return (c1.in_channels == 256 and c1.out_channels == 64 and c1.stride[0] == 1 and c1.groups == 1 and
+            c2.in_channels == 64 and c2.out_channels == 64 and c2.stride[0] == 1 and c2.padding[0] == 1 and
+            c2.dilation[0] == 1 and c2.groups == 1 and c3.in_channels == 64 and c3.out_channels == 256 and
+            c3.groups == 1)
 
 
 def _sum_into(a, b, out):

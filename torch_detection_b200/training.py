@@ -117,8 +117,12 @@ class BucketAllReduce(object):
                 if self._timing is not None:
                     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     t0.record(comm)
-                op = self.dist.ReduceOp.AVG if self.average else self.dist.ReduceOp.SUM
-                self.dist.all_reduce(out, op=op, group=self.group)
+                if self.average and AVG_IN_NCCL:
+                    self.dist.all_reduce(out, op=self.dist.ReduceOp.AVG, group=self.group)
+                else:
+                    self.dist.all_reduce(out, group=self.group)
+                    if self.average:
+                        out.div_(world)
                 if t1 is not None:
                     t1.record(comm)
                     self._timing.append((t0, t1))
@@ -140,6 +144,10 @@ class BucketAllReduce(object):
     def module_done(self):
         if not self.defer:
             self.finish()
+
+
+# ncclAvg (1) or ncclSum + a division pass on the side stream (0)
+AVG_IN_NCCL = __import__("os").environ.get("TDET_NCCL_AVG", "1") != "0"
 
 
 class GradBucket(object):
