@@ -384,6 +384,13 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
         sync.finish()
 
     ms_total, _ = timed_steps(ctx, step, steps, warmup)
+    # host time to ENQUEUE one step (no synchronisation inside): if it approaches ms_per_step the leg is launch-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    enqueue_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
     b0, n0 = sync.bytes_reduced, sync.buckets_reduced
     step()
     allreduce_mb = (sync.bytes_reduced - b0) / 1e6
@@ -413,7 +420,7 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
         res = {
             "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
             "img_s": value, "value": value, "unit": "img/s", "n_gpus": world, "steps": steps,
-            "ms_per_step": ms_total / steps, "batch_per_gpu": B,
+            "ms_per_step": ms_total / steps, "batch_per_gpu": B, "host_enqueue_ms_per_step": enqueue_ms,
             "allreduce_mb": allreduce_mb if world > 1 else 0.0, "buckets_per_step": buckets,
             "allreduce_device_ms": coll_ms, "allreduce_exposed_ms": exposed_ms,
             "overlap_ms": (coll_ms - max(exposed_ms, 0.0)) if coll_ms is not None else None,
@@ -469,7 +476,8 @@ def r101_leg(ctx, args, steps, warmup):
            "workload": "config 3: ResNet-101 + FPN forward, batch 64 sharded over %d GPU(s), %dx%d" % (
                ctx.world, x.shape[2], x.shape[3])}
     del bb, neck, x
-    torch.cuda.empty_cache()
+    if os.environ.get("TDET_BENCH_KEEP_CACHE", "0") == "0":
+        torch.cuda.empty_cache()
     return res
 
 
@@ -634,10 +642,15 @@ def main():
 
     # ---- secondary legs: config 3 (R101, batch 64 sharded) and config 4 (training, NCCL all-reduce) ------
     r101 = train = None
-    if "r101" in legs and args.io_dtype == "bf16":
-        r101 = r101_leg(ctx, args, 5, 3)
+    import gc
+    gc.collect()                 # the modules hold reference cycles: free their arenas before the next leg builds its own
+    torch.cuda.empty_cache()
     if "train" in legs and args.io_dtype == "bf16":
         train = train_leg(ctx, args, 10, 3)
+        gc.collect()
+        torch.cuda.empty_cache()
+    if "r101" in legs and args.io_dtype == "bf16":
+        r101 = r101_leg(ctx, args, 5, 3)
     if sampler:
         sampler.stop()
 

@@ -626,13 +626,16 @@ bottleneck_tail_kernel(const __grid_constant__ FbParams p) {
             const uint32_t w4[4] = {rr[c].x, rr[c].y, rr[c].z, rr[c].w};
             float x[8];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float lo, hi;
-              unpack16x2(w4[e], res_fp16, lo, hi);
-              const float2 s2 = *reinterpret_cast<const float2*>(sc3 + cb + 8 * c + 2 * e);
-              const float2 h2 = *reinterpret_cast<const float2*>(sh3 + cb + 8 * c + 2 * e);
-              x[2 * e] = fmaxf(fmaf(lo, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e]), s2.x, h2.x)), 0.0f);
-              x[2 * e + 1] = fmaxf(fmaf(hi, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 1]), s2.y, h2.y)), 0.0f);
+            for (int e = 0; e < 4; e += 2) {
+              float r0, r1, r2, r3;
+              unpack16x2(w4[e], res_fp16, r0, r1);
+              unpack16x2(w4[e + 1], res_fp16, r2, r3);
+              const float4 s4 = *reinterpret_cast<const float4*>(sc3 + cb + 8 * c + 2 * e);
+              const float4 h4 = *reinterpret_cast<const float4*>(sh3 + cb + 8 * c + 2 * e);
+              x[2 * e + 0] = fmaxf(fmaf(r0, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 0]), s4.x, h4.x)), 0.0f);
+              x[2 * e + 1] = fmaxf(fmaf(r1, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 1]), s4.y, h4.y)), 0.0f);
+              x[2 * e + 2] = fmaxf(fmaf(r2, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 2]), s4.z, h4.z)), 0.0f);
+              x[2 * e + 3] = fmaxf(fmaf(r3, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 3]), s4.w, h4.w)), 0.0f);
             }
             if (valid) {
 #pragma unroll
