@@ -272,38 +272,57 @@ class Ctx(object):
             self.dist.destroy_process_group()
 
 
+class quiet_host(object):
+    """Python's cyclic garbage collector paused for a timed region (collected just before): a generation-2 pass over
+    the modules / plans of earlier legs takes 20-200 ms of HOST time and, landing inside a 10-step loop, showed up as
+    9.3 ms training steps averaging 11-33 ms at random (per-step events: median 9.3, one outlier)."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self.was_enabled = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self.was_enabled:
+            gc.enable()
+
+
 def timed_steps(ctx, fn, steps, warmup):
     """W untimed steps, then exactly `steps` steps between barrier + synchronize, device events, max over ranks."""
     for _ in range(max(warmup, 3)):
         fn()
-    ctx.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        out = fn()
-    e1.record()
-    ctx.barrier()
+    with quiet_host():
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        ctx.barrier()
     return ctx.max_over_ranks([e0.elapsed_time(e1)])[0], out
 
 
 def sustained_leg(ctx, fn, images_per_step, min_seconds, sampler):
     """Loops the step until >= min_seconds of device time have passed (the power cap then sets the clock)."""
     fn()
-    ctx.barrier()
-    first = sampler.mark() if sampler else 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    steps = 0
-    while True:
-        for _ in range(20):
-            fn()
-        steps += 20
-        torch.cuda.synchronize()
-        if time.perf_counter() - t0 >= min_seconds:
-            break
-    e1.record()
-    ctx.barrier()
+    with quiet_host():
+        ctx.barrier()
+        first = sampler.mark() if sampler else 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        steps = 0
+        while True:
+            for _ in range(20):
+                fn()
+            steps += 20
+            torch.cuda.synchronize()
+            if time.perf_counter() - t0 >= min_seconds:
+                break
+        e1.record()
+        ctx.barrier()
     ms = ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
     clocks = sampler.summary(first, sampler.mark()) if sampler else None
     return {"value": ctx.world * images_per_step * steps / (ms / 1e3), "unit": "img/s", "seconds": ms / 1e3,
@@ -344,14 +363,15 @@ def e2e_leg(ctx, step, x_host, x_dev, out_like, steps, copy_levels):
                 h.copy_(o[lvl], non_blocking=True)
 
     loop(3)
-    ctx.barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    f0.record()
-    loop(steps)
-    f1.record()
-    ctx.barrier()
-    t_wall = time.perf_counter() - t_wall0
+    with quiet_host():
+        ctx.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        f0.record()
+        loop(steps)
+        f1.record()
+        ctx.barrier()
+        t_wall = time.perf_counter() - t_wall0
     ms = max(ctx.max_over_ranks([max(f0.elapsed_time(f1), 0.0), t_wall * 1e3]))  # events vs wall clock: the slower
     return (ctx.world * B * steps / (ms / 1e3), x_host.numel() * x_host.element_size(),
             sum(h.numel() * h.element_size() for h in host_out))
@@ -384,6 +404,14 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
         sync.finish()
 
     ms_total, _ = timed_steps(ctx, step, steps, warmup)
+    # per-step device times (events between steps): a hiccup shows up as max >> median
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        step()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
     # host time to ENQUEUE one step (no synchronisation inside): if it approaches ms_per_step the leg is launch-bound
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -421,6 +449,7 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
             "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
             "img_s": value, "value": value, "unit": "img/s", "n_gpus": world, "steps": steps,
             "ms_per_step": ms_total / steps, "batch_per_gpu": B, "host_enqueue_ms_per_step": enqueue_ms,
+            "per_step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
             "allreduce_mb": allreduce_mb if world > 1 else 0.0, "buckets_per_step": buckets,
             "allreduce_device_ms": coll_ms, "allreduce_exposed_ms": exposed_ms,
             "overlap_ms": (coll_ms - max(exposed_ms, 0.0)) if coll_ms is not None else None,
@@ -646,7 +675,10 @@ def main():
     gc.collect()                 # the modules hold reference cycles: free their arenas before the next leg builds its own
     torch.cuda.empty_cache()
     if "train" in legs and args.io_dtype == "bf16":
+        m0 = sampler.mark() if sampler else 0
         train = train_leg(ctx, args, 10, 3)
+        if train is not None and sampler:
+            train["clocks"] = sampler.summary(m0, sampler.mark())
         gc.collect()
         torch.cuda.empty_cache()
     if "r101" in legs and args.io_dtype == "bf16":
@@ -684,7 +716,8 @@ def main():
                                                                    args.io_dtype),
                        "images_per_gpu": B, "global_batch": B * world, "gflop_per_image": flops_img / 1e9,
                        "parallelism": "batch sharded, no data-path collective",
-                       "l2": "per-step working set (~1.4 GB/img of activations) >> 126 MB L2, no explicit flush"},
+                       "l2": "per-step working set (~1.4 GB/img of activations) >> 126 MB L2, no explicit flush",
+                       "host": "python's cyclic gc collected before and paused during every timed region"},
             "tflops_per_gpu": (value / world) * flops_img / 1e12,
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "public API neck(backbone(x)); pinned host batch -> H2D (copy stream, double buffered) -> "
