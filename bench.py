@@ -405,13 +405,25 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
 
     ms_total, _ = timed_steps(ctx, step, steps, warmup)
     # per-step device times (events between steps): a hiccup shows up as max >> median
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    evs[0].record()
-    for i in range(steps):
-        step()
-        evs[i + 1].record()
-    torch.cuda.synchronize()
-    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(steps))
+    n_probe = max(steps, 30)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_probe + 1)]
+    host_t = [0.0] * (n_probe + 1)
+    with quiet_host():
+        torch.cuda.synchronize()
+        evs[0].record()
+        host_t[0] = time.perf_counter()
+        segs = [0] * (n_probe + 1)
+        segs[0] = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+        for i in range(n_probe):
+            step()
+            evs[i + 1].record()
+            host_t[i + 1] = time.perf_counter()
+            segs[i + 1] = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
+        torch.cuda.synchronize()
+    dev_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_probe)]
+    host_step = [(host_t[i + 1] - host_t[i]) * 1e3 for i in range(n_probe)]
+    per_step = sorted(dev_step)
+    worst = max(range(n_probe), key=lambda i: dev_step[i])
     # host time to ENQUEUE one step (no synchronisation inside): if it approaches ms_per_step the leg is launch-bound
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -449,7 +461,11 @@ def train_leg(ctx, args, steps, warmup, launch_table=""):
             "metric": "ResNet-%d-FPN train (fwd+bwd) img/s @800x1333 bf16, frozen BN + stem + stage 1" % args.depth,
             "img_s": value, "value": value, "unit": "img/s", "n_gpus": world, "steps": steps,
             "ms_per_step": ms_total / steps, "batch_per_gpu": B, "host_enqueue_ms_per_step": enqueue_ms,
-            "per_step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+            "per_step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1],
+                            "n": n_probe, "worst_step": worst, "host_ms_around_worst": host_step[max(worst - 2, 0):worst + 2],
+                            "host_ms_max": max(host_step),
+                            "new_allocator_segments_per_step": [segs[i + 1] - segs[i] for i in range(n_probe)],
+                            "slow_host_step": max(range(n_probe), key=lambda i: host_step[i])},
             "allreduce_mb": allreduce_mb if world > 1 else 0.0, "buckets_per_step": buckets,
             "allreduce_device_ms": coll_ms, "allreduce_exposed_ms": exposed_ms,
             "overlap_ms": (coll_ms - max(exposed_ms, 0.0)) if coll_ms is not None else None,

@@ -88,7 +88,9 @@ typedef enum tdet_op_kind {
   TDET_OP_MAXPOOL_BWD = 15,  /* backward of MaxPool2d(3, 2, 1) fused with the ReLU backward of its input (stem) */
   TDET_OP_STEM_WGRAD = 16,   /* weight gradient of the 7x7/2 stem conv from the staged image */
   TDET_OP_PARITY_MERGE = 17, /* interleave the four parity-class results of a stride-2 3x3 dgrad (+ ReLU mask) */
-  TDET_OP_BOTTLENECK_TAIL = 18 /* fused conv2 (3x3) -> conv3 (1x1) + residual + ReLU [-> the next block's conv1] */
+  TDET_OP_BOTTLENECK_TAIL = 18, /* fused conv2 (3x3) -> conv3 (1x1) + residual + ReLU [-> the next block's conv1] */
+  TDET_OP_GN_STATS = 19,     /* GroupNorm statistics: per (image, group) sum and sum of squares */
+  TDET_OP_GN_APPLY = 20      /* GroupNorm normalise + affine (+ residual) (+ upsampled coarse level) (+ ReLU) */
 } tdet_op_kind;
 
 typedef enum tdet_dtype { TDET_BF16 = 0, TDET_F32 = 1, TDET_F16 = 2, TDET_U8 = 3 } tdet_dtype;
@@ -207,6 +209,15 @@ typedef struct tdet_tensor_meta {
  *                   TDET_FLAG_SCALED_OUT: y (F16) gets a device-chosen exponent; TDET_FLAG_SCALED_OUT2: y2 likewise.  The
  *                   exponents come from the chained bounds of bound_consts (conv2), bound_consts2 (conv3) and
  *                   bound_consts3 (next conv1); z2 is scaled like x (an F16 x with x_meta).
+ * TDET_OP_GN_STATS  nn.GroupNorm(groups, cin) (models/utils/layers.py:50-54,138-154: use_gn=True backbones, necks with
+ *                   normalize + use_gn), first pass.  x: raw conv output [n][h][w][cin] (x_dtype, x_meta exponent);
+ *                   dw: fp32 [n][groups][2] += {sum, sum of squares} of the true values (caller zeroes it).
+ *                   cin in {64, 128, ..., 2048} (a power of two), groups <= 64 dividing cin.
+ * TDET_OP_GN_APPLY  second pass: y = act( (x - mean) * rstd * scale[c] + shift[c] + residual + up2(coarse) ) with
+ *                   mean / rstd = 1/sqrt(var + eps) of x's (image, group) from dw (TDET_OP_GN_STATS output; biased
+ *                   variance); scale = gamma, shift = beta (fp32 [cin]); residual [n][h][w][cin] and coarse
+ *                   [n][h/2][w/2][cin] optional (16-bit, with metas); TDET_FLAG_RELU; y: 16-bit of y_dtype with
+ *                   exponent 0 (F16 saturates at +-65504); y_meta (optional) receives max |y|.
  * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;
  *                   its exponent field is left untouched)
  * TDET_OP_ZERO      y: buffer of x_stride[0] bytes, zero-filled
@@ -249,7 +260,7 @@ typedef struct tdet_op {
   const tdet_tensor_meta* x2_meta;
   int32_t cin2, stride2, h2, w2;
   int32_t x2_dtype;
-  int32_t reserved0;
+  float eps;                  /* TDET_OP_GN_APPLY: GroupNorm eps */
   /* ---- TDET_OP_BOTTLENECK_TAIL: conv3 and the next block's conv1 ---- */
   const void* wgt2;           /* conv3 weights [cout][cout2] of x_dtype */
   const float* scale2;

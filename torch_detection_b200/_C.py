@@ -27,6 +27,7 @@ OP_BN_AFFINE_GRAD = 13
 OP_SPLIT_COMBINE = 14
 OP_MAXPOOL_BWD, OP_STEM_WGRAD, OP_PARITY_MERGE = 15, 16, 17
 OP_BOTTLENECK_TAIL = 18
+OP_GN_STATS, OP_GN_APPLY = 19, 20
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1
@@ -61,7 +62,7 @@ class TdetOp(ctypes.Structure):
         ("dw", ctypes.c_void_p), ("gy_meta", ctypes.c_void_p),
         ("x2", ctypes.c_void_p), ("x2_meta", ctypes.c_void_p),
         ("cin2", ctypes.c_int32), ("stride2", ctypes.c_int32), ("h2", ctypes.c_int32), ("w2", ctypes.c_int32),
-        ("x2_dtype", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("x2_dtype", ctypes.c_int32), ("eps", ctypes.c_float),
         ("wgt2", ctypes.c_void_p), ("scale2", ctypes.c_void_p), ("shift2", ctypes.c_void_p),
         ("bound_consts2", ctypes.c_void_p),
         ("wgt3", ctypes.c_void_p), ("scale3", ctypes.c_void_p), ("shift3", ctypes.c_void_p),

@@ -754,6 +754,154 @@ add_mask_kernel(const AddMaskParams p) {
   }
 }
 
+// ---- GroupNorm (use_gn=True backbones, necks with normalize=GN; models/utils/layers.py:50-54,138-154) --------------
+// GroupNorm statistics depend on the data, so it cannot be folded into a GEMM epilogue: the conv writes its raw output
+// (16-bit, per-tensor exponent), gn_stats_kernel reduces sum / sum of squares of the TRUE values per (image, group) --
+// fp32 partial sums per thread, shared-memory bins per block, one atomicAdd per (block, group, moment) -- and
+// gn_apply_kernel writes act((x - mean) * rstd * gamma + beta [+ residual] [+ nearest-x2 upsampled coarse level]).
+// Both are HBM-bound passes with 16-byte accesses.  Groups are channel-contiguous in NHWC; a thread keeps ONE
+// 8-channel column of the tensor for its whole loop (the grid stride is a multiple of c / 8), so its eight channel
+// sums stay in registers.
+constexpr int kGnMaxGroups = 64;
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int hw, int c8, int groups, int x_fp16,
+                const TensorMeta* __restrict__ x_meta) {
+  // grid: (blocks per image, n); blockDim.x = 256, a multiple of c8 (c8 in {8, 16, ..., 256})
+  __shared__ float bins[2 * kGnMaxGroups];
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) bins[i] = 0.0f;
+  __syncthreads();
+  const int img = blockIdx.y;
+  const long long total = static_cast<long long>(hw) * c8;
+  const uint4* xi = x + static_cast<long long>(img) * total;
+  const float mul = ldexpf(1.0f, x_meta ? x_meta->e : 0);
+  const bool xf = x_fp16 != 0;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.0f;
+  const long long start = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;   // multiple of c8
+  for (long long i = start; i < total; i += stride) {
+    const uint4 v = __ldg(xi + i);
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi;
+      unpack16x2(w4[j], xf, lo, hi);
+      lo *= mul;
+      hi *= mul;
+      s1[2 * j] += lo;
+      s2[2 * j] = fmaf(lo, lo, s2[2 * j]);
+      s1[2 * j + 1] += hi;
+      s2[2 * j + 1] = fmaf(hi, hi, s2[2 * j + 1]);
+    }
+  }
+  const int cg = (c8 * 8) / groups;                     // channels per group
+  const int c0 = static_cast<int>(start % c8) * 8;      // this thread's first channel
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (c0 + e) / cg;
+    atomicAdd(&bins[2 * g], s1[e]);
+    atomicAdd(&bins[2 * g + 1], s2[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
+    atomicAdd(stats + static_cast<long long>(img) * 2 * groups + i, bins[i]);
+}
+
+struct GnApplyParams {
+  const uint4* x;          // raw conv output [n][h][w][c]
+  const uint4* res;        // nullable, same shape
+  const uint4* coarse;     // nullable, [n][h/2][w/2][c]: nearest-x2 upsample-add (FPN top-down path after the norm)
+  uint4* y;
+  const float* stats;      // [n][groups][2] sum, sum of squares of the true values
+  const float* gamma;
+  const float* beta;
+  int h, w, c8, groups;
+  float eps;
+  int relu;
+  int x_fp16, res_fp16, coarse_fp16, y_fp16;
+  const TensorMeta* x_meta;
+  const TensorMeta* res_meta;
+  const TensorMeta* coarse_meta;
+  TensorMeta* y_meta;      // nullable: receives max |y| (exponent 0)
+};
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const GnApplyParams p) {
+  __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+  const int img = blockIdx.y;
+  const int cg = (p.c8 * 8) / p.groups;
+  const float cnt = static_cast<float>(p.h) * p.w * cg;
+  for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+    const float s1 = p.stats[(static_cast<long long>(img) * p.groups + g) * 2];
+    const float s2 = p.stats[(static_cast<long long>(img) * p.groups + g) * 2 + 1];
+    const float mean = s1 / cnt;
+    const float var = fmaxf(s2 / cnt - mean * mean, 0.0f);   // biased variance, as nn.GroupNorm
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + p.eps);
+  }
+  __syncthreads();
+  const long long total = static_cast<long long>(p.h) * p.w * p.c8;
+  const long long base = static_cast<long long>(img) * total;
+  const float mx = ldexpf(1.0f, p.x_meta ? p.x_meta->e : 0);
+  const float mr = ldexpf(1.0f, (p.res && p.res_meta) ? p.res_meta->e : 0);
+  const float mc = ldexpf(1.0f, (p.coarse && p.coarse_meta) ? p.coarse_meta->e : 0);
+  const bool xf = p.x_fp16 != 0, rf = p.res_fp16 != 0, cf = p.coarse_fp16 != 0, yf = p.y_fp16 != 0;
+  const long long start = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;   // multiple of c8
+  const int c0 = static_cast<int>(start % p.c8) * 8;
+  float a[8], b[8];   // y = x * a + b for this thread's eight channels
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (c0 + e) / cg;
+    const float ga = __ldg(p.gamma + c0 + e) * s_rstd[g];
+    a[e] = ga * mx;
+    b[e] = __ldg(p.beta + c0 + e) - s_mean[g] * ga;
+  }
+  float amax = 0.0f;
+  const int hc = p.h >> 1, wc = p.w >> 1;
+  for (long long i = start; i < total; i += stride) {
+    const uint4 v = __ldg(p.x + base + i);
+    uint4 r = make_uint4(0u, 0u, 0u, 0u), cz = make_uint4(0u, 0u, 0u, 0u);
+    if (p.res) r = __ldg(p.res + base + i);
+    if (p.coarse) {
+      const long long pix = i / p.c8;
+      const int px = static_cast<int>(pix % p.w), py = static_cast<int>(pix / p.w);
+      cz = __ldg(p.coarse + ((static_cast<long long>(img) * hc + (py >> 1)) * wc + (px >> 1)) * p.c8 + (i % p.c8));
+    }
+    const uint32_t vw[4] = {v.x, v.y, v.z, v.w}, rw[4] = {r.x, r.y, r.z, r.w}, cw[4] = {cz.x, cz.y, cz.z, cz.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float lo, hi, rlo, rhi, clo, chi;
+      unpack16x2(vw[j], xf, lo, hi);
+      unpack16x2(rw[j], rf, rlo, rhi);
+      unpack16x2(cw[j], cf, clo, chi);
+      lo = fmaf(lo, a[2 * j], b[2 * j]);
+      hi = fmaf(hi, a[2 * j + 1], b[2 * j + 1]);
+      lo = fmaf(rlo, mr, fmaf(clo, mc, lo));
+      hi = fmaf(rhi, mr, fmaf(chi, mc, hi));
+      if (p.relu) {
+        lo = fmaxf(lo, 0.0f);
+        hi = fmaxf(hi, 0.0f);
+      }
+      if (yf) {   // plain fp16 (exponent 0): saturate instead of overflowing to infinity
+        lo = fminf(fmaxf(lo, -65504.0f), 65504.0f);
+        hi = fminf(fmaxf(hi, -65504.0f), 65504.0f);
+      }
+      amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
+      ow[j] = pack16x2(lo, hi, yf);
+    }
+    p.y[base + i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  if (p.y_meta) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&p.y_meta->amax_bits, __float_as_uint(amax));
+  }
+}
+
 // Stride-2 3x3 dgrad as four parity classes (TDET_OP_PARITY_MERGE): dx[2i+a][2j+b] only receives the filter taps of
 // matching parity, so the input gradient is four small stride-1 convs over the COARSE gradient g --
 //   (0,0): 1x1, tap (1,1)      (0,1): 1x2, taps (1,0),(1,2)      (1,0): 2x1, taps (0,1),(2,1)      (1,1): 2x2, the corners

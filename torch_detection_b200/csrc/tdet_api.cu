@@ -1380,6 +1380,23 @@ int build_launch(Launch& l, const DeviceInfo& di) {
       if (o.cin % 8 || !o.x || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "split_combine: bad arguments");
       l.bytes = 8.0 * o.n * o.cin * static_cast<double>(o.h) * o.w;
       return TDET_OK;
+    case TDET_OP_GN_STATS:
+    case TDET_OP_GN_APPLY: {
+      const int c8 = o.cin / 8;
+      if (o.cin <= 0 || o.cin % 8 || c8 > 256 || 256 % c8 || o.groups < 1 || o.groups > kGnMaxGroups || o.cin % o.groups ||
+          !o.x || !o.dw || !is16(o.x_dtype))
+        return fail(TDET_ERR_UNSUPPORTED_SHAPE,
+                    "groupnorm: cin must be a power of two in 64..2048 and groups <= %d divide it (cin %d, groups %d)",
+                    kGnMaxGroups, o.cin, o.groups);
+      if (o.kind == TDET_OP_GN_APPLY) {
+        if (!o.y || !o.scale || !o.shift || !is16(o.y_dtype) || (o.residual && !is16(o.residual_dtype)) ||
+            (o.coarse && (!is16(o.coarse_dtype) || o.h != 2 * o.hc || o.w != 2 * o.wc)) || !(o.eps > 0.0f))
+          return fail(TDET_ERR_INVALID_ARGUMENT, "gn_apply: bad arguments");
+      }
+      l.bytes = 2.0 * o.n * o.cin * static_cast<double>(o.h) * o.w *
+                (o.kind == TDET_OP_GN_STATS ? 1 : 2 + (o.residual ? 1 : 0) + (o.coarse ? 0.25 : 0));
+      return TDET_OK;
+    }
     case TDET_OP_BN_AFFINE_GRAD:
       if (o.cin <= 0 || o.cin % 64 || !o.x || !o.gy || !o.dw || !o.scale || !o.shift || !is16(o.x_dtype) ||
           !is16(o.gy_dtype) || (o.residual && !is16(o.residual_dtype)))
@@ -1592,6 +1609,44 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }
+    case TDET_OP_GN_STATS:
+    case TDET_OP_GN_APPLY: {
+      // grid (blocks per image, n): a block's 256 threads and the grid stride are multiples of c / 8
+      const int c8 = o.cin / 8;
+      const long long items = static_cast<long long>(o.h) * o.w * c8;
+      long long bx = (items + 255) / 256;
+      const long long cap = (static_cast<long long>(di.num_sms) * 16 + o.n - 1) / o.n;
+      if (bx > cap) bx = cap;
+      if (bx < 1) bx = 1;
+      const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(o.n), 1);
+      if (o.kind == TDET_OP_GN_STATS) {
+        gn_stats_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(o.x), o.dw, o.h * o.w, c8, o.groups,
+                                              o.x_dtype == TDET_F16 ? 1 : 0, reinterpret_cast<const TensorMeta*>(o.x_meta));
+      } else {
+        GnApplyParams gp{};
+        gp.x = static_cast<const uint4*>(o.x);
+        gp.res = static_cast<const uint4*>(o.residual);
+        gp.coarse = static_cast<const uint4*>(o.coarse);
+        gp.y = static_cast<uint4*>(o.y);
+        gp.stats = o.dw;
+        gp.gamma = o.scale;
+        gp.beta = o.shift;
+        gp.h = o.h; gp.w = o.w; gp.c8 = c8; gp.groups = o.groups;
+        gp.eps = o.eps;
+        gp.relu = (o.flags & TDET_FLAG_RELU) ? 1 : 0;
+        gp.x_fp16 = o.x_dtype == TDET_F16;
+        gp.res_fp16 = o.residual_dtype == TDET_F16;
+        gp.coarse_fp16 = o.coarse_dtype == TDET_F16;
+        gp.y_fp16 = o.y_dtype == TDET_F16;
+        gp.x_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
+        gp.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+        gp.coarse_meta = reinterpret_cast<const TensorMeta*>(o.coarse_meta);
+        gp.y_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+        gn_apply_kernel<<<grid, 256, 0, st>>>(gp);
+      }
+      TDET_CUDA(cudaGetLastError());
+      return TDET_OK;
+    }
     case TDET_OP_AMAX: {
       const long long total = static_cast<long long>(o.n) * o.h * o.w * (o.cin / 8);
       amax_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(
@@ -1625,7 +1680,7 @@ struct NvtxRange {
 const char* kind_name(int kind) {
   static const char* names[] = {"prep", "stem", "maxpool", "conv", "subsample", "wgrad", "dw_unpack", "colsum", "sumpool2",
                                 "dilate2", "add_mask", "zero", "amax", "bn_affine_grad", "split_combine", "maxpool_bwd",
-                                "stem_wgrad", "parity_merge", "bottleneck_tail"};
+                                "stem_wgrad", "parity_merge", "bottleneck_tail", "gn_stats", "gn_apply"};
   return (kind >= 0 && kind < static_cast<int>(sizeof(names) / sizeof(names[0]))) ? names[kind] : "op";
 }
 int run_launch_traced(const Launch& l, const DeviceInfo& di, cudaStream_t st, int index) {

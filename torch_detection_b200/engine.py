@@ -636,6 +636,42 @@ def op_stem_wgrad(n, h, w, staged, g, dw, scale=None):
     return op
 
 
+def op_gn_stats(x, stats, groups):
+    """stats (fp32 [n][groups][2], zeroed by the caller) += per (image, group) sum / sum of squares of x's true values."""
+    n, h, w, c = x.shape
+    assert stats.dtype == torch.float32 and stats.numel() == n * groups * 2
+    op = _C.TdetOp()
+    op.kind = _C.OP_GN_STATS
+    op.n, op.h, op.w, op.cin, op.groups = n, h, w, c, groups
+    op.x, op.x_dtype, op.x_meta = x.ptr, _TD[x.dtype], x.meta
+    op.dw = stats.data_ptr()
+    return op
+
+
+def op_gn_apply(x, stats, groups, gamma, beta, eps, y, residual=None, coarse=None, relu=False):
+    """y = act(GroupNorm(x) + residual + up2(coarse)) from the statistics of op_gn_stats; y has exponent 0 and its
+    meta (if any) receives max |y|."""
+    n, h, w, c = x.shape
+    assert y.shape == x.shape
+    op = _C.TdetOp()
+    op.kind = _C.OP_GN_APPLY
+    op.flags = _C.FLAG_RELU if relu else 0
+    op.n, op.h, op.w, op.cin, op.groups = n, h, w, c, groups
+    op.ho, op.wo, op.cout = h, w, c
+    op.x, op.x_dtype, op.x_meta = x.ptr, _TD[x.dtype], x.meta
+    op.y, op.y_dtype, op.y_meta = y.ptr, _TD[y.dtype], y.meta
+    op.dw = stats.data_ptr()
+    op.scale, op.shift = gamma.data_ptr(), beta.data_ptr()
+    op.eps = eps
+    if residual is not None:
+        assert residual.shape == x.shape
+        op.residual, op.residual_dtype, op.residual_meta = residual.ptr, _TD[residual.dtype], residual.meta
+    if coarse is not None:
+        op.coarse, op.coarse_dtype, op.coarse_meta = coarse.ptr, _TD[coarse.dtype], coarse.meta
+        op.hc, op.wc = coarse.shape[1], coarse.shape[2]
+    return op
+
+
 def op_amax(x, meta):
     """meta.amax = max |x| (true values); `meta` = device address of a tdet_tensor_meta."""
     n, h, w, c = x.shape

@@ -107,10 +107,12 @@ class BucketAllReduce(object):
             return out
         main = torch.cuda.current_stream(bucket.device)
         comm = self._comm_stream(bucket.device)
-        # The copy is allocated from the MAIN stream's pool (and the side stream recorded on it below).  Allocated on
-        # the side stream with record_stream(main), a freed copy only became reusable once the main stream had caught
-        # up with the host -- which runs a step ahead -- so the caching allocator fell back to cudaMalloc (a device
-        # synchronisation) in some runs on every step: 9.4 ms steps measured 15-33 ms at random.
+        # The copy comes from the MAIN stream's pool and is NOT record_stream()ed on the side stream: the object keeps
+        # a reference until finish() has made the main stream wait for the collective, so it cannot be freed (and
+        # handed to another main-stream allocation) while the side stream still works on it.  With record_stream a
+        # freed copy only became reusable once an event had completed, the pool kept growing by a segment every few
+        # steps, and each of those cudaMallocs can stall the host for 40-100 ms (measured: one 9.3 ms step in ten
+        # taking 50-100 ms at random).
         out = torch.empty_like(bucket)
         comm.wait_stream(main)
         with torch.cuda.stream(comm):
@@ -131,20 +133,19 @@ class BucketAllReduce(object):
                 if t1 is not None:
                     t1.record(comm)
                     self._timing.append((t0, t1))
-        out.record_stream(comm)
         self._copied[bucket.data_ptr()] = ev
         if any(p.grad is not None for p in params):
             # autograd will accumulate into existing gradients on the compute stream: order it after the collective
             main.wait_stream(comm)
             self.buckets_not_overlapped += 1
         else:
-            self._pending.append((bucket.device, comm))
+            self._pending.append((bucket.device, comm, out))
         return out
 
     def finish(self):
-        for device, comm in self._pending:
+        for device, comm, _out in self._pending:
             torch.cuda.current_stream(device).wait_stream(comm)
-        self._pending = []
+        self._pending = []   # (drops the references that kept the copies alive while the side stream used them)
 
     def module_done(self):
         if not self.defer:
