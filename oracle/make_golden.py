@@ -68,6 +68,43 @@ def make_gradient_golden(out_dir):
     print("r18_fpn_64x64_grads", len(arrays), "parameter gradients")
 
 
+def make_groupnorm_golden(out_dir):
+    """tests/golden/r50_gn_fpn_64x96.npz: use_gn=True backbone and neck (nn.GroupNorm(32, C) after every conv,
+    models/utils/layers.py:50-54), built through the reference's registry, GroupNorm affines randomised."""
+    depth, seed = 50, 2
+    ref_backbone, ref_necks, obj_from_dict = reference_shim.load()
+    torch.manual_seed(seed)
+    bb = obj_from_dict(dict(type="ResNet", depth=depth, use_gn=True), parent=ref_backbone)
+    bb.init_weights()
+    bb.eval()
+    neck = obj_from_dict(dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5,
+                              normalize=dict(type="GN"), use_gn=True), parent=ref_necks)
+    neck.init_weights()
+    neck.eval()
+    g = torch.Generator().manual_seed(1000 + seed)
+    for mod in (bb, neck):
+        sd = mod.state_dict()
+        orc.randomize_gn_affine(sd, generator=g)
+        mod.load_state_dict(sd)
+    # The input is bf16-representable: a chain of GroupNorms over 2x3 .. 16x24 maps amplifies the 2^-9 rounding of a
+    # bf16 image hand-off to 3.5e-3 .. 6.4e-3 at the outputs even in exact arithmetic (measured with the oracle), which
+    # would leave no budget for the path under test inside the 1e-2 gate.
+    x = torch.randn(2, 3, 64, 96, generator=torch.Generator().manual_seed(77 + seed)).to(torch.bfloat16).float()
+    with torch.no_grad():
+        feats = bb(x)
+        outs = neck(feats)
+    arrays = {"x": x.numpy()}
+    for i, t in enumerate(feats):
+        arrays["C%d" % (i + 2)] = t.numpy()
+    for i, t in enumerate(outs):
+        arrays["P%d" % (i + 2)] = t.numpy()
+    meta = dict(depth=depth, seed=seed, input_seed=77 + seed, bb_hash=state_hash(bb.state_dict()),
+                neck_hash=state_hash(neck.state_dict()))
+    np.savez(os.path.join(out_dir, "r50_gn_fpn_64x96.npz"), **arrays,
+             **{"meta_" + k: np.array(v) for k, v in meta.items()})
+    print("r50_gn_fpn_64x96", {k: v.shape for k, v in arrays.items()})
+
+
 def main():
     assert reference_shim.available(), "needs /root/reference"
     torch.set_num_threads(1)  # fixed reduction order
@@ -96,6 +133,7 @@ def main():
                  **arrays, **{"meta_" + k: np.array(v) for k, v in meta.items()})
         print(name, {k: v.shape for k, v in arrays.items()})
     make_gradient_golden(out_dir)
+    make_groupnorm_golden(out_dir)
 
 
 if __name__ == "__main__":

@@ -155,11 +155,30 @@ def randomize_bn_stats(sd, generator=None):
     return sd
 
 
+def randomize_gn_affine(sd, generator=None):
+    """Non-trivial gamma / beta for every GroupNorm of a use_gn=True state (init makes them 1 / 0): keys ``*.weight``
+    of rank 1 whose module has no running statistics."""
+    for k in list(sd.keys()):
+        if k.endswith(".weight") and sd[k].dim() == 1 and (k[:-len(".weight")] + ".running_var") not in sd:
+            p = k[:-len(".weight")]
+            ch = sd[k].numel()
+            sd[p + ".weight"] = 0.5 + torch.rand(ch, generator=generator)
+            sd[p + ".bias"] = 0.2 * torch.randn(ch, generator=generator)
+    return sd
+
+
 # ----------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------
 
+GN_GROUPS = 32  # get_group_gn (models/utils/layers.py:138-154): num_groups = 32 whatever the width
+GN_EPS = 1e-5   # nn.GroupNorm default
+
+
 def _bn(sd, p, x):
+    if (p + ".running_mean") not in sd:
+        # use_gn=True: norm_layer -> nn.GroupNorm(get_group_gn(planes), planes) (layers.py:50-54); no running statistics
+        return F.group_norm(x, GN_GROUPS, sd[p + ".weight"], sd[p + ".bias"], GN_EPS)
     # eval-mode BatchNorm2d == F.batch_norm(training=False): aten::native_batch_norm, as nn.BatchNorm2d
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"],
                         sd[p + ".bias"], False, 0.1, BN_EPS)
@@ -167,20 +186,21 @@ def _bn(sd, p, x):
 
 def _block(sd, p, x, kind, stride, dilation):
     has_ds = (p + ".downsample.0.weight") in sd
+    nm = ".gn" if (p + ".gn1.weight") in sd else ".bn"  # norm_names with use_gn=True (resnet.py:31,85-86)
     if kind == "bottleneck":  # resnet.py:97-119 ; stride on the 3x3 (:75)
         out = F.conv2d(x, sd[p + ".conv1.weight"])
-        out = F.relu_(_bn(sd, p + ".bn1", out))
+        out = F.relu_(_bn(sd, p + nm + "1", out))
         # groups > 1 for ResNeXt (models/backbone/resnext.py:84-87): inferred from the parameter's shape
         w2 = sd[p + ".conv2.weight"]
         out = F.conv2d(out, w2, None, stride, dilation, dilation, out.shape[1] // w2.shape[1])
-        out = F.relu_(_bn(sd, p + ".bn2", out))
+        out = F.relu_(_bn(sd, p + nm + "2", out))
         out = F.conv2d(out, sd[p + ".conv3.weight"])
-        out = _bn(sd, p + ".bn3", out)
+        out = _bn(sd, p + nm + "3", out)
     else:  # resnet.py:42-59 ; second 3x3 has dilation 1 / pad 1 (:23-24)
         out = F.conv2d(x, sd[p + ".conv1.weight"], None, stride, dilation, dilation)
-        out = F.relu_(_bn(sd, p + ".bn1", out))
+        out = F.relu_(_bn(sd, p + nm + "1", out))
         out = F.conv2d(out, sd[p + ".conv2.weight"], None, 1, 1, 1)
-        out = _bn(sd, p + ".bn2", out)
+        out = _bn(sd, p + nm + "2", out)
     residual = x
     if has_ds:  # resnet.py:129-136
         residual = F.conv2d(x, sd[p + ".downsample.0.weight"], None, stride)
@@ -194,7 +214,7 @@ def resnet_forward(sd, x, depth, num_stages=4, strides=(1, 2, 2, 2), dilations=(
     """ResNet.forward in eval/frozen-BN mode (models/backbone/resnet.py:253-268)."""
     kind, counts = ARCH[depth]
     x = F.conv2d(x, sd["conv1.weight"], None, 2, 3)
-    x = F.relu_(_bn(sd, "bn1", x))
+    x = F.relu_(_bn(sd, "gn1" if "gn1.weight" in sd else "bn1", x))  # norm_name (resnet.py:215)
     x = F.max_pool2d(x, 3, 2, 1)
     outs = []
     for li, nblocks in enumerate(counts[:num_stages]):
@@ -208,7 +228,7 @@ def resnet_forward(sd, x, depth, num_stages=4, strides=(1, 2, 2, 2), dilations=(
 
 def _cm(sd, prefix, x, stride=1, pad=0):
     """ConvModule.forward with activate_last=True and no activation (layers.py:120-127): conv (+bias), then the
-    norm layer if the module has one (eval-mode BatchNorm2d)."""
+    norm layer if the module has one (eval-mode BatchNorm2d, or GroupNorm with use_gn=True)."""
     y = F.conv2d(x, sd[prefix + ".conv.weight"], sd.get(prefix + ".conv.bias"), stride, pad)
     if (prefix + ".norm.weight") in sd:
         y = _bn(sd, prefix + ".norm", y)

@@ -47,6 +47,27 @@ def build_product_pair(depth, seed=0, out_channels=256, num_outs=5, bnstats=Fals
     return bb, neck
 
 
+def build_product_gn_pair(depth=50, seed=2, out_channels=256, num_outs=5):
+    """use_gn=True backbone + neck with the seeding protocol of oracle/make_golden.py:make_groupnorm_golden."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    from oracle import resnet_fpn_oracle as orc
+    torch.manual_seed(seed)
+    bb = obj_from_dict(dict(type="ResNet", depth=depth, use_gn=True), parent=models.backbone)
+    bb.init_weights()
+    bb.eval()
+    neck = obj_from_dict(dict(type="FPN", in_channels=in_channels_for(depth), out_channels=out_channels,
+                              num_outs=num_outs, normalize=dict(type="GN"), use_gn=True), parent=models.necks)
+    neck.init_weights()
+    neck.eval()
+    g = torch.Generator().manual_seed(1000 + seed)
+    for mod in (bb, neck):
+        sd = mod.state_dict()
+        orc.randomize_gn_affine(sd, generator=g)
+        mod.load_state_dict(sd)
+    return bb, neck
+
+
 def cpu_state(module):
     return OrderedDict((k, v.detach().cpu().clone()) for k, v in module.state_dict().items())
 

@@ -556,3 +556,55 @@ def test_cuda_graph_replay_equals_eager(cuda_device):
     bb.train()
     with pytest.raises(NotImplementedError):
         GraphedFeatureExtractor(bb, neck, xs[0])
+
+
+def test_groupnorm_backbone_and_neck(cuda_device):
+    """use_gn=True (nn.GroupNorm(32, C), models/utils/layers.py:50-54; resnet.py:193-232,
+    fpn.py:43-61) -- the golden fixture produced by the unmodified reference, then a larger seeded case against the
+    oracle with an odd batch, and the refusal to train through GroupNorm."""
+    meta, arrays = helpers.load_golden("r50_gn_fpn_64x96")
+    bb, neck = helpers.build_product_gn_pair(meta["depth"], seed=meta["seed"])
+    assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
+    feats, outs = _run_product(bb, neck, arrays["x"].to(torch.bfloat16), cuda_device)
+    e1 = _check_levels(feats, [arrays["C%d" % i] for i in range(2, 6)], ["C2", "C3", "C4", "C5"])
+    e2 = _check_levels(outs, [arrays["P%d" % i] for i in range(2, 7)], ["P2", "P3", "P4", "P5", "P6"])
+    print("groupnorm golden", e1, e2)
+    x = torch.randn(3, 3, 128, 192, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
+    want_f = orc.resnet_forward(helpers.cpu_state(bb), x.float(), 50)
+    want_p = orc.fpn_forward(helpers.cpu_state(neck), want_f, [256, 512, 1024, 2048], 256, 5)
+    feats, outs = _run_product(bb, neck, x, cuda_device)
+    e1 = _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
+    e2 = _check_levels(outs, want_p, ["P2", "P3", "P4", "P5", "P6"])
+    print("groupnorm 128x192", e1, e2)
+    # fp32 in -> fp32 out of the same values (no split-precision GroupNorm path)
+    feats32 = bb(x.float().to(cuda_device))
+    assert all(t.dtype == torch.float32 for t in feats32)
+    # (equal up to the summation order of the statistics' fp32 atomics, which differs from run to run)
+    assert all(orc.rel_l2(a, b.float()) < 2e-3 for a, b in zip(feats32, feats))
+    bb.train()
+    with pytest.raises(NotImplementedError):
+        bb(x.to(cuda_device))
+
+
+def test_groupnorm_basic_block_and_retinanet_neck(cuda_device):
+    """use_gn=True with BasicBlock (gn1 / gn2, resnet.py:29-31) and an add_extra_convs neck from level 1."""
+    from torch_detection_b200.models.backbone import ResNet
+    from torch_detection_b200.models.necks import FPN
+    torch.manual_seed(5)
+    bb = ResNet(18, use_gn=True)
+    bb.init_weights()
+    neck = FPN([64, 128, 256, 512], 256, 5, start_level=1, add_extra_convs=True, normalize=dict(type="GN"), use_gn=True)
+    neck.init_weights()
+    g = torch.Generator().manual_seed(6)
+    for mod in (bb, neck):
+        sd = mod.state_dict()
+        orc.randomize_gn_affine(sd, generator=g)
+        mod.load_state_dict(sd)
+    x = torch.randn(2, 3, 128, 128, generator=g).to(torch.bfloat16)
+    want_f = orc.resnet_forward(helpers.cpu_state(bb), x.float(), 18)
+    want_p = orc.fpn_forward(helpers.cpu_state(neck), want_f, [64, 128, 256, 512], 256, 5, start_level=1,
+                             add_extra_convs=True)
+    feats, outs = _run_product(bb, neck, x, cuda_device)
+    _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
+    e = _check_levels(outs, want_p, ["P3", "P4", "P5", "P6", "P7"])
+    print("groupnorm r18 + extra convs", e)

@@ -68,10 +68,11 @@ def test_constructor_errors():
         FPN([256, 512, 1024], 256, 2)
     with pytest.raises(AssertionError):
         FPN([256, 512, 1024], 256, 5, end_level=2)
-    with pytest.raises(NotImplementedError):
-        ResNet(50, use_gn=True)
-    with pytest.raises(NotImplementedError):
-        FPN([256, 512], 256, 2, normalize=dict(type="GN"), use_gn=True)   # GroupNorm cannot be folded
+    gn = ResNet(50, use_gn=True)          # resnet.py:215, :85-86: norm modules are named gn*
+    assert isinstance(gn.gn1, torch.nn.GroupNorm) and gn.gn1.num_groups == 32 and not hasattr(gn, "bn_eval")
+    assert isinstance(gn.layer1[0].gn3, torch.nn.GroupNorm) and isinstance(gn.layer1[0].downsample[1], torch.nn.GroupNorm)
+    assert isinstance(FPN([256, 512], 256, 2, normalize=dict(type="GN"), use_gn=True).fpn_convs[1].norm,
+                      torch.nn.GroupNorm)
     assert FPN([256, 512], 256, 2, normalize=dict(type="BN")).lateral_convs[0].with_norm
     with pytest.raises(TypeError):
         ResNet(18).init_weights(pretrained=3)

@@ -595,3 +595,74 @@ def test_unsupported_shapes_fail_loudly(cuda_device):
     x64 = engine.nhwc_empty(1, 8, 8, 64, dev)
     with pytest.raises(ValueError):  # mixed bf16 x fp16 operands are illegal on tcgen05
         engine.op_conv(engine.act_of(x64), wgt16, engine.act_of(y), 1, 1, 1, 0)
+
+
+GN_CASES = [
+    # n, h, w, c, groups, x dtype, exponent, y dtype, residual, coarse, relu
+    (2, 12, 20, 64, 32, torch.float16, -3, torch.float16, False, False, True),
+    (3, 9, 14, 256, 32, torch.float16, 2, torch.bfloat16, True, False, True),
+    (2, 10, 16, 256, 32, torch.bfloat16, 0, torch.bfloat16, False, True, False),
+    (1, 7, 5, 2048, 32, torch.float16, -1, torch.float16, True, False, True),
+    (2, 50, 84, 128, 32, torch.float16, 0, torch.bfloat16, False, False, False),   # more than one block per image
+    (2, 6, 6, 512, 64, torch.bfloat16, 0, torch.float16, True, True, True),
+]
+
+
+@pytest.mark.parametrize("case", GN_CASES)
+def test_group_norm_stats_and_apply(cuda_device, case):
+    """TDET_OP_GN_STATS + TDET_OP_GN_APPLY against F.group_norm (fp32, CPU) on the same stored 16-bit values:
+    nn.GroupNorm(32, C) of the reference's use_gn=True modules (models/utils/layers.py:50-54), with the
+    residual add / nearest-upsampled coarse add / ReLU that follow it in the backbone block (resnet.py:111-117)
+    and the FPN top-down path (fpn.py:98-101)."""
+    from torch_detection_b200 import engine
+    n, h, w, c, groups, xdt, e, ydt, with_res, with_coarse, relu = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    # per-channel offsets and scales so that group means / variances are far from 0 / 1
+    x = torch.randn(n, c, h, w, generator=g) * (0.5 + torch.rand(1, c, 1, 1, generator=g)) + torch.randn(1, c, 1, 1, generator=g)
+    xs = _nhwc(x.to(dev), xdt)
+    marena = engine.MetaArena(4, dev)
+    xm, rm, ym = marena.new(), marena.new(), marena.new()
+    marena.tensor[0, 0] = e
+    marena.tensor[1, 0] = 1
+    x_true = xs.float().cpu() * 2.0 ** e
+    gamma = (0.5 + torch.rand(c, generator=g)).to(dev)
+    beta = (0.3 * torch.randn(c, generator=g)).to(dev)
+    res = _nhwc(torch.randn(n, c, h, w, generator=g).to(dev), torch.float16) if with_res else None
+    coarse = None
+    if with_coarse:
+        assert h % 2 == 0 and w % 2 == 0
+        coarse = _nhwc(torch.randn(n, c, h // 2, w // 2, generator=g).to(dev), torch.bfloat16)
+    y = engine.nhwc_empty(n, h, w, c, dev, ydt)
+    stats = torch.zeros(n * groups * 2, dtype=torch.float32, device=dev)
+    xa = engine.act_of(xs, xm)
+    engine.run_op(engine.op_gn_stats(xa, stats, groups), dev)
+    engine.run_op(engine.op_gn_apply(xa, stats, groups, gamma, beta, 1e-5, engine.act_of(y, ym),
+                                     residual=engine.act_of(res, rm) if with_res else None,
+                                     coarse=engine.act_of(coarse) if with_coarse else None, relu=relu), dev)
+    torch.cuda.synchronize()
+    st = stats.view(n, groups, 2).cpu().double()
+    xg = x_true.double().reshape(n, groups, -1)
+    assert torch.allclose(st[..., 0], xg.sum(-1), rtol=1e-4, atol=1e-2 * 2.0 ** e)
+    assert torch.allclose(st[..., 1], (xg * xg).sum(-1), rtol=1e-4)
+    ref = F.group_norm(x_true, groups, gamma.cpu(), beta.cpu(), 1e-5)
+    if with_res:
+        ref = ref + res.float().cpu() * 2.0
+    if with_coarse:
+        ref = ref + F.interpolate(coarse.float().cpu(), scale_factor=2, mode="nearest")
+    if relu:
+        ref = F.relu(ref)
+    assert rel_l2(y.float().cpu(), ref) <= TOL[ydt]
+    amax = marena.read()[2]
+    # (the recorded maximum is taken before the output rounding: an upper bound within one ulp of the stored one)
+    ymax = float(y.float().abs().max())
+    assert amax[0] == 0 and ymax * (1 - 2.0 ** -8) <= amax[1] <= ymax * (1 + 2.0 ** -8)
+
+
+def test_group_norm_rejects_unsupported_widths(cuda_device):
+    from torch_detection_b200 import engine, _C
+    dev = cuda_device
+    x = engine.nhwc_empty(1, 4, 4, 192, dev)
+    stats = torch.zeros(64, dtype=torch.float32, device=dev)
+    with pytest.raises(_C.TdetError):
+        engine.run_op(engine.op_gn_stats(engine.act_of(x), stats, 32), dev)

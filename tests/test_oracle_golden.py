@@ -68,3 +68,22 @@ def test_gradient_oracle_reproduces_reference_gradient_fixture():
         got = (gb if k.startswith("bb.") else gn)[k.split(".", 1)[1]]
         sig = make_golden.grad_signature(got)
         assert np.allclose(sig, z[k], rtol=2e-4, atol=1e-6 * abs(z[k][0])), (k, sig[:3], z[k][:3])
+
+
+def test_oracle_groupnorm_matches_golden():
+    """use_gn=True fixture produced by the unmodified reference (oracle/make_golden.py:make_groupnorm_golden): the
+    product's host-side mirror rebuilds the same state (gn* keys) and the oracle's GroupNorm restatement reproduces
+    every level bit for bit."""
+    torch.set_num_threads(1)
+    meta, arrays = helpers.load_golden("r50_gn_fpn_64x96")
+    bb, neck = helpers.build_product_gn_pair(meta["depth"], seed=meta["seed"])
+    assert "gn1.weight" in bb.state_dict() and "layer1.0.gn3.bias" in bb.state_dict()
+    assert "lateral_convs.0.norm.weight" in neck.state_dict() and "lateral_convs.0.conv.bias" not in neck.state_dict()
+    assert helpers.state_hash(bb.state_dict()) == meta["bb_hash"]
+    assert helpers.state_hash(neck.state_dict()) == meta["neck_hash"]
+    feats = orc.resnet_forward(helpers.cpu_state(bb), arrays["x"], 50)
+    outs = orc.fpn_forward(helpers.cpu_state(neck), feats, [256, 512, 1024, 2048], 256, 5)
+    for i, t in enumerate(feats):
+        assert torch.equal(t, arrays["C%d" % (i + 2)]), "C%d" % (i + 2)
+    for i, t in enumerate(outs):
+        assert torch.equal(t, arrays["P%d" % (i + 2)]), "P%d" % (i + 2)

@@ -196,3 +196,33 @@ def test_resnext_oracle_and_mirror_match_reference():
         want = ref(x)
         got = orc.resnet_forward(a, x, 50)
     assert all(torch.equal(u, v) for u, v in zip(want, got))
+
+
+@pytest.mark.parametrize("depth", [18, 50])
+def test_oracle_groupnorm_matches_reference(depth):
+    """use_gn=True (models/utils/layers.py:50-54): GroupNorm(32, C) backbone and neck, eval mode, against the oracle's
+    restatement; the affine parameters are randomised (init makes them identity)."""
+    ref_backbone, ref_necks, obj_from_dict = reference_shim.load()
+    torch.manual_seed(1)
+    bb = obj_from_dict(dict(type="ResNet", depth=depth, use_gn=True), parent=ref_backbone)
+    bb.init_weights()
+    bb.eval()
+    chans = [64, 128, 256, 512] if depth < 50 else [256, 512, 1024, 2048]
+    neck = obj_from_dict(dict(type="FPN", in_channels=chans, out_channels=256, num_outs=5, normalize=dict(type="GN"),
+                              use_gn=True), parent=ref_necks)
+    neck.init_weights()
+    neck.eval()
+    g = torch.Generator().manual_seed(2)
+    for m in list(bb.modules()) + list(neck.modules()):
+        if isinstance(m, torch.nn.GroupNorm):
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+            m.bias.data = 0.2 * torch.randn(m.bias.shape, generator=g)
+    assert "gn1.weight" in bb.state_dict() and "layer1.0.gn2.bias" in bb.state_dict()
+    x = torch.randn(2, 3, 64, 96)
+    with torch.no_grad():
+        feats = bb(x)
+        outs = neck(feats)
+        f = orc.resnet_forward(bb.state_dict(), x, depth)
+        p = orc.fpn_forward(neck.state_dict(), f, chans, 256, 5)
+    for a, b in zip(tuple(feats) + tuple(outs), tuple(f) + tuple(p)):
+        assert torch.equal(a, b)

@@ -12,8 +12,9 @@ Outputs are dense NHWC bf16 buffers exposed as logical-NCHW ``channels_last`` te
 get fp32 views-by-copy of the same values).  Deliberate deviations from the reference, all listed in
 SURVEY.md Appendix G: ``train()`` returns ``self`` (reference returns None, F4) and implements the
 *intended* stage freezing (the reference raises AttributeError at resnet.py:288, F3).
-Unsupported on this path -> ``NotImplementedError``: ``use_gn=True``, batch-statistics BatchNorm
-(a BN child in training mode), CPU tensors.  There is no fallback.
+``use_gn=True`` (GroupNorm) runs inference through ``_build_plan_gn`` (raw conv -> statistics -> apply).
+Unsupported on this path -> ``NotImplementedError``: batch-statistics BatchNorm (a BN child in training
+mode), training through GroupNorm, CPU tensors.  There is no fallback.
 """
 import logging
 import os
@@ -49,7 +50,8 @@ class _ResidualUnit(nn.Module):
                                            groups=self.groups if idx == self.grouped_conv else 1))
         for idx, conv in enumerate(convs):
             self.add_module("conv%d" % (idx + 1), conv)
-        self.norm_names = ["bn%d" % (i + 1) for i in range(len(convs))]
+        # resnet.py:31,85-86
+        self.norm_names = [("gn%d" if use_gn else "bn%d") % (i + 1) for i in range(len(convs))]
         for name, (_, cout) in zip(self.norm_names, widths):
             self.add_module(name, norm_layer(cout, use_gn))
         self.relu = nn.ReLU(inplace=True)
@@ -138,7 +140,7 @@ class ResNet(nn.Module):
 
         self.inplanes = 64
         self.conv1 = conv7x7_group(3, 64, stride=2)
-        self.norm_name = "bn1"
+        self.norm_name = "gn1" if use_gn else "bn1"  # resnet.py:215
         self.add_module(self.norm_name, norm_layer(64, use_gn))
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
@@ -547,8 +549,142 @@ class ResNet(nn.Module):
             return plan, [tuple(o.shape) for o in outs], records, cints, geo
         return plan, [tuple(o.shape) for o in outs]
 
+    def _build_plan_gn(self, x, cache):
+        """use_gn=True (nn.GroupNorm(32, C) after every conv, layers.py:50-54): GroupNorm needs the statistics of the
+        whole conv output, so nothing folds into a GEMM epilogue.  Every conv launches RAW (no affine, no ReLU; fp16
+        significands with a device-chosen exponent), TDET_OP_GN_STATS reduces sum / sum of squares per (image,
+        group) and TDET_OP_GN_APPLY normalises, applies gamma / beta, adds the residual and applies the ReLU in one
+        pass.  Whole batch per launch, no fusions; inference only."""
+        n, _, h_in, w_in = x.shape
+        dev = x.device
+        tf = getattr(self, "_input_tf", None)
+        h, w = h_in, w_in
+        tf_scale = tf_shift = None
+        if tf is not None:
+            means, stds, div = tf
+            if div:
+                h, w = (h_in + div - 1) // div * div, (w_in + div - 1) // div * div
+            tf_scale, tf_shift = cache.get(("input_tf", tf), lambda out: (
+                torch.tensor([1.0 / s for s in stds], dtype=torch.float32, device=dev),
+                torch.tensor([-m / s for m, s in zip(means, stds)], dtype=torch.float32, device=dev)))
+        internal = INTERNAL_DTYPE
+        scaled = internal == torch.float16
+        ops = []
+        pool = _BufferPool(dev)
+        norms = [m for m in self.modules() if isinstance(m, nn.GroupNorm)]
+        meta = engine.MetaArena(16 + 2 * len(norms), dev)
+        gmax = max(m.num_groups for m in norms)
+        stats = torch.zeros(len(norms) * n * gmax * 2, dtype=torch.float32, device=dev)
+        ops.append(engine.op_zero(stats))
+        used = [0]
+
+        def new_act(shape, dtype):
+            return engine.Act(pool.get(shape), shape, dtype, meta.new())
+
+        def raw_conv(name, module, src):
+            k = module.kernel_size[0]
+            nb, hb, wb, _ = src.shape
+            oh = engine.conv_out(hb, k, module.stride[0], module.padding[0], module.dilation[0])
+            ow = engine.conv_out(wb, k, module.stride[0], module.padding[0], module.dilation[0])
+            if module.groups > 1:
+                wgt = cache.get((name, "w", src.dtype), lambda out: engine.pack_grouped_conv_weight(
+                    module.weight, module.groups, src.dtype, out=out), deps=(module.weight,))
+            else:
+                wgt = cache.get((name, "w", src.dtype),
+                                lambda out: engine.pack_conv_weight(module.weight, src.dtype, out=out),
+                                deps=(module.weight,))
+            consts = cache.get((name, "consts_raw", src.dtype), lambda out: engine.bound_consts(wgt, None, None, out=out),
+                               deps=(module.weight,)) if scaled else None
+            dst = new_act((nb, oh, ow, module.out_channels), internal)
+            ops.append(engine.op_conv(src, wgt, dst, k, k, module.stride[0], module.padding[0], module.dilation[0],
+                                      relu=False, consts=consts, scaled_out=scaled, groups=module.groups))
+            return dst
+
+        def group_norm(name, norm, raw, dst, residual=None, relu=True):
+            st = stats[used[0]:used[0] + raw.shape[0] * norm.num_groups * 2]
+            used[0] += st.numel()
+            gamma, beta = cache.get((name, "gn"), lambda out: _affine_copy(norm, out), deps=(norm.weight, norm.bias))
+            ops.append(engine.op_gn_stats(raw, st, norm.num_groups))
+            ops.append(engine.op_gn_apply(raw, st, norm.num_groups, gamma, beta, norm.eps, dst, residual=residual,
+                                          relu=relu))
+            pool.release(raw.buf)
+
+        ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
+        hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
+        staged = pool.get((n,) + engine.stem_staging_dims(ho, wo) + (4,))
+        staged_meta = meta.new()
+        ops.append(engine.op_prep(x, staged, ho, wo, y_meta=staged_meta, scale=tf_scale, shift=tf_shift,
+                                  padded_hw=(h, w)))
+        stem_w = cache.get(("conv1", "w"), lambda out: engine.pack_stem_weight(self.conv1.weight, out=out),
+                           deps=(self.conv1.weight,))
+        stem_consts = cache.get(("conv1", "consts_raw"), lambda out: engine.bound_consts(stem_w, None, None, out=out),
+                                deps=(self.conv1.weight,)) if scaled else None
+        raw = new_act((n, ho, wo, 64), internal)
+        ops.append(engine.op_stem(n, h, w, staged, stem_w, raw, None, None, relu=False, x_meta=staged_meta,
+                                  consts=stem_consts, scaled_out=scaled))
+        pool.release(staged)
+        act = new_act((n, ho, wo, 64), internal)
+        group_norm("conv1", getattr(self, self.norm_name), raw, act)
+        cur = engine.Act(pool.get((n, hq, wq, 64)), (n, hq, wq, 64), internal, act.meta)  # max-pool keeps the metadata
+        ops.append(engine.op_maxpool(act, cur))
+        pool.release(act.buf)
+        outs = []
+        for li, lname in enumerate(self.res_layers):
+            stage = getattr(self, lname)
+            for bi, unit in enumerate(stage):
+                pre = "%s.%d." % (lname, bi)
+                last = bi == len(stage) - 1
+                residual = cur
+                if unit.downsample is not None:
+                    raw = raw_conv(pre + "downsample", unit.downsample[0], cur)
+                    residual = new_act(raw.shape, internal)
+                    group_norm(pre + "downsample", unit.downsample[1], raw, residual, relu=False)
+                src = cur
+                nconv = len(unit.kernel_sizes)
+                for ci in range(nconv):
+                    module = getattr(unit, "conv%d" % (ci + 1))
+                    raw = raw_conv(pre + "conv%d" % (ci + 1), module, src)
+                    final = ci == nconv - 1
+                    dst = new_act(raw.shape, internal)
+                    group_norm(pre + "conv%d" % (ci + 1), getattr(unit, unit.norm_names[ci]), raw, dst,
+                               residual=residual if final else None)
+                    if src is not cur:
+                        pool.release(src.buf)
+                    src = dst
+                if residual is not cur:
+                    pool.release(residual.buf)
+                pool.release(cur.buf)
+                cur = src
+            if li in self.out_indices:
+                # the returned feature map is a bf16 copy: the next stage keeps reading the internal tensor (GroupNorm
+                # amplifies storage rounding by |mean| / std of each group, so the residual stream stays in fp16)
+                t = engine.nhwc_empty(n, cur.shape[1], cur.shape[2], cur.shape[3], dev)  # re-bound at run time
+                outs.append(t)
+                ops.append(engine.op_add_mask(cur, engine.Act(t, cur.shape, torch.bfloat16, meta.new())))
+        plan = engine.Plan(ops, [x] + outs, [cache, pool.all_buffers, stats], dev, meta=meta)
+        return plan, [tuple(o.shape) for o in outs]
+
     def forward(self, x):
         self._check_supported(x)
+        if self.use_gn:
+            if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+                raise NotImplementedError("training through GroupNorm (use_gn=True) is not on the B200 path: "
+                                          "inference only (wrap the call in torch.no_grad() or freeze the module)")
+            cache = self._get_operands(x.device)
+            key = ("gn", tuple(x.shape), x.dtype, tuple(x.stride()), x.device, INTERNAL_DTYPE,
+                   getattr(self, "_input_tf", None))
+            entry = self._plans.get(key)
+            if entry is None:
+                entry = self._build_plan_gn(x, cache)
+                self._plans[key] = entry
+            plan, out_shapes = entry
+            outs = [torch.empty(s, dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+                    for s in out_shapes]
+            plan.run([x] + outs)
+            self._last_run = (plan, [x] + outs)
+            if x.dtype == torch.float32:
+                outs = [_upcast(o) for o in outs]
+            return outs[0] if len(outs) == 1 else tuple(outs)
         if self.training and torch.is_grad_enabled():
             params = self._trainable_weights()
             if params:

@@ -80,7 +80,7 @@ class ResNeXt(ResNet):
 
         self.inplanes = 64
         self.conv1 = conv7x7_group(3, 64, stride=2)
-        self.norm_name = "bn1"
+        self.norm_name = "gn1" if use_gn else "bn1"
         self.add_module(self.norm_name, norm_layer(64, use_gn))
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)

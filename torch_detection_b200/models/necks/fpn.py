@@ -89,7 +89,11 @@ class FPN(nn.Module):
                 cache.get("%s%d.w" % (kind, j),
                           lambda out, conv=conv: engine.pack_conv_weight(conv.weight, out=out),
                           deps=(conv.weight,))
-                if cm.with_norm:
+                if cm.with_norm and isinstance(cm.norm, nn.GroupNorm):
+                    # GroupNorm runs after the raw conv (TDET_OP_GN_STATS / _APPLY): its operands are made by
+                    # _build_plan_gn
+                    pass
+                elif cm.with_norm:
                     # eval-mode BatchNorm folded to the epilogue's scale / shift (a conv bias folds into shift)
                     norm = cm.norm
                     cache.get("%s%d.bn" % (kind, j),
@@ -187,6 +191,101 @@ class FPN(nn.Module):
             return plan, [tuple(o.buf.shape) for o in outs], [tuple(t.shape) for t in f32]
         return plan, [tuple(o.buf.shape) for o in outs]
 
+    def _uses_gn(self):
+        return any(isinstance(m, nn.GroupNorm) for m in self.modules())
+
+    def _build_plan_gn(self, feats, operands):
+        """normalize=..., use_gn=True: every ConvModule is conv -> GroupNorm(32, C) (layers.py:120-124).  GroupNorm
+        needs the statistics of the whole conv output, so each conv launches raw (fp16 significands with a
+        device-chosen exponent; the inputs' max |x| comes from one TDET_OP_AMAX pass), TDET_OP_GN_STATS reduces the
+        per-(image, group) sums and TDET_OP_GN_APPLY normalises and -- for the laterals -- adds the nearest-upsampled
+        coarser level in the same pass (fpn.py:98-101)."""
+        if type(self) is not FPN:
+            raise NotImplementedError("%s with GroupNorm is not on the B200 path" % type(self).__name__)
+        dev = feats[0].device
+        n = feats[0].shape[0]
+        used = feats[self.start_level:self.backbone_end_level]
+        nl = len(used)
+        shapes = [(t.shape[0], t.shape[2], t.shape[3], t.shape[1]) for t in used]
+        for j in range(nl - 1, 0, -1):
+            for dim, a, b in ((2, shapes[j - 1][1], 2 * shapes[j][1]), (3, shapes[j - 1][2], 2 * shapes[j][2])):
+                if a != b:
+                    raise RuntimeError(
+                        "The size of tensor a (%d) must match the size of tensor b (%d) at "
+                        "non-singleton dimension %d" % (a, b, dim))
+        co = self.out_channels
+        n_norm = len(self.lateral_convs) + len(self.fpn_convs)
+        meta = engine.MetaArena(nl + 3 * n_norm + 4, dev)
+        groups = self.lateral_convs[0].norm.num_groups
+        stats = torch.zeros(n_norm * n * groups * 2, dtype=torch.float32, device=dev)
+        ops = [engine.op_zero(stats)]
+        keep = [stats]
+        used_stats = [0]
+
+        def conv_gn(key, cm, src, dst, stride=1, coarse=None, relu=False):
+            """dst = act(GroupNorm(conv(src) + bias) + up2(coarse))"""
+            conv, norm = cm.conv, cm.norm
+            k = conv.kernel_size[0]
+            nb, h, w, _ = src.shape
+            oh, ow = engine.conv_out(h, k, stride, conv.padding[0]), engine.conv_out(w, k, stride, conv.padding[0])
+            wgt = operands.get((key, "w", src.dtype),
+                               lambda out: engine.pack_conv_weight(conv.weight, src.dtype, out=out), deps=(conv.weight,))
+            bias = operands.get((key, "b"), lambda out: _bias_copy(conv.bias, out),
+                                deps=(conv.bias,)) if conv.bias is not None else None
+            deps = (conv.weight,) + ((conv.bias,) if conv.bias is not None else ())
+            consts = operands.get((key, "consts_raw", src.dtype),
+                                  lambda out: engine.bound_consts(wgt, None, bias, out=out), deps=deps)
+            raw = engine.Act(torch.empty(nb * oh * ow * co, dtype=torch.bfloat16, device=dev), (nb, oh, ow, co),
+                             torch.float16, meta.new())
+            keep.append(raw.buf)
+            ops.append(engine.op_conv(src, wgt, raw, k, k, stride, conv.padding[0], 1, shift=bias, consts=consts,
+                                      scaled_out=True))
+            st = stats[used_stats[0]:used_stats[0] + nb * norm.num_groups * 2]
+            used_stats[0] += st.numel()
+            gamma, beta = operands.get((key, "gn"), lambda out: _gn_affine(norm, out), deps=(norm.weight, norm.bias))
+            ops.append(engine.op_gn_stats(raw, st, norm.num_groups))
+            ops.append(engine.op_gn_apply(raw, st, norm.num_groups, gamma, beta, norm.eps, dst, coarse=coarse, relu=relu))
+
+        srcs = []
+        for j, t in enumerate(used):
+            a = engine.Act(t, shapes[j], torch.bfloat16, meta.new())
+            ops.append(engine.op_amax(engine.Act(t, shapes[j], torch.bfloat16), a.meta))
+            srcs.append(a)
+        lats = [None] * nl
+        for j in range(nl - 1, -1, -1):
+            nb, h, w, c = shapes[j]
+            lats[j] = engine.Act(torch.empty(nb * h * w * co, dtype=torch.bfloat16, device=dev), (nb, h, w, co),
+                                 torch.float16, meta.new())
+            conv_gn("lat%d" % j, self.lateral_convs[j], srcs[j], lats[j], coarse=lats[j + 1] if j < nl - 1 else None)
+        outs = []
+        for j in range(nl):
+            nb, h, w, _ = shapes[j]
+            o = engine.Act(engine.nhwc_empty(nb, h, w, co, dev), (nb, h, w, co), torch.bfloat16, meta.new())
+            conv_gn("out%d" % j, self.fpn_convs[j], lats[j], o)
+            outs.append(o)
+        if self.num_outs > nl:
+            if not self.add_extra_convs:
+                for _ in range(self.num_outs - nl):
+                    nb, h, w, _ = outs[-1].shape
+                    oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                    o = engine.Act(engine.nhwc_empty(nb, oh, ow, co, dev), (nb, oh, ow, co), torch.bfloat16)
+                    ops.append(engine.op_subsample(outs[-1], o))
+                    outs.append(o)
+            else:
+                src = srcs[-1]
+                for j in range(nl, self.num_outs):
+                    nb, h, w, c = src.shape
+                    oh, ow = engine.conv_out(h, 3, 2, 1), engine.conv_out(w, 3, 2, 1)
+                    o = engine.Act(engine.nhwc_empty(nb, oh, ow, co, dev), (nb, oh, ow, co), torch.bfloat16, meta.new())
+                    # (every extra level that feeds another one is returned post-ReLU, see _build_plan)
+                    conv_gn("out%d" % j, self.fpn_convs[j], src, o, stride=2, relu=(j < self.num_outs - 1))
+                    outs.append(o)
+                    src = o
+        ext = list(feats) + [o.buf for o in outs]
+        plan = engine.Plan(ops, ext, [operands, [l.buf for l in lats], keep], dev, meta=meta)
+        plan.lats = lats
+        return plan, [tuple(o.buf.shape) for o in outs]
+
     def _emit_outputs(self, ops, operands, lats, shapes, dev, wkey=None, split=False):
         """P_j = conv3x3(merged lateral j) + bias (fpn.py:106-108).  Returns (output Acts, buffers to keep
         alive); subclasses extend the pyramid here."""
@@ -228,7 +327,8 @@ class FPN(nn.Module):
         want_fp32 = all(t.dtype == torch.float32 for t in inputs)
         # (the training path saves bf16 laterals for its backward plan: it never takes the split-precision path,
         # also when a frozen / eval backbone handed over fp32-I/O stage outputs)
-        if allow_split and type(self) is FPN and all(getattr(t, "_tdet_split", None) is not None for t in inputs):
+        if allow_split and type(self) is FPN and not self._uses_gn() and \
+                all(getattr(t, "_tdet_split", None) is not None for t in inputs):
             return self._forward_split([t._tdet_split for t in inputs])
         feats = [self._as_bf16_nhwc(t) for t in inputs]
         for t, c in zip(feats, self.in_channels):
@@ -239,7 +339,7 @@ class FPN(nn.Module):
         key = tuple(tuple(t.shape) for t in feats) + (dev,)
         entry = self._plans.get(key)
         if entry is None:
-            entry = self._build_plan(feats, operands)
+            entry = self._build_plan_gn(feats, operands) if self._uses_gn() else self._build_plan(feats, operands)
             self._plans[key] = entry
         plan, out_shapes = entry
         outs = [torch.empty(s, dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
@@ -433,6 +533,15 @@ def _fold_conv_bn(conv, norm, out):
     if conv.bias is not None:
         sh.add_(conv.bias.detach().float() * sc)   # BN(conv + b) = scale*conv + (shift + scale*b)
     return sc, sh
+
+
+def _gn_affine(norm, out):
+    g, b = norm.weight.detach().float(), norm.bias.detach().float()
+    if out is None:
+        return g.contiguous().clone(), b.contiguous().clone()
+    out[0].copy_(g)
+    out[1].copy_(b)
+    return out
 
 
 def _bias_copy(bias, out):

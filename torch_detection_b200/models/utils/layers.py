@@ -30,24 +30,32 @@ def conv7x7_group(in_planes, out_planes, stride=1, groups=1):
     return _conv(in_planes, out_planes, 7, stride, 3, 1, groups, False)
 
 
+def get_group_gn(planes):
+    """Number of GroupNorm groups for a width (layers.py:138-154): always 32."""
+    num_groups = 32
+    assert planes % num_groups == 0
+    return num_groups
+
+
 def norm_layer(planes, use_gn=False):
-    """BatchNorm2d (layers.py:50-54).  GroupNorm cannot be folded into a GEMM epilogue."""
+    """BatchNorm2d, or GroupNorm(32, planes) with use_gn=True (layers.py:50-54).  An eval-mode BatchNorm folds
+    into the conv's epilogue; GroupNorm needs the statistics of the whole conv output, so it runs as two extra
+    kernels after a raw conv (TDET_OP_GN_STATS / TDET_OP_GN_APPLY)."""
     if use_gn:
-        raise NotImplementedError("use_gn=True (GroupNorm) is not supported on the B200 path")
+        return nn.GroupNorm(get_group_gn(planes), planes)
     return nn.BatchNorm2d(planes)
 
 
 class ConvModule(nn.Module):
     """conv (+bias) (+BatchNorm) (+ReLU) parameter container used by the necks (layers.py:57-135).  The
     owning neck's plan executes it: an eval-mode BatchNorm (``normalize`` not None, ``use_gn=False``) is
-    folded into the conv's fp32 epilogue; GroupNorm, ``activate_last=False`` and ReLU6 are refused."""
+    folded into the conv's fp32 epilogue, a GroupNorm (``use_gn=True``) runs as statistics + apply kernels after
+    the raw conv; ``activate_last=False`` and ReLU6 are refused."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, normalize=None, use_gn=False, activation=None,
                  activate_last=True):
         super(ConvModule, self).__init__()
-        if use_gn and normalize is not None:
-            raise NotImplementedError("GroupNorm cannot be folded into a GEMM epilogue (B200 neck path)")
         if activation not in (None, "relu"):
             raise NotImplementedError("ConvModule activation %r is not on the B200 neck path" % (activation,))
         if not activate_last:
@@ -65,7 +73,7 @@ class ConvModule(nn.Module):
                      "groups"):
             setattr(self, attr, getattr(self.conv, attr))
         if self.with_norm:
-            self.norm = norm_layer(out_channels, use_gn=False)   # created after the conv, as in the reference
+            self.norm = norm_layer(out_channels, use_gn=use_gn)   # created after the conv, as in the reference
         if self.with_activation:
             self.activate = nn.ReLU(inplace=True)
 
