@@ -645,8 +645,8 @@ def main():
                 inf["module"] = type(mod).__name__
                 inf["ms"] = t
                 launches.append(inf)
-        gemm = [l for l in launches if l["kind"] in (1, 3)]
-        dom = [l for l in gemm if l["tile_n"] == 256] or gemm
+        gemm = [l for l in launches if l["kind"] in (1, 3, 18)]  # conv, stem, fused bottleneck tail
+        dom = [l for l in gemm if l["tile_n"] == 256 and l["kind"] in (1, 3)] or gemm
         dom_ms = sum(l["ms"] for l in dom)
         dom_fl = sum(l["flops"] for l in dom)
         all_ms = sum(l["ms"] for l in launches)

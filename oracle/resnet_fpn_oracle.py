@@ -260,11 +260,12 @@ def pafpn_forward(sd, inputs, in_channels, out_channels, num_outs, start_level=0
                   add_extra_convs=False, activation=None):
     """PAFPN.forward (models/necks/pafpn.py:108-148), normalize=None: the FPN pyramid P, then the
     bottom-up path N_i = pa_convs2[i-1](P_i + pa_convs1[i-1](N_{i-1})) (:131-134); `activation` is the
-    ConvModule activation of the pa convs (None or 'relu', applied to each conv's output)."""
+    ConvModule activation of the pa convs (None, 'relu' or 'relu6', applied to each conv's output)."""
     assert len(inputs) == len(in_channels)
     lo, hi = fpn_level_range(len(in_channels), start_level, end_level)
     n = hi - lo
-    act = (lambda t: F.relu(t, inplace=True)) if activation == "relu" else (lambda t: t)
+    act = {None: (lambda t: t), "relu": (lambda t: F.relu(t, inplace=True)),
+           "relu6": (lambda t: F.relu6(t, inplace=True))}[activation]  # layers.py:114-119
     lats = [_cm(sd, "lateral_convs.%d" % j, inputs[lo + j]) for j in range(n)]
     for j in range(n - 1, 0, -1):
         lats[j - 1] += F.interpolate(lats[j], scale_factor=2, mode="nearest")

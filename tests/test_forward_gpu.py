@@ -212,7 +212,7 @@ def test_config5_sweep_depth_by_size(cuda_device, depth, hw, batch):
     print("rel-L2 sweep", depth, hw, batch, e)
 
 
-@pytest.mark.parametrize("activation", [None, "relu"])
+@pytest.mark.parametrize("activation", [None, "relu", "relu6"])
 def test_pafpn_neck(cuda_device, activation):
     """PAFPN (bottom-up path fused as conv + residual) against the CPU oracle."""
     from torch_detection_b200 import models
@@ -224,10 +224,18 @@ def test_pafpn_neck(cuda_device, activation):
                               activation=activation), parent=models.necks)
     neck.init_weights()
     neck.eval()
+    if activation == "relu6":
+        # make the clamp at 6 bite (ConvModule(activation='relu6'), layers.py:114-119)
+        with torch.no_grad():
+            for cm in list(neck.pa_convs1) + list(neck.pa_convs2):
+                cm.conv.weight.mul_(3.0)
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
     x = torch.randn(2, 3, 160, 224, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
     wf = orc.resnet_forward(bsd, x.float(), 50)
     wp = orc.pafpn_forward(nsd, [f.clone() for f in wf], [256, 512, 1024, 2048], 256, 5, activation=activation)
+    if activation == "relu6":
+        clipped = float((wp[2] == 6.0).float().mean())
+        assert 0.005 < clipped < 0.9, clipped
     feats, outs = _run_product(bb, neck, x, dev)
     assert len(outs) == 5 and all(o.dtype == torch.bfloat16 for o in outs)
     e = _check_levels(outs, wp, ["N2", "N3", "N4", "N5", "N6"])

@@ -117,7 +117,7 @@ def test_gradient_oracle_matches_reference_autograd(depth):
         assert torch.allclose(v, ref_b[k].grad, rtol=1e-5, atol=1e-7), k
 
 
-@pytest.mark.parametrize("activation", [None, "relu"])
+@pytest.mark.parametrize("activation", [None, "relu", "relu6"])
 def test_pafpn_oracle_and_mirror_match_reference(activation):
     """Row f3: the PAFPN restatement is bit-identical to the live reference neck, and the product module
     mirrors its state_dict (keys, shapes, values for the same seed)."""

@@ -35,6 +35,7 @@ FLAG_SCALED_OUT = 2
 FLAG_COARSE_PARITY = 4
 FLAG_SPLIT = 8
 FLAG_POOL = 16
+FLAG_RELU6 = 128
 FLAG_DUAL = 32
 FLAG_SCALED_OUT2 = 64
 

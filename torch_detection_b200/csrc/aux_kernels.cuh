@@ -885,6 +885,10 @@ gn_apply_kernel(const GnApplyParams p) {
       if (p.relu) {
         lo = fmaxf(lo, 0.0f);
         hi = fmaxf(hi, 0.0f);
+        if (p.relu == 2) {
+          lo = fminf(lo, 6.0f);
+          hi = fminf(hi, 6.0f);
+        }
       }
       if (yf) {   // plain fp16 (exponent 0): saturate instead of overflowing to infinity
         lo = fminf(fmaxf(lo, -65504.0f), 65504.0f);

@@ -1130,6 +1130,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+            if (p.relu == 2) {   // ReLU6 (plain outputs only: x is the true value)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = fminf(x[i], 6.0f);
+            }
           }
           if (MASKED && (mask_tma ? valid : (mask_row != nullptr))) {
 #pragma unroll

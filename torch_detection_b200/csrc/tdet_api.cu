@@ -439,8 +439,10 @@ int fill_epilogue(Launch& l) {
   const tdet_op& o = l.op;
   ConvGemmParams& gp = l.gp;
   if (!is16(o.y_dtype)) return fail(TDET_ERR_INVALID_ARGUMENT, "y_dtype must be BF16 or F16");
-  gp.relu = (o.flags & TDET_FLAG_RELU) ? 1 : 0;
+  gp.relu = (o.flags & TDET_FLAG_RELU6) ? 2 : (o.flags & TDET_FLAG_RELU) ? 1 : 0;
   gp.out_scaled = (o.flags & TDET_FLAG_SCALED_OUT) ? 1 : 0;
+  if (gp.relu == 2 && (gp.out_scaled || (o.flags & (TDET_FLAG_POOL | TDET_FLAG_SPLIT))))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "TDET_FLAG_RELU6: plain 16-bit outputs only (no SCALED_OUT / POOL / SPLIT)");
   gp.out_fp16 = o.y_dtype == TDET_F16;
   gp.res_fp16 = o.residual_dtype == TDET_F16;
   gp.coarse_fp16 = o.coarse_dtype == TDET_F16;
@@ -1633,7 +1635,7 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
         gp.beta = o.shift;
         gp.h = o.h; gp.w = o.w; gp.c8 = c8; gp.groups = o.groups;
         gp.eps = o.eps;
-        gp.relu = (o.flags & TDET_FLAG_RELU) ? 1 : 0;
+        gp.relu = (o.flags & TDET_FLAG_RELU6) ? 2 : (o.flags & TDET_FLAG_RELU) ? 1 : 0;
         gp.x_fp16 = o.x_dtype == TDET_F16;
         gp.res_fp16 = o.residual_dtype == TDET_F16;
         gp.coarse_fp16 = o.coarse_dtype == TDET_F16;

@@ -334,7 +334,7 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
             coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1,
-            split=False, dual=None):
+            split=False, dual=None, relu6=False):
     """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype.
     split: split-precision tensors (bf16 hi|lo pairs, 2x the logical channels in memory); Act shapes stay
     logical.
@@ -350,7 +350,8 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
                          % (wgt.dtype, x.dtype))
     op = _C.TdetOp()
     op.kind = _C.OP_CONV
-    op.flags = (_C.FLAG_RELU if relu else 0) | (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
+    op.flags = (_C.FLAG_RELU6 if relu6 else (_C.FLAG_RELU if relu else 0)) | \
+        (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
         (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_SPLIT if split else 0)
     if mask is not None:
         op.mask = mask.ptr
@@ -648,14 +649,14 @@ def op_gn_stats(x, stats, groups):
     return op
 
 
-def op_gn_apply(x, stats, groups, gamma, beta, eps, y, residual=None, coarse=None, relu=False):
+def op_gn_apply(x, stats, groups, gamma, beta, eps, y, residual=None, coarse=None, relu=False, relu6=False):
     """y = act(GroupNorm(x) + residual + up2(coarse)) from the statistics of op_gn_stats; y has exponent 0 and its
     meta (if any) receives max |y|."""
     n, h, w, c = x.shape
     assert y.shape == x.shape
     op = _C.TdetOp()
     op.kind = _C.OP_GN_APPLY
-    op.flags = _C.FLAG_RELU if relu else 0
+    op.flags = _C.FLAG_RELU6 if relu6 else (_C.FLAG_RELU if relu else 0)
     op.n, op.h, op.w, op.cin, op.groups = n, h, w, c, groups
     op.ho, op.wo, op.cout = h, w, c
     op.x, op.x_dtype, op.x_meta = x.ptr, _TD[x.dtype], x.meta

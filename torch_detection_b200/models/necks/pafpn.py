@@ -27,8 +27,8 @@ class PAFPN(FPN):
 
     def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1,
                  add_extra_convs=False, normalize=None, use_gn=False, activation=None):
-        if activation not in (None, "relu"):
-            raise ValueError("PAFPN activation must be None or 'relu'")
+        if activation not in (None, "relu", "relu6"):
+            raise ValueError("PAFPN activation must be None, 'relu' or 'relu6'")
         nn.Module.__init__(self)
         assert isinstance(in_channels, list)
         self.in_channels = in_channels
@@ -77,7 +77,8 @@ class PAFPN(FPN):
 
     def _emit_outputs(self, ops, operands, lats, shapes, dev):
         co = self.out_channels
-        relu = self.activation == "relu"
+        relu = self.activation is not None
+        relu6 = self.activation == "relu6"
         nl = len(lats)
         keep = []
 
@@ -105,14 +106,14 @@ class PAFPN(FPN):
                 # relu(conv + b) first, then + P_j (ConvModule applies the activation before the add)
                 t = temp((nb, h, w, co))
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), t, 3, 3, 2, 1, 1,
-                                          **_epi(operands, "pa1_%d" % (j - 1)), relu=True))
+                                          **_epi(operands, "pa1_%d" % (j - 1)), relu=True, relu6=relu6))
                 ops.append(engine.op_add_mask(t, s, residual=p))
             else:
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), s, 3, 3, 2, 1, 1,
                                           **_epi(operands, "pa1_%d" % (j - 1)), residual=p))
             nj = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
             ops.append(engine.op_conv(s, operands.value("pa2_%d.w" % (j - 1)), nj, 3, 3, 1, 1, 1,
-                                      **_epi(operands, "pa2_%d" % (j - 1)), relu=relu))
+                                      **_epi(operands, "pa2_%d" % (j - 1)), relu=relu, relu6=relu6))
             outs.append(nj)
             prev = nj
         return outs, keep

@@ -50,14 +50,13 @@ class ConvModule(nn.Module):
     """conv (+bias) (+BatchNorm) (+ReLU) parameter container used by the necks (layers.py:57-135).  The
     owning neck's plan executes it: an eval-mode BatchNorm (``normalize`` not None, ``use_gn=False``) is
     folded into the conv's fp32 epilogue, a GroupNorm (``use_gn=True``) runs as statistics + apply kernels after
-    the raw conv; ``activate_last=False`` and ReLU6 are refused."""
+    the raw conv; ``activate_last=False`` is refused (no neck of the reference uses it)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, normalize=None, use_gn=False, activation=None,
                  activate_last=True):
         super(ConvModule, self).__init__()
-        if activation not in (None, "relu"):
-            raise NotImplementedError("ConvModule activation %r is not on the B200 neck path" % (activation,))
+        assert activation in (None, "relu", "relu6"), "Only ReLU and ReLU6 are supported"
         if not activate_last:
             raise NotImplementedError("ConvModule(activate_last=False) is not on the B200 neck path")
         self.with_norm = normalize is not None
@@ -75,7 +74,7 @@ class ConvModule(nn.Module):
         if self.with_norm:
             self.norm = norm_layer(out_channels, use_gn=use_gn)   # created after the conv, as in the reference
         if self.with_activation:
-            self.activate = nn.ReLU(inplace=True)
+            self.activate = nn.ReLU6(inplace=True) if activation == "relu6" else nn.ReLU(inplace=True)
 
     def forward(self, x):
         raise NotImplementedError(
