@@ -57,6 +57,7 @@ extern "C" {
 #endif
 
 #define TDET_ABI_VERSION 10
+#define TDET_GN_STAT_BLOCKS 128 /* rows per image of the TDET_OP_GN_STATS output */
 
 typedef enum tdet_status {
   TDET_OK = 0,
@@ -213,11 +214,12 @@ typedef struct tdet_tensor_meta {
  *                   bound_consts3 (next conv1); z2 is scaled like x (an F16 x with x_meta).
  * TDET_OP_GN_STATS  nn.GroupNorm(groups, cin) (models/utils/layers.py:50-54,138-154: use_gn=True backbones, necks with
  *                   normalize + use_gn), first pass.  x: raw conv output [n][h][w][cin] (x_dtype, x_meta exponent);
- *                   dw: fp32 [n][groups][2] += {sum, sum of squares} of the true values (caller zeroes it).
- *                   cin in {64, 128, ..., 2048} (a power of two), groups <= 64 dividing cin.
+ *                   dw: fp32 [n][TDET_GN_STAT_BLOCKS][groups][2], partial {sum, sum of squares} of the true values,
+ *                   one row per thread block (no atomics: results are bit-reproducible; rows beyond the launched
+ *                   blocks are not touched).  cin in {64, 128, ..., 2048} (a power of two), groups <= 64 dividing it.
  * TDET_OP_GN_APPLY  second pass: y = act( (x - mean) * rstd * scale[c] + shift[c] + residual + up2(coarse) ) with
- *                   mean / rstd = 1/sqrt(var + eps) of x's (image, group) from dw (TDET_OP_GN_STATS output; biased
- *                   variance); scale = gamma, shift = beta (fp32 [cin]); residual [n][h][w][cin] and coarse
+ *                   mean / rstd = 1/sqrt(var + eps) of x's (image, group) from dw (the TDET_OP_GN_STATS output of the
+ *                   same x: the rows are added in order; biased variance); scale = gamma, shift = beta (fp32 [cin]); residual [n][h][w][cin] and coarse
  *                   [n][h/2][w/2][cin] optional (16-bit, with metas); TDET_FLAG_RELU; y: 16-bit of y_dtype with
  *                   exponent 0 (F16 saturates at +-65504); y_meta (optional) receives max |y|.
  * TDET_OP_AMAX      x: 16-bit [n][h][w][cin] (x_dtype, x_meta exponent); y_meta: receives max |x| (true values;

@@ -225,17 +225,18 @@ def test_pafpn_neck(cuda_device, activation):
     neck.init_weights()
     neck.eval()
     if activation == "relu6":
-        # make the clamp at 6 bite (ConvModule(activation='relu6'), layers.py:114-119)
+        # bring the pyramid (max ~1400 with these BatchNorm statistics) down to the scale of the clamp, so that
+        # ConvModule(activation='relu6') (layers.py:114-119) clips a fraction of the outputs, not nearly all of them
         with torch.no_grad():
-            for cm in list(neck.pa_convs1) + list(neck.pa_convs2):
-                cm.conv.weight.mul_(3.0)
+            for cm in neck.lateral_convs:
+                cm.conv.weight.mul_(0.005)
     bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
     x = torch.randn(2, 3, 160, 224, generator=torch.Generator().manual_seed(8)).to(torch.bfloat16)
     wf = orc.resnet_forward(bsd, x.float(), 50)
     wp = orc.pafpn_forward(nsd, [f.clone() for f in wf], [256, 512, 1024, 2048], 256, 5, activation=activation)
     if activation == "relu6":
-        clipped = float((wp[2] == 6.0).float().mean())
-        assert 0.005 < clipped < 0.9, clipped
+        clipped = float((wp[1] == 6.0).float().mean())
+        assert 0.005 < clipped < 0.2, clipped
     feats, outs = _run_product(bb, neck, x, dev)
     assert len(outs) == 5 and all(o.dtype == torch.bfloat16 for o in outs)
     e = _check_levels(outs, wp, ["N2", "N3", "N4", "N5", "N6"])
@@ -587,8 +588,11 @@ def test_groupnorm_backbone_and_neck(cuda_device):
     # fp32 in -> fp32 out of the same values (no split-precision GroupNorm path)
     feats32 = bb(x.float().to(cuda_device))
     assert all(t.dtype == torch.float32 for t in feats32)
-    # (equal up to the summation order of the statistics' fp32 atomics, which differs from run to run)
-    assert all(orc.rel_l2(a, b.float()) < 2e-3 for a, b in zip(feats32, feats))
+    # (the statistics use no atomics: bit-reproducible)
+    assert all(torch.equal(a, b.float()) for a, b in zip(feats32, feats))
+    # ... and independent of the batch an image travels in (sharded inference is bit-identical)
+    one = bb(x[1:2].to(cuda_device))
+    assert all(torch.equal(a[1:2], b) for a, b in zip(feats, one))
     bb.train()
     with pytest.raises(NotImplementedError):
         bb(x.to(cuda_device))

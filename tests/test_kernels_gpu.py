@@ -634,14 +634,18 @@ def test_group_norm_stats_and_apply(cuda_device, case):
         assert h % 2 == 0 and w % 2 == 0
         coarse = _nhwc(torch.randn(n, c, h // 2, w // 2, generator=g).to(dev), torch.bfloat16)
     y = engine.nhwc_empty(n, h, w, c, dev, ydt)
-    stats = torch.zeros(n * groups * 2, dtype=torch.float32, device=dev)
+    stats = torch.full((engine.gn_stats_numel(n, groups),), float("nan"), dtype=torch.float32, device=dev)
     xa = engine.act_of(xs, xm)
     engine.run_op(engine.op_gn_stats(xa, stats, groups), dev)
     engine.run_op(engine.op_gn_apply(xa, stats, groups, gamma, beta, 1e-5, engine.act_of(y, ym),
                                      residual=engine.act_of(res, rm) if with_res else None,
                                      coarse=engine.act_of(coarse) if with_coarse else None, relu=relu), dev)
     torch.cuda.synchronize()
-    st = stats.view(n, groups, 2).cpu().double()
+    from torch_detection_b200 import _C
+    rows = min(_C.GN_STAT_BLOCKS, (h * w * c // 8 + 255) // 256)
+    raw = stats.view(n, _C.GN_STAT_BLOCKS, groups, 2).cpu()
+    assert not torch.isnan(raw[:, :rows]).any() and (rows == _C.GN_STAT_BLOCKS or torch.isnan(raw[:, rows:]).all())
+    st = raw[:, :rows].double().sum(1)
     xg = x_true.double().reshape(n, groups, -1)
     assert torch.allclose(st[..., 0], xg.sum(-1), rtol=1e-4, atol=1e-2 * 2.0 ** e)
     assert torch.allclose(st[..., 1], (xg * xg).sum(-1), rtol=1e-4)
@@ -654,6 +658,15 @@ def test_group_norm_stats_and_apply(cuda_device, case):
         ref = F.relu(ref)
     assert rel_l2(y.float().cpu(), ref) <= TOL[ydt]
     amax = marena.read()[2]
+    # bit-reproducible: a second run of both kernels gives the same bytes
+    y2 = engine.nhwc_empty(n, h, w, c, dev, ydt)
+    stats2 = torch.zeros_like(stats)
+    engine.run_op(engine.op_gn_stats(xa, stats2, groups), dev)
+    engine.run_op(engine.op_gn_apply(xa, stats2, groups, gamma, beta, 1e-5, engine.act_of(y2),
+                                     residual=engine.act_of(res, rm) if with_res else None,
+                                     coarse=engine.act_of(coarse) if with_coarse else None, relu=relu), dev)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
     # (the recorded maximum is taken before the output rounding: an upper bound within one ulp of the stored one)
     ymax = float(y.float().abs().max())
     assert amax[0] == 0 and ymax * (1 - 2.0 ** -8) <= amax[1] <= ymax * (1 + 2.0 ** -8)
@@ -663,6 +676,36 @@ def test_group_norm_rejects_unsupported_widths(cuda_device):
     from torch_detection_b200 import engine, _C
     dev = cuda_device
     x = engine.nhwc_empty(1, 4, 4, 192, dev)
-    stats = torch.zeros(64, dtype=torch.float32, device=dev)
+    stats = torch.zeros(engine.gn_stats_numel(1, 32), dtype=torch.float32, device=dev)
     with pytest.raises(_C.TdetError):
         engine.run_op(engine.op_gn_stats(engine.act_of(x), stats, 32), dev)
+
+
+@pytest.mark.parametrize("case", [("1x1_256_256", 2, 20, 28, 256, 256, 1, 1, 0), ("3x3s2_256_256", 2, 21, 29, 256, 256, 3, 2, 1),
+                                  ("3x3_128_128", 2, 12, 20, 128, 128, 3, 1, 1), ("3x3_64_64", 1, 16, 16, 64, 64, 3, 1, 1)])
+def test_conv_relu6(cuda_device, case):
+    """TDET_FLAG_RELU6 (ConvModule(activation='relu6'), layers.py:114-119) in every epilogue a conv can be routed to
+    (256-wide, operand-swapped 128-wide, 64-wide halo-patch), against F.relu6(F.conv2d) with the clamp biting."""
+    from torch_detection_b200 import engine, _C
+    name, n, h, w, cin, cout, k, stride, pad = case
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    x = _nhwc(torch.randn(n, cin, h, w, generator=g).to(dev))
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (4.0 / (cin * k * k) ** 0.5)).to(dev)
+    bias = (torch.randn(cout, generator=g)).to(dev)
+    wp = engine.pack_conv_weight(wt)
+    ho, wo = engine.conv_out(h, k, stride, pad), engine.conv_out(w, k, stride, pad)
+    y = engine.nhwc_empty(n, ho, wo, cout, dev)
+    engine.run_op(engine.op_conv(engine.act_of(x), wp, engine.act_of(y), k, k, stride, pad, 1, shift=bias, relu6=True), dev)
+    torch.cuda.synchronize()
+    ref = F.relu6(F.conv2d(x.float().cpu(), wp.permute(0, 3, 1, 2).float().cpu(), bias.cpu(), stride, pad))
+    clipped = float((ref == 6.0).float().mean())
+    assert 0.01 < clipped < 0.5, clipped
+    assert float(y.float().max()) == 6.0 and float(y.float().min()) == 0.0
+    assert rel_l2(y.float().cpu(), ref) <= TOL[torch.bfloat16]
+    with pytest.raises(_C.TdetError):   # plain outputs only
+        meta = engine.MetaArena(2, dev)
+        consts = engine.bound_consts(wp, None, bias)
+        yh = engine.nhwc_empty(n, ho, wo, cout, dev, torch.float16)
+        engine.run_op(engine.op_conv(engine.act_of(x, meta.new()), wp, engine.act_of(yh, meta.new()), k, k, stride, pad, 1,
+                                     shift=bias, relu6=True, consts=consts, scaled_out=True), dev)

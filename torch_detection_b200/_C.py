@@ -28,6 +28,7 @@ OP_SPLIT_COMBINE = 14
 OP_MAXPOOL_BWD, OP_STEM_WGRAD, OP_PARITY_MERGE = 15, 16, 17
 OP_BOTTLENECK_TAIL = 18
 OP_GN_STATS, OP_GN_APPLY = 19, 20
+GN_STAT_BLOCKS = 128  # TDET_GN_STAT_BLOCKS
 # tdet_dtype
 BF16, F32, F16, U8 = 0, 1, 2, 3
 FLAG_RELU = 1

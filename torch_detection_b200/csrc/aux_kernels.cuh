@@ -764,13 +764,16 @@ add_mask_kernel(const AddMaskParams p) {
 // sums stay in registers.
 constexpr int kGnMaxGroups = 64;
 
+constexpr int kGnStatBlocks = TDET_GN_STAT_BLOCKS;   // partial-sum rows per image (at most; include/tdet_b200.h)
+
+// Deterministic: no atomics anywhere.  A thread owns eight fixed channels; the block's 256 x 16 partial sums are
+// combined per group by one thread in a fixed order and written to the block's own row of `stats`
+// ([n][kGnStatBlocks][groups][2]); gn_apply_kernel adds the rows of its image in order.
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int hw, int c8, int groups, int x_fp16,
                 const TensorMeta* __restrict__ x_meta) {
-  // grid: (blocks per image, n); blockDim.x = 256, a multiple of c8 (c8 in {8, 16, ..., 256})
-  __shared__ float bins[2 * kGnMaxGroups];
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) bins[i] = 0.0f;
-  __syncthreads();
+  // grid: (blocks per image <= kGnStatBlocks, n); blockDim.x = 256, a multiple of c8 (c8 in {8, 16, ..., 256})
+  __shared__ float part[16][257];   // [2 * channel-in-octet + {sum, sumsq}][thread], padded against bank conflicts
   const int img = blockIdx.y;
   const long long total = static_cast<long long>(hw) * c8;
   const uint4* xi = x + static_cast<long long>(img) * total;
@@ -796,17 +799,26 @@ gn_stats_kernel(const uint4* __restrict__ x, float* __restrict__ stats, int hw, 
       s2[2 * j + 1] = fmaf(hi, hi, s2[2 * j + 1]);
     }
   }
-  const int cg = (c8 * 8) / groups;                     // channels per group
-  const int c0 = static_cast<int>(start % c8) * 8;      // this thread's first channel
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int g = (c0 + e) / cg;
-    atomicAdd(&bins[2 * g], s1[e]);
-    atomicAdd(&bins[2 * g + 1], s2[e]);
+    part[2 * e][threadIdx.x] = s1[e];
+    part[2 * e + 1][threadIdx.x] = s2[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x)
-    atomicAdd(stats + static_cast<long long>(img) * 2 * groups + i, bins[i]);
+  // thread (g, which) adds, in a fixed order, every partial that belongs to group g: thread t holds channels
+  // [(t % c8) * 8, +8) (blockDim.x is a multiple of c8, so is the grid stride)
+  if (threadIdx.x < 2 * groups) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const int cg = (c8 * 8) / groups;                   // channels per group
+    const int ch_lo = g * cg, ch_hi = ch_lo + cg;
+    float acc = 0.0f;
+    for (int oct = ch_lo / 8; oct * 8 < ch_hi; ++oct) {
+      const int e_lo = max(ch_lo - oct * 8, 0), e_hi = min(ch_hi - oct * 8, 8);
+      for (int t = oct; t < 256; t += c8)
+        for (int e = e_lo; e < e_hi; ++e) acc += part[2 * e + which][t];
+    }
+    stats[((static_cast<long long>(img) * kGnStatBlocks + blockIdx.x) * groups + g) * 2 + which] = acc;
+  }
 }
 
 struct GnApplyParams {
@@ -814,7 +826,8 @@ struct GnApplyParams {
   const uint4* res;        // nullable, same shape
   const uint4* coarse;     // nullable, [n][h/2][w/2][c]: nearest-x2 upsample-add (FPN top-down path after the norm)
   uint4* y;
-  const float* stats;      // [n][groups][2] sum, sum of squares of the true values
+  const float* stats;      // [n][kGnStatBlocks][groups][2] partial sum, sum of squares of the true values
+  int stat_blocks;         // rows gn_stats_kernel wrote per image
   const float* gamma;
   const float* beta;
   int h, w, c8, groups;
@@ -834,8 +847,13 @@ gn_apply_kernel(const GnApplyParams p) {
   const int cg = (p.c8 * 8) / p.groups;
   const float cnt = static_cast<float>(p.h) * p.w * cg;
   for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
-    const float s1 = p.stats[(static_cast<long long>(img) * p.groups + g) * 2];
-    const float s2 = p.stats[(static_cast<long long>(img) * p.groups + g) * 2 + 1];
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int b = 0; b < p.stat_blocks; ++b) {   // fixed order: every block of the image computes the same statistics
+      const float2 v = __ldg(reinterpret_cast<const float2*>(
+          p.stats + ((static_cast<long long>(img) * kGnStatBlocks + b) * p.groups + g) * 2));
+      s1 += v.x;
+      s2 += v.y;
+    }
     const float mean = s1 / cnt;
     const float var = fmaxf(s2 / cnt - mean * mean, 0.0f);   // biased variance, as nn.GroupNorm
     s_mean[g] = mean;

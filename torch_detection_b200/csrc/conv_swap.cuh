@@ -313,7 +313,7 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
           for (int i = 0; i < 32; ++i) {
             const int pr = ck * 32 + i;  // pixel row inside the group's 128
             float y = fmaf(__uint_as_float(v[i]), sc, sh);
-            if (p.relu) y = fmaxf(y, 0.0f);
+            if (p.relu) y = p.relu == 2 ? fminf(fmaxf(y, 0.0f), 6.0f) : fmaxf(y, 0.0f);
             const bool ok = PATCH ? (h0 + (pr >> 3) < p.Ho && w0 + (pr & 7) < p.Wo) : (m0 + pr < p.M);
             if (ok) amax_local = fmaxf(amax_local, fabsf(y));
             uint16_t h;

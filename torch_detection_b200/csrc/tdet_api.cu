@@ -1616,10 +1616,16 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       // grid (blocks per image, n): a block's 256 threads and the grid stride are multiples of c / 8
       const int c8 = o.cin / 8;
       const long long items = static_cast<long long>(o.h) * o.w * c8;
+      // statistics: at most TDET_GN_STAT_BLOCKS blocks per image (one partial row each; the apply kernel must see
+      // the same count); apply: enough blocks to fill the device
+      long long sb = (items + 255) / 256;
+      if (sb > kGnStatBlocks) sb = kGnStatBlocks;
+      if (sb < 1) sb = 1;
       long long bx = (items + 255) / 256;
       const long long cap = (static_cast<long long>(di.num_sms) * 16 + o.n - 1) / o.n;
       if (bx > cap) bx = cap;
       if (bx < 1) bx = 1;
+      if (o.kind == TDET_OP_GN_STATS) bx = sb;
       const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(o.n), 1);
       if (o.kind == TDET_OP_GN_STATS) {
         gn_stats_kernel<<<grid, 256, 0, st>>>(static_cast<const uint4*>(o.x), o.dw, o.h * o.w, c8, o.groups,
@@ -1631,6 +1637,7 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
         gp.coarse = static_cast<const uint4*>(o.coarse);
         gp.y = static_cast<uint4*>(o.y);
         gp.stats = o.dw;
+        gp.stat_blocks = static_cast<int>(sb);
         gp.gamma = o.scale;
         gp.beta = o.shift;
         gp.h = o.h; gp.w = o.w; gp.c8 = c8; gp.groups = o.groups;

@@ -637,10 +637,16 @@ def op_stem_wgrad(n, h, w, staged, g, dw, scale=None):
     return op
 
 
+def gn_stats_numel(n, groups):
+    """Size of the statistics buffer of one GroupNorm: fp32 [n][TDET_GN_STAT_BLOCKS][groups][2]."""
+    return n * _C.GN_STAT_BLOCKS * groups * 2
+
+
 def op_gn_stats(x, stats, groups):
-    """stats (fp32 [n][groups][2], zeroed by the caller) += per (image, group) sum / sum of squares of x's true values."""
+    """stats (fp32 [n][TDET_GN_STAT_BLOCKS][groups][2]) <- per-block partial sum / sum of squares of x's true values
+    per (image, group); no atomics, bit-reproducible."""
     n, h, w, c = x.shape
-    assert stats.dtype == torch.float32 and stats.numel() == n * groups * 2
+    assert stats.dtype == torch.float32 and stats.numel() == gn_stats_numel(n, groups)
     op = _C.TdetOp()
     op.kind = _C.OP_GN_STATS
     op.n, op.h, op.w, op.cin, op.groups = n, h, w, c, groups

@@ -553,7 +553,8 @@ class ResNet(nn.Module):
         """use_gn=True (nn.GroupNorm(32, C) after every conv, layers.py:50-54): GroupNorm needs the statistics of the
         whole conv output, so nothing folds into a GEMM epilogue.  Every conv launches RAW (no affine, no ReLU; fp16
         significands with a device-chosen exponent), TDET_OP_GN_STATS reduces sum / sum of squares per (image,
-        group) and TDET_OP_GN_APPLY normalises, applies gamma / beta, adds the residual and applies the ReLU in one
+        group) -- without atomics: bit-reproducible, and independent of the batch an image travels in -- and
+        TDET_OP_GN_APPLY normalises, applies gamma / beta, adds the residual and applies the ReLU in one
         pass.  Whole batch per launch, no fusions; inference only."""
         n, _, h_in, w_in = x.shape
         dev = x.device
@@ -573,10 +574,9 @@ class ResNet(nn.Module):
         pool = _BufferPool(dev)
         norms = [m for m in self.modules() if isinstance(m, nn.GroupNorm)]
         meta = engine.MetaArena(16 + 2 * len(norms), dev)
-        gmax = max(m.num_groups for m in norms)
-        stats = torch.zeros(len(norms) * n * gmax * 2, dtype=torch.float32, device=dev)
-        ops.append(engine.op_zero(stats))
-        used = [0]
+        # one statistics buffer, reused by every GroupNorm in turn (stream order: its apply has run before the next
+        # statistics pass overwrites it)
+        stats = torch.empty(engine.gn_stats_numel(n, max(m.num_groups for m in norms)), dtype=torch.float32, device=dev)
 
         def new_act(shape, dtype):
             return engine.Act(pool.get(shape), shape, dtype, meta.new())
@@ -601,8 +601,7 @@ class ResNet(nn.Module):
             return dst
 
         def group_norm(name, norm, raw, dst, residual=None, relu=True):
-            st = stats[used[0]:used[0] + raw.shape[0] * norm.num_groups * 2]
-            used[0] += st.numel()
+            st = stats[:engine.gn_stats_numel(raw.shape[0], norm.num_groups)]
             gamma, beta = cache.get((name, "gn"), lambda out: _affine_copy(norm, out), deps=(norm.weight, norm.bias))
             ops.append(engine.op_gn_stats(raw, st, norm.num_groups))
             ops.append(engine.op_gn_apply(raw, st, norm.num_groups, gamma, beta, norm.eps, dst, residual=residual,

@@ -217,10 +217,9 @@ class FPN(nn.Module):
         n_norm = len(self.lateral_convs) + len(self.fpn_convs)
         meta = engine.MetaArena(nl + 3 * n_norm + 4, dev)
         groups = self.lateral_convs[0].norm.num_groups
-        stats = torch.zeros(n_norm * n * groups * 2, dtype=torch.float32, device=dev)
-        ops = [engine.op_zero(stats)]
+        stats = torch.empty(engine.gn_stats_numel(n, groups), dtype=torch.float32, device=dev)  # reused in stream order
+        ops = []
         keep = [stats]
-        used_stats = [0]
 
         def conv_gn(key, cm, src, dst, stride=1, coarse=None, relu=False):
             """dst = act(GroupNorm(conv(src) + bias) + up2(coarse))"""
@@ -240,8 +239,7 @@ class FPN(nn.Module):
             keep.append(raw.buf)
             ops.append(engine.op_conv(src, wgt, raw, k, k, stride, conv.padding[0], 1, shift=bias, consts=consts,
                                       scaled_out=True))
-            st = stats[used_stats[0]:used_stats[0] + nb * norm.num_groups * 2]
-            used_stats[0] += st.numel()
+            st = stats[:engine.gn_stats_numel(nb, norm.num_groups)]
             gamma, beta = operands.get((key, "gn"), lambda out: _gn_affine(norm, out), deps=(norm.weight, norm.bias))
             ops.append(engine.op_gn_stats(raw, st, norm.num_groups))
             ops.append(engine.op_gn_apply(raw, st, norm.num_groups, gamma, beta, norm.eps, dst, coarse=coarse, relu=relu))
