@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define TDET_ABI_VERSION 10
+#define TDET_ABI_VERSION 11
 #define TDET_GN_STAT_BLOCKS 128 /* rows per image of the TDET_OP_GN_STATS output */
 
 typedef enum tdet_status {
@@ -142,10 +142,12 @@ typedef struct tdet_tensor_meta {
  *                   as NCHW all work); hc/wc = valid extent (0 = h/w), zero-padded to the (h, w) the stem
  *                   sees (pad-to-size-divisor); optional scale/shift[3]: v*scale[c] + shift[c], the data
  *                   layer's (v - mean)/std (datasets/dataset_transforms.py:29-44 steps 2 and 5).
- *                   y: bf16 [n][hp][wp][4] with (hp, wp) = tdet_stem_staging_dims(ho, wo) (ho/wo = stem output
- *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.
+ *                   y: 16-bit [n][hp][wp][4] with (hp, wp) = tdet_stem_staging_dims(ho, wo) (ho/wo = stem output
+ *                   size), the image at offset (3,3), zero elsewhere, channel 3 zero.  y_dtype = TDET_BF16 (default),
+ *                   or TDET_F16: three more significand bits, |v| saturates at 65504 (used ahead of GroupNorm chains,
+ *                   which amplify the staging's rounding); not with TDET_FLAG_SPLIT.
  *                   y_meta (optional): receives the image's |max| (exponent 0).
- * TDET_OP_STEM      x: the PREP output (bf16); wgt: tdet_pack_stem_weight output (bf16 [64][448]);
+ * TDET_OP_STEM      x: the PREP output (x_dtype = its format); wgt: tdet_pack_stem_weight output of the same format;
  *                   scale/shift: folded bn1; y: [n][ho][wo][64] of y_dtype (with TDET_FLAG_POOL: the max-pooled
  *                   [n][(ho-1)/2+1][(wo-1)/2+1][64]).  h,w = image size.
  * TDET_OP_MAXPOOL   x: [n][h][w][cin] of x_dtype; y: [n][ho][wo][cin] same dtype; 3x3, stride 2,
@@ -308,8 +310,9 @@ int tdet_pack_conv_weight(const float* w_oihw, void* w_packed, int cout, int cin
  * ld >= kh*kw*cin lets two matrices be packed side by side ([W | W2], TDET_FLAG_DUAL). */
 int tdet_pack_conv_weight_scaled(const float* w_oihw, const float* scale, void* w_packed, int cout, int cin, int kh,
                                  int kw, int ld, int dtype, void* stream);
-/* fp32 [64][3][7][7] -> bf16 [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded. */
-int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream);
+/* fp32 [64][3][7][7] -> 16-bit [64][448]: k = r*64 + s*4 + c (s < 7, c < 3), zero padded.  dtype = TDET_BF16, or
+ * TDET_F16 for a stem over an fp16 staging (TDET_OP_PREP with y_dtype = TDET_F16). */
+int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, int32_t dtype, void* stream);
 /* eval-mode BatchNorm2d -> per-channel fp32 scale = gamma/sqrt(var+eps), shift = beta-mean*scale
  * (models/utils/layers.py:50-54 builds nn.BatchNorm2d; eps is its default 1e-5). */
 int tdet_fold_bn(const float* gamma, const float* beta, const float* mean, const float* var,

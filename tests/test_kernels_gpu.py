@@ -709,3 +709,55 @@ def test_conv_relu6(cuda_device, case):
         yh = engine.nhwc_empty(n, ho, wo, cout, dev, torch.float16)
         engine.run_op(engine.op_conv(engine.act_of(x, meta.new()), wp, engine.act_of(yh, meta.new()), k, k, stride, pad, 1,
                                      shift=bias, relu6=True, consts=consts, scaled_out=True), dev)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 37, 53)])
+@pytest.mark.parametrize("src", [torch.float32, torch.uint8])
+def test_stem_fp16_staging(cuda_device, shape, src):
+    """TDET_OP_PREP with y_dtype = F16 + the stem over it (fp16 weights): used ahead of GroupNorm chains.  The staged
+    values keep 11 significand bits of the fp32 / uint8 input (bf16: 8), the conv matches fp32 on fp16-rounded
+    operands to the fp16 tolerance, out-of-range pixels saturate."""
+    from torch_detection_b200 import engine
+    dev = cuda_device
+    n, h, w = shape
+    g = torch.Generator().manual_seed(5)
+    if src == torch.uint8:
+        x = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8).to(dev)
+        sc = torch.tensor([1 / 58.4, 1 / 57.1, 1 / 57.4], device=dev)
+        sh = torch.tensor([-123.7 / 58.4, -116.3 / 57.1, -103.5 / 57.4], device=dev)
+        want = x.float() * sc.view(1, 3, 1, 1) + sh.view(1, 3, 1, 1)
+    else:
+        x = torch.randn(n, 3, h, w, generator=g).to(dev)
+        x[0, 0, 0, 0] = 1e6     # saturates at 65504 in the staging
+        sc = sh = None
+        want = x.clamp(-65504, 65504)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) * (2.0 / (64 * 49)) ** 0.5).to(dev)
+    ho, wo = engine.conv_out(h, 7, 2, 3), engine.conv_out(w, 7, 2, 3)
+    hp, wp_ = engine.stem_staging_dims(ho, wo)
+    staged = torch.empty((n, hp, wp_, 4), dtype=torch.float16, device=dev)
+    arena = engine.MetaArena(2, dev)
+    m_in, m_out = arena.new(), arena.new()
+    engine.run_op(engine.op_prep(x, staged, ho, wo, y_meta=m_in, scale=sc, shift=sh, y_dtype=torch.float16), dev)
+    torch.cuda.synchronize()
+    exp = torch.zeros((n, hp, wp_, 4), dtype=torch.float16, device=dev)
+    exp[:, 3:3 + h, 3:3 + w, :3] = want.to(torch.float16).permute(0, 2, 3, 1)
+    assert torch.equal(staged, exp), "fp16 image staging mismatch"
+    assert arena.read()[0] == (0, float(exp.float().abs().max()))
+    if src == torch.float32:
+        x[0, 0, 0, 0] = 0.5
+        engine.run_op(engine.op_prep(x, staged, ho, wo, y_meta=m_in, y_dtype=torch.float16), dev)
+        want = x
+    wpk = engine.pack_stem_weight(wt, dtype=torch.float16)
+    assert wpk.dtype == torch.float16
+    consts = engine.bound_consts(wpk, None, None)
+    y = engine.nhwc_empty(n, ho, wo, 64, dev, torch.float16)
+    engine.run_op(engine.op_stem(n, h, w, staged, wpk, engine.act_of(y, m_out), None, None, relu=False, x_meta=m_in,
+                                 consts=consts, scaled_out=True, x_dtype=torch.float16), dev)
+    torch.cuda.synchronize()
+    e = arena.read()[1][0]
+    ref = F.conv2d(want.to(torch.float16).float(), wt.to(torch.float16).float(), None, 2, 3)
+    err = rel_l2(y.float() * 2.0 ** e, ref)
+    assert err <= TOL[torch.float16], "rel-L2 %.3e" % err
+    # mixing formats is refused
+    with pytest.raises(Exception):
+        engine.run_op(engine.op_prep(x, staged, ho, wo, split=True, y_dtype=torch.float16), dev)

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtdet_b200.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # tdet_status
 OK = 0
@@ -123,7 +123,7 @@ def lib():
     L.tdet_pack_stem_weight_split.argtypes = [vp, vp, vp]
     L.tdet_pack_grouped_conv_weight.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.tdet_pack_dgrad_weight.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.tdet_pack_stem_weight.argtypes = [vp, vp, vp]
+    L.tdet_pack_stem_weight.argtypes = [vp, vp, i32, vp]
     L.tdet_fold_bn.argtypes = [vp, vp, vp, vp, f32, vp, vp, i32, vp]
     L.tdet_conv_bound_consts.argtypes = [vp, i32, vp, vp, i32, i32, vp, vp]
     L.tdet_stem_staging_dims.argtypes = [i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]

@@ -25,8 +25,9 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
                   int n, int hv, int wv, int hp, int wp, const float* __restrict__ scale,
-                  const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta, int split) {
+                  const float* __restrict__ shift, uint2* __restrict__ y, TensorMeta* meta, int split, int y_fp16) {
   const long long total = static_cast<long long>(n) * hp * wp;
+  const bool yf = y_fp16 != 0;   // fp16 staging (three more significand bits; |v| saturates at 65504); never with split
   const unsigned pairs = static_cast<unsigned>(total >> 1);
   const unsigned wp2 = static_cast<unsigned>(wp) >> 1;
   float amax = 0.0f;
@@ -48,9 +49,21 @@ prep_image_kernel(const T* __restrict__ x, long long sn, long long sc, long long
         const int iw = xw + k - 3;
         if (iw >= 0 && iw < wv) {
           const T* px = row + iw * sw;
-          const float c0 = fmaf(prep_load(px), s0, b0);
-          const float c1 = fmaf(prep_load(px + sc), s1, b1);
-          const float c2 = fmaf(prep_load(px + 2 * sc), s2, b2);
+          float c0 = fmaf(prep_load(px), s0, b0);
+          float c1 = fmaf(prep_load(px + sc), s1, b1);
+          float c2 = fmaf(prep_load(px + 2 * sc), s2, b2);
+          if (yf) {
+            c0 = fminf(fmaxf(c0, -65504.0f), 65504.0f);
+            c1 = fminf(fmaxf(c1, -65504.0f), 65504.0f);
+            c2 = fminf(fmaxf(c2, -65504.0f), 65504.0f);
+            o[k].x = pack16x2(c0, c1, true);
+            o[k].y = pack16x2(c2, 0.0f, true);
+            float v0, v1, v2, vz;
+            unpack16x2(o[k].x, true, v0, v1);
+            unpack16x2(o[k].y, true, v2, vz);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fabsf(v2)));
+            continue;
+          }
           o[k].x = pack_bf16x2(c0, c1);
           o[k].y = pack_bf16x2(c2, 0.0f);
           amax = fmaxf(amax, fmaxf(fmaxf(fabsf(bf16_lo(o[k].x)), fabsf(bf16_hi(o[k].x))), fabsf(bf16_lo(o[k].y))));
@@ -307,10 +320,11 @@ pack_grouped_weight_kernel(const float* __restrict__ w, W* __restrict__ out, int
   }
 }
 
-// fp32 [64][3][7][7] -> bf16 [64][448], k = r*64 + s*4 + c for s < 7, c < 3 (zero elsewhere): one
+// fp32 [64][3][7][7] -> 16-bit [64][448], k = r*64 + s*4 + c for s < 7, c < 3 (zero elsewhere): one
 // 64-wide k-block per filter row, matching the 16-pixel x 4-channel window rows the stem loads.
+template <typename W>
 __global__ void __launch_bounds__(256)
-pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out) {
+pack_stem_weight_kernel(const float* __restrict__ w, W* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 448) return;
   const int co = i / 448;
@@ -320,7 +334,7 @@ pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__
   const int c = k & 3;
   float v = 0.0f;
   if (s < 7 && c < 3) v = w[((co * 3 + c) * 7 + r) * 7 + s];
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = to_w16<W>(v);
 }
 
 __global__ void __launch_bounds__(256)

@@ -1071,7 +1071,8 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   if (o.ho != out_dim(o.h, 7, 2, 3, 1) || o.wo != out_dim(o.w, 7, 2, 3, 1))
     return fail(TDET_ERR_INVALID_ARGUMENT, "stem output size inconsistent");
   if (!o.x || !o.wgt || !o.y) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: null tensor pointer");
-  if (o.x_dtype != TDET_BF16) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: staged image must be BF16");
+  if (o.x_dtype != TDET_BF16 && !(o.x_dtype == TDET_F16 && !(o.flags & TDET_FLAG_SPLIT)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "stem: staged image must be BF16 (or F16 without split precision)");
   if (o.residual || o.coarse) return fail(TDET_ERR_INVALID_ARGUMENT, "stem: no residual/coarse");
   const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
   const bool split = (o.flags & TDET_FLAG_SPLIT) != 0;  // staged batch = 2n planes (hi, lo); y = 128 channels (hi | lo)
@@ -1114,7 +1115,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
     gp.num_m_tiles = o.n * gp.tiles_w * gp.pool_h;
   }
   l.pool = pool;
-  gp.ab_fp16 = 0;
+  gp.ab_fp16 = o.x_dtype == TDET_F16 ? 1 : 0;   // staging and weights share one 16-bit format
   gp.num_kb_b = 7;
   gp.a_stage_bytes = kABytes;
   l.bn = 64;
@@ -1432,18 +1433,20 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
       TensorMeta* meta = reinterpret_cast<TensorMeta*>(o.y_meta);
       const int hv = o.hc ? o.hc : o.h, wv = o.wc ? o.wc : o.w;  // valid extent; the rest is zero padding
       const int split = (o.flags & TDET_FLAG_SPLIT) ? 1 : 0;     // y then holds 2n staged images: hi planes, lo planes
+      const int y_fp16 = o.y_dtype == TDET_F16 ? 1 : 0;
+      if (y_fp16 && split) return fail(TDET_ERR_INVALID_ARGUMENT, "prep: fp16 staging has no split-precision form");
       if (o.x_dtype == TDET_F32)
         prep_image_kernel<float><<<g, 256, 0, st>>>(static_cast<const float*>(o.x), o.x_stride[0],
                                                     o.x_stride[1], o.x_stride[2], o.x_stride[3], o.n, hv, wv,
-                                                    hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split);
+                                                    hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split, y_fp16);
       else if (o.x_dtype == TDET_U8)
         prep_image_kernel<uint8_t><<<g, 256, 0, st>>>(static_cast<const uint8_t*>(o.x), o.x_stride[0],
                                                       o.x_stride[1], o.x_stride[2], o.x_stride[3], o.n, hv, wv,
-                                                      hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split);
+                                                      hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split, y_fp16);
       else
         prep_image_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
             static_cast<const __nv_bfloat16*>(o.x), o.x_stride[0], o.x_stride[1], o.x_stride[2],
-            o.x_stride[3], o.n, hv, wv, hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split);
+            o.x_stride[3], o.n, hv, wv, hp, wp, o.scale, o.shift, static_cast<uint2*>(o.y), meta, split, y_fp16);
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }
@@ -1877,10 +1880,14 @@ int tdet_pack_dgrad_weight(const float* w_oihw, const float* scale, void* w_pack
   return TDET_OK;
 }
 
-int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, void* stream) {
-  if (!w_oihw || !w_packed) return fail(TDET_ERR_INVALID_ARGUMENT, "pack_stem_weight: null pointer");
-  pack_stem_weight_kernel<<<(64 * 448 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w_oihw, static_cast<__nv_bfloat16*>(w_packed));
+int tdet_pack_stem_weight(const float* w_oihw, void* w_packed, int32_t dtype, void* stream) {
+  if (!w_oihw || !w_packed || !is16(dtype)) return fail(TDET_ERR_INVALID_ARGUMENT, "pack_stem_weight: bad arguments");
+  if (dtype == TDET_F16)
+    pack_stem_weight_kernel<__half><<<(64 * 448 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, static_cast<__half*>(w_packed));
+  else
+    pack_stem_weight_kernel<__nv_bfloat16><<<(64 * 448 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w_oihw, static_cast<__nv_bfloat16*>(w_packed));
   TDET_CUDA(cudaGetLastError());
   return TDET_OK;
 }

@@ -273,8 +273,8 @@ def pack_dgrad_weight(w, scale=None, dtype=torch.bfloat16, out=None):
     return out
 
 
-def pack_stem_weight(w, out=None):
-    """fp32 [64][3][7][7] -> bf16 [64][448] stem operand."""
+def pack_stem_weight(w, out=None, dtype=torch.bfloat16):
+    """fp32 [64][3][7][7] -> 16-bit [64][448] stem operand (in the staging's format)."""
     require_cuda(w, "weight")
     w = w.detach()
     if tuple(w.shape) != (64, 3, 7, 7):
@@ -282,9 +282,9 @@ def pack_stem_weight(w, out=None):
     if w.dtype != torch.float32 or not w.is_contiguous():
         w = w.float().contiguous()
     if out is None:
-        out = torch.empty((64, 448), dtype=torch.bfloat16, device=w.device)
+        out = torch.empty((64, 448), dtype=dtype, device=w.device)
     with torch.cuda.device(w.device):
-        _C.check(_C.lib().tdet_pack_stem_weight(w.data_ptr(), out.data_ptr(), _stream_ptr(w.device)))
+        _C.check(_C.lib().tdet_pack_stem_weight(w.data_ptr(), out.data_ptr(), _TD[out.dtype], _stream_ptr(w.device)))
     return out
 
 
@@ -416,7 +416,7 @@ def op_bottleneck_tail(x, w2, y, residual, w3, bn2, bn3, consts2=None, consts3=N
     return op
 
 
-def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, split=False):
+def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, split=False, y_dtype=torch.bfloat16):
     """x: logical (n, 3, h, w) image batch (fp32 / bf16 / uint8, any strides: an HWC batch viewed as NCHW is
     fine); scale/shift: optional fp32[3] device vectors of the per-channel normalisation v*scale + shift;
     padded_hw: the (H, W) >= (h, w) the network sees, the difference is zero padding (size divisor)."""
@@ -435,14 +435,15 @@ def op_prep(x, y, ho, wo, y_meta=None, scale=None, shift=None, padded_hw=None, s
     for i, s in enumerate(x.stride()):
         op.x_stride[i] = s
     op.x, op.y = _ptr(x), _ptr(y)
+    op.y_dtype = _TD[y_dtype]   # format of the staging (bf16, or fp16: see TDET_OP_PREP)
     op.y_meta = y_meta
     op.scale, op.shift = _ptr(scale), _ptr(shift)
     return op
 
 
 def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=None, scaled_out=False, split=False,
-            pool=False):
-    """x: staged image buffer (bf16); y: ``Act`` of shape (n, ho, wo, 64) -- with ``pool`` the kernel also
+            pool=False, x_dtype=torch.bfloat16):
+    """x: staged image buffer (x_dtype); y: ``Act`` of shape (n, ho, wo, 64) -- with ``pool`` the kernel also
     applies the 3x3/2 max-pool and y is the pooled (n, (ho-1)//2+1, (wo-1)//2+1, 64)."""
     op = _C.TdetOp()
     op.kind = _C.OP_STEM
@@ -452,7 +453,7 @@ def op_stem(n, h, w, x, wgt, y, scale, shift, relu=True, x_meta=None, consts=Non
     op.cout, op.kh, op.kw = 64, 7, 7
     op.stride, op.pad, op.dil = 2, 3, 1
     op.ho, op.wo = conv_out(h, 7, 2, 3), conv_out(w, 7, 2, 3)
-    op.x_dtype, op.y_dtype = _C.BF16, _TD[y.dtype]
+    op.x_dtype, op.y_dtype = _TD[x_dtype], _TD[y.dtype]
     op.x, op.wgt, op.y = _ptr(x), _ptr(wgt), y.ptr
     op.x_meta, op.y_meta = x_meta, y.meta
     op.scale, op.shift = _ptr(scale), _ptr(shift)

@@ -612,15 +612,18 @@ class ResNet(nn.Module):
         hq, wq = engine.conv_out(ho, 3, 2, 1), engine.conv_out(wo, 3, 2, 1)
         staged = pool.get((n,) + engine.stem_staging_dims(ho, wo) + (4,))
         staged_meta = meta.new()
+        # fp16 staging and stem weights: a chain of GroupNorms amplifies the stem's operand rounding (bf16 weights
+        # alone cost 3e-3 at the outputs of the 64 x 96 fixture); normalised pixels are far inside fp16's range
         ops.append(engine.op_prep(x, staged, ho, wo, y_meta=staged_meta, scale=tf_scale, shift=tf_shift,
-                                  padded_hw=(h, w)))
-        stem_w = cache.get(("conv1", "w"), lambda out: engine.pack_stem_weight(self.conv1.weight, out=out),
+                                  padded_hw=(h, w), y_dtype=torch.float16))
+        stem_w = cache.get(("conv1", "w", torch.float16),
+                           lambda out: engine.pack_stem_weight(self.conv1.weight, out=out, dtype=torch.float16),
                            deps=(self.conv1.weight,))
         stem_consts = cache.get(("conv1", "consts_raw"), lambda out: engine.bound_consts(stem_w, None, None, out=out),
                                 deps=(self.conv1.weight,)) if scaled else None
         raw = new_act((n, ho, wo, 64), internal)
         ops.append(engine.op_stem(n, h, w, staged, stem_w, raw, None, None, relu=False, x_meta=staged_meta,
-                                  consts=stem_consts, scaled_out=scaled))
+                                  consts=stem_consts, scaled_out=scaled, x_dtype=torch.float16))
         pool.release(staged)
         act = new_act((n, ho, wo, 64), internal)
         group_norm("conv1", getattr(self, self.norm_name), raw, act)
