@@ -120,7 +120,8 @@ struct ConvGemmParams {
   int relu;
   int has_res;
   int ab_fp16;      // operand format of A: 1 = fp16, 0 = bf16
-  int b_fp16;       // operand format of B (weights); kind::f16 takes the two formats independently
+  int b_fp16;       // operand format of B (weights); the instruction descriptor has one field per operand, but a
+                    // mixed F16 x BF16 tcgen05.mma traps on B200 ("illegal instruction", measured): keep them equal
   int out_fp16, res_fp16, coarse_fp16;  // storage formats
   int out_scaled;   // choose a power-of-two output exponent from the bound (else exponent 0)
   const float* scale;

@@ -1116,6 +1116,7 @@ int build_stem(Launch& l, const DeviceInfo& di) {
   }
   l.pool = pool;
   gp.ab_fp16 = o.x_dtype == TDET_F16 ? 1 : 0;   // staging and weights share one 16-bit format
+  gp.b_fp16 = gp.ab_fp16;
   gp.num_kb_b = 7;
   gp.a_stage_bytes = kABytes;
   l.bn = 64;
