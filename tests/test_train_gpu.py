@@ -397,3 +397,62 @@ def test_gradient_accumulation_with_deferred_buckets(cuda_device):
     assert sync.buckets_not_overlapped > 0
     for p, a in zip(params, once):
         assert orc.rel_l2(p.grad, 2 * a) <= 1e-5
+
+
+@pytest.mark.parametrize("activation", [None, "relu"])
+def test_pafpn_gradients(cuda_device, activation):
+    """SURVEY 8(f) row f3, training: PAFPN's bottom-up path (pafpn.py:131-134) backward -- every neck parameter
+    gradient and the gradients handed back for C2..C5 against fp32 autograd of the oracle's PAFPN forward on the
+    same bf16 inputs.  Plain comparison: with activation='relu' the ReLU decisions of the two precisions differ on a
+    few elements, which is what the looser rel-L2 gate of that case absorbs (cosine >= 0.999 is asserted too)."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    dev = cuda_device
+    torch.manual_seed(21)
+    neck = obj_from_dict(dict(type="PAFPN", in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5,
+                              activation=activation), parent=models.necks)
+    neck.init_weights()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():   # biases away from zero
+        for p in neck.parameters():
+            if p.dim() == 1:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g))
+    nsd = helpers.cpu_state(neck)
+    neck = neck.to(dev).train()
+    shapes = [(2, 256, 40, 56), (2, 512, 20, 28), (2, 1024, 10, 14), (2, 2048, 5, 7)]
+    cs = [torch.randn(s, generator=g).abs().to(torch.bfloat16) for s in shapes]
+    feats = [c.to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(True) for c in cs]
+    for rep in range(2):
+        for p in neck.parameters():
+            p.grad = None
+        for f in feats:
+            f.grad = None
+        outs = neck(feats)
+        assert len(outs) == 5
+        grads = [torch.randn(o.shape, generator=torch.Generator().manual_seed(9 + i)).to(torch.bfloat16)
+                 for i, o in enumerate(outs)]
+        torch.autograd.backward(list(outs), [t.to(dev).contiguous(memory_format=torch.channels_last) for t in grads])
+        torch.cuda.synchronize()
+    leaf = {k: v.clone().float().requires_grad_(True) for k, v in nsd.items()}
+    cl = [c.float().requires_grad_(True) for c in cs]
+    ref = orc.pafpn_forward(leaf, cl, [256, 512, 1024, 2048], 256, 5, activation=activation)
+    for a, b in zip(outs, ref):
+        assert orc.rel_l2(a.float(), b.detach()) <= GATE
+    torch.autograd.backward(list(ref), [t.float() for t in grads])
+    worst = 0.0
+    tol = 1e-2 if activation is None else 4e-2
+    for k, p in neck.named_parameters():
+        assert p.grad is not None, k
+        e = orc.rel_l2(p.grad.cpu(), leaf[k].grad)
+        worst = max(worst, e)
+        assert e <= tol and _cos(p.grad.cpu(), leaf[k].grad) >= 0.999, (k, e)
+    for j, (f, c) in enumerate(zip(feats, cl)):
+        e = orc.rel_l2(f.grad.float().cpu(), c.grad)
+        worst = max(worst, e)
+        assert e <= tol and _cos(f.grad.float().cpu(), c.grad) >= 0.999, ("C%d" % (j + 2), e)
+    print("PAFPN %s gradients: worst rel-L2 %.2e" % (activation, worst))
+    if activation == "relu":
+        neck6 = obj_from_dict(dict(type="PAFPN", in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5,
+                                   activation="relu6"), parent=models.necks).to(dev).train()
+        with pytest.raises(NotImplementedError):
+            neck6(feats)

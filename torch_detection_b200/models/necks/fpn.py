@@ -410,7 +410,7 @@ class FPN(nn.Module):
         used = feats[self.start_level:self.backbone_end_level]
         nl = len(used)
         bb = training.BackwardBuilder(dev, operands)
-        convs = [cm.conv for cm in self.lateral_convs] + [cm.conv for cm in self.fpn_convs]
+        convs = [cm.conv for _, group in self._conv_groups() for cm in group]
         plist = []
         for c in convs:
             plist.append(c.weight)
@@ -450,6 +450,8 @@ class FPN(nn.Module):
                     bb.release(g)
                 g = g_prev
             extra_dc = g
+        # (subclasses whose returned levels are not the output convs' own results map the gradients back here)
+        gp = self._bwd_to_pyramid(bb, bucket, state, gp, out_acts, nl)
         d_feats = [engine.nhwc_empty(t.shape[0], t.shape[2], t.shape[3], t.shape[1], dev) for t in used]
         pooled = None
         for j in range(nl):
@@ -480,6 +482,11 @@ class FPN(nn.Module):
         ext = g_ext + list(feats) + d_feats + list(outs)
         bplan = engine.Plan(ops, ext, [operands, bb.buffers, bb.acc_ws, bucket.flat], dev)
         return bplan, bucket
+
+    def _bwd_to_pyramid(self, bb, bucket, state, gp, out_acts, nl):
+        """Gradients w.r.t. the output convs' results P_0..P_{nl-1}, given those w.r.t. the returned levels: the
+        same thing for an FPN."""
+        return gp
 
     def _train_backward(self, state, gouts):
         if state["serial"] != getattr(self, "_train_serial", 0):

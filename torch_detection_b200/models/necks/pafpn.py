@@ -11,7 +11,8 @@ the bottom-up path of pafpn.py:131-134
 runs as two fused convs per level: the stride-2 3x3 ``pa_convs1`` takes P_i as its residual operand
 (bias + add in the fp32 epilogue, so the sum is written once), then the 3x3 ``pa_convs2``.  With
 ``activation='relu'`` the ReLU sits between conv and add (pafpn.py:63-80 -> ConvModule), so the add is a
-separate fused add op.  Inference only on this path for now: training raises NotImplementedError.
+separate fused add op.  Training runs as one ``autograd.Function`` like the FPN's (``_bwd_to_pyramid`` maps the
+gradients of the returned levels back to the pyramid); ``activation='relu6'`` is inference only.
 """
 import torch
 import torch.nn as nn
@@ -89,12 +90,15 @@ class PAFPN(FPN):
 
         outs = []
         prev = None
+        saved = dict(P=[None] * nl, s=[None] * nl, t=[None] * nl)   # what the backward plan reads (training)
+        self._pa_saved = saved
         for j in range(nl):
             nb, h, w, _ = shapes[j]
             # P_j: the returned N_0 for the finest level, a temporary otherwise
             p = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev)) if j == 0 else temp((nb, h, w, co))
             ops.append(engine.op_conv(lats[j], operands.value("out%d.w" % j), p, 3, 3, 1, 1, 1,
                                       **_epi(operands, "out%d" % j)))
+            saved["P"][j] = p
             if j == 0:
                 prev = p
                 outs.append(p)
@@ -108,9 +112,11 @@ class PAFPN(FPN):
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), t, 3, 3, 2, 1, 1,
                                           **_epi(operands, "pa1_%d" % (j - 1)), relu=True, relu6=relu6))
                 ops.append(engine.op_add_mask(t, s, residual=p))
+                saved["t"][j] = t
             else:
                 ops.append(engine.op_conv(prev, operands.value("pa1_%d.w" % (j - 1)), s, 3, 3, 2, 1, 1,
                                           **_epi(operands, "pa1_%d" % (j - 1)), residual=p))
+            saved["s"][j] = s
             nj = engine.act_of(engine.nhwc_empty(nb, h, w, co, dev))
             ops.append(engine.op_conv(s, operands.value("pa2_%d.w" % (j - 1)), nj, 3, 3, 1, 1, 1,
                                       **_epi(operands, "pa2_%d" % (j - 1)), relu=relu, relu6=relu6))
@@ -118,12 +124,63 @@ class PAFPN(FPN):
             prev = nj
         return outs, keep
 
+    def _build_plan(self, feats, operands, split=False):
+        entry = FPN._build_plan(self, feats, operands, split=split)
+        entry[0].pa = self._pa_saved   # P_j, s_j = P_j + act(pa1(N_{j-1})), t_j = act(pa1(N_{j-1})): saved activations
+        return entry
+
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)
         if self.training and torch.is_grad_enabled() and (
                 any(p.requires_grad for p in self.parameters()) or any(t.requires_grad for t in inputs)):
-            raise NotImplementedError("PAFPN training is not on the B200 path yet (inference only)")
-        return self._forward_infer(inputs)
+            if self.activation == "relu6":
+                raise NotImplementedError("PAFPN(activation='relu6') training is not on the B200 path: the backward "
+                                          "kernels' mask operand encodes ReLU only (inference runs)")
+        return FPN.forward(self, inputs)
+
+    def _bwd_to_pyramid(self, bb, bucket, state, gp, out_acts, nl):
+        """Backward of the bottom-up path (pafpn.py:131-134), top level first:
+            N_j = act(pa2(s_j)),  s_j = P_j + t_j,  t_j = act(pa1(N_{j-1}))        (N_0 = P_0)
+        gp[j] arrives as dL/dN_j from outside (extra levels already folded in) and leaves as dL/dP_j.  The ReLU
+        backward of N_j rides in the epilogue of the stride-2 dgrad that delivers level j + 1's contribution (mask
+        operand), the one of t_j is one masked copy."""
+        saved = state["plan"].pa
+        relu = self.activation == "relu"
+        gP = list(gp)
+        carry = None   # dL/dN_j complete (outside + level j + 1) and already masked with N_j > 0
+        for j in range(nl - 1, 0, -1):
+            pa1, pa2 = self.pa_convs1[j - 1].conv, self.pa_convs2[j - 1].conv
+            if carry is not None:
+                g2 = carry
+            elif relu:
+                g2 = bb.new_act(gp[j].shape)
+                bb.ops.append(engine.op_add_mask(gp[j], g2, mask=out_acts[j]))
+            else:
+                g2 = gp[j]
+            s_j, t_j = saved["s"][j], saved["t"][j]
+            bb.wgrad("pa2_%d" % (j - 1), pa2, None, s_j, g2, bucket.view(bucket.index_of(pa2.weight)))
+            if pa2.bias is not None:
+                bb.ops.append(engine.op_colsum(g2, bucket.view(bucket.index_of(pa2.bias))))
+            g_s = bb.dgrad("pa2_%d" % (j - 1), pa2, None, g2, s_j.shape)
+            if g2 is not gp[j]:
+                bb.release(g2)
+            gP[j] = g_s                      # s_j = P_j + t_j
+            if relu:
+                g_t = bb.new_act(g_s.shape)
+                bb.ops.append(engine.op_add_mask(g_s, g_t, mask=t_j))
+            else:
+                g_t = g_s
+            n_prev = out_acts[j - 1]
+            bb.wgrad("pa1_%d" % (j - 1), pa1, None, n_prev, g_t, bucket.view(bucket.index_of(pa1.weight)))
+            if pa1.bias is not None:
+                bb.ops.append(engine.op_colsum(g_t, bucket.view(bucket.index_of(pa1.bias))))
+            carry = bb.dgrad("pa1_%d" % (j - 1), pa1, None, g_t, n_prev.shape, residual=gp[j - 1],
+                             mask=out_acts[j - 1] if (relu and j - 1 > 0) else None)
+            if g_t is not g_s:
+                bb.release(g_t)
+        if carry is not None:
+            gP[0] = carry
+        return gP
 
 
 def _pa_conv(channels, stride, normalize, bias, use_gn, activation):
