@@ -403,8 +403,9 @@ def test_gradient_accumulation_with_deferred_buckets(cuda_device):
 def test_pafpn_gradients(cuda_device, activation):
     """SURVEY 8(f) row f3, training: PAFPN's bottom-up path (pafpn.py:131-134) backward -- every neck parameter
     gradient and the gradients handed back for C2..C5 against fp32 autograd of the oracle's PAFPN forward on the
-    same bf16 inputs.  Plain comparison: with activation='relu' the ReLU decisions of the two precisions differ on a
-    few elements, which is what the looser rel-L2 gate of that case absorbs (cosine >= 0.999 is asserted too)."""
+    same bf16 inputs.  With activation='relu' the comparison is mask-matched like the backbone's: the
+    oracle's ReLUs take the decisions (and forward values) of the kernels' own stored t_j / N_j, so that a handful of
+    flipped elements does not hide -- or fake -- a backward error; the plain comparison's cosine is asserted too."""
     from torch_detection_b200 import models
     from torch_detection_b200.utils import obj_from_dict
     dev = cuda_device
@@ -438,18 +439,40 @@ def test_pafpn_gradients(cuda_device, activation):
     ref = orc.pafpn_forward(leaf, cl, [256, 512, 1024, 2048], 256, 5, activation=activation)
     for a, b in zip(outs, ref):
         assert orc.rel_l2(a.float(), b.detach()) <= GATE
+    if activation == "relu":
+        plain = torch.autograd.grad(list(ref), [leaf[k] for k, _ in neck.named_parameters()], [t.float() for t in grads])
+        for (k, p), gr in zip(neck.named_parameters(), plain):
+            assert _cos(p.grad.cpu(), gr) >= 0.99, (k, _cos(p.grad.cpu(), gr))
+        # mask-matched oracle: the same forward with the kernels' own ReLU decisions
+        saved = neck._train_state["plan"].pa
+
+        def stored(act):
+            n, h, w, c = act.shape
+            return act.buf[act.offset:act.offset + n * h * w * c].view(n, h, w, c).permute(0, 3, 1, 2).float().cpu()
+
+        leaf = {k: v.clone().float().requires_grad_(True) for k, v in nsd.items()}
+        cl = [c.float().requires_grad_(True) for c in cs]
+        pyr = list(orc.fpn_forward(leaf, cl, [256, 512, 1024, 2048], 256, 4))
+        conv = torch.nn.functional.conv2d
+        ref = [pyr[0]]
+        for j in range(1, 4):
+            t = conv(ref[-1], leaf["pa_convs1.%d.conv.weight" % (j - 1)], leaf["pa_convs1.%d.conv.bias" % (j - 1)], 2, 1)
+            t = grad_oracle._force(t, stored(saved["t"][j]), True)
+            nj = conv(pyr[j] + t, leaf["pa_convs2.%d.conv.weight" % (j - 1)], leaf["pa_convs2.%d.conv.bias" % (j - 1)], 1, 1)
+            ref.append(grad_oracle._force(nj, outs[j].detach().float().cpu(), True))
+        ref.append(torch.nn.functional.max_pool2d(ref[-1], 1, stride=2))
     torch.autograd.backward(list(ref), [t.float() for t in grads])
     worst = 0.0
-    tol = 1e-2 if activation is None else 4e-2
+    tol = 1e-2
     for k, p in neck.named_parameters():
         assert p.grad is not None, k
         e = orc.rel_l2(p.grad.cpu(), leaf[k].grad)
         worst = max(worst, e)
-        assert e <= tol and _cos(p.grad.cpu(), leaf[k].grad) >= 0.999, (k, e)
+        assert e <= tol, (k, e)
     for j, (f, c) in enumerate(zip(feats, cl)):
         e = orc.rel_l2(f.grad.float().cpu(), c.grad)
         worst = max(worst, e)
-        assert e <= tol and _cos(f.grad.float().cpu(), c.grad) >= 0.999, ("C%d" % (j + 2), e)
+        assert e <= tol, ("C%d" % (j + 2), e)
     print("PAFPN %s gradients: worst rel-L2 %.2e" % (activation, worst))
     if activation == "relu":
         neck6 = obj_from_dict(dict(type="PAFPN", in_channels=[256, 512, 1024, 2048], out_channels=256, num_outs=5,
