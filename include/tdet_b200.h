@@ -173,7 +173,8 @@ typedef struct tdet_tensor_meta {
  *                   dw: fp32 [cout][kh][kw][cin], ACCUMULATED (caller zeroes it):
  *                   dw[co][r][s][ci] += scale[co] * sum_{n,p,q} gy[n][p][q][co] * x[n][p*stride-pad+r*dil][..][ci]
  *                   (scale = folded BN scale or NULL = 1).  geometry fields as for the forward conv.
- * TDET_OP_DW_UNPACK x: fp32 [cout][kh][kw][cin]; y: fp32 [cout][cin][kh][kw]
+ * TDET_OP_DW_UNPACK x: fp32 [cout][kh][kw][cin]; y: fp32 [cout][cin / groups][kh][kw] (groups > 1: x is the DENSE weight
+ *                   gradient of a grouped conv, y keeps each output channel's own group: resnext.py:84-87)
  * TDET_OP_COLSUM    x: 16-bit [n*h*w][cin]; dw: fp32 [cin] += column sums (caller zeroes it)
  * TDET_OP_SUMPOOL2  y[n][i][j][:] = sum_{a,b<2} x[n][2i+a][2j+b][:]   (h == 2*ho, w == 2*wo), bf16,
  *                   fp32 accumulation

@@ -150,10 +150,12 @@ def teacher_forced_grads(bb_sd, neck_sd, saved_bb, saved_neck, depth, grad_outs,
         wdtype = wdtype or bb_weight_dtype
         scale = bb[bnp + ".weight"] / torch.sqrt(bb[bnp + ".running_var"] + orc.BN_EPS)
         shift = bb[bnp + ".bias"] - bb[bnp + ".running_mean"] * scale
+        groups = inp.shape[1] // bb[wkey].shape[1]   # > 1: ResNeXt's grouped 3x3 (models/backbone/resnext.py:84-87)
         if kr:
+            assert groups == 1, "the kernel-rounding model covers dense convs"
             y = _ConvBNKernelModel.apply(inp, bb[wkey], scale, shift, stride, pad, wdtype)
         else:
-            y = F.conv2d(inp, _ste(bb[wkey], wdtype), None, stride, pad)
+            y = F.conv2d(inp, _ste(bb[wkey], wdtype), None, stride, pad, 1, groups)
             y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
         if res is not None:
             y = y + res

@@ -479,3 +479,47 @@ def test_pafpn_gradients(cuda_device, activation):
                                    activation="relu6"), parent=models.necks).to(dev).train()
         with pytest.raises(NotImplementedError):
             neck6(feats)
+
+
+@pytest.mark.parametrize("base_width,cardinality,frozen", [(4, 32, 1), (8, 16, 2)])
+def test_resnext_gradients(cuda_device, base_width, cardinality, frozen):
+    """SURVEY 8(f) row f4, training: ResNeXt-50 (grouped 3x3, models/backbone/resnext.py:84-87).  The data gradient of
+    the grouped conv runs as a grouped conv over the block-diagonal operand, its weight gradient is accumulated dense
+    and unpacked to the block diagonal; every gradient against the teacher-forced fp32 oracle (exact backward over the
+    kernels' own stored activations, <= 1e-2) and, for direction, the plain fp32 oracle (cosine >= 0.95)."""
+    from torch_detection_b200 import models
+    from torch_detection_b200.utils import obj_from_dict
+    dev = cuda_device
+    torch.manual_seed(13)
+    bb = obj_from_dict(dict(type="ResNeXt", depth=50, base_width=base_width, cardinality=cardinality,
+                            frozen_stages=frozen, bn_eval=True, bn_frozen=True), parent=models.backbone)
+    bb.init_weights()
+    sd = bb.state_dict()
+    orc.randomize_bn_stats(sd, generator=torch.Generator().manual_seed(3))
+    bb.load_state_dict(sd)
+    _, neck = helpers.build_product_pair(50, seed=5)
+    bsd, nsd = helpers.cpu_state(bb), helpers.cpu_state(neck)
+    bb, neck = bb.to(dev).train(), neck.to(dev).train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 96, 128, generator=g).to(torch.bfloat16)
+    outs = neck(bb(x.to(dev)))
+    grads = [torch.randn(o.shape, generator=g).to(torch.bfloat16) for o in outs]
+    torch.autograd.backward(list(outs), [t.to(dev).contiguous(memory_format=torch.channels_last) for t in grads])
+    torch.cuda.synchronize()
+    got_b = {k: p.grad.detach().cpu() for k, p in bb.named_parameters() if p.grad is not None}
+    assert all(got_b[k].shape == bsd[k].shape for k in got_b)
+    grouped = [k for k in got_b if k.endswith("conv2.weight")]
+    assert grouped and all(bsd[k].shape[1] * cardinality == bsd[k].shape[0] for k in grouped)
+    xb, xn, _, _ = grad_oracle.teacher_forced_grads(bsd, nsd, bb.saved_activations(), neck.saved_activations(), 50, grads,
+                                                    train_from_stage=frozen, bb_weight_dtype=_backbone_weight_dtype(),
+                                                    x=x.float())
+    pb, _, _, _ = grad_oracle.plain_grads(bsd, nsd, x.float(), 50, grads, train_from_stage=frozen)
+    assert set(got_b) == set(xb)
+    errs = {k: orc.rel_l2(got_b[k], xb[k]) for k in xb}
+    worst = max(errs, key=errs.get)
+    print("ResNeXt-50 %dx%dd gradients (%d): max rel-L2 %.2e (%s), grouped convs max %.2e" %
+          (cardinality, base_width, len(errs), errs[worst], worst, max(errs[k] for k in grouped)))
+    bad = {k: v for k, v in errs.items() if not v <= GATE}
+    assert not bad, bad
+    low = {k: _cos(got_b[k], pb[k]) for k in pb if not _cos(got_b[k], pb[k]) >= 0.95}
+    assert not low, low

@@ -397,18 +397,22 @@ pack_dgrad_weight_kernel(const float* __restrict__ w, const float* __restrict__ 
   }
 }
 
-// fp32 [cout][kh][kw][cin] -> fp32 [cout][cin][kh][kw]
+// fp32 [cout][kh][kw][cin] -> fp32 [cout][cin / groups][kh][kw]: the OIHW gradient of a (grouped) conv.  With
+// groups > 1 the input is the DENSE weight gradient and only each output channel's own group of input channels is
+// kept (the block diagonal; models/backbone/resnext.py:84-87).
 __global__ void __launch_bounds__(256)
-dw_unpack_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int kh, int kw) {
-  const long long total = static_cast<long long>(cout) * cin * kh * kw;
+dw_unpack_kernel(const float* __restrict__ in, float* __restrict__ out, int cout, int cin, int kh, int kw, int groups) {
+  const int cig = cin / groups, cog = cout / groups;
+  const long long total = static_cast<long long>(cout) * cig * kh * kw;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int s = static_cast<int>(i % kw);
     long long t = i / kw;
     const int r = static_cast<int>(t % kh);
     t /= kh;
-    const int ci = static_cast<int>(t % cin);
-    const int co = static_cast<int>(t / cin);
+    const int cl = static_cast<int>(t % cig);
+    const int co = static_cast<int>(t / cig);
+    const int ci = (co / cog) * cig + cl;
     out[i] = in[((static_cast<long long>(co) * kh + r) * kw + s) * cin + ci];
   }
 }

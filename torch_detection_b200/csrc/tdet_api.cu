@@ -1321,7 +1321,8 @@ int build_launch(Launch& l, const DeviceInfo& di) {
       return TDET_OK;
     case TDET_OP_WGRAD: return build_wgrad(l, di);
     case TDET_OP_DW_UNPACK:
-      if (!o.x || !o.y || o.cout <= 0 || o.cin <= 0 || o.kh <= 0 || o.kw <= 0)
+      if (!o.x || !o.y || o.cout <= 0 || o.cin <= 0 || o.kh <= 0 || o.kw <= 0 ||
+          (o.groups > 1 && (o.cin % o.groups || o.cout % o.groups)))
         return fail(TDET_ERR_INVALID_ARGUMENT, "dw_unpack: bad arguments");
       l.bytes = 8.0 * o.cout * o.cin * o.kh * o.kw;
       return TDET_OK;
@@ -1478,9 +1479,10 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
     }
     case TDET_OP_WGRAD: return launch_wgrad(l, st);
     case TDET_OP_DW_UNPACK: {
-      const long long total = static_cast<long long>(o.cout) * o.cin * o.kh * o.kw;
+      const int groups = o.groups > 1 ? o.groups : 1;
+      const long long total = static_cast<long long>(o.cout) * (o.cin / groups) * o.kh * o.kw;
       dw_unpack_kernel<<<grid_for(total, di.num_sms), 256, 0, st>>>(
-          static_cast<const float*>(o.x), static_cast<float*>(o.y), o.cout, o.cin, o.kh, o.kw);
+          static_cast<const float*>(o.x), static_cast<float*>(o.y), o.cout, o.cin, o.kh, o.kw, groups);
       TDET_CUDA(cudaGetLastError());
       return TDET_OK;
     }

@@ -194,6 +194,18 @@ def pack_conv_weight(w, dtype=torch.bfloat16, out=None):
     return out
 
 
+def dense_group_weight(w, groups):
+    """[cout][cin / groups][kh][kw] parameter of a grouped conv -> its dense block-diagonal [cout][cin][kh][kw] form
+    (operand preparation when the weights change; the training path derives its dgrad operand from it)."""
+    w = w.detach().float()
+    cout, cig, kh, kw = w.shape
+    cog = cout // groups
+    dense = w.new_zeros(groups, cog, groups, cig, kh, kw)
+    idx = torch.arange(groups, device=w.device)
+    dense[idx, :, idx] = w.view(groups, cog, cig, kh, kw)
+    return dense.view(cout, groups * cig, kh, kw)
+
+
 def pack_dual_weight(w, scale, w2, scale2, dtype=torch.bfloat16, out=None):
     """[cout][cin + cin2] 16-bit operand of a dual-source 1x1 conv: [scale * w | scale2 * w2] (each BatchNorm scale
     folded into its half before the one rounding)."""
@@ -522,9 +534,12 @@ def op_wgrad(x, gy, dw, kh, kw, stride, pad, dil=1, scale=None):
     return op
 
 
-def op_dw_unpack(src, dst, cout, cin, kh, kw):
+def op_dw_unpack(src, dst, cout, cin, kh, kw, groups=1):
+    """fp32 [cout][kh][kw][cin] accumulator -> fp32 OIHW gradient [cout][cin / groups][kh][kw] (groups > 1: the block
+    diagonal of the dense gradient)."""
     op = _C.TdetOp()
     op.kind = _C.OP_DW_UNPACK
+    op.groups = groups
     op.cout, op.cin, op.kh, op.kw = cout, cin, kh, kw
     op.x, op.y = src.data_ptr(), dst.data_ptr()
     return op

@@ -744,8 +744,6 @@ class ResNet(nn.Module):
             convs = [m for m in stage.modules() if isinstance(m, nn.Conv2d)]
             bns = [m for m in stage.modules() if isinstance(m, nn.BatchNorm2d)]
             flags = [m.weight.requires_grad for m in convs]
-            if any(flags) and any(m.groups > 1 for m in convs):
-                raise NotImplementedError("training grouped convolutions (ResNeXt) is not on the B200 path yet")
             bflags = [p.requires_grad for m in bns for p in (m.weight, m.bias)]
             if any(flags):
                 if not all(flags):

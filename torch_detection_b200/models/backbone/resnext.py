@@ -13,7 +13,9 @@ usual 32x4d / 32x8d / 64x4d variants at every stage up to D = 64).
 
 Only the bottleneck depths (50/101/152) are offered: the reference's basic-block ResNeXt is broken
 (``_make_resX_layer`` passes ``base_width`` where ``ResNeXtBasicBlock`` expects ``cardinality``,
-resnext.py:150-158 vs :14-21).  Inference only for now: training grouped convs raises NotImplementedError.
+resnext.py:150-158 vs :14-21).  Training runs through the ResNet plan compiler: the grouped conv's data gradient
+is a grouped conv over the block-diagonal dgrad operand, its weight gradient is accumulated dense and unpacked to the
+block diagonal (``training.BackwardBuilder``).
 """
 import math
 

@@ -218,6 +218,14 @@ class BackwardBuilder(object):
     def dgrad_weight(self, name, module, scale, deps=()):
         """`scale` is the folded-BN scale tensor of the conv (refreshed in place before this entry: the
         cache keeps insertion order); `deps` = the BatchNorm parameters / buffers it derives from."""
+        if module.groups > 1:
+            # grouped conv (ResNeXt): the data-gradient operand of its dense block-diagonal form, which is again
+            # block diagonal -- the dgrad conv runs as a grouped conv of the same cardinality
+            return self.cache.get((name, "wd", self.dtype),
+                                  lambda out: engine.pack_dgrad_weight(
+                                      engine.dense_group_weight(module.weight, module.groups), scale, dtype=self.dtype,
+                                      out=out),
+                                  deps=(module.weight,) + tuple(deps))
         return self.cache.get((name, "wd", self.dtype),
                               lambda out: engine.pack_dgrad_weight(module.weight, scale, dtype=self.dtype, out=out),
                               deps=(module.weight,) + tuple(deps))
@@ -231,7 +239,7 @@ class BackwardBuilder(object):
 
     def conv_dgrad_op(self, name, module, wd, src, dx, k, pad, dil, deps=(), **kw):
         self.ops.append(engine.op_conv(src, wd, dx, k, k, 1, pad, dil, consts=self.dgrad_consts(name, module, wd, deps),
-                                       scaled_out=self.scaled, **kw))
+                                       scaled_out=self.scaled, groups=module.groups if GROUPED_DGRAD else 1, **kw))
 
     def dgrad(self, name, module, scale, g, in_shape, residual=None, coarse=None, mask=None, deps=()):
         """Gradient w.r.t. the input (shape `in_shape`, NHWC) of conv `module` given g = dL/d(BN(conv))."""
@@ -287,7 +295,8 @@ class BackwardBuilder(object):
                                             lambda out, w_ab=w_ab: engine.bound_consts(w_ab, None, None, out=out),
                                             deps=(module.weight,) + tuple(deps))
                 part = self.new_act((n, hc + 2 * pad - kh + 1, wc + 2 * pad - kw + 1, cin))
-                self.ops.append(engine.op_conv(g, w_ab, part, kh, kw, 1, pad, 1, consts=consts, scaled_out=self.scaled))
+                self.ops.append(engine.op_conv(g, w_ab, part, kh, kw, 1, pad, 1, consts=consts, scaled_out=self.scaled,
+                                               groups=module.groups if GROUPED_DGRAD else 1))
                 parts.append(part)
         dx = self.new_act(in_shape)
         self.ops.append(engine.op_parity_merge(parts, dx, hc, wc, mask=mask, scaled_out=self.scaled))
@@ -300,10 +309,13 @@ class BackwardBuilder(object):
         k = module.kernel_size[0]
         cout, cin = module.out_channels, module.in_channels
         stride, pad, dil = module.stride[0], module.padding[0], module.dilation[0]
+        if module.groups > 1 and k == 1:
+            raise NotImplementedError("wgrad of a grouped 1x1 conv")
         if k == 1:
             self.ops.append(engine.op_wgrad(x, g, dst, 1, 1, stride, pad, dil, scale=scale))
         else:
-            self.acc_jobs.append((len(self.ops), name, cout, cin, k, stride, pad, dil, scale, x, g, dst))
+            # (a grouped conv accumulates its DENSE weight gradient; the unpack keeps the block diagonal)
+            self.acc_jobs.append((len(self.ops), name, cout, cin, k, stride, pad, dil, scale, x, g, dst, module.groups))
             self.ops.append(None)  # placeholder: resolved once the accumulator workspace exists
             self.ops.append(None)
 
@@ -315,14 +327,17 @@ class BackwardBuilder(object):
             self.acc_ws = torch.zeros(total, dtype=torch.float32, device=self.device)
             head.append(engine.op_zero(self.acc_ws))
             off = 0
-            for (idx, name, cout, cin, k, stride, pad, dil, scale, x, g, dst) in self.acc_jobs:
+            for (idx, name, cout, cin, k, stride, pad, dil, scale, x, g, dst, groups) in self.acc_jobs:
                 n = cout * cin * k * k
                 acc = self.acc_ws[off:off + n]
                 off += n
                 self.ops[idx] = engine.op_wgrad(x, g, acc, k, k, stride, pad, dil, scale=scale)
-                self.ops[idx + 1] = engine.op_dw_unpack(acc, dst, cout, cin, k, k)
+                self.ops[idx + 1] = engine.op_dw_unpack(acc, dst, cout, cin, k, k, groups=groups)
         return head + self.ops, len(head)
 
+
+# dgrad of a grouped conv as a grouped conv (64-channel band kernel); 0 = dense over the block-diagonal operand
+GROUPED_DGRAD = __import__("os").environ.get("TDET_GROUPED_DGRAD", "1") != "0"
 
 # stride-2 3x3 dgrad as four parity-class convs (default) instead of a 3x3 conv over the zero-inserted gradient
 S2_DGRAD_PARITY = __import__("os").environ.get("TDET_S2_DGRAD", "parity").lower() != "dilate"
