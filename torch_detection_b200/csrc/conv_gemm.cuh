@@ -52,6 +52,7 @@ constexpr int kBK = 64;          // 16-bit elements per 128-byte swizzle row
 constexpr int kUmmaK = 16;       // K per tcgen05.mma for 16-bit operands
 constexpr int kGemmThreads = 384;       // 12 warps; warp 11 is the B producer of the patch mode
 constexpr int kGemmThreadsNoPatch = 352; // 11 warps otherwise: 186 instead of 170 registers per thread
+constexpr int kGemmThreadsNG4 = 608;     // 3 role warps + 16 epilogue warps (four groups): 104 registers per thread
 constexpr int kEpiThreads = 256;         // 8 epilogue warps: two warps per TMEM lane quadrant
 constexpr int kABytes = kBM * kBK * 2;   // 16 KiB per stage
 constexpr int kSlabBytes = kBM * 128;    // 128 rows x 64 columns x 2 B (one swizzle-128B slab)
@@ -154,13 +155,15 @@ struct ConvGemmParams {
   const TensorMeta* in2_meta;     // nullable
 };
 
-// BRES_KB > 0: the whole weight panel (up to BRES_KB k-blocks; requires a single n-tile) is loaded
-// once per CTA and stays resident in shared memory; only A tiles stream through the ring.
+// BRES_KB > 0: the whole weight panel of the CTA's n-tile (up to BRES_KB k-blocks; one n-tile, or a grid that is a
+// multiple of the number of n-tiles so that a CTA never changes its n-tile) is loaded once per CTA and stays resident
+// in shared memory; only A tiles stream through the ring.
 // PATCH: A_PATCH pipeline (A ring of kPatchStages halo patches; STAGES then counts B tiles).
 // OSLABS: staging slabs per epilogue group (1: a group's stores serialise with its next slab; 2: double
 // buffered).
 // PAIR: CTA pair (cta_group::2): each CTA stages only its half of the weight tile's N rows.
-template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool PAIR = false>
+// NG: epilogue groups (2, or 4 = one group per 64-column slab of a 256-wide tile).
+template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool PAIR = false, int NG = 2>
 struct GemmSmem {
   static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 2;
   static constexpr int kBSlots = BRES_KB > 0 ? BRES_KB : STAGES;
@@ -169,7 +172,7 @@ struct GemmSmem {
   static constexpr int kBOffset = kAStages * kAStageBytes;
   static constexpr int kResOffset = kBOffset + kBSlots * kBBytes;
   static constexpr int kOutOffset = kResOffset + RES_SLABS * kSlabBytes;
-  static constexpr int kBarOffset = kOutOffset + 2 * OSLABS * kSlabBytes;
+  static constexpr int kBarOffset = kOutOffset + NG * OSLABS * kSlabBytes;
   // the coarse-staging variants (BN 256, ring of 1 or 2 slabs) cut each slab into quarter-size slots
   static constexpr bool kCoarseRing = BN == 256 && !PATCH && !PAIR && OSLABS == 1 && (RES_SLABS == 1 || RES_SLABS == 2);
   static constexpr int kRingBars = kCoarseRing ? kRingSplit * RES_SLABS : (RES_SLABS > 0 ? RES_SLABS : 1);
@@ -178,8 +181,8 @@ struct GemmSmem {
   static constexpr int kParamOffset = (kTmemPtrOffset + 16 + 15) / 16 * 16;
   // scale/shift per epilogue group: a group only touches the columns of its own slabs (half of BN),
   // except for one-slab tiles where the groups alternate tiles
-  static constexpr int kGroupCols = BN == 64 ? 64 : BN / 2;
-  static constexpr int kDynamic = kParamOffset + 2 * 2 * kGroupCols * 4;
+  static constexpr int kGroupCols = BN == 64 ? 64 : BN / NG;
+  static constexpr int kDynamic = kParamOffset + NG * 2 * kGroupCols * 4;
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
 };
 
@@ -222,13 +225,29 @@ constexpr int kPoolStep = 56;  // pooled columns per strip
 #define TDET_MMA_SINGLE_THREAD 0
 #endif
 
+// NG = 4 (256-wide tiles of the short-K 1x1 convs: conv3 + residual, dual-source conv3, FPN laterals): FOUR epilogue
+// groups, one per 64-column slab, and 16-column conversion steps so that 19 warps fit the register file.  Those
+// kernels are bound by their epilogue -- ~12 000 warp instructions per 128 x 256 tile at 41 % issue utilisation with
+// eight warps (ncu, layer3 conv3: 8 600 cycles per tile against ~1 000 of MMA) -- not by the tensor pipe or HBM.
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
+
 template <int BN, int STAGES, int RES_SLABS, int BRES_KB, bool PATCH, int OSLABS, bool MASKED, bool SPLIT = false,
-          bool PAIR = false, bool POOL = false>
-__global__ void __launch_bounds__(PATCH ? kGemmThreads : kGemmThreadsNoPatch, 1)
+          bool PAIR = false, bool POOL = false, int NG = 2>
+__global__ void __launch_bounds__(NG == 4 ? kGemmThreadsNG4 : (PATCH ? kGemmThreads : kGemmThreadsNoPatch), 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  static_assert(NG == 2 || (NG == 4 && BN == 256 && !PATCH && !SPLIT && !POOL && !PAIR),
+                "four epilogue groups: 256-wide tiles, tiled / spatial A, one CTA");
+  constexpr int kEW = NG == 4 ? 16 : 32;   // accumulator columns converted per step
+  constexpr int kEJ = kEW / 8;             // 16-byte chunks per step
+  constexpr int kParts = 64 / kEW;         // steps per 64-column slab
   static_assert(!POOL || (BN == 64 && BRES_KB > 0 && !PATCH && !SPLIT && !PAIR && !MASKED && RES_SLABS == 0),
                 "POOL: the stem kernel only");
-  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, PAIR>;
+  using L = GemmSmem<BN, STAGES, RES_SLABS, BRES_KB, PATCH, OSLABS, PAIR, NG>;
   static_assert(!PAIR || (BN >= 128 && BRES_KB == 0 && !SPLIT), "CTA pairs: streamed weight tiles, 128/256 wide");
   // Split precision keeps TWO accumulators per tile: hi*hi in one, the small cross terms lo*hi + hi*lo in the
   // other, summed in fp32 by the epilogue.  tcgen05's fp32 accumulation is not exact -- measured ~0.17 ulp of
@@ -292,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       // one arrive per warp draining buffer a (the leader's barrier collects both CTAs of a pair)
-      mbar_init(tempty_bar(a), ((kSlabsPerTile == 1 && !POOL) ? 4 : 8) * (PAIR ? 2 : 1));
+      mbar_init(tempty_bar(a), ((kSlabsPerTile == 1 && !POOL) ? 4 : 4 * NG) * (PAIR ? 2 : 1));
     }
     for (int s = 0; s < kRB; ++s) {
       mbar_init(rfull_bar(s), 1);
@@ -359,9 +378,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int stage = 0;
     uint32_t phase = 0;
     if (BRES_KB > 0 && lane == 0) {
+      // (several n-tiles: the host sizes the grid to a multiple of their number, so that every tile of this CTA
+      // belongs to n-tile tile0 % num_n_tiles and its weight panel can stay resident)
+      const int n_res = (tile0 % p.num_n_tiles) * BN;
       mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.num_kb_b) * L::kBBytes);
       for (int kb = 0; kb < p.num_kb_b; ++kb)
-        tma_load_2d(smem_b + kb * L::kBBytes, &p.tmap_b, bres_bar, kb * kBK, 0);
+        tma_load_2d(smem_b + kb * L::kBBytes, &p.tmap_b, bres_bar, kb * kBK, n_res);
     }
     const uint32_t stage_tx = static_cast<uint32_t>(p.a_stage_bytes) + (BRES_KB > 0 ? 0u : L::kBBytes);
     if (PATCH) {
@@ -704,7 +726,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     }
-  } else if (warp == 11) {
+  } else if (PATCH && warp == 11) {
     // ------------------------------------------------------------------ TMA producer (B, patch mode)
     if (PATCH && BRES_KB == 0) {
       int stage = 0;
@@ -735,7 +757,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ------------------------------------------------------------------ epilogue (warps 3..10)
     const int quad = warp & 3;             // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;      // accumulator row == TMEM lane == staging row
-    const int group = (warp - 3) >> 2;     // epilogue group: slabs (or tiles) with index % 2 == group
+    const int group = (warp - 3) >> 2;     // epilogue group: slabs (or tiles) with index % NG == group
     constexpr bool kByTile = kSlabsPerTile == 1;
     const int gtid = (threadIdx.x - 96) & (kEpiGroupThreads - 1);
     const uint32_t gbar = 1u + group;      // the group's named barrier
@@ -906,7 +928,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         named_bar_sync(gbar, kEpiGroupThreads);
         for (int i = gtid; i < L::kGroupCols; i += kEpiGroupThreads) {
           // local column i of this group = column (i & 63) of its (i >> 6)-th slab
-          const int col = kByTile ? i : (((i >> 6) * 2 + group) * 64 + (i & 63));
+          const int col = kByTile ? i : (((i >> 6) * NG + group) * 64 + (i & 63));
           s_scale[i] = (p.scale ? __ldg(p.scale + n0 + col) : 1.0f) * mul_in;
           s_shift[i] = (p.shift ? __ldg(p.shift + n0 + col) : 0.0f) * mul_shift;
         }
@@ -965,7 +987,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                               static_cast<uint32_t>(acc * kAccStride);
 #pragma unroll 1
-      for (int slab = kByTile ? 0 : group; slab < kSlabsPerTile; slab += kByTile ? 1 : 2) {
+      for (int slab = kByTile ? 0 : group; slab < kSlabsPerTile; slab += kByTile ? 1 : NG) {
         // residual slabs are produced in tile order into one ring shared by both groups; consecutive
         // slabs of a group are two ring positions apart, so with any ring depth >= 2 the previous fill of
         // a slot has completed before the group waits for the next one (no parity aliasing)
@@ -1001,52 +1023,52 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
         const uint32_t mk_row = smem_res + ms * kSlabBytes + row * 128;
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + slab * 64 + half * 32, v);
-          uint4 rco[4];
+        for (int half = 0; half < kParts; ++half) {   // (a 32- or 16-column step of the slab)
+          uint32_t v[kEW];
+          tmem_ld_cols<kEW>(t_addr + slab * 64 + half * kEW, v);
+          uint4 rco[kEJ];
           if (coarse_row) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * 32 + j * 8) * 2);
+            for (int j = 0; j < kEJ; ++j) rco[j] = ldg_nc_v4(coarse_row + (slab * 64 + half * kEW + j * 8) * 2);
           }
-          uint4 rmk[4];
+          uint4 rmk[kEJ];
           if (!MASKED) {
           } else if (mask_tma) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t a = mk_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+            for (int j = 0; j < kEJ; ++j) {
+              const uint32_t a = mk_row + (((half * kEJ + j) ^ (row & 7)) << 4);
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(rmk[j].x), "=r"(rmk[j].y), "=r"(rmk[j].z), "=r"(rmk[j].w)
                            : "r"(a));
             }
           } else if (mask_row) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rmk[j] = ldg_nc_v4(mask_row + (slab * 64 + half * 32 + j * 8) * 2);
+            for (int j = 0; j < kEJ; ++j) rmk[j] = ldg_nc_v4(mask_row + (slab * 64 + half * kEW + j * 8) * 2);
           }
-          uint4 rres[4];
+          uint4 rres[kEJ];
           if (has_res) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t a = res_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+            for (int j = 0; j < kEJ; ++j) {
+              const uint32_t a = res_row + (((half * kEJ + j) ^ (row & 7)) << 4);
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(rres[j].x), "=r"(rres[j].y), "=r"(rres[j].z), "=r"(rres[j].w)
                            : "r"(a));
             }
           }
           tmem_ld_wait();
-          float x[32];
+          float x[kEW];
           if (SPLIT && split) {
             // main (hi*hi) + cross (lo*hi + hi*lo) accumulators, summed in fp32
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
-            tmem_ld_32x32b_x32(t_addr + BN + slab * 64 + half * 32, v);
+            for (int i = 0; i < kEW; ++i) x[i] = __uint_as_float(v[i]);
+            tmem_ld_cols<kEW>(t_addr + BN + slab * 64 + half * kEW, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(x[i] + __uint_as_float(v[i]));
+            for (int i = 0; i < kEW; ++i) v[i] = __float_as_uint(x[i] + __uint_as_float(v[i]));
           }
-          const int cb = (kByTile ? slab : (slab >> 1)) * 64 + half * 32;  // group-local column
+          const int cb = (kByTile ? slab : (slab / NG)) * 64 + half * kEW;  // group-local column
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kEW / 4; ++j) {
             const float4 sc = *reinterpret_cast<const float4*>(s_scale + cb + j * 4);
             const float4 sh = *reinterpret_cast<const float4*>(s_shift + cb + j * 4);
             x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
@@ -1056,7 +1078,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           if (has_res) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kEJ; ++j) {
               const uint32_t w4[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -1069,8 +1091,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (SPLIT && split) {
               // lo half of the residual pair (next ring slot)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t a = mk_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+              for (int j = 0; j < kEJ; ++j) {
+                const uint32_t a = mk_row + (((half * kEJ + j) ^ (row & 7)) << 4);
                 uint4 r2;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(r2.x), "=r"(r2.y), "=r"(r2.z), "=r"(r2.w)
@@ -1086,7 +1108,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           if (coarse_row) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kEJ; ++j) {
               const uint32_t w4[4] = {rco[j].x, rco[j].y, rco[j].z, rco[j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -1098,8 +1120,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
             if (SPLIT && split) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 c2 = ldg_nc_v4(coarse_row + (p.N + slab * 64 + half * 32 + j * 8) * 2);
+              for (int j = 0; j < kEJ; ++j) {
+                const uint4 c2 = ldg_nc_v4(coarse_row + (p.N + slab * 64 + half * kEW + j * 8) * 2);
                 const uint32_t w4[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -1112,8 +1134,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (crow >= 0) {
             const uint32_t cbase = smem_res + rs * rslot + crow * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t a = cbase + ((((half << 2) | j) ^ (crow & 7)) << 4);
+            for (int j = 0; j < kEJ; ++j) {
+              const uint32_t a = cbase + (((half * kEJ + j) ^ (crow & 7)) << 4);
               uint4 c4;
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(c4.x), "=r"(c4.y), "=r"(c4.z), "=r"(c4.w)
@@ -1130,15 +1152,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+            for (int i = 0; i < kEW; ++i) x[i] = fmaxf(x[i], 0.0f);
             if (p.relu == 2) {   // ReLU6 (plain outputs only: x is the true value)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = fminf(x[i], 6.0f);
+              for (int i = 0; i < kEW; ++i) x[i] = fminf(x[i], 6.0f);
             }
           }
           if (MASKED && (mask_tma ? valid : (mask_row != nullptr))) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < kEJ; ++j) {
               const uint32_t w4[4] = {rmk[j].x, rmk[j].y, rmk[j].z, rmk[j].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -1150,16 +1172,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
           if (valid && p.out_meta) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) amax_local = fmaxf(amax_local, fabsf(x[i]));
+            for (int i = 0; i < kEW; ++i) amax_local = fmaxf(amax_local, fabsf(x[i]));
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kEJ; ++j) {
             uint4 o;
             o.x = pack16x2(x[8 * j + 0], x[8 * j + 1], out_fp16);
             o.y = pack16x2(x[8 * j + 2], x[8 * j + 3], out_fp16);
             o.z = pack16x2(x[8 * j + 4], x[8 * j + 5], out_fp16);
             o.w = pack16x2(x[8 * j + 6], x[8 * j + 7], out_fp16);
-            const uint32_t a = out_row + ((((half << 2) | j) ^ (row & 7)) << 4);
+            const uint32_t a = out_row + (((half * kEJ + j) ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y),
                          "r"(o.z), "r"(o.w)
                          : "memory");
@@ -1176,7 +1198,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             }
           }
         }
-        if (slab + (kByTile ? 1 : 2) >= kSlabsPerTile) {
+        if (slab + (kByTile ? 1 : NG) >= kSlabsPerTile) {
           // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();

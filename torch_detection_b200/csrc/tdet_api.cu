@@ -134,6 +134,7 @@ struct Launch {
   bool pair = false;      // CTA-pair kernel (clusters of 2)
   bool pool = false;      // stem kernel with the fused max-pool
   bool swap = false;      // operand-swapped kernel for Cout <= 128 (conv_swap.cuh)
+  bool ng4 = false;       // four epilogue groups (conv_gemm_kernel<..., NG = 4>): short-K 256-wide forward convs
   bool no_patch = false;  // debugging hook: force the im2col loader
   // fused bottleneck tail
   FbParams fb{};
@@ -279,6 +280,21 @@ int launch_gemm_m(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
                     PATCH ? kGemmThreads : kGemmThreadsNoPatch, L::kDynamic, st, gp);
 }
 
+// four epilogue groups (NG = 4): forward-only 256-wide instantiations
+template <int STAGES, int RES_SLABS, int BRES_KB, int OSLABS>
+int launch_gemm_ng4(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
+  using L = GemmSmem<256, STAGES, RES_SLABS, BRES_KB, false, OSLABS, false, 4>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  TDET_CUDA(cudaGetDevice(&dev));
+  auto kernel = conv_gemm_kernel<256, STAGES, RES_SLABS, BRES_KB, false, OSLABS, false, false, false, false, 4>;
+  if (!attr_set[dev]) {
+    TDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
+    attr_set[dev] = true;
+  }
+  return launch_pdl(kernel, grid, kGemmThreadsNG4, L::kDynamic, st, gp);
+}
+
 template <int BN, int STAGES, int RES_SLABS>
 int launch_gemm_split(const ConvGemmParams& gp, dim3 grid, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, RES_SLABS, 0, false, 2>;
@@ -401,6 +417,16 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     return fail(TDET_ERR_INVALID_ARGUMENT, "no patch-mode GEMM instantiation for tile %d/%d/%d/%d", l.bn,
                 l.stages, l.res_slabs, l.bres_kb);
   }
+  if (l.ng4) {
+    switch (vkey(l.bn, l.stages, l.res_slabs, l.bres_kb, l.oslabs)) {
+      case vkey(256, 2, 3, 0, 1): return launch_gemm_ng4<2, 3, 0, 1>(l.gp, l.grid, st);   // conv3 + residual
+      case vkey(256, 3, 0, 0, 1): return launch_gemm_ng4<3, 0, 0, 1>(l.gp, l.grid, st);   // 1x1 without ring operands
+      case vkey(256, 2, 0, 4, 1): return launch_gemm_ng4<2, 0, 4, 1>(l.gp, l.grid, st);   // resident weights (dual conv3)
+      case vkey(256, 2, 2, 0, 1): return launch_gemm_ng4<2, 2, 0, 1>(l.gp, l.grid, st);   // coarse ring (FPN lateral)
+    }
+    return fail(TDET_ERR_INVALID_ARGUMENT, "no 4-group GEMM instantiation for tile %d/%d/%d/%d/%d", l.bn, l.stages,
+                l.res_slabs, l.bres_kb, l.oslabs);
+  }
   switch (vkey(l.bn, l.stages, l.res_slabs, l.bres_kb, l.oslabs)) {
     // streaming weights
     case vkey(64, 6, 2, 0, 1): return launch_gemm_t<64, 6, 2, 0, false, 1>(l.gp, l.grid, st);
@@ -429,6 +455,8 @@ int launch_gemm(const Launch& l, cudaStream_t st) {
     case vkey(256, 4, 0, 4, 1): return launch_gemm_t<256, 4, 0, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 3, 1, 4, 1): return launch_gemm_t<256, 3, 1, 4, false, 1>(l.gp, l.grid, st);
     case vkey(256, 2, 0, 4, 2): return launch_gemm_t<256, 2, 0, 4, false, 2>(l.gp, l.grid, st);
+    case vkey(256, 4, 3, 2, 1): return launch_gemm_t<256, 4, 3, 2, false, 1>(l.gp, l.grid, st);   // resident panel, K <= 128
+    case vkey(256, 2, 2, 4, 1): return launch_gemm_t<256, 2, 2, 4, false, 1>(l.gp, l.grid, st);   // resident panel, K <= 256
   }
   return fail(TDET_ERR_INVALID_ARGUMENT, "no GEMM instantiation for tile %d/%d/%d/%d/%d", l.bn, l.stages,
               l.res_slabs, l.bres_kb, l.oslabs);
@@ -758,6 +786,18 @@ int build_conv(Launch& l, const DeviceInfo& di) {
         l.res_slabs = 0; l.bres_kb = 4;
         if (vs & 64) { l.stages = 2; l.oslabs = 2; } else { l.stages = 4; l.oslabs = 1; }
       }
+    } else if (resident_b_enabled() && !split && !grouped && !dual && l.bn == 256 && gp.num_n_tiles > 1 &&
+               (di.num_sms - di.sm_reserve) % gp.num_n_tiles == 0 && !o.mask && !o.coarse &&
+               gp.num_m_tiles * gp.num_n_tiles >= 4 * di.num_sms && (env_int("TDET_BRES_MULTI", 0) & 1)) {
+      // Several n-tiles, short K (conv3 of a bottleneck: 128 -> 512, 256 -> 1024): with a grid that is a multiple
+      // of the number of n-tiles every CTA keeps ONE n-tile, so its weight panel stays resident instead of being
+      // streamed again for every 128-row tile (a 256 x 256 panel is twice the bytes of the A tile it multiplies).
+      // OFF by default (TDET_BRES_MULTI bit 1: K <= 128, bit 2: K <= 256): measured on R50 batch 16, K = 128 gains
+      // 2 % per launch timed alone and LOSES 0.7 % of the whole step (the panel load lengthens the prologue that
+      // overlaps the previous kernel); K = 256 leaves room for two A stages only and is 50 % slower.
+      const int bm = env_int("TDET_BRES_MULTI", 0);
+      if (gp.num_kb_b <= 2 && naux == 1) { l.bres_kb = 2; l.stages = 4; l.res_slabs = 3; l.oslabs = 1; }
+      else if (gp.num_kb_b <= 4 && naux == 1 && (bm & 2)) { l.bres_kb = 4; l.stages = 2; l.res_slabs = 2; l.oslabs = 1; }
     }
   }
 
@@ -807,6 +847,22 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     if (l.bn == 256) l.stages = 6;
   }
 
+  // Short-K 256-wide 1x1 convs (conv3 + residual, dual-source conv3, no-operand 1x1, FPN laterals) are bound by
+  // their EPILOGUE (ncu: 41 % issue utilisation with eight epilogue warps, ~8 600 cycles per 128 x 256 tile against
+  // ~1 000 of MMA): they run with FOUR epilogue groups -- one per 64-column slab, 16 warps, 16-column conversion steps
+  // -- and a ring one stage shorter to pay for the two extra staging slabs.  TDET_EPI4=0 switches back.
+  l.ng4 = false;
+  if (env_int("TDET_EPI4", 1) && l.bn == 256 && !l.patch && !l.pair && !l.swap && !split && !grouped && !o.mask &&
+      gp.num_kb_b <= 8 && l.oslabs == 1 && (!o.coarse || spatial)) {
+    // (measured per launch, R50 batch 16: resident weights -27 us; the streamed-weight variants LOSE 4-29 us each to
+    // the ring stage the extra staging slabs cost -- bit 2 of TDET_EPI4 enables them anyway)
+    const int e4 = env_int("TDET_EPI4", 1);
+    if (!spatial && l.bres_kb == 4 && naux == 0 && l.res_slabs == 0 && l.stages == 4) { l.ng4 = true; l.stages = 2; }
+    else if (!(e4 & 2)) {}
+    else if (spatial && l.bres_kb == 0 && l.res_slabs == 2) { l.ng4 = true; l.stages = 2; }
+    else if (!spatial && l.bres_kb == 0 && naux == 1 && l.res_slabs == 3) { l.ng4 = true; l.stages = 2; }
+    else if (!spatial && l.bres_kb == 0 && naux == 0 && l.res_slabs == 0 && l.stages == 4) { l.ng4 = true; l.stages = 3; }
+  }
   {
     const int nload = (o.residual ? 1 : 0) + 1;
     gp.mask_tma = (o.mask && l.res_slabs >= 2 * nload) ? 1 : 0;
