@@ -321,23 +321,27 @@ def _tail_reference(x, xres, w2, w3, w1n, bn2, bn3, bn1n, dtype, ydtype):
 
 @pytest.mark.parametrize("shape", [(2, 24, 40), (1, 50, 84), (3, 100, 84), (2, 37, 29)],
                          ids=["2x24x40", "1x50x84", "3x100x84_many_tiles", "2x37x29_ragged"])
-@pytest.mark.parametrize("fuse_next", [True, False], ids=["next_conv1", "tail_only"])
+@pytest.mark.parametrize("variant", ["next_conv1", "tail_only", "planes128"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
-def test_bottleneck_tail(cuda_device, shape, fuse_next, dtype):
+def test_bottleneck_tail(cuda_device, shape, variant, dtype):
     """TDET_OP_BOTTLENECK_TAIL: conv2 3x3 -> conv3 1x1 + residual + ReLU (-> the next block's conv1) of a layer1
-    bottleneck (resnet.py:101-118) in one kernel, against fp32 convs of the same rounded operands."""
+    bottleneck (planes = 64) or a layer2 bottleneck (planes = 128, tail only) (resnet.py:101-118) in one kernel, against
+    fp32 convs of the same rounded operands."""
     from torch_detection_b200 import engine
     dev = cuda_device
     n, h, w = shape
+    fuse_next = variant == "next_conv1"
+    pl = 128 if variant == "planes128" else 64
     g = torch.Generator().manual_seed(h * w + n)
-    x = _nhwc(torch.randn(n, 64, h, w, generator=g).to(dev), dtype)
-    xres = _nhwc(torch.randn(n, 256, h, w, generator=g).to(dev), dtype)
-    w2 = (torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5).to(dev)
-    w3 = (torch.randn(256, 64, 1, 1, generator=g) * (2.0 / 64) ** 0.5).to(dev)
-    w1n = (torch.randn(64, 256, 1, 1, generator=g) * (2.0 / 256) ** 0.5).to(dev)
-    bns = [((0.5 + torch.rand(c, generator=g)).to(dev), (0.3 * torch.randn(c, generator=g)).to(dev)) for c in (64, 256, 64)]
-    y = engine.nhwc_empty(n, h, w, 256, dev, dtype)
-    y2 = engine.nhwc_empty(n, h, w, 64, dev, dtype)
+    x = _nhwc(torch.randn(n, pl, h, w, generator=g).to(dev), dtype)
+    xres = _nhwc(torch.randn(n, 4 * pl, h, w, generator=g).to(dev), dtype)
+    w2 = (torch.randn(pl, pl, 3, 3, generator=g) * (2.0 / (9 * pl)) ** 0.5).to(dev)
+    w3 = (torch.randn(4 * pl, pl, 1, 1, generator=g) * (2.0 / pl) ** 0.5).to(dev)
+    w1n = (torch.randn(pl, 4 * pl, 1, 1, generator=g) * (2.0 / (4 * pl)) ** 0.5).to(dev)
+    bns = [((0.5 + torch.rand(c, generator=g)).to(dev), (0.3 * torch.randn(c, generator=g)).to(dev))
+           for c in (pl, 4 * pl, pl)]
+    y = engine.nhwc_empty(n, h, w, 4 * pl, dev, dtype)
+    y2 = engine.nhwc_empty(n, h, w, pl, dev, dtype)
     y2.zero_()
     nxt = dict(w=engine.pack_conv_weight(w1n, dtype), bn=bns[2], y=engine.act_of(y2)) if fuse_next else None
     op = engine.op_bottleneck_tail(engine.act_of(x), engine.pack_conv_weight(w2, dtype), engine.act_of(y),
@@ -346,7 +350,7 @@ def test_bottleneck_tail(cuda_device, shape, fuse_next, dtype):
     torch.cuda.synchronize()
     ref_y, ref_y2 = _tail_reference(x, xres, w2, w3, w1n if fuse_next else None, bns[0], bns[1], bns[2], dtype, dtype)
     err = rel_l2(y.float(), ref_y)
-    print("bottleneck tail %s %s next=%s: y rel-L2 %.3e" % (shape, dtype, fuse_next, err))
+    print("bottleneck tail %s %s %s: y rel-L2 %.3e" % (shape, dtype, variant, err))
     assert err <= TOL[dtype], "y rel-L2 %.3e" % err
     if fuse_next:
         # y2 is computed from the kernel's own 16-bit y: reference it on that
@@ -354,15 +358,23 @@ def test_bottleneck_tail(cuda_device, shape, fuse_next, dtype):
         err2 = rel_l2(y2.float(), ref2)
         assert err2 <= TOL[dtype], "y2 rel-L2 %.3e" % err2
         assert rel_l2(y2.float(), ref_y2) <= 3 * TOL[dtype]
-    # the op equals the three unfused launches bit for bit (same arithmetic, same rounding points)
-    z2 = engine.nhwc_empty(n, h, w, 64, dev, dtype)
-    yb = engine.nhwc_empty(n, h, w, 256, dev, dtype)
+    # planes = 64: the op equals the unfused launches bit for bit (same arithmetic, same k-block order, same rounding
+    # points).  planes = 128: the unfused conv2 runs on the operand-swapped kernel, whose k-block order depends on the
+    # loader the shape selects (tap-major im2col vs chunk-major halo patch), so fp32 accumulation may round
+    # differently: a handful of 1-ulp flips of the 16-bit result are allowed, nothing more.
+    z2 = engine.nhwc_empty(n, h, w, pl, dev, dtype)
+    yb = engine.nhwc_empty(n, h, w, 4 * pl, dev, dtype)
     engine.run_op(engine.op_conv(engine.act_of(x), engine.pack_conv_weight(w2, dtype), engine.act_of(z2), 3, 3, 1, 1, 1,
                                  scale=bns[0][0], shift=bns[0][1], relu=True), dev)
     engine.run_op(engine.op_conv(engine.act_of(z2), engine.pack_conv_weight(w3, dtype), engine.act_of(yb), 1, 1, 1, 0, 1,
                                  scale=bns[1][0], shift=bns[1][1], residual=engine.act_of(xres), relu=True), dev)
     torch.cuda.synchronize()
-    assert torch.equal(y, yb), "fused tail differs from conv2 -> conv3 + residual launched separately"
+    nd = int((y != yb).sum())
+    print("  differing elements vs the unfused pair: %d (max |diff| %.3e)" % (nd, float((y.float() - yb.float()).abs().max())))
+    if pl == 64:
+        assert torch.equal(y, yb), "fused tail differs from conv2 -> conv3 + residual launched separately"
+    else:
+        assert nd <= 1e-2 * y.numel() and rel_l2(y.float(), yb.float()) <= 0.1 * TOL[dtype]
 
 
 def test_bottleneck_tail_scaled(cuda_device):

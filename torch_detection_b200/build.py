@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(CSRC, "libtdet_b200.so")
 SOURCES = ["tdet_api.cu"]
-HEADERS = ["conv_gemm.cuh", "conv_swap.cuh", "bottleneck_fused.cuh", "wgrad_gemm.cuh", "aux_kernels.cuh", "ptx_sm100.cuh",
+HEADERS = ["conv_gemm.cuh", "conv_swap.cuh", "bottleneck_fused.cuh", "bottleneck_tail2.cuh", "wgrad_gemm.cuh", "aux_kernels.cuh", "ptx_sm100.cuh",
            os.path.join("..", "..", "include", "tdet_b200.h")]
 
 NVCC_FLAGS = [

@@ -18,6 +18,7 @@
 #include "wgrad_gemm.cuh"
 #include "conv_swap.cuh"
 #include "bottleneck_fused.cuh"
+#include "bottleneck_tail2.cuh"
 #include "aux_kernels.cuh"
 
 namespace {
@@ -139,6 +140,8 @@ struct Launch {
   // fused bottleneck tail
   FbParams fb{};
   int fb_n3 = 0;
+  T2Params t2{};          // planes = 128 variant (bottleneck_tail2.cuh)
+  bool fb_t2 = false;
   // wgrad
   WgradParams wp{};
   int wg_nb = 0, wg_pix = 0, wg_mt = 1;
@@ -1268,11 +1271,119 @@ int launch_fb_t(const FbParams& fp, dim3 grid, cudaStream_t st) {
   return launch_pdl(bottleneck_tail_kernel<N3>, grid, kFbThreads, L::kDynamic, st, fp);
 }
 
+template <bool PAIR>
+int launch_t2_t(const T2Params& tp, dim3 grid, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  static int max_clusters[64] = {};
+  int dev = 0;
+  TDET_CUDA(cudaGetDevice(&dev));
+  auto kernel = bottleneck_tail2_kernel<PAIR>;
+  if (!attr_set[dev]) {
+    TDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem::kDynamic));
+    if (PAIR) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * 74, 1, 1);
+      cfg.blockDim = dim3(kFbThreads, 1, 1);
+      cfg.dynamicSmemBytes = T2Smem::kDynamic;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      TDET_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+      if (n < 1) return fail(TDET_ERR_DRIVER, "no CTA pair of the bottleneck tail kernel fits on device %d", dev);
+      max_clusters[dev] = n;
+    }
+    attr_set[dev] = true;
+  }
+  if (PAIR && grid.x > 2u * static_cast<unsigned>(max_clusters[dev])) grid.x = 2u * static_cast<unsigned>(max_clusters[dev]);
+  return launch_pdl(kernel, grid, kFbThreads, T2Smem::kDynamic, st, tp, PAIR ? 2 : 1);
+}
+
+// planes = 128 (layer2): 128 -> 128 (3x3) -> 512 (1x1) + residual, tail only
+int build_bottleneck_tail2(Launch& l, const DeviceInfo& di) {
+  const tdet_op& o = l.op;
+  if (o.wgt3 || o.cout3 != 0)
+    return fail(TDET_ERR_UNSUPPORTED_SHAPE, "bottleneck tail (planes = 128): no next-conv1 fusion");
+  if (o.kh != 3 || o.kw != 3 || o.stride != 1 || o.pad != 1 || o.dil != 1 || o.ho != o.h || o.wo != o.w)
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: conv2 must be 3x3 / stride 1 / pad 1");
+  if (!o.x || !o.wgt || !o.wgt2 || !o.y || !o.residual)
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: null tensor pointer");
+  if (!is16(o.x_dtype) || !is16(o.y_dtype) || !is16(o.residual_dtype))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: 16-bit tensors only");
+  if (o.coarse || o.mask || o.groups > 1 || (o.flags & (TDET_FLAG_SPLIT | TDET_FLAG_DUAL | TDET_FLAG_COARSE_PARITY)))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: no coarse / mask / groups / split / dual operands");
+  const bool out_scaled = (o.flags & TDET_FLAG_SCALED_OUT) != 0;
+  const bool z2_scaled = o.x_dtype == TDET_F16 && o.x_meta && o.bound_consts;
+  if (out_scaled && (o.y_dtype != TDET_F16 || !o.y_meta))
+    return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: a scaled output must be F16 with a meta");
+  if (out_scaled && (!o.bound_consts || !o.bound_consts2 || !o.x_meta || !o.residual_meta))
+    return fail(TDET_ERR_INVALID_ARGUMENT,
+                "bottleneck tail: scaled outputs need x_meta, residual_meta and the bound constants of every conv");
+  const long long m_ll = static_cast<long long>(o.n) * o.h * o.w;
+  if (m_ll <= 0 || m_ll > 0x7FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "M out of range");
+  T2Params& tp = l.t2;
+  memset(&tp, 0, sizeof(tp));
+  tp.H = o.h;
+  tp.W = o.w;
+  tp.N = o.n;
+  tp.tiles_w = (o.w + kPatchBW - 1) / kPatchBW;
+  tp.tiles_h = (o.h + kPatchBH - 1) / kPatchBH;
+  const long long tiles = static_cast<long long>(o.n) * tp.tiles_w * tp.tiles_h;
+  if (tiles > 0x3FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "too many tiles");
+  tp.num_tiles = static_cast<int>(tiles);
+  tp.x_fp16 = o.x_dtype == TDET_F16;
+  tp.out_fp16 = o.y_dtype == TDET_F16;
+  tp.res_fp16 = o.residual_dtype == TDET_F16;
+  tp.z2_scaled = z2_scaled ? 1 : 0;
+  tp.out_scaled = out_scaled ? 1 : 0;
+  tp.scale2 = o.scale; tp.shift2 = o.shift;
+  tp.scale3 = o.scale2; tp.shift3 = o.shift2;
+  tp.consts2 = o.bound_consts; tp.consts3 = o.bound_consts2;
+  tp.z1_meta = reinterpret_cast<const TensorMeta*>(o.x_meta);
+  tp.res_meta = reinterpret_cast<const TensorMeta*>(o.residual_meta);
+  tp.out_meta = reinterpret_cast<TensorMeta*>(o.y_meta);
+  tp.res_prefetch = env_int("TDET_TAIL_PREFETCH", 1);
+  tp.dbg = env_int("TDET_T2_DBG", 0);
+  tp.trace = reinterpret_cast<unsigned long long*>(o.dw);  // debugging aid: cycle trace of CTA 0 (NULL in normal runs)
+  int rc = encode_4d(&tp.tmap_z1, o.x, o.x_dtype, 128, o.w, o.h, o.n, kPatchPW, kPatchPH, "conv2 halo patch");
+  if (rc) return rc;
+  // CTA pairs (TDET_TAIL2_PAIR, default 1): every CTA stages its half of each weight block (64-row boxes)
+  const bool pair = env_int("TDET_TAIL2_PAIR", 1) != 0 && tp.num_tiles >= 2;
+  rc = encode_2d(&tp.tmap_w2, o.wgt, o.x_dtype, 9 * 128, 128, pair ? 64 : 128, "conv2 weights");
+  if (rc) return rc;
+  rc = encode_2d(&tp.tmap_w3, o.wgt2, o.x_dtype, 128, 512, pair ? 64 : 128, "conv3 weights");
+  if (rc) return rc;
+  rc = encode_4d(&tp.tmap_res, o.residual, o.residual_dtype, 512, o.w, o.h, o.n, kPatchBW, kPatchBH, "residual");
+  if (rc) return rc;
+  rc = encode_4d(&tp.tmap_out, o.y, o.y_dtype, 512, o.w, o.h, o.n, kPatchBW, kPatchBH, "block output");
+  if (rc) return rc;
+  int g = di.num_sms - di.sm_reserve;
+  if (pair) {
+    g &= ~1;
+    if (g > 2 * ((tp.num_tiles + 1) / 2)) g = 2 * ((tp.num_tiles + 1) / 2);
+  } else if (g > tp.num_tiles) {
+    g = tp.num_tiles;
+  }
+  l.grid = dim3(static_cast<unsigned>(g), 1, 1);
+  l.bn = 256;
+  l.fb_t2 = true;
+  l.pair = pair;
+  const double rows = static_cast<double>(m_ll);
+  l.flops = 2.0 * rows * (128.0 * 1152 + 512.0 * 128);
+  l.bytes = 2.0 * (rows * (128 + 512 + 512) + 128.0 * 1152 + 512.0 * 128);
+  return TDET_OK;
+}
+
 int build_bottleneck_tail(Launch& l, const DeviceInfo& di) {
   const tdet_op& o = l.op;
+  if (o.cin == 128 && o.cout2 == 128 && o.cout == 512) return build_bottleneck_tail2(l, di);
   if (o.cin != 64 || o.cout2 != 64 || o.cout != 256 || (o.wgt3 && o.cout3 != 64) || (!o.wgt3 && o.cout3 != 0))
     return fail(TDET_ERR_UNSUPPORTED_SHAPE,
-                "bottleneck tail: 64 -> 64 (3x3) -> 256 (1x1) [-> 64 (1x1)] only (got %d -> %d -> %d -> %d)", o.cin,
+                "bottleneck tail: 64 -> 64 (3x3) -> 256 (1x1) [-> 64 (1x1)] or 128 -> 128 -> 512 only (got %d -> %d -> %d -> %d)", o.cin,
                 o.cout2, o.cout, o.cout3);
   if (o.kh != 3 || o.kw != 3 || o.stride != 1 || o.pad != 1 || o.dil != 1 || o.ho != o.h || o.wo != o.w)
     return fail(TDET_ERR_INVALID_ARGUMENT, "bottleneck tail: conv2 must be 3x3 / stride 1 / pad 1");
@@ -1294,6 +1405,7 @@ int build_bottleneck_tail(Launch& l, const DeviceInfo& di) {
   const long long m_ll = static_cast<long long>(o.n) * o.h * o.w;
   if (m_ll <= 0 || m_ll > 0x7FFFFF00LL) return fail(TDET_ERR_UNSUPPORTED_SHAPE, "M out of range");
   FbParams& fp = l.fb;
+  l.fb_t2 = false;
   memset(&fp, 0, sizeof(fp));
   fp.H = o.h;
   fp.W = o.w;
@@ -1482,6 +1594,7 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
     case TDET_OP_CONV:
     case TDET_OP_STEM: return launch_gemm(l, st);
     case TDET_OP_BOTTLENECK_TAIL:
+      if (l.fb_t2) return l.pair ? launch_t2_t<true>(l.t2, l.grid, st) : launch_t2_t<false>(l.t2, l.grid, st);
       return l.fb_n3 ? launch_fb_t<64>(l.fb, l.grid, st) : launch_fb_t<0>(l.fb, l.grid, st);
     case TDET_OP_PREP: {
       const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
@@ -2144,10 +2257,10 @@ int tdet_plan_launch_info(const tdet_plan* plan, int index, tdet_launch_info* ou
     out->tile_n = 256;
     out->grid = static_cast<int32_t>(l.grid.x);
     out->a_mode = A_PATCH;
-    out->m = l.fb.num_tiles * kBM;
-    out->n = 256;
-    out->k = 576 + 64 + l.fb_n3 * 4;
-    out->variant = 32768 + l.fb_n3;
+    out->m = (l.fb_t2 ? l.t2.num_tiles : l.fb.num_tiles) * kBM;
+    out->n = l.fb_t2 ? 512 : 256;
+    out->k = l.fb_t2 ? 1152 + 128 : 576 + 64 + l.fb_n3 * 4;
+    out->variant = 32768 + (l.fb_t2 ? 128 : l.fb_n3);
     out->flops = l.flops;
     out->bytes = l.bytes;
     return TDET_OK;

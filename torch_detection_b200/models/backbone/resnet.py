@@ -472,7 +472,8 @@ class ResNet(nn.Module):
                                 z1 = new_act((nb, hb, wb, unit.conv1.out_channels), internal)
                                 conv(pre + "conv1", unit.conv1, getattr(unit, unit.norm_names[0]), cur, z1)
                             dst = boundary_act(li, i0, cn) if last else new_act((nb, hb, wb, unit.conv3.out_channels), internal)
-                            head = stage[bi + 1] if (FUSE_TAIL_NEXT and not last and _fuses_tail(stage[bi + 1])) else None
+                            head = stage[bi + 1] if (FUSE_TAIL_NEXT and unit.conv2.out_channels == 64 and not last and
+                                                     _fuses_tail(stage[bi + 1])) else None
                             pending_z1 = tail(pre, unit, z1, cur, dst, head, "%s.%d." % (lname, bi + 1))
                             pool.release(z1.buf)
                             if cur_pooled:
@@ -1058,6 +1059,8 @@ FUSE_TAIL = os.environ.get("TDET_FUSE_TAIL", "1") != "0"
 # ... and the next block's conv1 in the same kernel (measured: no faster than the tail-only kernel + a separate conv1,
 # the tail-only variant keeps W2 resident; kept as an experiment switch)
 FUSE_TAIL_NEXT = os.environ.get("TDET_FUSE_TAIL_NEXT", "0") != "0"
+# the planes = 128 tail kernel for layer2's identity blocks (bottleneck_tail2.cuh)
+FUSE_TAIL2 = os.environ.get("TDET_FUSE_TAIL2", "1") != "0"
 
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
@@ -1076,13 +1079,17 @@ def _fuses_shortcut(unit):
 
 def _fuses_tail(unit):
     """True if conv2 -> conv3 + residual (-> the next block's conv1) of this unit run as ONE kernel
-    (TDET_OP_BOTTLENECK_TAIL): an identity-shortcut bottleneck with planes = 64 (layer1 of ResNet-50/101/152)."""
+    (TDET_OP_BOTTLENECK_TAIL): an identity-shortcut bottleneck with planes = 64 (layer1 of ResNet-50/101/152) or
+    planes = 128 (layer2; tail only)."""
     if not FUSE_TAIL or unit.downsample is not None or tuple(unit.kernel_sizes) != (1, 3, 1):
         return False
     c1, c2, c3 = unit.conv1, unit.conv2, unit.conv3
-    return (c1.in_channels == 256 and c1.out_channels == 64 and c1.stride[0] == 1 and c1.groups == 1 and
-            c2.in_channels == 64 and c2.out_channels == 64 and c2.stride[0] == 1 and c2.padding[0] == 1 and
-            c2.dilation[0] == 1 and c2.groups == 1 and c3.in_channels == 64 and c3.out_channels == 256 and
+    pl = c2.out_channels
+    if pl != 64 and not (pl == 128 and FUSE_TAIL2):
+        return False
+    return (c1.in_channels == 4 * pl and c1.out_channels == pl and c1.stride[0] == 1 and c1.groups == 1 and
+            c2.in_channels == pl and c2.stride[0] == 1 and c2.padding[0] == 1 and
+            c2.dilation[0] == 1 and c2.groups == 1 and c3.in_channels == pl and c3.out_channels == 4 * pl and
             c3.groups == 1)
 
 
