@@ -40,6 +40,7 @@
 // come from the same rigorous bounds, chained (the true |max| of an intermediate is not known before the kernel
 // ends): |z2| <= G2*amax(z1) + S2, |out| <= G3*|z2| + S3 + amax(x), |z1'| <= G1'*|out| + S1'.
 #pragma once
+#include <type_traits>
 #include "conv_gemm.cuh"
 
 namespace tdet {
@@ -604,53 +605,62 @@ bottleneck_tail_kernel(const __grid_constant__ FbParams p) {
         mbar_wait(r_full(j), ph);
         trace(72);  // residual slab landed
         const uint32_t rbase = s_out + j * kSlabBytes + row * 128;
-        // both halves of the slab's accumulator are requested before any arithmetic (two tcgen05.ld in flight)
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32b_x32(lane_base + kD2 + static_cast<uint32_t>(j * 64), va);
-        tmem_ld_32x32b_x32(lane_base + kD2 + static_cast<uint32_t>(j * 64 + 32), vb);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t (&v)[32] = half ? vb : va;
-          uint4 rr[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t a = rbase + ((((half << 2) | c) ^ (row & 7)) << 4);
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(rr[c].x), "=r"(rr[c].y), "=r"(rr[c].z), "=r"(rr[c].w)
-                         : "r"(a));
-          }
-          if (half == 0) tmem_ld_wait();
-          const int cb = j * 64 + half * 32;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t w4[4] = {rr[c].x, rr[c].y, rr[c].z, rr[c].w};
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 4; e += 2) {
-              float r0, r1, r2, r3;
-              unpack16x2(w4[e], res_fp16, r0, r1);
-              unpack16x2(w4[e + 1], res_fp16, r2, r3);
-              const float4 s4 = *reinterpret_cast<const float4*>(sc3 + cb + 8 * c + 2 * e);
-              const float4 h4 = *reinterpret_cast<const float4*>(sh3 + cb + 8 * c + 2 * e);
-              x[2 * e + 0] = fmaxf(fmaf(r0, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 0]), s4.x, h4.x)), 0.0f);
-              x[2 * e + 1] = fmaxf(fmaf(r1, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 1]), s4.y, h4.y)), 0.0f);
-              x[2 * e + 2] = fmaxf(fmaf(r2, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 2]), s4.z, h4.z)), 0.0f);
-              x[2 * e + 3] = fmaxf(fmaf(r3, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 3]), s4.w, h4.w)), 0.0f);
+        // (storage formats as compile-time constants: with run-time flags the compiler computes both the fp16 and the
+        // bf16 side of every unpack / pack in the unrolled loops)
+        auto convert = [&](auto res16_c, auto out16_c) {
+          constexpr bool kR16 = decltype(res16_c)::value, kO16 = decltype(out16_c)::value;
+          // both halves of the slab's accumulator are requested before any arithmetic (two tcgen05.ld in flight)
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32b_x32(lane_base + kD2 + static_cast<uint32_t>(j * 64), va);
+          tmem_ld_32x32b_x32(lane_base + kD2 + static_cast<uint32_t>(j * 64 + 32), vb);
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t (&v)[32] = half ? vb : va;
+            uint4 rr[4];
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t a = rbase + ((((half << 2) | c) ^ (row & 7)) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rr[c].x), "=r"(rr[c].y), "=r"(rr[c].z), "=r"(rr[c].w)
+                           : "r"(a));
             }
-            if (valid) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) amax_out = fmaxf(amax_out, x[e]);
+            if (half == 0) tmem_ld_wait();
+            const int cb = j * 64 + half * 32;
+  #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t w4[4] = {rr[c].x, rr[c].y, rr[c].z, rr[c].w};
+              float x[8];
+  #pragma unroll
+              for (int e = 0; e < 4; e += 2) {
+                float r0, r1, r2, r3;
+                unpack16x2(w4[e], kR16, r0, r1);
+                unpack16x2(w4[e + 1], kR16, r2, r3);
+                const float4 s4 = *reinterpret_cast<const float4*>(sc3 + cb + 8 * c + 2 * e);
+                const float4 h4 = *reinterpret_cast<const float4*>(sh3 + cb + 8 * c + 2 * e);
+                x[2 * e + 0] = fmaxf(fmaf(r0, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 0]), s4.x, h4.x)), 0.0f);
+                x[2 * e + 1] = fmaxf(fmaf(r1, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 1]), s4.y, h4.y)), 0.0f);
+                x[2 * e + 2] = fmaxf(fmaf(r2, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 2]), s4.z, h4.z)), 0.0f);
+                x[2 * e + 3] = fmaxf(fmaf(r3, mul_res, fmaf(__uint_as_float(v[8 * c + 2 * e + 3]), s4.w, h4.w)), 0.0f);
+              }
+              if (valid) {
+  #pragma unroll
+                for (int e = 0; e < 8; ++e) amax_out = fmaxf(amax_out, x[e]);
+              }
+              uint4 o;
+              o.x = pack16x2(x[0], x[1], kO16);
+              o.y = pack16x2(x[2], x[3], kO16);
+              o.z = pack16x2(x[4], x[5], kO16);
+              o.w = pack16x2(x[6], x[7], kO16);
+              const uint32_t a = rbase + ((((half << 2) | c) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
+                           : "memory");
             }
-            uint4 o;
-            o.x = pack16x2(x[0], x[1], out_fp16);
-            o.y = pack16x2(x[2], x[3], out_fp16);
-            o.z = pack16x2(x[4], x[5], out_fp16);
-            o.w = pack16x2(x[6], x[7], out_fp16);
-            const uint32_t a = rbase + ((((half << 2) | c) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w)
-                         : "memory");
           }
-        }
+        };
+        using T = std::true_type;
+        using F = std::false_type;
+        if (res_fp16) { if (out_fp16) convert(T{}, T{}); else convert(T{}, F{}); }
+        else { if (out_fp16) convert(F{}, T{}); else convert(F{}, F{}); }
         if (jj == 1) tc_fence_before();
         fence_proxy_async_smem();
         __syncwarp();

@@ -153,6 +153,7 @@ struct ConvGemmParams {
   int k_chunks2;
   int stride2;
   const TensorMeta* in2_meta;     // nullable
+  int epi_fast;                   // 1: compile-time epilogue variants where one matches (TDET_EPI_FAST, default 1)
 };
 
 // BRES_KB > 0: the whole weight panel of the CTA's n-tile (up to BRES_KB k-blocks; one n-tile, or a grid that is a
@@ -184,6 +185,15 @@ struct GemmSmem {
   static constexpr int kGroupCols = BN == 64 ? 64 : BN / NG;
   static constexpr int kDynamic = kParamOffset + NG * 2 * kGroupCols * 4;
   static_assert(kDynamic <= 232448, "exceeds the 227 KiB shared memory limit");
+};
+
+// Compile-time description of the epilogue's conversion step (conv_gemm_kernel): mode 0 = every flag at run time (the
+// general code), 1 = no residual / coarse operand, 2 = fp16 residual, 3 = bf16 coarse operand (FPN laterals).
+template <int MODE, bool OUT16, bool RELU>
+struct EpiFast {
+  static constexpr int mode = MODE;
+  static constexpr bool out16 = OUT16;
+  static constexpr bool relu = RELU;
 };
 
 __device__ __forceinline__ void unpack16x2(uint32_t w, bool fp16, float& lo, float& hi) {
@@ -763,14 +773,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t gbar = 1u + group;      // the group's named barrier
     const bool ws = p.warp_stores != 0 && !POOL;
     const bool issuer = ws ? (lane == 0) : (gtid == 0);  // issues the TMA stores (its warp's / its group's), frees residual slabs
-    const bool has_res = RES_SLABS > 0 && p.has_res;
+    const bool has_res_rt = RES_SLABS > 0 && p.has_res;
+    const bool has_res = has_res_rt;
     const bool mask_tma = MASKED && RES_SLABS > 0 && p.mask_tma != 0;
     const bool split = SPLIT && p.split != 0;
     static_assert(!SPLIT || OSLABS == 2, "split precision stages the hi and the lo slab side by side");
     // split mode: the residual's lo slab rides in the ring slot the mask would use
     const int nload = coarse_tma ? 1 : (split && has_res) ? 2 : (has_res ? 1 : 0) + (mask_tma ? 1 : 0);
     const bool has_coarse = p.coarse != nullptr;
-    const bool out_fp16 = p.out_fp16 != 0, res_fp16 = p.res_fp16 != 0, co_fp16 = p.coarse_fp16 != 0;
+    const bool out_fp16_rt = p.out_fp16 != 0, res_fp16_rt = p.res_fp16 != 0, co_fp16_rt = p.coarse_fp16 != 0;
+    const bool out_fp16 = out_fp16_rt;
     float* s_scale = s_params + group * 2 * L::kGroupCols;
     float* s_shift = s_scale + L::kGroupCols;
     const uint32_t smem_out_g = smem_out + group * OSLABS * kSlabBytes;
@@ -796,6 +808,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const float mul_res = ldexpf(1.0f, e_res - e_out);
     const float mul_co = ldexpf(1.0f, e_co - e_out);
     float amax_local = 0.0f;
+    // conversion-step variant (EpiFast): the common forward epilogues run with their flags fixed at compile time
+    int epi_variant = 0;
+    if (!MASKED && !(SPLIT && split) && !POOL && p.relu != 2 && p.epi_fast) {
+      const bool r1 = p.relu == 1;
+      if (!has_res_rt && !has_coarse) epi_variant = out_fp16_rt ? (r1 ? 1 : 3) : (r1 ? 2 : 4);
+      else if (has_res_rt && !has_coarse && res_fp16_rt && r1) epi_variant = out_fp16_rt ? 5 : 6;
+      else if (!has_res_rt && has_coarse && !co_fp16_rt && !out_fp16_rt && !r1) epi_variant = 7;
+    }
 
     if (POOL) {
       // ---- stem + 3x3/2 max-pool: this group owns channels [32 group, 32 group + 32) of every conv row.
@@ -959,13 +979,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         pix = m;
         st_c1 = m_tile * kBM;
       }
-      const uint8_t* coarse_row = nullptr;
+      const uint8_t* coarse_row_rt = nullptr;
       // TMA-staged coarse operand: this thread's pixel (hl, wl) of the 8 x 16 tile reads coarse box row
       // (hl/2)*4 + wl/2; parity mode only adds at even pixels
-      int crow = -1;
+      int crow_rt = -1;
       if (coarse_tma && valid) {
         const int hl = row / p.tile_bw, wl = row - hl * p.tile_bw;
-        if (!(p.coarse_parity && ((hl | wl) & 1))) crow = (hl >> 1) * (p.tile_bw >> 1) + (wl >> 1);
+        if (!(p.coarse_parity && ((hl | wl) & 1))) crow_rt = (hl >> 1) * (p.tile_bw >> 1) + (wl >> 1);
       }
       if (valid && has_coarse && !coarse_tma) {
         const int m = static_cast<int>(pix);
@@ -974,7 +994,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int pp = t % p.Ho;
         const int img = t / p.Ho;
         if (!(p.coarse_parity && ((pp | q) & 1)))
-          coarse_row = static_cast<const uint8_t*>(p.coarse) +
+          coarse_row_rt = static_cast<const uint8_t*>(p.coarse) +
                        (((static_cast<long long>(img) * p.Hc + (pp >> 1)) * p.Wc + (q >> 1)) *
                             (split ? 2 * p.N : p.N) + n0) * 2;
       }
@@ -1022,8 +1042,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint32_t out_row = smem_out_g + ob * kSlabBytes + row * 128;
         const uint32_t res_row = smem_res + rs * kSlabBytes + row * 128;
         const uint32_t mk_row = smem_res + ms * kSlabBytes + row * 128;
+        auto convert_slab = [&](auto fast) {
 #pragma unroll 1
         for (int half = 0; half < kParts; ++half) {   // (a 32- or 16-column step of the slab)
+          // Fast variants fix the operand set and the storage formats at compile time.  With run-time flags the
+          // compiler if-converts every per-element format / operand branch of the unrolled loops and computes BOTH
+          // sides (SASS of the residual kernel: 560 instructions per 32 columns, 17 per element, of them 160 FFMA and
+          // 64 fp16 + 57 bf16 unpack operations) -- and these kernels are bound by exactly this instruction stream.
+          constexpr int kMode = decltype(fast)::mode;   // 0 generic, 1 no operand, 2 fp16 residual, 3 bf16 coarse
+          constexpr bool kGen = kMode == 0;
+          const bool has_res = kGen ? has_res_rt : (kMode == 2);
+          const bool res_fp16 = kGen ? res_fp16_rt : true;
+          const bool co_fp16 = kGen ? co_fp16_rt : false;
+          const bool out_fp16 = kGen ? out_fp16_rt : decltype(fast)::out16;
+          const int relu = kGen ? p.relu : (decltype(fast)::relu ? 1 : 0);
+          const uint8_t* const coarse_row = (kGen || kMode == 3) ? coarse_row_rt : nullptr;
+          const int crow = (kGen || kMode == 3) ? crow_rt : -1;
           uint32_t v[kEW];
           tmem_ld_cols<kEW>(t_addr + slab * 64 + half * kEW, v);
           uint4 rco[kEJ];
@@ -1150,10 +1184,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
             }
           }
-          if (p.relu) {
+          if (relu) {
 #pragma unroll
             for (int i = 0; i < kEW; ++i) x[i] = fmaxf(x[i], 0.0f);
-            if (p.relu == 2) {   // ReLU6 (plain outputs only: x is the true value)
+            if (relu == 2) {   // ReLU6 (plain outputs only: x is the true value)
 #pragma unroll
               for (int i = 0; i < kEW; ++i) x[i] = fminf(x[i], 6.0f);
             }
@@ -1197,6 +1231,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                            : "memory");
             }
           }
+        }
+        };
+        switch (epi_variant) {
+          case 1: convert_slab(EpiFast<1, true, true>{}); break;
+          case 2: convert_slab(EpiFast<1, false, true>{}); break;
+          case 3: convert_slab(EpiFast<1, true, false>{}); break;
+          case 4: convert_slab(EpiFast<1, false, false>{}); break;
+          case 5: if constexpr (RES_SLABS > 0) { convert_slab(EpiFast<2, true, true>{}); } break;
+          case 6: if constexpr (RES_SLABS > 0) { convert_slab(EpiFast<2, false, true>{}); } break;
+          case 7: convert_slab(EpiFast<3, false, false>{}); break;
+          default: convert_slab(EpiFast<0, false, false>{}); break;
         }
         if (slab + (kByTile ? 1 : NG) >= kSlabsPerTile) {
           // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp

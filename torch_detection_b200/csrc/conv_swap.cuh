@@ -27,6 +27,7 @@
 // over it (8-pixel row groups 10 rows apart: SBO = 1280 B), so the activations are read 1.3x instead of 9x; the
 // weight tiles stream through their own ring.
 #pragma once
+#include <type_traits>
 #include "conv_gemm.cuh"
 
 namespace tdet {
@@ -304,29 +305,44 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
       if (active) {
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                 static_cast<uint32_t>(acc * kSwapPix + group * 128);
+        // every pixel row of this group's half lies inside the tensor (all but edge tiles): no per-element test
+        const bool all_ok = PATCH ? (h0 + 16 <= p.Ho && w0 + 8 <= p.Wo) : (m0 + 128 <= p.M);
+        // (format / activation / bounds fixed at compile time in the common variants: with run-time flags the compiler
+        // computes both sides of every per-element branch of the unrolled loop)
+        auto convert = [&](auto kOut16, auto kAllOk, auto kFast) {
 #pragma unroll 1
-        for (int ck = 0; ck < 4; ++ck) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + ck * 32, v);
-          tmem_ld_wait();
+          for (int ck = 0; ck < 4; ++ck) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_addr + ck * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int pr = ck * 32 + i;  // pixel row inside the group's 128
-            float y = fmaf(__uint_as_float(v[i]), sc, sh);
-            if (p.relu) y = p.relu == 2 ? fminf(fmaxf(y, 0.0f), 6.0f) : fmaxf(y, 0.0f);
-            const bool ok = PATCH ? (h0 + (pr >> 3) < p.Ho && w0 + (pr & 7) < p.Wo) : (m0 + pr < p.M);
-            if (ok) amax_local = fmaxf(amax_local, fabsf(y));
-            uint16_t h;
-            if (out_fp16) {
-              const __half hh = __float2half_rn(y);
-              h = *reinterpret_cast<const uint16_t*>(&hh);
-            } else {
-              const __nv_bfloat16 bb = __float2bfloat16_rn(y);
-              h = *reinterpret_cast<const uint16_t*>(&bb);
+            for (int i = 0; i < 32; ++i) {
+              const int pr = ck * 32 + i;  // pixel row inside the group's 128
+              float y = fmaf(__uint_as_float(v[i]), sc, sh);
+              if (decltype(kFast)::value) y = fmaxf(y, 0.0f);
+              else if (p.relu) y = p.relu == 2 ? fminf(fmaxf(y, 0.0f), 6.0f) : fmaxf(y, 0.0f);
+              const bool ok = decltype(kAllOk)::value ||
+                              (PATCH ? (h0 + (pr >> 3) < p.Ho && w0 + (pr & 7) < p.Wo) : (m0 + pr < p.M));
+              if (ok) amax_local = fmaxf(amax_local, fabsf(y));
+              uint16_t h;
+              if (decltype(kFast)::value ? decltype(kOut16)::value : out_fp16) {
+                const __half hh = __float2half_rn(y);
+                h = *reinterpret_cast<const uint16_t*>(&hh);
+              } else {
+                const __nv_bfloat16 bb = __float2bfloat16_rn(y);
+                h = *reinterpret_cast<const uint16_t*>(&bb);
+              }
+              const uint32_t a = st_base + pr * 128 + ((chunk16 ^ (pr & 7)) << 4);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
             }
-            const uint32_t a = st_base + pr * 128 + ((chunk16 ^ (pr & 7)) << 4);
-            asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(h) : "memory");
           }
+        };
+        using T = std::true_type;
+        using F = std::false_type;
+        if (p.relu == 1 && all_ok && p.epi_fast) {
+          if (out_fp16) convert(T{}, T{}, T{}); else convert(F{}, T{}, T{});
+        } else {
+          convert(F{}, F{}, F{});
         }
       }
       // all TMEM reads of this warp are complete: hand the accumulator back

@@ -572,6 +572,7 @@ int build_conv_swap(Launch& l, const DeviceInfo& di) {
   }
   if (rc) return rc;
   l.swap = true;
+  gp.epi_fast = env_int("TDET_EPI_FAST", 1);
   l.bn = 256;
   l.stages = l.patch ? 4 : 3;
   l.res_slabs = 0;
@@ -891,6 +892,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   const bool wst = ws_mode == 2 || (ws_mode == 1 && gp.num_kb_b <= 8);
   gp.warp_stores = wst ? 1 : 0;
   gp.res_prefetch = (o.residual || o.mask) ? env_int("TDET_RES_PREFETCH", 0) : 0;
+  gp.epi_fast = env_int("TDET_EPI_FAST", 1);
   const int out_bh = wst ? kWarpRows / kPatchBW : kPatchBH;  // spatial tiles: rows of the output box
   if (spatial) {
     rc = encode_4d(&gp.tmap_out, o.y, o.y_dtype, o.cout, o.wo, o.ho, o.n, kPatchBW, out_bh, "output");
@@ -1271,36 +1273,33 @@ int launch_fb_t(const FbParams& fp, dim3 grid, cudaStream_t st) {
   return launch_pdl(bottleneck_tail_kernel<N3>, grid, kFbThreads, L::kDynamic, st, fp);
 }
 
-template <bool PAIR>
-int launch_t2_t(const T2Params& tp, dim3 grid, cudaStream_t st) {
+int launch_t2(const T2Params& tp, dim3 grid, cudaStream_t st) {
   static bool attr_set[64] = {};
   static int max_clusters[64] = {};
   int dev = 0;
   TDET_CUDA(cudaGetDevice(&dev));
-  auto kernel = bottleneck_tail2_kernel<PAIR>;
+  auto kernel = bottleneck_tail2_kernel;
   if (!attr_set[dev]) {
     TDET_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem::kDynamic));
-    if (PAIR) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * 74, 1, 1);
-      cfg.blockDim = dim3(kFbThreads, 1, 1);
-      cfg.dynamicSmemBytes = T2Smem::kDynamic;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      int n = 0;
-      TDET_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
-      if (n < 1) return fail(TDET_ERR_DRIVER, "no CTA pair of the bottleneck tail kernel fits on device %d", dev);
-      max_clusters[dev] = n;
-    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 74, 1, 1);
+    cfg.blockDim = dim3(kT2Threads, 1, 1);
+    cfg.dynamicSmemBytes = T2Smem::kDynamic;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    TDET_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+    if (n < 1) return fail(TDET_ERR_DRIVER, "no CTA pair of the bottleneck tail kernel fits on device %d", dev);
+    max_clusters[dev] = n;
     attr_set[dev] = true;
   }
-  if (PAIR && grid.x > 2u * static_cast<unsigned>(max_clusters[dev])) grid.x = 2u * static_cast<unsigned>(max_clusters[dev]);
-  return launch_pdl(kernel, grid, kFbThreads, T2Smem::kDynamic, st, tp, PAIR ? 2 : 1);
+  if (grid.x > 2u * static_cast<unsigned>(max_clusters[dev])) grid.x = 2u * static_cast<unsigned>(max_clusters[dev]);
+  return launch_pdl(kernel, grid, kT2Threads, T2Smem::kDynamic, st, tp, 2);
 }
 
 // planes = 128 (layer2): 128 -> 128 (3x3) -> 512 (1x1) + residual, tail only
@@ -1351,27 +1350,21 @@ int build_bottleneck_tail2(Launch& l, const DeviceInfo& di) {
   tp.trace = reinterpret_cast<unsigned long long*>(o.dw);  // debugging aid: cycle trace of CTA 0 (NULL in normal runs)
   int rc = encode_4d(&tp.tmap_z1, o.x, o.x_dtype, 128, o.w, o.h, o.n, kPatchPW, kPatchPH, "conv2 halo patch");
   if (rc) return rc;
-  // CTA pairs (TDET_TAIL2_PAIR, default 1): every CTA stages its half of each weight block (64-row boxes)
-  const bool pair = env_int("TDET_TAIL2_PAIR", 1) != 0 && tp.num_tiles >= 2;
-  rc = encode_2d(&tp.tmap_w2, o.wgt, o.x_dtype, 9 * 128, 128, pair ? 64 : 128, "conv2 weights");
+  // CTA pairs: every CTA stages its half of each weight block (64-row boxes)
+  rc = encode_2d(&tp.tmap_w2, o.wgt, o.x_dtype, 9 * 128, 128, 64, "conv2 weights");
   if (rc) return rc;
-  rc = encode_2d(&tp.tmap_w3, o.wgt2, o.x_dtype, 128, 512, pair ? 64 : 128, "conv3 weights");
+  rc = encode_2d(&tp.tmap_w3, o.wgt2, o.x_dtype, 128, 512, 64, "conv3 weights");
   if (rc) return rc;
   rc = encode_4d(&tp.tmap_res, o.residual, o.residual_dtype, 512, o.w, o.h, o.n, kPatchBW, kPatchBH, "residual");
   if (rc) return rc;
   rc = encode_4d(&tp.tmap_out, o.y, o.y_dtype, 512, o.w, o.h, o.n, kPatchBW, kPatchBH, "block output");
   if (rc) return rc;
-  int g = di.num_sms - di.sm_reserve;
-  if (pair) {
-    g &= ~1;
-    if (g > 2 * ((tp.num_tiles + 1) / 2)) g = 2 * ((tp.num_tiles + 1) / 2);
-  } else if (g > tp.num_tiles) {
-    g = tp.num_tiles;
-  }
+  int g = (di.num_sms - di.sm_reserve) & ~1;
+  if (g > 2 * ((tp.num_tiles + 1) / 2)) g = 2 * ((tp.num_tiles + 1) / 2);
   l.grid = dim3(static_cast<unsigned>(g), 1, 1);
   l.bn = 256;
   l.fb_t2 = true;
-  l.pair = pair;
+  l.pair = true;
   const double rows = static_cast<double>(m_ll);
   l.flops = 2.0 * rows * (128.0 * 1152 + 512.0 * 128);
   l.bytes = 2.0 * (rows * (128 + 512 + 512) + 128.0 * 1152 + 512.0 * 128);
@@ -1594,7 +1587,7 @@ int run_launch(const Launch& l, const DeviceInfo& di, cudaStream_t st) {
     case TDET_OP_CONV:
     case TDET_OP_STEM: return launch_gemm(l, st);
     case TDET_OP_BOTTLENECK_TAIL:
-      if (l.fb_t2) return l.pair ? launch_t2_t<true>(l.t2, l.grid, st) : launch_t2_t<false>(l.t2, l.grid, st);
+      if (l.fb_t2) return launch_t2(l.t2, l.grid, st);
       return l.fb_n3 ? launch_fb_t<64>(l.fb, l.grid, st) : launch_fb_t<0>(l.fb, l.grid, st);
     case TDET_OP_PREP: {
       const int hp = stem_hp(o.ho), wp = stem_wp(o.wo);
