@@ -41,6 +41,7 @@
 // overflow-free for any input without calibration.  With all metadata pointers null the exponents
 // are 0 and the tensors are plain bf16/fp16.
 #pragma once
+#include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ptx_sm100.cuh"
@@ -848,86 +849,91 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(ld_acc));
       };
-      // one conv row of this thread's pixel: BN + ReLU, packed to 16 x (2 x 16 bit); zeros outside the image
-      auto conv_row = [&](const uint32_t (&v)[32], int r, int col, uint32_t (&o)[16]) {
-        if (r >= 0 && r < p.Ho && col >= 0 && col < p.Wo) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + group * 32 + 4 * j);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + group * 32 + 4 * j);
-            // (PTX max: max(-0, +0) = +0, so the packed values order like unsigned integers)
-            o[2 * j] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.0f),
-                                fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.0f), out_fp16);
-            o[2 * j + 1] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.0f),
-                                    fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.0f), out_fp16);
+      // (the output format as a compile-time constant: a run-time flag costs a second, predicated pack per pair)
+      auto pool_rows = [&](auto out16_c) {
+        constexpr bool out_fp16 = decltype(out16_c)::value;
+        // one conv row of this thread's pixel: BN + ReLU, packed to 16 x (2 x 16 bit); zeros outside the image
+        auto conv_row = [&](const uint32_t (&v)[32], int r, int col, uint32_t (&o)[16]) {
+          if (r >= 0 && r < p.Ho && col >= 0 && col < p.Wo) {
+  #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + group * 32 + 4 * j);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + group * 32 + 4 * j);
+              // (PTX max: max(-0, +0) = +0, so the packed values order like unsigned integers)
+              o[2 * j] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j]), sc.x, sh.x), 0.0f),
+                                  fmaxf(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), 0.0f), out_fp16);
+              o[2 * j + 1] = pack16x2(fmaxf(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), 0.0f),
+                                      fmaxf(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), 0.0f), out_fp16);
+            }
+          } else {
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = 0u;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = 0u;
+        };
+        for (int g = pool_g0; g < pool_g1;) {
+          const int unit = g / p.pool_h;
+          const int pa = g - unit * p.pool_h;
+          const int len = min(p.pool_h - pa, pool_g1 - g);
+          const int img = unit / p.tiles_w;
+          const int strip = unit - img * p.tiles_w;
+          const int col = 2 * kPoolStep * strip - 8 + row;  // conv column of this thread's accumulator row
+          uint32_t va[32], vb2[32];
+          uint32_t prev[16], vm[16];
+          issue_ld(va);                 // row 2 pa - 1
+          finish_ld();
+          issue_ld(vb2);                // row 2 pa
+          conv_row(va, 2 * pa - 1, col, prev);
+          for (int pr = pa; pr < pa + len; ++pr) {
+            finish_ld();
+            issue_ld(va);               // row 2 pr + 1
+            conv_row(vb2, 2 * pr, col, vm);
+  #pragma unroll
+            for (int j = 0; j < 16; ++j) vm[j] = __vmaxu2(vm[j], prev[j]);
+            finish_ld();
+            if (pr + 1 < pa + len) issue_ld(vb2);  // row 2 pr + 2
+            conv_row(va, 2 * pr + 1, col, prev);
+            const uint32_t dst = vbuf + static_cast<uint32_t>(vb) * 8192u + row * 64;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 m;
+              m.x = __vmaxu2(vm[4 * j], prev[4 * j]);
+              m.y = __vmaxu2(vm[4 * j + 1], prev[4 * j + 1]);
+              m.z = __vmaxu2(vm[4 * j + 2], prev[4 * j + 2]);
+              m.w = __vmaxu2(vm[4 * j + 3], prev[4 * j + 3]);
+              amax_pk = __vmaxu2(amax_pk, __vmaxu2(__vmaxu2(m.x, m.y), __vmaxu2(m.z, m.w)));
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ ((row >> 1) & 3)) << 4)),
+                           "r"(m.x), "r"(m.y), "r"(m.z), "r"(m.w)
+                           : "memory");
+            }
+            named_bar_sync(gbar, kEpiGroupThreads);
+            // pooled row pr: horizontal max over conv columns 2q-1 .. 2q+1 (this strip's rows 2 ql + 7 .. + 9)
+            const uint32_t rb = vbuf + static_cast<uint32_t>(vb) * 8192u;
+            for (int it = gtid; it < kPoolStep * 4; it += kEpiGroupThreads) {
+              const int ql = it >> 2, c = it & 3;
+              const int q = kPoolStep * strip + ql;
+              if (q < p.pool_w) {
+                uint4 t[3];
+  #pragma unroll
+                for (int dc = 0; dc < 3; ++dc) {
+                  const int i = 2 * ql + 7 + dc;
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                               : "=r"(t[dc].x), "=r"(t[dc].y), "=r"(t[dc].z), "=r"(t[dc].w)
+                               : "r"(rb + i * 64 + ((c ^ ((i >> 1) & 3)) << 4)));
+                }
+                uint4 m;
+                m.x = __vmaxu2(__vmaxu2(t[0].x, t[1].x), t[2].x);
+                m.y = __vmaxu2(__vmaxu2(t[0].y, t[1].y), t[2].y);
+                m.z = __vmaxu2(__vmaxu2(t[0].z, t[1].z), t[2].z);
+                m.w = __vmaxu2(__vmaxu2(t[0].w, t[1].w), t[2].w);
+                stg_v4(out + ((static_cast<long long>(img) * p.pool_h + pr) * p.pool_w + q) * 128 + group * 64 + c * 16, m);
+              }
+            }
+            vb ^= 1;  // (the other buffer was last read before this row's barrier)
+          }
+          g += len;
         }
       };
-      for (int g = pool_g0; g < pool_g1;) {
-        const int unit = g / p.pool_h;
-        const int pa = g - unit * p.pool_h;
-        const int len = min(p.pool_h - pa, pool_g1 - g);
-        const int img = unit / p.tiles_w;
-        const int strip = unit - img * p.tiles_w;
-        const int col = 2 * kPoolStep * strip - 8 + row;  // conv column of this thread's accumulator row
-        uint32_t va[32], vb2[32];
-        uint32_t prev[16], vm[16];
-        issue_ld(va);                 // row 2 pa - 1
-        finish_ld();
-        issue_ld(vb2);                // row 2 pa
-        conv_row(va, 2 * pa - 1, col, prev);
-        for (int pr = pa; pr < pa + len; ++pr) {
-          finish_ld();
-          issue_ld(va);               // row 2 pr + 1
-          conv_row(vb2, 2 * pr, col, vm);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) vm[j] = __vmaxu2(vm[j], prev[j]);
-          finish_ld();
-          if (pr + 1 < pa + len) issue_ld(vb2);  // row 2 pr + 2
-          conv_row(va, 2 * pr + 1, col, prev);
-          const uint32_t dst = vbuf + static_cast<uint32_t>(vb) * 8192u + row * 64;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 m;
-            m.x = __vmaxu2(vm[4 * j], prev[4 * j]);
-            m.y = __vmaxu2(vm[4 * j + 1], prev[4 * j + 1]);
-            m.z = __vmaxu2(vm[4 * j + 2], prev[4 * j + 2]);
-            m.w = __vmaxu2(vm[4 * j + 3], prev[4 * j + 3]);
-            amax_pk = __vmaxu2(amax_pk, __vmaxu2(__vmaxu2(m.x, m.y), __vmaxu2(m.z, m.w)));
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((j ^ ((row >> 1) & 3)) << 4)),
-                         "r"(m.x), "r"(m.y), "r"(m.z), "r"(m.w)
-                         : "memory");
-          }
-          named_bar_sync(gbar, kEpiGroupThreads);
-          // pooled row pr: horizontal max over conv columns 2q-1 .. 2q+1 (this strip's rows 2 ql + 7 .. + 9)
-          const uint32_t rb = vbuf + static_cast<uint32_t>(vb) * 8192u;
-          for (int it = gtid; it < kPoolStep * 4; it += kEpiGroupThreads) {
-            const int ql = it >> 2, c = it & 3;
-            const int q = kPoolStep * strip + ql;
-            if (q < p.pool_w) {
-              uint4 t[3];
-#pragma unroll
-              for (int dc = 0; dc < 3; ++dc) {
-                const int i = 2 * ql + 7 + dc;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(t[dc].x), "=r"(t[dc].y), "=r"(t[dc].z), "=r"(t[dc].w)
-                             : "r"(rb + i * 64 + ((c ^ ((i >> 1) & 3)) << 4)));
-              }
-              uint4 m;
-              m.x = __vmaxu2(__vmaxu2(t[0].x, t[1].x), t[2].x);
-              m.y = __vmaxu2(__vmaxu2(t[0].y, t[1].y), t[2].y);
-              m.z = __vmaxu2(__vmaxu2(t[0].z, t[1].z), t[2].z);
-              m.w = __vmaxu2(__vmaxu2(t[0].w, t[1].w), t[2].w);
-              stg_v4(out + ((static_cast<long long>(img) * p.pool_h + pr) * p.pool_w + q) * 128 + group * 64 + c * 16, m);
-            }
-          }
-          vb ^= 1;  // (the other buffer was last read before this row's barrier)
-        }
-        g += len;
-      }
+      if (out_fp16_rt) pool_rows(std::true_type{}); else pool_rows(std::false_type{});
       {
         float lo, hi;
         unpack16x2(amax_pk, out_fp16, lo, hi);
