@@ -1059,8 +1059,10 @@ FUSE_TAIL = os.environ.get("TDET_FUSE_TAIL", "1") != "0"
 # ... and the next block's conv1 in the same kernel (measured: no faster than the tail-only kernel + a separate conv1,
 # the tail-only variant keeps W2 resident; kept as an experiment switch)
 FUSE_TAIL_NEXT = os.environ.get("TDET_FUSE_TAIL_NEXT", "0") != "0"
-# the planes = 128 tail kernel for layer2's identity blocks (bottleneck_tail2.cuh)
-FUSE_TAIL2 = os.environ.get("TDET_FUSE_TAIL2", "1") != "0"
+# the planes = 128 tail kernel for layer2's identity blocks (bottleneck_tail2.cuh).  Off by default: same-box A/B at
+# batch 16 @800x1344 measured the three fused blocks 50 us EACH slower than conv2 + conv3 launched separately
+# (265 vs 88 + 127 us in situ; 2785 vs 2855 img/s for the whole step).  The kernel and its tests stay (TDET_FUSE_TAIL2=1).
+FUSE_TAIL2 = os.environ.get("TDET_FUSE_TAIL2", "0") != "0"
 
 # Images per chunk for stage 1, 2, ... ("0" or missing = whole batch); TDET_CHUNKS overrides.
 DEFAULT_CHUNKS = "0"
