@@ -115,6 +115,10 @@ enum {
   TDET_FLAG_SCALED_OUT2 = 64, /* TDET_OP_BOTTLENECK_TAIL: y2 is stored with a device-chosen exponent (needs y2_meta) */
   TDET_FLAG_RELU6 = 128,    /* TDET_OP_CONV / TDET_OP_GN_APPLY: y = min(max(v, 0), 6) -- ConvModule(activation='relu6'),
                                models/utils/layers.py:114-119.  Plain outputs only (not with TDET_FLAG_SCALED_OUT). */
+  TDET_FLAG_REVERSE = 256,  /* TDET_OP_CONV: the persistent kernel walks its output tiles from the last to the first.
+                               Results are identical; tdet_plan_create sets it on every second conv of a plan
+                               (TDET_SERPENTINE, default on) so that a launch starts on the rows its producer wrote
+                               last, i.e. the ones still resident in L2.  No reference counterpart (scheduling only). */
   TDET_FLAG_DUAL = 32       /* TDET_OP_CONV, 1x1 / stride 1 / cout % 256 == 0 only: a SECOND input,
                                y = act( ([x | x2'] * wgt^T) * scale + shift ),  x2' = x2 sampled with stride2,
                                i.e. wgt is the K-concatenation [cout][cin + cin2] of two 1x1 weight matrices and both

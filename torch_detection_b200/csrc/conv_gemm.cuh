@@ -155,6 +155,10 @@ struct ConvGemmParams {
   int stride2;
   const TensorMeta* in2_meta;     // nullable
   int epi_fast;                   // 1: compile-time epilogue variants where one matches (TDET_EPI_FAST, default 1)
+  // reverse: the persistent tile loop walks the tiles from the LAST to the first (TDET_FLAG_REVERSE).  Results are
+  // identical; consecutive launches of a plan alternate direction so that a kernel starts on the part of its input
+  // the previous kernel wrote last -- the part that is still in the 126 MB L2 when the tensor is larger than L2.
+  int reverse;
 };
 
 // BRES_KB > 0: the whole weight panel of the CTA's n-tile (up to BRES_KB k-blocks; one n-tile, or a grid that is a
@@ -373,8 +377,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const int tile0 = POOL ? 0 : PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = POOL ? 1 : PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_tiles = POOL ? pool_tiles : (PAIR ? (p.num_m_tiles + 1) >> 1 : p.num_m_tiles) * p.num_n_tiles;
+  const int rev_last = (!POOL && p.reverse) ? num_tiles - 1 : -1;
+  auto phys = [&](int tile) { return rev_last >= 0 ? rev_last - tile : tile; };   // loop index -> tile
   auto m_tile_of = [&](int tile) {
-    const int mt = tile / p.num_n_tiles;
+    const int mt = phys(tile) / p.num_n_tiles;
     return PAIR ? 2 * mt + static_cast<int>(cta_rank) : mt;
   };
   // grouped convs (group width divides 64): output channels [64j, 64j+64) only see input channels of the
@@ -391,7 +397,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     if (BRES_KB > 0 && lane == 0) {
       // (several n-tiles: the host sizes the grid to a multiple of their number, so that every tile of this CTA
       // belongs to n-tile tile0 % num_n_tiles and its weight panel can stay resident)
-      const int n_res = (tile0 % p.num_n_tiles) * BN;
+      const int n_res = (phys(tile0) % p.num_n_tiles) * BN;
       mbar_arrive_expect_tx(bres_bar, static_cast<uint32_t>(p.num_kb_b) * L::kBBytes);
       for (int kb = 0; kb < p.num_kb_b; ++kb)
         tma_load_2d(smem_b + kb * L::kBBytes, &p.tmap_b, bres_bar, kb * kBK, n_res);
@@ -405,7 +411,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int t = m_tile / p.tiles_w;
         const int th = t % p.tiles_h;
         const int img = t / p.tiles_h;
-        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        const int kc_lo = p.grouped ? (phys(tile) % p.num_n_tiles) : 0;
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(aempty_bar(stage), phase ^ 1u);
           if (lane == 0) {
@@ -446,7 +452,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     } else
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_tile = m_tile_of(tile);
-      const int n_tile = tile % p.num_n_tiles;
+      const int n_tile = phys(tile) % p.num_n_tiles;
       const int n0 = n_tile * BN;
       const int m_ld = PAIR ? min(m_tile, p.num_m_tiles - 1) : m_tile;
       // tile origin in the A coordinate space
@@ -576,7 +582,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
-        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        const int kc_lo = p.grouped ? (phys(tile) % p.num_n_tiles) : 0;
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           mbar_wait(afull_bar(as), aphase);
           tc_fence_after();
@@ -692,14 +698,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t rphase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_tile = m_tile_of(tile);
-        const int n_tile = tile % p.num_n_tiles;
+        const int n_tile = phys(tile) % p.num_n_tiles;
         // The ring only looks ~one slab ahead of the epilogue, far less than the HBM latency under load: pull the
         // residual / mask tile of a later tile into L2 now (128 rows x BN columns; 2D operands only)
         if (p.res_prefetch > 0 && !coarse_tma && p.a_mode < A_STEM && lane == 0) {
           const int ptile = tile + p.res_prefetch * tile_step;
           if (ptile < num_tiles) {
             const int pm = PAIR ? min(m_tile_of(ptile), p.num_m_tiles - 1) : m_tile_of(ptile);
-            const int pn = (ptile % p.num_n_tiles) * BN;
+            const int pn = (phys(ptile) % p.num_n_tiles) * BN;
             for (int s = 0; s < kSlabsPerTile; ++s) {
               if (p.has_res) tma_prefetch_l2_2d(&p.tmap_res, pn + s * 64, pm * kBM);
               if (MASKED && p.mask_tma) tma_prefetch_l2_2d(&p.tmap_mask, pn + s * 64, pm * kBM);
@@ -743,8 +749,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int n0 = (tile % p.num_n_tiles) * BN;
-        const int kc_lo = p.grouped ? (tile % p.num_n_tiles) : 0;
+        const int n0 = (phys(tile) % p.num_n_tiles) * BN;
+        const int kc_lo = p.grouped ? (phys(tile) % p.num_n_tiles) : 0;
         for (int kc = kc_lo; kc < kc_lo + kcn; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -948,7 +954,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int acc = kAccBufs == 2 ? (seq & 1) : 0;
       const uint32_t acc_phase = static_cast<uint32_t>(kAccBufs == 2 ? (seq >> 1) : seq) & 1u;
       const int m_tile = m_tile_of(tile);
-      const int n_tile = tile % p.num_n_tiles;
+      const int n_tile = phys(tile) % p.num_n_tiles;
       const int n0 = n_tile * BN;
       if (n_tile != cur_n_tile) {
         named_bar_sync(gbar, kEpiGroupThreads);

@@ -116,7 +116,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH) {
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = blockIdx.x; it < num_tiles; it += gridDim.x) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
         const int tw = tile % p.tiles_w;
         const int t = tile / p.tiles_w;
         const int th = t % p.tiles_h;
@@ -133,7 +134,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
         }
       }
     } else
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < num_tiles; it += gridDim.x) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
       int cw = 0, ch = 0, cn = 0;
       if (p.a_mode == A_IM2COL) {
         const int m0 = tile * kSwapPix;
@@ -171,7 +173,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
     if (PATCH) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = blockIdx.x; it < num_tiles; it += gridDim.x) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -203,7 +206,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
         const uint64_t dwp0 = make_smem_desc_sw128(base + L::kWOffset);
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int it = blockIdx.x; it < num_tiles; it += gridDim.x) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
           mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kSwapPix);
@@ -233,7 +237,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
           if (acc == 0) acc_phase ^= 1u;
         }
       } else
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = blockIdx.x; it < num_tiles; it += gridDim.x) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kSwapPix);
@@ -284,7 +289,8 @@ conv_swap_kernel(const __grid_constant__ ConvGemmParams p) {
     float amax_local = 0.0f;
 
     int seq = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
+    for (int it = blockIdx.x; it < num_tiles; it += gridDim.x, ++seq) {
+  const int tile = p.reverse ? num_tiles - 1 - it : it;  // TDET_FLAG_REVERSE
       const int acc = seq & 1;
       const uint32_t acc_phase = static_cast<uint32_t>(seq >> 1) & 1u;
       const int m0 = tile * kSwapPix + group * 128;  // first pixel of this group's half

@@ -472,6 +472,7 @@ int fill_epilogue(Launch& l) {
   if (!is16(o.y_dtype)) return fail(TDET_ERR_INVALID_ARGUMENT, "y_dtype must be BF16 or F16");
   gp.relu = (o.flags & TDET_FLAG_RELU6) ? 2 : (o.flags & TDET_FLAG_RELU) ? 1 : 0;
   gp.out_scaled = (o.flags & TDET_FLAG_SCALED_OUT) ? 1 : 0;
+  gp.reverse = (o.flags & TDET_FLAG_REVERSE) ? 1 : 0;
   if (gp.relu == 2 && (gp.out_scaled || (o.flags & (TDET_FLAG_POOL | TDET_FLAG_SPLIT))))
     return fail(TDET_ERR_INVALID_ARGUMENT, "TDET_FLAG_RELU6: plain 16-bit outputs only (no SCALED_OUT / POOL / SPLIT)");
   gp.out_fp16 = o.y_dtype == TDET_F16;
@@ -2118,9 +2119,21 @@ int tdet_plan_create(tdet_plan** out, const tdet_op* ops, int n_ops, const void*
   plan->meta_count = meta_arena ? meta_count : 0;
   if (n_ext > 0) plan->ext.assign(ext_ptrs, ext_ptrs + n_ext);
   plan->launches.resize(n_ops);
+  // Serpentine tile order (TDET_SERPENTINE, default 1): consecutive conv launches of a plan walk their tiles in
+  // opposite directions, so a launch starts on the rows the previous launch wrote LAST -- still in L2 when the
+  // tensor exceeds its 126 MB (a same-direction walk evicts exactly the rows it is about to need).  The fused
+  // tails and the stem walk forwards; a conv after one of them walks backwards.  Ops that carry the flag keep it.
+  static const bool serpentine = env_int("TDET_SERPENTINE", 1) != 0;
+  bool prev_reversed = false;
   for (int i = 0; i < n_ops; ++i) {
     Launch& l = plan->launches[i];
     l.op = ops[i];
+    if (serpentine && l.op.kind == TDET_OP_CONV) {
+      if (!prev_reversed) l.op.flags |= TDET_FLAG_REVERSE;
+      prev_reversed = (l.op.flags & TDET_FLAG_REVERSE) != 0;
+    } else if (l.op.kind == TDET_OP_STEM || l.op.kind == TDET_OP_BOTTLENECK_TAIL) {
+      prev_reversed = false;
+    }
     for (int f = 0; f < kExtFields; ++f) {
       const char* fp = static_cast<const char*>(get_field(l.op, f));
       if (!fp) continue;
