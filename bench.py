@@ -338,13 +338,24 @@ def e2e_leg(ctx, step, x_host, x_dev, out_like, steps, copy_levels):
     stage = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    host_out = [torch.empty(out_like[i].shape, dtype=out_like[i].dtype).contiguous(
-        memory_format=torch.channels_last).pin_memory() for i in copy_levels]
+    host_sets = [[torch.empty(out_like[i].shape, dtype=out_like[i].dtype).contiguous(
+        memory_format=torch.channels_last).pin_memory() for i in copy_levels] for _ in range(2 if len(copy_levels) > 1 else 1)]
+    host_out = host_sets[0]
     main_stream = torch.cuda.current_stream(dev)
+    # more than one level back (the PCIe-bound full copy): the D2H runs on a stream of its own from device-side
+    # snapshots of the pyramid (two sets, 0.25 ms of HBM copies per step), so it overlaps the NEXT steps' compute and
+    # H2D instead of serialising with them; the host buffers of a step are complete when its `landed` event fires
+    overlap_d2h = len(copy_levels) > 1
+    d2h_stream = torch.cuda.Stream(device=dev) if overlap_d2h else None
+    snap = [[torch.empty_like(out_like[i]) for i in copy_levels] for _ in range(2)] if overlap_d2h else None
+    snapped = [torch.cuda.Event(), torch.cuda.Event()]
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
 
     def loop(n_steps):
         for b in range(2):
             consumed[b].record(main_stream)
+            if overlap_d2h:
+                landed[b].record(d2h_stream)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[0])
             stage[0].copy_(x_host, non_blocking=True)
@@ -359,8 +370,22 @@ def e2e_leg(ctx, step, x_host, x_dev, out_like, steps, copy_levels):
             main_stream.wait_event(ready[cur])
             o = step(stage[cur])
             consumed[cur].record(main_stream)
-            for h, lvl in zip(host_out, copy_levels):
-                h.copy_(o[lvl], non_blocking=True)
+            if overlap_d2h:
+                main_stream.wait_event(landed[cur])      # snapshot set `cur` has left for the host (step i - 2)
+                for d, lvl in zip(snap[cur], copy_levels):
+                    d.copy_(o[lvl], non_blocking=True)
+                snapped[cur].record(main_stream)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(snapped[cur])
+                    for h, d in zip(host_sets[cur], snap[cur]):
+                        h.copy_(d, non_blocking=True)
+                    landed[cur].record(d2h_stream)
+            else:
+                for h, lvl in zip(host_out, copy_levels):
+                    h.copy_(o[lvl], non_blocking=True)
+        if overlap_d2h:
+            for b in range(2):
+                main_stream.wait_event(landed[b])        # the timed region ends when the last results are on the host
 
     loop(3)
     with quiet_host():
@@ -622,7 +647,7 @@ def main():
     if "full" in legs:
         fv, fh, fd = e2e_leg(ctx, step, x_host, x_dev, outs, max(args.steps // 2, 5), list(range(len(outs))))
         full = {"value": fv, "unit": "img/s", "h2d_bytes_per_step": fh, "d2h_bytes_per_step": fd,
-                "note": "as e2e, but ALL of P2..P6 are copied back to pinned host memory every step (PCIe-bound)"}
+                "note": "as e2e, but ALL of P2..P6 are copied back to pinned host memory every step (PCIe-bound): D2H on its own stream from device-side snapshots, overlapped with the following steps"}
     if "sustained" in legs:
         sustained = sustained_leg(ctx, lambda: step(x_dev), B, 3.0, sampler)
 
