@@ -135,6 +135,52 @@ def test_conv_op(cuda_device, case, epi, dtype):
     assert err <= TOL[dtype], "rel-L2 %.3e" % err
 
 
+REVERSE_CASES = [
+    # name, n, h, w, cin, cout, k, stride, pad -- one per kernel family / loader (see the ids)
+    ("1x1_64_256_res_resident_panel", 3, 100, 84, 64, 256, 1, 1, 0),
+    ("1x1_256_1024_res_multi_n_tile", 2, 50, 84, 256, 1024, 1, 1, 0),
+    ("1x1_1024_256_pair_long_k", 2, 50, 84, 1024, 256, 1, 1, 0),
+    ("3x3_256_512_pair_odd_m_tiles", 1, 25, 42, 256, 512, 3, 1, 1),
+    ("3x3_256_256_patch_pair", 1, 48, 32, 256, 256, 3, 1, 1),
+    ("3x3_64_64_patch", 4, 50, 84, 64, 64, 3, 1, 1),
+    ("3x3_128_128_swapped_patch", 3, 32, 40, 128, 128, 3, 1, 1),
+    ("1x1_512_128_swapped", 2, 37, 53, 512, 128, 1, 1, 0),
+    ("3x3s2_128_128_im2col", 2, 41, 57, 128, 128, 3, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", REVERSE_CASES, ids=[c[0] for c in REVERSE_CASES])
+def test_conv_reverse_tile_order_is_bit_identical(cuda_device, case):
+    """TDET_FLAG_REVERSE (the serpentine schedule tdet_plan_create applies to every second conv of a plan) only changes
+    the ORDER in which the persistent kernel visits its tiles: outputs and the recorded |max| must not change by a bit,
+    for every loader / tile family (more tiles than CTAs would be the full-size case; here ragged and odd counts)."""
+    from torch_detection_b200 import engine
+    name, n, h, w, cin, cout, k, stride, pad = case
+    dev = cuda_device
+    dtype = torch.float16
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    xb = _nhwc(torch.randn(n, cin, h, w, generator=g).to(dev), dtype)
+    wp = engine.pack_conv_weight((torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(dev), dtype)
+    ho, wo = engine.conv_out(h, k, stride, pad, 1), engine.conv_out(w, k, stride, pad, 1)
+    scale = (0.5 + torch.rand(cout, generator=g)).to(dev)
+    shift = (0.3 * torch.randn(cout, generator=g)).to(dev)
+    res = _nhwc(torch.randn(n, cout, ho, wo, generator=g).to(dev), dtype) if "res" in name else None
+    outs = []
+    for reverse in (False, True):
+        y = engine.nhwc_empty(n, ho, wo, cout, dev, dtype)
+        y.fill_(float("nan"))
+        op = engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), k, k, stride, pad, 1, scale=scale, shift=shift,
+                            residual=engine.act_of(res) if res is not None else None, relu=True, reverse=reverse)
+        engine.run_op(op, dev)
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert not torch.isnan(outs[1]).any(), "reverse order left tiles unwritten"
+    assert torch.equal(outs[0], outs[1])
+    ref = F.relu(F.conv2d(xb.float(), wp.permute(0, 3, 1, 2).float(), None, stride, pad) * scale.view(1, -1, 1, 1)
+                 + shift.view(1, -1, 1, 1) + (res.float() if res is not None else 0.0))
+    assert rel_l2(outs[1].float(), ref) <= TOL[dtype]
+
+
 PAIR_CASES = [c for c in CONV_CASES if c[5] % 256 == 0] + [
     ("1x1_1024_256_long_k", 2, 50, 84, 1024, 256, 1, 1, 0, 1),     # 66 m-tiles: the default pair selection
     ("3x3_256_256_odd_tiles", 1, 25, 42, 256, 512, 3, 1, 1, 1),    # 9 m-tiles x 2 n-tiles: padding tile in a pair

@@ -39,6 +39,7 @@ FLAG_POOL = 16
 FLAG_RELU6 = 128
 FLAG_DUAL = 32
 FLAG_SCALED_OUT2 = 64
+FLAG_REVERSE = 256
 
 
 class TdetOp(ctypes.Structure):

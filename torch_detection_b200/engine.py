@@ -346,8 +346,10 @@ def nhwc_empty(n, h, w, c, device, dtype=torch.bfloat16):
 
 def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, residual=None,
             coarse=None, relu=False, consts=None, scaled_out=False, mask=None, coarse_parity=False, groups=1,
-            split=False, dual=None, relu6=False):
+            split=False, dual=None, relu6=False, reverse=False):
     """x, y, residual, coarse, mask: ``Act`` handles; wgt packed [cout][kh][kw][cin] in x's dtype.
+    reverse: the kernel walks its tiles from the last to the first (TDET_FLAG_REVERSE; same results -- plans set it
+    on every second conv by themselves).
     split: split-precision tensors (bf16 hi|lo pairs, 2x the logical channels in memory); Act shapes stay
     logical.
     dual: (x2 Act, stride2) -- second input of a 1x1 conv (TDET_FLAG_DUAL: the projection shortcut of a stage's
@@ -364,7 +366,8 @@ def op_conv(x, wgt, y, kh, kw, stride, pad, dil=1, scale=None, shift=None, resid
     op.kind = _C.OP_CONV
     op.flags = (_C.FLAG_RELU6 if relu6 else (_C.FLAG_RELU if relu else 0)) | \
         (_C.FLAG_SCALED_OUT if scaled_out else 0) | \
-        (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_SPLIT if split else 0)
+        (_C.FLAG_COARSE_PARITY if coarse_parity else 0) | (_C.FLAG_SPLIT if split else 0) | \
+        (_C.FLAG_REVERSE if reverse else 0)
     if mask is not None:
         op.mask = mask.ptr
     op.groups = groups
