@@ -194,7 +194,11 @@ int stem_version() { return env_int("TDET_STEM", 2); }
 constexpr int kDefaultVariantSet = 0;
 constexpr int kDefaultSwapMode = 1;
 constexpr int kDefaultPairMode = 9;  // measured: long-K streamed convs 5-9 %, 256-wide halo-patch 3x3 6 % faster; others lose
-constexpr int kDefaultResVariant = 0;  // residual convs with streamed weights: 0 (256,3,2) 1 (256,2,4,os2) 2 BN=128 3 (256,2,6)
+// residual convs with streamed weights: 0 (256,3,3) 1 (256,2,4,os2) 2 BN=128 3 (256,2,6: two weight stages, six ring slabs)
+// 4 = by K: (256,2,6) for K <= 256 -- two stages cover a four-k-block main loop and the deeper ring hides more of the
+// residual's HBM latency (same-box, in situ: layer2 conv3 128 -> 123.5 us, layer3 conv3 76.8 -> 74.5 us) -- and
+// (256,3,3) beyond (layer4's K = 512 conv3 loses 10 us per launch with two stages)
+constexpr int kDefaultResVariant = 4;
 constexpr int kDefaultRes1Ring = 3;
 
 bool is16(int dt) { return dt == TDET_BF16 || dt == TDET_F16; }
@@ -709,7 +713,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   if (o.cout % 256 == 0 && !grouped && !(resv == 2 && naux >= 1)) {
     l.bn = 256;
     if (naux == 2 || (naux == 1 && (resv == 1))) { l.stages = 2; l.res_slabs = 4; l.oslabs = 2; }
-    else if (naux == 1 && resv == 3) { l.stages = 2; l.res_slabs = 6; l.oslabs = 1; }
+    else if (naux == 1 && (resv == 3 || (resv == 4 && o.kh * o.kw * o.cin <= 256 && !dual))) { l.stages = 2; l.res_slabs = 6; l.oslabs = 1; }
     else if (naux == 1) { l.stages = 3; l.res_slabs = 3; l.oslabs = 1; }
     else if (vs & 2) { l.stages = 3; l.res_slabs = 0; l.oslabs = 2; }
     else { l.stages = 4; l.res_slabs = 0; l.oslabs = 1; }
