@@ -551,13 +551,14 @@ int build_conv_swap(Launch& l, const DeviceInfo& di) {
   gp.a_mode = tiled ? A_TILED : A_IM2COL;
   rc = encode_2d(&gp.tmap_b, o.wgt, o.x_dtype, static_cast<long long>(o.kh) * o.kw * o.cin, o.cout, 128, "weights");
   if (rc) return rc;
-  // 3x3 s1: 8 x 32 spatial tiles with one halo patch per channel chunk, when the tiling wastes <= 30 % of the pixels
-  // (layer2 at 100 x 168: 28 % waste, still 6 % faster than re-reading the pixel tile per tap through im2col)
+  // 3x3 s1: 8 x 32 spatial tiles with one halo patch per channel chunk, when the tiling wastes <= 20 % of the pixels
+  // (layer2 at 100 x 168, 28 % waste: 6 % faster than im2col before the compile-time epilogue variants, 6.5 % SLOWER
+  // since -- 87.5 vs 81.8 us in situ, per-launch sweep of the final build)
   l.patch = false;
   if (o.kh == 3 && o.kw == 3 && o.stride == 1 && o.pad == 1 && o.dil == 1 && env_int("TDET_SWAP_PATCH", 1)) {
     const int tw = (o.wo + kSwapPW - 1) / kSwapPW, th = (o.ho + kSwapPH - 1) / kSwapPH;
     const double px = static_cast<double>(o.n) * tw * th * kSwapPix;
-    if (px <= 0x7FFFFF00LL && px * 100.0 <= static_cast<double>(gp.M) * (100.0 + env_int("TDET_SWAP_PATCH_WASTE", 30))) {
+    if (px <= 0x7FFFFF00LL && px * 100.0 <= static_cast<double>(gp.M) * (100.0 + env_int("TDET_SWAP_PATCH_WASTE", 20))) {
       l.patch = true;
       gp.a_mode = A_PATCH;
       gp.tiles_w = tw;
@@ -845,7 +846,7 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   l.pair = false;
   const int pair_mode = env_int("TDET_PAIR", kDefaultPairMode);
   if (!l.patch && !spatial && l.bn == 256 && l.bres_kb == 0 && !split && naux <= 1 && !l.no_patch &&
-      gp.num_m_tiles >= 2 && ((pair_mode & 2) || ((pair_mode & 1) && naux == 0 && gp.num_kb_b >= 16))) {
+      gp.num_m_tiles >= 2 && ((pair_mode & 2) || ((pair_mode & 1) && naux == 0 && gp.num_kb_b >= 12))) {   // (12: layer3's dual-source conv3, K = 256 + 512: 107 -> 95 us)
     l.pair = true;
     l.oslabs = 1;
     if (naux == 1) { l.stages = 4; l.res_slabs = 3; } else { l.stages = 6; l.res_slabs = 0; }
