@@ -846,7 +846,10 @@ int build_conv(Launch& l, const DeviceInfo& di) {
   l.pair = false;
   const int pair_mode = env_int("TDET_PAIR", kDefaultPairMode);
   if (!l.patch && !spatial && l.bn == 256 && l.bres_kb == 0 && !split && naux <= 1 && !l.no_patch &&
-      gp.num_m_tiles >= 2 && ((pair_mode & 2) || ((pair_mode & 1) && naux == 0 && gp.num_kb_b >= 12))) {   // (12: layer3's dual-source conv3, K = 256 + 512: 107 -> 95 us)
+      gp.num_m_tiles >= 2 && ((pair_mode & 2) || ((pair_mode & 1) && ((naux == 0 && gp.num_kb_b >= 12) || (naux == 1 && gp.num_kb_b >= 16))))) {
+    // (12: layer3's dual-source conv3, K = 256 + 512: 107 -> 95 us.  One ring operand and K >= 1024 -- the masked 3x3
+    // dgrads of layers 3-4 and of the FPN outputs -- gain 2-10 us per launch as pairs, per-launch sweep of the
+    // training step; the forward has no such conv)
     l.pair = true;
     l.oslabs = 1;
     if (naux == 1) { l.stages = 4; l.res_slabs = 3; } else { l.stages = 6; l.res_slabs = 0; }
@@ -867,7 +870,9 @@ int build_conv(Launch& l, const DeviceInfo& di) {
     // (measured per launch, R50 batch 16: resident weights -27 us; the streamed-weight variants LOSE 4-29 us each to
     // the ring stage the extra staging slabs cost -- bit 2 of TDET_EPI4 enables them anyway)
     const int e4 = env_int("TDET_EPI4", 1);
-    if (!spatial && l.bres_kb == 4 && naux == 0 && l.res_slabs == 0 && l.stages == 4) { l.ng4 = true; l.stages = 2; }
+    // (resident panel: up to two k-blocks per tile only -- with four, the 1x1 dgrad of the FPN's P2 lateral, two A
+    // stages starve the MMA: 128 us against 91 us with two epilogue groups and four stages)
+    if (!spatial && l.bres_kb == 4 && naux == 0 && l.res_slabs == 0 && l.stages == 4 && (gp.num_kb_b <= 2 || (e4 & 4))) { l.ng4 = true; l.stages = 2; }
     else if (!(e4 & 2)) {}
     else if (spatial && l.bres_kb == 0 && l.res_slabs == 2) { l.ng4 = true; l.stages = 2; }
     else if (!spatial && l.bres_kb == 0 && naux == 1 && l.res_slabs == 3) { l.ng4 = true; l.stages = 2; }
