@@ -35,6 +35,10 @@
 // Warp roles (20 warps): warp 0 lane 0 patches, lane 1 the W ring; warp 1 MMA issuer (leader only); warp 2 residual producer (into
 // the output slabs; the residual two passes ahead is prefetched into L2); warp 3 store issuer; warps 4-19 epilogue in
 // four groups: E1 (D1 -> z2, 32 columns per group), E2 (32 columns of D2 + residual -> half an output slab, in place).
+// Status (round 2, final build): correct and bit-identical, but 265 us per block in situ against 88 + 127 us for the
+// unfused pair, so the plan compiler leaves it off (TDET_FUSE_TAIL2=1 enables).  TDET_T2_DBG and a seven-slot ring
+// variant showed that neither the weight ring nor the G1 MMAs bound it: each epilogue warp runs five serial 32-column
+// conversion steps per tile (E2 x 4 + E1) of 2 400 - 4 000 cycles each.
 // Numerics are those of the unfused launches (fp32 accumulation, k-blocks in chunk-major / tap-minor order like the
 // halo-patch conv kernels, fp32 scale/shift/residual/ReLU, one rounding per stored tensor); exponents as in
 // bottleneck_fused.cuh.
