@@ -148,6 +148,24 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_C.TdetOp) == 384  # static_assert(sizeof(tdet_op) == 384) in tdet_api.cu
 
 
+def test_binding_constants_match_the_header():
+    """Every TDET_OP_* / TDET_FLAG_* / dtype / status value the ctypes binding hard-codes equals the header's enum (a
+    drifted constant would silently launch a different op)."""
+    header = open(os.path.join(ROOT, "include", "tdet_b200.h")).read()
+    enums = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(TDET_[A-Z0-9_]+)\s*=\s*(-?\d+)", header)}
+    for prefix, strip in (("TDET_OP_", "OP_"), ("TDET_FLAG_", "FLAG_"), ("TDET_ERR_", "ERR_")):
+        names = [n for n in enums if n.startswith(prefix)]
+        assert names, prefix
+        for n in names:
+            py = strip + n[len(prefix):]
+            assert hasattr(_C, py), "%s has no binding constant %s" % (n, py)
+            assert getattr(_C, py) == enums[n], (n, enums[n], getattr(_C, py))
+    for n, py in (("TDET_BF16", "BF16"), ("TDET_F32", "F32"), ("TDET_F16", "F16"), ("TDET_U8", "U8")):
+        assert getattr(_C, py) == enums[n]
+    flags = [v for n, v in enums.items() if n.startswith("TDET_FLAG_")]
+    assert len(set(flags)) == len(flags) and all(v & (v - 1) == 0 for v in flags), "flags must be distinct bits"
+
+
 def test_no_gpu_calls_fail_cleanly_without_device():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
