@@ -622,3 +622,51 @@ def test_groupnorm_basic_block_and_retinanet_neck(cuda_device):
     _check_levels(feats, want_f, ["C2", "C3", "C4", "C5"])
     e = _check_levels(outs, want_p, ["P3", "P4", "P5", "P6", "P7"])
     print("groupnorm r18 + extra convs", e)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [
+    dict(k=1, stride=1, pad=0, bias=True, norm=False, act=None),       # an FPN lateral
+    dict(k=3, stride=1, pad=1, bias=True, norm=False, act=None),       # an FPN output conv
+    dict(k=3, stride=2, pad=1, bias=False, norm=True, act="relu"),     # conv + BN + ReLU (layers.py type 3)
+    dict(k=3, stride=1, pad=1, bias=True, norm=True, act="relu6"),     # norm and bias together (warned, as the reference)
+], ids=["1x1_bias", "3x3_bias", "3x3s2_bn_relu", "3x3_bias_bn_relu6"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_conv_module_stand_alone_call(cuda_device, cfg, dtype):
+    """ConvModule.forward outside a neck (layers.py:121-135): one launch with bias / eval BatchNorm / activation in the
+    epilogue, against the same module evaluated by PyTorch in fp32 on the bf16-rounded input and weights."""
+    import warnings
+    from torch_detection_b200.models.utils.layers import ConvModule
+    dev = cuda_device
+    torch.manual_seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = ConvModule(128, 256, cfg["k"], stride=cfg["stride"], padding=cfg["pad"], bias=cfg["bias"],
+                       normalize=dict(type="BN") if cfg["norm"] else None, activation=cfg["act"])
+    if cfg["norm"]:
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            m.norm.weight.copy_(0.5 + torch.rand(256, generator=g))
+            m.norm.bias.copy_(0.2 * torch.randn(256, generator=g))
+            m.norm.running_mean.copy_(0.3 * torch.randn(256, generator=g))
+            m.norm.running_var.copy_(0.5 + torch.rand(256, generator=g))
+    m = m.to(dev).eval()
+    x = torch.randn(2, 128, 37, 45, generator=torch.Generator().manual_seed(5)).to(dev).to(dtype)
+    with torch.no_grad():
+        y = m(x)
+        xr = x.to(torch.bfloat16).float()
+        ref = torch.nn.functional.conv2d(xr, m.conv.weight.to(torch.bfloat16).float(), m.conv.bias, cfg["stride"],
+                                         cfg["pad"])
+        if cfg["norm"]:
+            ref = m.norm(ref)
+        if cfg["act"] == "relu":
+            ref = torch.relu(ref)
+        elif cfg["act"] == "relu6":
+            ref = torch.clamp(ref, 0.0, 6.0)
+    assert y.dtype == dtype and tuple(y.shape) == tuple(ref.shape)
+    err = orc.rel_l2(y.float(), ref)
+    assert err <= 5e-3, err
+    # what stays refused says so: training, batch-statistics BatchNorm
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x)

@@ -50,7 +50,8 @@ class ConvModule(nn.Module):
     """conv (+bias) (+BatchNorm) (+ReLU) parameter container used by the necks (layers.py:57-135).  The
     owning neck's plan executes it: an eval-mode BatchNorm (``normalize`` not None, ``use_gn=False``) is
     folded into the conv's fp32 epilogue, a GroupNorm (``use_gn=True``) runs as statistics + apply kernels after
-    the raw conv; ``activate_last=False`` is refused (no neck of the reference uses it)."""
+    the raw conv; ``activate_last=False`` is refused (no neck of the reference uses it).  ``forward`` is a stand-alone
+    inference call (one launch) for code that uses the class outside a neck."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1,
                  groups=1, bias=True, normalize=None, use_gn=False, activation=None,
@@ -77,5 +78,43 @@ class ConvModule(nn.Module):
             self.activate = nn.ReLU6(inplace=True) if activation == "relu6" else nn.ReLU(inplace=True)
 
     def forward(self, x):
-        raise NotImplementedError(
-            "ConvModule is a parameter container here; the owning FPN executes it through the plan")
+        """Stand-alone call, as heads built on the reference use it (layers.py:121-135); the necks do NOT come through
+        here, they execute their ConvModules inside their own plans.  Inference only: ONE launch of the implicit-GEMM
+        kernel with the bias / eval-mode BatchNorm and ReLU / ReLU6 in its epilogue, bf16 NHWC arithmetic, operands
+        re-packed on every call (nothing is cached on this convenience path).  NCHW in, NCHW (channels_last memory) out,
+        bf16 for a bf16 input and fp32 for an fp32 one."""
+        import torch
+        from ... import engine
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and
+                                                          any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError("stand-alone ConvModule training is not on the B200 path: the necks train "
+                                      "through their plans; call it under torch.no_grad() / in eval mode")
+        if self.with_norm and not isinstance(self.norm, nn.BatchNorm2d):
+            raise NotImplementedError("stand-alone ConvModule with GroupNorm: use it through FPN / PAFPN (use_gn=True)")
+        if self.with_norm and self.norm.training:
+            raise NotImplementedError("batch-statistics BatchNorm is not on the B200 path (call .eval())")
+        engine.require_cuda(x, "ConvModule input")
+        conv = self.conv
+        if conv.groups != 1 or conv.kernel_size[0] != conv.kernel_size[1] or conv.stride[0] != conv.stride[1] or \
+                conv.padding[0] != conv.padding[1] or conv.dilation[0] != conv.dilation[1]:
+            raise NotImplementedError("stand-alone ConvModule: dense convs with square geometry only")
+        if x.dtype not in (torch.bfloat16, torch.float32):
+            raise NotImplementedError("ConvModule input dtype %s (supported: float32, bfloat16)" % x.dtype)
+        xb = x if (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)) else \
+            x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wp = engine.pack_conv_weight(conv.weight, torch.bfloat16)
+        scale = shift = None
+        if self.with_norm:
+            scale, shift = engine.fold_bn(self.norm)
+            if conv.bias is not None:
+                shift = shift + conv.bias.detach().float() * scale   # BN(conv + b) = scale * conv + (shift + scale * b)
+        elif conv.bias is not None:
+            shift = conv.bias.detach().float().contiguous()
+        k, st, pd, dl = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+        n, _, h, w = xb.shape
+        y = engine.nhwc_empty(n, engine.conv_out(h, k, st, pd, dl), engine.conv_out(w, k, st, pd, dl),
+                              conv.out_channels, x.device)
+        op = engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), k, k, st, pd, dl, scale=scale, shift=shift,
+                            relu=self.activation == "relu", relu6=self.activation == "relu6")
+        engine.run_op(op, x.device)
+        return y.float() if x.dtype == torch.float32 else y
