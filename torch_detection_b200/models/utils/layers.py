@@ -89,9 +89,8 @@ class ConvModule(nn.Module):
                                                           any(p.requires_grad for p in self.parameters()))):
             raise NotImplementedError("stand-alone ConvModule training is not on the B200 path: the necks train "
                                       "through their plans; call it under torch.no_grad() / in eval mode")
-        if self.with_norm and not isinstance(self.norm, nn.BatchNorm2d):
-            raise NotImplementedError("stand-alone ConvModule with GroupNorm: use it through FPN / PAFPN (use_gn=True)")
-        if self.with_norm and self.norm.training:
+        gn = self.with_norm and isinstance(self.norm, nn.GroupNorm)
+        if self.with_norm and not gn and self.norm.training:
             raise NotImplementedError("batch-statistics BatchNorm is not on the B200 path (call .eval())")
         engine.require_cuda(x, "ConvModule input")
         conv = self.conv
@@ -103,6 +102,30 @@ class ConvModule(nn.Module):
         xb = x if (x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)) else \
             x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         wp = engine.pack_conv_weight(conv.weight, torch.bfloat16)
+        k, st, pd, dl = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+        n, _, h, w = xb.shape
+        oh, ow, co = engine.conv_out(h, k, st, pd, dl), engine.conv_out(w, k, st, pd, dl), conv.out_channels
+        if gn:
+            # GroupNorm's statistics span the whole conv output: raw conv (fp16 significands with a device-chosen
+            # exponent) -> statistics -> normalise + affine + activation, as the necks' GroupNorm plans do (fpn.py)
+            dev = x.device
+            meta = engine.MetaArena(3, dev)
+            src = engine.Act(xb, (n, h, w, xb.shape[1]), torch.bfloat16, meta.new())
+            engine.run_op(engine.op_amax(engine.Act(xb, src.shape, torch.bfloat16), src.meta), dev)
+            bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+            raw = engine.Act(torch.empty(n * oh * ow * co, dtype=torch.bfloat16, device=dev), (n, oh, ow, co),
+                             torch.float16, meta.new())
+            engine.run_op(engine.op_conv(src, wp, raw, k, k, st, pd, dl, shift=bias,
+                                         consts=engine.bound_consts(wp, None, bias), scaled_out=True), dev)
+            groups = self.norm.num_groups
+            stats = torch.empty(engine.gn_stats_numel(n, groups), dtype=torch.float32, device=dev)
+            y = engine.nhwc_empty(n, oh, ow, co, dev)
+            engine.run_op(engine.op_gn_stats(raw, stats, groups), dev)
+            engine.run_op(engine.op_gn_apply(raw, stats, groups, self.norm.weight.detach().float().contiguous(),
+                                             self.norm.bias.detach().float().contiguous(), self.norm.eps,
+                                             engine.Act(y, (n, oh, ow, co), torch.bfloat16, meta.new()),
+                                             relu=self.activation == "relu", relu6=self.activation == "relu6"), dev)
+            return y.float() if x.dtype == torch.float32 else y
         scale = shift = None
         if self.with_norm:
             scale, shift = engine.fold_bn(self.norm)
@@ -110,10 +133,7 @@ class ConvModule(nn.Module):
                 shift = shift + conv.bias.detach().float() * scale   # BN(conv + b) = scale * conv + (shift + scale * b)
         elif conv.bias is not None:
             shift = conv.bias.detach().float().contiguous()
-        k, st, pd, dl = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
-        n, _, h, w = xb.shape
-        y = engine.nhwc_empty(n, engine.conv_out(h, k, st, pd, dl), engine.conv_out(w, k, st, pd, dl),
-                              conv.out_channels, x.device)
+        y = engine.nhwc_empty(n, oh, ow, co, x.device)
         op = engine.op_conv(engine.act_of(xb), wp, engine.act_of(y), k, k, st, pd, dl, scale=scale, shift=shift,
                             relu=self.activation == "relu", relu6=self.activation == "relu6")
         engine.run_op(op, x.device)
